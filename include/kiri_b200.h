@@ -1,0 +1,225 @@
+/* kiri_b200.h — C ABI of libkiri_b200.so: B200 (sm_100a) kernels for kiri-ocr's batched
+ * text-line recognition path.
+ *
+ * The reference (mrrtmob/kiri-ocr, pure Python/PyTorch) has no FFI of its own; every entry
+ * point below replaces a *call site* of the reference's hot path and cites it.  A Python
+ * binding (ctypes) is what the reference-side maintainer adds — see INTEGRATION.md.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller unless the name ends in _host;
+ *  - every function is asynchronous on `stream`, allocates no device memory, returns 0 on
+ *    success and a negative code on failure (kiri_last_error() gives the thread-local text);
+ *  - bf16 tensors are passed as void*; "NHWC" activations are [lines, rows, cols, channels];
+ *  - handles are not thread-safe; use one per (device, stream).
+ *  - buffers read with 32-bit loads (kiri_preprocess_pack `src`) need 4 readable bytes of
+ *    slack after their last byte.
+ */
+#ifndef KIRI_B200_H_
+#define KIRI_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#define KIRI_DTYPE_F32 0
+#define KIRI_DTYPE_BF16 1
+#define KIRI_MAX_LAYERS 8
+
+/* epilogues of kiri_gemm_bf16 / kiri_conv3x3_bf16 */
+#define KIRI_EPI_BIAS_BF16 0      /* out_bf16 = acc + bias                      */
+#define KIRI_EPI_BIAS_SILU_BF16 1 /* out_bf16 = silu(acc + bias)                */
+#define KIRI_EPI_BIAS_GELU_BF16 2 /* out_bf16 = gelu_erf(acc + bias)            */
+#define KIRI_EPI_BIAS_RESID_F32 3 /* out_f32  = resid + acc + bias              */
+#define KIRI_EPI_BIAS_F32 4       /* out_f32  = acc + bias                      */
+#define KIRI_EPI_BIAS_RESID_LN 5  /* out_f32 = resid + acc + bias; out2_bf16 = LayerNorm(out_f32) (N = 256) */
+
+const char* kiri_last_error(void);
+int kiri_version(void);
+/* 1 when the current device is compute capability 10.x (the kernels are sm_100a-only). */
+int kiri_device_ok(void);
+
+/* ---------------------------------------------------------------- K1: preprocessing
+ * Replaces OCR._preprocess_region (kiri_ocr/core.py:489-528) + ResizeKeepRatioPadNoCrop /
+ * preprocess_pil (kiri_ocr/model.py:316-339), i.e. numpy slicing + Pillow BILINEAR + pad,
+ * done per line on the CPU by the reference.  Bit-exact with Pillow's fixed-point resample. */
+typedef struct {
+  int64_t src_offset; /* byte offset of the crop's top-left pixel inside `src`            */
+  int32_t pitch;      /* bytes between source rows                                         */
+  int32_t w, h;       /* crop size after the reference's clamp-pad (core.py:510-515)       */
+  int32_t nw;         /* max(1, round(w * img_h / h)) — Python round (model.py:321-322)    */
+  int32_t out_index;  /* line slot in the output batch                                     */
+  int32_t strip_w;    /* output columns resampled per pass (fits the shared-memory budget) */
+} KiriCropDesc;
+
+/* shared memory needed by one crop for a given strip width (host helper, no GPU call) */
+int kiri_preprocess_smem_bytes(int w, int h, int nw, int img_h, int Wb, int strip_w);
+
+/* planes_u8: [n_slots, img_h, Wb] uint8; norm_bf16 (nullable): same shape, (v/255-0.5)/0.5 */
+int kiri_preprocess_pack(const uint8_t* src, const KiriCropDesc* descs, int n_crops, int img_h, int Wb,
+                         int smem_bytes, uint8_t* planes_u8, void* norm_bf16, cudaStream_t stream);
+
+/* ---------------------------------------------------------------- K2: stem layer 1
+ * Replaces ConvStem.net[0:3] (kiri_ocr/model.py:215-217).  w_host[48*9], b_host[48]: BN-folded
+ * fp32 weights in HOST memory (they travel as kernel parameters).  out: NHWC bf16, 64 channels
+ * (48 + 16 zero).  W must be a multiple of 128. */
+int kiri_conv1(const uint8_t* planes_u8, const float* w_host, const float* b_host, int n_lines, int H,
+               int W, void* out_bf16_nhwc64, cudaStream_t stream);
+
+/* ---------------------------------------------------------------- K3-K5, K8, K9, K11: tcgen05 GEMMs
+ * 3x3 conv as implicit GEMM (replaces ConvStem.net[3:12], kiri_ocr/model.py:218-226): input NHWC
+ * bf16 [n, IH, IW, Cin] (Cin % 32 == 0), weights bf16 [N, 9*Cin] ordered (ky, kx, cin), pad 1,
+ * stride (sh, sw); output NHWC bf16 [n, OH, OW, N] = silu(conv + bias). */
+int kiri_conv3x3_bf16(const void* in_nhwc, const void* w, const float* bias, int n, int IH, int IW,
+                      int Cin, int N, int sh, int sw, void* out_nhwc, cudaStream_t stream);
+/* out[M, N] = epilogue(a[M, K] @ w[N, K]^T + bias) — replaces the nn.Linear call sites of the
+ * encoder / CTC head / decoder (kiri_ocr/model.py:246-297).  K % 64 == 0.  `resid` (fp32 [M, N])
+ * may alias `out`.  For KIRI_EPI_BIAS_RESID_LN: N == 256, out2 = bf16 [M, 256]. */
+int kiri_gemm_bf16(const void* a, const void* w, const float* bias, int M, int N, int K, int epi,
+                   void* out, const float* resid, const float* ln_g, const float* ln_b, void* out2,
+                   cudaStream_t stream);
+/* plain CUDA-core reference GEMM (fp32 accumulate) used by the tests to cross-check the
+ * tensor-core kernel on the device: out_f32[M,N] = a[M,K] @ w[N,K]^T. */
+int kiri_gemm_ref(const void* a, const void* w, int M, int N, int K, float* out_f32, cudaStream_t stream);
+
+/* ---------------------------------------------------------------- K6/K7 + LayerNorms
+ * mean over RH stem rows + positional table + LayerNorm (+ optional second LayerNorm):
+ * replaces PosEnc2D / adaptive_avg_pool2d / permute / enc_ln_in (kiri_ocr/model.py:194-208, 302-304). */
+int kiri_pool_pos_ln(const void* act_bf16, const float* pos_table, int n_lines, int RH, int T, int D,
+                     const float* g0, const float* b0, const float* g1, const float* b1, float* x_f32,
+                     void* a_bf16, cudaStream_t stream);
+/* y = LN0(x) -> y_f32 / y_bf16 (nullable); z_bf16 = LN1(y) (nullable).  D must be 256. */
+int kiri_layernorm(const float* x, int n_tok, int D, const float* g0, const float* b0, float* y_f32,
+                   void* y_bf16, const float* g1, const float* b1, void* z_bf16, cudaStream_t stream);
+
+/* ---------------------------------------------------------------- K8: encoder self-attention
+ * Replaces the SDPA inside nn.TransformerEncoderLayer (kiri_ocr/model.py:246-261).
+ * qkv: bf16 [n_lines*T, 3*D] rows = [Q | K | V]; out: bf16 [n_lines*T, D]; head_dim 32;
+ * T in {32,64,96,128,160}; kv_len (nullable): per-line number of valid keys. */
+int kiri_encoder_attention(const void* qkv_bf16, void* out_bf16, int n_lines, int T, int heads, int D,
+                           const int* kv_len, cudaStream_t stream);
+
+/* ---------------------------------------------------------------- K10: fused CTC greedy
+ * Replaces compute_ctc_confidence + the id-level part of CharTokenizer.decode_ctc
+ * (kiri_ocr/model.py:343-373, 109-119).  logits: [n_lines, T, ld] (first C columns valid).
+ * ids: [n_lines, T] collapsed ids (repeats removed, ids >= 2), n_ids[n_lines] = their count
+ * (= the reference's length estimate), conf[n_lines] = mean over frames of the max soft-max
+ * probability.  frame_ids / frame_prob ([n_lines, T], nullable) serve the streaming API. */
+int kiri_ctc_greedy(const void* logits, int logits_dtype, int n_lines, int T, int C, int ld, int* ids,
+                    int* n_ids, float* conf, int* frame_ids, float* frame_prob, cudaStream_t stream);
+
+/* ---------------------------------------------------------------- model-level handle
+ * Packed weights (produced once per checkpoint by kiri_ocr_b200/weights.py): BN folded into the conv
+ * weights, Linear weights [out, in] in bf16, biases / LayerNorm affines in fp32. */
+typedef struct {
+  int32_t img_h;        /* 48 */
+  int32_t enc_dim;      /* 256 */
+  int32_t enc_layers, enc_heads, enc_ff;
+  int32_t dec_dim, dec_layers, dec_heads, dec_ff;
+  int32_t ctc_classes;  /* V + 2 */
+  int32_t dec_vocab;    /* V + 3 */
+  int32_t max_pos;      /* rows of dec_pe */
+  int32_t max_t;        /* rows of pos_table (IMG_W / 4) */
+  int32_t has_dec_pos;  /* 0 for old checkpoints without dec_pos_enc.pe (core.py:255-263) */
+} KiriDims;
+
+typedef struct {
+  const void* wqkv; const float* bqkv;   /* [3D, D], [3D] */
+  const void* wo;   const float* bo;     /* [D, D],  [D]  */
+  const void* w1;   const float* b1;     /* [FF, D], [FF] */
+  const void* w2;   const float* b2;     /* [D, FF], [D]  */
+  const float* ln1_g; const float* ln1_b;
+  const float* ln2_g; const float* ln2_b;
+} KiriEncLayerWeights;
+
+typedef struct {
+  const void* wqkv; const float* bqkv;   /* self-attention in_proj */
+  const void* wo;   const float* bo;
+  const void* wcq;  const float* bcq;    /* cross-attention query rows of multihead_attn.in_proj */
+  const void* wco;  const float* bco;
+  const void* w1;   const float* b1;
+  const void* w2;   const float* b2;
+  const float* ln1_g; const float* ln1_b;
+  const float* ln2_g; const float* ln2_b;
+  const float* ln3_g; const float* ln3_b;
+} KiriDecLayerWeights;
+
+typedef struct {
+  const float* conv1_w_host; const float* conv1_b_host;   /* HOST: [48*9], [48] */
+  const void* conv2_w; const float* conv2_b;               /* [96, 9*64]  */
+  const void* conv3_w; const float* conv3_b;               /* [160, 9*96] */
+  const void* conv4_w; const float* conv4_b;               /* [256, 9*160]*/
+  const float* pos_table;                                   /* [max_t, 256] */
+  const float* enc_ln_in_g; const float* enc_ln_in_b;
+  KiriEncLayerWeights enc[KIRI_MAX_LAYERS];
+  const float* enc_ln_g; const float* enc_ln_b;
+  const float* ctc_ln_g; const float* ctc_ln_b;
+  const void* ctc_w; const float* ctc_b;                   /* [Cp, 256], [Cp]: Cp = roundup(C, 16), zero padded */
+  /* decoder */
+  const void* crosskv_w; const float* crosskv_b;           /* [dec_layers*2*D, 256]: (W_k;W_v)_l @ W_memproj */
+  const float* dec_emb;                                     /* fp32 [Vd, D] */
+  const float* dec_pe;                                      /* fp32 [max_pos, D] */
+  KiriDecLayerWeights dec[KIRI_MAX_LAYERS];
+  const float* dec_ln_g; const float* dec_ln_b;
+  const void* heads_w; const float* heads_b;               /* [2*Vp, D], [2*Vp]: dec_head rows then lm_head rows, Vp = roundup(Vd, 16) */
+} KiriWeights;
+
+typedef struct KiriHandle KiriHandle;
+int kiri_create(const KiriDims* dims, const KiriWeights* weights, KiriHandle** out);
+void kiri_destroy(KiriHandle* h);
+
+/* scratch bytes kiri_encode needs for a batch of B lines of width Wb, processing the stem in
+ * sub-batches of `stem_chunk` lines (so its activations stay L2-resident; 0 = whole batch). */
+size_t kiri_encode_workspace_bytes(const KiriHandle* h, int B, int Wb, int stem_chunk);
+
+/* Stem + encoder + CTC head for B preprocessed planes ([B, img_h, Wb] uint8): replaces
+ * KiriOCR.encode + ctc_head (kiri_ocr/model.py:299-307, 264-268) as called from
+ * OCR.recognize_region (kiri_ocr/core.py:546-552).
+ *   mem_f32   (nullable) fp32 [B*T, D]   encoder output ("mem")
+ *   mem_bf16  (nullable) bf16 [B*T, D]   same, for kiri_dec_prepare
+ *   logits    (nullable) fp32 [B*T, Cp]  CTC logits, Cp = roundup(C, 16); columns >= C are zero
+ *   tok_f32   (nullable) fp32 [B*T, D]   encoder input tokens after enc_ln_in (stage parity)
+ *   kv_len    (nullable) int  [B]        valid frames per line (masked bucketed mode) */
+int kiri_encode(KiriHandle* h, const uint8_t* planes_u8, int B, int Wb, int stem_chunk, void* workspace,
+                size_t workspace_bytes, float* mem_f32, void* mem_bf16, float* logits, float* tok_f32,
+                const int* kv_len, cudaStream_t stream);
+
+/* ---------------------------------------------------------------- greedy attention decoder
+ * Replaces beam_decode_one_batched at BEAM=1 (kiri_ocr/model.py:390-600 via core.py:560-568)
+ * and the token rule of greedy_decode_streaming (model.py:779-946), batched over lines with
+ * a per-layer self-attention KV cache and cross K/V computed once per batch. */
+typedef struct {
+  float lm_alpha;              /* LM_FUSION_ALPHA if fusion is on, else 0 */
+  float eos_bias, eos_boost;   /* EOS_LOGP_BIAS / EOS_LOGP_BOOST */
+  int32_t eos_bias_until_len;  /* EOS_BIAS_UNTIL_LEN */
+  float rep_last, rep_bigram, rep_trigram, unk_penalty;
+  int32_t unk_id;              /* decoder id of <unk> */
+  double len_ratio;            /* DEC_MAX_LEN_RATIO */
+  int32_t len_pad;             /* DEC_MAX_LEN_PAD */
+  double mem_ratio;            /* MEM_MAX_LEN_RATIO */
+  int32_t max_dec_len;         /* MAX_DEC_LEN */
+  int32_t select_raw;          /* 0: arg-max of fused+penalised log-prob (model.py:537);
+                                  1: arg-max of raw dec_head soft-max (streaming, model.py:915-917) */
+} KiriDecodeParams;
+
+size_t kiri_decode_workspace_bytes(const KiriHandle* h, int B, int T, int Lmax);
+/* mem_bf16 [B*T, D]; len_est [B] (from kiri_ctc_greedy n_ids).  Outputs: ids [B, Lmax] chosen
+ * tokens (EOS included when emitted), n_out [B], sum_logp [B] (sum of chosen penalised log-probs),
+ * step_logp / step_prob [B, Lmax] (nullable).  Runs until every line has emitted EOS or reached
+ * its own max_steps; `max_steps_cap` (<= Lmax) bounds the loop.  The call synchronises the
+ * stream every `poll_every` steps to read the alive counter. */
+int kiri_decode_greedy(KiriHandle* h, const void* mem_bf16, const int* len_est, int B, int T, int Lmax,
+                       const KiriDecodeParams* p, void* workspace, size_t workspace_bytes, int* ids,
+                       int* n_out, float* sum_logp, float* step_logp, float* step_prob,
+                       const int* forced_ids, int* steps_run_host, int poll_every, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KIRI_B200_H_ */

@@ -1,0 +1,231 @@
+// C ABI glue: error text, kernel-level GEMM/conv entry points, the model handle and the
+// stem + encoder + CTC-head pipeline (kiri_encode).  See include/kiri_b200.h.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+#include "gemm_tc.cuh"
+#include "kiri_b200.h"
+
+namespace kiri {
+
+static thread_local char g_err[1024] = "";
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// CUDA-core cross-check GEMM: one thread per output element, fp32 accumulate.
+__global__ void gemm_ref_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ w,
+                                int M, int N, int K, float* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (n >= N || m >= M) return;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k)
+    acc = fmaf(__bfloat162float(a[(size_t)m * K + k]), __bfloat162float(w[(size_t)n * K + k]), acc);
+  out[(size_t)m * N + n] = acc;
+}
+
+}  // namespace kiri
+
+using namespace kiri;
+
+extern "C" const char* kiri_last_error(void) { return g_err; }
+extern "C" int kiri_version(void) { return 100; }
+extern "C" int kiri_device_ok(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10;
+}
+
+extern "C" int kiri_gemm_ref(const void* a, const void* w, int M, int N, int K, float* out_f32,
+                             cudaStream_t stream) {
+  KIRI_REQUIRE(a && w && out_f32, "kiri_gemm_ref: null pointer");
+  if (M == 0 || N == 0) return 0;
+  dim3 grid((N + 127) / 128, M);
+  gemm_ref_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(a),
+                                            reinterpret_cast<const __nv_bfloat16*>(w), M, N, K, out_f32);
+  KIRI_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int gemm_call(const void* a, const void* w, const float* bias, int M, int N, int K, int epi, void* out,
+                     const float* resid, const float* ln_g, const float* ln_b, void* out2,
+                     cudaStream_t stream) {
+  if (M == 0) return 0;
+  GemmLaunch L;
+  memset(&L, 0, sizeof(L));
+  L.a = a; L.w = w;
+  L.NB = 1; L.IH = 1; L.IW = M; L.Cin = K;
+  L.OH = 1; L.OW = M;
+  L.sw = 1; L.sh = 1; L.pad = 0; L.kw = 1; L.kh = 1;
+  L.N = N; L.epi = epi;
+  L.e.out = out; L.e.bias = bias; L.e.resid = resid; L.e.ldc = N; L.e.n_valid = N;
+  L.e.ln_g = ln_g; L.e.ln_b = ln_b; L.e.out2 = out2;
+  return launch_gemm_tc(L, stream);
+}
+
+extern "C" int kiri_gemm_bf16(const void* a, const void* w, const float* bias, int M, int N, int K, int epi,
+                              void* out, const float* resid, const float* ln_g, const float* ln_b,
+                              void* out2, cudaStream_t stream) {
+  KIRI_REQUIRE(a && w && bias && out, "kiri_gemm_bf16: null pointer");
+  KIRI_REQUIRE(epi >= 0 && epi <= 5, "kiri_gemm_bf16: unknown epilogue %d", epi);
+  KIRI_REQUIRE((epi != KIRI_EPI_BIAS_RESID_F32 && epi != KIRI_EPI_BIAS_RESID_LN) || resid,
+               "kiri_gemm_bf16: residual epilogue without resid");
+  return gemm_call(a, w, bias, M, N, K, epi, out, resid, ln_g, ln_b, out2, stream);
+}
+
+static int conv_call(const void* in, const void* w, const float* bias, int n, int IH, int IW, int Cin, int N,
+                     int sh, int sw, void* out, cudaStream_t stream) {
+  if (n == 0) return 0;
+  GemmLaunch L;
+  memset(&L, 0, sizeof(L));
+  L.a = in; L.w = w;
+  L.NB = n; L.IH = IH; L.IW = IW; L.Cin = Cin;
+  L.OH = (IH + 2 - 3) / sh + 1; L.OW = (IW + 2 - 3) / sw + 1;
+  L.sw = sw; L.sh = sh; L.pad = 1; L.kw = 3; L.kh = 3;
+  L.N = N; L.epi = EPI_BIAS_SILU_BF16;
+  L.e.out = out; L.e.bias = bias; L.e.resid = nullptr; L.e.ldc = N; L.e.n_valid = N;
+  return launch_gemm_tc(L, stream);
+}
+
+extern "C" int kiri_conv3x3_bf16(const void* in_nhwc, const void* w, const float* bias, int n, int IH, int IW,
+                                 int Cin, int N, int sh, int sw, void* out_nhwc, cudaStream_t stream) {
+  KIRI_REQUIRE(in_nhwc && w && bias && out_nhwc, "kiri_conv3x3_bf16: null pointer");
+  return conv_call(in_nhwc, w, bias, n, IH, IW, Cin, N, sh, sw, out_nhwc, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// model handle
+// ------------------------------------------------------------------------------------------------
+struct KiriHandle {
+  KiriDims d;
+  KiriWeights w;
+  float conv1_w[48 * 9];
+  float conv1_b[48];
+};
+
+extern "C" int kiri_create(const KiriDims* dims, const KiriWeights* weights, KiriHandle** out) {
+  KIRI_REQUIRE(dims && weights && out, "kiri_create: null pointer");
+  KIRI_REQUIRE(kiri_device_ok(), "kiri_create: the current CUDA device is not compute capability 10.x (B200)");
+  KIRI_REQUIRE(dims->enc_dim == 256 && dims->dec_dim == 256, "kiri_create: kernels are built for ENC_DIM = DEC_DIM = 256");
+  KIRI_REQUIRE(dims->enc_heads * 32 == dims->enc_dim && dims->dec_heads * 32 == dims->dec_dim,
+               "kiri_create: head_dim must be 32");
+  KIRI_REQUIRE(dims->enc_layers <= KIRI_MAX_LAYERS && dims->dec_layers <= KIRI_MAX_LAYERS, "kiri_create: too many layers");
+  KIRI_REQUIRE(dims->enc_ff % 64 == 0 && dims->dec_ff % 64 == 0, "kiri_create: FF width must be a multiple of 64");
+  KIRI_REQUIRE(dims->img_h % 8 == 0, "kiri_create: IMG_H must be a multiple of 8");
+  KiriHandle* h = new (std::nothrow) KiriHandle;
+  KIRI_REQUIRE(h, "kiri_create: out of host memory");
+  h->d = *dims;
+  h->w = *weights;
+  memcpy(h->conv1_w, weights->conv1_w_host, sizeof(h->conv1_w));
+  memcpy(h->conv1_b, weights->conv1_b_host, sizeof(h->conv1_b));
+  h->w.conv1_w_host = h->conv1_w;
+  h->w.conv1_b_host = h->conv1_b;
+  *out = h;
+  return 0;
+}
+extern "C" void kiri_destroy(KiriHandle* h) { delete h; }
+
+const KiriDims* kiri_handle_dims(const KiriHandle* h) { return &h->d; }
+const KiriWeights* kiri_handle_weights(const KiriHandle* h) { return &h->w; }
+
+namespace {
+struct EncodeWs {          // byte offsets into the caller's workspace
+  size_t act1, act2, act3, act4, x, a, qkv, o, hbuf, logits_pad, total;
+};
+inline size_t al(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+EncodeWs plan_encode(const KiriDims& d, int B, int Wb, int stem_chunk) {
+  const int H = d.img_h;
+  const int sc = (stem_chunk <= 0 || stem_chunk > B) ? B : stem_chunk;
+  const size_t T = Wb / 4, M = static_cast<size_t>(B) * T;
+  EncodeWs w;
+  size_t off = 0;
+  w.act1 = off; off += al(static_cast<size_t>(sc) * H * Wb * 64 * 2);
+  w.act2 = off; off += al(static_cast<size_t>(sc) * (H / 2) * (Wb / 2) * 96 * 2);
+  w.act3 = off; off += al(static_cast<size_t>(sc) * (H / 4) * (Wb / 4) * 160 * 2);
+  w.act4 = off; off += al(static_cast<size_t>(B) * (H / 8) * T * 256 * 2);
+  w.x = off;    off += al(M * 256 * 4);
+  w.a = off;    off += al(M * 256 * 2);
+  w.qkv = off;  off += al(M * 768 * 2);
+  w.o = off;    off += al(M * 256 * 2);
+  w.hbuf = off; off += al(M * static_cast<size_t>(d.enc_ff) * 2);
+  w.logits_pad = off;
+  w.total = off;
+  return w;
+}
+}  // namespace
+
+extern "C" size_t kiri_encode_workspace_bytes(const KiriHandle* h, int B, int Wb, int stem_chunk) {
+  if (!h || B <= 0 || Wb <= 0) return 0;
+  return plan_encode(h->d, B, Wb, stem_chunk).total;
+}
+
+#define KIRI_TRY(expr)            \
+  do {                            \
+    int _rc = (expr);             \
+    if (_rc != 0) return _rc;     \
+  } while (0)
+
+extern "C" int kiri_encode(KiriHandle* h, const uint8_t* planes_u8, int B, int Wb, int stem_chunk,
+                           void* workspace, size_t workspace_bytes, float* mem_f32, void* mem_bf16,
+                           float* logits, float* tok_f32, const int* kv_len, cudaStream_t stream) {
+  KIRI_REQUIRE(h && planes_u8 && workspace, "kiri_encode: null pointer");
+  KIRI_REQUIRE(B > 0 && Wb > 0 && Wb % 128 == 0 && Wb / 4 <= h->d.max_t,
+               "kiri_encode: batch width %d must be a positive multiple of 128 and <= %d", Wb, h->d.max_t * 4);
+  const KiriDims& d = h->d;
+  const KiriWeights& w = h->w;
+  const EncodeWs ws = plan_encode(d, B, Wb, stem_chunk);
+  KIRI_REQUIRE(workspace_bytes >= ws.total, "kiri_encode: workspace of %zu bytes given, %zu needed", workspace_bytes, ws.total);
+  uint8_t* base = reinterpret_cast<uint8_t*>(workspace);
+  const int H = d.img_h, T = Wb / 4, D = d.enc_dim;
+  const int M = B * T;
+  const int sc = (stem_chunk <= 0 || stem_chunk > B) ? B : stem_chunk;
+
+  // ---- stem, in sub-batches whose activations stay L2-resident
+  for (int b0 = 0; b0 < B; b0 += sc) {
+    const int nb = (B - b0) < sc ? (B - b0) : sc;
+    KIRI_TRY(kiri_conv1(planes_u8 + static_cast<size_t>(b0) * H * Wb, w.conv1_w_host, w.conv1_b_host, nb, H, Wb,
+                        base + ws.act1, stream));
+    KIRI_TRY(conv_call(base + ws.act1, w.conv2_w, w.conv2_b, nb, H, Wb, 64, 96, 2, 2, base + ws.act2, stream));
+    KIRI_TRY(conv_call(base + ws.act2, w.conv3_w, w.conv3_b, nb, H / 2, Wb / 2, 96, 160, 2, 2, base + ws.act3, stream));
+    KIRI_TRY(conv_call(base + ws.act3, w.conv4_w, w.conv4_b, nb, H / 4, Wb / 4, 160, 256, 2, 1,
+                       base + ws.act4 + static_cast<size_t>(b0) * (H / 8) * T * 256 * 2, stream));
+  }
+  float* x = reinterpret_cast<float*>(base + ws.x);
+  void* a = base + ws.a;
+  // ---- pool + positional table + enc_ln_in (+ norm1 of layer 0)
+  KIRI_TRY(kiri_pool_pos_ln(base + ws.act4, w.pos_table, B, H / 8, T, D, w.enc_ln_in_g, w.enc_ln_in_b,
+                            w.enc[0].ln1_g, w.enc[0].ln1_b, x, a, stream));
+  if (tok_f32) KIRI_CHECK_CUDA(cudaMemcpyAsync(tok_f32, x, static_cast<size_t>(M) * D * 4, cudaMemcpyDeviceToDevice, stream));
+  // ---- encoder layers
+  for (int l = 0; l < d.enc_layers; ++l) {
+    const KiriEncLayerWeights& lw = w.enc[l];
+    KIRI_TRY(gemm_call(a, lw.wqkv, lw.bqkv, M, 3 * D, D, EPI_BIAS_BF16, base + ws.qkv, nullptr, nullptr, nullptr, nullptr, stream));
+    KIRI_TRY(kiri_encoder_attention(base + ws.qkv, base + ws.o, B, T, d.enc_heads, D, kv_len, stream));
+    // x += out_proj(o); a = norm2(x)
+    KIRI_TRY(gemm_call(base + ws.o, lw.wo, lw.bo, M, D, D, EPI_BIAS_RESID_LN, x, x, lw.ln2_g, lw.ln2_b, a, stream));
+    KIRI_TRY(gemm_call(a, lw.w1, lw.b1, M, d.enc_ff, D, EPI_BIAS_GELU_BF16, base + ws.hbuf, nullptr, nullptr, nullptr, nullptr, stream));
+    // x += linear2(h); a = next layer's norm1(x)  (last layer: enc_ln, handled below)
+    if (l + 1 < d.enc_layers) {
+      KIRI_TRY(gemm_call(base + ws.hbuf, lw.w2, lw.b2, M, D, d.enc_ff, EPI_BIAS_RESID_LN, x, x, w.enc[l + 1].ln1_g,
+                         w.enc[l + 1].ln1_b, a, stream));
+    } else {
+      KIRI_TRY(gemm_call(base + ws.hbuf, lw.w2, lw.b2, M, D, d.enc_ff, EPI_BIAS_RESID_F32, x, x, nullptr, nullptr, nullptr, stream));
+    }
+  }
+  // ---- mem = enc_ln(x); head input = ctc_head.0(mem)
+  void* mem_b = mem_bf16 ? mem_bf16 : base + ws.o;     // o is free now
+  KIRI_TRY(kiri_layernorm(x, M, D, w.enc_ln_g, w.enc_ln_b, mem_f32, mem_b, w.ctc_ln_g, w.ctc_ln_b, a, stream));
+  if (logits)
+    KIRI_TRY(gemm_call(a, w.ctc_w, w.ctc_b, M, (d.ctc_classes + 15) / 16 * 16, D, EPI_BIAS_F32, logits, nullptr, nullptr, nullptr,
+                       nullptr, stream));
+  return 0;
+}

@@ -1,0 +1,71 @@
+// tcgen05 / TMEM / TMA implicit-GEMM for the conv stem (3x3, NHWC bf16) and every dense layer.
+//
+// One kernel serves K3-K5, K8, K9, K11 of SURVEY.md §2.3:
+//   D[128 x bn] (fp32, TMEM) = sum over (tap, 32-channel chunk) A[128 x 32] * B[bn x 32]^T
+// * A rows are output pixels.  A tile is NSEG "segments"; one segment is an R x SEG patch of
+//   output pixels fetched by ONE 5-D TMA box (c32, W, H, chunk, image) whose W/H traversal
+//   strides are the conv strides and whose out-of-bounds taps are zero-filled by TMA -> the
+//   3x3 halo, the stride-2 sampling and the zero padding cost no instructions.  A plain
+//   [M,K] matrix is the degenerate case (1 tap, R=1, SEG=128, H=1, one image).
+// * B is the [N, taps*Cin] weight matrix (K contiguous), fetched by a 3-D box (c32, N, chunk).
+// * K is cut into 32-element (64-byte) chunks, SWIZZLE_64B, because the stem's channel counts
+//   (64, 96, 160) are multiples of 32 but not of 64.  A pipeline stage holds CPS chunks.
+// * Warp roles: warp0 = TMA producer (1 thread), warp1 = MMA issuer (1 thread) + TMEM owner,
+//   warps 2..5 = epilogue (tcgen05.ld -> bias/activation/residual -> global).  Two fp32
+//   accumulators (2 x 256 TMEM columns) let the epilogue of tile i overlap the MMAs of i+1.
+// * Persistent: grid = min(#tiles, #SMs); tiles are taken round-robin.
+#pragma once
+
+#include "common.cuh"
+
+namespace kiri {
+
+enum EpiMode : int {
+  EPI_BIAS_BF16 = 0,       // out_bf16 = acc + bias
+  EPI_BIAS_SILU_BF16 = 1,  // out_bf16 = silu(acc + bias)          (conv + folded BN + SiLU)
+  EPI_BIAS_GELU_BF16 = 2,  // out_bf16 = gelu_erf(acc + bias)      (FFN first linear)
+  EPI_BIAS_RESID_F32 = 3,  // out_f32  = resid_f32 + acc + bias    (attention out-proj, FFN second)
+  EPI_BIAS_F32 = 4,        // out_f32  = acc + bias                (CTC / decoder heads)
+  EPI_BIAS_RESID_LN = 5,   // out_f32  = resid + acc + bias; out2_bf16 = LayerNorm(out_f32), N == 256
+};
+
+struct ConvGeom {
+  int n_seg_total;     // segments in the whole problem
+  int segs_per_img;    // (OH/R) * (OW/SEG)
+  int segs_per_row;    // OW / SEG
+  int OH, OW;          // output spatial size (GEMM: OH=1, OW=M)
+  int R, SEG;          // segment = R output rows x SEG output columns; NSEG*R*SEG == 128
+  int sw, sh, pad;     // conv stride (w,h) and padding (GEMM: 1,1,0)
+  int kw;              // kernel width (3 or 1)
+  int taps;            // kw*kh (9 or 1)
+  int chunks_per_tap;  // Cin / 32
+  int cgs;             // chunk groups per tap = chunks_per_tap / CPS
+};
+
+struct EpiParams {
+  void* out;           // bf16 or fp32, row-major [rows, ldc]
+  const float* bias;   // [N] (never null; pass zeros for bias-free layers)
+  const float* resid;  // fp32 [rows, ldc] for EPI_BIAS_RESID_F32 (may alias out)
+  int ldc;             // elements per output row
+  int n_valid;         // N (columns >= n_valid are neither read from bias nor stored)
+  const float* ln_g;   // EPI_BIAS_RESID_LN: LayerNorm affine [256]
+  const float* ln_b;
+  void* out2;          // EPI_BIAS_RESID_LN: bf16 [rows, 256]
+};
+
+// Host launcher (gemm_tc.cu).  A is described by an NHWC activation [NB, IH, IW, Cin]
+// (Cin % 32 == 0) or, for a plain GEMM, [1, 1, M, K]; W is [N, taps*Cin] bf16.
+struct GemmLaunch {
+  const void* a;       // bf16 activations
+  const void* w;       // bf16 weights [N, taps*Cin]
+  int NB, IH, IW, Cin; // input geometry
+  int OH, OW;          // output geometry
+  int sw, sh, pad, kw, kh;
+  int N;               // output channels
+  int epi;             // EpiMode
+  EpiParams e;
+};
+int launch_gemm_tc(const GemmLaunch& L, cudaStream_t stream);
+int gemm_tc_num_sms();
+
+}  // namespace kiri

@@ -1,0 +1,131 @@
+// K6/K7 + every LayerNorm of the encoder/decoder: one warp per token, D = 256 (8 channels per
+// lane, 16-byte accesses), fp32 statistics, eps 1e-5.
+//
+//   pool_pos_ln : mean over the RH stem rows + constant 2-D positional table + enc_ln_in
+//                 (+ optionally the first layer's norm1)      model.py:194-208, 302-304
+//   ln_chain    : LN (-> fp32 and/or bf16) [-> second LN -> bf16]
+//                 used for norm1/norm2 of each layer, and for enc_ln followed by ctc_head.0
+//                 (model.py:306, 264-268).
+#include "common.cuh"
+#include "kiri_b200.h"
+
+namespace kiri {
+
+static constexpr int kD = 256;
+static constexpr int kLnThreads = 256;    // 8 tokens per CTA
+static constexpr float kLnEps = 1e-5f;
+
+__device__ __forceinline__ void ln8(float (&v)[8], const float* __restrict__ g,
+                                    const float* __restrict__ b, int lane) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += v[i];
+  const float mean = warp_sum(s) * (1.0f / kD);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; q += d * d; }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / kD) + kLnEps);
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(g) + lane * 2);
+  const float4 g1 = __ldg(reinterpret_cast<const float4*>(g) + lane * 2 + 1);
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(b) + lane * 2);
+  const float4 b1 = __ldg(reinterpret_cast<const float4*>(b) + lane * 2 + 1);
+  const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+  const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = (v[i] - mean) * rstd * gg[i] + bb[i];
+}
+
+__device__ __forceinline__ void st_f32x8(float* p, const float (&v)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void st_bf16x8(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 pk;
+  pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]);
+  pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = pk;
+}
+
+// act: bf16 [B, RH, T, 256] (NHWC stem output); pos: fp32 [T, 256]
+__global__ void __launch_bounds__(kLnThreads)
+pool_pos_ln_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ pos, int n_tok,
+                   int RH, int T, const float* g0, const float* b0, const float* g1, const float* b1,
+                   float* __restrict__ x_f32, __nv_bfloat16* __restrict__ a_bf16) {
+  const int lane = threadIdx.x & 31;
+  const int tok = blockIdx.x * (kLnThreads / 32) + (threadIdx.x >> 5);
+  if (tok >= n_tok) return;
+  const int b = tok / T, t = tok - b * T;
+  float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int r = 0; r < RH; ++r) {
+    const uint4 pk = __ldg(reinterpret_cast<const uint4*>(
+        act + ((static_cast<size_t>(b) * RH + r) * T + t) * kD + lane * 8));
+    v[0] += bf16_lo(pk.x); v[1] += bf16_hi(pk.x); v[2] += bf16_lo(pk.y); v[3] += bf16_hi(pk.y);
+    v[4] += bf16_lo(pk.z); v[5] += bf16_hi(pk.z); v[6] += bf16_lo(pk.w); v[7] += bf16_hi(pk.w);
+  }
+  const float inv = 1.0f / static_cast<float>(RH);
+  const float4 p0 = __ldg(reinterpret_cast<const float4*>(pos + static_cast<size_t>(t) * kD) + lane * 2);
+  const float4 p1 = __ldg(reinterpret_cast<const float4*>(pos + static_cast<size_t>(t) * kD) + lane * 2 + 1);
+  const float pp[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = v[i] * inv + pp[i];
+  ln8(v, g0, b0, lane);
+  st_f32x8(x_f32 + static_cast<size_t>(tok) * kD + lane * 8, v);
+  if (a_bf16) {
+    ln8(v, g1, b1, lane);
+    st_bf16x8(a_bf16 + static_cast<size_t>(tok) * kD + lane * 8, v);
+  }
+}
+
+__global__ void __launch_bounds__(kLnThreads)
+ln_chain_kernel(const float* __restrict__ x, int n_tok, const float* g0, const float* b0,
+                float* __restrict__ y_f32, __nv_bfloat16* __restrict__ y_bf16, const float* g1,
+                const float* b1, __nv_bfloat16* __restrict__ z_bf16) {
+  const int lane = threadIdx.x & 31;
+  const int tok = blockIdx.x * (kLnThreads / 32) + (threadIdx.x >> 5);
+  if (tok >= n_tok) return;
+  const float4 x0 = *reinterpret_cast<const float4*>(x + static_cast<size_t>(tok) * kD + lane * 8);
+  const float4 x1 = *reinterpret_cast<const float4*>(x + static_cast<size_t>(tok) * kD + lane * 8 + 4);
+  float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+  ln8(v, g0, b0, lane);
+  if (y_f32) st_f32x8(y_f32 + static_cast<size_t>(tok) * kD + lane * 8, v);
+  if (y_bf16) st_bf16x8(y_bf16 + static_cast<size_t>(tok) * kD + lane * 8, v);
+  if (z_bf16) {
+    ln8(v, g1, b1, lane);
+    st_bf16x8(z_bf16 + static_cast<size_t>(tok) * kD + lane * 8, v);
+  }
+}
+
+}  // namespace kiri
+
+using namespace kiri;
+
+extern "C" int kiri_pool_pos_ln(const void* act_bf16, const float* pos_table, int n_lines, int RH, int T,
+                                int D, const float* g0, const float* b0, const float* g1, const float* b1,
+                                float* x_f32, void* a_bf16, cudaStream_t stream) {
+  KIRI_REQUIRE(D == kD, "kiri_pool_pos_ln: model width %d unsupported (kernels are built for 256)", D);
+  KIRI_REQUIRE(act_bf16 && pos_table && g0 && b0 && x_f32, "kiri_pool_pos_ln: null pointer");
+  KIRI_REQUIRE(!a_bf16 || (g1 && b1), "kiri_pool_pos_ln: second LayerNorm needs its affine");
+  const int n_tok = n_lines * T;
+  if (n_tok == 0) return 0;
+  const int per = kLnThreads / 32;
+  pool_pos_ln_kernel<<<(n_tok + per - 1) / per, kLnThreads, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(act_bf16), pos_table, n_tok, RH, T, g0, b0, g1, b1, x_f32,
+      reinterpret_cast<__nv_bfloat16*>(a_bf16));
+  KIRI_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int kiri_layernorm(const float* x, int n_tok, int D, const float* g0, const float* b0, float* y_f32,
+                              void* y_bf16, const float* g1, const float* b1, void* z_bf16,
+                              cudaStream_t stream) {
+  KIRI_REQUIRE(D == kD, "kiri_layernorm: model width %d unsupported (kernels are built for 256)", D);
+  KIRI_REQUIRE(x && g0 && b0, "kiri_layernorm: null pointer");
+  KIRI_REQUIRE(!z_bf16 || (g1 && b1), "kiri_layernorm: second LayerNorm needs its affine");
+  if (n_tok == 0) return 0;
+  const int per = kLnThreads / 32;
+  ln_chain_kernel<<<(n_tok + per - 1) / per, kLnThreads, 0, stream>>>(
+      x, n_tok, g0, b0, y_f32, reinterpret_cast<__nv_bfloat16*>(y_bf16), g1, b1,
+      reinterpret_cast<__nv_bfloat16*>(z_bf16));
+  KIRI_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,266 @@
+// K1: crop -> (invert if dark) -> Pillow-exact bilinear resize to the line height -> crop/pad
+// to the batch width -> uint8 plane (+ optional normalised bf16).
+//
+// Replaces  OCR._preprocess_region        kiri_ocr/core.py:489-528
+//           ResizeKeepRatioPadNoCrop      kiri_ocr/model.py:316-331
+//           preprocess_pil                kiri_ocr/model.py:334-339   (per line, CPU, Pillow)
+//
+// One CTA per crop.  Pillow's resample is integer fixed point: float64 triangle weights,
+// normalised, quantised to int(0.5 + w*2^22); each pass accumulates in integers, adds 2^21,
+// shifts by 22 and clips to uint8.  The weights are recomputed on the device in float64 with
+// explicitly rounded operations (no FMA contraction), which reproduces the host bit for bit.
+// Horizontal pass first (source rows staged through shared memory with 32-bit loads), the
+// intermediate lives in shared memory, then the vertical pass writes coalesced rows.
+#include "common.cuh"
+#include "kiri_b200.h"
+
+namespace kiri {
+
+static constexpr int kPrecisionBits = 22;
+static constexpr int kPreThreads = 256;
+static constexpr int kRowBlock = 8;       // source rows staged per step
+static constexpr int kMaxTaps = 64;       // supports down-scaling up to ~31x
+
+struct Coef {           // double-precision replica of Pillow's precompute_coeffs for one index
+  int xmin, n;
+};
+
+__device__ __forceinline__ Coef coef_bounds(int xx, double scale, double support, int in_size,
+                                            double& center) {
+  center = __dmul_rn(static_cast<double>(xx) + 0.5, scale);
+  int xmin = __double2int_rz(__dadd_rn(__dsub_rn(center, support), 0.5));
+  if (xmin < 0) xmin = 0;
+  int xmax = __double2int_rz(__dadd_rn(__dadd_rn(center, support), 0.5));
+  if (xmax > in_size) xmax = in_size;
+  Coef c;
+  c.xmin = xmin;
+  c.n = xmax - xmin;
+  return c;
+}
+__device__ __forceinline__ double tri_weight(int x, int xmin, double center, double ss) {
+  double arg = __dmul_rn(__dadd_rn(__dsub_rn(static_cast<double>(x + xmin), center), 0.5), ss);
+  arg = fabs(arg);
+  return arg < 1.0 ? __dsub_rn(1.0, arg) : 0.0;
+}
+// writes taps [0, ksize) for output index xx into k[tap * kstride]
+__device__ __forceinline__ int fill_coefs(int xx, int in_size, int out_size, int ksize, int* k,
+                                          int kstride) {
+  const double scale = __ddiv_rn(static_cast<double>(in_size), static_cast<double>(out_size));
+  const double fs = scale < 1.0 ? 1.0 : scale;
+  const double ss = __ddiv_rn(1.0, fs);
+  double center;
+  const Coef c = coef_bounds(xx, scale, fs, in_size, center);
+  double ww = 0.0;
+  for (int x = 0; x < c.n; ++x) ww = __dadd_rn(ww, tri_weight(x, c.xmin, center, ss));
+  for (int x = 0; x < ksize; ++x) {
+    int q = 0;
+    if (x < c.n) {
+      double w = tri_weight(x, c.xmin, center, ss);
+      if (ww != 0.0) w = __ddiv_rn(w, ww);
+      q = __double2int_rz(__dadd_rn(0.5, __dmul_rn(w, 4194304.0)));
+    }
+    k[x * kstride] = q;
+  }
+  return c.xmin;
+}
+
+__device__ __forceinline__ uint8_t clip8(int acc) {
+  acc >>= kPrecisionBits;
+  return static_cast<uint8_t>(acc < 0 ? 0 : (acc > 255 ? 255 : acc));
+}
+
+__global__ void __launch_bounds__(kPreThreads)
+preprocess_pack_kernel(const uint8_t* __restrict__ src, const KiriCropDesc* __restrict__ descs,
+                       int img_h, int Wb, uint8_t* __restrict__ planes,
+                       __nv_bfloat16* __restrict__ norm_out, int smem_bytes) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  __shared__ unsigned long long s_sum;
+  const KiriCropDesc d = descs[blockIdx.x];
+  const int tid = threadIdx.x;
+  const int w = d.w, h = d.h, nw = d.nw;
+  const int Wout = nw < Wb ? nw : Wb;
+  const uint8_t* crop = src + d.src_offset;
+  uint8_t* plane = planes + static_cast<size_t>(d.out_index) * img_h * Wb;
+  __nv_bfloat16* nplane = norm_out ? norm_out + static_cast<size_t>(d.out_index) * img_h * Wb : nullptr;
+
+  // ---------------- pass 0: sum of the crop -> invert decision (core.py:524) ----------------
+  if (tid == 0) s_sum = 0ull;
+  __syncthreads();
+  {
+    unsigned int local = 0;
+    const int warp = tid >> 5, lane = tid & 31, nwarps = kPreThreads >> 5;
+    for (int r = warp; r < h; r += nwarps) {
+      const uint8_t* row = crop + static_cast<size_t>(r) * d.pitch;
+      const uintptr_t a = reinterpret_cast<uintptr_t>(row);
+      const int head = static_cast<int>(a & 3);          // bytes before `row` in its first word
+      const uint32_t* wp = reinterpret_cast<const uint32_t*>(a - head);
+      const int nwords = (head + w + 3) >> 2;
+      for (int i = lane; i < nwords; i += 32) {
+        uint32_t v = __ldg(wp + i);
+        const int lo = i * 4 - head;                     // crop column of byte 0 of this word
+        uint32_t mask = 0xffffffffu;
+        if (lo < 0) mask &= 0xffffffffu << (8 * (-lo));
+        if (lo + 4 > w) mask &= 0xffffffffu >> (8 * (lo + 4 - w));
+        local = __dp4a(v & mask, 0x01010101u, local);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if (lane == 0) atomicAdd(&s_sum, static_cast<unsigned long long>(local));
+  }
+  __syncthreads();
+  const bool invert = s_sum < 127ull * static_cast<unsigned long long>(w) * h;
+  const uint32_t inv_mask = invert ? 0xffffffffu : 0u;
+
+  // ---------------- coefficient geometry ----------------
+  const bool do_h = (nw != w);
+  const bool do_v = (h != img_h);
+  const double hscale = static_cast<double>(w) / static_cast<double>(nw);
+  const double vscale = static_cast<double>(h) / static_cast<double>(img_h);
+  const int ksize_h = do_h ? (static_cast<int>(ceil(hscale < 1.0 ? 1.0 : hscale)) * 2 + 1) : 1;
+  const int ksize_v = do_v ? (static_cast<int>(ceil(vscale < 1.0 ? 1.0 : vscale)) * 2 + 1) : 1;
+  const int Ws = d.strip_w;                               // output columns per strip (host-chosen)
+
+  // shared-memory carve (all 16-byte aligned)
+  int off = 0;
+  int* kv = reinterpret_cast<int*>(sm + off);      off += ((img_h * ksize_v * 4 + 15) & ~15);
+  int* ymin = reinterpret_cast<int*>(sm + off);    off += ((img_h * 4 + 15) & ~15);
+  int* kh = reinterpret_cast<int*>(sm + off);      off += ((Ws * ksize_h * 4 + 15) & ~15);
+  int* xmin = reinterpret_cast<int*>(sm + off);    off += ((Ws * 4 + 15) & ~15);
+  uint8_t* inter = sm + off;                       off += ((h * Ws + 15) & ~15);
+  uint8_t* srow = sm + off;                        // kRowBlock rows of staged source
+  const int srow_cap = (smem_bytes - off) / kRowBlock & ~15;
+
+  if (do_v) {
+    for (int y = tid; y < img_h; y += kPreThreads) ymin[y] = fill_coefs(y, h, img_h, ksize_v, kv + y * ksize_v, 1);
+  }
+
+  for (int c0 = 0; c0 < Wout; c0 += Ws) {
+    const int cw = (Wout - c0) < Ws ? (Wout - c0) : Ws;
+    __syncthreads();
+    // horizontal coefficients of this strip, tap-major so lanes hit consecutive banks
+    if (do_h) {
+      for (int x = tid; x < cw; x += kPreThreads) xmin[x] = fill_coefs(c0 + x, w, nw, ksize_h, kh + x, Ws);
+    } else {
+      for (int x = tid; x < cw; x += kPreThreads) xmin[x] = c0 + x;
+    }
+    __syncthreads();
+    const int sx0 = xmin[0];                                  // first source column needed
+    const int sx1 = do_h ? (xmin[cw - 1] + ksize_h) : (c0 + cw);
+    const int span = (sx1 < w ? sx1 : w) - sx0;               // source columns to stage
+
+    for (int r0 = 0; r0 < h; r0 += kRowBlock) {
+      const int nr = (h - r0) < kRowBlock ? (h - r0) : kRowBlock;
+      // stage rows r0..r0+nr, columns sx0..sx0+span, inverted if needed, with 32-bit loads
+      for (int rr = 0; rr < nr; ++rr) {
+        const uint8_t* row = crop + static_cast<size_t>(r0 + rr) * d.pitch + sx0;
+        const uintptr_t a = reinterpret_cast<uintptr_t>(row);
+        const int head = static_cast<int>(a & 3);
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(a - head);
+        const int nwords = (head + span + 3) >> 2;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(srow + rr * srow_cap);
+        for (int i = tid; i < nwords; i += kPreThreads) dst[i] = __ldg(wp + i) ^ inv_mask;
+      }
+      __syncthreads();
+      // horizontal pass -> inter[r][x]
+      for (int idx = tid; idx < nr * cw; idx += kPreThreads) {
+        const int rr = idx / cw, x = idx - rr * cw;
+        const uint8_t* row = crop + static_cast<size_t>(r0 + rr) * d.pitch + sx0;
+        const int head = static_cast<int>(reinterpret_cast<uintptr_t>(row) & 3);
+        const uint8_t* s = srow + rr * srow_cap + head + (xmin[x] - sx0);
+        uint8_t o;
+        if (do_h) {
+          int acc = 1 << (kPrecisionBits - 1);
+          const int avail = w - xmin[x];                      // taps beyond the row carry weight 0
+          for (int k = 0; k < ksize_h; ++k) {
+            const int kk = kh[k * Ws + x];
+            if (k < avail) acc += static_cast<int>(s[k]) * kk;
+          }
+          o = clip8(acc);
+        } else {
+          o = s[0];
+        }
+        inter[(r0 + rr) * Ws + x] = o;
+      }
+      __syncthreads();
+    }
+    // vertical pass -> plane rows
+    for (int idx = tid; idx < img_h * cw; idx += kPreThreads) {
+      const int y = idx / cw, x = idx - y * cw;
+      uint8_t o;
+      if (do_v) {
+        int acc = 1 << (kPrecisionBits - 1);
+        const int y0 = ymin[y];
+        const int avail = h - y0;
+        for (int k = 0; k < ksize_v; ++k) {
+          const int kk = kv[y * ksize_v + k];
+          if (k < avail) acc += static_cast<int>(inter[(y0 + k) * Ws + x]) * kk;
+        }
+        o = clip8(acc);
+      } else {
+        o = inter[y * Ws + x];
+      }
+      plane[y * Wb + c0 + x] = o;
+      if (nplane) {
+        const float f = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(o), 255.0f), 0.5f), 0.5f);
+        nplane[y * Wb + c0 + x] = __float2bfloat16_rn(f);
+      }
+    }
+  }
+  // gray-128 padding on the right (model.py:329-330)
+  const int padw = Wb - Wout;
+  if (padw > 0) {
+    const float f = __fdiv_rn(__fsub_rn(__fdiv_rn(128.0f, 255.0f), 0.5f), 0.5f);
+    const __nv_bfloat16 fb = __float2bfloat16_rn(f);
+    for (int idx = tid; idx < img_h * padw; idx += kPreThreads) {
+      const int y = idx / padw, x = idx - y * padw;
+      plane[y * Wb + Wout + x] = 128;
+      if (nplane) nplane[y * Wb + Wout + x] = fb;
+    }
+  }
+}
+
+}  // namespace kiri
+
+using namespace kiri;
+
+extern "C" int kiri_preprocess_smem_bytes(int w, int h, int nw, int img_h, int Wb, int strip_w) {
+  const int Wout = nw < Wb ? nw : Wb;
+  const int Ws = strip_w < Wout ? strip_w : Wout;
+  const double hs = (double)w / nw, vs = (double)h / img_h;
+  const int ksh = (nw != w) ? ((int)ceil(hs < 1.0 ? 1.0 : hs) * 2 + 1) : 1;
+  const int ksv = (h != img_h) ? ((int)ceil(vs < 1.0 ? 1.0 : vs) * 2 + 1) : 1;
+  long long off = 0;
+  off += ((long long)img_h * ksv * 4 + 15) & ~15ll;
+  off += ((long long)img_h * 4 + 15) & ~15ll;
+  off += ((long long)Ws * ksh * 4 + 15) & ~15ll;
+  off += ((long long)Ws * 4 + 15) & ~15ll;
+  off += ((long long)h * Ws + 15) & ~15ll;
+  // staged source rows: span of a strip plus slack for the 4-byte alignment head and taps
+  const long long span = (long long)ceil((hs < 1.0 ? 1.0 : hs) * Ws) + 2 * ksh + 8;
+  const long long per_row = (span + 4 + 15) & ~15ll;
+  off += per_row * kRowBlock + 16 * kRowBlock;
+  return off > 0x7fffffff ? 0x7fffffff : (int)off;
+}
+
+extern "C" int kiri_preprocess_pack(const uint8_t* src, const KiriCropDesc* descs_dev, int n_crops,
+                                    int img_h, int Wb, int smem_bytes, uint8_t* planes_u8,
+                                    void* norm_bf16, cudaStream_t stream) {
+  KIRI_REQUIRE(src && descs_dev && planes_u8, "kiri_preprocess_pack: null pointer");
+  KIRI_REQUIRE(n_crops >= 0 && img_h > 0 && Wb > 0, "kiri_preprocess_pack: bad sizes");
+  if (n_crops == 0) return 0;
+  static int max_optin = 0;
+  if (!max_optin) {
+    int dev = 0;
+    KIRI_CHECK_CUDA(cudaGetDevice(&dev));
+    KIRI_CHECK_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    KIRI_CHECK_CUDA(cudaFuncSetAttribute(preprocess_pack_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+  }
+  KIRI_REQUIRE(smem_bytes <= max_optin, "kiri_preprocess_pack: %d bytes of shared memory requested, %d available",
+               smem_bytes, max_optin);
+  preprocess_pack_kernel<<<n_crops, kPreThreads, smem_bytes, stream>>>(
+      src, descs_dev, img_h, Wb, planes_u8, reinterpret_cast<__nv_bfloat16*>(norm_bf16), smem_bytes);
+  KIRI_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

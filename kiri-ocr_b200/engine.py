@@ -1,0 +1,335 @@
+"""BatchedRecognizer — host orchestration of the B200 line-recognition path.
+
+Takes line crops (or pages + boxes), runs preprocess -> stem -> encoder -> CTC head -> CTC greedy
+("ctc") or the greedy attention decoder ("decoder") on the device through ``libkiri_b200.so``, and
+returns the reference's ``(text, confidence)`` per line.  It replaces the per-line loop body of
+``OCR.process_document`` (kiri_ocr/core.py:770-776: ``_preprocess_region`` + ``recognize_region``).
+
+Width modes:
+  * ``"parity"``   — every line is padded to ``cfg.IMG_W`` (640) exactly like the reference;
+  * ``"bucketed"`` — lines are grouped by the smallest bucket in {128,...,640} that holds their
+    resized width; a group of width Wb equals the reference run with ``cfg.IMG_W = Wb``;
+  * ``"masked"``   — bucketed + per-line key mask in self-attention (no reference equivalent).
+PyTorch is used for device memory, pinned staging and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import CFG, CharTokenizer
+from .weights import PackedWeights
+
+BUCKETS = (128, 256, 384, 512, 640)
+DESC_DTYPE = np.dtype([("src_offset", "<i8"), ("pitch", "<i4"), ("w", "<i4"), ("h", "<i4"),
+                       ("nw", "<i4"), ("out_index", "<i4"), ("strip_w", "<i4")])
+assert DESC_DTYPE.itemsize == C.sizeof(_lib.KiriCropDesc)
+PRE_SMEM_CAP = 100 * 1024          # two preprocessing CTAs per SM
+
+
+@dataclass
+class LineResult:
+    text: str
+    confidence: float
+    ctc_confidence: float
+    ids: np.ndarray                 # collapsed CTC ids ("ctc") or decoder ids ("decoder")
+    step_logp: Optional[np.ndarray] = None
+    step_prob: Optional[np.ndarray] = None
+    frame_ids: Optional[np.ndarray] = None
+    frame_prob: Optional[np.ndarray] = None
+
+
+def target_widths(w: np.ndarray, h: np.ndarray, img_h: int) -> np.ndarray:
+    """``max(1, int(round(iw * (img_h / float(ih)))))`` (model.py:321-322), vectorised; numpy's
+    rint is round-half-to-even like Python's round."""
+    scale = float(img_h) / h.astype(np.float64)
+    return np.maximum(1, np.rint(w.astype(np.float64) * scale)).astype(np.int64)
+
+
+def _pre_smem(w, h, nw, img_h, Wb, strip):
+    """numpy mirror of kiri_preprocess_smem_bytes (csrc/preprocess.cu)."""
+    wout = np.minimum(nw, Wb)
+    ws = np.minimum(strip, wout)
+    hs = w / nw
+    vs = h / img_h
+    ksh = np.where(nw != w, np.ceil(np.maximum(hs, 1.0)).astype(np.int64) * 2 + 1, 1)
+    ksv = np.where(h != img_h, np.ceil(np.maximum(vs, 1.0)).astype(np.int64) * 2 + 1, 1)
+    a16 = lambda v: (v + 15) & ~15          # noqa: E731
+    off = a16(img_h * ksv * 4) + a16(np.full_like(ksv, img_h * 4)) + a16(ws * ksh * 4) + a16(ws * 4) + a16(h * ws)
+    span = np.ceil(np.maximum(hs, 1.0) * ws).astype(np.int64) + 2 * ksh + 8
+    per_row = a16(span + 4)
+    return off + per_row * 8 + 16 * 8
+
+
+def plan_groups(entries: np.ndarray, cfg: CFG, width_mode: str = "parity"
+                ) -> Dict[int, Tuple[np.ndarray, np.ndarray, int]]:
+    """Group lines by batch width; returns {Wb: (line indices, descriptors, smem bytes)}."""
+    img_h = cfg.IMG_H
+    w, h = entries[:, 2], entries[:, 3]
+    nw = target_widths(w, h, img_h)
+    if width_mode == "parity":
+        wb = np.full(len(entries), cfg.IMG_W, np.int64)
+    else:
+        bk = np.array(tuple(b for b in BUCKETS if b <= cfg.IMG_W) or (cfg.IMG_W,), np.int64)
+        wb = bk[np.minimum(np.searchsorted(bk, np.minimum(nw, bk[-1])), len(bk) - 1)]
+    groups = {}
+    for Wb in np.unique(wb):
+        idx = np.nonzero(wb == Wb)[0]
+        gw, gh, gnw = w[idx], h[idx], nw[idx]
+        strip = np.minimum(gnw, Wb)
+        need = _pre_smem(gw, gh, gnw, img_h, int(Wb), strip)
+        for _ in range(6):                                   # halve strips until they fit
+            big = need > PRE_SMEM_CAP
+            if not big.any():
+                break
+            strip = np.where(big & (strip > 32), np.maximum(32, (strip // 2 + 31) // 32 * 32), strip)
+            need = _pre_smem(gw, gh, gnw, img_h, int(Wb), strip)
+        d = np.zeros(len(idx), DESC_DTYPE)
+        d["src_offset"], d["pitch"], d["w"], d["h"] = entries[idx, 0], entries[idx, 1], gw, gh
+        d["nw"], d["out_index"], d["strip_w"] = gnw, np.arange(len(idx)), strip
+        groups[int(Wb)] = (idx, d, int(need.max()))
+    return groups
+
+
+class BatchedRecognizer:
+    def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: CFG, tokenizer: CharTokenizer,
+                 device: str = "cuda", width_mode: str = "parity", stem_chunk: int = 16):
+        _lib.require_device()
+        self.lib = _lib.load()
+        self.cfg, self.tok = cfg, tokenizer
+        self.device = torch.device(device if device != "cuda" else f"cuda:{torch.cuda.current_device()}")
+        if width_mode not in ("parity", "bucketed", "masked"):
+            raise ValueError(f"unknown width_mode {width_mode!r}")
+        self.width_mode = width_mode
+        self.stem_chunk = stem_chunk
+        self.pw = PackedWeights(state_dict, cfg, tokenizer.vocab_size, self.device)
+        h = C.c_void_p()
+        _lib.check(self.lib.kiri_create(C.byref(self.pw.dims), C.byref(self.pw.struct), C.byref(h)), "kiri_create")
+        self.handle = h
+        self._ws: Optional[torch.Tensor] = None
+        self._dws: Optional[torch.Tensor] = None
+        self.launches = 0           # kernels launched by this engine (for bench's gpu_launches)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.kiri_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ host-side planning
+    def buckets(self) -> Tuple[int, ...]:
+        return tuple(b for b in BUCKETS if b <= self.cfg.IMG_W) or (self.cfg.IMG_W,)
+
+    @staticmethod
+    def pack_crops(crops: Sequence[np.ndarray]) -> Tuple[torch.Tensor, np.ndarray]:
+        """Concatenate uint8 crops into one pinned buffer; returns (buffer, entries[n,4] =
+        offset, pitch, w, h)."""
+        sizes = np.array([c.size for c in crops], dtype=np.int64)
+        offs = np.concatenate([[0], np.cumsum(sizes)[:-1]]) if len(crops) else np.zeros(0, np.int64)
+        buf = torch.empty(int(sizes.sum()) + 16, dtype=torch.uint8).pin_memory()
+        nb = buf.numpy()
+        ent = np.zeros((len(crops), 4), np.int64)
+        for i, c in enumerate(crops):
+            if c.dtype != np.uint8 or c.ndim != 2:
+                raise ValueError("crops must be 2-D uint8 arrays")
+            nb[offs[i]:offs[i] + c.size] = np.ascontiguousarray(c).reshape(-1)
+            ent[i] = (offs[i], c.shape[1], c.shape[1], c.shape[0])
+        return buf, ent
+
+    @staticmethod
+    def boxes_to_entries(page_shape: Tuple[int, int], boxes: Sequence[Sequence[int]], page_offset: int = 0,
+                         extra_padding: int = 5) -> Tuple[np.ndarray, np.ndarray]:
+        """core.py:506-517 for every box: clamp-pad by 5 px; returns (entries, valid mask)."""
+        H, W = page_shape
+        b = np.asarray(boxes, dtype=np.int64).reshape(-1, 4)
+        x1 = np.maximum(0, b[:, 0] - extra_padding)
+        y1 = np.maximum(0, b[:, 1] - extra_padding)
+        x2 = np.minimum(W, b[:, 0] + b[:, 2] + extra_padding)
+        y2 = np.minimum(H, b[:, 1] + b[:, 3] + extra_padding)
+        valid = (x2 > x1) & (y2 > y1)
+        ent = np.stack([page_offset + y1 * W + x1, np.full_like(x1, W), x2 - x1, y2 - y1], axis=1)
+        return ent, valid
+
+    def plan(self, entries: np.ndarray) -> Dict[int, Tuple[np.ndarray, np.ndarray, int]]:
+        return plan_groups(entries, self.cfg, self.width_mode)
+
+    # ------------------------------------------------------------------ device stages
+    def _workspace(self, nbytes: int, which: str = "_ws") -> torch.Tensor:
+        cur = getattr(self, which)
+        if cur is None or cur.numel() < nbytes:
+            cur = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            setattr(self, which, cur)
+        return cur
+
+    def preprocess(self, src_dev: torch.Tensor, descs: np.ndarray, Wb: int, smem: int,
+                   want_norm: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+        n = len(descs)
+        dd = torch.from_numpy(descs.view(np.uint8).reshape(-1)).pin_memory().to(self.device, non_blocking=True)
+        planes = torch.empty((n, self.cfg.IMG_H, Wb), dtype=torch.uint8, device=self.device)
+        norm = torch.empty((n, self.cfg.IMG_H, Wb), dtype=torch.bfloat16, device=self.device) if want_norm else None
+        _lib.check(self.lib.kiri_preprocess_pack(src_dev.data_ptr(), dd.data_ptr(), n, self.cfg.IMG_H, Wb, smem,
+                                                 planes.data_ptr(), _lib.ptr(norm), _lib.stream_ptr()),
+                   "kiri_preprocess_pack")
+        self.launches += 1
+        return planes, norm
+
+    def encode(self, planes: torch.Tensor, want_mem_f32: bool = False, want_tokens: bool = False,
+               kv_len: Optional[torch.Tensor] = None, want_logits: bool = True):
+        """[B, IMG_H, Wb] uint8 -> dict(mem_bf16, logits [B,T,Cp], mem_f32?, tokens?)."""
+        B, H, Wb = planes.shape
+        T, D = Wb // 4, self.cfg.ENC_DIM
+        need = self.lib.kiri_encode_workspace_bytes(self.handle, B, Wb, self.stem_chunk)
+        ws = self._workspace(need)
+        out = {"mem_bf16": torch.empty((B * T, D), dtype=torch.bfloat16, device=self.device)}
+        if want_logits:
+            out["logits"] = torch.empty((B, T, self.pw.Cp), dtype=torch.float32, device=self.device)
+        if want_mem_f32:
+            out["mem_f32"] = torch.empty((B, T, D), dtype=torch.float32, device=self.device)
+        if want_tokens:
+            out["tokens"] = torch.empty((B, T, D), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.kiri_encode(self.handle, planes.data_ptr(), B, Wb, self.stem_chunk, ws.data_ptr(), need,
+                                        _lib.ptr(out.get("mem_f32")), out["mem_bf16"].data_ptr(),
+                                        _lib.ptr(out.get("logits")), _lib.ptr(out.get("tokens")), _lib.ptr(kv_len),
+                                        _lib.stream_ptr()), "kiri_encode")
+        n_chunks = math.ceil(B / (self.stem_chunk if 0 < self.stem_chunk <= B else B))
+        self.launches += 4 * n_chunks + 1 + 4 * self.pw.enc_layers + 1 + (1 if want_logits else 0)
+        return out
+
+    def ctc_greedy(self, logits: torch.Tensor, want_frames: bool = False):
+        B, T, Cp = logits.shape
+        ids = torch.empty((B, T), dtype=torch.int32, device=self.device)
+        n_ids = torch.empty(B, dtype=torch.int32, device=self.device)
+        conf = torch.empty(B, dtype=torch.float32, device=self.device)
+        fids = torch.empty((B, T), dtype=torch.int32, device=self.device) if want_frames else None
+        fprob = torch.empty((B, T), dtype=torch.float32, device=self.device) if want_frames else None
+        _lib.check(self.lib.kiri_ctc_greedy(logits.data_ptr(), _lib.DTYPE_F32, B, T, self.pw.C, Cp, ids.data_ptr(),
+                                            n_ids.data_ptr(), conf.data_ptr(), _lib.ptr(fids), _lib.ptr(fprob),
+                                            _lib.stream_ptr()), "kiri_ctc_greedy")
+        self.launches += 1
+        return ids, n_ids, conf, fids, fprob
+
+    def decode_params(self, select_raw: bool = False) -> "_lib.KiriDecodeParams":
+        cfg = self.cfg
+        p = _lib.KiriDecodeParams()
+        fuse = cfg.USE_LM and cfg.USE_LM_FUSION_EVAL and self.pw.has_lm
+        p.lm_alpha = cfg.LM_FUSION_ALPHA if fuse else 0.0
+        p.eos_bias, p.eos_boost, p.eos_bias_until_len = cfg.EOS_LOGP_BIAS, cfg.EOS_LOGP_BOOST, cfg.EOS_BIAS_UNTIL_LEN
+        p.rep_last, p.rep_bigram, p.rep_trigram = cfg.REPEAT_LAST_PENALTY, cfg.REPEAT_BIGRAM_PENALTY, cfg.REPEAT_TRIGRAM_PENALTY
+        p.unk_penalty, p.unk_id = cfg.UNK_LOGP_PENALTY, self.tok.unk_id + self.tok.dec_offset
+        p.len_ratio, p.len_pad, p.mem_ratio, p.max_dec_len = cfg.DEC_MAX_LEN_RATIO, cfg.DEC_MAX_LEN_PAD, cfg.MEM_MAX_LEN_RATIO, cfg.MAX_DEC_LEN
+        p.select_raw = int(select_raw)
+        return p
+
+    def max_steps_bound(self, len_est_max: int, T: int) -> int:
+        cfg = self.cfg
+        a = min(cfg.MAX_DEC_LEN, int(len_est_max * cfg.DEC_MAX_LEN_RATIO) + cfg.DEC_MAX_LEN_PAD)
+        b = min(cfg.MAX_DEC_LEN, int(T * cfg.MEM_MAX_LEN_RATIO) + cfg.DEC_MAX_LEN_PAD)
+        return max(a, b, 1)
+
+    def decode_greedy(self, mem_bf16: torch.Tensor, len_est: torch.Tensor, B: int, T: int, Lmax: int,
+                      select_raw: bool = False, forced: Optional[torch.Tensor] = None, want_steps: bool = False,
+                      poll_every: int = 8):
+        p = self.decode_params(select_raw)
+        need = self.lib.kiri_decode_workspace_bytes(self.handle, B, T, Lmax)
+        ws = self._workspace(need, "_dws")
+        ids = torch.zeros((B, Lmax), dtype=torch.int32, device=self.device)
+        n_out = torch.zeros(B, dtype=torch.int32, device=self.device)
+        sum_lp = torch.zeros(B, dtype=torch.float32, device=self.device)
+        slp = torch.zeros((B, Lmax), dtype=torch.float32, device=self.device) if want_steps else None
+        spr = torch.zeros((B, Lmax), dtype=torch.float32, device=self.device) if want_steps else None
+        steps = C.c_int(0)
+        _lib.check(self.lib.kiri_decode_greedy(self.handle, mem_bf16.data_ptr(), len_est.data_ptr(), B, T, Lmax,
+                                               C.byref(p), ws.data_ptr(), need, ids.data_ptr(), n_out.data_ptr(),
+                                               sum_lp.data_ptr(), _lib.ptr(slp), _lib.ptr(spr), _lib.ptr(forced),
+                                               C.byref(steps), poll_every, _lib.stream_ptr()), "kiri_decode_greedy")
+        self.launches += 3 + steps.value * (3 + 8 * self.pw.dec_layers)
+        return ids, n_out, sum_lp, slp, spr, steps.value
+
+    # ------------------------------------------------------------------ public API
+    @torch.no_grad()
+    def recognize_packed(self, src: torch.Tensor, entries: np.ndarray, method: str = "ctc",
+                         streaming: bool = False) -> List[Optional[LineResult]]:
+        """``src``: uint8 buffer (pinned host or device) holding pages/crops; ``entries[n,4]`` =
+        (byte offset, pitch, w, h) of every crop after the reference's clamp-pad."""
+        if method not in ("ctc", "decoder"):
+            raise ValueError("method must be 'ctc' or 'decoder'")
+        n = len(entries)
+        results: List[Optional[LineResult]] = [None] * n
+        if n == 0:
+            return results
+        src_dev = src if src.is_cuda else src.to(self.device, non_blocking=True)
+        pending = []
+        for Wb, (idx, descs, smem) in self.plan(entries).items():
+            planes, _ = self.preprocess(src_dev, descs, Wb, smem)
+            kv_len = None
+            if self.width_mode == "masked":
+                kv_len = torch.from_numpy(np.minimum((descs["nw"] + 3) // 4, Wb // 4).astype(np.int32)).to(self.device)
+            enc = self.encode(planes, kv_len=kv_len)
+            B, T = len(idx), Wb // 4
+            ids, n_ids, conf, fids, fprob = self.ctc_greedy(enc["logits"], want_frames=streaming and method == "ctc")
+            if method == "ctc":
+                pending.append((idx, "ctc", ids, n_ids, conf, fids, fprob))
+            else:
+                n_host = n_ids.cpu()                                  # length estimates bound the loop
+                Lmax = self.max_steps_bound(int(n_host.max()), T)
+                d_ids, n_out, sum_lp, slp, spr, _ = self.decode_greedy(enc["mem_bf16"], n_ids, B, T, Lmax,
+                                                                      select_raw=streaming, want_steps=True)
+                pending.append((idx, "decoder", d_ids, n_out, sum_lp, conf, slp, spr))
+        torch.cuda.current_stream().synchronize()
+        tok = self.tok
+        for item in pending:
+            idx = item[0]
+            if item[1] == "ctc":
+                _, _, ids, n_ids, conf, fids, fprob = item
+                ids_h, n_h, c_h = ids.cpu().numpy(), n_ids.cpu().numpy(), conf.cpu().numpy()
+                f_h = fids.cpu().numpy() if fids is not None else None
+                p_h = fprob.cpu().numpy() if fprob is not None else None
+                for j, li in enumerate(idx):
+                    row = ids_h[j, :n_h[j]]
+                    results[li] = LineResult(tok.decode_collapsed_ctc(row.tolist()), float(c_h[j]), float(c_h[j]), row,
+                                             frame_ids=None if f_h is None else f_h[j],
+                                             frame_prob=None if p_h is None else p_h[j])
+            else:
+                _, _, d_ids, n_out, sum_lp, conf, slp, spr = item
+                ids_h, n_h, s_h, c_h = d_ids.cpu().numpy(), n_out.cpu().numpy(), sum_lp.cpu().numpy(), conf.cpu().numpy()
+                slp_h, spr_h = slp.cpu().numpy(), spr.cpu().numpy()
+                for j, li in enumerate(idx):
+                    row = ids_h[j, :n_h[j]]
+                    text_ids = []
+                    for t in row.tolist():
+                        if t == tok.dec_eos:
+                            break
+                        text_ids.append(t)
+                    lps = slp_h[j, :n_h[j]].astype(np.float64)
+                    dec_conf = min(1.0, max(0.0, math.exp(float(lps.sum()) / len(lps)))) if len(lps) else 0.0
+                    results[li] = LineResult(tok.decode_dec(text_ids), 0.6 * dec_conf + 0.4 * float(c_h[j]),
+                                             float(c_h[j]), row, step_logp=slp_h[j, :n_h[j]], step_prob=spr_h[j, :n_h[j]])
+        return results
+
+    def recognize_crops(self, crops: Sequence[np.ndarray], method: str = "ctc", streaming: bool = False):
+        buf, ent = self.pack_crops(crops)
+        return self.recognize_packed(buf, ent, method, streaming)
+
+    def recognize_boxes(self, page_gray: np.ndarray, boxes: Sequence[Sequence[int]], method: str = "ctc",
+                        streaming: bool = False) -> List[Optional[LineResult]]:
+        """All boxes of one grayscale page; boxes whose clamped crop is empty give ``None``
+        (the reference skips them, core.py:516-517 / 773-774)."""
+        page = np.ascontiguousarray(page_gray)
+        if page.dtype != np.uint8 or page.ndim != 2:
+            raise ValueError("page must be a 2-D uint8 array")
+        ent, valid = self.boxes_to_entries(page.shape, boxes)
+        buf = torch.empty(page.size + 16, dtype=torch.uint8).pin_memory()
+        buf.numpy()[:page.size] = page.reshape(-1)
+        res = self.recognize_packed(buf, ent[valid], method, streaming)
+        out: List[Optional[LineResult]] = [None] * len(boxes)
+        for k, i in enumerate(np.nonzero(valid)[0]):
+            out[i] = res[k]
+        return out

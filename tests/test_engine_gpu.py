@@ -1,0 +1,145 @@
+"""End-to-end parity of the B200 path against the CPU oracle and the reference goldens (-m gpu).
+
+Floating-point tolerance (stated, bf16 operands with fp32 accumulation and an fp32 residual
+stream): encoder memory  max-abs <= MEM_ATOL  and relative L2 <= MEM_RTOL;  CTC logits
+max-abs <= LOGIT_ATOL.  Token ids must be identical on every frame whose oracle top-1 margin
+exceeds 2 * LOGIT_ATOL ("margin-safe"); collapsed ids / text must be identical for lines whose
+frames are all margin-safe.  Measured values are written to gpurun_out/parity_report.json.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from kiri_ocr_b200 import _lib, fixtures as FX  # noqa: E402
+from kiri_ocr_b200.config import CFG  # noqa: E402
+from tests.golden.cases import VARIANTS, golden_crops, lines_for  # noqa: E402
+
+MEM_ATOL, MEM_RTOL, LOGIT_ATOL = 0.12, 0.02, 0.35
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPORT = {}
+
+
+def _report(key, value):
+    REPORT[key] = value
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "parity_report.json"), "w") as f:
+        json.dump(REPORT, f, indent=1, sort_keys=True)
+
+
+@pytest.fixture(scope="module")
+def engines(tok_cfg):
+    from kiri_ocr_b200.engine import BatchedRecognizer
+    tok, cfg = tok_cfg
+    cache = {}
+
+    def get(name, mode="parity"):
+        if (name, mode) not in cache:
+            sd = FX.make_state_dict(CFG(), 202, **VARIANTS[name])
+            cache[(name, mode)] = (BatchedRecognizer(sd, cfg, tok, width_mode=mode), sd)
+        return cache[(name, mode)]
+    return get
+
+
+def oracle_line(sd, plane):
+    from oracle import model as OM, preprocess as OP
+    x = torch.from_numpy(OP.normalise(plane))[None, None]
+    tokens = OM.stem_tokens(sd, x)
+    mem = OM.encode(sd, x)
+    return tokens[0].numpy(), mem[0].numpy(), OM.ctc_logits(sd, mem)[0].numpy()
+
+
+@pytest.mark.parametrize("name", ["hard", "default"])
+def test_encoder_and_ctc_parity(engines, golden, name):
+    from oracle import decode as OD, preprocess as OP
+    eng, sd = engines(name)
+    crops = golden_crops()[: lines_for(name)]
+    buf, ent = eng.pack_crops(crops)
+    groups = eng.plan(ent)
+    assert list(groups) == [640]
+    idx, descs, smem = groups[640]
+    planes, _ = eng.preprocess(buf.cuda(), descs, 640, smem)
+    enc = eng.encode(planes, want_mem_f32=True, want_tokens=True)
+    ids, n_ids, conf, fids, fprob = eng.ctc_greedy(enc["logits"], want_frames=True)
+    torch.cuda.synchronize()
+    planes_h = planes.cpu().numpy()
+    mem_h, tok_h = enc["mem_f32"].cpu().numpy(), enc["tokens"].cpu().numpy()
+    lg_h = enc["logits"].cpu().numpy()[:, :, :204]
+    stats = {"tok_maxabs": 0.0, "mem_maxabs": 0.0, "mem_rel_l2": 0.0, "logit_maxabs": 0.0, "frames": 0,
+             "frames_equal": 0, "safe_frames": 0, "safe_equal": 0, "lines_text_equal": 0, "lines": len(crops)}
+    for i, c in enumerate(crops):
+        want_plane = OP.resize_keep_ratio_pad(c)
+        assert np.array_equal(planes_h[i], want_plane), i
+        tk, mem, lg = oracle_line(sd, want_plane)
+        stats["tok_maxabs"] = max(stats["tok_maxabs"], float(np.abs(tok_h[i] - tk).max()))
+        stats["mem_maxabs"] = max(stats["mem_maxabs"], float(np.abs(mem_h[i] - mem).max()))
+        stats["mem_rel_l2"] = max(stats["mem_rel_l2"], float(np.linalg.norm(mem_h[i] - mem) / np.linalg.norm(mem)))
+        stats["logit_maxabs"] = max(stats["logit_maxabs"], float(np.abs(lg_h[i] - lg).max()))
+        best, collapsed, cf, length = OD.ctc_greedy(lg)
+        srt = np.sort(lg, axis=1)
+        margin = srt[:, -1] - srt[:, -2]
+        safe = margin > 2 * LOGIT_ATOL
+        got = fids[i].cpu().numpy()
+        stats["frames"] += len(best)
+        stats["frames_equal"] += int((got == best).sum())
+        stats["safe_frames"] += int(safe.sum())
+        stats["safe_equal"] += int((got[safe] == best[safe]).sum())
+        n = int(n_ids[i])
+        if safe.all():
+            assert np.array_equal(ids[i, :n].cpu().numpy(), collapsed), i
+        text = eng.tok.decode_collapsed_ctc(ids[i, :n].cpu().tolist())
+        stats["lines_text_equal"] += int(text == str(golden[f"{name}/{i}/fast_text"]))
+        assert abs(float(conf[i]) - cf) < 0.05
+    _report(f"encoder_ctc/{name}", stats)
+    assert stats["mem_maxabs"] <= MEM_ATOL, stats
+    assert stats["mem_rel_l2"] <= MEM_RTOL, stats
+    assert stats["logit_maxabs"] <= LOGIT_ATOL, stats
+    assert stats["safe_equal"] == stats["safe_frames"], stats
+
+
+def test_recognize_crops_fast_matches_goldens(engines, golden):
+    eng, sd = engines("hard")
+    crops = golden_crops()
+    res = eng.recognize_crops(crops, "ctc")
+    same = sum(r.text == str(golden[f"hard/{i}/fast_text"]) for i, r in enumerate(res))
+    confd = max(abs(r.confidence - float(golden[f"hard/{i}/ctc_conf"])) for i, r in enumerate(res))
+    _report("fast_text/hard", {"lines": len(crops), "equal": same, "max_conf_diff": confd})
+    assert confd < 0.05
+    assert same >= len(crops) - 2          # near-tie frames may flip under bf16; see parity report
+
+
+def test_bucketed_equals_reference_with_img_w(engines):
+    """width_mode='bucketed': a line in bucket Wb must equal the oracle run with IMG_W = Wb."""
+    from oracle import decode as OD, model as OM, preprocess as OP
+    eng, sd = engines("hard", "bucketed")
+    crops = FX.make_line_crops(24, seed=11)
+    buf, ent = eng.pack_crops(crops)
+    groups = eng.plan(ent)
+    assert len(groups) >= 3
+    worst = 0.0
+    for Wb, (idx, descs, smem) in groups.items():
+        planes, _ = eng.preprocess(buf.cuda(), descs, Wb, smem)
+        enc = eng.encode(planes)
+        torch.cuda.synchronize()
+        lg = enc["logits"].cpu().numpy()[:, :, :204]
+        for j, li in enumerate(idx[:3]):
+            want_plane = OP.resize_keep_ratio_pad(crops[li], 48, Wb)
+            assert np.array_equal(planes[j].cpu().numpy(), want_plane)
+            x = torch.from_numpy(OP.normalise(want_plane))[None, None]
+            ref = OM.ctc_logits(sd, OM.encode(sd, x))[0].numpy()
+            worst = max(worst, float(np.abs(lg[j] - ref).max()))
+    _report("bucketed/logit_maxabs", worst)
+    assert worst <= LOGIT_ATOL
+
+
+def test_page_boxes_and_empty_crop(engines):
+    from tests.golden.cases import page_case
+    eng, _ = engines("hard")
+    page, boxes = page_case()
+    res = eng.recognize_boxes(page, boxes, "ctc")
+    assert len(res) == len(boxes)
+    assert res[-1] is None and all(r is not None for r in res[:-1])

@@ -1,0 +1,92 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every declared symbol
+(no compute is issued), and the host planning logic matches the oracle / Python semantics."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from kiri_ocr_b200 import _lib
+from kiri_ocr_b200.config import CFG
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build_library()
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "kiri_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(kiri_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/kiri_b200.h but not exported"
+    assert declared == set(_lib.EXPORTED_SYMBOLS)
+    assert lib.kiri_version() >= 100
+
+
+def test_struct_sizes_match_header_layout():
+    import ctypes as C
+    assert C.sizeof(_lib.KiriCropDesc) == 32
+    assert C.sizeof(_lib.KiriDims) == 14 * 4
+    assert C.sizeof(_lib.KiriEncLayerWeights) == 12 * 8
+    assert C.sizeof(_lib.KiriDecLayerWeights) == 18 * 8
+
+
+def test_missing_device_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.KiriError):
+        _lib.require_device()
+
+
+def test_target_width_matches_python_round():
+    from kiri_ocr_b200.engine import target_widths
+    rng = np.random.default_rng(0)
+    w = rng.integers(1, 5000, 20000)
+    h = rng.integers(1, 400, 20000)
+    # include exact .5 cases (banker's rounding): w*48/h = k + 0.5
+    w = np.concatenate([w, np.array([1, 3, 5, 7, 9, 11]) * 1]); h = np.concatenate([h, np.full(6, 96)])
+    got = target_widths(w, h, 48)
+    want = np.array([max(1, int(round(int(a) * (48 / float(b))))) for a, b in zip(w, h)])
+    assert np.array_equal(got, want)
+
+
+def test_boxes_to_entries_matches_oracle_crop():
+    from kiri_ocr_b200.engine import BatchedRecognizer
+    from oracle import preprocess as OP
+    from tests.golden.cases import page_case
+    page, boxes = page_case()
+    ent, valid = BatchedRecognizer.boxes_to_entries(page.shape, boxes)
+    flat = page.reshape(-1)
+    for (off, pitch, w, h), ok, box in zip(ent, valid, boxes):
+        roi = OP.crop_region(page, box)
+        if roi is None:
+            assert not ok
+            continue
+        assert ok
+        got = np.stack([flat[off + r * pitch: off + r * pitch + w] for r in range(h)])
+        raw = got if np.array_equal(got, roi) else 255 - got          # oracle applies the inversion
+        assert np.array_equal(raw, roi)
+
+
+def test_plan_groups_buckets_and_smem_mirror():
+    from kiri_ocr_b200.engine import plan_groups, _pre_smem
+    from kiri_ocr_b200 import fixtures as FX
+    crops = FX.make_line_crops(200, seed=3)
+    ent = np.array([(0, c.shape[1], c.shape[1], c.shape[0]) for c in crops], np.int64)
+    g = plan_groups(ent, CFG(), "bucketed")
+    assert set(g) <= {128, 256, 384, 512, 640} and len(g) == 5
+    assert sum(len(v[0]) for v in g.values()) == 200
+    for Wb, (idx, d, smem) in g.items():
+        assert (np.minimum(d["nw"], 640) <= Wb).all()
+        assert smem <= 100 * 1024
+    gp = plan_groups(ent, CFG(), "parity")
+    assert list(gp) == [640]
+    # numpy mirror == C helper
+    lib = _lib.load()
+    for (w, h, nw, strip) in [(853, 64, 640, 640), (2000, 130, 738, 320), (50, 9, 267, 267), (300, 48, 300, 300), (1, 37, 1, 1)]:
+        a = int(_pre_smem(np.array([w]), np.array([h]), np.array([nw]), 48, 640, np.array([strip]))[0])
+        assert a == lib.kiri_preprocess_smem_bytes(w, h, nw, 48, 640, strip)

@@ -45,6 +45,14 @@ int kiri_version(void);
 /* 1 when the current device is compute capability 10.x (the kernels are sm_100a-only). */
 int kiri_device_ok(void);
 
+/* Per-stage CUDA-event timing of kiri_encode / kiri_decode_greedy (used by bench.py for the roofline
+ * numbers).  kiri_profile_begin() starts recording and returns the number of stages;
+ * kiri_profile_end() synchronises the device and returns, per stage, the summed milliseconds and
+ * the number of timed intervals.  Stage order: conv1, conv2, conv3, conv4, pool_ln, qkv, attention,
+ * out_proj, ff1, ff2, ln_final, ctc_head, dec_crosskv, dec_step. */
+int kiri_profile_begin(void);
+int kiri_profile_end(double* ms_by_stage_host, int* count_by_stage_host, int n);
+
 /* ---------------------------------------------------------------- K1: preprocessing
  * Replaces OCR._preprocess_region (kiri_ocr/core.py:489-528) + ResizeKeepRatioPadNoCrop /
  * preprocess_pil (kiri_ocr/model.py:316-339), i.e. numpy slicing + Pillow BILINEAR + pad,

@@ -65,6 +65,8 @@ _SIGS = {
     "kiri_last_error": (C.c_char_p, []),
     "kiri_version": (C.c_int, []),
     "kiri_device_ok": (C.c_int, []),
+    "kiri_profile_begin": (C.c_int, []),
+    "kiri_profile_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]),
     "kiri_preprocess_smem_bytes": (C.c_int, [C.c_int] * 6),
     "kiri_preprocess_pack": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
     "kiri_conv1": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]),
@@ -134,6 +136,10 @@ def require_device() -> None:
         raise KiriError("kiri_ocr_b200 needs a CUDA device (B200, sm_100a); none is visible and there is no CPU path")
     if not load().kiri_device_ok():
         raise KiriError("kiri_ocr_b200 kernels are built for sm_100a only; the current device is not compute capability 10.x")
+
+
+PROFILE_STAGES = ("conv1", "conv2", "conv3", "conv4", "pool_ln", "qkv", "attention", "out_proj", "ff1", "ff2",
+                  "ln_final", "ctc_head", "dec_crosskv", "dec_step")
 
 
 def ptr(t) -> int:

@@ -4,10 +4,9 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <vector>
 
-#include "common.cuh"
-#include "gemm_tc.cuh"
-#include "kiri_b200.h"
+#include "internal.cuh"
 
 namespace kiri {
 
@@ -17,6 +16,28 @@ void set_last_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+// ---- per-stage event profiler
+struct ProfRec { int stage; cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_ev_pool;
+static cudaEvent_t g_open[PS_COUNT];
+static cudaEvent_t ev_get() {
+  if (!g_ev_pool.empty()) { cudaEvent_t e = g_ev_pool.back(); g_ev_pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+void prof_begin(int stage, cudaStream_t s) {
+  if (!g_prof_on) return;
+  g_open[stage] = ev_get();
+  cudaEventRecord(g_open[stage], s);
+}
+void prof_end(int stage, cudaStream_t s) {
+  if (!g_prof_on) return;
+  cudaEvent_t e = ev_get();
+  cudaEventRecord(e, s);
+  g_prof.push_back({stage, g_open[stage], e});
 }
 
 // CUDA-core cross-check GEMM: one thread per output element, fp32 accumulate.
@@ -44,6 +65,28 @@ extern "C" int kiri_device_ok(void) {
   return major == 10;
 }
 
+extern "C" int kiri_profile_begin(void) {
+  for (auto& r : g_prof) { g_ev_pool.push_back(r.a); g_ev_pool.push_back(r.b); }
+  g_prof.clear();
+  g_prof_on = true;
+  return PS_COUNT;
+}
+extern "C" int kiri_profile_end(double* ms_by_stage, int* count_by_stage, int n) {
+  g_prof_on = false;
+  KIRI_REQUIRE(ms_by_stage && count_by_stage && n >= PS_COUNT, "kiri_profile_end: need arrays of %d entries", (int)PS_COUNT);
+  for (int i = 0; i < n; ++i) { ms_by_stage[i] = 0.0; count_by_stage[i] = 0; }
+  KIRI_CHECK_CUDA(cudaDeviceSynchronize());
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    KIRI_CHECK_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+    ms_by_stage[r.stage] += ms;
+    count_by_stage[r.stage] += 1;
+    g_ev_pool.push_back(r.a); g_ev_pool.push_back(r.b);
+  }
+  g_prof.clear();
+  return 0;
+}
+
 extern "C" int kiri_gemm_ref(const void* a, const void* w, int M, int N, int K, float* out_f32,
                              cudaStream_t stream) {
   KIRI_REQUIRE(a && w && out_f32, "kiri_gemm_ref: null pointer");
@@ -55,7 +98,7 @@ extern "C" int kiri_gemm_ref(const void* a, const void* w, int M, int N, int K, 
   return 0;
 }
 
-static int gemm_call(const void* a, const void* w, const float* bias, int M, int N, int K, int epi, void* out,
+int kiri::gemm_call(const void* a, const void* w, const float* bias, int M, int N, int K, int epi, void* out,
                      const float* resid, const float* ln_g, const float* ln_b, void* out2,
                      cudaStream_t stream) {
   if (M == 0) return 0;
@@ -104,13 +147,6 @@ extern "C" int kiri_conv3x3_bf16(const void* in_nhwc, const void* w, const float
 // ------------------------------------------------------------------------------------------------
 // model handle
 // ------------------------------------------------------------------------------------------------
-struct KiriHandle {
-  KiriDims d;
-  KiriWeights w;
-  float conv1_w[48 * 9];
-  float conv1_b[48];
-};
-
 extern "C" int kiri_create(const KiriDims* dims, const KiriWeights* weights, KiriHandle** out) {
   KIRI_REQUIRE(dims && weights && out, "kiri_create: null pointer");
   KIRI_REQUIRE(kiri_device_ok(), "kiri_create: the current CUDA device is not compute capability 10.x (B200)");
@@ -132,9 +168,6 @@ extern "C" int kiri_create(const KiriDims* dims, const KiriWeights* weights, Kir
   return 0;
 }
 extern "C" void kiri_destroy(KiriHandle* h) { delete h; }
-
-const KiriDims* kiri_handle_dims(const KiriHandle* h) { return &h->d; }
-const KiriWeights* kiri_handle_weights(const KiriHandle* h) { return &h->w; }
 
 namespace {
 struct EncodeWs {          // byte offsets into the caller's workspace
@@ -168,12 +201,6 @@ extern "C" size_t kiri_encode_workspace_bytes(const KiriHandle* h, int B, int Wb
   return plan_encode(h->d, B, Wb, stem_chunk).total;
 }
 
-#define KIRI_TRY(expr)            \
-  do {                            \
-    int _rc = (expr);             \
-    if (_rc != 0) return _rc;     \
-  } while (0)
-
 extern "C" int kiri_encode(KiriHandle* h, const uint8_t* planes_u8, int B, int Wb, int stem_chunk,
                            void* workspace, size_t workspace_bytes, float* mem_f32, void* mem_bf16,
                            float* logits, float* tok_f32, const int* kv_len, cudaStream_t stream) {
@@ -192,27 +219,37 @@ extern "C" int kiri_encode(KiriHandle* h, const uint8_t* planes_u8, int B, int W
   // ---- stem, in sub-batches whose activations stay L2-resident
   for (int b0 = 0; b0 < B; b0 += sc) {
     const int nb = (B - b0) < sc ? (B - b0) : sc;
-    KIRI_TRY(kiri_conv1(planes_u8 + static_cast<size_t>(b0) * H * Wb, w.conv1_w_host, w.conv1_b_host, nb, H, Wb,
-                        base + ws.act1, stream));
-    KIRI_TRY(conv_call(base + ws.act1, w.conv2_w, w.conv2_b, nb, H, Wb, 64, 96, 2, 2, base + ws.act2, stream));
-    KIRI_TRY(conv_call(base + ws.act2, w.conv3_w, w.conv3_b, nb, H / 2, Wb / 2, 96, 160, 2, 2, base + ws.act3, stream));
-    KIRI_TRY(conv_call(base + ws.act3, w.conv4_w, w.conv4_b, nb, H / 4, Wb / 4, 160, 256, 2, 1,
-                       base + ws.act4 + static_cast<size_t>(b0) * (H / 8) * T * 256 * 2, stream));
+    { ProfScope ps(PS_CONV1, stream);
+      KIRI_TRY(kiri_conv1(planes_u8 + static_cast<size_t>(b0) * H * Wb, w.conv1_w_host, w.conv1_b_host, nb, H, Wb,
+                          base + ws.act1, stream)); }
+    { ProfScope ps(PS_CONV2, stream);
+      KIRI_TRY(conv_call(base + ws.act1, w.conv2_w, w.conv2_b, nb, H, Wb, 64, 96, 2, 2, base + ws.act2, stream)); }
+    { ProfScope ps(PS_CONV3, stream);
+      KIRI_TRY(conv_call(base + ws.act2, w.conv3_w, w.conv3_b, nb, H / 2, Wb / 2, 96, 160, 2, 2, base + ws.act3, stream)); }
+    { ProfScope ps(PS_CONV4, stream);
+      KIRI_TRY(conv_call(base + ws.act3, w.conv4_w, w.conv4_b, nb, H / 4, Wb / 4, 160, 256, 2, 1,
+                         base + ws.act4 + static_cast<size_t>(b0) * (H / 8) * T * 256 * 2, stream)); }
   }
   float* x = reinterpret_cast<float*>(base + ws.x);
   void* a = base + ws.a;
   // ---- pool + positional table + enc_ln_in (+ norm1 of layer 0)
-  KIRI_TRY(kiri_pool_pos_ln(base + ws.act4, w.pos_table, B, H / 8, T, D, w.enc_ln_in_g, w.enc_ln_in_b,
-                            w.enc[0].ln1_g, w.enc[0].ln1_b, x, a, stream));
+  { ProfScope ps(PS_POOL_LN, stream);
+    KIRI_TRY(kiri_pool_pos_ln(base + ws.act4, w.pos_table, B, H / 8, T, D, w.enc_ln_in_g, w.enc_ln_in_b,
+                              w.enc[0].ln1_g, w.enc[0].ln1_b, x, a, stream)); }
   if (tok_f32) KIRI_CHECK_CUDA(cudaMemcpyAsync(tok_f32, x, static_cast<size_t>(M) * D * 4, cudaMemcpyDeviceToDevice, stream));
   // ---- encoder layers
   for (int l = 0; l < d.enc_layers; ++l) {
     const KiriEncLayerWeights& lw = w.enc[l];
-    KIRI_TRY(gemm_call(a, lw.wqkv, lw.bqkv, M, 3 * D, D, EPI_BIAS_BF16, base + ws.qkv, nullptr, nullptr, nullptr, nullptr, stream));
-    KIRI_TRY(kiri_encoder_attention(base + ws.qkv, base + ws.o, B, T, d.enc_heads, D, kv_len, stream));
+    { ProfScope ps(PS_QKV, stream);
+      KIRI_TRY(gemm_call(a, lw.wqkv, lw.bqkv, M, 3 * D, D, EPI_BIAS_BF16, base + ws.qkv, nullptr, nullptr, nullptr, nullptr, stream)); }
+    { ProfScope ps(PS_ATTN, stream);
+      KIRI_TRY(kiri_encoder_attention(base + ws.qkv, base + ws.o, B, T, d.enc_heads, D, kv_len, stream)); }
     // x += out_proj(o); a = norm2(x)
-    KIRI_TRY(gemm_call(base + ws.o, lw.wo, lw.bo, M, D, D, EPI_BIAS_RESID_LN, x, x, lw.ln2_g, lw.ln2_b, a, stream));
-    KIRI_TRY(gemm_call(a, lw.w1, lw.b1, M, d.enc_ff, D, EPI_BIAS_GELU_BF16, base + ws.hbuf, nullptr, nullptr, nullptr, nullptr, stream));
+    { ProfScope ps(PS_OUTPROJ, stream);
+      KIRI_TRY(gemm_call(base + ws.o, lw.wo, lw.bo, M, D, D, EPI_BIAS_RESID_LN, x, x, lw.ln2_g, lw.ln2_b, a, stream)); }
+    { ProfScope ps(PS_FF1, stream);
+      KIRI_TRY(gemm_call(a, lw.w1, lw.b1, M, d.enc_ff, D, EPI_BIAS_GELU_BF16, base + ws.hbuf, nullptr, nullptr, nullptr, nullptr, stream)); }
+    ProfScope ps_ff2(PS_FF2, stream);
     // x += linear2(h); a = next layer's norm1(x)  (last layer: enc_ln, handled below)
     if (l + 1 < d.enc_layers) {
       KIRI_TRY(gemm_call(base + ws.hbuf, lw.w2, lw.b2, M, D, d.enc_ff, EPI_BIAS_RESID_LN, x, x, w.enc[l + 1].ln1_g,
@@ -223,7 +260,9 @@ extern "C" int kiri_encode(KiriHandle* h, const uint8_t* planes_u8, int B, int W
   }
   // ---- mem = enc_ln(x); head input = ctc_head.0(mem)
   void* mem_b = mem_bf16 ? mem_bf16 : base + ws.o;     // o is free now
-  KIRI_TRY(kiri_layernorm(x, M, D, w.enc_ln_g, w.enc_ln_b, mem_f32, mem_b, w.ctc_ln_g, w.ctc_ln_b, a, stream));
+  { ProfScope ps(PS_LN_FINAL, stream);
+    KIRI_TRY(kiri_layernorm(x, M, D, w.enc_ln_g, w.enc_ln_b, mem_f32, mem_b, w.ctc_ln_g, w.ctc_ln_b, a, stream)); }
+  ProfScope ps_head(PS_CTC_HEAD, stream);
   if (logits)
     KIRI_TRY(gemm_call(a, w.ctc_w, w.ctc_b, M, (d.ctc_classes + 15) / 16 * 16, D, EPI_BIAS_F32, logits, nullptr, nullptr, nullptr,
                        nullptr, stream));

@@ -1,0 +1,40 @@
+// Internal (non-ABI) declarations shared by api.cu and decoder.cu.
+#pragma once
+#include "common.cuh"
+#include "gemm_tc.cuh"
+#include "kiri_b200.h"
+
+struct KiriHandle {
+  KiriDims d;
+  KiriWeights w;
+  float conv1_w[48 * 9];
+  float conv1_b[48];
+};
+
+namespace kiri {
+// out[M,N] = epilogue(a[M,K] @ w[N,K]^T + bias) on the tcgen05 kernel (api.cu)
+int gemm_call(const void* a, const void* w, const float* bias, int M, int N, int K, int epi, void* out,
+              const float* resid, const float* ln_g, const float* ln_b, void* out2, cudaStream_t stream);
+}  // namespace kiri
+
+namespace kiri {
+// Optional per-stage CUDA-event timing (bench.py's roofline numbers): events are recorded on the
+// launching stream around each stage while profiling is on.
+enum ProfStage : int {
+  PS_CONV1 = 0, PS_CONV2, PS_CONV3, PS_CONV4, PS_POOL_LN, PS_QKV, PS_ATTN, PS_OUTPROJ, PS_FF1, PS_FF2,
+  PS_LN_FINAL, PS_CTC_HEAD, PS_DEC_CROSSKV, PS_DEC_STEP, PS_COUNT
+};
+void prof_begin(int stage, cudaStream_t s);
+void prof_end(int stage, cudaStream_t s);
+struct ProfScope {
+  int st; cudaStream_t s;
+  ProfScope(int stage, cudaStream_t stream) : st(stage), s(stream) { prof_begin(st, s); }
+  ~ProfScope() { prof_end(st, s); }
+};
+}  // namespace kiri
+
+#define KIRI_TRY(expr)            \
+  do {                            \
+    int _rc = (expr);             \
+    if (_rc != 0) return _rc;     \
+  } while (0)

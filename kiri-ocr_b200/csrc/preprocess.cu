@@ -19,7 +19,6 @@ namespace kiri {
 static constexpr int kPrecisionBits = 22;
 static constexpr int kPreThreads = 256;
 static constexpr int kRowBlock = 8;       // source rows staged per step
-static constexpr int kMaxTaps = 64;       // supports down-scaling up to ~31x
 
 struct Coef {           // double-precision replica of Pillow's precompute_coeffs for one index
   int xmin, n;
@@ -253,9 +252,14 @@ extern "C" int kiri_preprocess_pack(const uint8_t* src, const KiriCropDesc* desc
   if (!max_optin) {
     int dev = 0;
     KIRI_CHECK_CUDA(cudaGetDevice(&dev));
-    KIRI_CHECK_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    int optin = 0;
+    KIRI_CHECK_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    cudaFuncAttributes fa;
+    KIRI_CHECK_CUDA(cudaFuncGetAttributes(&fa, preprocess_pack_kernel));
+    optin -= static_cast<int>(fa.sharedSizeBytes);           // static + dynamic must fit the opt-in limit
     KIRI_CHECK_CUDA(cudaFuncSetAttribute(preprocess_pack_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+    max_optin = optin;
   }
   KIRI_REQUIRE(smem_bytes <= max_optin, "kiri_preprocess_pack: %d bytes of shared memory requested, %d available",
                smem_bytes, max_optin);

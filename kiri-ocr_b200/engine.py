@@ -253,6 +253,54 @@ class BatchedRecognizer:
         self.launches += 3 + steps.value * (3 + 8 * self.pw.dec_layers)
         return ids, n_out, sum_lp, slp, spr, steps.value
 
+    # ------------------------------------------------------------------ device-resident stepping (bench)
+    def prepare_resident(self, src: torch.Tensor, entries: np.ndarray):
+        """Upload the source buffer and the crop descriptors once; returns an opaque plan that
+        ``step_resident`` replays with no host<->device traffic."""
+        src_dev = src if src.is_cuda else src.to(self.device)
+        plan = []
+        for Wb, (idx, descs, smem) in self.plan(entries).items():
+            dd = torch.from_numpy(descs.view(np.uint8).reshape(-1).copy()).to(self.device)
+            planes = torch.empty((len(idx), self.cfg.IMG_H, Wb), dtype=torch.uint8, device=self.device)
+            kv_len = None
+            if self.width_mode == "masked":
+                kv_len = torch.from_numpy(np.minimum((descs["nw"] + 3) // 4, Wb // 4).astype(np.int32)).to(self.device)
+            plan.append({"Wb": Wb, "idx": idx, "descs": dd, "n": len(idx), "smem": smem, "planes": planes,
+                         "kv_len": kv_len})
+        torch.cuda.synchronize()
+        return {"src": src_dev, "groups": plan}
+
+    def step_resident(self, prep, method: str = "ctc"):
+        """One pass of the hot path over the prepared batch, inputs already in HBM.  Returns the
+        per-group device outputs (no synchronisation)."""
+        outs = []
+        for g in prep["groups"]:
+            _lib.check(self.lib.kiri_preprocess_pack(prep["src"].data_ptr(), g["descs"].data_ptr(), g["n"],
+                                                     self.cfg.IMG_H, g["Wb"], g["smem"], g["planes"].data_ptr(), 0,
+                                                     _lib.stream_ptr()), "kiri_preprocess_pack")
+            self.launches += 1
+            enc = self.encode(g["planes"], kv_len=g["kv_len"])
+            ids, n_ids, conf, _, _ = self.ctc_greedy(enc["logits"])
+            if method == "decoder":
+                T = g["Wb"] // 4
+                Lmax = self.max_steps_bound(int(n_ids.max().item()), T)
+                d_ids, n_out, sum_lp, _, _, _ = self.decode_greedy(enc["mem_bf16"], n_ids, g["n"], T, Lmax)
+                outs.append((d_ids, n_out, sum_lp, conf))
+            else:
+                outs.append((ids, n_ids, conf))
+        return outs
+
+    def profile(self, fn):
+        """Run ``fn()`` with per-stage CUDA-event timing on; returns {stage: (ms, intervals)}."""
+        n = self.lib.kiri_profile_begin()
+        try:
+            fn()
+        finally:
+            ms = (C.c_double * n)()
+            cnt = (C.c_int * n)()
+            _lib.check(self.lib.kiri_profile_end(ms, cnt, n), "kiri_profile_end")
+        return {name: (ms[i], cnt[i]) for i, name in enumerate(_lib.PROFILE_STAGES[:n])}
+
     # ------------------------------------------------------------------ public API
     @torch.no_grad()
     def recognize_packed(self, src: torch.Tensor, entries: np.ndarray, method: str = "ctc",

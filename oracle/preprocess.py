@@ -119,3 +119,8 @@ def preprocess_region(page: np.ndarray, box, img_h: int = 48, img_w: int = 640,
     if roi is None:
         return None
     return resize_keep_ratio_pad(roi, img_h, img_w)
+
+
+def preprocess_crop(crop: np.ndarray, img_h: int = 48, img_w: int = 640) -> np.ndarray:
+    """A stand-alone crop (already cut out of its page): invert-if-dark, resize, crop/pad."""
+    return resize_keep_ratio_pad(crop_region(crop, (0, 0, crop.shape[1], crop.shape[0]), 0), img_h, img_w)

@@ -25,9 +25,15 @@ REPORT = {}
 
 
 def _report(key, value):
+    path = os.path.join(ROOT, "gpurun_out", "parity_report.json")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    if not REPORT and os.path.exists(path):
+        try:
+            REPORT.update(json.load(open(path)))
+        except Exception:
+            pass
     REPORT[key] = value
-    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", "parity_report.json"), "w") as f:
+    with open(path, "w") as f:
         json.dump(REPORT, f, indent=1, sort_keys=True)
 
 
@@ -72,7 +78,7 @@ def test_encoder_and_ctc_parity(engines, golden, name):
     stats = {"tok_maxabs": 0.0, "mem_maxabs": 0.0, "mem_rel_l2": 0.0, "logit_maxabs": 0.0, "frames": 0,
              "frames_equal": 0, "safe_frames": 0, "safe_equal": 0, "lines_text_equal": 0, "lines": len(crops)}
     for i, c in enumerate(crops):
-        want_plane = OP.resize_keep_ratio_pad(c)
+        want_plane = OP.preprocess_crop(c)
         assert np.array_equal(planes_h[i], want_plane), i
         tk, mem, lg = oracle_line(sd, want_plane)
         stats["tok_maxabs"] = max(stats["tok_maxabs"], float(np.abs(tok_h[i] - tk).max()))
@@ -127,7 +133,7 @@ def test_bucketed_equals_reference_with_img_w(engines):
         torch.cuda.synchronize()
         lg = enc["logits"].cpu().numpy()[:, :, :204]
         for j, li in enumerate(idx[:3]):
-            want_plane = OP.resize_keep_ratio_pad(crops[li], 48, Wb)
+            want_plane = OP.preprocess_crop(crops[li], 48, Wb)
             assert np.array_equal(planes[j].cpu().numpy(), want_plane)
             x = torch.from_numpy(OP.normalise(want_plane))[None, None]
             ref = OM.ctc_logits(sd, OM.encode(sd, x))[0].numpy()

@@ -71,11 +71,18 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -83,13 +90,16 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
+        lo, hi = (self.t0 or 0.0) - 0.03, (self.t1 or 1e18) + 0.03
+        rows = [r for t, r in self.rows if lo <= t <= hi] or [r for t, r in self.rows[-3:]]
+        self.rows = rows
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -182,6 +192,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                                     # nvidia-smi needs a while to come up
     cfg, tok, sd = make_model()
     eng = BatchedRecognizer(sd, cfg, tok, device="cuda", width_mode=args.width_mode, stem_chunk=args.stem_chunk)
     method = "ctc" if args.method == "fast" else "decoder"
@@ -218,18 +231,17 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         gather(eng.step_resident(prep, method))
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = eng.launches
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    sampler.mark_begin()
     for a, b in ev:
         flush.zero_()                                       # evict L2 between timed iterations (untimed)
         a.record()
         gather(eng.step_resident(prep, method))
         b.record()
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     launches = (eng.launches - launches0) // max(1, args.steps)
     ms = sum(a.elapsed_time(b) for a, b in ev)
@@ -319,7 +331,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--method", default="fast", choices=["fast", "accurate"])

@@ -1,0 +1,99 @@
+"""Multi-GPU sharding of line crops.
+
+Every line is independent (eval-mode BN, no cross-line state), so the path shards with no
+data-path collective: each rank recognises a contiguous, width-balanced range of the global line
+index with replicated weights.  The single exchange step is an all-gather of fixed-stride int32
+records ``{line_idx, n_ids, confidence bits, ids[Lmax]}`` over ``torch.distributed`` (NCCL on the
+B200 box, gloo in the CPU tests); ids are mapped to strings after the gather and the global order
+is restored from ``line_idx``.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+
+def shard_bounds(weights: Sequence[float], world: int) -> List[Tuple[int, int]]:
+    """Contiguous ranges [lo, hi) of the line index with near-equal total weight per rank
+    (weight = resized line width, i.e. work)."""
+    w = np.asarray(weights, dtype=np.float64)
+    n = len(w)
+    if n == 0:
+        return [(0, 0)] * world
+    cum = np.concatenate([[0.0], np.cumsum(w)])
+    cuts = [0]
+    for r in range(1, world):
+        target = cum[-1] * r / world
+        k = int(np.searchsorted(cum, target, side="left"))
+        cuts.append(min(max(k, cuts[-1]), n))
+    cuts.append(n)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def pack_records(line_idx: np.ndarray, ids: List[np.ndarray], conf: Sequence[float], lmax: int) -> torch.Tensor:
+    rec = np.zeros((len(line_idx), 3 + lmax), np.int32)
+    rec[:, 0] = line_idx
+    for i, row in enumerate(ids):
+        k = min(len(row), lmax)
+        rec[i, 1] = k
+        rec[i, 3:3 + k] = row[:k]
+    rec[:, 2] = np.asarray(conf, np.float32).view(np.int32)
+    return torch.from_numpy(rec)
+
+
+def all_gather_records(rec: torch.Tensor, group=None) -> torch.Tensor:
+    """All ranks' records, padded per rank to the largest shard (padding rows carry line_idx -1)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    n_local = torch.tensor([rec.shape[0]], dtype=torch.int64, device=rec.device)
+    counts = [torch.zeros_like(n_local) for _ in range(world)]
+    dist.all_gather(counts, n_local, group=group)
+    n_max = int(max(int(c.item()) for c in counts))
+    padded = torch.full((n_max, rec.shape[1]), -1, dtype=torch.int32, device=rec.device)
+    padded[: rec.shape[0]] = rec
+    out = torch.empty((world * n_max, rec.shape[1]), dtype=torch.int32, device=rec.device)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    return out[out[:, 0] >= 0]
+
+
+def unpack_records(rec: torch.Tensor, n_total: int):
+    """-> (ids per line, confidence per line) in global line order; missing lines give None."""
+    r = rec.cpu().numpy()
+    ids: List[Optional[np.ndarray]] = [None] * n_total
+    conf: List[Optional[float]] = [None] * n_total
+    for row in r:
+        li, k = int(row[0]), int(row[1])
+        ids[li] = row[3:3 + k].copy()
+        conf[li] = float(row[2:3].view(np.float32)[0])
+    return ids, conf
+
+
+def recognize_sharded(engine, src: torch.Tensor, entries: np.ndarray, method: str = "ctc", group=None):
+    """Recognise ``entries`` across all ranks of the process group; every rank returns the full,
+    ordered list of ``(text, confidence)``.  ``engine.recognize_packed`` does the local work."""
+    import torch.distributed as dist
+    from .engine import target_widths
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    nw = np.minimum(target_widths(entries[:, 2], entries[:, 3], engine.cfg.IMG_H), engine.cfg.IMG_W)
+    lo, hi = shard_bounds(nw, world)[rank]
+    local = engine.recognize_packed(src, entries[lo:hi], method)
+    lmax = engine.cfg.IMG_W // 4 if method == "ctc" else engine.cfg.MAX_DEC_LEN
+    rec = pack_records(np.arange(lo, hi), [r.ids for r in local], [r.confidence for r in local], lmax)
+    dev = getattr(engine, "device", torch.device("cpu"))
+    allrec = all_gather_records(rec.to(dev) if dist.get_backend(group) == "nccl" else rec, group)
+    ids, conf = unpack_records(allrec, len(entries))
+    tok = engine.tok
+    out = []
+    for row, c in zip(ids, conf):
+        if row is None:
+            out.append(None)
+        elif method == "ctc":
+            out.append((tok.decode_collapsed_ctc(row.tolist()), c))
+        else:
+            cut = row.tolist()
+            if tok.dec_eos in cut:
+                cut = cut[: cut.index(tok.dec_eos)]
+            out.append((tok.decode_dec(cut), c))
+    return out

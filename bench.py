@@ -228,6 +228,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident throughput (value) ----------------
+    torch.cuda.set_stream(eng.stream)                      # the engine's own (capturable) stream
     for _ in range(max(args.warmup, 3)):
         gather(eng.step_resident(prep, method))
     barrier()

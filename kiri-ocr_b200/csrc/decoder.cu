@@ -13,6 +13,8 @@
 //     UNK/EOS adjustments, arg-max and the stop rule run in one warp per line on the device.
 // All B lines advance in lock-step; finished lines are frozen.  M = B is small, so the step is
 // latency-bound (weights stay L2-resident); see DESIGN.md.
+#include <cstdlib>
+
 #include "internal.cuh"
 #include "ln_utils.cuh"
 
@@ -77,13 +79,14 @@ __global__ void dec_init_kernel(const int* __restrict__ len_est, int B, int T, i
 
 // ------------------------------------------------------------------ embedding + position + LN
 __global__ void __launch_bounds__(256)
-dec_embed_ln_kernel(const int* __restrict__ seq, const int* __restrict__ finished, int B, int Lmax, int step,
-                    const float* __restrict__ emb,
+dec_embed_ln_kernel(const int* __restrict__ seq, const int* __restrict__ finished, int B, int Lmax,
+                    const int* __restrict__ step_dev, const float* __restrict__ emb,
                     const float* __restrict__ pe, int has_pos, const float* g, const float* bta,
                     float* __restrict__ x, __nv_bfloat16* __restrict__ a) {
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (b >= B) return;
+  const int step = *step_dev;
   // finished lines are frozen: their seq row is not extended, so feed the pad token
   const int tokid = finished[b] ? 0 : seq[static_cast<size_t>(b) * (Lmax + 1) + step];
   const float4* e = reinterpret_cast<const float4*>(emb + static_cast<size_t>(tokid) * kD) + lane * 2;
@@ -107,14 +110,16 @@ template <bool APPEND, int MAXCH>
 __global__ void __launch_bounds__(128)
 dec_attention_kernel(const __nv_bfloat16* __restrict__ q, int q_ld, const __nv_bfloat16* __restrict__ knew,
                      const __nv_bfloat16* __restrict__ vnew, __nv_bfloat16* __restrict__ kbase,
-                     __nv_bfloat16* __restrict__ vbase, int kv_rows, int kv_ld, int n_keys, const int* kv_len,
-                     int B, int heads, __nv_bfloat16* __restrict__ out) {
+                     __nv_bfloat16* __restrict__ vbase, int kv_rows, int kv_ld, int n_keys_static,
+                     const int* __restrict__ step_dev, const int* kv_len, int B, int heads,
+                     __nv_bfloat16* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int wid = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (wid >= B * heads) return;
   const int b = wid / heads, head = wid - b * heads;
   __nv_bfloat16* kb = kbase + static_cast<size_t>(b) * kv_rows * kv_ld + head * kHdDec;
   __nv_bfloat16* vb = vbase + static_cast<size_t>(b) * kv_rows * kv_ld + head * kHdDec;
+  const int n_keys = APPEND ? (*step_dev + 1) : n_keys_static;   // self-attention: keys 0..step
   int len = n_keys;
   if (kv_len) len = min(len, kv_len[b]);
   if (APPEND) {
@@ -191,7 +196,8 @@ __device__ __forceinline__ float warp_lse(const float* __restrict__ x, int n, in
 }
 
 __global__ void __launch_bounds__(128)
-dec_select_kernel(const float* __restrict__ logits, int B, int Vd, int Vp, int Lmax, int step, KiriDecodeParams p,
+dec_select_kernel(const float* __restrict__ logits, int B, int Vd, int Vp, int Lmax,
+                  const int* __restrict__ step_dev, KiriDecodeParams p,
                   int* seq, int* n_tok, int* finished, const int* __restrict__ max_steps,
                   const int* __restrict__ target, int* alive, const int* __restrict__ forced, int* ids_out,
                   int* n_out, float* sum_logp, float* step_logp, float* step_prob) {
@@ -199,6 +205,7 @@ dec_select_kernel(const float* __restrict__ logits, int B, int Vd, int Vp, int L
   const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (b >= B) return;
   if (finished[b]) return;
+  const int step = *step_dev;
   const float* dec = logits + static_cast<size_t>(b) * 2 * Vp;
   const float* lm = dec + Vp;
   const float lse_d = warp_lse(dec, Vd, lane);
@@ -269,20 +276,33 @@ dec_select_kernel(const float* __restrict__ logits, int B, int Vd, int Vp, int L
   }
 }
 
+__global__ void dec_advance_kernel(int* step_dev) { *step_dev += 1; }
+
+// MAXCH buckets of the self-attention kernel (keys = 32 * MAXCH)
+static const int kAttBuckets[6] = {1, 2, 3, 5, 8, 17};
+static int att_bucket(int n_keys) {
+  const int ch = (n_keys + 31) / 32;
+  for (int i = 0; i < 6; ++i)
+    if (ch <= kAttBuckets[i]) return i;
+  return -1;
+}
+
 template <bool APPEND>
 static int launch_attention(const __nv_bfloat16* q, int q_ld, const __nv_bfloat16* knew, const __nv_bfloat16* vnew,
-                            __nv_bfloat16* kb, __nv_bfloat16* vb, int kv_rows, int kv_ld, int n_keys,
-                            const int* kv_len, int B, int heads, __nv_bfloat16* out, cudaStream_t stream) {
+                            __nv_bfloat16* kb, __nv_bfloat16* vb, int kv_rows, int kv_ld, int n_keys, int bucket,
+                            const int* step_dev, const int* kv_len, int B, int heads, __nv_bfloat16* out,
+                            cudaStream_t stream) {
   const int grid = (B * heads + 3) / 4;
-  const int ch = (n_keys + 31) / 32;
-#define KIRI_ATT(N) dec_attention_kernel<APPEND, N><<<grid, 128, 0, stream>>>(q, q_ld, knew, vnew, kb, vb, kv_rows, kv_ld, n_keys, kv_len, B, heads, out)
-  if (ch <= 1) KIRI_ATT(1);
-  else if (ch <= 2) KIRI_ATT(2);
-  else if (ch <= 3) KIRI_ATT(3);
-  else if (ch <= 5) KIRI_ATT(5);
-  else if (ch <= 8) KIRI_ATT(8);
-  else if (ch <= 17) KIRI_ATT(17);
-  else KIRI_REQUIRE(false, "decoder attention over %d keys unsupported (max 544)", n_keys);
+#define KIRI_ATT(N) dec_attention_kernel<APPEND, N><<<grid, 128, 0, stream>>>(q, q_ld, knew, vnew, kb, vb, kv_rows, kv_ld, n_keys, step_dev, kv_len, B, heads, out)
+  switch (bucket) {
+    case 0: KIRI_ATT(1); break;
+    case 1: KIRI_ATT(2); break;
+    case 2: KIRI_ATT(3); break;
+    case 3: KIRI_ATT(5); break;
+    case 4: KIRI_ATT(8); break;
+    case 5: KIRI_ATT(17); break;
+    default: KIRI_REQUIRE(false, "decoder attention over %d keys unsupported (max 544)", n_keys);
+  }
 #undef KIRI_ATT
   KIRI_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -336,26 +356,30 @@ extern "C" int kiri_decode_greedy(KiriHandle* h, const void* mem_bf16, const int
                                                        alive, n_out, sum_logp);
   KIRI_CHECK_CUDA(cudaGetLastError());
 
-  static int* alive_host = nullptr;
-  if (!alive_host) KIRI_CHECK_CUDA(cudaMallocHost(&alive_host, sizeof(int)));
-  if (poll_every <= 0) poll_every = 8;
-  int step = 0;
-  for (; step < Lmax; ++step) {
-    ProfScope ps_step(PS_DEC_STEP, stream);
-    dec_embed_ln_kernel<<<(B + 7) / 8, 256, 0, stream>>>(seq, finished, B, Lmax, step, w.dec_emb, w.dec_pe, d.has_dec_pos,
-                                                         w.dec[0].ln1_g, w.dec[0].ln1_b, x, a);
+  int* step_dev = alive + 1;                     // lives next to the alive counter
+  KIRI_CHECK_CUDA(cudaMemsetAsync(step_dev, 0, sizeof(int), stream));
+
+  // one decode step = 3 + 11 * layers launches reading `step` from device memory, so a step can be
+  // captured once per self-attention bucket and replayed as a CUDA graph (the step is launch-bound)
+  const int cross_bucket = att_bucket(T);
+  KIRI_REQUIRE(cross_bucket >= 0, "kiri_decode_greedy: memory length %d unsupported", T);
+  auto enqueue_step = [&](int self_bucket) -> int {
+    dec_embed_ln_kernel<<<(B + 7) / 8, 256, 0, stream>>>(seq, finished, B, Lmax, step_dev, w.dec_emb, w.dec_pe,
+                                                         d.has_dec_pos, w.dec[0].ln1_g, w.dec[0].ln1_b, x, a);
     KIRI_CHECK_CUDA(cudaGetLastError());
     for (int l = 0; l < L; ++l) {
       const KiriDecLayerWeights& lw = w.dec[l];
       KIRI_TRY(gemm_call(a, lw.wqkv, lw.bqkv, B, 3 * D, D, EPI_BIAS_BF16, qkv, nullptr, nullptr, nullptr, nullptr, stream));
       __nv_bfloat16* kc = self_k + static_cast<size_t>(l) * B * Lmax * D;
       __nv_bfloat16* vc = self_v + static_cast<size_t>(l) * B * Lmax * D;
-      KIRI_TRY(launch_attention<true>(qkv, 3 * D, qkv + D, qkv + 2 * D, kc, vc, Lmax, D, step + 1, nullptr, B, heads, o, stream));
+      KIRI_TRY(launch_attention<true>(qkv, 3 * D, qkv + D, qkv + 2 * D, kc, vc, Lmax, D, 0, self_bucket, step_dev,
+                                      nullptr, B, heads, o, stream));
       KIRI_TRY(gemm_call(o, lw.wo, lw.bo, B, D, D, EPI_BIAS_RESID_LN, x, x, lw.ln2_g, lw.ln2_b, a, stream));
       KIRI_TRY(gemm_call(a, lw.wcq, lw.bcq, B, D, D, EPI_BIAS_BF16, qc, nullptr, nullptr, nullptr, nullptr, stream));
       // cross K/V of layer l: columns [l*2D, l*2D + D) are K, the next D are V; rows b*T + t
       KIRI_TRY(launch_attention<false>(qc, D, nullptr, nullptr, crosskv + static_cast<size_t>(l) * 2 * D,
-                                       crosskv + static_cast<size_t>(l) * 2 * D + D, T, L * 2 * D, T, nullptr, B, heads, o, stream));
+                                       crosskv + static_cast<size_t>(l) * 2 * D + D, T, L * 2 * D, T, cross_bucket,
+                                       step_dev, nullptr, B, heads, o, stream));
       KIRI_TRY(gemm_call(o, lw.wco, lw.bco, B, D, D, EPI_BIAS_RESID_LN, x, x, lw.ln3_g, lw.ln3_b, a, stream));
       KIRI_TRY(gemm_call(a, lw.w1, lw.b1, B, d.dec_ff, D, EPI_BIAS_GELU_BF16, hb, nullptr, nullptr, nullptr, nullptr, stream));
       const float* ng = (l + 1 < L) ? w.dec[l + 1].ln1_g : w.dec_ln_g;
@@ -363,15 +387,52 @@ extern "C" int kiri_decode_greedy(KiriHandle* h, const void* mem_bf16, const int
       KIRI_TRY(gemm_call(hb, lw.w2, lw.b2, B, D, d.dec_ff, EPI_BIAS_RESID_LN, x, x, ng, nb, a, stream));
     }
     KIRI_TRY(gemm_call(a, w.heads_w, w.heads_b, B, 2 * Vp, D, EPI_BIAS_F32, logits, nullptr, nullptr, nullptr, nullptr, stream));
-    dec_select_kernel<<<(B + 3) / 4, 128, 0, stream>>>(logits, B, Vd, Vp, Lmax, step, *p, seq, n_tok, finished, max_steps,
-                                                       target, alive, forced_ids, ids, n_out, sum_logp, step_logp, step_prob);
+    dec_select_kernel<<<(B + 3) / 4, 128, 0, stream>>>(logits, B, Vd, Vp, Lmax, step_dev, *p, seq, n_tok, finished,
+                                                       max_steps, target, alive, forced_ids, ids, n_out, sum_logp,
+                                                       step_logp, step_prob);
     KIRI_CHECK_CUDA(cudaGetLastError());
+    dec_advance_kernel<<<1, 1, 0, stream>>>(step_dev);
+    KIRI_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  };
+
+  static int* alive_host = nullptr;
+  if (!alive_host) KIRI_CHECK_CUDA(cudaMallocHost(&alive_host, sizeof(int)));
+  if (poll_every <= 0) poll_every = 8;
+  cudaGraphExec_t graphs[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // the legacy default stream cannot be captured: fall back to plain launches there
+  const bool use_graphs = getenv("KIRI_NO_GRAPH") == nullptr && stream != nullptr && stream != cudaStreamLegacy;
+  int rc = 0;
+  int step = 0;
+  for (; step < Lmax; ++step) {
+    ProfScope ps_step(PS_DEC_STEP, stream);
+    const int bucket = att_bucket(step + 1);
+    if (step == 0 || !use_graphs) {
+      // the first step runs eagerly (it also sets the kernels' one-time attributes)
+      if ((rc = enqueue_step(bucket)) != 0) break;
+    } else {
+      if (!graphs[bucket]) {
+        cudaGraph_t g = nullptr;
+        if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) { rc = -2; set_last_error("kiri_decode_greedy: stream capture failed to begin"); break; }
+        const int erc = enqueue_step(bucket);
+        const cudaError_t ce = cudaStreamEndCapture(stream, &g);
+        if (erc != 0 || ce != cudaSuccess || !g) { rc = erc ? erc : -2; if (!erc) set_last_error("kiri_decode_greedy: stream capture failed: %s", cudaGetErrorString(ce)); break; }
+        const cudaError_t ie = cudaGraphInstantiate(&graphs[bucket], g, 0);
+        cudaGraphDestroy(g);
+        if (ie != cudaSuccess) { rc = -2; set_last_error("kiri_decode_greedy: graph instantiate failed: %s", cudaGetErrorString(ie)); break; }
+      }
+      if (cudaGraphLaunch(graphs[bucket], stream) != cudaSuccess) { rc = -2; set_last_error("kiri_decode_greedy: graph launch failed"); break; }
+    }
     if ((step + 1) % poll_every == 0 || step + 1 == Lmax) {
-      KIRI_CHECK_CUDA(cudaMemcpyAsync(alive_host, alive, sizeof(int), cudaMemcpyDeviceToHost, stream));
-      KIRI_CHECK_CUDA(cudaStreamSynchronize(stream));
+      if (cudaMemcpyAsync(alive_host, alive, sizeof(int), cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+          cudaStreamSynchronize(stream) != cudaSuccess) { rc = -2; set_last_error("kiri_decode_greedy: poll failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
       if (*alive_host <= 0) { ++step; break; }
     }
   }
+  if (rc == 0) cudaStreamSynchronize(stream);      // graphs must be idle before they are destroyed
+  for (int i = 0; i < 6; ++i)
+    if (graphs[i]) cudaGraphExecDestroy(graphs[i]);
+  if (rc != 0) return rc;
   if (steps_run_host) *steps_run_host = step;
   return 0;
 }

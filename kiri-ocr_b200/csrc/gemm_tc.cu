@@ -1,86 +1,69 @@
 // tcgen05/TMEM/TMA implicit-GEMM kernel + host launcher.  See gemm_tc.cuh for the design.
 #include "gemm_tc.cuh"
 
+#include <cstring>
 #include <mutex>
+#include <unordered_map>
 
 namespace kiri {
 
 static constexpr int kTileM = 128;
-static constexpr int kChunkBytes = 64;                  // 32 bf16 of K
-static constexpr int kATileBytes = kTileM * kChunkBytes;  // one A chunk tile: 8 KiB
+// K is consumed in chunks of KC = 32 or 64 bf16 (64- or 128-byte rows, SWIZZLE_64B / _128B).
+// 64-byte rows exist because the stem's channel counts 96 and 160 are multiples of 32 only.
 static constexpr int kAccStride = 256;                  // TMEM columns per accumulator
 static constexpr int kTmemCols = 512;
 static constexpr int kNumThreads = 192;                 // warp0 TMA, warp1 MMA, warps2-5 epilogue
 static constexpr int kMaxStages = 8;
+static constexpr int kStageBufBytes = 4096;             // 32 rows x 128 B epilogue staging tile
+static constexpr int kResDepth = 4;                     // residual chunks prefetched per warp
 
-struct __align__(8) PipeBarriers {
+struct __align__(16) PipeBarriers {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
+  uint64_t res_full[4][kResDepth];   // per epilogue warp: residual chunk landed
   uint32_t tmem_base;
-  uint32_t pad;
+  uint32_t pad[3];
+  float bias[2][256];                // bias slice of the tile being drained, per accumulator
 };
 
-template <int EPI>
-__device__ __forceinline__ void epilogue_store(const float* v, int ncols, int col0, size_t row,
-                                               const EpiParams& e) {
-  // v[0..ncols) are acc values for columns col0..col0+ncols of output row `row`.
-  // ncols is 16 or 32; stores are predicated per 8 (bf16) / 4 (fp32) columns on n_valid.
-  if (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_F32) {
-    float* out = reinterpret_cast<float*>(e.out) + row * (size_t)e.ldc + col0;
-    const float* res = (EPI == EPI_BIAS_RESID_F32) ? e.resid + row * (size_t)e.ldc + col0 : nullptr;
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      if (j < ncols && col0 + j + 4 <= e.n_valid) {
-        float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col0 + j));
-        float4 o = make_float4(v[j] + b.x, v[j + 1] + b.y, v[j + 2] + b.z, v[j + 3] + b.w);
-        if (EPI == EPI_BIAS_RESID_F32) {
-          float4 r = *reinterpret_cast<const float4*>(res + j);
-          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-        }
-        *reinterpret_cast<float4*>(out + j) = o;
-      }
-    }
-  } else {
-    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(e.out) + row * (size_t)e.ldc + col0;
-#pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      if (j < ncols && col0 + j + 8 <= e.n_valid) {
-        float4 b0 = __ldg(reinterpret_cast<const float4*>(e.bias + col0 + j));
-        float4 b1 = __ldg(reinterpret_cast<const float4*>(e.bias + col0 + j + 4));
-        float t[8] = {v[j] + b0.x,     v[j + 1] + b0.y, v[j + 2] + b0.z, v[j + 3] + b0.w,
-                      v[j + 4] + b1.x, v[j + 5] + b1.y, v[j + 6] + b1.z, v[j + 7] + b1.w};
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          if (EPI == EPI_BIAS_SILU_BF16) t[q] = silu_fast(t[q]);
-          if (EPI == EPI_BIAS_GELU_BF16) t[q] = gelu_erf(t[q]);
-        }
-        uint4 pk;
-        pk.x = pack_bf16x2(t[0], t[1]);
-        pk.y = pack_bf16x2(t[2], t[3]);
-        pk.z = pack_bf16x2(t[4], t[5]);
-        pk.w = pack_bf16x2(t[6], t[7]);
-        *reinterpret_cast<uint4*>(out + j) = pk;
-      }
-    }
-  }
+// 16-byte chunk j of row `lane` inside a 32 x 128 B tile laid out with the 128-byte swizzle that the
+// TMA tensor maps of the epilogue use: conflict-free for "one thread = one row" accesses.
+__device__ __forceinline__ uint32_t stg_off(int lane, int j) {
+  return static_cast<uint32_t>(lane * 128 + ((j ^ (lane & 7)) << 4));
 }
 
-template <int CPS, int NSEG, int EPI>
+template <int EPI>
+__device__ __forceinline__ float epi_act(float v) {
+  if (EPI == EPI_BIAS_SILU_BF16) return silu_fast(v);
+  if (EPI == EPI_BIAS_GELU_BF16) return gelu_erf_fast(v);
+  return v;
+}
+
+template <int KC, int CPS, int NSEG, int EPI>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const ConvGeom g, const EpiParams e, const int bn, const int num_m_tiles,
-               const int num_n_tiles, const int stages) {
+               const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
+               const __grid_constant__ CUtensorMap tmOut2, const ConvGeom g, const EpiParams e,
+               const int bn, const int num_m_tiles, const int num_n_tiles, const int stages) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [stages][A: CPS*8K][B: CPS*bn*64] then barriers
+  constexpr int kChunkBytes = KC * 2;
+  constexpr int kATileBytes = kTileM * kChunkBytes;
+  constexpr uint32_t kSBO = 8 * kChunkBytes;                 // 8-row group pitch
+  constexpr uint64_t kLayout = (KC == 64) ? UMMA_LAYOUT_SW128 : UMMA_LAYOUT_SW64;
+  constexpr bool kF32Out = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_F32 || EPI == EPI_BIAS_RESID_LN);
+  constexpr bool kResid = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_RESID_LN);
+  // carve: [stages][A: CPS chunk tiles][B: CPS chunk tiles] | staging 4x2x4K | residual ring | barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   const uint32_t a_stage_bytes = CPS * kATileBytes;
   const uint32_t b_chunk_bytes = bn * kChunkBytes;
   const uint32_t b_stage_bytes = CPS * b_chunk_bytes;
   const uint32_t stage_bytes = a_stage_bytes + b_stage_bytes;
-  PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(smem + (size_t)stages * stage_bytes);
+  uint8_t* staging = smem + (size_t)stages * stage_bytes;
+  uint8_t* resring = staging + 4 * 2 * kStageBufBytes;
+  PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(resring + (kResid ? 4 * kResDepth * kStageBufBytes : 0));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -96,9 +79,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&bars->tmem_full[a], 1);
       mbar_init(&bars->tmem_empty[a], 4);
     }
+    for (int wq = 0; wq < 4; ++wq)
+      for (int r = 0; r < kResDepth; ++r) mbar_init(&bars->res_full[wq][r], 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut);
   }
   if (warp == 1) {
     tmem_alloc(&bars->tmem_base, kTmemCols);
@@ -112,14 +98,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ============================ TMA producer ============================
     if (lane == 0) {
-      // one TMA box = one 32-channel chunk of one segment: R*SEG rows x 64 B
+      // one TMA box = one KC-channel chunk of one segment: R*SEG rows x (KC*2) B
       const uint32_t box_bytes = g.R * g.SEG * kChunkBytes;
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n_tile = tile % num_n_tiles;
         const int m_tile = tile / num_n_tiles;
-        // decode the tile's segments once
         int seg_b[NSEG], seg_x[NSEG], seg_y[NSEG];
         int nvalid = 0;
 #pragma unroll
@@ -185,9 +170,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int c = 0; c < CPS; ++c) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const uint64_t ad = umma_desc_kmajor(a_addr + c * kATileBytes + h * 32, 512, UMMA_LAYOUT_SW64);
-              const uint64_t bd = umma_desc_kmajor(b_addr + c * b_chunk_bytes + h * 32, 512, UMMA_LAYOUT_SW64);
+            for (int h = 0; h < KC / 16; ++h) {
+              const uint64_t ad = umma_desc_kmajor(a_addr + c * kATileBytes + h * 32, kSBO, kLayout);
+              const uint64_t bd = umma_desc_kmajor(b_addr + c * b_chunk_bytes + h * 32, kSBO, kLayout);
               umma_bf16(d_tmem, ad, bd, idesc, (kb | c | h) != 0 ? 1u : 0u);
             }
           }
@@ -199,10 +184,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ============================ epilogue warps ============================
+    // Thread = one tile row (TMEM lane).  Everything that touches global memory goes through
+    // 32-row x 128-byte shared-memory tiles moved by TMA (bulk tensor stores / loads), so the
+    // global traffic is whole 128-byte lines although a thread owns a row, not a column range.
     const int q = warp & 3;                        // TMEM lane quarter this warp may read
-    const int m = q * 32 + lane;                   // tile row
-    const int j = m / (g.R * g.SEG);               // segment within tile
-    const int within = m - j * (g.R * g.SEG);
+    const int ew = warp - 2;                       // staging / residual slot of this warp
+    uint8_t* stg = staging + ew * 2 * kStageBufBytes;
+    uint8_t* rring = resring + ew * kResDepth * kStageBufBytes;
+    uint32_t stg_cnt = 0;                          // staging tiles issued (for buffer rotation)
+    uint32_t res_cnt = 0;                          // residual chunks consumed (slot + parity)
+    // first row of this warp inside the tile and its decomposition
+    const int m0 = q * 32;
+    const int j = m0 / (g.R * g.SEG);
+    const int within = m0 - j * (g.R * g.SEG);
     const int jj = within / g.SEG;
     const int ii = within - jj * g.SEG;
     int it = 0;
@@ -211,10 +205,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m_tile = tile / num_n_tiles;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      // output row of this thread
+      // output row of the warp's first lane; the warp's 32 rows are consecutive output rows
       const int s = m_tile * NSEG + j;
       bool valid = s < g.n_seg_total;
-      size_t row = 0;
+      int row0 = 0;
       if (valid) {
         const int b = s / g.segs_per_img;
         const int rem = s - b * g.segs_per_img;
@@ -223,106 +217,185 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int oy = yb * g.R + jj;
         const int ox = xb * g.SEG + ii;
         valid = (oy < g.OH) && (ox < g.OW);
-        row = ((size_t)b * g.OH + oy) * g.OW + ox;
+        row0 = (b * g.OH + oy) * g.OW + ox;
+      }
+      const int col_base = n_tile * bn;
+      // stage this tile's bias slice in shared memory (overlaps the wait for the accumulator)
+      float* sbias = bars->bias[acc];
+      {
+        const int t = ew * 32 + lane;
+        for (int c = t; c < 256; c += 128) sbias[c] = (c < bn && col_base + c < e.n_valid) ? __ldg(e.bias + col_base + c) : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      if (kResid && valid && lane == 0) {
+        // the residual does not depend on the accumulator: request the first chunks now
+#pragma unroll
+        for (int r = 0; r < kResDepth; ++r) {
+          const uint32_t slot = (res_cnt + r) % kResDepth;
+          mbar_arrive_expect_tx(&bars->res_full[ew][slot], kStageBufBytes);
+          tma_load_2d(rring + slot * kStageBufBytes, &tmRes, &bars->res_full[ew][slot], r * 32, row0);
+        }
       }
       mbar_wait(&bars->tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccStride;
-      const int col_base = n_tile * bn;
-      if (EPI == EPI_BIAS_RESID_LN) {
-        // x = resid + acc + bias is written out AND parked back in TMEM, so the row statistics
-        // and the normalised bf16 copy need no second trip to global memory.  bn == N == 256.
-        float* xo = reinterpret_cast<float*>(e.out) + row * (size_t)e.ldc;
-        const float* xr = e.resid + row * (size_t)e.ldc;
+
+      if (kResid) {
+        // ---- x = resid + acc + bias (fp32 out); EPI_BIAS_RESID_LN also emits LayerNorm(x) in bf16.
+        // x is parked back in TMEM so the statistics need no second trip to memory.  bn == 256.
         float sum = 0.f;
-        for (int c0 = 0; c0 < 256; c0 += 32) {
+        for (int c = 0; c < 8; ++c) {
           uint32_t r[32];
-          tmem_ld32(taddr + c0, r);
+          tmem_ld32(taddr + c * 32, r);
+          const uint32_t slot = res_cnt % kResDepth;
+          const uint32_t par = (res_cnt / kResDepth) & 1;
+          if (valid) mbar_wait(&bars->res_full[ew][slot], par);
           tmem_ld_wait();
-          if (valid) {
+          const uint8_t* rb = rring + slot * kStageBufBytes;
+          uint8_t* ob = stg + (stg_cnt & 1) * kStageBufBytes;
+          if (lane == 0) bulk_wait_group_read<1>();
+          __syncwarp();
 #pragma unroll
-            for (int t = 0; t < 32; t += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + c0 + t));
-              const float4 q4 = *reinterpret_cast<const float4*>(xr + c0 + t);
-              float4 o;
-              o.x = __uint_as_float(r[t]) + b.x + q4.x;
-              o.y = __uint_as_float(r[t + 1]) + b.y + q4.y;
-              o.z = __uint_as_float(r[t + 2]) + b.z + q4.z;
-              o.w = __uint_as_float(r[t + 3]) + b.w + q4.w;
-              *reinterpret_cast<float4*>(xo + c0 + t) = o;
-              sum += (o.x + o.y) + (o.z + o.w);
-              r[t] = __float_as_uint(o.x); r[t + 1] = __float_as_uint(o.y);
-              r[t + 2] = __float_as_uint(o.z); r[t + 3] = __float_as_uint(o.w);
+          for (int t = 0; t < 8; ++t) {
+            const float4 b = *reinterpret_cast<const float4*>(sbias + c * 32 + 4 * t);
+            float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) q4 = *reinterpret_cast<const float4*>(rb + stg_off(lane, t));
+            float4 o;
+            o.x = __uint_as_float(r[4 * t]) + b.x + q4.x;
+            o.y = __uint_as_float(r[4 * t + 1]) + b.y + q4.y;
+            o.z = __uint_as_float(r[4 * t + 2]) + b.z + q4.z;
+            o.w = __uint_as_float(r[4 * t + 3]) + b.w + q4.w;
+            *reinterpret_cast<float4*>(ob + stg_off(lane, t)) = o;
+            sum += (o.x + o.y) + (o.z + o.w);
+            r[4 * t] = __float_as_uint(o.x); r[4 * t + 1] = __float_as_uint(o.y);
+            r[4 * t + 2] = __float_as_uint(o.z); r[4 * t + 3] = __float_as_uint(o.w);
+          }
+          if (EPI == EPI_BIAS_RESID_LN) tmem_st32(taddr + c * 32, r);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && valid) {
+            tma_store_2d(&tmOut, ob, c * 32, row0);
+            bulk_commit_group();
+            // this residual slot is free again: request chunk c + kResDepth of the same tile
+            if (c + kResDepth < 8) {
+              mbar_arrive_expect_tx(&bars->res_full[ew][slot], kStageBufBytes);
+              tma_load_2d(rring + slot * kStageBufBytes, &tmRes, &bars->res_full[ew][slot], (c + kResDepth) * 32, row0);
             }
           }
-          tmem_st32(taddr + c0, r);
+          ++stg_cnt;
+          if (valid) ++res_cnt;
         }
-        tmem_st_wait();
-        const float mean = sum * (1.0f / 256.0f);
-        float sq = 0.f;
-        for (int c0 = 0; c0 < 256; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(taddr + c0, r);
-          tmem_ld_wait();
+        if (EPI == EPI_BIAS_RESID_LN) {
+          tmem_st_wait();
+          const float mean = sum * (1.0f / 256.0f);
+          float sq = 0.f;
+          for (int c = 0; c < 8; ++c) {
+            uint32_t r[32];
+            tmem_ld32(taddr + c * 32, r);
+            tmem_ld_wait();
 #pragma unroll
-          for (int t = 0; t < 32; ++t) { const float d = __uint_as_float(r[t]) - mean; sq = fmaf(d, d, sq); }
-        }
-        const float rstd = 1.0f / sqrtf(sq * (1.0f / 256.0f) + 1e-5f);
-        __nv_bfloat16* ao = reinterpret_cast<__nv_bfloat16*>(e.out2) + row * (size_t)256;
-        for (int c0 = 0; c0 < 256; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(taddr + c0, r);
-          tmem_ld_wait();
-          if (valid) {
+            for (int t = 0; t < 32; ++t) { const float d = __uint_as_float(r[t]) - mean; sq = fmaf(d, d, sq); }
+          }
+          const float rstd = 1.0f / sqrtf(sq * (1.0f / 256.0f) + 1e-5f);
+          for (int c = 0; c < 4; ++c) {                       // 64 bf16 columns = 128 B per row
+            uint32_t ra[32], rb2[32];
+            tmem_ld32(taddr + c * 64, ra);
+            tmem_ld32(taddr + c * 64 + 32, rb2);
+            tmem_ld_wait();
+            uint8_t* ob = stg + (stg_cnt & 1) * kStageBufBytes;
+            if (lane == 0) bulk_wait_group_read<1>();
+            __syncwarp();
 #pragma unroll
-            for (int t = 0; t < 32; t += 8) {
-              const float4 g0 = __ldg(reinterpret_cast<const float4*>(e.ln_g + c0 + t));
-              const float4 g1 = __ldg(reinterpret_cast<const float4*>(e.ln_g + c0 + t + 4));
-              const float4 h0 = __ldg(reinterpret_cast<const float4*>(e.ln_b + c0 + t));
-              const float4 h1 = __ldg(reinterpret_cast<const float4*>(e.ln_b + c0 + t + 4));
+            for (int t = 0; t < 8; ++t) {
+              const uint32_t* src = (t < 4) ? ra : rb2;
+              const int o8 = (t & 3) * 8;
+              const int col = c * 64 + t * 8;
+              const float4 g0 = __ldg(reinterpret_cast<const float4*>(e.ln_g + col));
+              const float4 g1 = __ldg(reinterpret_cast<const float4*>(e.ln_g + col + 4));
+              const float4 h0 = __ldg(reinterpret_cast<const float4*>(e.ln_b + col));
+              const float4 h1 = __ldg(reinterpret_cast<const float4*>(e.ln_b + col + 4));
               const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
               const float hh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
               float y[8];
 #pragma unroll
-              for (int u = 0; u < 8; ++u) y[u] = (__uint_as_float(r[t + u]) - mean) * rstd * gg[u] + hh[u];
+              for (int u = 0; u < 8; ++u) y[u] = (__uint_as_float(src[o8 + u]) - mean) * rstd * gg[u] + hh[u];
               uint4 pk;
               pk.x = pack_bf16x2(y[0], y[1]); pk.y = pack_bf16x2(y[2], y[3]);
               pk.z = pack_bf16x2(y[4], y[5]); pk.w = pack_bf16x2(y[6], y[7]);
-              *reinterpret_cast<uint4*>(ao + c0 + t) = pk;
+              *reinterpret_cast<uint4*>(ob + stg_off(lane, t)) = pk;
             }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0 && valid) {
+              tma_store_2d(&tmOut2, ob, c * 64, row0);
+              bulk_commit_group();
+            }
+            ++stg_cnt;
           }
         }
+      } else if (kF32Out) {
+        // ---- fp32 out = acc + bias, 32 columns (128 B per row) per staging tile
+        for (int c0 = 0; c0 < bn; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c0, r);
+          tmem_ld_wait();
+          uint8_t* ob = stg + (stg_cnt & 1) * kStageBufBytes;
+          if (lane == 0) bulk_wait_group_read<1>();
+          __syncwarp();
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const float4 b = *reinterpret_cast<const float4*>(sbias + c0 + 4 * t);
+            const float4 o = make_float4(__uint_as_float(r[4 * t]) + b.x, __uint_as_float(r[4 * t + 1]) + b.y,
+                                         __uint_as_float(r[4 * t + 2]) + b.z, __uint_as_float(r[4 * t + 3]) + b.w);
+            *reinterpret_cast<float4*>(ob + stg_off(lane, t)) = o;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && valid) {
+            tma_store_2d(&tmOut, ob, col_base + c0, row0);
+            bulk_commit_group();
+          }
+          ++stg_cnt;
+        }
       } else {
-      int c0 = 0;
-      for (; c0 + 32 <= bn; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(taddr + c0, r);
-        tmem_ld_wait();
-        if (valid) {
-          float v[32];
+        // ---- bf16 out = act(acc + bias), 64 columns (128 B per row) per staging tile
+        for (int c0 = 0; c0 < bn; c0 += 64) {
+          uint32_t ra[32], rb2[32];
+          tmem_ld32(taddr + c0, ra);
+          tmem_ld32(taddr + c0 + 32, rb2);        // may run past bn: columns are clipped by the store
+          tmem_ld_wait();
+          uint8_t* ob = stg + (stg_cnt & 1) * kStageBufBytes;
+          if (lane == 0) bulk_wait_group_read<1>();
+          __syncwarp();
 #pragma unroll
-          for (int t = 0; t < 32; ++t) v[t] = __uint_as_float(r[t]);
-          epilogue_store<EPI>(v, 32, col_base + c0, row, e);
+          for (int t = 0; t < 8; ++t) {
+            const uint32_t* src = (t < 4) ? ra : rb2;
+            const int o8 = (t & 3) * 8;
+            const float4 b0 = *reinterpret_cast<const float4*>(sbias + c0 + t * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(sbias + c0 + t * 8 + 4);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            float y[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) y[u] = epi_act<EPI>(__uint_as_float(src[o8 + u]) + bb[u]);
+            uint4 pk;
+            pk.x = pack_bf16x2(y[0], y[1]); pk.y = pack_bf16x2(y[2], y[3]);
+            pk.z = pack_bf16x2(y[4], y[5]); pk.w = pack_bf16x2(y[6], y[7]);
+            *reinterpret_cast<uint4*>(ob + stg_off(lane, t)) = pk;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && valid) {
+            tma_store_2d(&tmOut, ob, col_base + c0, row0);
+            bulk_commit_group();
+          }
+          ++stg_cnt;
         }
-      }
-      if (c0 < bn) {
-        uint32_t r[16];
-        tmem_ld16(taddr + c0, r);
-        tmem_ld_wait();
-        if (valid) {
-          float v[32];
-#pragma unroll
-          for (int t = 0; t < 16; ++t) v[t] = __uint_as_float(r[t]);
-#pragma unroll
-          for (int t = 16; t < 32; ++t) v[t] = 0.f;
-          epilogue_store<EPI>(v, 16, col_base + c0, row, e);
-        }
-      }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
     }
+    if (lane == 0) bulk_wait_group<0>();          // all stores of this warp have landed
   }
 
   tc_fence_before();
@@ -367,31 +440,78 @@ int gemm_tc_num_sms() {
   return g_num_sms;
 }
 
+// cuTensorMapEncodeTiled costs several microseconds on the host; the recogniser re-issues the same
+// few dozen (pointer, shape) combinations every step, so encoded maps are cached.
+struct MapKey {
+  const void* base;
+  int rank, swz;
+  cuuint64_t dims[5], strides[4];
+  cuuint32_t box[5], estr[5];
+  bool operator==(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) == 0; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    const uint64_t* p = reinterpret_cast<const uint64_t*>(&k);
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(MapKey) / 8; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+    return static_cast<size_t>(h);
+  }
+};
+static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
+static std::mutex g_map_mutex;
+
 static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims,
-                      const cuuint64_t* strides, const cuuint32_t* box, const cuuint32_t* estr) {
+                      const cuuint64_t* strides, const cuuint32_t* box, const cuuint32_t* estr,
+                      CUtensorMapSwizzle swz, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
+  MapKey key;
+  memset(&key, 0, sizeof(key));
+  key.base = base; key.rank = rank; key.swz = static_cast<int>(swz) | (static_cast<int>(dtype) << 8);
+  for (int i = 0; i < rank; ++i) { key.dims[i] = dims[i]; key.box[i] = box[i]; key.estr[i] = estr[i]; }
+  for (int i = 0; i < rank - 1; ++i) key.strides[i] = strides[i];
+  {
+    std::lock_guard<std::mutex> lock(g_map_mutex);
+    auto it = g_map_cache.find(key);
+    if (it != g_map_cache.end()) { *m = it->second; return 0; }
+  }
   EncodeTiledFn fn = get_encode_fn();
   KIRI_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides,
-                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+  CUresult r = fn(m, dtype, rank, const_cast<void*>(base), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   KIRI_REQUIRE(r == CUDA_SUCCESS,
                "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu,%llu,%llu box %u,%u,%u", (int)r,
                rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
-               (unsigned long long)dims[2], box[0], box[1], box[2]);
+               (unsigned long long)(rank > 2 ? dims[2] : 0), box[0], box[1], rank > 2 ? box[2] : 0);
+  std::lock_guard<std::mutex> lock(g_map_mutex);
+  if (g_map_cache.size() > 8192) g_map_cache.clear();
+  g_map_cache.emplace(key, *m);
   return 0;
 }
 
-template <int CPS, int NSEG, int EPI>
-static int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGeom& g,
-                       const EpiParams& e, int bn, int num_m_tiles, int num_n_tiles,
-                       cudaStream_t stream) {
-  const int stage_bytes = CPS * kATileBytes + CPS * bn * kChunkBytes;
-  const int overhead = 1024 + (int)sizeof(PipeBarriers);
+// 2-D row-major [rows, cols] view moved in 32-row x 128-byte tiles (epilogue stores / residual loads)
+static int encode_rowtile_map(CUtensorMap* m, const void* base, long long rows, int cols, int ld, bool f32) {
+  const int esz = f32 ? 4 : 2;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t str[1] = {(cuuint64_t)ld * esz};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esz), 32};
+  cuuint32_t es[2] = {1, 1};
+  return encode_map(m, base, 2, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_128B,
+                    f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+}
+
+template <int KC, int CPS, int NSEG, int EPI>
+static int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
+                       const CUtensorMap& tmRes, const CUtensorMap& tmOut2, const ConvGeom& g,
+                       const EpiParams& e, int bn, int num_m_tiles, int num_n_tiles, cudaStream_t stream) {
+  constexpr bool kResid = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_RESID_LN);
+  const int stage_bytes = CPS * kTileM * KC * 2 + CPS * bn * KC * 2;
+  const int overhead = 1024 + (int)sizeof(PipeBarriers) + 4 * 2 * kStageBufBytes +
+                       (kResid ? 4 * kResDepth * kStageBufBytes : 0);
   int stages = (g_max_smem - overhead) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   KIRI_REQUIRE(stages >= 2, "gemm_tc: stage of %d bytes does not fit twice in shared memory", stage_bytes);
   const int smem = stages * stage_bytes + overhead;
-  auto kern = gemm_tc_kernel<CPS, NSEG, EPI>;
+  auto kern = gemm_tc_kernel<KC, CPS, NSEG, EPI>;
   static int configured = 0;
   if (configured < smem) {
     KIRI_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
@@ -399,7 +519,7 @@ static int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
   }
   int grid = num_m_tiles * num_n_tiles;
   if (grid > g_num_sms) grid = g_num_sms;
-  kern<<<grid, kNumThreads, smem, stream>>>(tmA, tmB, g, e, bn, num_m_tiles, num_n_tiles, stages);
+  kern<<<grid, kNumThreads, smem, stream>>>(tmA, tmB, tmOut, tmRes, tmOut2, g, e, bn, num_m_tiles, num_n_tiles, stages);
   KIRI_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -408,27 +528,30 @@ int launch_gemm_tc(const GemmLaunch& L, cudaStream_t stream) {
   gemm_tc_num_sms();
   KIRI_REQUIRE(L.Cin % 32 == 0, "gemm_tc: Cin=%d must be a multiple of 32", L.Cin);
   KIRI_REQUIRE(L.e.bias != nullptr && L.e.out != nullptr, "gemm_tc: bias/out must not be null");
-  const int chunks = L.Cin / 32;
   const bool is_gemm = (L.kw == 1 && L.kh == 1);
+  const int KC = (L.Cin % 64 == 0) ? 64 : 32;             // 128-byte rows whenever the channels allow
+  const int chunks = L.Cin / KC;
   ConvGeom g;
   int NSEG = 1, CPS = 1;
   if (is_gemm) {
     KIRI_REQUIRE(L.IH == 1 && L.NB == 1 && L.OH == 1 && L.OW == L.IW, "gemm_tc: plain GEMM wants [1,1,M,K]");
     g.R = 1; g.SEG = 128;
-    KIRI_REQUIRE(chunks % 2 == 0, "gemm_tc: GEMM K=%d must be a multiple of 64", L.Cin);
-    CPS = 2;
+    KIRI_REQUIRE(KC == 64, "gemm_tc: GEMM K=%d must be a multiple of 64", L.Cin);
+    CPS = 1;
   } else {
     if (L.OW % 128 == 0) { g.R = 1; g.SEG = 128; }
     else if (L.OW % 64 == 0 && L.OH % 2 == 0) { g.R = 2; g.SEG = 64; }
     else if (L.OW % 32 == 0 && L.OH % 4 == 0) { g.R = 4; g.SEG = 32; }
     else if (L.OW % 32 == 0) { g.R = 1; g.SEG = 32; NSEG = 4; }
     else { KIRI_REQUIRE(false, "gemm_tc: conv output width %d must be a multiple of 32", L.OW); }
-    CPS = (NSEG == 1 && chunks <= 3) ? chunks : 1;
+    if (KC == 64) CPS = 1;
+    else CPS = (NSEG == 1 && chunks <= 3) ? chunks : 1;
     KIRI_REQUIRE(L.epi == EPI_BIAS_SILU_BF16, "gemm_tc: conv path is built with the SiLU epilogue only");
   }
   g.OH = L.OH; g.OW = L.OW;
   g.sw = L.sw; g.sh = L.sh; g.pad = L.pad; g.kw = L.kw; g.taps = L.kw * L.kh;
   g.chunks_per_tap = chunks; g.cgs = chunks / CPS;
+  KIRI_REQUIRE(chunks % CPS == 0, "gemm_tc: %d chunks per tap not divisible by %d", chunks, CPS);
   g.segs_per_row = (L.OW + g.SEG - 1) / g.SEG;
   g.segs_per_img = ((L.OH + g.R - 1) / g.R) * g.segs_per_row;
   g.n_seg_total = L.NB * g.segs_per_img;
@@ -438,52 +561,66 @@ int launch_gemm_tc(const GemmLaunch& L, cudaStream_t stream) {
   const int num_n_tiles = (L.N + bn - 1) / bn;
   KIRI_REQUIRE(g.SEG * g.sw <= 256 && g.R * g.sh <= 256, "gemm_tc: TMA box too large");
   KIRI_REQUIRE(L.e.n_valid == L.N, "gemm_tc: n_valid must equal N");
-  KIRI_REQUIRE(L.e.n_valid % ((L.epi == EPI_BIAS_F32 || L.epi == EPI_BIAS_RESID_F32 || L.epi == EPI_BIAS_RESID_LN) ? 4 : 8) == 0,
-               "gemm_tc: N=%d not storable with vector stores for epilogue %d", L.N, L.epi);
+  const bool f32_out = (L.epi == EPI_BIAS_F32 || L.epi == EPI_BIAS_RESID_F32 || L.epi == EPI_BIAS_RESID_LN);
+  KIRI_REQUIRE((static_cast<long long>(L.e.ldc) * (f32_out ? 4 : 2)) % 16 == 0,
+               "gemm_tc: output row pitch must be a multiple of 16 bytes (ldc=%d)", L.e.ldc);
+  KIRI_REQUIRE((reinterpret_cast<uintptr_t>(L.e.out) & 15) == 0, "gemm_tc: output must be 16-byte aligned");
 
-  // Tensor maps keep global strides ascending; a box covers ONE 32-channel chunk, so a box lands
-  // in shared memory as [rows][64 B] — exactly the K-major SWIZZLE_64B operand tile.
-  // A: (c32, chunk, W, H, image)
-  CUtensorMap tmA, tmB;
+  // Tensor maps keep global strides ascending; a box covers ONE KC-channel chunk, so a box lands
+  // in shared memory as [rows][KC*2 B] — exactly the K-major swizzled operand tile.
+  // A: (cKC, chunk, W, H, image)
+  CUtensorMap tmA, tmB, tmOut, tmRes, tmOut2;
+  const CUtensorMapSwizzle swz = (KC == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   {
-    cuuint64_t dims[5] = {32, (cuuint64_t)chunks, (cuuint64_t)L.IW, (cuuint64_t)L.IH, (cuuint64_t)L.NB};
-    cuuint64_t str[4] = {64, (cuuint64_t)L.Cin * 2, (cuuint64_t)L.IW * L.Cin * 2,
+    cuuint64_t dims[5] = {(cuuint64_t)KC, (cuuint64_t)chunks, (cuuint64_t)L.IW, (cuuint64_t)L.IH, (cuuint64_t)L.NB};
+    cuuint64_t str[4] = {(cuuint64_t)KC * 2, (cuuint64_t)L.Cin * 2, (cuuint64_t)L.IW * L.Cin * 2,
                          (cuuint64_t)L.IH * L.IW * L.Cin * 2};
-    cuuint32_t box[5] = {32, 1, (cuuint32_t)(g.SEG * g.sw), (cuuint32_t)(g.R * g.sh), 1};
+    cuuint32_t box[5] = {(cuuint32_t)KC, 1, (cuuint32_t)(g.SEG * g.sw), (cuuint32_t)(g.R * g.sh), 1};
     cuuint32_t es[5] = {1, 1, (cuuint32_t)g.sw, (cuuint32_t)g.sh, 1};
-    if (encode_map(&tmA, L.a, 5, dims, str, box, es)) return -1;
+    if (encode_map(&tmA, L.a, 5, dims, str, box, es, swz)) return -1;
   }
-  {  // B: (c32, chunk, N)
+  {  // B: (cKC, chunk, N)
     const int ktot = g.taps * L.Cin;
-    cuuint64_t dims[3] = {32, (cuuint64_t)(ktot / 32), (cuuint64_t)L.N};
-    cuuint64_t str[2] = {64, (cuuint64_t)ktot * 2};
-    cuuint32_t box[3] = {32, 1, (cuuint32_t)bn};
+    cuuint64_t dims[3] = {(cuuint64_t)KC, (cuuint64_t)(ktot / KC), (cuuint64_t)L.N};
+    cuuint64_t str[2] = {(cuuint64_t)KC * 2, (cuuint64_t)ktot * 2};
+    cuuint32_t box[3] = {(cuuint32_t)KC, 1, (cuuint32_t)bn};
     cuuint32_t es[3] = {1, 1, 1};
-    if (encode_map(&tmB, L.w, 3, dims, str, box, es)) return -1;
+    if (encode_map(&tmB, L.w, 3, dims, str, box, es, swz)) return -1;
+  }
+  const long long rows_total = static_cast<long long>(L.NB) * L.OH * L.OW;
+  if (encode_rowtile_map(&tmOut, L.e.out, rows_total, L.N, L.e.ldc, f32_out)) return -1;
+  tmRes = tmOut;
+  tmOut2 = tmOut;
+  if (L.epi == EPI_BIAS_RESID_F32 || L.epi == EPI_BIAS_RESID_LN) {
+    KIRI_REQUIRE(L.N == 256 && L.e.ldc == 256 && L.e.resid, "gemm_tc: residual epilogues need N = ldc = 256 and resid");
+    if (encode_rowtile_map(&tmRes, L.e.resid, rows_total, 256, 256, true)) return -1;
+  }
+  if (L.epi == EPI_BIAS_RESID_LN) {
+    KIRI_REQUIRE(L.e.ln_g && L.e.ln_b && L.e.out2, "gemm_tc: LayerNorm epilogue needs ln_g, ln_b, out2");
+    if (encode_rowtile_map(&tmOut2, L.e.out2, rows_total, 256, 256, false)) return -1;
   }
 
-#define KIRI_LAUNCH(C, S, E) \
-  return launch_inst<C, S, E>(tmA, tmB, g, L.e, bn, num_m_tiles, num_n_tiles, stream)
+#define KIRI_LAUNCH(K, C, S, E) \
+  return launch_inst<K, C, S, E>(tmA, tmB, tmOut, tmRes, tmOut2, g, L.e, bn, num_m_tiles, num_n_tiles, stream)
   if (!is_gemm) {
-    if (CPS == 1 && NSEG == 1) KIRI_LAUNCH(1, 1, EPI_BIAS_SILU_BF16);
-    if (CPS == 1 && NSEG == 4) KIRI_LAUNCH(1, 4, EPI_BIAS_SILU_BF16);
-    if (CPS == 2 && NSEG == 1) KIRI_LAUNCH(2, 1, EPI_BIAS_SILU_BF16);
-    if (CPS == 3 && NSEG == 1) KIRI_LAUNCH(3, 1, EPI_BIAS_SILU_BF16);
+    if (KC == 64 && NSEG == 1) KIRI_LAUNCH(64, 1, 1, EPI_BIAS_SILU_BF16);
+    if (KC == 64 && NSEG == 4) KIRI_LAUNCH(64, 1, 4, EPI_BIAS_SILU_BF16);
+    if (KC == 32 && CPS == 1 && NSEG == 1) KIRI_LAUNCH(32, 1, 1, EPI_BIAS_SILU_BF16);
+    if (KC == 32 && CPS == 1 && NSEG == 4) KIRI_LAUNCH(32, 1, 4, EPI_BIAS_SILU_BF16);
+    if (KC == 32 && CPS == 3 && NSEG == 1) KIRI_LAUNCH(32, 3, 1, EPI_BIAS_SILU_BF16);
   } else {
     switch (L.epi) {
-      case EPI_BIAS_BF16: KIRI_LAUNCH(2, 1, EPI_BIAS_BF16);
-      case EPI_BIAS_SILU_BF16: KIRI_LAUNCH(2, 1, EPI_BIAS_SILU_BF16);
-      case EPI_BIAS_GELU_BF16: KIRI_LAUNCH(2, 1, EPI_BIAS_GELU_BF16);
-      case EPI_BIAS_RESID_F32: KIRI_LAUNCH(2, 1, EPI_BIAS_RESID_F32);
-      case EPI_BIAS_F32: KIRI_LAUNCH(2, 1, EPI_BIAS_F32);
-      case EPI_BIAS_RESID_LN:
-        if (L.N != 256 || L.e.ldc != 256 || !L.e.ln_g || !L.e.ln_b || !L.e.out2 || !L.e.resid) break;
-        KIRI_LAUNCH(2, 1, EPI_BIAS_RESID_LN);
+      case EPI_BIAS_BF16: KIRI_LAUNCH(64, 1, 1, EPI_BIAS_BF16);
+      case EPI_BIAS_SILU_BF16: KIRI_LAUNCH(64, 1, 1, EPI_BIAS_SILU_BF16);
+      case EPI_BIAS_GELU_BF16: KIRI_LAUNCH(64, 1, 1, EPI_BIAS_GELU_BF16);
+      case EPI_BIAS_RESID_F32: KIRI_LAUNCH(64, 1, 1, EPI_BIAS_RESID_F32);
+      case EPI_BIAS_F32: KIRI_LAUNCH(64, 1, 1, EPI_BIAS_F32);
+      case EPI_BIAS_RESID_LN: KIRI_LAUNCH(64, 1, 1, EPI_BIAS_RESID_LN);
       default: break;
     }
   }
 #undef KIRI_LAUNCH
-  KIRI_REQUIRE(false, "gemm_tc: no kernel instance for CPS=%d NSEG=%d epi=%d", CPS, NSEG, L.epi);
+  KIRI_REQUIRE(false, "gemm_tc: no kernel instance for KC=%d CPS=%d NSEG=%d epi=%d", KC, CPS, NSEG, L.epi);
 }
 
 }  // namespace kiri

@@ -112,6 +112,8 @@ class BatchedRecognizer:
         h = C.c_void_p()
         _lib.check(self.lib.kiri_create(C.byref(self.pw.dims), C.byref(self.pw.struct), C.byref(h)), "kiri_create")
         self.handle = h
+        # the engine runs on its own (capturable) stream; public calls fence it against the caller's stream
+        self.stream = torch.cuda.Stream(device=self.device)
         self._ws: Optional[torch.Tensor] = None
         self._dws: Optional[torch.Tensor] = None
         self.launches = 0           # kernels launched by this engine (for bench's gpu_launches)
@@ -309,6 +311,13 @@ class BatchedRecognizer:
         (byte offset, pitch, w, h) of every crop after the reference's clamp-pad."""
         if method not in ("ctc", "decoder"):
             raise ValueError("method must be 'ctc' or 'decoder'")
+        caller = torch.cuda.current_stream(self.device)
+        if caller != self.stream:
+            self.stream.wait_stream(caller)
+            with torch.cuda.stream(self.stream):
+                out = self.recognize_packed(src, entries, method, streaming)
+            caller.wait_stream(self.stream)
+            return out
         n = len(entries)
         results: List[Optional[LineResult]] = [None] * n
         if n == 0:

@@ -43,6 +43,7 @@ class LineResult:
     step_prob: Optional[np.ndarray] = None
     frame_ids: Optional[np.ndarray] = None
     frame_prob: Optional[np.ndarray] = None
+    len_est: int = 0                # CTC length estimate that bounds the decoder (model.py:416-425)
 
 
 def target_widths(w: np.ndarray, h: np.ndarray, img_h: int) -> np.ndarray:
@@ -339,7 +340,7 @@ class BatchedRecognizer:
                 Lmax = self.max_steps_bound(int(n_host.max()), T)
                 d_ids, n_out, sum_lp, slp, spr, _ = self.decode_greedy(enc["mem_bf16"], n_ids, B, T, Lmax,
                                                                       select_raw=streaming, want_steps=True)
-                pending.append((idx, "decoder", d_ids, n_out, sum_lp, conf, slp, spr))
+                pending.append((idx, "decoder", d_ids, n_out, sum_lp, conf, slp, spr, n_host.numpy()))
         torch.cuda.current_stream().synchronize()
         tok = self.tok
         for item in pending:
@@ -353,9 +354,9 @@ class BatchedRecognizer:
                     row = ids_h[j, :n_h[j]]
                     results[li] = LineResult(tok.decode_collapsed_ctc(row.tolist()), float(c_h[j]), float(c_h[j]), row,
                                              frame_ids=None if f_h is None else f_h[j],
-                                             frame_prob=None if p_h is None else p_h[j])
+                                             frame_prob=None if p_h is None else p_h[j], len_est=int(n_h[j]))
             else:
-                _, _, d_ids, n_out, sum_lp, conf, slp, spr = item
+                _, _, d_ids, n_out, sum_lp, conf, slp, spr, len_h = item
                 ids_h, n_h, s_h, c_h = d_ids.cpu().numpy(), n_out.cpu().numpy(), sum_lp.cpu().numpy(), conf.cpu().numpy()
                 slp_h, spr_h = slp.cpu().numpy(), spr.cpu().numpy()
                 for j, li in enumerate(idx):
@@ -368,7 +369,8 @@ class BatchedRecognizer:
                     lps = slp_h[j, :n_h[j]].astype(np.float64)
                     dec_conf = min(1.0, max(0.0, math.exp(float(lps.sum()) / len(lps)))) if len(lps) else 0.0
                     results[li] = LineResult(tok.decode_dec(text_ids), 0.6 * dec_conf + 0.4 * float(c_h[j]),
-                                             float(c_h[j]), row, step_logp=slp_h[j, :n_h[j]], step_prob=spr_h[j, :n_h[j]])
+                                             float(c_h[j]), row, step_logp=slp_h[j, :n_h[j]], step_prob=spr_h[j, :n_h[j]],
+                                             len_est=int(len_h[j]))
         return results
 
     def recognize_crops(self, crops: Sequence[np.ndarray], method: str = "ctc", streaming: bool = False):

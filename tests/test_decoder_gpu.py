@@ -65,14 +65,20 @@ def test_teacher_forced_step_logp(engines, golden, tok_cfg, name):
 
 
 @pytest.mark.parametrize("name", ["hard", "eos", "blank", "default"])
-def test_free_running_accurate_vs_goldens(engines, golden, name):
+def test_free_running_accurate_vs_goldens(engines, golden, tok_cfg, name):
+    """Free-running greedy decode.  A line whose ids equal the golden must also match its
+    confidence.  A line that diverges must diverge at a NEAR TIE: the oracle, teacher-forced on the
+    device's own sequence, must rank every device-chosen token within 2*DEC_LOGP_ATOL of its own
+    top-1 at that step (so ids are bit-exact wherever the margin exceeds the tolerance)."""
+    from oracle import decode as OD, model as OM, preprocess as OP
+    tok, cfg = tok_cfg
     eng, sd = engines(name)
     n = lines_for(name)
     crops = golden_crops()[:n]
     res = eng.recognize_crops(crops, "decoder")
     same_text = same_ids = 0
     first_div = []
-    conf_diff = 0.0
+    conf_diff = worst_gap = 0.0
     for i, r in enumerate(res):
         g = golden[f"{name}/{i}/dec_ids"].astype(np.int32)
         eq = len(r.ids) == len(g) and np.array_equal(r.ids, g)
@@ -80,18 +86,35 @@ def test_free_running_accurate_vs_goldens(engines, golden, name):
         same_text += int(r.text == str(golden[f"{name}/{i}/acc_text"]))
         if eq:
             conf_diff = max(conf_diff, abs(r.confidence - float(golden[f"{name}/{i}/acc_conf"])))
-        else:
-            m = min(len(r.ids), len(g))
-            dv = np.nonzero(r.ids[:m] != g[:m])[0]
-            first_div.append(int(dv[0]) if len(dv) else m)
+            continue
+        m = min(len(r.ids), len(g))
+        dv = np.nonzero(r.ids[:m] != g[:m])[0]
+        first_div.append(int(dv[0]) if len(dv) else m)
+        x = torch.from_numpy(OP.normalise(OP.preprocess_crop(crops[i])))[None, None]
+        mem = OM.encode(sd, x)
+        _, _, _, length = OD.ctc_greedy(OM.ctc_logits(sd, mem)[0].numpy())
+        assert length == int(golden[f"{name}/{i}/len_est"])
+        # the device bounds its loop with ITS OWN CTC length estimate, which may differ from the
+        # oracle's by the near-tie frames (checked in test_engine_gpu); feed it to the oracle
+        assert abs(r.len_est - length) <= 3, (i, r.len_est, length)
+        length = r.len_est
+        ids = [int(t) for t in r.ids]
+        _, lps, rows = OD.greedy_decode(sd, OM.mem_proj(sd, mem), cfg, tok.unk_id + 3, length, forced=ids,
+                                        return_logp=True)
+        assert len(lps) == len(ids), (i, len(lps), len(ids))      # same stop rule / max_steps
+        gap = (rows[:len(ids)].max(dim=1).values - torch.tensor(lps)).numpy()
+        worst_gap = max(worst_gap, float(gap.max()))
+        assert gap.max() <= 2 * DEC_LOGP_ATOL, (i, int(gap.argmax()), float(gap.max()))
+        d = np.abs(r.step_logp - np.asarray(lps, np.float32))
+        assert d.max() <= DEC_LOGP_ATOL, (i, float(d.max()))
     _report(f"decoder_free/{name}", {"lines": n, "ids_equal": same_ids, "text_equal": same_text,
-                                     "first_divergence_steps": first_div, "max_conf_diff_on_equal": conf_diff})
+                                     "first_divergence_steps": first_div, "max_conf_diff_on_equal": conf_diff,
+                                     "worst_oracle_gap_of_device_choice": worst_gap})
     assert conf_diff < 0.02
     if name == "blank":
         assert all(len(r.ids) == 170 for r in res)          # len_ctc == 0 -> 170 steps (model.py:421-425)
     if name == "eos":
         assert sum(int(r.ids[-1]) == 2 for r in res) >= 3  # EOS termination at mixed steps
-    assert same_ids >= n // 2
 
 
 def test_streaming_rule_raw_argmax(engines, golden, tok_cfg):

@@ -108,14 +108,43 @@ def test_encoder_and_ctc_parity(engines, golden, name):
 
 
 def test_recognize_crops_fast_matches_goldens(engines, golden):
+    """Public fast path vs the reference goldens.  Rule (north_star): frame ids are bit-exact on
+    every frame whose oracle top-1 margin exceeds 2*LOGIT_ATOL; on a near-tie frame the device may
+    pick any class whose oracle logit is within 2*LOGIT_ATOL of the top; the collapsed ids must be
+    EXACTLY collapse(device frame ids) (integer work); text of all-safe lines equals the golden."""
+    from oracle import decode as OD, preprocess as OP
     eng, sd = engines("hard")
     crops = golden_crops()
-    res = eng.recognize_crops(crops, "ctc")
-    same = sum(r.text == str(golden[f"hard/{i}/fast_text"]) for i, r in enumerate(res))
-    confd = max(abs(r.confidence - float(golden[f"hard/{i}/ctc_conf"])) for i, r in enumerate(res))
-    _report("fast_text/hard", {"lines": len(crops), "equal": same, "max_conf_diff": confd})
+    res = eng.recognize_crops(crops, "ctc", streaming=True)
+    same = safe_lines = safe_lines_equal = near_tie_flips = 0
+    confd = 0.0
+    for i, r in enumerate(res):
+        gold_text = str(golden[f"hard/{i}/fast_text"])
+        gold_frames = golden[f"hard/{i}/frame_ids"].astype(np.int64)
+        confd = max(confd, abs(r.confidence - float(golden[f"hard/{i}/ctc_conf"])))
+        _, _, lg = oracle_line(sd, OP.preprocess_crop(crops[i]))
+        assert np.array_equal(lg.argmax(1), gold_frames)           # oracle == reference on frame ids
+        top = lg.max(1)
+        margin = top - np.sort(lg, axis=1)[:, -2]
+        safe = margin > 2 * LOGIT_ATOL
+        got = np.asarray(r.frame_ids, np.int64)
+        assert np.array_equal(got[safe], gold_frames[safe]), i
+        # near-tie frames: the chosen class must itself be within the tolerance band of the top
+        assert np.all(top - lg[np.arange(len(got)), got] <= 2 * LOGIT_ATOL), i
+        near_tie_flips += int((got != gold_frames).sum())
+        # integer work: the device collapse of ITS frame ids is bit-exact against the oracle rule
+        want_ids = [int(a) for k, a in enumerate(got) if a >= 2 and (k == 0 or a != got[k - 1])]
+        assert r.ids.tolist() == want_ids, i
+        assert r.text == eng.tok.decode_collapsed_ctc(want_ids)
+        same += int(r.text == gold_text)
+        if safe.all():
+            safe_lines += 1
+            safe_lines_equal += int(r.text == gold_text)
+    _report("fast_text/hard", {"lines": len(crops), "equal": same, "max_conf_diff": confd,
+                               "all_safe_lines": safe_lines, "all_safe_lines_equal": safe_lines_equal,
+                               "near_tie_frames_flipped": near_tie_flips})
     assert confd < 0.05
-    assert same >= len(crops) - 2          # near-tie frames may flip under bf16; see parity report
+    assert safe_lines_equal == safe_lines
 
 
 def test_bucketed_equals_reference_with_img_w(engines):

@@ -164,10 +164,19 @@ extern "C" int kiri_create(const KiriDims* dims, const KiriWeights* weights, Kir
   memcpy(h->conv1_b, weights->conv1_b_host, sizeof(h->conv1_b));
   h->w.conv1_w_host = h->conv1_w;
   h->w.conv1_b_host = h->conv1_b;
+  h->fused = nullptr;
+  if (dims->dec_layers > 0 && weights->heads_w && weights->dec[0].wqkv) {
+    const int rc = fused_decoder_build(h);
+    if (rc != 0) { delete h; return rc; }
+  }
   *out = h;
   return 0;
 }
-extern "C" void kiri_destroy(KiriHandle* h) { delete h; }
+extern "C" void kiri_destroy(KiriHandle* h) {
+  if (!h) return;
+  fused_decoder_free(h);
+  delete h;
+}
 
 namespace {
 struct EncodeWs {          // byte offsets into the caller's workspace

@@ -352,12 +352,31 @@ extern "C" int kiri_decode_greedy(KiriHandle* h, const void* mem_bf16, const int
   { ProfScope ps(PS_DEC_CROSSKV, stream);
     KIRI_TRY(gemm_call(mem_bf16, w.crosskv_w, w.crosskv_b, B * T, L * 2 * D, d.enc_dim, EPI_BIAS_BF16, crosskv, nullptr,
                        nullptr, nullptr, nullptr, stream)); }
+  int* step_dev = alive + 1;                     // lives next to the alive counter
+  KIRI_CHECK_CUDA(cudaMemsetAsync(step_dev, 0, sizeof(int), stream));
+
+  static int* alive_host = nullptr;
+  if (!alive_host) KIRI_CHECK_CUDA(cudaMallocHost(&alive_host, sizeof(int)));
+
+  // Default: the whole decode in ONE persistent cluster kernel (decoder_fused.cu).  The
+  // step-per-launch path below is kept for A/B runs (KIRI_DEC_LEGACY=1).
+  if (getenv("KIRI_DEC_LEGACY") == nullptr) {
+    int cs = 8;
+    if (const char* e = getenv("KIRI_DEC_CLUSTER")) cs = atoi(e);
+    { ProfScope ps_step(PS_DEC_STEP, stream);
+      KIRI_TRY(fused_decoder_run(h, crosskv, L * 2 * D, nullptr, nullptr, T, self_k, self_v, len_est, forced_ids, B, Lmax, p,
+                                 ids, n_out, sum_logp, step_logp, step_prob, step_dev, cs, stream)); }
+    if (steps_run_host) {
+      KIRI_CHECK_CUDA(cudaMemcpyAsync(alive_host, step_dev, sizeof(int), cudaMemcpyDeviceToHost, stream));
+      KIRI_CHECK_CUDA(cudaStreamSynchronize(stream));
+      *steps_run_host = *alive_host;
+    }
+    return 0;
+  }
   dec_init_kernel<<<(B + 127) / 128, 128, 0, stream>>>(len_est, B, T, Lmax, *p, seq, n_tok, finished, max_steps, target,
                                                        alive, n_out, sum_logp);
   KIRI_CHECK_CUDA(cudaGetLastError());
 
-  int* step_dev = alive + 1;                     // lives next to the alive counter
-  KIRI_CHECK_CUDA(cudaMemsetAsync(step_dev, 0, sizeof(int), stream));
 
   // one decode step = 3 + 11 * layers launches reading `step` from device memory, so a step can be
   // captured once per self-attention bucket and replayed as a CUDA graph (the step is launch-bound)
@@ -396,8 +415,6 @@ extern "C" int kiri_decode_greedy(KiriHandle* h, const void* mem_bf16, const int
     return 0;
   };
 
-  static int* alive_host = nullptr;
-  if (!alive_host) KIRI_CHECK_CUDA(cudaMallocHost(&alive_host, sizeof(int)));
   if (poll_every <= 0) poll_every = 8;
   cudaGraphExec_t graphs[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   // the legacy default stream cannot be captured: fall back to plain launches there

@@ -1,0 +1,720 @@
+// K12 (fused): the whole greedy attention decode of a batch in ONE persistent cluster kernel.
+//
+// Replaces  beam_decode_one_batched at BEAM=1   kiri_ocr/model.py:390-600 (core.py:560-568)
+//           greedy_decode_streaming (token rule) kiri_ocr/model.py:779-946
+//
+// The step-per-launch decoder (decoder.cu) spends ~430 us per step in 27 dependent small kernels
+// (profiles/r01_launches_acc.csv).  The decode step is a latency / weight-streaming problem
+// (M = lines, 6.3 MB of bf16 weights and ~0.5 MB of cross K/V per line per step), so here:
+//   * a thread-block CLUSTER of CS CTAs owns 16 lines (the M of mma.m16n8k16) for the whole decode:
+//     no launches, no host polling, per-cluster early exit when its 16 lines are done;
+//   * the cluster is tensor-parallel: CTA r owns heads [r*8/CS, ...) of both attentions and a 1/CS
+//     column slice of every projection, so each SM streams only 1/CS of the weights per step;
+//     slices are exchanged with DSMEM stores (st.shared::cluster) + barrier.cluster, 19 per step;
+//   * weights are pre-packed in mma B-fragment order (pack_frag_kernel), so a warp streams its
+//     n-tile with fully coalesced 512-byte LDG.128 straight from L2 into registers - no staging;
+//   * residual stream, LayerNorms, LM fusion, the four cumulative repeat penalties, arg-max and
+//     the stop rule are replicated in every CTA of the cluster (identical inputs -> identical
+//     tokens), so no token broadcast is needed; rank 0 writes the global outputs.
+// Numerics follow decoder.cu: bf16 operands, fp32 accumulate, fp32 residual stream.
+#include <cooperative_groups.h>
+
+#include <cstdlib>
+#include <cstring>
+
+#include "internal.cuh"
+#include "ln_utils.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace kiri {
+
+static constexpr int kFL = 16;          // lines per cluster (MMA M)
+static constexpr int kFWarps = 16;
+static constexpr int kFThreads = kFWarps * 32;
+static constexpr int kHd = 32;
+static constexpr int kHeads = 8;
+static constexpr int kTokBOS = 1, kTokEOS = 2;
+static constexpr int kPad = 8;          // bf16 elements of row padding (bank spread for A fragments)
+
+struct FusedLayer {
+  const uint4 *wqkv, *wo, *wcq, *wco, *w1, *w2;      // fragment-packed bf16
+  const float *bqkv, *bo, *bcq, *bco, *b1, *b2;
+  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *ln3_g, *ln3_b;
+};
+struct FusedArgs {
+  FusedLayer layer[KIRI_MAX_LAYERS];
+  const uint4* wheads; const float* bheads;
+  const float *dec_ln_g, *dec_ln_b, *emb, *pe;
+  int layers, ff, Vd, Vp, has_pos;
+  const __nv_bfloat16* crosskv; int crosskv_ld;       // [rows, layers*2*D]
+  const int* mem_row0; const int* mem_len;            // per line (nullable -> b*T, T)
+  int T;
+  __nv_bfloat16 *self_k, *self_v;                     // [layers][B][Lmax][D]
+  const int* len_est; const int* forced;
+  int B, Lmax;
+  KiriDecodeParams p;
+  int *ids, *n_out; float *sum_logp, *step_logp, *step_prob;
+  int* steps_max;                                     // device int: max steps run by any cluster
+  int timing;                                         // 1: accumulate phase cycles into g_dec_prof
+};
+
+// ---------------------------------------------------------------- weight packing
+// dst word ((nt*K/32 + kt)*32 + lane)*4 + wd  =  W[nt*8 + lane/4][kt*32 + wd*8 + (lane%4)*2 .. +1]
+__global__ void pack_frag_kernel(const __nv_bfloat16* __restrict__ w, int N, int K, uint32_t* __restrict__ dst) {
+  const size_t total = static_cast<size_t>(N) * K / 2;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int wd = i & 3, lane = (i >> 2) & 31;
+    const size_t t = i >> 7;
+    const int kt = t % (K / 32), nt = t / (K / 32);
+    const int n = nt * 8 + (lane >> 2), k = kt * 32 + wd * 8 + (lane & 3) * 2;
+    dst[i] = *reinterpret_cast<const uint32_t*>(w + static_cast<size_t>(n) * K + k);
+  }
+}
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                               uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
+// c += A[16 x (k32 tiles kb..ke)] * W_ntile^T ; wp points at the n-tile's packed stream
+__device__ __forceinline__ void mma_ntile(float (&c)[4], const uint4* __restrict__ wp, const __nv_bfloat16* A, int lda,
+                                          int kb, int ke, int lane) {
+  const int r = lane >> 2, cq = (lane & 3) * 2;
+  const __nv_bfloat16* a_lo = A + r * lda + cq;
+  const __nv_bfloat16* a_hi = a_lo + 8 * lda;
+#pragma unroll 8
+  for (int kt = kb; kt < ke; ++kt) {
+    const uint4 w = ldg_stream(wp + kt * 32 + lane);
+    const int k = kt * 32;
+    const uint32_t a0 = *reinterpret_cast<const uint32_t*>(a_lo + k), a1 = *reinterpret_cast<const uint32_t*>(a_hi + k);
+    const uint32_t a2 = *reinterpret_cast<const uint32_t*>(a_lo + k + 8), a3 = *reinterpret_cast<const uint32_t*>(a_hi + k + 8);
+    mma_bf16_16816(c, a0, a1, a2, a3, w.x, w.y);
+    const uint32_t e0 = *reinterpret_cast<const uint32_t*>(a_lo + k + 16), e1 = *reinterpret_cast<const uint32_t*>(a_hi + k + 16);
+    const uint32_t e2 = *reinterpret_cast<const uint32_t*>(a_lo + k + 24), e3 = *reinterpret_cast<const uint32_t*>(a_hi + k + 24);
+    mma_bf16_16816(c, e0, e1, e2, e3, w.z, w.w);
+  }
+}
+
+// Y[16 x (8*nt_count)] = A[16 x K] * W^T for the n-tiles nt_of(0..nt_count-1) of a packed matrix.
+// epi(row, global_col (even), v0, v1) is called exactly once per column pair.  Ends with all
+// epilogues issued (caller synchronises).  `part` is shared scratch of >= 16*512 bytes.
+template <class NtOf, class Epi>
+__device__ __forceinline__ void cta_gemm(const uint4* __restrict__ wp, int K, const __nv_bfloat16* A, int lda,
+                                         int nt_count, NtOf nt_of, float* part, Epi epi) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k32 = K / 32;
+  int KS = 1;
+  while (nt_count * KS * 2 <= kFWarps && (k32 % (KS * 2)) == 0 && KS < 8) KS *= 2;
+  const int items = nt_count * KS;
+  const int kper = k32 / KS;
+  for (int item = warp; item < items; item += kFWarps) {
+    const int ni = item / KS, ks = item - ni * KS;
+    const int nt = nt_of(ni);
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+    mma_ntile(c, wp + static_cast<size_t>(nt) * k32 * 32, A, lda, ks * kper, (ks + 1) * kper, lane);
+    if (KS == 1) {
+      const int r = lane >> 2, col = nt * 8 + (lane & 3) * 2;
+      epi(r, col, c[0], c[1]);
+      epi(r + 8, col, c[2], c[3]);
+    } else {
+      *reinterpret_cast<float4*>(part + (item * 32 + lane) * 4) = make_float4(c[0], c[1], c[2], c[3]);
+    }
+  }
+  if (KS > 1) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nt_count * 64; idx += kFThreads) {
+      const int ni = idx >> 6, e = idx & 63, l = e >> 1, hi = e & 1;
+      float v0 = 0.f, v1 = 0.f;
+      for (int ks = 0; ks < KS; ++ks) {
+        const float2 pv = *reinterpret_cast<const float2*>(part + ((ni * KS + ks) * 32 + l) * 4 + hi * 2);
+        v0 += pv.x; v1 += pv.y;
+      }
+      epi((l >> 2) + hi * 8, nt_of(ni) * 8 + (l & 3) * 2, v0, v1);
+    }
+  }
+}
+
+// per-line decode state, replicated in every CTA of the cluster
+struct LineState {
+  int hist[kFL][8];      // sequence so far (ring is unnecessary: only the last 6 are needed) - kept as last-8 window
+  int n_tok[kFL];
+  int finished[kFL];
+  int max_steps[kFL];
+  int target[kFL];
+  int cur_tok[kFL];
+  int valid[kFL];
+  int row0[kFL];
+  int mlen[kFL];
+};
+
+struct FusedSmem {                       // byte offsets into dynamic shared memory
+  int x, gath, a, obuf, hbuf, qloc, logits, part, vstage, state, total;
+};
+__host__ __device__ inline FusedSmem fused_smem_plan(int ff, int Vp, int cs) {
+  FusedSmem s;
+  int off = 0;
+  auto take = [&](int bytes) { const int o = off; off += (bytes + 127) & ~127; return o; };
+  s.x = take(kFL * 256 * 4);
+  s.gath = take(kFL * 256 * 4);
+  s.a = take(kFL * (256 + kPad) * 2);
+  s.obuf = take(kFL * (256 + kPad) * 2);
+  s.hbuf = take(kFL * (ff + kPad) * 2);
+  s.qloc = take(kFL * (256 / cs) * 4);
+  s.logits = take(kFL * 2 * Vp * 4);
+  s.part = take(kFWarps * 512);
+  s.vstage = take(kFWarps * 32 * kHd * 2);
+  s.state = take(static_cast<int>(sizeof(LineState)));
+  s.total = off;
+  return s;
+}
+
+// single-query attention of one warp over n keys; K/V rows are 32 bf16 at base + j*ld.
+// q: 32 fp32 in shared memory; vst: this warp's 32x32 bf16 staging tile.  Returns o[lane].
+template <bool READONLY>
+__device__ __forceinline__ float attend_warp(const float* q, const __nv_bfloat16* kbase, const __nv_bfloat16* vbase,
+                                             size_t ld, int n, __nv_bfloat16* vst, int lane) {
+  float qf[kHd];
+#pragma unroll
+  for (int i = 0; i < kHd; i += 4) {
+    const float4 t = *reinterpret_cast<const float4*>(q + i);
+    qf[i] = t.x; qf[i + 1] = t.y; qf[i + 2] = t.z; qf[i + 3] = t.w;
+  }
+  const float scale = 0.17677669529663687f;           // 1/sqrt(32)
+  float m_run = -INFINITY, l_run = 0.f, o = 0.f;
+  for (int c0 = 0; c0 < n; c0 += 32) {
+    const int j = c0 + lane;
+    float s = -INFINITY;
+    uint4 vv[4];
+    if (j < n) {
+      const uint4* kp = reinterpret_cast<const uint4*>(kbase + static_cast<size_t>(j) * ld);
+      const uint4* vp = reinterpret_cast<const uint4*>(vbase + static_cast<size_t>(j) * ld);
+      uint4 kk[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (READONLY) { kk[i] = __ldg(kp + i); vv[i] = __ldg(vp + i); }
+        else { kk[i] = kp[i]; vv[i] = vp[i]; }
+      }
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint4 u = kk[i];
+        acc = fmaf(qf[8 * i + 0], bf16_lo(u.x), acc); acc = fmaf(qf[8 * i + 1], bf16_hi(u.x), acc);
+        acc = fmaf(qf[8 * i + 2], bf16_lo(u.y), acc); acc = fmaf(qf[8 * i + 3], bf16_hi(u.y), acc);
+        acc = fmaf(qf[8 * i + 4], bf16_lo(u.z), acc); acc = fmaf(qf[8 * i + 5], bf16_hi(u.z), acc);
+        acc = fmaf(qf[8 * i + 6], bf16_lo(u.w), acc); acc = fmaf(qf[8 * i + 7], bf16_hi(u.w), acc);
+      }
+      s = acc * scale;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) vv[i] = make_uint4(0, 0, 0, 0);
+    }
+    // stage V rows (row = key, 64 B) with a 16-byte-chunk rotation so column reads are conflict-free
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      *reinterpret_cast<uint4*>(vst + lane * kHd + ((i + (lane >> 1)) & 3) * 8) = vv[i];
+    const float cm = warp_max(s);
+    const float m_new = fmaxf(m_run, cm);
+    const float corr = __expf(m_run - m_new);
+    const float p = (j < n) ? __expf(s - m_new) : 0.f;
+    l_run = l_run * corr + warp_sum(p);
+    o *= corr;
+    __syncwarp();
+    const int n_here = min(32, n - c0);
+    for (int jj = 0; jj < n_here; ++jj) {
+      const float pj = __shfl_sync(0xffffffffu, p, jj);
+      const int chunk = ((lane >> 3) + (jj >> 1)) & 3;
+      o = fmaf(pj, __bfloat162float(vst[jj * kHd + chunk * 8 + (lane & 7)]), o);
+    }
+    __syncwarp();
+    m_run = m_new;
+  }
+  return o / l_run;
+}
+
+__device__ __forceinline__ float warp_lse_s(const float* x, int n, int lane) {
+  float m = -INFINITY;
+  for (int v = lane; v < n; v += 32) m = fmaxf(m, x[v]);
+  m = warp_max(m);
+  float s = 0.f;
+  for (int v = lane; v < n; v += 32) s += expf(x[v] - m);
+  s = warp_sum(s);
+  return m + logf(s);
+}
+
+// Phase timing of cluster 0 / rank 0 (clock64 deltas), read back with kiri_debug_decode_timing().
+__device__ long long g_dec_prof[32];
+#define DEC_TICK(slot)                                                   \
+  do {                                                                   \
+    if (A.timing && blockIdx.x == 0 && threadIdx.x == 0) {               \
+      const long long t_now = clock64();                                 \
+      g_dec_prof[slot] += t_now - t_last;                                \
+      t_last = t_now;                                                    \
+    }                                                                    \
+  } while (0)
+
+template <int CS>
+__global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_constant__ FusedArgs A) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (CS == 1) ? 0 : static_cast<int>(cluster.block_rank());
+  const int cid = blockIdx.x / CS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int HPC = kHeads / CS;                 // heads per CTA
+  constexpr int DC = 256 / CS;                     // output columns of a D-wide projection per CTA
+  const FusedSmem L = fused_smem_plan(A.ff, A.Vp, CS);
+  float* x = reinterpret_cast<float*>(sm + L.x);
+  float* gath = reinterpret_cast<float*>(sm + L.gath);
+  __nv_bfloat16* a = reinterpret_cast<__nv_bfloat16*>(sm + L.a);
+  __nv_bfloat16* obuf = reinterpret_cast<__nv_bfloat16*>(sm + L.obuf);
+  __nv_bfloat16* hbuf = reinterpret_cast<__nv_bfloat16*>(sm + L.hbuf);
+  float* qloc = reinterpret_cast<float*>(sm + L.qloc);
+  float* logits = reinterpret_cast<float*>(sm + L.logits);
+  float* part = reinterpret_cast<float*>(sm + L.part);
+  __nv_bfloat16* vst = reinterpret_cast<__nv_bfloat16*>(sm + L.vstage) + warp * 32 * kHd;
+  LineState* st = reinterpret_cast<LineState*>(sm + L.state);
+  constexpr int lda = 256 + kPad;
+  const int ldh = A.ff + kPad;
+  const int b0 = cid * kFL;
+  const int D = 256;
+
+  // remote views of the exchange buffers
+  __nv_bfloat16* r_obuf[CS]; float* r_gath[CS]; __nv_bfloat16* r_hbuf[CS]; float* r_logits[CS];
+#pragma unroll
+  for (int d = 0; d < CS; ++d) {
+    if (CS == 1) { r_obuf[d] = obuf; r_gath[d] = gath; r_hbuf[d] = hbuf; r_logits[d] = logits; }
+    else {
+      r_obuf[d] = cluster.map_shared_rank(obuf, d); r_gath[d] = cluster.map_shared_rank(gath, d);
+      r_hbuf[d] = cluster.map_shared_rank(hbuf, d); r_logits[d] = cluster.map_shared_rank(logits, d);
+    }
+  }
+  auto csync = [&]() { if (CS == 1) __syncthreads(); else cluster.sync(); };
+
+  // ---- init (model.py:416-425: Python float arithmetic, int() truncation)
+  if (threadIdx.x < kFL) {
+    const int i = threadIdx.x, b = b0 + i;
+    const bool ok = b < A.B;
+    int ms = 0, tl = 0, Tm = A.T, r0 = 0;
+    if (ok) {
+      tl = A.len_est[b];
+      Tm = A.mem_len ? A.mem_len[b] : A.T;
+      r0 = A.mem_row0 ? A.mem_row0[b] : b * A.T;
+      if (tl > 0) ms = __double2int_rz(__dmul_rn(static_cast<double>(tl), A.p.len_ratio)) + A.p.len_pad;
+      else ms = __double2int_rz(__dmul_rn(static_cast<double>(Tm), A.p.mem_ratio)) + A.p.len_pad;
+      if (ms > A.p.max_dec_len) ms = A.p.max_dec_len;
+      if (ms > A.Lmax) ms = A.Lmax;
+    }
+    st->valid[i] = ok; st->row0[i] = r0; st->mlen[i] = Tm;
+    st->max_steps[i] = ms; st->target[i] = tl;
+    st->finished[i] = (!ok || ms <= 0) ? 1 : 0;
+    st->n_tok[i] = 1; st->cur_tok[i] = kTokBOS;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) st->hist[i][k] = -1 - k;
+    st->hist[i][0] = kTokBOS;
+    if (ok && rank == 0) { A.n_out[b] = 0; A.sum_logp[b] = 0.f; }
+  }
+  __syncthreads();
+  csync();                                          // every CTA of the cluster is resident and initialised
+
+  long long t_last = clock64();
+  int step = 0;
+  for (; step < A.Lmax; ++step) {
+    {
+      int alive = 0;
+#pragma unroll
+      for (int i = 0; i < kFL; ++i) alive += st->finished[i] ? 0 : 1;
+      if (alive == 0) break;
+    }
+    // ---- S0: x = emb[tok] + pe[step]; a = LN1_0(x)   (one warp per line)
+    {
+      const int i = warp;
+      const int tokid = st->finished[i] ? 0 : st->cur_tok[i];   // finished lines feed the pad token
+      const float4* e = reinterpret_cast<const float4*>(A.emb + static_cast<size_t>(tokid) * D) + lane * 2;
+      const float4 e0 = __ldg(e), e1 = __ldg(e + 1);
+      float v[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+      if (A.has_pos) {
+        const float4* pp = reinterpret_cast<const float4*>(A.pe + static_cast<size_t>(step) * D) + lane * 2;
+        const float4 p0 = __ldg(pp), p1 = __ldg(pp + 1);
+        v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w;
+        v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
+      }
+      st_f32x8(x + i * D + lane * 8, v);
+      ln8(v, A.layer[0].ln1_g, A.layer[0].ln1_b, lane);
+      st_bf16x8(a + i * lda + lane * 8, v);
+    }
+    __syncthreads();
+    DEC_TICK(0);
+
+    for (int l = 0; l < A.layers; ++l) {
+      const FusedLayer& W = A.layer[l];
+      __nv_bfloat16* kc = A.self_k + static_cast<size_t>(l) * A.B * A.Lmax * D;
+      __nv_bfloat16* vc = A.self_v + static_cast<size_t>(l) * A.B * A.Lmax * D;
+      // ---- A: q,k,v of my heads.  q -> qloc (fp32), k/v -> global cache row `step` (bf16)
+      cta_gemm(W.wqkv, D, a, lda, 12 * HPC,
+               [&](int i) { const int sec = i / (4 * HPC), rem = i - sec * 4 * HPC; return sec * 32 + rank * HPC * 4 + rem; },
+               part,
+               [&](int row, int col, float v0, float v1) {
+                 v0 += __ldg(W.bqkv + col); v1 += __ldg(W.bqkv + col + 1);
+                 const int sec = col >> 8, c = col & 255;
+                 if (sec == 0) {
+                   *reinterpret_cast<float2*>(qloc + row * DC + (c - rank * DC)) = make_float2(v0, v1);
+                 } else if (st->valid[row]) {
+                   __nv_bfloat16* dst = (sec == 1 ? kc : vc) + (static_cast<size_t>(b0 + row) * A.Lmax + step) * D + c;
+                   *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(v0, v1);
+                 }
+               });
+      __syncthreads();
+      DEC_TICK(1);
+      // ---- B: self-attention of my heads over keys 0..step -> o slices broadcast to every CTA
+      for (int pidx = warp; pidx < kFL * HPC; pidx += kFWarps) {
+        const int i = pidx % kFL, hl = pidx / kFL, head = rank * HPC + hl;
+        float o = 0.f;
+        if (st->valid[i]) {
+          const size_t base = (static_cast<size_t>(b0 + i) * A.Lmax) * D + head * kHd;
+          o = attend_warp<false>(qloc + i * DC + hl * kHd, kc + base, vc + base, D, step + 1, vst, lane);
+        }
+        const float on = __shfl_down_sync(0xffffffffu, o, 1);
+        if ((lane & 1) == 0) {
+          const uint32_t pk = pack_bf16x2(o, on);
+#pragma unroll
+          for (int d = 0; d < CS; ++d) *reinterpret_cast<uint32_t*>(r_obuf[d] + i * lda + head * kHd + lane) = pk;
+        }
+      }
+      DEC_TICK(2);
+      csync();
+      DEC_TICK(3);
+      // ---- C: out-proj slice -> gath (all CTAs)
+      cta_gemm(W.wo, D, obuf, lda, DC / 8, [&](int i) { return rank * (DC / 8) + i; }, part,
+               [&](int row, int col, float v0, float v1) {
+                 const float2 v = make_float2(v0 + __ldg(W.bo + col), v1 + __ldg(W.bo + col + 1));
+#pragma unroll
+                 for (int d = 0; d < CS; ++d) *reinterpret_cast<float2*>(r_gath[d] + row * D + col) = v;
+               });
+      DEC_TICK(4);
+      csync();
+      DEC_TICK(5);
+      // ---- D: x += gath; a = LN2(x)
+      {
+        const int i = warp;
+        float v[8];
+        const float4 x0 = *reinterpret_cast<const float4*>(x + i * D + lane * 8), x1 = *reinterpret_cast<const float4*>(x + i * D + lane * 8 + 4);
+        const float4 g0 = *reinterpret_cast<const float4*>(gath + i * D + lane * 8), g1 = *reinterpret_cast<const float4*>(gath + i * D + lane * 8 + 4);
+        v[0] = x0.x + g0.x; v[1] = x0.y + g0.y; v[2] = x0.z + g0.z; v[3] = x0.w + g0.w;
+        v[4] = x1.x + g1.x; v[5] = x1.y + g1.y; v[6] = x1.z + g1.z; v[7] = x1.w + g1.w;
+        st_f32x8(x + i * D + lane * 8, v);
+        ln8(v, W.ln2_g, W.ln2_b, lane);
+        st_bf16x8(a + i * lda + lane * 8, v);
+      }
+      __syncthreads();
+      DEC_TICK(6);
+      // ---- E: cross-attention query of my heads
+      cta_gemm(W.wcq, D, a, lda, DC / 8, [&](int i) { return rank * (DC / 8) + i; }, part,
+               [&](int row, int col, float v0, float v1) {
+                 *reinterpret_cast<float2*>(qloc + row * DC + (col - rank * DC)) =
+                     make_float2(v0 + __ldg(W.bcq + col), v1 + __ldg(W.bcq + col + 1));
+               });
+      __syncthreads();
+      DEC_TICK(7);
+      // ---- F: cross-attention over the line's memory (K | V of layer l inside the crosskv row)
+      for (int pidx = warp; pidx < kFL * HPC; pidx += kFWarps) {
+        const int i = pidx % kFL, hl = pidx / kFL, head = rank * HPC + hl;
+        float o = 0.f;
+        if (st->valid[i]) {
+          const __nv_bfloat16* kb = A.crosskv + static_cast<size_t>(st->row0[i]) * A.crosskv_ld + l * 2 * D + head * kHd;
+          o = attend_warp<true>(qloc + i * DC + hl * kHd, kb, kb + D, A.crosskv_ld, st->mlen[i], vst, lane);
+        }
+        const float on = __shfl_down_sync(0xffffffffu, o, 1);
+        if ((lane & 1) == 0) {
+          const uint32_t pk = pack_bf16x2(o, on);
+#pragma unroll
+          for (int d = 0; d < CS; ++d) *reinterpret_cast<uint32_t*>(r_obuf[d] + i * lda + head * kHd + lane) = pk;
+        }
+      }
+      DEC_TICK(8);
+      csync();
+      DEC_TICK(9);
+      // ---- G: cross out-proj slice -> gath
+      cta_gemm(W.wco, D, obuf, lda, DC / 8, [&](int i) { return rank * (DC / 8) + i; }, part,
+               [&](int row, int col, float v0, float v1) {
+                 const float2 v = make_float2(v0 + __ldg(W.bco + col), v1 + __ldg(W.bco + col + 1));
+#pragma unroll
+                 for (int d = 0; d < CS; ++d) *reinterpret_cast<float2*>(r_gath[d] + row * D + col) = v;
+               });
+      DEC_TICK(10);
+      csync();
+      DEC_TICK(11);
+      // ---- H: x += gath; a = LN3(x)
+      {
+        const int i = warp;
+        float v[8];
+        const float4 x0 = *reinterpret_cast<const float4*>(x + i * D + lane * 8), x1 = *reinterpret_cast<const float4*>(x + i * D + lane * 8 + 4);
+        const float4 g0 = *reinterpret_cast<const float4*>(gath + i * D + lane * 8), g1 = *reinterpret_cast<const float4*>(gath + i * D + lane * 8 + 4);
+        v[0] = x0.x + g0.x; v[1] = x0.y + g0.y; v[2] = x0.z + g0.z; v[3] = x0.w + g0.w;
+        v[4] = x1.x + g1.x; v[5] = x1.y + g1.y; v[6] = x1.z + g1.z; v[7] = x1.w + g1.w;
+        st_f32x8(x + i * D + lane * 8, v);
+        ln8(v, W.ln3_g, W.ln3_b, lane);
+        st_bf16x8(a + i * lda + lane * 8, v);
+      }
+      __syncthreads();
+      DEC_TICK(12);
+      // ---- I: FFN first linear + GELU(erf) slice -> hbuf (all CTAs)
+      {
+        const int ntc = A.ff / 8 / CS;
+        cta_gemm(W.w1, D, a, lda, ntc, [&](int i) { return rank * ntc + i; }, part,
+                 [&](int row, int col, float v0, float v1) {
+                   const uint32_t pk = pack_bf16x2(gelu_erf(v0 + __ldg(W.b1 + col)), gelu_erf(v1 + __ldg(W.b1 + col + 1)));
+#pragma unroll
+                   for (int d = 0; d < CS; ++d) *reinterpret_cast<uint32_t*>(r_hbuf[d] + row * ldh + col) = pk;
+                 });
+      }
+      DEC_TICK(13);
+      csync();
+      DEC_TICK(14);
+      // ---- J: FFN second linear slice -> gath
+      cta_gemm(W.w2, A.ff, hbuf, ldh, DC / 8, [&](int i) { return rank * (DC / 8) + i; }, part,
+               [&](int row, int col, float v0, float v1) {
+                 const float2 v = make_float2(v0 + __ldg(W.b2 + col), v1 + __ldg(W.b2 + col + 1));
+#pragma unroll
+                 for (int d = 0; d < CS; ++d) *reinterpret_cast<float2*>(r_gath[d] + row * D + col) = v;
+               });
+      DEC_TICK(15);
+      csync();
+      DEC_TICK(16);
+      // ---- K: x += gath; a = LN1 of the next layer (or dec_ln)
+      {
+        const float* ng = (l + 1 < A.layers) ? A.layer[l + 1].ln1_g : A.dec_ln_g;
+        const float* nb = (l + 1 < A.layers) ? A.layer[l + 1].ln1_b : A.dec_ln_b;
+        const int i = warp;
+        float v[8];
+        const float4 x0 = *reinterpret_cast<const float4*>(x + i * D + lane * 8), x1 = *reinterpret_cast<const float4*>(x + i * D + lane * 8 + 4);
+        const float4 g0 = *reinterpret_cast<const float4*>(gath + i * D + lane * 8), g1 = *reinterpret_cast<const float4*>(gath + i * D + lane * 8 + 4);
+        v[0] = x0.x + g0.x; v[1] = x0.y + g0.y; v[2] = x0.z + g0.z; v[3] = x0.w + g0.w;
+        v[4] = x1.x + g1.x; v[5] = x1.y + g1.y; v[6] = x1.z + g1.z; v[7] = x1.w + g1.w;
+        st_f32x8(x + i * D + lane * 8, v);
+        ln8(v, ng, nb, lane);
+        st_bf16x8(a + i * lda + lane * 8, v);
+      }
+      __syncthreads();
+      DEC_TICK(17);
+    }
+    // ---- heads: dec_head | lm_head slices -> logits (all CTAs)
+    {
+      const int nth = 2 * A.Vp / 8;
+      const int t0 = rank * nth / CS, t1 = (rank + 1) * nth / CS;
+      cta_gemm(A.wheads, D, a, lda, t1 - t0, [&](int i) { return t0 + i; }, part,
+               [&](int row, int col, float v0, float v1) {
+                 const float2 v = make_float2(v0 + __ldg(A.bheads + col), v1 + __ldg(A.bheads + col + 1));
+#pragma unroll
+                 for (int d = 0; d < CS; ++d) *reinterpret_cast<float2*>(r_logits[d] + row * 2 * A.Vp + col) = v;
+               });
+    }
+    DEC_TICK(18);
+    csync();
+    DEC_TICK(19);
+    // ---- token selection, one warp per line, replicated in every CTA (model.py:480-537)
+    {
+      const int i = warp, b = b0 + i;
+      if (!st->finished[i]) {
+        const KiriDecodeParams& p = A.p;
+        const float* dec = logits + i * 2 * A.Vp;
+        const float* lm = dec + A.Vp;
+        const int Vd = A.Vd;
+        const float lse_d = warp_lse_s(dec, Vd, lane);
+        const float lse_l = p.lm_alpha != 0.f ? warp_lse_s(lm, Vd, lane) : 0.f;
+        const int n = st->n_tok[i];                       // ids so far, BOS included (== step + 1)
+        int pid[8]; float pam[8]; int np = 0;
+        const int cur_len = n - 1, tl = st->target[i];
+        if (tl > 0) {
+          int half = __double2int_rz(__dmul_rn(static_cast<double>(tl), 0.5));
+          if (half < 1) half = 1;
+          const int min_len = p.eos_bias_until_len < half ? p.eos_bias_until_len : half;
+          if (cur_len < min_len) { pid[np] = kTokEOS; pam[np++] = p.eos_bias; }
+          else if (cur_len >= tl) { pid[np] = kTokEOS; pam[np++] = -p.eos_boost; }
+        } else if (cur_len < p.eos_bias_until_len) { pid[np] = kTokEOS; pam[np++] = p.eos_bias; }
+        // hist[k] = k-th most recent id (k = 0 newest); entries beyond the sequence hold distinct negatives
+        const int s1 = st->hist[i][0], s2 = st->hist[i][1], s3 = st->hist[i][2];
+        const int s4 = st->hist[i][3], s5 = st->hist[i][4], s6 = st->hist[i][5];
+        if (n >= 4 && s1 == s2 && s2 == s3) { pid[np] = s1; pam[np++] = p.rep_last; }
+        if (n >= 4 && s2 == s4 && s1 == s3) {
+          pid[np] = s1; pam[np++] = p.rep_bigram;
+          pid[np] = s2; pam[np++] = p.rep_bigram;
+        }
+        if (n >= 4 && s1 == s3 && s2 == s4) { pid[np] = s1; pam[np++] = p.rep_bigram; }
+        if (n >= 6 && s3 == s6 && s2 == s5 && s1 == s4) {
+          pid[np] = s1; pam[np++] = p.rep_trigram;
+          pid[np] = s2; pam[np++] = p.rep_trigram;
+          pid[np] = s3; pam[np++] = p.rep_trigram;
+        }
+        auto fused = [&](int v) -> float {
+          float lp = dec[v] - lse_d;
+          if (p.lm_alpha != 0.f) lp += p.lm_alpha * (lm[v] - lse_l);
+          for (int k = 0; k < np; ++k)
+            if (pid[k] == v) lp -= pam[k];
+          if (v == p.unk_id) lp -= p.unk_penalty;
+          return lp;
+        };
+        float best = -INFINITY;
+        int bid = 0x7fffffff;
+        for (int v = lane; v < Vd; v += 32) {
+          const float val = p.select_raw ? dec[v] : fused(v);
+          if (val > best) { best = val; bid = v; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bid, o);
+          if (ob > best || (ob == best && oi < bid)) { best = ob; bid = oi; }
+        }
+        if (A.forced) bid = A.forced[static_cast<size_t>(b) * A.Lmax + step];
+        __syncwarp();
+        if (lane == 0) {
+          const float lp = fused(bid);
+#pragma unroll
+          for (int k = 7; k > 0; --k) st->hist[i][k] = st->hist[i][k - 1];
+          st->hist[i][0] = bid;
+          st->n_tok[i] = n + 1;
+          st->cur_tok[i] = bid;
+          const bool done = (bid == kTokEOS) || (step + 1 >= st->max_steps[i]);
+          if (done) st->finished[i] = 1;
+          if (rank == 0) {
+            A.ids[static_cast<size_t>(b) * A.Lmax + step] = bid;
+            A.n_out[b] = step + 1;
+            A.sum_logp[b] += lp;
+            if (A.step_logp) A.step_logp[static_cast<size_t>(b) * A.Lmax + step] = lp;
+            if (A.step_prob) A.step_prob[static_cast<size_t>(b) * A.Lmax + step] = expf(dec[bid] - lse_d);
+          }
+        }
+      }
+    }
+    // the next heads-GEMM writes `logits` remotely only after 18 more cluster barriers, and
+    // `st` is CTA-local: a block barrier is enough here
+    __syncthreads();
+    DEC_TICK(20);
+  }
+  if (rank == 0 && threadIdx.x == 0 && A.steps_max) atomicMax(A.steps_max, step);
+  csync();                                          // no CTA may exit while peers can still write its smem
+}
+
+// ---------------------------------------------------------------- host side
+struct FusedPacked {
+  void* blob = nullptr;
+  FusedArgs args;
+};
+
+static size_t packed_words(int N, int K) { return static_cast<size_t>(N) * K / 2; }
+
+int fused_decoder_build(KiriHandle* h) {
+  const KiriDims& d = h->d;
+  const KiriWeights& w = h->w;
+  const int D = d.dec_dim, FF = d.dec_ff, L = d.dec_layers;
+  const int Vp = (d.dec_vocab + 15) / 16 * 16;
+  KIRI_REQUIRE(D == 256 && d.dec_heads == kHeads, "fused decoder: DEC_DIM must be 256 with 8 heads");
+  KIRI_REQUIRE(FF % 256 == 0 && FF <= 2048, "fused decoder: DEC_FF=%d must be a multiple of 256 (<= 2048)", FF);
+  size_t words = 0;
+  const size_t per_layer = packed_words(3 * D, D) + 3 * packed_words(D, D) + 2 * packed_words(FF, D);
+  words = per_layer * L + packed_words(2 * Vp, D);
+  FusedPacked* fp = new FusedPacked;
+  KIRI_CHECK_CUDA(cudaMalloc(&fp->blob, words * 4));
+  uint32_t* cur = reinterpret_cast<uint32_t*>(fp->blob);
+  auto pack = [&](const void* src, int N, int K) -> const uint4* {
+    uint32_t* dst = cur;
+    cur += packed_words(N, K);
+    pack_frag_kernel<<<148, 256>>>(reinterpret_cast<const __nv_bfloat16*>(src), N, K, dst);
+    return reinterpret_cast<const uint4*>(dst);
+  };
+  FusedArgs& a = fp->args;
+  memset(&a, 0, sizeof(a));
+  for (int l = 0; l < L; ++l) {
+    const KiriDecLayerWeights& s = w.dec[l];
+    FusedLayer& t = a.layer[l];
+    t.wqkv = pack(s.wqkv, 3 * D, D); t.wo = pack(s.wo, D, D); t.wcq = pack(s.wcq, D, D);
+    t.wco = pack(s.wco, D, D); t.w1 = pack(s.w1, FF, D); t.w2 = pack(s.w2, D, FF);
+    t.bqkv = s.bqkv; t.bo = s.bo; t.bcq = s.bcq; t.bco = s.bco; t.b1 = s.b1; t.b2 = s.b2;
+    t.ln1_g = s.ln1_g; t.ln1_b = s.ln1_b; t.ln2_g = s.ln2_g; t.ln2_b = s.ln2_b; t.ln3_g = s.ln3_g; t.ln3_b = s.ln3_b;
+  }
+  a.wheads = pack(w.heads_w, 2 * Vp, D);
+  a.bheads = w.heads_b;
+  a.dec_ln_g = w.dec_ln_g; a.dec_ln_b = w.dec_ln_b; a.emb = w.dec_emb; a.pe = w.dec_pe;
+  a.layers = L; a.ff = FF; a.Vd = d.dec_vocab; a.Vp = Vp; a.has_pos = d.has_dec_pos;
+  KIRI_CHECK_CUDA(cudaGetLastError());
+  KIRI_CHECK_CUDA(cudaDeviceSynchronize());
+  h->fused = fp;
+  return 0;
+}
+
+void fused_decoder_free(KiriHandle* h) {
+  FusedPacked* fp = reinterpret_cast<FusedPacked*>(h->fused);
+  if (!fp) return;
+  cudaFree(fp->blob);
+  delete fp;
+  h->fused = nullptr;
+}
+
+template <int CS>
+static int launch_fused(const FusedArgs& a, int n_clusters, cudaStream_t stream) {
+  const FusedSmem L = fused_smem_plan(a.ff, a.Vp, CS);
+  auto kern = dec_fused_kernel<CS>;
+  static int configured = 0;
+  if (configured < L.total) {
+    KIRI_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    configured = L.total;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(n_clusters * CS);
+  cfg.blockDim = dim3(kFThreads);
+  cfg.dynamicSmemBytes = L.total;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  KIRI_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+  return 0;
+}
+
+// Runs the whole greedy decode; crosskv must already hold the cross K/V rows.
+int fused_decoder_run(KiriHandle* h, const __nv_bfloat16* crosskv, int crosskv_ld, const int* mem_row0, const int* mem_len,
+                      int T, __nv_bfloat16* self_k, __nv_bfloat16* self_v, const int* len_est, const int* forced, int B,
+                      int Lmax, const KiriDecodeParams* p, int* ids, int* n_out, float* sum_logp, float* step_logp,
+                      float* step_prob, int* steps_max_dev, int cluster_size, cudaStream_t stream) {
+  FusedPacked* fp = reinterpret_cast<FusedPacked*>(h->fused);
+  KIRI_REQUIRE(fp, "fused decoder: handle was created without decoder weights");
+  FusedArgs a = fp->args;
+  a.crosskv = crosskv; a.crosskv_ld = crosskv_ld; a.mem_row0 = mem_row0; a.mem_len = mem_len; a.T = T;
+  a.self_k = self_k; a.self_v = self_v; a.len_est = len_est; a.forced = forced; a.B = B; a.Lmax = Lmax; a.p = *p;
+  a.ids = ids; a.n_out = n_out; a.sum_logp = sum_logp; a.step_logp = step_logp; a.step_prob = step_prob;
+  a.steps_max = steps_max_dev;
+  a.timing = getenv("KIRI_DEC_TIMING") != nullptr;
+  const int n_clusters = (B + kFL - 1) / kFL;
+  switch (cluster_size) {
+    case 1: return launch_fused<1>(a, n_clusters, stream);
+    case 2: return launch_fused<2>(a, n_clusters, stream);
+    case 4: return launch_fused<4>(a, n_clusters, stream);
+    case 8: return launch_fused<8>(a, n_clusters, stream);
+    default: KIRI_REQUIRE(false, "fused decoder: cluster size %d not in {1,2,4,8}", cluster_size);
+  }
+}
+
+}  // namespace kiri
+
+// Debug: cycles per decode phase of cluster 0 / CTA 0 accumulated since the last call (KIRI_DEC_TIMING=1).
+extern "C" int kiri_debug_decode_timing(long long* out_host, int n) {
+  long long buf[32];
+  if (cudaDeviceSynchronize() != cudaSuccess) return -2;
+  if (cudaMemcpyFromSymbol(buf, kiri::g_dec_prof, sizeof(buf)) != cudaSuccess) return -2;
+  for (int i = 0; i < n && i < 32; ++i) out_host[i] = buf[i];
+  long long zero[32] = {0};
+  if (cudaMemcpyToSymbol(kiri::g_dec_prof, zero, sizeof(zero)) != cudaSuccess) return -2;
+  return 0;
+}

@@ -9,12 +9,21 @@ struct KiriHandle {
   KiriWeights w;
   float conv1_w[48 * 9];
   float conv1_b[48];
+  void* fused;          // fragment-packed decoder weights of the fused decode kernel (decoder_fused.cu)
 };
 
 namespace kiri {
 // out[M,N] = epilogue(a[M,K] @ w[N,K]^T + bias) on the tcgen05 kernel (api.cu)
 int gemm_call(const void* a, const void* w, const float* bias, int M, int N, int K, int epi, void* out,
               const float* resid, const float* ln_g, const float* ln_b, void* out2, cudaStream_t stream);
+
+// decoder_fused.cu: whole-decode persistent cluster kernel
+int fused_decoder_build(KiriHandle* h);
+void fused_decoder_free(KiriHandle* h);
+int fused_decoder_run(KiriHandle* h, const __nv_bfloat16* crosskv, int crosskv_ld, const int* mem_row0, const int* mem_len,
+                      int T, __nv_bfloat16* self_k, __nv_bfloat16* self_v, const int* len_est, const int* forced, int B,
+                      int Lmax, const KiriDecodeParams* p, int* ids, int* n_out, float* sum_logp, float* step_logp,
+                      float* step_prob, int* steps_max_dev, int cluster_size, cudaStream_t stream);
 }  // namespace kiri
 
 namespace kiri {

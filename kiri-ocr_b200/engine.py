@@ -253,7 +253,7 @@ class BatchedRecognizer:
                                                C.byref(p), ws.data_ptr(), need, ids.data_ptr(), n_out.data_ptr(),
                                                sum_lp.data_ptr(), _lib.ptr(slp), _lib.ptr(spr), _lib.ptr(forced),
                                                C.byref(steps), poll_every, _lib.stream_ptr()), "kiri_decode_greedy")
-        self.launches += 3 + steps.value * (3 + 8 * self.pw.dec_layers)
+        self.launches += 2          # cross-K/V GEMM + the persistent decode kernel
         return ids, n_out, sum_lp, slp, spr, steps.value
 
     # ------------------------------------------------------------------ device-resident stepping (bench)

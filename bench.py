@@ -277,10 +277,10 @@ def run_ours(args):
     # ---------------- per-stage profile + roofline of the dominant kernel ----------------
     pk = peaks()
     for _ in range(2):
-        eng.step_resident(prep, "ctc")
+        eng.step_resident(prep, method)
     torch.cuda.synchronize()
     reps = 5
-    prof = eng.profile(lambda: [eng.step_resident(prep, "ctc") for _ in range(reps)])
+    prof = eng.profile(lambda: [eng.step_resident(prep, method) for _ in range(reps)])
     widths = {g["Wb"]: g["n"] for g in prep["groups"]}
     total_ms = sum(v[0] for v in prof.values()) or 1.0
     stages = {}
@@ -308,6 +308,24 @@ def run_ours(args):
     whole = sum(flops_per_line(wb) * n for wb, n in widths.items()) * world
     tensor_frac = whole * args.steps / (ms_total / 1e3) / 1e12 / pk["bf16_tflops_sustained"] / world
 
+    # ---------------- the other decode method of the metric, device-resident, a few steps ----------------
+    other = None
+    if world == 1:
+        om = "decoder" if method == "ctc" else "ctc"
+        for _ in range(2):
+            eng.step_resident(prep, om)
+        torch.cuda.synchronize()
+        oev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+        for a, b in oev:
+            flush.zero_()
+            a.record()
+            eng.step_resident(prep, om)
+            b.record()
+        torch.cuda.synchronize()
+        oms = sum(a.elapsed_time(b) for a, b in oev) / len(oev)
+        other = {"decode_method": "accurate" if om == "decoder" else "fast", "value": BATCH / (oms / 1e3),
+                 "unit": "lines/s", "ms_per_step": oms, "steps": len(oev)}
+
     # ---------------- CPU baseline (oracle port of the reference algorithm) ----------------
     cb_v, cb_n, cb_dt = cpu_baseline(cfg, tok, sd, crops, method, budget_s=12.0 if method == "ctc" else 20.0)
     out = {
@@ -320,7 +338,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "lines/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_dt / args.steps * 1e3},
         "gpu_launches": int(launches), "clocks": clocks,
-        "roofline": roof, "whole_step_tensor_frac": tensor_frac, "stages": stages,
+        "roofline": roof, "whole_step_tensor_frac": tensor_frac, "stages": stages, "other_method": other,
         "cpu_baseline": {"value": cb_v, "unit": "lines/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{cb_n} lines of the same workload in {cb_dt:.1f} s, one line at a time, fp32 oracle"},
     }
@@ -337,7 +355,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--method", default="fast", choices=["fast", "accurate"])
     ap.add_argument("--width-mode", default="bucketed", choices=["parity", "bucketed", "masked"])
-    ap.add_argument("--stem-chunk", type=int, default=16)
+    ap.add_argument("--stem-chunk", type=int, default=64)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

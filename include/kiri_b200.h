@@ -198,6 +198,23 @@ int kiri_encode(KiriHandle* h, const uint8_t* planes_u8, int B, int Wb, int stem
                 size_t workspace_bytes, float* mem_f32, void* mem_bf16, float* logits, float* tok_f32,
                 const int* kv_len, cudaStream_t stream);
 
+/* The same for several width groups at once (bucketed mode): every group runs
+ * its own stem, but the encoder layers and the CTC head run ONCE over the concatenation of all
+ * groups' tokens (a GEMM does not see line boundaries), so small groups do not pay a launch and a
+ * partial wave per layer.  `groups` is a HOST array.  Outputs are token-major and concatenated in
+ * group order: group g owns rows [sum_{i<g} n_lines_i * Wb_i / 4, ...).  kv_len (nullable) has one
+ * entry per line in the same order. */
+typedef struct {
+  const uint8_t* planes; /* device: [n_lines, img_h, Wb] uint8 */
+  int32_t n_lines;
+  int32_t Wb;
+} KiriGroup;
+size_t kiri_encode_multi_workspace_bytes(const KiriHandle* h, const KiriGroup* groups_host, int n_groups,
+                                         int stem_chunk);
+int kiri_encode_multi(KiriHandle* h, const KiriGroup* groups_host, int n_groups, int stem_chunk, void* workspace,
+                      size_t workspace_bytes, float* mem_f32, void* mem_bf16, float* logits, float* tok_f32,
+                      const int* kv_len, cudaStream_t stream);
+
 /* ---------------------------------------------------------------- greedy attention decoder
  * Replaces beam_decode_one_batched at BEAM=1 (kiri_ocr/model.py:390-600 via core.py:560-568)
  * and the token rule of greedy_decode_streaming (model.py:779-946), batched over lines with
@@ -226,6 +243,14 @@ int kiri_decode_greedy(KiriHandle* h, const void* mem_bf16, const int* len_est, 
                        const KiriDecodeParams* p, void* workspace, size_t workspace_bytes, int* ids,
                        int* n_out, float* sum_logp, float* step_logp, float* step_prob,
                        const int* forced_ids, int* steps_run_host, int poll_every, cudaStream_t stream);
+/* The same over the concatenated token stream of kiri_encode_multi: line b attends to the memory
+ * rows [mem_row0[b], mem_row0[b] + mem_len[b]) of mem_bf16 [M_total, D] (device int arrays). */
+size_t kiri_decode_multi_workspace_bytes(const KiriHandle* h, int B, long long M_total, int Lmax);
+int kiri_decode_greedy_multi(KiriHandle* h, const void* mem_bf16, long long M_total, const int* mem_row0,
+                             const int* mem_len, const int* len_est, int B, int Lmax, const KiriDecodeParams* p,
+                             void* workspace, size_t workspace_bytes, int* ids, int* n_out, float* sum_logp,
+                             float* step_logp, float* step_prob, const int* forced_ids, int* steps_run_host,
+                             cudaStream_t stream);
 
 #ifdef __cplusplus
 }

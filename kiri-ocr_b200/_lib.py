@@ -53,6 +53,10 @@ class KiriWeights(C.Structure):
                 + [(n, vp) for n in ("dec_ln_g", "dec_ln_b", "heads_w", "heads_b")])
 
 
+class KiriGroup(C.Structure):
+    _fields_ = [("planes", C.c_void_p), ("n_lines", C.c_int32), ("Wb", C.c_int32)]
+
+
 class KiriDecodeParams(C.Structure):
     _fields_ = [("lm_alpha", C.c_float), ("eos_bias", C.c_float), ("eos_boost", C.c_float),
                 ("eos_bias_until_len", C.c_int32), ("rep_last", C.c_float), ("rep_bigram", C.c_float),
@@ -81,7 +85,12 @@ _SIGS = {
     "kiri_destroy": (None, [vp]),
     "kiri_encode_workspace_bytes": (C.c_size_t, [vp, C.c_int, C.c_int, C.c_int]),
     "kiri_encode": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, vp, vp, vp, vp, vp, vp]),
+    "kiri_encode_multi_workspace_bytes": (C.c_size_t, [vp, C.POINTER(KiriGroup), C.c_int, C.c_int]),
+    "kiri_encode_multi": (C.c_int, [vp, C.POINTER(KiriGroup), C.c_int, C.c_int, vp, C.c_size_t, vp, vp, vp, vp, vp, vp]),
     "kiri_decode_workspace_bytes": (C.c_size_t, [vp, C.c_int, C.c_int, C.c_int]),
+    "kiri_decode_multi_workspace_bytes": (C.c_size_t, [vp, C.c_int, C.c_longlong, C.c_int]),
+    "kiri_decode_greedy_multi": (C.c_int, [vp, vp, C.c_longlong, vp, vp, vp, C.c_int, C.c_int, C.POINTER(KiriDecodeParams),
+                                           vp, C.c_size_t, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int), vp]),
     "kiri_decode_greedy": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(KiriDecodeParams), vp,
                                      C.c_size_t, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int), C.c_int, vp]),
 }

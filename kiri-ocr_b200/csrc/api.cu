@@ -2,6 +2,7 @@
 // stem + encoder + CTC-head pipeline (kiri_encode).  See include/kiri_b200.h.
 #include <cstdarg>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -180,79 +181,123 @@ extern "C" void kiri_destroy(KiriHandle* h) {
 
 namespace {
 struct EncodeWs {          // byte offsets into the caller's workspace
-  size_t act1, act2, act3, act4, x, a, qkv, o, hbuf, logits_pad, total;
+  size_t act1, act2, act3, act4, x, a, qkv, o, hbuf, total;
+  long long m_total;       // tokens of all groups
 };
 inline size_t al(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
 
-EncodeWs plan_encode(const KiriDims& d, int B, int Wb, int stem_chunk) {
+// Workspace of a multi-group encode: the stem buffers are sized for the largest sub-batch of any
+// group, the token-stream buffers for the concatenation of all groups.
+EncodeWs plan_encode(const KiriDims& d, const KiriGroup* groups, int n_groups, int stem_chunk) {
   const int H = d.img_h;
-  const int sc = (stem_chunk <= 0 || stem_chunk > B) ? B : stem_chunk;
-  const size_t T = Wb / 4, M = static_cast<size_t>(B) * T;
+  size_t a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+  long long M = 0;
+  for (int g = 0; g < n_groups; ++g) {
+    const int B = groups[g].n_lines, Wb = groups[g].Wb;
+    const int sc = (stem_chunk <= 0 || stem_chunk > B) ? B : stem_chunk;
+    const size_t T = Wb / 4;
+    a1 = std::max(a1, static_cast<size_t>(sc) * H * Wb * 64 * 2);
+    a2 = std::max(a2, static_cast<size_t>(sc) * (H / 2) * (Wb / 2) * 96 * 2);
+    a3 = std::max(a3, static_cast<size_t>(sc) * (H / 4) * (Wb / 4) * 160 * 2);
+    a4 = std::max(a4, static_cast<size_t>(B) * (H / 8) * T * 256 * 2);
+    M += static_cast<long long>(B) * T;
+  }
   EncodeWs w;
   size_t off = 0;
-  w.act1 = off; off += al(static_cast<size_t>(sc) * H * Wb * 64 * 2);
-  w.act2 = off; off += al(static_cast<size_t>(sc) * (H / 2) * (Wb / 2) * 96 * 2);
-  w.act3 = off; off += al(static_cast<size_t>(sc) * (H / 4) * (Wb / 4) * 160 * 2);
-  w.act4 = off; off += al(static_cast<size_t>(B) * (H / 8) * T * 256 * 2);
-  w.x = off;    off += al(M * 256 * 4);
-  w.a = off;    off += al(M * 256 * 2);
-  w.qkv = off;  off += al(M * 768 * 2);
-  w.o = off;    off += al(M * 256 * 2);
-  w.hbuf = off; off += al(M * static_cast<size_t>(d.enc_ff) * 2);
-  w.logits_pad = off;
+  w.act1 = off; off += al(a1);
+  w.act2 = off; off += al(a2);
+  w.act3 = off; off += al(a3);
+  w.act4 = off; off += al(a4);
+  w.x = off;    off += al(static_cast<size_t>(M) * 256 * 4);
+  w.a = off;    off += al(static_cast<size_t>(M) * 256 * 2);
+  w.qkv = off;  off += al(static_cast<size_t>(M) * 768 * 2);
+  w.o = off;    off += al(static_cast<size_t>(M) * 256 * 2);
+  w.hbuf = off; off += al(static_cast<size_t>(M) * static_cast<size_t>(d.enc_ff) * 2);
   w.total = off;
+  w.m_total = M;
   return w;
 }
 }  // namespace
 
 extern "C" size_t kiri_encode_workspace_bytes(const KiriHandle* h, int B, int Wb, int stem_chunk) {
   if (!h || B <= 0 || Wb <= 0) return 0;
-  return plan_encode(h->d, B, Wb, stem_chunk).total;
+  KiriGroup g = {nullptr, B, Wb};
+  return plan_encode(h->d, &g, 1, stem_chunk).total;
+}
+extern "C" size_t kiri_encode_multi_workspace_bytes(const KiriHandle* h, const KiriGroup* groups, int n_groups,
+                                                    int stem_chunk) {
+  if (!h || !groups || n_groups <= 0) return 0;
+  return plan_encode(h->d, groups, n_groups, stem_chunk).total;
 }
 
 extern "C" int kiri_encode(KiriHandle* h, const uint8_t* planes_u8, int B, int Wb, int stem_chunk,
                            void* workspace, size_t workspace_bytes, float* mem_f32, void* mem_bf16,
                            float* logits, float* tok_f32, const int* kv_len, cudaStream_t stream) {
   KIRI_REQUIRE(h && planes_u8 && workspace, "kiri_encode: null pointer");
-  KIRI_REQUIRE(B > 0 && Wb > 0 && Wb % 128 == 0 && Wb / 4 <= h->d.max_t,
-               "kiri_encode: batch width %d must be a positive multiple of 128 and <= %d", Wb, h->d.max_t * 4);
+  KiriGroup g = {planes_u8, B, Wb};
+  return kiri_encode_multi(h, &g, 1, stem_chunk, workspace, workspace_bytes, mem_f32, mem_bf16, logits, tok_f32, kv_len,
+                           stream);
+}
+
+extern "C" int kiri_encode_multi(KiriHandle* h, const KiriGroup* groups, int n_groups, int stem_chunk,
+                                 void* workspace, size_t workspace_bytes, float* mem_f32, void* mem_bf16,
+                                 float* logits, float* tok_f32, const int* kv_len, cudaStream_t stream) {
+  KIRI_REQUIRE(h && groups && workspace && n_groups > 0, "kiri_encode_multi: null pointer");
   const KiriDims& d = h->d;
   const KiriWeights& w = h->w;
-  const EncodeWs ws = plan_encode(d, B, Wb, stem_chunk);
-  KIRI_REQUIRE(workspace_bytes >= ws.total, "kiri_encode: workspace of %zu bytes given, %zu needed", workspace_bytes, ws.total);
-  uint8_t* base = reinterpret_cast<uint8_t*>(workspace);
-  const int H = d.img_h, T = Wb / 4, D = d.enc_dim;
-  const int M = B * T;
-  const int sc = (stem_chunk <= 0 || stem_chunk > B) ? B : stem_chunk;
-
-  // ---- stem, in sub-batches whose activations stay L2-resident
-  for (int b0 = 0; b0 < B; b0 += sc) {
-    const int nb = (B - b0) < sc ? (B - b0) : sc;
-    { ProfScope ps(PS_CONV1, stream);
-      KIRI_TRY(kiri_conv1(planes_u8 + static_cast<size_t>(b0) * H * Wb, w.conv1_w_host, w.conv1_b_host, nb, H, Wb,
-                          base + ws.act1, stream)); }
-    { ProfScope ps(PS_CONV2, stream);
-      KIRI_TRY(conv_call(base + ws.act1, w.conv2_w, w.conv2_b, nb, H, Wb, 64, 96, 2, 2, base + ws.act2, stream)); }
-    { ProfScope ps(PS_CONV3, stream);
-      KIRI_TRY(conv_call(base + ws.act2, w.conv3_w, w.conv3_b, nb, H / 2, Wb / 2, 96, 160, 2, 2, base + ws.act3, stream)); }
-    { ProfScope ps(PS_CONV4, stream);
-      KIRI_TRY(conv_call(base + ws.act3, w.conv4_w, w.conv4_b, nb, H / 4, Wb / 4, 160, 256, 2, 1,
-                         base + ws.act4 + static_cast<size_t>(b0) * (H / 8) * T * 256 * 2, stream)); }
+  for (int g = 0; g < n_groups; ++g) {
+    KIRI_REQUIRE(groups[g].planes && groups[g].n_lines > 0, "kiri_encode_multi: group %d is empty", g);
+    KIRI_REQUIRE(groups[g].Wb > 0 && groups[g].Wb % 128 == 0 && groups[g].Wb / 4 <= d.max_t,
+                 "kiri_encode: batch width %d must be a positive multiple of 128 and <= %d", groups[g].Wb, d.max_t * 4);
   }
+  const EncodeWs ws = plan_encode(d, groups, n_groups, stem_chunk);
+  KIRI_REQUIRE(workspace_bytes >= ws.total, "kiri_encode: workspace of %zu bytes given, %zu needed", workspace_bytes, ws.total);
+  KIRI_REQUIRE(ws.m_total < (1ll << 31), "kiri_encode: too many tokens");
+  uint8_t* base = reinterpret_cast<uint8_t*>(workspace);
+  const int H = d.img_h, D = d.enc_dim;
+  const int M = static_cast<int>(ws.m_total);
   float* x = reinterpret_cast<float*>(base + ws.x);
-  void* a = base + ws.a;
-  // ---- pool + positional table + enc_ln_in (+ norm1 of layer 0)
-  { ProfScope ps(PS_POOL_LN, stream);
-    KIRI_TRY(kiri_pool_pos_ln(base + ws.act4, w.pos_table, B, H / 8, T, D, w.enc_ln_in_g, w.enc_ln_in_b,
-                              w.enc[0].ln1_g, w.enc[0].ln1_b, x, a, stream)); }
+  uint8_t* a = base + ws.a;
+
+  // ---- per group: stem (in sub-batches), then pool + positional table + enc_ln_in (+ norm1 of layer 0)
+  // written at the group's row offset of the concatenated token stream
+  size_t row0 = 0;
+  for (int g = 0; g < n_groups; ++g) {
+    const int B = groups[g].n_lines, Wb = groups[g].Wb, T = Wb / 4;
+    const int sc = (stem_chunk <= 0 || stem_chunk > B) ? B : stem_chunk;
+    for (int b0 = 0; b0 < B; b0 += sc) {
+      const int nb = (B - b0) < sc ? (B - b0) : sc;
+      { ProfScope ps(PS_CONV1, stream);
+        KIRI_TRY(kiri_conv1(groups[g].planes + static_cast<size_t>(b0) * H * Wb, w.conv1_w_host, w.conv1_b_host, nb, H, Wb,
+                            base + ws.act1, stream)); }
+      { ProfScope ps(PS_CONV2, stream);
+        KIRI_TRY(conv_call(base + ws.act1, w.conv2_w, w.conv2_b, nb, H, Wb, 64, 96, 2, 2, base + ws.act2, stream)); }
+      { ProfScope ps(PS_CONV3, stream);
+        KIRI_TRY(conv_call(base + ws.act2, w.conv3_w, w.conv3_b, nb, H / 2, Wb / 2, 96, 160, 2, 2, base + ws.act3, stream)); }
+      { ProfScope ps(PS_CONV4, stream);
+        KIRI_TRY(conv_call(base + ws.act3, w.conv4_w, w.conv4_b, nb, H / 4, Wb / 4, 160, 256, 2, 1,
+                           base + ws.act4 + static_cast<size_t>(b0) * (H / 8) * T * 256 * 2, stream)); }
+    }
+    { ProfScope ps(PS_POOL_LN, stream);
+      KIRI_TRY(kiri_pool_pos_ln(base + ws.act4, w.pos_table, B, H / 8, T, D, w.enc_ln_in_g, w.enc_ln_in_b,
+                                w.enc[0].ln1_g, w.enc[0].ln1_b, x + row0 * D, a + row0 * D * 2, stream)); }
+    row0 += static_cast<size_t>(B) * T;
+  }
   if (tok_f32) KIRI_CHECK_CUDA(cudaMemcpyAsync(tok_f32, x, static_cast<size_t>(M) * D * 4, cudaMemcpyDeviceToDevice, stream));
-  // ---- encoder layers
+  // ---- encoder layers over the concatenated token stream (the GEMMs do not see line boundaries)
   for (int l = 0; l < d.enc_layers; ++l) {
     const KiriEncLayerWeights& lw = w.enc[l];
     { ProfScope ps(PS_QKV, stream);
       KIRI_TRY(gemm_call(a, lw.wqkv, lw.bqkv, M, 3 * D, D, EPI_BIAS_BF16, base + ws.qkv, nullptr, nullptr, nullptr, nullptr, stream)); }
     { ProfScope ps(PS_ATTN, stream);
-      KIRI_TRY(kiri_encoder_attention(base + ws.qkv, base + ws.o, B, T, d.enc_heads, D, kv_len, stream)); }
+      size_t r0 = 0, l0 = 0;
+      for (int g = 0; g < n_groups; ++g) {
+        const int B = groups[g].n_lines, T = groups[g].Wb / 4;
+        KIRI_TRY(kiri_encoder_attention(base + ws.qkv + r0 * 3 * D * 2, base + ws.o + r0 * D * 2, B, T, d.enc_heads, D,
+                                        kv_len ? kv_len + l0 : nullptr, stream));
+        r0 += static_cast<size_t>(B) * T;
+        l0 += B;
+      } }
     // x += out_proj(o); a = norm2(x)
     { ProfScope ps(PS_OUTPROJ, stream);
       KIRI_TRY(gemm_call(base + ws.o, lw.wo, lw.bo, M, D, D, EPI_BIAS_RESID_LN, x, x, lw.ln2_g, lw.ln2_b, a, stream)); }

@@ -453,3 +453,49 @@ extern "C" int kiri_decode_greedy(KiriHandle* h, const void* mem_bf16, const int
   if (steps_run_host) *steps_run_host = step;
   return 0;
 }
+
+// ------------------------------------------------------------------ multi-group (concatenated token stream)
+extern "C" size_t kiri_decode_multi_workspace_bytes(const KiriHandle* h, int B, long long M_total, int Lmax) {
+  if (!h || B <= 0 || M_total <= 0 || Lmax <= 0) return 0;
+  const size_t L = h->d.dec_layers, D = h->d.dec_dim;
+  return al256(static_cast<size_t>(M_total) * L * 2 * D * 2) + 2 * al256(L * B * Lmax * D * 2) + 256;
+}
+
+extern "C" int kiri_decode_greedy_multi(KiriHandle* h, const void* mem_bf16, long long M_total, const int* mem_row0,
+                                        const int* mem_len, const int* len_est, int B, int Lmax,
+                                        const KiriDecodeParams* p, void* workspace, size_t workspace_bytes, int* ids,
+                                        int* n_out, float* sum_logp, float* step_logp, float* step_prob,
+                                        const int* forced_ids, int* steps_run_host, cudaStream_t stream) {
+  KIRI_REQUIRE(h && mem_bf16 && mem_row0 && mem_len && len_est && p && workspace && ids && n_out && sum_logp,
+               "kiri_decode_greedy_multi: null pointer");
+  KIRI_REQUIRE(B > 0 && M_total > 0 && M_total < (1ll << 31) && Lmax > 0 && Lmax <= h->d.max_pos && Lmax <= 544,
+               "kiri_decode_greedy_multi: bad sizes B=%d M=%lld Lmax=%d", B, M_total, Lmax);
+  const KiriDims& d = h->d;
+  const KiriWeights& w = h->w;
+  const size_t L = d.dec_layers, D = d.dec_dim;
+  KIRI_REQUIRE(workspace_bytes >= kiri_decode_multi_workspace_bytes(h, B, M_total, Lmax),
+               "kiri_decode_greedy_multi: workspace too small");
+  uint8_t* base = reinterpret_cast<uint8_t*>(workspace);
+  __nv_bfloat16* crosskv = reinterpret_cast<__nv_bfloat16*>(base);
+  size_t off = al256(static_cast<size_t>(M_total) * L * 2 * D * 2);
+  __nv_bfloat16* self_k = reinterpret_cast<__nv_bfloat16*>(base + off); off += al256(L * B * Lmax * D * 2);
+  __nv_bfloat16* self_v = reinterpret_cast<__nv_bfloat16*>(base + off); off += al256(L * B * Lmax * D * 2);
+  int* steps_dev = reinterpret_cast<int*>(base + off);
+  { ProfScope ps(PS_DEC_CROSSKV, stream);
+    KIRI_TRY(gemm_call(mem_bf16, w.crosskv_w, w.crosskv_b, static_cast<int>(M_total), static_cast<int>(L * 2 * D), d.enc_dim,
+                       EPI_BIAS_BF16, crosskv, nullptr, nullptr, nullptr, nullptr, stream)); }
+  KIRI_CHECK_CUDA(cudaMemsetAsync(steps_dev, 0, sizeof(int), stream));
+  int cs = 8;
+  if (const char* e = getenv("KIRI_DEC_CLUSTER")) cs = atoi(e);
+  { ProfScope ps_step(PS_DEC_STEP, stream);
+    KIRI_TRY(fused_decoder_run(h, crosskv, static_cast<int>(L * 2 * D), mem_row0, mem_len, 0, self_k, self_v, len_est,
+                               forced_ids, B, Lmax, p, ids, n_out, sum_logp, step_logp, step_prob, steps_dev, cs, stream)); }
+  if (steps_run_host) {
+    static int* steps_host = nullptr;
+    if (!steps_host) KIRI_CHECK_CUDA(cudaMallocHost(&steps_host, sizeof(int)));
+    KIRI_CHECK_CUDA(cudaMemcpyAsync(steps_host, steps_dev, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    KIRI_CHECK_CUDA(cudaStreamSynchronize(stream));
+    *steps_run_host = *steps_host;
+  }
+  return 0;
+}

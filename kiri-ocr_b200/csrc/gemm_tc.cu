@@ -1,6 +1,7 @@
 // tcgen05/TMEM/TMA implicit-GEMM kernel + host launcher.  See gemm_tc.cuh for the design.
 #include "gemm_tc.cuh"
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
@@ -12,20 +13,27 @@ static constexpr int kTileM = 128;
 // 64-byte rows exist because the stem's channel counts 96 and 160 are multiples of 32 only.
 static constexpr int kAccStride = 256;                  // TMEM columns per accumulator
 static constexpr int kTmemCols = 512;
-static constexpr int kNumThreads = 192;                 // warp0 TMA, warp1 MMA, warps2-5 epilogue
+static constexpr int kEpiWarps = 8;                     // two per TMEM lane quarter (column halves)
+// Epilogue warps take the LOW warp ids: the SM sub-partition arbiter favours the highest warp id, and
+// the single-lane TMA / MMA issuers (warps 8, 9) must never be starved by epilogue arithmetic.
+static constexpr int kTmaWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
+static constexpr int kNumThreads = 64 + kEpiWarps * 32;
 static constexpr int kMaxStages = 8;
-static constexpr int kStageBufBytes = 4096;             // 32 rows x 128 B epilogue staging tile
-static constexpr int kResDepth = 4;                     // residual chunks prefetched per warp
+static constexpr int kBufBytes = 4096;                  // 32 rows x 128 B epilogue staging tile
+static constexpr int kMaxBResident = 128 * 1024;        // weights kept in shared memory when they fit
 
 struct __align__(16) PipeBarriers {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
-  uint64_t res_full[4][kResDepth];   // per epilogue warp: residual chunk landed
+  uint64_t b_full, b_empty;          // resident-B handshake (TMA <-> MMA)
+  uint64_t res_full[kEpiWarps][4];   // per epilogue warp: residual chunk landed
   uint32_t tmem_base;
   uint32_t pad[3];
   float bias[2][256];                // bias slice of the tile being drained, per accumulator
+  float ln_g[256], ln_b[256];
+  float xch[2][2][128];              // LayerNorm partial sums: [stat][column half][tile row]
 };
 
 // 16-byte chunk j of row `lane` inside a 32 x 128 B tile laid out with the 128-byte swizzle that the
@@ -34,19 +42,42 @@ __device__ __forceinline__ uint32_t stg_off(int lane, int j) {
   return static_cast<uint32_t>(lane * 128 + ((j ^ (lane & 7)) << 4));
 }
 
+// erf-GELU with erf(z) ~ tanh(z (a + b z^2 + c z^4)), |err| < 4.1e-5 on the clamped range: ONE MUFU
+// per element (the FFN epilogue is MUFU/issue-bound: 32 K activations per 128 x 256 tile).
+__device__ __forceinline__ float gelu_tanh_erf(float v) {
+  const float u = fminf(fmaxf(v * 0.70710678118654752440f, -4.5f), 4.5f);
+  const float u2 = u * u;
+  float p = fmaf(-0.00181363f, u2, 0.10414107f);
+  p = fmaf(p, u2, 1.12812423f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u * p));
+  const float h = 0.5f * v;
+  return fmaf(h, t, h);
+}
+
 template <int EPI>
 __device__ __forceinline__ float epi_act(float v) {
   if (EPI == EPI_BIAS_SILU_BF16) return silu_fast(v);
-  if (EPI == EPI_BIAS_GELU_BF16) return gelu_erf_fast(v);
+  if (EPI == EPI_BIAS_GELU_BF16) return gelu_tanh_erf(v);
   return v;
 }
 
-template <int KC, int CPS, int NSEG, int EPI>
+// Role-level cycle accounting of CTA 0 (KIRI_GEMM_TIMING=1 -> EpiParams::timing), read back with
+// kiri_debug_gemm_timing(): [0] TMA wait-empty [1] TMA total [2] MMA wait-full [3] MMA wait-tmem-empty
+// [4] MMA total [5] EPI wait-tmem-full [6] EPI total [7] EPI wait-residual [8] EPI wait-store-read [9] tiles
+__device__ long long g_gemm_prof[16];
+// cycles are accumulated in registers (acc) and flushed once per role: a global read-modify-write
+// per sample would stall the single-lane issuers for an L2 round trip and distort the picture
+#define GT_BEGIN(var) long long var = 0; if (timing) var = clock64()
+#define GT_ACC(acc, var) do { if (timing) { const long long _t = clock64(); acc += _t - var; var = _t; } } while (0)
+#define GT_FLUSH(slot, acc) do { if (timing) g_gemm_prof[slot] += acc; } while (0)
+
+template <int KC, int NSEG, int EPI, bool BSTAT>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                const __grid_constant__ CUtensorMap tmOut2, const ConvGeom g, const EpiParams e,
-               const int bn, const int num_m_tiles, const int num_n_tiles, const int stages) {
+               const int bn, const int num_m_tiles, const int num_n_tiles, const int stages, const int CPS) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int kChunkBytes = KC * 2;
   constexpr int kATileBytes = kTileM * kChunkBytes;
@@ -54,57 +85,83 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr uint64_t kLayout = (KC == 64) ? UMMA_LAYOUT_SW128 : UMMA_LAYOUT_SW64;
   constexpr bool kF32Out = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_F32 || EPI == EPI_BIAS_RESID_LN);
   constexpr bool kResid = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_RESID_LN);
-  // carve: [stages][A: CPS chunk tiles][B: CPS chunk tiles] | staging 4x2x4K | residual ring | barriers
+  constexpr int kNBuf = kResid ? 4 : (BSTAT ? 1 : 2);        // staging tiles per epilogue warp
+  // carve: [resident B] | [stages][A: CPS chunk tiles][B: CPS chunk tiles] | staging | barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  const uint32_t a_stage_bytes = CPS * kATileBytes;
+  const int num_chunks = g.taps * g.chunks_per_tap;          // K / KC
   const uint32_t b_chunk_bytes = bn * kChunkBytes;
-  const uint32_t b_stage_bytes = CPS * b_chunk_bytes;
-  const uint32_t stage_bytes = a_stage_bytes + b_stage_bytes;
-  uint8_t* staging = smem + (size_t)stages * stage_bytes;
-  uint8_t* resring = staging + 4 * 2 * kStageBufBytes;
-  PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(resring + (kResid ? 4 * kResDepth * kStageBufBytes : 0));
+  const uint32_t b_res_bytes = BSTAT ? ((num_chunks * b_chunk_bytes + 1023u) & ~1023u) : 0u;
+  const uint32_t a_stage_bytes = CPS * kATileBytes;
+  const uint32_t b_stage_bytes = BSTAT ? 0u : CPS * b_chunk_bytes;
+  const uint32_t stage_bytes = (a_stage_bytes + b_stage_bytes + 1023u) & ~1023u;
+  uint8_t* bres = smem;
+  uint8_t* pipe = smem + b_res_bytes;
+  uint8_t* staging = pipe + (size_t)stages * stage_bytes;
+  PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(staging + kEpiWarps * kNBuf * kBufBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = num_m_tiles * num_n_tiles;
+  // contiguous, n-major tile range of this CTA: B changes at most twice per CTA
+  const int t_begin = static_cast<int>(static_cast<long long>(blockIdx.x) * total_tiles / gridDim.x);
+  const int t_end = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * total_tiles / gridDim.x);
   const int num_kb = g.taps * g.cgs;
+  const bool timing = e.timing != 0 && blockIdx.x == 0;
 
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == kTmaWarp * 32) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(&bars->full[s], 1);
       mbar_init(&bars->empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&bars->tmem_full[a], 1);
-      mbar_init(&bars->tmem_empty[a], 4);
+      mbar_init(&bars->tmem_empty[a], kEpiWarps);
     }
-    for (int wq = 0; wq < 4; ++wq)
-      for (int r = 0; r < kResDepth; ++r) mbar_init(&bars->res_full[wq][r], 1);
+    mbar_init(&bars->b_full, 1);
+    mbar_init(&bars->b_empty, 1);
+    for (int wq = 0; wq < kEpiWarps; ++wq)
+      for (int r = 0; r < 4; ++r) mbar_init(&bars->res_full[wq][r], 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmOut);
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tmem_alloc(&bars->tmem_base, kTmemCols);
     tmem_relinquish();
+  }
+  if (EPI == EPI_BIAS_RESID_LN && threadIdx.x < 256) {
+    const int t = threadIdx.x;
+    bars->ln_g[t] = __ldg(e.ln_g + t);
+    bars->ln_b[t] = __ldg(e.ln_b + t);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
-  if (warp == 0) {
+  if (warp == kTmaWarp) {
     // ============================ TMA producer ============================
     if (lane == 0) {
       // one TMA box = one KC-channel chunk of one segment: R*SEG rows x (KC*2) B
       const uint32_t box_bytes = g.R * g.SEG * kChunkBytes;
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n_tile = tile % num_n_tiles;
-        const int m_tile = tile / num_n_tiles;
+      int cur_n = -1, b_loads = 0;
+      GT_BEGIN(tt0);
+      long long tt_all = tt0, acc_we = 0, acc_tt = 0;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        const int n_tile = tile / num_m_tiles;
+        const int m_tile = tile - n_tile * num_m_tiles;
+        if (BSTAT && n_tile != cur_n) {
+          if (b_loads > 0) mbar_wait(&bars->b_empty, (b_loads - 1) & 1);   // MMAs on the old B retired
+          mbar_arrive_expect_tx(&bars->b_full, num_chunks * b_chunk_bytes);
+          for (int ck = 0; ck < num_chunks; ++ck)
+            tma_load_3d(bres + (size_t)ck * b_chunk_bytes, &tmB, &bars->b_full, 0, ck, n_tile * bn);
+          cur_n = n_tile;
+          ++b_loads;
+        }
         int seg_b[NSEG], seg_x[NSEG], seg_y[NSEG];
         int nvalid = 0;
 #pragma unroll
@@ -129,11 +186,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int cg = kb - tap * g.cgs;
           const int ky = tap / g.kw;
           const int kx = tap - ky * g.kw;
+          if (timing) tt0 = clock64();
           mbar_wait(&bars->empty[stage], phase ^ 1);
-          uint8_t* a_dst = smem + (size_t)stage * stage_bytes;
+          GT_ACC(acc_we, tt0);
+          uint8_t* a_dst = pipe + (size_t)stage * stage_bytes;
           uint8_t* b_dst = a_dst + a_stage_bytes;
           mbar_arrive_expect_tx(&bars->full[stage], tx_bytes);
-#pragma unroll
           for (int c = 0; c < CPS; ++c) {
 #pragma unroll
             for (int j = 0; j < NSEG; ++j) {
@@ -142,32 +200,48 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             &bars->full[stage], 0, cg * CPS + c, seg_x[j] + kx, seg_y[j] + ky,
                             seg_b[j]);
             }
-            tma_load_3d(b_dst + (size_t)c * b_chunk_bytes, &tmB, &bars->full[stage], 0,
-                        tap * g.chunks_per_tap + cg * CPS + c, n_tile * bn);
+            if (!BSTAT)
+              tma_load_3d(b_dst + (size_t)c * b_chunk_bytes, &tmB, &bars->full[stage], 0,
+                          tap * g.chunks_per_tap + cg * CPS + c, n_tile * bn);
           }
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
+      GT_ACC(acc_tt, tt_all);
+      GT_FLUSH(0, acc_we); GT_FLUSH(1, acc_tt);
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ============================ MMA issuer ============================
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(kTileM, bn);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      int cur_n = -1, b_loads = 0;
+      const uint32_t bres_addr = smem_u32(bres);
+      GT_BEGIN(tm0);
+      long long tm_all = tm0, acc_wf = 0, acc_wt = 0, acc_mt = 0;
+      for (int tile = t_begin; tile < t_end; ++tile, ++it) {
+        const int n_tile = tile / num_m_tiles;
+        if (BSTAT && n_tile != cur_n) {
+          mbar_wait(&bars->b_full, b_loads & 1);
+          cur_n = n_tile;
+          ++b_loads;
+        }
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
+        if (timing) tm0 = clock64();
         mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
+        GT_ACC(acc_wt, tm0);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kAccStride;
         for (int kb = 0; kb < num_kb; ++kb) {
+          if (timing) tm0 = clock64();
           mbar_wait(&bars->full[stage], phase);
+          GT_ACC(acc_wf, tm0);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint32_t b_addr = a_addr + a_stage_bytes;
-#pragma unroll
+          const uint32_t a_addr = smem_u32(pipe + (size_t)stage * stage_bytes);
+          const uint32_t b_addr = BSTAT ? bres_addr + (uint32_t)(kb * CPS) * b_chunk_bytes : a_addr + a_stage_bytes;
           for (int c = 0; c < CPS; ++c) {
 #pragma unroll
             for (int h = 0; h < KC / 16; ++h) {
@@ -180,207 +254,222 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&bars->tmem_full[acc]);       // accumulator complete -> epilogue
+        if (BSTAT && (tile + 1 == t_end || (tile + 1) / num_m_tiles != n_tile))
+          umma_commit(&bars->b_empty);            // last MMAs that read this B
       }
+      GT_ACC(acc_mt, tm_all);
+      GT_FLUSH(2, acc_wf); GT_FLUSH(3, acc_wt); GT_FLUSH(4, acc_mt);
+      if (timing) g_gemm_prof[9] += t_end - t_begin;
     }
   } else {
     // ============================ epilogue warps ============================
-    // Thread = one tile row (TMEM lane).  Everything that touches global memory goes through
-    // 32-row x 128-byte shared-memory tiles moved by TMA (bulk tensor stores / loads), so the
-    // global traffic is whole 128-byte lines although a thread owns a row, not a column range.
+    // Thread = one tile row (TMEM lane) x one column half.  Everything that touches global memory
+    // goes through 32-row x 128-byte shared-memory tiles moved by TMA (bulk tensor stores / loads),
+    // so the global traffic is whole 128-byte lines although a thread owns a row, not a column range.
     const int q = warp & 3;                        // TMEM lane quarter this warp may read
-    const int ew = warp - 2;                       // staging / residual slot of this warp
-    uint8_t* stg = staging + ew * 2 * kStageBufBytes;
-    uint8_t* rring = resring + ew * kResDepth * kStageBufBytes;
+    const int ew = warp;                           // staging / residual slot of this warp
+    const int half = ew >> 2;                      // column half (chunks are dealt round-robin)
+    uint8_t* bufs = staging + ew * kNBuf * kBufBytes;
     uint32_t stg_cnt = 0;                          // staging tiles issued (for buffer rotation)
-    uint32_t res_cnt = 0;                          // residual chunks consumed (slot + parity)
     // first row of this warp inside the tile and its decomposition
     const int m0 = q * 32;
     const int j = m0 / (g.R * g.SEG);
     const int within = m0 - j * (g.R * g.SEG);
     const int jj = within / g.SEG;
     const int ii = within - jj * g.SEG;
+    auto tile_rows = [&](int tile, int& row0) -> bool {
+      const int n_tile = tile / num_m_tiles;
+      const int m_tile = tile - n_tile * num_m_tiles;
+      const int s = m_tile * NSEG + j;
+      row0 = 0;
+      if (s >= g.n_seg_total) return false;
+      const int b = s / g.segs_per_img;
+      const int rem = s - b * g.segs_per_img;
+      const int yb = rem / g.segs_per_row;
+      const int xb = rem - yb * g.segs_per_row;
+      const int oy = yb * g.R + jj;
+      const int ox = xb * g.SEG + ii;
+      row0 = (b * g.OH + oy) * g.OW + ox;
+      return (oy < g.OH) && (ox < g.OW);
+    };
+    if (kResid && lane == 0 && t_begin < t_end) {
+      int row0;
+      if (tile_rows(t_begin, row0)) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          mbar_arrive_expect_tx(&bars->res_full[ew][c], kBufBytes);
+          tma_load_2d(bufs + c * kBufBytes, &tmRes, &bars->res_full[ew][c], half * 128 + c * 32, row0);
+        }
+      }
+    }
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int n_tile = tile % num_n_tiles;
-      const int m_tile = tile / num_n_tiles;
+    uint32_t res_tiles = 0;                        // valid residual tiles consumed (parity)
+    const bool etime = timing && warp == 2 && lane == 0;   // epilogue warp 2 (quarter 2, first column half)
+    long long te0 = 0, te_all = 0, acc_ef = 0, acc_er = 0, acc_es = 0;
+    if (etime) { te0 = clock64(); te_all = te0; }
+    for (int tile = t_begin; tile < t_end; ++tile, ++it) {
+      const int n_tile = tile / num_m_tiles;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      // output row of the warp's first lane; the warp's 32 rows are consecutive output rows
-      const int s = m_tile * NSEG + j;
-      bool valid = s < g.n_seg_total;
-      int row0 = 0;
-      if (valid) {
-        const int b = s / g.segs_per_img;
-        const int rem = s - b * g.segs_per_img;
-        const int yb = rem / g.segs_per_row;
-        const int xb = rem - yb * g.segs_per_row;
-        const int oy = yb * g.R + jj;
-        const int ox = xb * g.SEG + ii;
-        valid = (oy < g.OH) && (ox < g.OW);
-        row0 = (b * g.OH + oy) * g.OW + ox;
-      }
+      int row0;
+      const bool valid = tile_rows(tile, row0);
       const int col_base = n_tile * bn;
       // stage this tile's bias slice in shared memory (overlaps the wait for the accumulator)
       float* sbias = bars->bias[acc];
       {
         const int t = ew * 32 + lane;
-        for (int c = t; c < 256; c += 128) sbias[c] = (c < bn && col_base + c < e.n_valid) ? __ldg(e.bias + col_base + c) : 0.f;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        sbias[t] = (t < bn && col_base + t < e.n_valid) ? __ldg(e.bias + col_base + t) : 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      if (kResid && valid && lane == 0) {
-        // the residual does not depend on the accumulator: request the first chunks now
-#pragma unroll
-        for (int r = 0; r < kResDepth; ++r) {
-          const uint32_t slot = (res_cnt + r) % kResDepth;
-          mbar_arrive_expect_tx(&bars->res_full[ew][slot], kStageBufBytes);
-          tma_load_2d(rring + slot * kStageBufBytes, &tmRes, &bars->res_full[ew][slot], r * 32, row0);
-        }
-      }
+      if (etime) te0 = clock64();
       mbar_wait(&bars->tmem_full[acc], acc_phase);
+      if (etime) acc_ef += clock64() - te0;
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccStride;
 
       if (kResid) {
         // ---- x = resid + acc + bias (fp32 out); EPI_BIAS_RESID_LN also emits LayerNorm(x) in bf16.
-        // x is parked back in TMEM so the statistics need no second trip to memory.  bn == 256.
+        // The thread's 128 columns live in registers: ONE pass over TMEM, the accumulator is released
+        // before any arithmetic, and the row statistics are exchanged with the other column half.
+        const int cb = half * 128;
+        uint32_t v[128];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld32(taddr + cb + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
         float sum = 0.f;
-        for (int c = 0; c < 8; ++c) {
-          uint32_t r[32];
-          tmem_ld32(taddr + c * 32, r);
-          const uint32_t slot = res_cnt % kResDepth;
-          const uint32_t par = (res_cnt / kResDepth) & 1;
-          if (valid) mbar_wait(&bars->res_full[ew][slot], par);
-          tmem_ld_wait();
-          const uint8_t* rb = rring + slot * kStageBufBytes;
-          uint8_t* ob = stg + (stg_cnt & 1) * kStageBufBytes;
-          if (lane == 0) bulk_wait_group_read<1>();
-          __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (etime) te0 = clock64();
+          if (valid) mbar_wait(&bars->res_full[ew][c], res_tiles & 1);
+          if (etime) acc_er += clock64() - te0;
+          uint8_t* rb = bufs + c * kBufBytes;
 #pragma unroll
           for (int t = 0; t < 8; ++t) {
-            const float4 b = *reinterpret_cast<const float4*>(sbias + c * 32 + 4 * t);
+            const float4 b = *reinterpret_cast<const float4*>(sbias + cb + c * 32 + 4 * t);
             float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (valid) q4 = *reinterpret_cast<const float4*>(rb + stg_off(lane, t));
             float4 o;
-            o.x = __uint_as_float(r[4 * t]) + b.x + q4.x;
-            o.y = __uint_as_float(r[4 * t + 1]) + b.y + q4.y;
-            o.z = __uint_as_float(r[4 * t + 2]) + b.z + q4.z;
-            o.w = __uint_as_float(r[4 * t + 3]) + b.w + q4.w;
-            *reinterpret_cast<float4*>(ob + stg_off(lane, t)) = o;
+            o.x = __uint_as_float(v[c * 32 + 4 * t]) + b.x + q4.x;
+            o.y = __uint_as_float(v[c * 32 + 4 * t + 1]) + b.y + q4.y;
+            o.z = __uint_as_float(v[c * 32 + 4 * t + 2]) + b.z + q4.z;
+            o.w = __uint_as_float(v[c * 32 + 4 * t + 3]) + b.w + q4.w;
+            *reinterpret_cast<float4*>(rb + stg_off(lane, t)) = o;      // in place: becomes the x tile
             sum += (o.x + o.y) + (o.z + o.w);
-            r[4 * t] = __float_as_uint(o.x); r[4 * t + 1] = __float_as_uint(o.y);
-            r[4 * t + 2] = __float_as_uint(o.z); r[4 * t + 3] = __float_as_uint(o.w);
+            v[c * 32 + 4 * t] = __float_as_uint(o.x); v[c * 32 + 4 * t + 1] = __float_as_uint(o.y);
+            v[c * 32 + 4 * t + 2] = __float_as_uint(o.z); v[c * 32 + 4 * t + 3] = __float_as_uint(o.w);
           }
-          if (EPI == EPI_BIAS_RESID_LN) tmem_st32(taddr + c * 32, r);
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0 && valid) {
-            tma_store_2d(&tmOut, ob, c * 32, row0);
-            bulk_commit_group();
-            // this residual slot is free again: request chunk c + kResDepth of the same tile
-            if (c + kResDepth < 8) {
-              mbar_arrive_expect_tx(&bars->res_full[ew][slot], kStageBufBytes);
-              tma_load_2d(rring + slot * kStageBufBytes, &tmRes, &bars->res_full[ew][slot], (c + kResDepth) * 32, row0);
-            }
-          }
-          ++stg_cnt;
-          if (valid) ++res_cnt;
         }
-        if (EPI == EPI_BIAS_RESID_LN) {
-          tmem_st_wait();
-          const float mean = sum * (1.0f / 256.0f);
-          float sq = 0.f;
-          for (int c = 0; c < 8; ++c) {
-            uint32_t r[32];
-            tmem_ld32(taddr + c * 32, r);
-            tmem_ld_wait();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && valid) {
 #pragma unroll
-            for (int t = 0; t < 32; ++t) { const float d = __uint_as_float(r[t]) - mean; sq = fmaf(d, d, sq); }
-          }
-          const float rstd = 1.0f / sqrtf(sq * (1.0f / 256.0f) + 1e-5f);
-          for (int c = 0; c < 4; ++c) {                       // 64 bf16 columns = 128 B per row
-            uint32_t ra[32], rb2[32];
-            tmem_ld32(taddr + c * 64, ra);
-            tmem_ld32(taddr + c * 64 + 32, rb2);
-            tmem_ld_wait();
-            uint8_t* ob = stg + (stg_cnt & 1) * kStageBufBytes;
-            if (lane == 0) bulk_wait_group_read<1>();
-            __syncwarp();
+          for (int c = 0; c < 4; ++c) tma_store_2d(&tmOut, bufs + c * kBufBytes, cb + c * 32, row0);
+          bulk_commit_group();
+        }
+        if (valid) ++res_tiles;
+        if (EPI == EPI_BIAS_RESID_LN) {
+          const int trow = q * 32 + lane;
+          bars->xch[0][half][trow] = sum;
+          asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+          const float mean = (sum + bars->xch[0][half ^ 1][trow]) * (1.0f / 256.0f);
+          float sq = 0.f;
+#pragma unroll
+          for (int t = 0; t < 128; ++t) { const float d = __uint_as_float(v[t]) - mean; sq = fmaf(d, d, sq); }
+          bars->xch[1][half][trow] = sq;
+          asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+          const float rstd = 1.0f / sqrtf((sq + bars->xch[1][half ^ 1][trow]) * (1.0f / 256.0f) + 1e-5f);
+          if (etime) te0 = clock64();
+          if (lane == 0) bulk_wait_group_read<0>();              // the x stores have read their tiles
+          if (etime) acc_es += clock64() - te0;
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {                          // 64 bf16 columns = 128 B per row
+            uint8_t* ob = bufs + c * kBufBytes;
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
-              const uint32_t* src = (t < 4) ? ra : rb2;
-              const int o8 = (t & 3) * 8;
-              const int col = c * 64 + t * 8;
-              const float4 g0 = __ldg(reinterpret_cast<const float4*>(e.ln_g + col));
-              const float4 g1 = __ldg(reinterpret_cast<const float4*>(e.ln_g + col + 4));
-              const float4 h0 = __ldg(reinterpret_cast<const float4*>(e.ln_b + col));
-              const float4 h1 = __ldg(reinterpret_cast<const float4*>(e.ln_b + col + 4));
+              const int col = cb + c * 64 + t * 8;
+              const float4 g0 = *reinterpret_cast<const float4*>(bars->ln_g + col);
+              const float4 g1 = *reinterpret_cast<const float4*>(bars->ln_g + col + 4);
+              const float4 h0 = *reinterpret_cast<const float4*>(bars->ln_b + col);
+              const float4 h1 = *reinterpret_cast<const float4*>(bars->ln_b + col + 4);
               const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
               const float hh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
               float y[8];
 #pragma unroll
-              for (int u = 0; u < 8; ++u) y[u] = (__uint_as_float(src[o8 + u]) - mean) * rstd * gg[u] + hh[u];
+              for (int u = 0; u < 8; ++u) y[u] = (__uint_as_float(v[c * 64 + t * 8 + u]) - mean) * rstd * gg[u] + hh[u];
               uint4 pk;
               pk.x = pack_bf16x2(y[0], y[1]); pk.y = pack_bf16x2(y[2], y[3]);
               pk.z = pack_bf16x2(y[4], y[5]); pk.w = pack_bf16x2(y[6], y[7]);
               *reinterpret_cast<uint4*>(ob + stg_off(lane, t)) = pk;
             }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0 && valid) {
-              tma_store_2d(&tmOut2, ob, c * 64, row0);
-              bulk_commit_group();
-            }
-            ++stg_cnt;
-          }
-        }
-      } else if (kF32Out) {
-        // ---- fp32 out = acc + bias, 32 columns (128 B per row) per staging tile
-        for (int c0 = 0; c0 < bn; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(taddr + c0, r);
-          tmem_ld_wait();
-          uint8_t* ob = stg + (stg_cnt & 1) * kStageBufBytes;
-          if (lane == 0) bulk_wait_group_read<1>();
-          __syncwarp();
-#pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            const float4 b = *reinterpret_cast<const float4*>(sbias + c0 + 4 * t);
-            const float4 o = make_float4(__uint_as_float(r[4 * t]) + b.x, __uint_as_float(r[4 * t + 1]) + b.y,
-                                         __uint_as_float(r[4 * t + 2]) + b.z, __uint_as_float(r[4 * t + 3]) + b.w);
-            *reinterpret_cast<float4*>(ob + stg_off(lane, t)) = o;
           }
           fence_proxy_async();
           __syncwarp();
           if (lane == 0 && valid) {
-            tma_store_2d(&tmOut, ob, col_base + c0, row0);
+            tma_store_2d(&tmOut2, bufs, cb, row0);
+            tma_store_2d(&tmOut2, bufs + kBufBytes, cb + 64, row0);
             bulk_commit_group();
           }
-          ++stg_cnt;
         }
+        // the residual of the next tile can land as soon as the stores have read the tiles
+        if (lane == 0 && tile + 1 < t_end) {
+          int nrow0;
+          if (tile_rows(tile + 1, nrow0)) {
+            bulk_wait_group_read<0>();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              mbar_arrive_expect_tx(&bars->res_full[ew][c], kBufBytes);
+              tma_load_2d(bufs + c * kBufBytes, &tmRes, &bars->res_full[ew][c], cb + c * 32, nrow0);
+            }
+          }
+        }
+        __syncwarp();
       } else {
-        // ---- bf16 out = act(acc + bias), 64 columns (128 B per row) per staging tile
-        for (int c0 = 0; c0 < bn; c0 += 64) {
+        constexpr int kCols = kF32Out ? 32 : 64;                 // columns per 128-byte staging row
+        const int nch = (bn + kCols - 1) / kCols;
+        for (int ch = half; ch < nch; ch += 2) {
+          const int c0 = ch * kCols;
           uint32_t ra[32], rb2[32];
           tmem_ld32(taddr + c0, ra);
-          tmem_ld32(taddr + c0 + 32, rb2);        // may run past bn: columns are clipped by the store
+          if (!kF32Out) tmem_ld32(taddr + c0 + 32, rb2);         // may run past bn: columns are clipped by the store
           tmem_ld_wait();
-          uint8_t* ob = stg + (stg_cnt & 1) * kStageBufBytes;
-          if (lane == 0) bulk_wait_group_read<1>();
+          if (ch + 2 >= nch) {                                   // last chunk of this warp: accumulator drained
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
+          }
+          uint8_t* ob = bufs + (stg_cnt % kNBuf) * kBufBytes;
+          if (etime) te0 = clock64();
+          if (lane == 0) bulk_wait_group_read<kNBuf - 1>();
+          if (etime) acc_es += clock64() - te0;
           __syncwarp();
+          if (kF32Out) {
 #pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            const uint32_t* src = (t < 4) ? ra : rb2;
-            const int o8 = (t & 3) * 8;
-            const float4 b0 = *reinterpret_cast<const float4*>(sbias + c0 + t * 8);
-            const float4 b1 = *reinterpret_cast<const float4*>(sbias + c0 + t * 8 + 4);
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-            float y[8];
+            for (int t = 0; t < 8; ++t) {
+              const float4 b = *reinterpret_cast<const float4*>(sbias + c0 + 4 * t);
+              const float4 o = make_float4(__uint_as_float(ra[4 * t]) + b.x, __uint_as_float(ra[4 * t + 1]) + b.y,
+                                           __uint_as_float(ra[4 * t + 2]) + b.z, __uint_as_float(ra[4 * t + 3]) + b.w);
+              *reinterpret_cast<float4*>(ob + stg_off(lane, t)) = o;
+            }
+          } else {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) y[u] = epi_act<EPI>(__uint_as_float(src[o8 + u]) + bb[u]);
-            uint4 pk;
-            pk.x = pack_bf16x2(y[0], y[1]); pk.y = pack_bf16x2(y[2], y[3]);
-            pk.z = pack_bf16x2(y[4], y[5]); pk.w = pack_bf16x2(y[6], y[7]);
-            *reinterpret_cast<uint4*>(ob + stg_off(lane, t)) = pk;
+            for (int t = 0; t < 8; ++t) {
+              const uint32_t* src = (t < 4) ? ra : rb2;
+              const int o8 = (t & 3) * 8;
+              const float4 b0 = *reinterpret_cast<const float4*>(sbias + c0 + t * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(sbias + c0 + t * 8 + 4);
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+              float y[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) y[u] = epi_act<EPI>(__uint_as_float(src[o8 + u]) + bb[u]);
+              uint4 pk;
+              pk.x = pack_bf16x2(y[0], y[1]); pk.y = pack_bf16x2(y[2], y[3]);
+              pk.z = pack_bf16x2(y[4], y[5]); pk.w = pack_bf16x2(y[6], y[7]);
+              *reinterpret_cast<uint4*>(ob + stg_off(lane, t)) = pk;
+            }
           }
           fence_proxy_async();
           __syncwarp();
@@ -390,17 +479,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           ++stg_cnt;
         }
+        if (half >= nch) {                                       // no chunk for this warp (bn <= 64 / 32)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
+        }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
+    }
+    if (etime) {
+      g_gemm_prof[6] += clock64() - te_all;
+      g_gemm_prof[5] += acc_ef; g_gemm_prof[7] += acc_er; g_gemm_prof[8] += acc_es;
     }
     if (lane == 0) bulk_wait_group<0>();          // all stores of this warp have landed
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
@@ -499,19 +594,21 @@ static int encode_rowtile_map(CUtensorMap* m, const void* base, long long rows, 
                     f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
 }
 
-template <int KC, int CPS, int NSEG, int EPI>
+template <int KC, int NSEG, int EPI, bool BSTAT>
 static int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
                        const CUtensorMap& tmRes, const CUtensorMap& tmOut2, const ConvGeom& g,
-                       const EpiParams& e, int bn, int num_m_tiles, int num_n_tiles, cudaStream_t stream) {
+                       const EpiParams& e, int bn, int num_m_tiles, int num_n_tiles, int CPS, cudaStream_t stream) {
   constexpr bool kResid = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_RESID_LN);
-  const int stage_bytes = CPS * kTileM * KC * 2 + CPS * bn * KC * 2;
-  const int overhead = 1024 + (int)sizeof(PipeBarriers) + 4 * 2 * kStageBufBytes +
-                       (kResid ? 4 * kResDepth * kStageBufBytes : 0);
+  constexpr int kNBuf = kResid ? 4 : (BSTAT ? 1 : 2);
+  const int num_chunks = g.taps * g.chunks_per_tap;
+  const int b_res = BSTAT ? ((num_chunks * bn * KC * 2 + 1023) & ~1023) : 0;
+  const int stage_bytes = (CPS * kTileM * KC * 2 + (BSTAT ? 0 : CPS * bn * KC * 2) + 1023) & ~1023;
+  const int overhead = 1024 + (int)sizeof(PipeBarriers) + kEpiWarps * kNBuf * kBufBytes + b_res;
   int stages = (g_max_smem - overhead) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   KIRI_REQUIRE(stages >= 2, "gemm_tc: stage of %d bytes does not fit twice in shared memory", stage_bytes);
   const int smem = stages * stage_bytes + overhead;
-  auto kern = gemm_tc_kernel<KC, CPS, NSEG, EPI>;
+  auto kern = gemm_tc_kernel<KC, NSEG, EPI, BSTAT>;
   static int configured = 0;
   if (configured < smem) {
     KIRI_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
@@ -519,24 +616,30 @@ static int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   }
   int grid = num_m_tiles * num_n_tiles;
   if (grid > g_num_sms) grid = g_num_sms;
-  kern<<<grid, kNumThreads, smem, stream>>>(tmA, tmB, tmOut, tmRes, tmOut2, g, e, bn, num_m_tiles, num_n_tiles, stages);
+  kern<<<grid, kNumThreads, smem, stream>>>(tmA, tmB, tmOut, tmRes, tmOut2, g, e, bn, num_m_tiles, num_n_tiles, stages, CPS);
   KIRI_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-int launch_gemm_tc(const GemmLaunch& L, cudaStream_t stream) {
+int launch_gemm_tc(const GemmLaunch& L_in, cudaStream_t stream) {
+  GemmLaunch L = L_in;
+  static const int timing_on = getenv("KIRI_GEMM_TIMING") != nullptr;
+  L.e.timing = timing_on;
   gemm_tc_num_sms();
   KIRI_REQUIRE(L.Cin % 32 == 0, "gemm_tc: Cin=%d must be a multiple of 32", L.Cin);
   KIRI_REQUIRE(L.e.bias != nullptr && L.e.out != nullptr, "gemm_tc: bias/out must not be null");
   const bool is_gemm = (L.kw == 1 && L.kh == 1);
-  const int KC = (L.Cin % 64 == 0) ? 64 : 32;             // 128-byte rows whenever the channels allow
+  // 128-byte K rows whenever the channels allow; the residual/LayerNorm epilogues keep 128 KB of
+  // staging tiles, so their pipeline uses the half-size (64-byte) stages to still be 3 deep
+  const bool resid_epi = (L.epi == EPI_BIAS_RESID_F32 || L.epi == EPI_BIAS_RESID_LN);
+  const int KC = (L.Cin % 64 == 0 && !resid_epi) ? 64 : 32;
   const int chunks = L.Cin / KC;
   ConvGeom g;
   int NSEG = 1, CPS = 1;
   if (is_gemm) {
     KIRI_REQUIRE(L.IH == 1 && L.NB == 1 && L.OH == 1 && L.OW == L.IW, "gemm_tc: plain GEMM wants [1,1,M,K]");
     g.R = 1; g.SEG = 128;
-    KIRI_REQUIRE(KC == 64, "gemm_tc: GEMM K=%d must be a multiple of 64", L.Cin);
+    KIRI_REQUIRE(L.Cin % 64 == 0, "gemm_tc: GEMM K=%d must be a multiple of 64", L.Cin);
     CPS = 1;
   } else {
     if (L.OW % 128 == 0) { g.R = 1; g.SEG = 128; }
@@ -600,27 +703,47 @@ int launch_gemm_tc(const GemmLaunch& L, cudaStream_t stream) {
     if (encode_rowtile_map(&tmOut2, L.e.out2, rows_total, 256, 256, false)) return -1;
   }
 
-#define KIRI_LAUNCH(K, C, S, E) \
-  return launch_inst<K, C, S, E>(tmA, tmB, tmOut, tmRes, tmOut2, g, L.e, bn, num_m_tiles, num_n_tiles, stream)
+  // weights stay resident in shared memory for the whole CTA when they fit beside >= 3 A stages
+  const int b_total = g.taps * L.Cin * bn * 2;
+  const bool bstat = !resid_epi && b_total <= kMaxBResident && getenv("KIRI_GEMM_NO_BSTAT") == nullptr &&
+                     (g_max_smem - 1024 - (int)sizeof(PipeBarriers) - kEpiWarps * kBufBytes - b_total) >= 3 * CPS * kTileM * KC * 2;
+#define KIRI_LAUNCH(K, S, E)                                                                                          \
+  do {                                                                                                                 \
+    if (bstat) return launch_inst<K, S, E, true>(tmA, tmB, tmOut, tmRes, tmOut2, g, L.e, bn, num_m_tiles, num_n_tiles, CPS, stream); \
+    return launch_inst<K, S, E, false>(tmA, tmB, tmOut, tmRes, tmOut2, g, L.e, bn, num_m_tiles, num_n_tiles, CPS, stream);           \
+  } while (0)
+#define KIRI_LAUNCH_NB(K, S, E) \
+  return launch_inst<K, S, E, false>(tmA, tmB, tmOut, tmRes, tmOut2, g, L.e, bn, num_m_tiles, num_n_tiles, CPS, stream)
   if (!is_gemm) {
-    if (KC == 64 && NSEG == 1) KIRI_LAUNCH(64, 1, 1, EPI_BIAS_SILU_BF16);
-    if (KC == 64 && NSEG == 4) KIRI_LAUNCH(64, 1, 4, EPI_BIAS_SILU_BF16);
-    if (KC == 32 && CPS == 1 && NSEG == 1) KIRI_LAUNCH(32, 1, 1, EPI_BIAS_SILU_BF16);
-    if (KC == 32 && CPS == 1 && NSEG == 4) KIRI_LAUNCH(32, 1, 4, EPI_BIAS_SILU_BF16);
-    if (KC == 32 && CPS == 3 && NSEG == 1) KIRI_LAUNCH(32, 3, 1, EPI_BIAS_SILU_BF16);
+    if (KC == 64 && NSEG == 1) KIRI_LAUNCH(64, 1, EPI_BIAS_SILU_BF16);
+    if (KC == 64 && NSEG == 4) KIRI_LAUNCH(64, 4, EPI_BIAS_SILU_BF16);
+    if (KC == 32 && NSEG == 1) KIRI_LAUNCH_NB(32, 1, EPI_BIAS_SILU_BF16);
+    if (KC == 32 && NSEG == 4) KIRI_LAUNCH_NB(32, 4, EPI_BIAS_SILU_BF16);
   } else {
     switch (L.epi) {
-      case EPI_BIAS_BF16: KIRI_LAUNCH(64, 1, 1, EPI_BIAS_BF16);
-      case EPI_BIAS_SILU_BF16: KIRI_LAUNCH(64, 1, 1, EPI_BIAS_SILU_BF16);
-      case EPI_BIAS_GELU_BF16: KIRI_LAUNCH(64, 1, 1, EPI_BIAS_GELU_BF16);
-      case EPI_BIAS_RESID_F32: KIRI_LAUNCH(64, 1, 1, EPI_BIAS_RESID_F32);
-      case EPI_BIAS_F32: KIRI_LAUNCH(64, 1, 1, EPI_BIAS_F32);
-      case EPI_BIAS_RESID_LN: KIRI_LAUNCH(64, 1, 1, EPI_BIAS_RESID_LN);
+      case EPI_BIAS_BF16: KIRI_LAUNCH(64, 1, EPI_BIAS_BF16);
+      case EPI_BIAS_SILU_BF16: KIRI_LAUNCH(64, 1, EPI_BIAS_SILU_BF16);
+      case EPI_BIAS_GELU_BF16: KIRI_LAUNCH(64, 1, EPI_BIAS_GELU_BF16);
+      case EPI_BIAS_RESID_F32: KIRI_LAUNCH_NB(32, 1, EPI_BIAS_RESID_F32);
+      case EPI_BIAS_F32: KIRI_LAUNCH(64, 1, EPI_BIAS_F32);
+      case EPI_BIAS_RESID_LN: KIRI_LAUNCH_NB(32, 1, EPI_BIAS_RESID_LN);
       default: break;
     }
   }
+#undef KIRI_LAUNCH_NB
 #undef KIRI_LAUNCH
   KIRI_REQUIRE(false, "gemm_tc: no kernel instance for KC=%d CPS=%d NSEG=%d epi=%d", KC, CPS, NSEG, L.epi);
 }
 
 }  // namespace kiri
+
+// Debug: role-level cycles of CTA 0 accumulated since the last call (KIRI_GEMM_TIMING=1).
+extern "C" int kiri_debug_gemm_timing(long long* out_host, int n) {
+  long long buf[16];
+  if (cudaDeviceSynchronize() != cudaSuccess) return -2;
+  if (cudaMemcpyFromSymbol(buf, kiri::g_gemm_prof, sizeof(buf)) != cudaSuccess) return -2;
+  for (int i = 0; i < n && i < 16; ++i) out_host[i] = buf[i];
+  long long zero[16] = {0};
+  if (cudaMemcpyToSymbol(kiri::g_gemm_prof, zero, sizeof(zero)) != cudaSuccess) return -2;
+  return 0;
+}

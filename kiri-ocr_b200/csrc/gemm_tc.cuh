@@ -51,6 +51,7 @@ struct EpiParams {
   const float* ln_g;   // EPI_BIAS_RESID_LN: LayerNorm affine [256]
   const float* ln_b;
   void* out2;          // EPI_BIAS_RESID_LN: bf16 [rows, 256]
+  int timing;          // debug: accumulate role-level cycle counts of CTA 0 (set by the launcher)
 };
 
 // Host launcher (gemm_tc.cu).  A is described by an NHWC activation [NB, IH, IW, Cin]

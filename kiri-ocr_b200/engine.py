@@ -100,7 +100,7 @@ def plan_groups(entries: np.ndarray, cfg: CFG, width_mode: str = "parity"
 
 class BatchedRecognizer:
     def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: CFG, tokenizer: CharTokenizer,
-                 device: str = "cuda", width_mode: str = "parity", stem_chunk: int = 16):
+                 device: str = "cuda", width_mode: str = "parity", stem_chunk: int = 64):
         _lib.require_device()
         self.lib = _lib.load()
         self.cfg, self.tok = cfg, tokenizer
@@ -206,6 +206,60 @@ class BatchedRecognizer:
         self.launches += 4 * n_chunks + 1 + 4 * self.pw.enc_layers + 1 + (1 if want_logits else 0)
         return out
 
+    def encode_multi(self, planes_list: Sequence[torch.Tensor], want_mem_f32: bool = False, want_tokens: bool = False,
+                     kv_len: Optional[torch.Tensor] = None, want_logits: bool = True):
+        """Several width groups ([B_g, IMG_H, Wb_g] uint8 each) in one call: per-group stems, ONE pass
+        of the encoder / CTC head over the concatenated token stream.  Returns the outputs token-major
+        ([M, ...], M = sum B_g * Wb_g / 4) plus ``rows`` = [(row0, B_g, T_g)] per group."""
+        D = self.cfg.ENC_DIM
+        n = len(planes_list)
+        garr = (_lib.KiriGroup * n)()
+        rows, M = [], 0
+        for i, pl in enumerate(planes_list):
+            B, H, Wb = pl.shape
+            garr[i].planes, garr[i].n_lines, garr[i].Wb = pl.data_ptr(), B, Wb
+            rows.append((M, B, Wb // 4))
+            M += B * (Wb // 4)
+        need = self.lib.kiri_encode_multi_workspace_bytes(self.handle, garr, n, self.stem_chunk)
+        ws = self._workspace(need)
+        out = {"mem_bf16": torch.empty((M, D), dtype=torch.bfloat16, device=self.device), "rows": rows}
+        if want_logits:
+            out["logits"] = torch.empty((M, self.pw.Cp), dtype=torch.float32, device=self.device)
+        if want_mem_f32:
+            out["mem_f32"] = torch.empty((M, D), dtype=torch.float32, device=self.device)
+        if want_tokens:
+            out["tokens"] = torch.empty((M, D), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.kiri_encode_multi(self.handle, garr, n, self.stem_chunk, ws.data_ptr(), need,
+                                              _lib.ptr(out.get("mem_f32")), out["mem_bf16"].data_ptr(),
+                                              _lib.ptr(out.get("logits")), _lib.ptr(out.get("tokens")), _lib.ptr(kv_len),
+                                              _lib.stream_ptr()), "kiri_encode_multi")
+        for _, B, _ in rows:
+            n_chunks = math.ceil(B / (self.stem_chunk if 0 < self.stem_chunk <= B else B))
+            self.launches += 4 * n_chunks + 1 + self.pw.enc_layers          # stem, pool, attention per group
+        self.launches += 4 * self.pw.enc_layers + 1 + (1 if want_logits else 0)
+        return out
+
+    def decode_greedy_multi(self, mem_bf16: torch.Tensor, mem_row0: torch.Tensor, mem_len: torch.Tensor,
+                            len_est: torch.Tensor, Lmax: int, select_raw: bool = False,
+                            forced: Optional[torch.Tensor] = None, want_steps: bool = False):
+        """One persistent decode over every line of every group (concatenated token stream)."""
+        p = self.decode_params(select_raw)
+        B, M = int(len_est.numel()), int(mem_bf16.shape[0])
+        need = self.lib.kiri_decode_multi_workspace_bytes(self.handle, B, M, Lmax)
+        ws = self._workspace(need, "_dws")
+        ids = torch.zeros((B, Lmax), dtype=torch.int32, device=self.device)
+        n_out = torch.zeros(B, dtype=torch.int32, device=self.device)
+        sum_lp = torch.zeros(B, dtype=torch.float32, device=self.device)
+        slp = torch.zeros((B, Lmax), dtype=torch.float32, device=self.device) if want_steps else None
+        spr = torch.zeros((B, Lmax), dtype=torch.float32, device=self.device) if want_steps else None
+        _lib.check(self.lib.kiri_decode_greedy_multi(self.handle, mem_bf16.data_ptr(), M, mem_row0.data_ptr(),
+                                                     mem_len.data_ptr(), len_est.data_ptr(), B, Lmax, C.byref(p),
+                                                     ws.data_ptr(), need, ids.data_ptr(), n_out.data_ptr(),
+                                                     sum_lp.data_ptr(), _lib.ptr(slp), _lib.ptr(spr), _lib.ptr(forced),
+                                                     None, _lib.stream_ptr()), "kiri_decode_greedy_multi")
+        self.launches += 2          # cross-K/V GEMM + the persistent decode kernel
+        return ids, n_out, sum_lp, slp, spr
+
     def ctc_greedy(self, logits: torch.Tensor, want_frames: bool = False):
         B, T, Cp = logits.shape
         ids = torch.empty((B, T), dtype=torch.int32, device=self.device)
@@ -262,36 +316,45 @@ class BatchedRecognizer:
         ``step_resident`` replays with no host<->device traffic."""
         src_dev = src if src.is_cuda else src.to(self.device)
         plan = []
+        row0 = 0
+        mem_row0, mem_len, kv = [], [], []
         for Wb, (idx, descs, smem) in self.plan(entries).items():
             dd = torch.from_numpy(descs.view(np.uint8).reshape(-1).copy()).to(self.device)
             planes = torch.empty((len(idx), self.cfg.IMG_H, Wb), dtype=torch.uint8, device=self.device)
-            kv_len = None
-            if self.width_mode == "masked":
-                kv_len = torch.from_numpy(np.minimum((descs["nw"] + 3) // 4, Wb // 4).astype(np.int32)).to(self.device)
-            plan.append({"Wb": Wb, "idx": idx, "descs": dd, "n": len(idx), "smem": smem, "planes": planes,
-                         "kv_len": kv_len})
+            T = Wb // 4
+            mem_row0.append(row0 + np.arange(len(idx), dtype=np.int32) * T)
+            mem_len.append(np.full(len(idx), T, np.int32))
+            kv.append(np.minimum((descs["nw"] + 3) // 4, T).astype(np.int32))
+            row0 += len(idx) * T
+            plan.append({"Wb": Wb, "idx": idx, "descs": dd, "n": len(idx), "smem": smem, "planes": planes})
+        kv_len = torch.from_numpy(np.concatenate(kv)).to(self.device) if self.width_mode == "masked" else None
+        out = {"src": src_dev, "groups": plan, "kv_len": kv_len,
+               "mem_row0": torch.from_numpy(np.concatenate(mem_row0)).to(self.device),
+               "mem_len": torch.from_numpy(np.concatenate(mem_len)).to(self.device),
+               "T_max": max(g["Wb"] for g in plan) // 4}
         torch.cuda.synchronize()
-        return {"src": src_dev, "groups": plan}
+        return out
 
     def step_resident(self, prep, method: str = "ctc"):
         """One pass of the hot path over the prepared batch, inputs already in HBM.  Returns the
-        per-group device outputs (no synchronisation)."""
-        outs = []
+        device outputs (no synchronisation in "ctc" mode; the decoder needs the CTC length
+        estimates on the host once to bound its loop)."""
         for g in prep["groups"]:
             _lib.check(self.lib.kiri_preprocess_pack(prep["src"].data_ptr(), g["descs"].data_ptr(), g["n"],
                                                      self.cfg.IMG_H, g["Wb"], g["smem"], g["planes"].data_ptr(), 0,
                                                      _lib.stream_ptr()), "kiri_preprocess_pack")
             self.launches += 1
-            enc = self.encode(g["planes"], kv_len=g["kv_len"])
-            ids, n_ids, conf, _, _ = self.ctc_greedy(enc["logits"])
-            if method == "decoder":
-                T = g["Wb"] // 4
-                Lmax = self.max_steps_bound(int(n_ids.max().item()), T)
-                d_ids, n_out, sum_lp, _, _, _ = self.decode_greedy(enc["mem_bf16"], n_ids, g["n"], T, Lmax)
-                outs.append((d_ids, n_out, sum_lp, conf))
-            else:
-                outs.append((ids, n_ids, conf))
-        return outs
+        enc = self.encode_multi([g["planes"] for g in prep["groups"]], kv_len=prep["kv_len"])
+        outs = []
+        for (row0, B, T) in enc["rows"]:
+            outs.append(self.ctc_greedy(enc["logits"][row0:row0 + B * T].view(B, T, self.pw.Cp))[:3])
+        if method != "decoder":
+            return outs
+        len_est = torch.cat([o[1] for o in outs]) if len(outs) > 1 else outs[0][1]
+        conf = torch.cat([o[2] for o in outs]) if len(outs) > 1 else outs[0][2]
+        Lmax = self.max_steps_bound(int(len_est.max().item()), prep["T_max"])
+        d_ids, n_out, sum_lp, _, _ = self.decode_greedy_multi(enc["mem_bf16"], prep["mem_row0"], prep["mem_len"], len_est, Lmax)
+        return [(d_ids, n_out, sum_lp, conf)]
 
     def profile(self, fn):
         """Run ``fn()`` with per-stage CUDA-event timing on; returns {stage: (ms, intervals)}."""
@@ -324,53 +387,63 @@ class BatchedRecognizer:
         if n == 0:
             return results
         src_dev = src if src.is_cuda else src.to(self.device, non_blocking=True)
-        pending = []
-        for Wb, (idx, descs, smem) in self.plan(entries).items():
-            planes, _ = self.preprocess(src_dev, descs, Wb, smem)
-            kv_len = None
-            if self.width_mode == "masked":
-                kv_len = torch.from_numpy(np.minimum((descs["nw"] + 3) // 4, Wb // 4).astype(np.int32)).to(self.device)
-            enc = self.encode(planes, kv_len=kv_len)
-            B, T = len(idx), Wb // 4
-            ids, n_ids, conf, fids, fprob = self.ctc_greedy(enc["logits"], want_frames=streaming and method == "ctc")
-            if method == "ctc":
-                pending.append((idx, "ctc", ids, n_ids, conf, fids, fprob))
-            else:
-                n_host = n_ids.cpu()                                  # length estimates bound the loop
-                Lmax = self.max_steps_bound(int(n_host.max()), T)
-                d_ids, n_out, sum_lp, slp, spr, _ = self.decode_greedy(enc["mem_bf16"], n_ids, B, T, Lmax,
-                                                                      select_raw=streaming, want_steps=True)
-                pending.append((idx, "decoder", d_ids, n_out, sum_lp, conf, slp, spr, n_host.numpy()))
-        torch.cuda.current_stream().synchronize()
+        groups = list(self.plan(entries).items())
+        planes_list, kv, mem_row0, mem_len = [], [], [], []
+        row0 = 0
+        for Wb, (idx, descs, smem) in groups:
+            planes_list.append(self.preprocess(src_dev, descs, Wb, smem)[0])
+            T = Wb // 4
+            kv.append(np.minimum((descs["nw"] + 3) // 4, T).astype(np.int32))
+            mem_row0.append(row0 + np.arange(len(idx), dtype=np.int32) * T)
+            mem_len.append(np.full(len(idx), T, np.int32))
+            row0 += len(idx) * T
+        kv_len = None
+        if self.width_mode == "masked":
+            kv_len = torch.from_numpy(np.concatenate(kv)).pin_memory().to(self.device, non_blocking=True)
+        enc = self.encode_multi(planes_list, kv_len=kv_len)
+        ctc = []
+        for (r0, B, T) in enc["rows"]:
+            ctc.append(self.ctc_greedy(enc["logits"][r0:r0 + B * T].view(B, T, self.pw.Cp),
+                                       want_frames=streaming and method == "ctc"))
+        order = np.concatenate([idx for _, (idx, _, _) in groups])          # line index of every concatenated slot
         tok = self.tok
-        for item in pending:
-            idx = item[0]
-            if item[1] == "ctc":
-                _, _, ids, n_ids, conf, fids, fprob = item
+        if method == "ctc":
+            torch.cuda.current_stream().synchronize()
+            pos = 0
+            for (ids, n_ids, conf, fids, fprob) in ctc:
                 ids_h, n_h, c_h = ids.cpu().numpy(), n_ids.cpu().numpy(), conf.cpu().numpy()
                 f_h = fids.cpu().numpy() if fids is not None else None
                 p_h = fprob.cpu().numpy() if fprob is not None else None
-                for j, li in enumerate(idx):
+                for j in range(len(n_h)):
                     row = ids_h[j, :n_h[j]]
-                    results[li] = LineResult(tok.decode_collapsed_ctc(row.tolist()), float(c_h[j]), float(c_h[j]), row,
-                                             frame_ids=None if f_h is None else f_h[j],
-                                             frame_prob=None if p_h is None else p_h[j], len_est=int(n_h[j]))
-            else:
-                _, _, d_ids, n_out, sum_lp, conf, slp, spr, len_h = item
-                ids_h, n_h, s_h, c_h = d_ids.cpu().numpy(), n_out.cpu().numpy(), sum_lp.cpu().numpy(), conf.cpu().numpy()
-                slp_h, spr_h = slp.cpu().numpy(), spr.cpu().numpy()
-                for j, li in enumerate(idx):
-                    row = ids_h[j, :n_h[j]]
-                    text_ids = []
-                    for t in row.tolist():
-                        if t == tok.dec_eos:
-                            break
-                        text_ids.append(t)
-                    lps = slp_h[j, :n_h[j]].astype(np.float64)
-                    dec_conf = min(1.0, max(0.0, math.exp(float(lps.sum()) / len(lps)))) if len(lps) else 0.0
-                    results[li] = LineResult(tok.decode_dec(text_ids), 0.6 * dec_conf + 0.4 * float(c_h[j]),
-                                             float(c_h[j]), row, step_logp=slp_h[j, :n_h[j]], step_prob=spr_h[j, :n_h[j]],
-                                             len_est=int(len_h[j]))
+                    results[order[pos + j]] = LineResult(tok.decode_collapsed_ctc(row.tolist()), float(c_h[j]), float(c_h[j]),
+                                                         row, frame_ids=None if f_h is None else f_h[j],
+                                                         frame_prob=None if p_h is None else p_h[j], len_est=int(n_h[j]))
+                pos += len(n_h)
+            return results
+        len_est = torch.cat([c[1] for c in ctc]) if len(ctc) > 1 else ctc[0][1]
+        conf = torch.cat([c[2] for c in ctc]) if len(ctc) > 1 else ctc[0][2]
+        len_h = len_est.cpu().numpy()                              # length estimates bound the loop
+        Lmax = self.max_steps_bound(int(len_h.max()), max(T for _, _, T in enc["rows"]))
+        r0_dev = torch.from_numpy(np.concatenate(mem_row0)).pin_memory().to(self.device, non_blocking=True)
+        ml_dev = torch.from_numpy(np.concatenate(mem_len)).pin_memory().to(self.device, non_blocking=True)
+        d_ids, n_out, sum_lp, slp, spr = self.decode_greedy_multi(enc["mem_bf16"], r0_dev, ml_dev, len_est, Lmax,
+                                                                  select_raw=streaming, want_steps=True)
+        torch.cuda.current_stream().synchronize()
+        ids_h, n_h, c_h = d_ids.cpu().numpy(), n_out.cpu().numpy(), conf.cpu().numpy()
+        slp_h, spr_h = slp.cpu().numpy(), spr.cpu().numpy()
+        for j, li in enumerate(order):
+            row = ids_h[j, :n_h[j]]
+            text_ids = []
+            for t in row.tolist():
+                if t == tok.dec_eos:
+                    break
+                text_ids.append(t)
+            lps = slp_h[j, :n_h[j]].astype(np.float64)
+            dec_conf = min(1.0, max(0.0, math.exp(float(lps.sum()) / len(lps)))) if len(lps) else 0.0
+            results[li] = LineResult(tok.decode_dec(text_ids), 0.6 * dec_conf + 0.4 * float(c_h[j]),
+                                     float(c_h[j]), row, step_logp=slp_h[j, :n_h[j]], step_prob=spr_h[j, :n_h[j]],
+                                     len_est=int(len_h[j]))
         return results
 
     def recognize_crops(self, crops: Sequence[np.ndarray], method: str = "ctc", streaming: bool = False):

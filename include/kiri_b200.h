@@ -63,15 +63,17 @@ typedef struct {
   int32_t w, h;       /* crop size after the reference's clamp-pad (core.py:510-515)       */
   int32_t nw;         /* max(1, round(w * img_h / h)) — Python round (model.py:321-322)    */
   int32_t out_index;  /* line slot in the output batch                                     */
-  int32_t strip_w;    /* output columns resampled per pass (fits the shared-memory budget) */
+  int32_t strip_w;    /* output columns resampled by one CTA (fits the shared-memory budget)  */
 } KiriCropDesc;
 
 /* shared memory needed by one crop for a given strip width (host helper, no GPU call) */
 int kiri_preprocess_smem_bytes(int w, int h, int nw, int img_h, int Wb, int strip_w);
 
-/* planes_u8: [n_slots, img_h, Wb] uint8; norm_bf16 (nullable): same shape, (v/255-0.5)/0.5 */
+/* planes_u8: [n_slots, img_h, Wb] uint8; norm_bf16 (nullable): same shape, (v/255-0.5)/0.5.
+ * One CTA resamples one strip of strip_w output columns of one crop; max_strips >= the largest
+ * ceil(min(nw, Wb) / strip_w) over the crops (grid = n_crops x max_strips). */
 int kiri_preprocess_pack(const uint8_t* src, const KiriCropDesc* descs, int n_crops, int img_h, int Wb,
-                         int smem_bytes, uint8_t* planes_u8, void* norm_bf16, cudaStream_t stream);
+                         int smem_bytes, int max_strips, uint8_t* planes_u8, void* norm_bf16, cudaStream_t stream);
 
 /* ---------------------------------------------------------------- K2: stem layer 1
  * Replaces ConvStem.net[0:3] (kiri_ocr/model.py:215-217).  w_host[48*9], b_host[48]: BN-folded
@@ -244,10 +246,14 @@ int kiri_decode_greedy(KiriHandle* h, const void* mem_bf16, const int* len_est, 
                        int* n_out, float* sum_logp, float* step_logp, float* step_prob,
                        const int* forced_ids, int* steps_run_host, int poll_every, cudaStream_t stream);
 /* The same over the concatenated token stream of kiri_encode_multi: line b attends to the memory
- * rows [mem_row0[b], mem_row0[b] + mem_len[b]) of mem_bf16 [M_total, D] (device int arrays). */
+ * rows [mem_row0[b], mem_row0[b] + mem_len[b]) of mem_bf16 [M_total, D] (device int arrays).
+ * line_perm (nullable, device int[B]): decode slot -> line.  Sixteen consecutive slots share one
+ * thread-block cluster, so listing the lines by decreasing len_est lets every cluster stop early
+ * and lets the clusters that do not fit in the first wave hide behind the longest ones. */
 size_t kiri_decode_multi_workspace_bytes(const KiriHandle* h, int B, long long M_total, int Lmax);
 int kiri_decode_greedy_multi(KiriHandle* h, const void* mem_bf16, long long M_total, const int* mem_row0,
-                             const int* mem_len, const int* len_est, int B, int Lmax, const KiriDecodeParams* p,
+                             const int* mem_len, const int* len_est, const int* line_perm, int B, int Lmax,
+                             const KiriDecodeParams* p,
                              void* workspace, size_t workspace_bytes, int* ids, int* n_out, float* sum_logp,
                              float* step_logp, float* step_prob, const int* forced_ids, int* steps_run_host,
                              cudaStream_t stream);

@@ -72,7 +72,7 @@ _SIGS = {
     "kiri_profile_begin": (C.c_int, []),
     "kiri_profile_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]),
     "kiri_preprocess_smem_bytes": (C.c_int, [C.c_int] * 6),
-    "kiri_preprocess_pack": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
+    "kiri_preprocess_pack": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
     "kiri_conv1": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]),
     "kiri_conv3x3_bf16": (C.c_int, [vp, vp, vp] + [C.c_int] * 7 + [vp, vp]),
     "kiri_gemm_bf16": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),
@@ -89,7 +89,7 @@ _SIGS = {
     "kiri_encode_multi": (C.c_int, [vp, C.POINTER(KiriGroup), C.c_int, C.c_int, vp, C.c_size_t, vp, vp, vp, vp, vp, vp]),
     "kiri_decode_workspace_bytes": (C.c_size_t, [vp, C.c_int, C.c_int, C.c_int]),
     "kiri_decode_multi_workspace_bytes": (C.c_size_t, [vp, C.c_int, C.c_longlong, C.c_int]),
-    "kiri_decode_greedy_multi": (C.c_int, [vp, vp, C.c_longlong, vp, vp, vp, C.c_int, C.c_int, C.POINTER(KiriDecodeParams),
+    "kiri_decode_greedy_multi": (C.c_int, [vp, vp, C.c_longlong, vp, vp, vp, vp, C.c_int, C.c_int, C.POINTER(KiriDecodeParams),
                                            vp, C.c_size_t, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int), vp]),
     "kiri_decode_greedy": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(KiriDecodeParams), vp,
                                      C.c_size_t, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int), C.c_int, vp]),

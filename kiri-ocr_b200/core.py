@@ -256,8 +256,8 @@ class OCR:
         buf = torch.empty(page.size + 16, dtype=torch.uint8).pin_memory()
         buf.numpy()[:page.size] = page.reshape(-1)
         from .engine import plan_groups
-        (idx, descs, smem), = plan_groups(ent, self.cfg, "parity").values()
-        planes, _ = eng.preprocess(buf.to(eng.device), descs, self.cfg.IMG_W, smem)
+        (idx, descs, smem, n_strips), = plan_groups(ent, self.cfg, "parity").values()
+        planes, _ = eng.preprocess(buf.to(eng.device), descs, self.cfg.IMG_W, smem, n_strips)
         t = planes[0].float().cpu() / 255.0
         return ((t - 0.5) / 0.5).unsqueeze(0).unsqueeze(0)
 

@@ -364,7 +364,7 @@ extern "C" int kiri_decode_greedy(KiriHandle* h, const void* mem_bf16, const int
     int cs = 8;
     if (const char* e = getenv("KIRI_DEC_CLUSTER")) cs = atoi(e);
     { ProfScope ps_step(PS_DEC_STEP, stream);
-      KIRI_TRY(fused_decoder_run(h, crosskv, L * 2 * D, nullptr, nullptr, T, self_k, self_v, len_est, forced_ids, B, Lmax, p,
+      KIRI_TRY(fused_decoder_run(h, crosskv, L * 2 * D, nullptr, nullptr, T, self_k, self_v, len_est, forced_ids, nullptr, B, Lmax, p,
                                  ids, n_out, sum_logp, step_logp, step_prob, step_dev, cs, stream)); }
     if (steps_run_host) {
       KIRI_CHECK_CUDA(cudaMemcpyAsync(alive_host, step_dev, sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -462,7 +462,7 @@ extern "C" size_t kiri_decode_multi_workspace_bytes(const KiriHandle* h, int B, 
 }
 
 extern "C" int kiri_decode_greedy_multi(KiriHandle* h, const void* mem_bf16, long long M_total, const int* mem_row0,
-                                        const int* mem_len, const int* len_est, int B, int Lmax,
+                                        const int* mem_len, const int* len_est, const int* line_perm, int B, int Lmax,
                                         const KiriDecodeParams* p, void* workspace, size_t workspace_bytes, int* ids,
                                         int* n_out, float* sum_logp, float* step_logp, float* step_prob,
                                         const int* forced_ids, int* steps_run_host, cudaStream_t stream) {
@@ -489,7 +489,7 @@ extern "C" int kiri_decode_greedy_multi(KiriHandle* h, const void* mem_bf16, lon
   if (const char* e = getenv("KIRI_DEC_CLUSTER")) cs = atoi(e);
   { ProfScope ps_step(PS_DEC_STEP, stream);
     KIRI_TRY(fused_decoder_run(h, crosskv, static_cast<int>(L * 2 * D), mem_row0, mem_len, 0, self_k, self_v, len_est,
-                               forced_ids, B, Lmax, p, ids, n_out, sum_logp, step_logp, step_prob, steps_dev, cs, stream)); }
+                               forced_ids, line_perm, B, Lmax, p, ids, n_out, sum_logp, step_logp, step_prob, steps_dev, cs, stream)); }
   if (steps_run_host) {
     static int* steps_host = nullptr;
     if (!steps_host) KIRI_CHECK_CUDA(cudaMallocHost(&steps_host, sizeof(int)));

@@ -52,6 +52,7 @@ struct FusedArgs {
   int T;
   __nv_bfloat16 *self_k, *self_v;                     // [layers][B][Lmax][D]
   const int* len_est; const int* forced;
+  const int* line_perm;                               // nullable: decode slot -> line (longest lines first)
   int B, Lmax;
   KiriDecodeParams p;
   int *ids, *n_out; float *sum_logp, *step_logp, *step_prob;
@@ -156,12 +157,17 @@ struct LineState {
   int valid[kFL];
   int row0[kFL];
   int mlen[kFL];
+  int line[kFL];         // global line index of each slot (outputs, forced ids)
 };
 
 struct FusedSmem {                       // byte offsets into dynamic shared memory
-  int x, gath, a, obuf, hbuf, qloc, logits, part, vstage, state, total;
+  int x, gath, a, obuf, hbuf, qloc, logits, part, vstage, state, params, total;
 };
-__host__ __device__ inline FusedSmem fused_smem_plan(int ff, int Vp, int cs) {
+// Biases and LayerNorm affines of every layer live in shared memory for the whole decode: every
+// cluster barrier invalidates L1, so a parameter read from global costs an L2 round trip per phase.
+// Per layer (floats): bqkv 768 | bo 256 | bcq 256 | bco 256 | b1 ff | b2 256 | ln1 g,b | ln2 g,b | ln3 g,b
+__host__ __device__ inline int fused_layer_floats(int ff) { return 768 + 4 * 256 + ff + 6 * 256; }
+__host__ __device__ inline FusedSmem fused_smem_plan(int ff, int Vp, int cs, int layers) {
   FusedSmem s;
   int off = 0;
   auto take = [&](int bytes) { const int o = off; off += (bytes + 127) & ~127; return o; };
@@ -175,6 +181,7 @@ __host__ __device__ inline FusedSmem fused_smem_plan(int ff, int Vp, int cs) {
   s.part = take(kFWarps * 512);
   s.vstage = take(kFWarps * 32 * kHd * 2);
   s.state = take(static_cast<int>(sizeof(LineState)));
+  s.params = take((layers * fused_layer_floats(ff) + 2 * Vp + 512) * 4);
   s.total = off;
   return s;
 }
@@ -242,6 +249,24 @@ __device__ __forceinline__ float attend_warp(const float* q, const __nv_bfloat16
   return o / l_run;
 }
 
+// ln8 (ln_utils.cuh) with the affine in shared memory (plain loads)
+__device__ __forceinline__ void ln8s(float (&v)[8], const float* g, const float* b, int lane) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += v[i];
+  const float mean = warp_sum(s) * (1.0f / kD);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; q += d * d; }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / kD) + kLnEps);
+  const float4 g0 = *reinterpret_cast<const float4*>(g + lane * 8), g1 = *reinterpret_cast<const float4*>(g + lane * 8 + 4);
+  const float4 b0 = *reinterpret_cast<const float4*>(b + lane * 8), b1 = *reinterpret_cast<const float4*>(b + lane * 8 + 4);
+  const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+  const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = (v[i] - mean) * rstd * gg[i] + bb[i];
+}
+
 __device__ __forceinline__ float warp_lse_s(const float* x, int n, int lane) {
   float m = -INFINITY;
   for (int v = lane; v < n; v += 32) m = fmaxf(m, x[v]);
@@ -254,6 +279,7 @@ __device__ __forceinline__ float warp_lse_s(const float* x, int n, int lane) {
 
 // Phase timing of cluster 0 / rank 0 (clock64 deltas), read back with kiri_debug_decode_timing().
 __device__ long long g_dec_prof[32];
+__device__ long long g_dec_clu[64 * 4];     // per cluster: start ns, end ns, steps, smid of rank 0
 #define DEC_TICK(slot)                                                   \
   do {                                                                   \
     if (A.timing && blockIdx.x == 0 && threadIdx.x == 0) {               \
@@ -272,7 +298,7 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int HPC = kHeads / CS;                 // heads per CTA
   constexpr int DC = 256 / CS;                     // output columns of a D-wide projection per CTA
-  const FusedSmem L = fused_smem_plan(A.ff, A.Vp, CS);
+  const FusedSmem L = fused_smem_plan(A.ff, A.Vp, CS, A.layers);
   float* x = reinterpret_cast<float*>(sm + L.x);
   float* gath = reinterpret_cast<float*>(sm + L.gath);
   __nv_bfloat16* a = reinterpret_cast<__nv_bfloat16*>(sm + L.a);
@@ -283,6 +309,25 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
   float* part = reinterpret_cast<float*>(sm + L.part);
   __nv_bfloat16* vst = reinterpret_cast<__nv_bfloat16*>(sm + L.vstage) + warp * 32 * kHd;
   LineState* st = reinterpret_cast<LineState*>(sm + L.state);
+  float* prm = reinterpret_cast<float*>(sm + L.params);
+  const int lfl = fused_layer_floats(A.ff);
+  float* p_heads = prm + A.layers * lfl;            // 2*Vp head biases, then dec_ln g | b
+  float* p_decln = p_heads + 2 * A.Vp;
+  for (int l = 0; l < A.layers; ++l) {
+    const FusedLayer& W = A.layer[l];
+    float* d = prm + l * lfl;
+    for (int t = threadIdx.x; t < 768; t += kFThreads) d[t] = __ldg(W.bqkv + t);
+    for (int t = threadIdx.x; t < 256; t += kFThreads) {
+      d[768 + t] = __ldg(W.bo + t); d[1024 + t] = __ldg(W.bcq + t); d[1280 + t] = __ldg(W.bco + t);
+      d[1536 + A.ff + t] = __ldg(W.b2 + t);
+      float* n = d + 1792 + A.ff;
+      n[t] = __ldg(W.ln1_g + t); n[256 + t] = __ldg(W.ln1_b + t); n[512 + t] = __ldg(W.ln2_g + t);
+      n[768 + t] = __ldg(W.ln2_b + t); n[1024 + t] = __ldg(W.ln3_g + t); n[1280 + t] = __ldg(W.ln3_b + t);
+    }
+    for (int t = threadIdx.x; t < A.ff; t += kFThreads) d[1536 + t] = __ldg(W.b1 + t);
+  }
+  for (int t = threadIdx.x; t < 2 * A.Vp; t += kFThreads) p_heads[t] = __ldg(A.bheads + t);
+  for (int t = threadIdx.x; t < 256; t += kFThreads) { p_decln[t] = __ldg(A.dec_ln_g + t); p_decln[256 + t] = __ldg(A.dec_ln_b + t); }
   constexpr int lda = 256 + kPad;
   const int ldh = A.ff + kPad;
   const int b0 = cid * kFL;
@@ -302,8 +347,10 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
 
   // ---- init (model.py:416-425: Python float arithmetic, int() truncation)
   if (threadIdx.x < kFL) {
-    const int i = threadIdx.x, b = b0 + i;
-    const bool ok = b < A.B;
+    const int i = threadIdx.x;
+    const bool ok = b0 + i < A.B;
+    const int b = ok ? (A.line_perm ? A.line_perm[b0 + i] : b0 + i) : 0;
+    st->line[i] = b;
     int ms = 0, tl = 0, Tm = A.T, r0 = 0;
     if (ok) {
       tl = A.len_est[b];
@@ -327,6 +374,13 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
   csync();                                          // every CTA of the cluster is resident and initialised
 
   long long t_last = clock64();
+  if (A.timing && rank == 0 && threadIdx.x == 0 && cid < 64) {
+    unsigned long long ns; unsigned smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    g_dec_clu[cid * 4 + 0] = static_cast<long long>(ns);
+    g_dec_clu[cid * 4 + 3] = smid;
+  }
   int step = 0;
   for (; step < A.Lmax; ++step) {
     {
@@ -349,7 +403,7 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
         v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
       }
       st_f32x8(x + i * D + lane * 8, v);
-      ln8(v, A.layer[0].ln1_g, A.layer[0].ln1_b, lane);
+      ln8s(v, prm + 1792 + A.ff, prm + 1792 + A.ff + 256, lane);
       st_bf16x8(a + i * lda + lane * 8, v);
     }
     __syncthreads();
@@ -357,6 +411,8 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
 
     for (int l = 0; l < A.layers; ++l) {
       const FusedLayer& W = A.layer[l];
+      const float* PB = prm + l * lfl;                 // this layer's biases
+      const float* PN = PB + 1792 + A.ff;              // ln1 g,b | ln2 g,b | ln3 g,b
       __nv_bfloat16* kc = A.self_k + static_cast<size_t>(l) * A.B * A.Lmax * D;
       __nv_bfloat16* vc = A.self_v + static_cast<size_t>(l) * A.B * A.Lmax * D;
       // ---- A: q,k,v of my heads.  q -> qloc (fp32), k/v -> global cache row `step` (bf16)
@@ -364,7 +420,7 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
                [&](int i) { const int sec = i / (4 * HPC), rem = i - sec * 4 * HPC; return sec * 32 + rank * HPC * 4 + rem; },
                part,
                [&](int row, int col, float v0, float v1) {
-                 v0 += __ldg(W.bqkv + col); v1 += __ldg(W.bqkv + col + 1);
+                 v0 += PB[col]; v1 += PB[col + 1];
                  const int sec = col >> 8, c = col & 255;
                  if (sec == 0) {
                    *reinterpret_cast<float2*>(qloc + row * DC + (c - rank * DC)) = make_float2(v0, v1);
@@ -396,7 +452,7 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
       // ---- C: out-proj slice -> gath (all CTAs)
       cta_gemm(W.wo, D, obuf, lda, DC / 8, [&](int i) { return rank * (DC / 8) + i; }, part,
                [&](int row, int col, float v0, float v1) {
-                 const float2 v = make_float2(v0 + __ldg(W.bo + col), v1 + __ldg(W.bo + col + 1));
+                 const float2 v = make_float2(v0 + PB[768 + col], v1 + PB[768 + col + 1]);
 #pragma unroll
                  for (int d = 0; d < CS; ++d) *reinterpret_cast<float2*>(r_gath[d] + row * D + col) = v;
                });
@@ -412,7 +468,7 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
         v[0] = x0.x + g0.x; v[1] = x0.y + g0.y; v[2] = x0.z + g0.z; v[3] = x0.w + g0.w;
         v[4] = x1.x + g1.x; v[5] = x1.y + g1.y; v[6] = x1.z + g1.z; v[7] = x1.w + g1.w;
         st_f32x8(x + i * D + lane * 8, v);
-        ln8(v, W.ln2_g, W.ln2_b, lane);
+        ln8s(v, PN + 512, PN + 768, lane);
         st_bf16x8(a + i * lda + lane * 8, v);
       }
       __syncthreads();
@@ -421,7 +477,7 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
       cta_gemm(W.wcq, D, a, lda, DC / 8, [&](int i) { return rank * (DC / 8) + i; }, part,
                [&](int row, int col, float v0, float v1) {
                  *reinterpret_cast<float2*>(qloc + row * DC + (col - rank * DC)) =
-                     make_float2(v0 + __ldg(W.bcq + col), v1 + __ldg(W.bcq + col + 1));
+                     make_float2(v0 + PB[1024 + col], v1 + PB[1024 + col + 1]);
                });
       __syncthreads();
       DEC_TICK(7);
@@ -446,7 +502,7 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
       // ---- G: cross out-proj slice -> gath
       cta_gemm(W.wco, D, obuf, lda, DC / 8, [&](int i) { return rank * (DC / 8) + i; }, part,
                [&](int row, int col, float v0, float v1) {
-                 const float2 v = make_float2(v0 + __ldg(W.bco + col), v1 + __ldg(W.bco + col + 1));
+                 const float2 v = make_float2(v0 + PB[1280 + col], v1 + PB[1280 + col + 1]);
 #pragma unroll
                  for (int d = 0; d < CS; ++d) *reinterpret_cast<float2*>(r_gath[d] + row * D + col) = v;
                });
@@ -462,7 +518,7 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
         v[0] = x0.x + g0.x; v[1] = x0.y + g0.y; v[2] = x0.z + g0.z; v[3] = x0.w + g0.w;
         v[4] = x1.x + g1.x; v[5] = x1.y + g1.y; v[6] = x1.z + g1.z; v[7] = x1.w + g1.w;
         st_f32x8(x + i * D + lane * 8, v);
-        ln8(v, W.ln3_g, W.ln3_b, lane);
+        ln8s(v, PN + 1024, PN + 1280, lane);
         st_bf16x8(a + i * lda + lane * 8, v);
       }
       __syncthreads();
@@ -472,7 +528,7 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
         const int ntc = A.ff / 8 / CS;
         cta_gemm(W.w1, D, a, lda, ntc, [&](int i) { return rank * ntc + i; }, part,
                  [&](int row, int col, float v0, float v1) {
-                   const uint32_t pk = pack_bf16x2(gelu_erf(v0 + __ldg(W.b1 + col)), gelu_erf(v1 + __ldg(W.b1 + col + 1)));
+                   const uint32_t pk = pack_bf16x2(gelu_erf(v0 + PB[1536 + col]), gelu_erf(v1 + PB[1536 + col + 1]));
 #pragma unroll
                    for (int d = 0; d < CS; ++d) *reinterpret_cast<uint32_t*>(r_hbuf[d] + row * ldh + col) = pk;
                  });
@@ -483,7 +539,7 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
       // ---- J: FFN second linear slice -> gath
       cta_gemm(W.w2, A.ff, hbuf, ldh, DC / 8, [&](int i) { return rank * (DC / 8) + i; }, part,
                [&](int row, int col, float v0, float v1) {
-                 const float2 v = make_float2(v0 + __ldg(W.b2 + col), v1 + __ldg(W.b2 + col + 1));
+                 const float2 v = make_float2(v0 + PB[1536 + A.ff + col], v1 + PB[1536 + A.ff + col + 1]);
 #pragma unroll
                  for (int d = 0; d < CS; ++d) *reinterpret_cast<float2*>(r_gath[d] + row * D + col) = v;
                });
@@ -492,8 +548,8 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
       DEC_TICK(16);
       // ---- K: x += gath; a = LN1 of the next layer (or dec_ln)
       {
-        const float* ng = (l + 1 < A.layers) ? A.layer[l + 1].ln1_g : A.dec_ln_g;
-        const float* nb = (l + 1 < A.layers) ? A.layer[l + 1].ln1_b : A.dec_ln_b;
+        const float* ng = (l + 1 < A.layers) ? PN + lfl : p_decln;            // next layer's ln1, or dec_ln
+        const float* nb = ng + 256;
         const int i = warp;
         float v[8];
         const float4 x0 = *reinterpret_cast<const float4*>(x + i * D + lane * 8), x1 = *reinterpret_cast<const float4*>(x + i * D + lane * 8 + 4);
@@ -501,7 +557,7 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
         v[0] = x0.x + g0.x; v[1] = x0.y + g0.y; v[2] = x0.z + g0.z; v[3] = x0.w + g0.w;
         v[4] = x1.x + g1.x; v[5] = x1.y + g1.y; v[6] = x1.z + g1.z; v[7] = x1.w + g1.w;
         st_f32x8(x + i * D + lane * 8, v);
-        ln8(v, ng, nb, lane);
+        ln8s(v, ng, nb, lane);
         st_bf16x8(a + i * lda + lane * 8, v);
       }
       __syncthreads();
@@ -513,7 +569,7 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
       const int t0 = rank * nth / CS, t1 = (rank + 1) * nth / CS;
       cta_gemm(A.wheads, D, a, lda, t1 - t0, [&](int i) { return t0 + i; }, part,
                [&](int row, int col, float v0, float v1) {
-                 const float2 v = make_float2(v0 + __ldg(A.bheads + col), v1 + __ldg(A.bheads + col + 1));
+                 const float2 v = make_float2(v0 + p_heads[col], v1 + p_heads[col + 1]);
 #pragma unroll
                  for (int d = 0; d < CS; ++d) *reinterpret_cast<float2*>(r_logits[d] + row * 2 * A.Vp + col) = v;
                });
@@ -523,7 +579,7 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
     DEC_TICK(19);
     // ---- token selection, one warp per line, replicated in every CTA (model.py:480-537)
     {
-      const int i = warp, b = b0 + i;
+      const int i = warp, b = st->line[i];
       if (!st->finished[i]) {
         const KiriDecodeParams& p = A.p;
         const float* dec = logits + i * 2 * A.Vp;
@@ -602,6 +658,12 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
     DEC_TICK(20);
   }
   if (rank == 0 && threadIdx.x == 0 && A.steps_max) atomicMax(A.steps_max, step);
+  if (A.timing && rank == 0 && threadIdx.x == 0 && cid < 64) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    g_dec_clu[cid * 4 + 1] = static_cast<long long>(ns);
+    g_dec_clu[cid * 4 + 2] = step;
+  }
   csync();                                          // no CTA may exit while peers can still write its smem
 }
 
@@ -662,7 +724,7 @@ void fused_decoder_free(KiriHandle* h) {
 
 template <int CS>
 static int launch_fused(const FusedArgs& a, int n_clusters, cudaStream_t stream) {
-  const FusedSmem L = fused_smem_plan(a.ff, a.Vp, CS);
+  const FusedSmem L = fused_smem_plan(a.ff, a.Vp, CS, a.layers);
   auto kern = dec_fused_kernel<CS>;
   static int configured = 0;
   if (configured < L.total) {
@@ -685,14 +747,15 @@ static int launch_fused(const FusedArgs& a, int n_clusters, cudaStream_t stream)
 
 // Runs the whole greedy decode; crosskv must already hold the cross K/V rows.
 int fused_decoder_run(KiriHandle* h, const __nv_bfloat16* crosskv, int crosskv_ld, const int* mem_row0, const int* mem_len,
-                      int T, __nv_bfloat16* self_k, __nv_bfloat16* self_v, const int* len_est, const int* forced, int B,
-                      int Lmax, const KiriDecodeParams* p, int* ids, int* n_out, float* sum_logp, float* step_logp,
-                      float* step_prob, int* steps_max_dev, int cluster_size, cudaStream_t stream) {
+                      int T, __nv_bfloat16* self_k, __nv_bfloat16* self_v, const int* len_est, const int* forced,
+                      const int* line_perm, int B, int Lmax, const KiriDecodeParams* p, int* ids, int* n_out,
+                      float* sum_logp, float* step_logp, float* step_prob, int* steps_max_dev, int cluster_size,
+                      cudaStream_t stream) {
   FusedPacked* fp = reinterpret_cast<FusedPacked*>(h->fused);
   KIRI_REQUIRE(fp, "fused decoder: handle was created without decoder weights");
   FusedArgs a = fp->args;
   a.crosskv = crosskv; a.crosskv_ld = crosskv_ld; a.mem_row0 = mem_row0; a.mem_len = mem_len; a.T = T;
-  a.self_k = self_k; a.self_v = self_v; a.len_est = len_est; a.forced = forced; a.B = B; a.Lmax = Lmax; a.p = *p;
+  a.self_k = self_k; a.self_v = self_v; a.len_est = len_est; a.forced = forced; a.line_perm = line_perm; a.B = B; a.Lmax = Lmax; a.p = *p;
   a.ids = ids; a.n_out = n_out; a.sum_logp = sum_logp; a.step_logp = step_logp; a.step_prob = step_prob;
   a.steps_max = steps_max_dev;
   a.timing = getenv("KIRI_DEC_TIMING") != nullptr;
@@ -716,5 +779,11 @@ extern "C" int kiri_debug_decode_timing(long long* out_host, int n) {
   for (int i = 0; i < n && i < 32; ++i) out_host[i] = buf[i];
   long long zero[32] = {0};
   if (cudaMemcpyToSymbol(kiri::g_dec_prof, zero, sizeof(zero)) != cudaSuccess) return -2;
+  return 0;
+}
+extern "C" int kiri_debug_decode_clusters(long long* out_host, int n) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return -2;
+  if (n > 256) n = 256;
+  if (cudaMemcpyFromSymbol(out_host, kiri::g_dec_clu, sizeof(long long) * n) != cudaSuccess) return -2;
   return 0;
 }

@@ -21,9 +21,10 @@ int gemm_call(const void* a, const void* w, const float* bias, int M, int N, int
 int fused_decoder_build(KiriHandle* h);
 void fused_decoder_free(KiriHandle* h);
 int fused_decoder_run(KiriHandle* h, const __nv_bfloat16* crosskv, int crosskv_ld, const int* mem_row0, const int* mem_len,
-                      int T, __nv_bfloat16* self_k, __nv_bfloat16* self_v, const int* len_est, const int* forced, int B,
-                      int Lmax, const KiriDecodeParams* p, int* ids, int* n_out, float* sum_logp, float* step_logp,
-                      float* step_prob, int* steps_max_dev, int cluster_size, cudaStream_t stream);
+                      int T, __nv_bfloat16* self_k, __nv_bfloat16* self_v, const int* len_est, const int* forced,
+                      const int* line_perm, int B, int Lmax, const KiriDecodeParams* p, int* ids, int* n_out,
+                      float* sum_logp, float* step_logp, float* step_prob, int* steps_max_dev, int cluster_size,
+                      cudaStream_t stream);
 }  // namespace kiri
 
 namespace kiri {

@@ -5,7 +5,9 @@
 //           ResizeKeepRatioPadNoCrop      kiri_ocr/model.py:316-331
 //           preprocess_pil                kiri_ocr/model.py:334-339   (per line, CPU, Pillow)
 //
-// One CTA per crop.  Pillow's resample is integer fixed point: float64 triangle weights,
+// One CTA per (crop, strip of output columns): a 640-wide line is five independent CTAs, so a
+// 256-line batch fills the machine instead of leaving it latency-bound on 256 long-running CTAs.
+// Pillow's resample is integer fixed point: float64 triangle weights,
 // normalised, quantised to int(0.5 + w*2^22); each pass accumulates in integers, adds 2^21,
 // shifts by 22 and clips to uint8.  The weights are recomputed on the device in float64 with
 // explicitly rounded operations (no FMA contraction), which reproduces the host bit for bit.
@@ -78,6 +80,8 @@ preprocess_pack_kernel(const uint8_t* __restrict__ src, const KiriCropDesc* __re
   const int tid = threadIdx.x;
   const int w = d.w, h = d.h, nw = d.nw;
   const int Wout = nw < Wb ? nw : Wb;
+  const int strip0 = static_cast<int>(blockIdx.y) * d.strip_w;   // first output column of this CTA
+  if (strip0 >= Wout) return;                                    // (whole CTA: no barrier is skipped)
   const uint8_t* crop = src + d.src_offset;
   uint8_t* plane = planes + static_cast<size_t>(d.out_index) * img_h * Wb;
   __nv_bfloat16* nplane = norm_out ? norm_out + static_cast<size_t>(d.out_index) * img_h * Wb : nullptr;
@@ -134,7 +138,8 @@ preprocess_pack_kernel(const uint8_t* __restrict__ src, const KiriCropDesc* __re
     for (int y = tid; y < img_h; y += kPreThreads) ymin[y] = fill_coefs(y, h, img_h, ksize_v, kv + y * ksize_v, 1);
   }
 
-  for (int c0 = 0; c0 < Wout; c0 += Ws) {
+  {
+    const int c0 = strip0;
     const int cw = (Wout - c0) < Ws ? (Wout - c0) : Ws;
     __syncthreads();
     // horizontal coefficients of this strip, tap-major so lanes hit consecutive banks
@@ -208,7 +213,7 @@ preprocess_pack_kernel(const uint8_t* __restrict__ src, const KiriCropDesc* __re
   }
   // gray-128 padding on the right (model.py:329-330)
   const int padw = Wb - Wout;
-  if (padw > 0) {
+  if (padw > 0 && blockIdx.y == 0) {
     const float f = __fdiv_rn(__fsub_rn(__fdiv_rn(128.0f, 255.0f), 0.5f), 0.5f);
     const __nv_bfloat16 fb = __float2bfloat16_rn(f);
     for (int idx = tid; idx < img_h * padw; idx += kPreThreads) {
@@ -243,10 +248,10 @@ extern "C" int kiri_preprocess_smem_bytes(int w, int h, int nw, int img_h, int W
 }
 
 extern "C" int kiri_preprocess_pack(const uint8_t* src, const KiriCropDesc* descs_dev, int n_crops,
-                                    int img_h, int Wb, int smem_bytes, uint8_t* planes_u8,
+                                    int img_h, int Wb, int smem_bytes, int max_strips, uint8_t* planes_u8,
                                     void* norm_bf16, cudaStream_t stream) {
   KIRI_REQUIRE(src && descs_dev && planes_u8, "kiri_preprocess_pack: null pointer");
-  KIRI_REQUIRE(n_crops >= 0 && img_h > 0 && Wb > 0, "kiri_preprocess_pack: bad sizes");
+  KIRI_REQUIRE(n_crops >= 0 && img_h > 0 && Wb > 0 && max_strips >= 1 && max_strips <= 65535, "kiri_preprocess_pack: bad sizes");
   if (n_crops == 0) return 0;
   static int max_optin = 0;
   if (!max_optin) {
@@ -263,7 +268,7 @@ extern "C" int kiri_preprocess_pack(const uint8_t* src, const KiriCropDesc* desc
   }
   KIRI_REQUIRE(smem_bytes <= max_optin, "kiri_preprocess_pack: %d bytes of shared memory requested, %d available",
                smem_bytes, max_optin);
-  preprocess_pack_kernel<<<n_crops, kPreThreads, smem_bytes, stream>>>(
+  preprocess_pack_kernel<<<dim3(n_crops, max_strips), kPreThreads, smem_bytes, stream>>>(
       src, descs_dev, img_h, Wb, planes_u8, reinterpret_cast<__nv_bfloat16*>(norm_bf16), smem_bytes);
   KIRI_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -30,10 +30,11 @@ BUCKETS = (128, 256, 384, 512, 640)
 DESC_DTYPE = np.dtype([("src_offset", "<i8"), ("pitch", "<i4"), ("w", "<i4"), ("h", "<i4"),
                        ("nw", "<i4"), ("out_index", "<i4"), ("strip_w", "<i4")])
 assert DESC_DTYPE.itemsize == C.sizeof(_lib.KiriCropDesc)
-PRE_SMEM_CAP = 100 * 1024          # two preprocessing CTAs per SM
+PRE_SMEM_CAP = 56 * 1024           # four preprocessing CTAs per SM
+PRE_STRIP = 128                    # output columns per preprocessing CTA
 
 
-@dataclass
+@dataclass(slots=True)
 class LineResult:
     text: str
     confidence: float
@@ -70,7 +71,7 @@ def _pre_smem(w, h, nw, img_h, Wb, strip):
 
 def plan_groups(entries: np.ndarray, cfg: CFG, width_mode: str = "parity"
                 ) -> Dict[int, Tuple[np.ndarray, np.ndarray, int]]:
-    """Group lines by batch width; returns {Wb: (line indices, descriptors, smem bytes)}."""
+    """Group lines by batch width; returns {Wb: (line indices, descriptors, smem bytes, max strips)}."""
     img_h = cfg.IMG_H
     w, h = entries[:, 2], entries[:, 3]
     nw = target_widths(w, h, img_h)
@@ -79,22 +80,29 @@ def plan_groups(entries: np.ndarray, cfg: CFG, width_mode: str = "parity"
     else:
         bk = np.array(tuple(b for b in BUCKETS if b <= cfg.IMG_W) or (cfg.IMG_W,), np.int64)
         wb = bk[np.minimum(np.searchsorted(bk, np.minimum(nw, bk[-1])), len(bk) - 1)]
+    # everything per line is computed once for the whole batch; the per-group work is slicing only
+    wout = np.minimum(nw, wb)
+    strip = np.minimum(wout, PRE_STRIP)
+    need = _pre_smem(w, h, nw, img_h, wb, strip)
+    for _ in range(6):                                       # halve strips until they fit
+        big = need > PRE_SMEM_CAP
+        if not big.any():
+            break
+        strip = np.where(big & (strip > 32), np.maximum(32, (strip // 2 + 31) // 32 * 32), strip)
+        need = _pre_smem(w, h, nw, img_h, wb, strip)
+    nstr = (wout + strip - 1) // strip
+    d_all = np.zeros(len(entries), DESC_DTYPE)
+    d_all["src_offset"], d_all["pitch"], d_all["w"], d_all["h"] = entries[:, 0], entries[:, 1], w, h
+    d_all["nw"], d_all["strip_w"] = nw, strip
+    order = np.argsort(wb, kind="stable")
+    wbs = wb[order]
+    cuts = np.nonzero(np.diff(wbs))[0] + 1
     groups = {}
-    for Wb in np.unique(wb):
-        idx = np.nonzero(wb == Wb)[0]
-        gw, gh, gnw = w[idx], h[idx], nw[idx]
-        strip = np.minimum(gnw, Wb)
-        need = _pre_smem(gw, gh, gnw, img_h, int(Wb), strip)
-        for _ in range(6):                                   # halve strips until they fit
-            big = need > PRE_SMEM_CAP
-            if not big.any():
-                break
-            strip = np.where(big & (strip > 32), np.maximum(32, (strip // 2 + 31) // 32 * 32), strip)
-            need = _pre_smem(gw, gh, gnw, img_h, int(Wb), strip)
-        d = np.zeros(len(idx), DESC_DTYPE)
-        d["src_offset"], d["pitch"], d["w"], d["h"] = entries[idx, 0], entries[idx, 1], gw, gh
-        d["nw"], d["out_index"], d["strip_w"] = gnw, np.arange(len(idx)), strip
-        groups[int(Wb)] = (idx, d, int(need.max()))
+    for lo, hi in zip(np.concatenate([[0], cuts]), np.concatenate([cuts, [len(order)]])):
+        idx = order[lo:hi]
+        d = d_all[idx]
+        d["out_index"] = np.arange(hi - lo)
+        groups[int(wbs[lo])] = (idx, d, int(need[idx].max()), int(nstr[idx].max()))
     return groups
 
 
@@ -117,6 +125,7 @@ class BatchedRecognizer:
         self.stream = torch.cuda.Stream(device=self.device)
         self._ws: Optional[torch.Tensor] = None
         self._dws: Optional[torch.Tensor] = None
+        self._build_tables()
         self.launches = 0           # kernels launched by this engine (for bench's gpu_launches)
 
     def __del__(self):
@@ -161,7 +170,7 @@ class BatchedRecognizer:
         ent = np.stack([page_offset + y1 * W + x1, np.full_like(x1, W), x2 - x1, y2 - y1], axis=1)
         return ent, valid
 
-    def plan(self, entries: np.ndarray) -> Dict[int, Tuple[np.ndarray, np.ndarray, int]]:
+    def plan(self, entries: np.ndarray) -> Dict[int, Tuple[np.ndarray, np.ndarray, int, int]]:
         return plan_groups(entries, self.cfg, self.width_mode)
 
     # ------------------------------------------------------------------ device stages
@@ -172,13 +181,48 @@ class BatchedRecognizer:
             setattr(self, which, cur)
         return cur
 
-    def preprocess(self, src_dev: torch.Tensor, descs: np.ndarray, Wb: int, smem: int,
+    def _pinned(self, name: str, n: int, dtype) -> torch.Tensor:
+        """Persistent pinned host staging buffer of at least n elements."""
+        cur = getattr(self, name, None)
+        if cur is None or cur.numel() < n:
+            cur = torch.empty(max(n, 1024), dtype=dtype).pin_memory()
+            setattr(self, name, cur)
+        return cur
+
+    def _device(self, name: str, n: int, dtype) -> torch.Tensor:
+        cur = getattr(self, name, None)
+        if cur is None or cur.numel() < n:
+            cur = torch.empty(max(n, 1024), dtype=dtype, device=self.device)
+            setattr(self, name, cur)
+        return cur
+
+    def _build_tables(self):
+        """id -> text lookup tables (object arrays) equivalent to CharTokenizer.decode_collapsed_ctc /
+        decode_dec (model.py:109-135): out-of-range ids, specials and <unk> map to ''."""
+        tok = self.tok
+        ctc = np.empty(self.pw.Cp + 1, dtype=object)
+        ctc[:] = ""
+        for i in range(self.pw.C):
+            raw = i - tok.ctc_offset
+            if 0 <= raw < tok.vocab_size:
+                ch = tok.id_to_token.get(raw, "")
+                ctc[i] = "" if ch == tok.unk_token else ch
+        dec = np.empty(self.pw.Vp + 1, dtype=object)
+        dec[:] = ""
+        for i in range(self.pw.Vd):
+            raw = i - tok.dec_offset
+            if i not in (tok.dec_pad, tok.dec_bos, tok.dec_eos) and 0 <= raw < tok.vocab_size:
+                ch = tok.id_to_token.get(raw, tok.unk_token)
+                dec[i] = "" if ch == tok.unk_token else ch
+        self._ctc_table, self._dec_table = ctc.tolist(), dec.tolist()     # plain lists: fastest per-id lookup
+
+    def preprocess(self, src_dev: torch.Tensor, descs: np.ndarray, Wb: int, smem: int, n_strips: int,
                    want_norm: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
         n = len(descs)
         dd = torch.from_numpy(descs.view(np.uint8).reshape(-1)).pin_memory().to(self.device, non_blocking=True)
         planes = torch.empty((n, self.cfg.IMG_H, Wb), dtype=torch.uint8, device=self.device)
         norm = torch.empty((n, self.cfg.IMG_H, Wb), dtype=torch.bfloat16, device=self.device) if want_norm else None
-        _lib.check(self.lib.kiri_preprocess_pack(src_dev.data_ptr(), dd.data_ptr(), n, self.cfg.IMG_H, Wb, smem,
+        _lib.check(self.lib.kiri_preprocess_pack(src_dev.data_ptr(), dd.data_ptr(), n, self.cfg.IMG_H, Wb, smem, n_strips,
                                                  planes.data_ptr(), _lib.ptr(norm), _lib.stream_ptr()),
                    "kiri_preprocess_pack")
         self.launches += 1
@@ -241,19 +285,24 @@ class BatchedRecognizer:
 
     def decode_greedy_multi(self, mem_bf16: torch.Tensor, mem_row0: torch.Tensor, mem_len: torch.Tensor,
                             len_est: torch.Tensor, Lmax: int, select_raw: bool = False,
-                            forced: Optional[torch.Tensor] = None, want_steps: bool = False):
+                            forced: Optional[torch.Tensor] = None, want_steps: bool = False, out=None):
         """One persistent decode over every line of every group (concatenated token stream)."""
         p = self.decode_params(select_raw)
         B, M = int(len_est.numel()), int(mem_bf16.shape[0])
         need = self.lib.kiri_decode_multi_workspace_bytes(self.handle, B, M, Lmax)
         ws = self._workspace(need, "_dws")
-        ids = torch.zeros((B, Lmax), dtype=torch.int32, device=self.device)
-        n_out = torch.zeros(B, dtype=torch.int32, device=self.device)
-        sum_lp = torch.zeros(B, dtype=torch.float32, device=self.device)
-        slp = torch.zeros((B, Lmax), dtype=torch.float32, device=self.device) if want_steps else None
-        spr = torch.zeros((B, Lmax), dtype=torch.float32, device=self.device) if want_steps else None
+        # longest lines first: sixteen consecutive slots share a cluster (see kiri_b200.h)
+        perm = torch.argsort(len_est, descending=True, stable=True).to(torch.int32)
+        if out is not None:
+            ids, n_out, sum_lp, slp, spr = out
+        else:
+            ids = torch.zeros((B, Lmax), dtype=torch.int32, device=self.device)
+            n_out = torch.zeros(B, dtype=torch.int32, device=self.device)
+            sum_lp = torch.zeros(B, dtype=torch.float32, device=self.device)
+            slp = torch.zeros((B, Lmax), dtype=torch.float32, device=self.device) if want_steps else None
+            spr = torch.zeros((B, Lmax), dtype=torch.float32, device=self.device) if want_steps else None
         _lib.check(self.lib.kiri_decode_greedy_multi(self.handle, mem_bf16.data_ptr(), M, mem_row0.data_ptr(),
-                                                     mem_len.data_ptr(), len_est.data_ptr(), B, Lmax, C.byref(p),
+                                                     mem_len.data_ptr(), len_est.data_ptr(), perm.data_ptr(), B, Lmax, C.byref(p),
                                                      ws.data_ptr(), need, ids.data_ptr(), n_out.data_ptr(),
                                                      sum_lp.data_ptr(), _lib.ptr(slp), _lib.ptr(spr), _lib.ptr(forced),
                                                      None, _lib.stream_ptr()), "kiri_decode_greedy_multi")
@@ -318,7 +367,7 @@ class BatchedRecognizer:
         plan = []
         row0 = 0
         mem_row0, mem_len, kv = [], [], []
-        for Wb, (idx, descs, smem) in self.plan(entries).items():
+        for Wb, (idx, descs, smem, n_strips) in self.plan(entries).items():
             dd = torch.from_numpy(descs.view(np.uint8).reshape(-1).copy()).to(self.device)
             planes = torch.empty((len(idx), self.cfg.IMG_H, Wb), dtype=torch.uint8, device=self.device)
             T = Wb // 4
@@ -326,7 +375,8 @@ class BatchedRecognizer:
             mem_len.append(np.full(len(idx), T, np.int32))
             kv.append(np.minimum((descs["nw"] + 3) // 4, T).astype(np.int32))
             row0 += len(idx) * T
-            plan.append({"Wb": Wb, "idx": idx, "descs": dd, "n": len(idx), "smem": smem, "planes": planes})
+            plan.append({"Wb": Wb, "idx": idx, "descs": dd, "n": len(idx), "smem": smem, "planes": planes,
+                         "n_strips": n_strips})
         kv_len = torch.from_numpy(np.concatenate(kv)).to(self.device) if self.width_mode == "masked" else None
         out = {"src": src_dev, "groups": plan, "kv_len": kv_len,
                "mem_row0": torch.from_numpy(np.concatenate(mem_row0)).to(self.device),
@@ -341,8 +391,8 @@ class BatchedRecognizer:
         estimates on the host once to bound its loop)."""
         for g in prep["groups"]:
             _lib.check(self.lib.kiri_preprocess_pack(prep["src"].data_ptr(), g["descs"].data_ptr(), g["n"],
-                                                     self.cfg.IMG_H, g["Wb"], g["smem"], g["planes"].data_ptr(), 0,
-                                                     _lib.stream_ptr()), "kiri_preprocess_pack")
+                                                     self.cfg.IMG_H, g["Wb"], g["smem"], g["n_strips"],
+                                                     g["planes"].data_ptr(), 0, _lib.stream_ptr()), "kiri_preprocess_pack")
             self.launches += 1
         enc = self.encode_multi([g["planes"] for g in prep["groups"]], kv_len=prep["kv_len"])
         outs = []
@@ -388,61 +438,112 @@ class BatchedRecognizer:
             return results
         src_dev = src if src.is_cuda else src.to(self.device, non_blocking=True)
         groups = list(self.plan(entries).items())
-        planes_list, kv, mem_row0, mem_len = [], [], [], []
-        row0 = 0
-        for Wb, (idx, descs, smem) in groups:
-            planes_list.append(self.preprocess(src_dev, descs, Wb, smem)[0])
-            T = Wb // 4
-            kv.append(np.minimum((descs["nw"] + 3) // 4, T).astype(np.int32))
-            mem_row0.append(row0 + np.arange(len(idx), dtype=np.int32) * T)
-            mem_len.append(np.full(len(idx), T, np.int32))
+        IMG_H, Cp = self.cfg.IMG_H, self.pw.Cp
+        n_lines = sum(len(g[1][0]) for g in groups)
+        M = sum(len(g[0]) * (Wb // 4) for Wb, g in groups)
+        # ---- ONE pinned staging buffer -> ONE H2D copy for every descriptor / per-line table
+        desc_bytes = sum(g[1][1].nbytes for g in groups)
+        meta_words = desc_bytes // 4 + 3 * n_lines                       # descs | kv_len | mem_row0 | mem_len
+        hmeta = self._pinned("_hmeta", meta_words, torch.int32)
+        hm = hmeta.numpy()
+        off, line0, row0 = 0, 0, 0
+        desc_off = []
+        kvo, r0o, mlo = desc_bytes // 4, desc_bytes // 4 + n_lines, desc_bytes // 4 + 2 * n_lines
+        for Wb, (idx, descs, smem, n_strips) in groups:
+            nb, T = descs.nbytes // 4, Wb // 4
+            hm[off:off + nb] = descs.view(np.int32).reshape(-1)
+            desc_off.append(off)
+            hm[kvo + line0:kvo + line0 + len(idx)] = np.minimum((descs["nw"] + 3) // 4, T)
+            hm[r0o + line0:r0o + line0 + len(idx)] = row0 + np.arange(len(idx), dtype=np.int32) * T
+            hm[mlo + line0:mlo + line0 + len(idx)] = T
+            off += nb
+            line0 += len(idx)
             row0 += len(idx) * T
-        kv_len = None
-        if self.width_mode == "masked":
-            kv_len = torch.from_numpy(np.concatenate(kv)).pin_memory().to(self.device, non_blocking=True)
+        dmeta = self._device("_dmeta", meta_words, torch.int32)
+        dmeta[:meta_words].copy_(hmeta[:meta_words], non_blocking=True)
+        # ---- preprocess per group, one encoder pass over all groups
+        planes_all = self._device("_planes", M * 4 * IMG_H, torch.uint8)
+        planes_list, p0 = [], 0
+        for gi, (Wb, (idx, descs, smem, n_strips)) in enumerate(groups):
+            nb = len(idx) * IMG_H * Wb
+            planes = planes_all[p0:p0 + nb].view(len(idx), IMG_H, Wb)
+            p0 += nb
+            _lib.check(self.lib.kiri_preprocess_pack(src_dev.data_ptr(), dmeta[desc_off[gi]:].data_ptr(), len(idx), IMG_H, Wb,
+                                                     smem, n_strips, planes.data_ptr(), 0, _lib.stream_ptr()),
+                       "kiri_preprocess_pack")
+            self.launches += 1
+            planes_list.append(planes)
+        kv_len = dmeta[kvo:kvo + n_lines] if self.width_mode == "masked" else None
         enc = self.encode_multi(planes_list, kv_len=kv_len)
-        ctc = []
+        # ---- CTC greedy per group into ONE packed result buffer: ids[M] | n_ids[L] | conf[L] | frames
+        want_frames = streaming and method == "ctc"
+        res_words = M + 2 * n_lines + (2 * M if want_frames else 0)
+        dres = self._device("_dres", res_words, torch.int32)
+        ids_all, n_all = dres[:M], dres[M:M + n_lines]
+        conf_all = dres[M + n_lines:M + 2 * n_lines].view(torch.float32)
+        fid_all = dres[M + 2 * n_lines:2 * M + 2 * n_lines] if want_frames else None
+        fpr_all = dres[2 * M + 2 * n_lines:3 * M + 2 * n_lines].view(torch.float32) if want_frames else None
+        line0 = 0
         for (r0, B, T) in enc["rows"]:
-            ctc.append(self.ctc_greedy(enc["logits"][r0:r0 + B * T].view(B, T, self.pw.Cp),
-                                       want_frames=streaming and method == "ctc"))
-        order = np.concatenate([idx for _, (idx, _, _) in groups])          # line index of every concatenated slot
-        tok = self.tok
-        if method == "ctc":
-            torch.cuda.current_stream().synchronize()
-            pos = 0
-            for (ids, n_ids, conf, fids, fprob) in ctc:
-                ids_h, n_h, c_h = ids.cpu().numpy(), n_ids.cpu().numpy(), conf.cpu().numpy()
-                f_h = fids.cpu().numpy() if fids is not None else None
-                p_h = fprob.cpu().numpy() if fprob is not None else None
-                for j in range(len(n_h)):
-                    row = ids_h[j, :n_h[j]]
-                    results[order[pos + j]] = LineResult(tok.decode_collapsed_ctc(row.tolist()), float(c_h[j]), float(c_h[j]),
-                                                         row, frame_ids=None if f_h is None else f_h[j],
-                                                         frame_prob=None if p_h is None else p_h[j], len_est=int(n_h[j]))
-                pos += len(n_h)
-            return results
-        len_est = torch.cat([c[1] for c in ctc]) if len(ctc) > 1 else ctc[0][1]
-        conf = torch.cat([c[2] for c in ctc]) if len(ctc) > 1 else ctc[0][2]
-        len_h = len_est.cpu().numpy()                              # length estimates bound the loop
-        Lmax = self.max_steps_bound(int(len_h.max()), max(T for _, _, T in enc["rows"]))
-        r0_dev = torch.from_numpy(np.concatenate(mem_row0)).pin_memory().to(self.device, non_blocking=True)
-        ml_dev = torch.from_numpy(np.concatenate(mem_len)).pin_memory().to(self.device, non_blocking=True)
-        d_ids, n_out, sum_lp, slp, spr = self.decode_greedy_multi(enc["mem_bf16"], r0_dev, ml_dev, len_est, Lmax,
-                                                                  select_raw=streaming, want_steps=True)
+            _lib.check(self.lib.kiri_ctc_greedy(enc["logits"][r0:].data_ptr(), _lib.DTYPE_F32, B, T, self.pw.C, Cp,
+                                                ids_all[r0:].data_ptr(), n_all[line0:].data_ptr(), conf_all[line0:].data_ptr(),
+                                                _lib.ptr(fid_all[r0:] if want_frames else None),
+                                                _lib.ptr(fpr_all[r0:] if want_frames else None), _lib.stream_ptr()),
+                       "kiri_ctc_greedy")
+            self.launches += 1
+            line0 += B
+        order = np.concatenate([g[1][0] for g in groups])          # line index of every concatenated slot
+        hres = self._pinned("_hres", res_words, torch.int32)
+        hres[:res_words].copy_(dres[:res_words], non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        ids_h, n_h, c_h = d_ids.cpu().numpy(), n_out.cpu().numpy(), conf.cpu().numpy()
-        slp_h, spr_h = slp.cpu().numpy(), spr.cpu().numpy()
+        hr = hres.numpy()[:res_words].copy()                        # the pinned buffer is reused by the next call
+        n_h = hr[M:M + n_lines]
+        c_h = hr[M + n_lines:M + 2 * n_lines].view(np.float32)
+        if method == "ctc":
+            tab = self._ctc_table
+            pos = 0
+            for (r0, B, T) in enc["rows"]:
+                ids_h = hr[r0:r0 + B * T].reshape(B, T)
+                f_h = hr[M + 2 * n_lines + r0:M + 2 * n_lines + r0 + B * T].reshape(B, T) if want_frames else None
+                p_h = hr[2 * M + 2 * n_lines + r0:2 * M + 2 * n_lines + r0 + B * T].view(np.float32).reshape(B, T) if want_frames else None
+                for j in range(B):
+                    k = pos + j
+                    row = ids_h[j, :n_h[k]]
+                    cf = float(c_h[k])
+                    results[order[k]] = LineResult("".join([tab[i] for i in row.tolist()]), cf, cf, row,
+                                                   frame_ids=None if f_h is None else f_h[j],
+                                                   frame_prob=None if p_h is None else p_h[j], len_est=int(n_h[k]))
+                pos += B
+            return results
+        # ---- greedy attention decoder over all lines at once
+        len_h = n_h                                                  # length estimates bound the loop
+        Lmax = self.max_steps_bound(int(len_h.max()), max(T for _, _, T in enc["rows"]))
+        dec_words = n_lines * Lmax * 3 + 2 * n_lines
+        ddec = self._device("_ddec", dec_words, torch.int32)
+        LL = n_lines * Lmax
+        d_ids, n_out = ddec[:LL].view(n_lines, Lmax), ddec[LL:LL + n_lines]
+        sum_lp = ddec[LL + n_lines:LL + 2 * n_lines].view(torch.float32)
+        slp = ddec[LL + 2 * n_lines:2 * LL + 2 * n_lines].view(torch.float32).view(n_lines, Lmax)
+        spr = ddec[2 * LL + 2 * n_lines:3 * LL + 2 * n_lines].view(torch.float32).view(n_lines, Lmax)
+        self.decode_greedy_multi(enc["mem_bf16"], dmeta[r0o:r0o + n_lines], dmeta[mlo:mlo + n_lines], n_all, Lmax,
+                                 select_raw=streaming, out=(d_ids, n_out, sum_lp, slp, spr))
+        hdec = self._pinned("_hdec", dec_words, torch.int32)
+        hdec[:dec_words].copy_(ddec[:dec_words], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        hd = hdec.numpy()[:dec_words].copy()
+        ids_h, no_h = hd[:LL].reshape(n_lines, Lmax), hd[LL:LL + n_lines]
+        slp_h = hd[LL + 2 * n_lines:2 * LL + 2 * n_lines].view(np.float32).reshape(n_lines, Lmax)
+        spr_h = hd[2 * LL + 2 * n_lines:3 * LL + 2 * n_lines].view(np.float32).reshape(n_lines, Lmax)
+        tab, eos = self._dec_table, self.tok.dec_eos
         for j, li in enumerate(order):
-            row = ids_h[j, :n_h[j]]
-            text_ids = []
-            for t in row.tolist():
-                if t == tok.dec_eos:
-                    break
-                text_ids.append(t)
-            lps = slp_h[j, :n_h[j]].astype(np.float64)
-            dec_conf = min(1.0, max(0.0, math.exp(float(lps.sum()) / len(lps)))) if len(lps) else 0.0
-            results[li] = LineResult(tok.decode_dec(text_ids), 0.6 * dec_conf + 0.4 * float(c_h[j]),
-                                     float(c_h[j]), row, step_logp=slp_h[j, :n_h[j]], step_prob=spr_h[j, :n_h[j]],
+            nj = int(no_h[j])
+            row = ids_h[j, :nj]
+            hit = np.nonzero(row == eos)[0]
+            text_ids = row[:hit[0]] if len(hit) else row
+            lps = slp_h[j, :nj].astype(np.float64)
+            dec_conf = min(1.0, max(0.0, math.exp(float(lps.sum()) / nj))) if nj else 0.0
+            results[li] = LineResult("".join([tab[i] for i in text_ids.tolist()]), 0.6 * dec_conf + 0.4 * float(c_h[j]),
+                                     float(c_h[j]), row, step_logp=slp_h[j, :nj], step_prob=spr_h[j, :nj],
                                      len_est=int(len_h[j]))
         return results
 

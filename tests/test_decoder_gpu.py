@@ -22,8 +22,8 @@ DEC_LOGP_ATOL = 0.35
 
 def _encode(eng, crops):
     buf, ent = eng.pack_crops(crops)
-    idx, descs, smem = eng.plan(ent)[640]
-    planes, _ = eng.preprocess(buf.cuda(), descs, 640, smem)
+    idx, descs, smem, n_strips = eng.plan(ent)[640]
+    planes, _ = eng.preprocess(buf.cuda(), descs, 640, smem, n_strips)
     enc = eng.encode(planes)
     ids, n_ids, conf, _, _ = eng.ctc_greedy(enc["logits"])
     return enc, n_ids, conf

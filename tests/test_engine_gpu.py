@@ -67,8 +67,8 @@ def test_encoder_and_ctc_parity(engines, golden, name):
     buf, ent = eng.pack_crops(crops)
     groups = eng.plan(ent)
     assert list(groups) == [640]
-    idx, descs, smem = groups[640]
-    planes, _ = eng.preprocess(buf.cuda(), descs, 640, smem)
+    idx, descs, smem, n_strips = groups[640]
+    planes, _ = eng.preprocess(buf.cuda(), descs, 640, smem, n_strips)
     enc = eng.encode(planes, want_mem_f32=True, want_tokens=True)
     ids, n_ids, conf, fids, fprob = eng.ctc_greedy(enc["logits"], want_frames=True)
     torch.cuda.synchronize()
@@ -156,8 +156,8 @@ def test_bucketed_equals_reference_with_img_w(engines):
     groups = eng.plan(ent)
     assert len(groups) >= 3
     worst = 0.0
-    for Wb, (idx, descs, smem) in groups.items():
-        planes, _ = eng.preprocess(buf.cuda(), descs, Wb, smem)
+    for Wb, (idx, descs, smem, n_strips) in groups.items():
+        planes, _ = eng.preprocess(buf.cuda(), descs, Wb, smem, n_strips)
         enc = eng.encode(planes)
         torch.cuda.synchronize()
         lg = enc["logits"].cpu().numpy()[:, :, :204]

@@ -80,9 +80,10 @@ def test_plan_groups_buckets_and_smem_mirror():
     g = plan_groups(ent, CFG(), "bucketed")
     assert set(g) <= {128, 256, 384, 512, 640} and len(g) == 5
     assert sum(len(v[0]) for v in g.values()) == 200
-    for Wb, (idx, d, smem) in g.items():
+    for Wb, (idx, d, smem, n_strips) in g.items():
         assert (np.minimum(d["nw"], 640) <= Wb).all()
         assert smem <= 100 * 1024
+        assert (d["strip_w"] <= 128).all() and n_strips == int(np.max((np.minimum(d["nw"], Wb) + d["strip_w"] - 1) // d["strip_w"]))
     gp = plan_groups(ent, CFG(), "parity")
     assert list(gp) == [640]
     # numpy mirror == C helper

@@ -66,7 +66,7 @@ def test_ctc_greedy_matches_oracle(lib, dtype):
 
 
 # --------------------------------------------------------------------------- preprocess
-def run_preprocess(lib, crops_or_pages, boxes, Wb, img_h=48, want_norm=False, smem_cap=200 * 1024):
+def run_preprocess(lib, crops_or_pages, boxes, Wb, img_h=48, want_norm=False, smem_cap=200 * 1024, strip_cap=128):
     """crops_or_pages: list of 2-D uint8 arrays; boxes: list of (page_idx, x, y, w, h) already clamped."""
     offs, total = [], 0
     for p in crops_or_pages:
@@ -76,16 +76,17 @@ def run_preprocess(lib, crops_or_pages, boxes, Wb, img_h=48, want_norm=False, sm
     for p, o in zip(crops_or_pages, offs):
         buf[o:o + p.size] = p.reshape(-1)
     descs = (_lib.KiriCropDesc * len(boxes))()
-    smem = 0
+    smem, max_strips = 0, 1
     for i, (pi, x, y, w, h) in enumerate(boxes):
         page = crops_or_pages[pi]
         nw = max(1, int(round(w * (img_h / float(h)))))
         wout = min(nw, Wb)
-        strip = wout
+        strip = min(wout, strip_cap)
         while lib.kiri_preprocess_smem_bytes(w, h, nw, img_h, Wb, strip) > smem_cap and strip > 32:
             strip = max(32, (strip // 2 + 31) // 32 * 32)
         need = lib.kiri_preprocess_smem_bytes(w, h, nw, img_h, Wb, strip)
         smem = max(smem, need)
+        max_strips = max(max_strips, (wout + strip - 1) // strip)
         d = descs[i]
         d.src_offset = offs[pi] + y * page.shape[1] + x
         d.pitch, d.w, d.h, d.nw, d.out_index, d.strip_w = page.shape[1], w, h, nw, i, strip
@@ -93,8 +94,8 @@ def run_preprocess(lib, crops_or_pages, boxes, Wb, img_h=48, want_norm=False, sm
     dd = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8).cuda()
     planes = torch.zeros((len(boxes), img_h, Wb), dtype=torch.uint8, device="cuda")
     norm = torch.zeros((len(boxes), img_h, Wb), dtype=torch.bfloat16, device="cuda") if want_norm else None
-    _lib.check(lib.kiri_preprocess_pack(src.data_ptr(), dd.data_ptr(), len(boxes), img_h, Wb, smem, planes.data_ptr(),
-                                        _lib.ptr(norm), _lib.stream_ptr()))
+    _lib.check(lib.kiri_preprocess_pack(src.data_ptr(), dd.data_ptr(), len(boxes), img_h, Wb, smem, max_strips,
+                                        planes.data_ptr(), _lib.ptr(norm), _lib.stream_ptr()))
     sync()
     return planes.cpu().numpy(), (norm.float().cpu().numpy() if want_norm else None)
 

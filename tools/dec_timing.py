@@ -32,3 +32,12 @@ print(f"step_resident(decoder) {e0.elapsed_time(e1):.3f} ms; max steps {steps}; 
 print(f"cluster 0 total {tot} cycles = {tot/1.9e3:.1f} us; per step {tot/max(1,int(n_out[:16].max()))/1.9e3:.1f} us")
 for i, nme in enumerate(names):
     print(f"  {nme:14s} {buf_[i]:10d} cyc  {100*buf_[i]/tot:5.1f}%  per step {buf_[i]/max(1,int(n_out[:16].max())):8.0f}")
+
+lib.kiri_debug_decode_clusters.restype = C.c_int
+lib.kiri_debug_decode_clusters.argtypes = [C.POINTER(C.c_longlong), C.c_int]
+cb = (C.c_longlong * 256)()
+lib.kiri_debug_decode_clusters(cb, 256)
+t0 = min(cb[c * 4] for c in range(16))
+print("cluster: start_us end_us dur_us steps smid  (lines' max steps)")
+for c in range(16):
+    print(f"  {c:2d}: {(cb[c*4]-t0)/1e3:8.1f} {(cb[c*4+1]-t0)/1e3:8.1f} {(cb[c*4+1]-cb[c*4])/1e3:8.1f} {cb[c*4+2]:4d} {cb[c*4+3]:4d}   {int(n_out[c*16:(c+1)*16].max())}")

@@ -258,6 +258,28 @@ int kiri_decode_greedy_multi(KiriHandle* h, const void* mem_bf16, long long M_to
                              float* step_logp, float* step_prob, const int* forced_ids, int* steps_run_host,
                              cudaStream_t stream);
 
+/* ---------------------------------------------------------------- beam search (decode_method="beam")
+ * Replaces beam_decode_one_batched at BEAM > 1 (kiri_ocr/model.py:390-600): `beam` (<= 5) hypotheses
+ * per line, top-`beam` expansion of every alive hypothesis, stable prune by the length-normalised
+ * score ((5+L)/6)^lenp with finished hypotheses listed first (model.py:550-559).  The K/V cache is
+ * never copied: every hypothesis keeps a per-position table of the physical slot its ancestor
+ * wrote.  Outputs per line and hypothesis: bm_state (0 none, 1 alive at the step limit, 2 ended
+ * with EOS), bm_score (sum of the chosen penalised log-probs, double like the reference's Python
+ * float), bm_len (tokens after BOS), bm_ids / bm_logp [B, beam, Lmax].  The final CTC-fused
+ * ranking (model.py:562-579) is done by the caller with kiri_ctc_align_score. */
+size_t kiri_decode_beam_workspace_bytes(const KiriHandle* h, int B, long long M_total, int Lmax, int beam);
+int kiri_decode_beam_multi(KiriHandle* h, const void* mem_bf16, long long M_total, const int* mem_row0,
+                           const int* mem_len, const int* len_est, const int* line_perm, int B, int Lmax, int beam,
+                           double lenp, const KiriDecodeParams* p, void* workspace, size_t workspace_bytes,
+                           double* bm_score, int* bm_len, int* bm_state, int* bm_ids, float* bm_logp,
+                           cudaStream_t stream);
+/* K13: CTC forward-algorithm score of every hypothesis = compute_ctc_alignment_score
+ * (kiri_ocr/model.py:603-668).  logits: fp32 [M_total, ld] CTC logits (first C columns valid); line b
+ * owns rows [mem_row0[b], +mem_len[b]); max_T >= every mem_len.  out: [n_lines, beam] fp32. */
+int kiri_ctc_align_score(const float* logits, int ld, int C, const int* mem_row0, const int* mem_len, int n_lines,
+                         int beam, int Lmax, const int* bm_ids, const int* bm_len, const int* bm_state,
+                         int vocab_size, int unk_ctc_id, int max_T, float* out, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,7 +7,8 @@ plug-in boundary (core.py:469-485, 746-756: anything with ``detect_lines_objects
 ``detect_lines`` / ``detect_words``).  What changes is the loop body: instead of one
 ``_preprocess_region`` + ``recognize_region`` per box on the host, all boxes of a page go through
 ``BatchedRecognizer`` in one batch.  There is no CPU path: ``device`` must be a CUDA device.
-``decode_method="beam"`` is accepted but not built yet.
+``decode_method="beam"`` runs the device beam search (widths 1..5, ``ocr.cfg.BEAM``) and the device CTC
+forward rescoring; its streaming form replays the final best hypothesis.
 """
 from __future__ import annotations
 
@@ -238,8 +239,6 @@ class OCR:
     # ==================== recognition ====================
     def _method(self, decode_method: Optional[str] = None) -> str:
         m = self._normalize_decode_method(decode_method) if decode_method is not None else self.decode_method
-        if m == "beam":
-            raise NotImplementedError("decode_method='beam' is not built in kiri_ocr_b200 yet; use 'fast' or 'accurate'")
         return m
 
     def _preprocess_region(self, img: np.ndarray, box, extra_padding: int = 5) -> Optional[torch.Tensor]:

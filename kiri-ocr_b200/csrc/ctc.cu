@@ -118,3 +118,127 @@ extern "C" int kiri_ctc_greedy(const void* logits, int logits_dtype, int n_lines
   KIRI_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// K13: CTC forward-algorithm score of decoder hypotheses (beam rescoring).
+//
+// Replaces  compute_ctc_alignment_score   kiri_ocr/model.py:603-668  (a Python double loop of
+//           T x S torch.logsumexp calls, ~0.5 s per hypothesis on the CPU)
+// One CTA per line: all warps first reduce the per-frame log-softmax statistics, then warp r runs
+// the alpha recursion of hypothesis r over the extended label sequence [b, l0, b, l1, ..., b] in
+// fp32 log space, with the same 1/2/3-term logsumexp as the reference.
+namespace kiri {
+
+__device__ __forceinline__ float lse2(float a, float b) {
+  const float m = fmaxf(a, b);
+  if (m == -INFINITY) return -INFINITY;
+  return m + logf(expf(a - m) + expf(b - m));
+}
+__device__ __forceinline__ float lse3(float a, float b, float c) {
+  const float m = fmaxf(a, fmaxf(b, c));
+  if (m == -INFINITY) return -INFINITY;
+  return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
+}
+
+__global__ void __launch_bounds__(256)
+ctc_align_kernel(const float* __restrict__ logits, int ld, int C, const int* __restrict__ mem_row0,
+                 const int* __restrict__ mem_len, int beam, int Lmax, const int* __restrict__ bm_ids,
+                 const int* __restrict__ bm_len, const int* __restrict__ bm_state, int vocab_size, int unk_ctc,
+                 float* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  const int b = blockIdx.x;
+  const int T = mem_len[b];
+  const float* lg = logits + static_cast<size_t>(mem_row0[b]) * ld;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  float* fmax_s = reinterpret_cast<float*>(sm_raw);              // [T] row max
+  float* flog_s = fmax_s + T;                                    // [T] log(sum(exp(x - max)))
+  const int Smax = 2 * Lmax + 1;
+  int* ext_all = reinterpret_cast<int*>(flog_s + T);
+  // ---- per-frame log-softmax statistics (torch: x - max - log(sum(exp(x - max))))
+  for (int t = warp; t < T; t += nwarps) {
+    const float* row = lg + static_cast<size_t>(t) * ld;
+    float m = -INFINITY;
+    for (int c = lane; c < C; c += 32) m = fmaxf(m, row[c]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += expf(row[c] - m);
+    s = warp_sum(s);
+    if (lane == 0) { fmax_s[t] = m; flog_s[t] = logf(s); }
+  }
+  __syncthreads();
+  if (warp >= beam) return;
+  const int r = warp;
+  if (bm_state[b * beam + r] == 0) { if (lane == 0) out[b * beam + r] = 0.f; return; }
+  int* ext = ext_all + r * 3 * Smax;
+  float* a0 = reinterpret_cast<float*>(ext + Smax);
+  float* a1 = a0 + Smax;
+  // ---- labels: ids up to EOS, pad/bos skipped, mapped to CTC ids (model.py:611-620, 137-144)
+  const int* seq = bm_ids + (static_cast<size_t>(b) * beam + r) * Lmax;
+  const int n_tok = bm_len[b * beam + r];
+  int n_lab = 0;
+  if (lane == 0) {
+    for (int i = 0; i < n_tok; ++i) {
+      const int x = seq[i];
+      if (x == 2) break;
+      if (x == 0 || x == 1) continue;
+      const int raw = x - 3;
+      ext[2 * n_lab + 1] = (raw >= 0 && raw < vocab_size) ? raw + 2 : unk_ctc;
+      ++n_lab;
+    }
+    for (int i = 0; i <= n_lab; ++i) ext[2 * i] = 0;
+  }
+  n_lab = __shfl_sync(0xffffffffu, n_lab, 0);
+  __syncwarp();
+  auto lp = [&](int t, int c) { return (lg[static_cast<size_t>(t) * ld + c] - fmax_s[t]) - flog_s[t]; };
+  if (n_lab == 0) {
+    float s = 0.f;
+    for (int t = lane; t < T; t += 32) s += lp(t, 0);
+    s = warp_sum(s);
+    if (lane == 0) out[b * beam + r] = s / static_cast<float>(T > 1 ? T : 1);
+    return;
+  }
+  const int S = 2 * n_lab + 1;
+  for (int s = lane; s < S; s += 32) a0[s] = -INFINITY;
+  __syncwarp();
+  if (lane == 0) { a0[0] = lp(0, 0); a0[1] = lp(0, ext[1]); }
+  __syncwarp();
+  float* cur = a0;
+  float* nxt = a1;
+  for (int t = 1; t < T; ++t) {
+    for (int s = lane; s < S; s += 32) {
+      const int e = ext[s];
+      float v;
+      if (s == 0) v = cur[0];
+      else if (s > 1 && e != 0 && e != ext[s - 2]) v = lse3(cur[s], cur[s - 1], cur[s - 2]);
+      else v = lse2(cur[s], cur[s - 1]);
+      nxt[s] = v + lp(t, e);
+    }
+    __syncwarp();
+    float* tmp = cur; cur = nxt; nxt = tmp;
+  }
+  if (lane == 0) {
+    const float total = lse2(cur[S - 1], cur[S - 2]);
+    out[b * beam + r] = total / static_cast<float>(n_lab);
+  }
+}
+
+}  // namespace kiri
+
+extern "C" int kiri_ctc_align_score(const float* logits, int ld, int C, const int* mem_row0, const int* mem_len,
+                                    int n_lines, int beam, int Lmax, const int* bm_ids, const int* bm_len,
+                                    const int* bm_state, int vocab_size, int unk_ctc_id, int max_T, float* out,
+                                    cudaStream_t stream) {
+  KIRI_REQUIRE(logits && mem_row0 && mem_len && bm_ids && bm_len && bm_state && out, "kiri_ctc_align_score: null pointer");
+  KIRI_REQUIRE(beam >= 1 && beam <= 8 && Lmax > 0 && max_T > 0, "kiri_ctc_align_score: bad sizes");
+  if (n_lines == 0) return 0;
+  const int smem = max_T * 8 + beam * 3 * (2 * Lmax + 1) * 4;
+  static int configured = 0;
+  if (smem > 48 * 1024 && configured < smem) {
+    KIRI_CHECK_CUDA(cudaFuncSetAttribute(kiri::ctc_align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  kiri::ctc_align_kernel<<<n_lines, 256, smem, stream>>>(logits, ld, C, mem_row0, mem_len, beam, Lmax, bm_ids, bm_len,
+                                                         bm_state, vocab_size, unk_ctc_id, out);
+  KIRI_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

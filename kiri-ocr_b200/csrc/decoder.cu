@@ -499,3 +499,49 @@ extern "C" int kiri_decode_greedy_multi(KiriHandle* h, const void* mem_bf16, lon
   }
   return 0;
 }
+
+// ------------------------------------------------------------------ beam search (config 4)
+extern "C" size_t kiri_decode_beam_workspace_bytes(const KiriHandle* h, int B, long long M_total, int Lmax, int beam) {
+  if (!h || B <= 0 || M_total <= 0 || Lmax <= 0 || beam < 1 || beam > 5) return 0;
+  const size_t L = h->d.dec_layers, D = h->d.dec_dim, ns = fused_decoder_slots(B, beam);
+  return al256(static_cast<size_t>(M_total) * L * 2 * D * 2) + 2 * al256(L * ns * Lmax * D * 2) +
+         2 * al256(2 * ns * static_cast<size_t>(Lmax) * 4) + 256;
+}
+
+extern "C" int kiri_decode_beam_multi(KiriHandle* h, const void* mem_bf16, long long M_total, const int* mem_row0,
+                                      const int* mem_len, const int* len_est, const int* line_perm, int B, int Lmax,
+                                      int beam, double lenp, const KiriDecodeParams* p, void* workspace,
+                                      size_t workspace_bytes, double* bm_score, int* bm_len, int* bm_state,
+                                      int* bm_ids, float* bm_logp, cudaStream_t stream) {
+  KIRI_REQUIRE(h && mem_bf16 && mem_row0 && mem_len && len_est && p && workspace && bm_score && bm_len && bm_state &&
+               bm_ids && bm_logp, "kiri_decode_beam_multi: null pointer");
+  KIRI_REQUIRE(B > 0 && M_total > 0 && M_total < (1ll << 31) && Lmax > 0 && Lmax <= h->d.max_pos && Lmax <= 544 &&
+               beam >= 1 && beam <= 5, "kiri_decode_beam_multi: bad sizes B=%d M=%lld Lmax=%d beam=%d", B, M_total, Lmax, beam);
+  KIRI_REQUIRE(p->select_raw == 0, "kiri_decode_beam_multi: the raw-logit selection rule is greedy-only");
+  const KiriDims& d = h->d;
+  const KiriWeights& w = h->w;
+  const size_t L = d.dec_layers, D = d.dec_dim, ns = fused_decoder_slots(B, beam);
+  KIRI_REQUIRE(workspace_bytes >= kiri_decode_beam_workspace_bytes(h, B, M_total, Lmax, beam),
+               "kiri_decode_beam_multi: workspace too small");
+  uint8_t* base = reinterpret_cast<uint8_t*>(workspace);
+  size_t off = 0;
+  __nv_bfloat16* crosskv = reinterpret_cast<__nv_bfloat16*>(base); off += al256(static_cast<size_t>(M_total) * L * 2 * D * 2);
+  __nv_bfloat16* self_k = reinterpret_cast<__nv_bfloat16*>(base + off); off += al256(L * ns * Lmax * D * 2);
+  __nv_bfloat16* self_v = reinterpret_cast<__nv_bfloat16*>(base + off); off += al256(L * ns * Lmax * D * 2);
+  FusedBeam fb;
+  fb.beam = beam; fb.lenp = lenp;
+  fb.seqbuf = reinterpret_cast<int*>(base + off); off += al256(2 * ns * static_cast<size_t>(Lmax) * 4);
+  fb.lpbuf = reinterpret_cast<float*>(base + off); off += al256(2 * ns * static_cast<size_t>(Lmax) * 4);
+  int* steps_dev = reinterpret_cast<int*>(base + off);
+  fb.score = bm_score; fb.len = bm_len; fb.state = bm_state; fb.ids = bm_ids; fb.logp = bm_logp;
+  { ProfScope ps(PS_DEC_CROSSKV, stream);
+    KIRI_TRY(gemm_call(mem_bf16, w.crosskv_w, w.crosskv_b, static_cast<int>(M_total), static_cast<int>(L * 2 * D), d.enc_dim,
+                       EPI_BIAS_BF16, crosskv, nullptr, nullptr, nullptr, nullptr, stream)); }
+  KIRI_CHECK_CUDA(cudaMemsetAsync(steps_dev, 0, sizeof(int), stream));
+  int cs = 8;
+  if (const char* e = getenv("KIRI_DEC_CLUSTER")) cs = atoi(e);
+  ProfScope ps_step(PS_DEC_STEP, stream);
+  // the self-attention cache is indexed by physical slot: B of the run function = decode slots in use
+  return fused_decoder_run(h, crosskv, static_cast<int>(L * 2 * D), mem_row0, mem_len, 0, self_k, self_v, len_est, nullptr,
+                           line_perm, B, Lmax, p, nullptr, nullptr, nullptr, nullptr, nullptr, steps_dev, cs, stream, &fb);
+}

@@ -57,6 +57,13 @@ struct FusedArgs {
   KiriDecodeParams p;
   int *ids, *n_out; float *sum_logp, *step_logp, *step_prob;
   int* steps_max;                                     // device int: max steps run by any cluster
+  // beam search (model.py:536-559): `beam` hypotheses per line share a cluster (16 / beam lines each)
+  int beam;                                           // hypotheses per line (1 when greedy)
+  int bmode;                                          // 1: beam bookkeeping + bm_* outputs, 0: greedy outputs
+  double lenp;                                        // cfg.BEAM_LENP
+  int* seqbuf; float* lpbuf;                          // [2][n_slots][Lmax] ping-pong hypothesis records (rank 0)
+  double* bm_score; int* bm_len; int* bm_state;       // [B, beam]
+  int* bm_ids; float* bm_logp;                        // [B, beam, Lmax]
   int timing;                                         // 1: accumulate phase cycles into g_dec_prof
 };
 
@@ -160,14 +167,26 @@ struct LineState {
   int line[kFL];         // global line index of each slot (outputs, forced ids)
 };
 
+// beam bookkeeping, replicated in every CTA of the cluster
+struct BeamState {
+  double score[kFL];     // sum of chosen log-probs (Python float in the reference)
+  int state[kFL];        // 0 empty, 1 alive, 2 done
+  float cand_v[kFL][8];  // top-`beam` penalised log-probs of every alive slot
+  int cand_i[kFL][8];
+  int line_done[kFL];    // per line of the cluster
+  int src[kFL];          // scratch of the selection: old slot each new slot descends from,
+  int new_tok[kFL];      //   appended token (-1: a finished hypothesis carried over),
+  float new_v[kFL];      //   its penalised log-prob,
+  int old_len[kFL];      //   tokens after BOS before this step
+};
 struct FusedSmem {                       // byte offsets into dynamic shared memory
-  int x, gath, a, obuf, hbuf, qloc, logits, part, vstage, state, params, total;
+  int x, gath, a, obuf, hbuf, qloc, logits, part, vstage, state, params, beam, anc, total;
 };
 // Biases and LayerNorm affines of every layer live in shared memory for the whole decode: every
 // cluster barrier invalidates L1, so a parameter read from global costs an L2 round trip per phase.
 // Per layer (floats): bqkv 768 | bo 256 | bcq 256 | bco 256 | b1 ff | b2 256 | ln1 g,b | ln2 g,b | ln3 g,b
 __host__ __device__ inline int fused_layer_floats(int ff) { return 768 + 4 * 256 + ff + 6 * 256; }
-__host__ __device__ inline FusedSmem fused_smem_plan(int ff, int Vp, int cs, int layers) {
+__host__ __device__ inline FusedSmem fused_smem_plan(int ff, int Vp, int cs, int layers, int beam = 0, int Lmax = 0) {
   FusedSmem s;
   int off = 0;
   auto take = [&](int bytes) { const int o = off; off += (bytes + 127) & ~127; return o; };
@@ -182,15 +201,17 @@ __host__ __device__ inline FusedSmem fused_smem_plan(int ff, int Vp, int cs, int
   s.vstage = take(kFWarps * 32 * kHd * 2);
   s.state = take(static_cast<int>(sizeof(LineState)));
   s.params = take((layers * fused_layer_floats(ff) + 2 * Vp + 512) * 4);
+  s.beam = take(beam >= 1 ? static_cast<int>(sizeof(BeamState)) : 0);       // beam = 0: greedy, no bookkeeping
+  s.anc = take(beam >= 1 ? 2 * kFL * ((Lmax + 15) & ~15) : 0);      // [2][slot][pos] -> physical K/V slot
   s.total = off;
   return s;
 }
 
 // single-query attention of one warp over n keys; K/V rows are 32 bf16 at base + j*ld.
 // q: 32 fp32 in shared memory; vst: this warp's 32x32 bf16 staging tile.  Returns o[lane].
-template <bool READONLY>
+template <bool READONLY, class RowOff>
 __device__ __forceinline__ float attend_warp(const float* q, const __nv_bfloat16* kbase, const __nv_bfloat16* vbase,
-                                             size_t ld, int n, __nv_bfloat16* vst, int lane) {
+                                             RowOff row_off, int n, __nv_bfloat16* vst, int lane) {
   float qf[kHd];
 #pragma unroll
   for (int i = 0; i < kHd; i += 4) {
@@ -204,8 +225,9 @@ __device__ __forceinline__ float attend_warp(const float* q, const __nv_bfloat16
     float s = -INFINITY;
     uint4 vv[4];
     if (j < n) {
-      const uint4* kp = reinterpret_cast<const uint4*>(kbase + static_cast<size_t>(j) * ld);
-      const uint4* vp = reinterpret_cast<const uint4*>(vbase + static_cast<size_t>(j) * ld);
+      const size_t ro = row_off(j);
+      const uint4* kp = reinterpret_cast<const uint4*>(kbase + ro);
+      const uint4* vp = reinterpret_cast<const uint4*>(vbase + ro);
       uint4 kk[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -298,7 +320,7 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int HPC = kHeads / CS;                 // heads per CTA
   constexpr int DC = 256 / CS;                     // output columns of a D-wide projection per CTA
-  const FusedSmem L = fused_smem_plan(A.ff, A.Vp, CS, A.layers);
+  const FusedSmem L = fused_smem_plan(A.ff, A.Vp, CS, A.layers, A.bmode ? A.beam : 0, A.Lmax);
   float* x = reinterpret_cast<float*>(sm + L.x);
   float* gath = reinterpret_cast<float*>(sm + L.gath);
   __nv_bfloat16* a = reinterpret_cast<__nv_bfloat16*>(sm + L.a);
@@ -330,8 +352,15 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
   for (int t = threadIdx.x; t < 256; t += kFThreads) { p_decln[t] = __ldg(A.dec_ln_g + t); p_decln[256 + t] = __ldg(A.dec_ln_b + t); }
   constexpr int lda = 256 + kPad;
   const int ldh = A.ff + kPad;
-  const int b0 = cid * kFL;
+  const int b0 = cid * kFL;                          // first physical slot (K/V cache, hypothesis records)
   const int D = 256;
+  const int BEAM = A.beam;
+  const bool BM = A.bmode != 0;                      // beam bookkeeping (even at width 1) vs greedy
+  const int LPC = kFL / BEAM;                        // lines per cluster (16 when greedy)
+  BeamState* bs = reinterpret_cast<BeamState*>(sm + L.beam);
+  const int anc_ld = (A.Lmax + 15) & ~15;
+  uint8_t* anc = sm + L.anc;                         // [2][slot][pos], beam mode only
+  int pp = 0;                                        // ping-pong index of anc / seqbuf / lpbuf
 
   // remote views of the exchange buffers
   __nv_bfloat16* r_obuf[CS]; float* r_gath[CS]; __nv_bfloat16* r_hbuf[CS]; float* r_logits[CS];
@@ -348,8 +377,10 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
   // ---- init (model.py:416-425: Python float arithmetic, int() truncation)
   if (threadIdx.x < kFL) {
     const int i = threadIdx.x;
-    const bool ok = b0 + i < A.B;
-    const int b = ok ? (A.line_perm ? A.line_perm[b0 + i] : b0 + i) : 0;
+    const int li = i / BEAM, bi = i - li * BEAM;     // line of the cluster, hypothesis of the line
+    const int dslot = cid * LPC + li;                // decode order index of the line
+    const bool ok = li < LPC && dslot < A.B;
+    const int b = ok ? (A.line_perm ? A.line_perm[dslot] : dslot) : 0;
     st->line[i] = b;
     int ms = 0, tl = 0, Tm = A.T, r0 = 0;
     if (ok) {
@@ -363,12 +394,24 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
     }
     st->valid[i] = ok; st->row0[i] = r0; st->mlen[i] = Tm;
     st->max_steps[i] = ms; st->target[i] = tl;
-    st->finished[i] = (!ok || ms <= 0) ? 1 : 0;
+    st->finished[i] = (!ok || ms <= 0 || bi != 0) ? 1 : 0;       // a line starts with ONE hypothesis [BOS]
     st->n_tok[i] = 1; st->cur_tok[i] = kTokBOS;
 #pragma unroll
     for (int k = 0; k < 8; ++k) st->hist[i][k] = -1 - k;
     st->hist[i][0] = kTokBOS;
-    if (ok && rank == 0) { A.n_out[b] = 0; A.sum_logp[b] = 0.f; }
+    if (!BM) {
+      if (ok && rank == 0) { A.n_out[b] = 0; A.sum_logp[b] = 0.f; }
+    } else {
+      bs->score[i] = 0.0;
+      bs->state[i] = st->finished[i] ? 0 : 1;
+      if (bi == 0) bs->line_done[li] = (!ok || ms <= 0) ? 1 : 0;
+      if (ok && rank == 0) {
+        // a line whose step budget is 0 keeps its initial hypothesis [BOS] (model.py:431-443)
+        A.bm_state[b * BEAM + bi] = (bi == 0) ? 1 : 0;
+        A.bm_score[b * BEAM + bi] = 0.0;
+        A.bm_len[b * BEAM + bi] = 0;
+      }
+    }
   }
   __syncthreads();
   csync();                                          // every CTA of the cluster is resident and initialised
@@ -385,13 +428,18 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
   for (; step < A.Lmax; ++step) {
     {
       int alive = 0;
+      if (!BM) {
 #pragma unroll
-      for (int i = 0; i < kFL; ++i) alive += st->finished[i] ? 0 : 1;
+        for (int i = 0; i < kFL; ++i) alive += st->finished[i] ? 0 : 1;
+      } else {
+        for (int li = 0; li < LPC; ++li) alive += bs->line_done[li] ? 0 : 1;
+      }
       if (alive == 0) break;
     }
     // ---- S0: x = emb[tok] + pe[step]; a = LN1_0(x)   (one warp per line)
     {
       const int i = warp;
+      if (BM && lane == 0) anc[(pp * kFL + i) * anc_ld + step] = static_cast<uint8_t>(i);
       const int tokid = st->finished[i] ? 0 : st->cur_tok[i];   // finished lines feed the pad token
       const float4* e = reinterpret_cast<const float4*>(A.emb + static_cast<size_t>(tokid) * D) + lane * 2;
       const float4 e0 = __ldg(e), e1 = __ldg(e + 1);
@@ -413,8 +461,10 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
       const FusedLayer& W = A.layer[l];
       const float* PB = prm + l * lfl;                 // this layer's biases
       const float* PN = PB + 1792 + A.ff;              // ln1 g,b | ln2 g,b | ln3 g,b
-      __nv_bfloat16* kc = A.self_k + static_cast<size_t>(l) * A.B * A.Lmax * D;
-      __nv_bfloat16* vc = A.self_v + static_cast<size_t>(l) * A.B * A.Lmax * D;
+      // the cache is indexed by PHYSICAL slot: B slots when greedy, 16 per cluster in beam mode
+      const size_t cache_slots = !BM ? static_cast<size_t>(A.B) : static_cast<size_t>(gridDim.x / CS) * kFL;
+      __nv_bfloat16* kc = A.self_k + static_cast<size_t>(l) * cache_slots * A.Lmax * D;
+      __nv_bfloat16* vc = A.self_v + static_cast<size_t>(l) * cache_slots * A.Lmax * D;
       // ---- A: q,k,v of my heads.  q -> qloc (fp32), k/v -> global cache row `step` (bf16)
       cta_gemm(W.wqkv, D, a, lda, 12 * HPC,
                [&](int i) { const int sec = i / (4 * HPC), rem = i - sec * 4 * HPC; return sec * 32 + rank * HPC * 4 + rem; },
@@ -435,9 +485,18 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
       for (int pidx = warp; pidx < kFL * HPC; pidx += kFWarps) {
         const int i = pidx % kFL, hl = pidx / kFL, head = rank * HPC + hl;
         float o = 0.f;
-        if (st->valid[i]) {
-          const size_t base = (static_cast<size_t>(b0 + i) * A.Lmax) * D + head * kHd;
-          o = attend_warp<false>(qloc + i * DC + hl * kHd, kc + base, vc + base, D, step + 1, vst, lane);
+        if (st->valid[i] && !st->finished[i]) {
+          if (!BM) {
+            const size_t base = (static_cast<size_t>(b0 + i) * A.Lmax) * D + head * kHd;
+            o = attend_warp<false>(qloc + i * DC + hl * kHd, kc + base, vc + base,
+                                   [&](int j) { return static_cast<size_t>(j) * D; }, step + 1, vst, lane);
+          } else {
+            // hypothesis i reads position j from the physical slot its ancestor wrote it to
+            const uint8_t* ar = anc + (pp * kFL + i) * anc_ld;
+            const size_t base = static_cast<size_t>(head) * kHd;
+            o = attend_warp<false>(qloc + i * DC + hl * kHd, kc + base, vc + base,
+                                   [&](int j) { return (static_cast<size_t>(b0 + ar[j]) * A.Lmax + j) * D; }, step + 1, vst, lane);
+          }
         }
         const float on = __shfl_down_sync(0xffffffffu, o, 1);
         if ((lane & 1) == 0) {
@@ -485,9 +544,10 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
       for (int pidx = warp; pidx < kFL * HPC; pidx += kFWarps) {
         const int i = pidx % kFL, hl = pidx / kFL, head = rank * HPC + hl;
         float o = 0.f;
-        if (st->valid[i]) {
+        if (st->valid[i] && !st->finished[i]) {
           const __nv_bfloat16* kb = A.crosskv + static_cast<size_t>(st->row0[i]) * A.crosskv_ld + l * 2 * D + head * kHd;
-          o = attend_warp<true>(qloc + i * DC + hl * kHd, kb, kb + D, A.crosskv_ld, st->mlen[i], vst, lane);
+          const size_t ldk = A.crosskv_ld;
+          o = attend_warp<true>(qloc + i * DC + hl * kHd, kb, kb + D, [&](int j) { return j * ldk; }, st->mlen[i], vst, lane);
         }
         const float on = __shfl_down_sync(0xffffffffu, o, 1);
         if ((lane & 1) == 0) {
@@ -619,6 +679,7 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
           if (v == p.unk_id) lp -= p.unk_penalty;
           return lp;
         };
+        if (!BM) {
         float best = -INFINITY;
         int bid = 0x7fffffff;
         for (int v = lane; v < Vd; v += 32) {
@@ -650,7 +711,147 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
             if (A.step_prob) A.step_prob[static_cast<size_t>(b) * A.Lmax + step] = expf(dec[bid] - lse_d);
           }
         }
+        } else {
+          // top-BEAM of the penalised log-probs (torch.topk, model.py:537): BEAM warp arg-max rounds
+          int chosen[8];
+          for (int k = 0; k < BEAM; ++k) {
+            float best = -INFINITY;
+            int bid = 0x7fffffff;
+            for (int v = lane; v < Vd; v += 32) {
+              bool taken = false;
+              for (int t = 0; t < k; ++t) taken |= (chosen[t] == v);
+              if (!taken) {
+                const float val = fused(v);
+                if (val > best) { best = val; bid = v; }
+              }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+              const int oi = __shfl_xor_sync(0xffffffffu, bid, o);
+              if (ob > best || (ob == best && oi < bid)) { best = ob; bid = oi; }
+            }
+            chosen[k] = bid;
+            if (lane == 0) { bs->cand_v[i][k] = best; bs->cand_i[i][k] = bid; }
+          }
+        }
       }
+    }
+    if (BM) {
+      __syncthreads();
+      // ---- beam bookkeeping, one warp per line (model.py:539-559): candidates = finished hypotheses
+      // (in order) then every alive hypothesis' top-BEAM (in order); stable sort by the length-normalised
+      // score, keep BEAM.  Lane = candidate.
+      const int li = warp;
+      if (li < LPC && !bs->line_done[li]) {
+        const int s0 = li * BEAM;
+        int n_done = 0, n_alive = 0, done_slot[8], alive_slot[8];
+        for (int r = 0; r < BEAM; ++r) {
+          const int stt = bs->state[s0 + r];
+          if (stt == 2) done_slot[n_done++] = s0 + r;
+          else if (stt == 1) alive_slot[n_alive++] = s0 + r;
+        }
+        const int n_cand = n_done + n_alive * BEAM;             // <= 30 for BEAM <= 5
+        const bool has = lane < n_cand;
+        int src = s0, tok = -1, ntok_new = 1;
+        float cv = 0.f;
+        double sc = 0.0;
+        bool fin = true;
+        if (has) {
+          if (lane < n_done) {
+            for (int r = 0; r < n_done; ++r) if (r == lane) src = done_slot[r];
+            sc = bs->score[src]; ntok_new = st->n_tok[src];
+          } else {
+            const int a = (lane - n_done) / BEAM, k = (lane - n_done) - a * BEAM;
+            for (int r = 0; r < n_alive; ++r) if (r == a) src = alive_slot[r];
+            tok = bs->cand_i[src][k]; cv = bs->cand_v[src][k];
+            sc = bs->score[src] + static_cast<double>(cv);        // Python: base_score + float(v)
+            ntok_new = st->n_tok[src] + 1;
+            fin = (tok == kTokEOS);
+          }
+        }
+        const int Ln = ntok_new - 1 > 1 ? ntok_new - 1 : 1;
+        const double pen = pow(5.0 + static_cast<double>(Ln), A.lenp) / pow(6.0, A.lenp);
+        const double normed = has ? sc / pen : -1e300;
+        int rk = 0;
+        for (int j = 0; j < n_cand; ++j) {
+          const double oj = __shfl_sync(0xffffffffu, normed, j);
+          if (j != lane && (oj > normed || (oj == normed && j < lane))) ++rk;
+        }
+        const int nb = n_cand < BEAM ? n_cand : BEAM;
+        const bool win = has && rk < nb;
+        // read everything the new hypothesis inherits BEFORE any slot is overwritten
+        int h_old[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) h_old[k] = st->hist[src][k];
+        const int cur_old = st->cur_tok[src], len_old = st->n_tok[src] - 1;
+        __syncwarp();
+        if (win) {
+          const int ns = s0 + rk;
+          bs->score[ns] = sc;
+          bs->state[ns] = fin ? 2 : 1;
+          st->finished[ns] = fin ? 1 : 0;
+          st->n_tok[ns] = ntok_new;
+          if (tok >= 0) {
+            st->cur_tok[ns] = tok;
+            st->hist[ns][0] = tok;
+#pragma unroll
+            for (int k = 1; k < 8; ++k) st->hist[ns][k] = h_old[k - 1];
+          } else {
+            st->cur_tok[ns] = cur_old;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) st->hist[ns][k] = h_old[k];
+          }
+          bs->src[ns] = src; bs->new_tok[ns] = tok; bs->new_v[ns] = cv; bs->old_len[ns] = len_old;
+        }
+        if (lane >= nb && lane < BEAM) { bs->state[s0 + lane] = 0; st->finished[s0 + lane] = 1; }
+        __syncwarp();
+        // inherit the ancestors' K/V slots and (rank 0) the hypothesis records, ping-pong buffers
+        bool all_done = true;
+        for (int r = 0; r < nb; ++r) {
+          const int ns = s0 + r, sr = bs->src[ns], ol = bs->old_len[ns], tk = bs->new_tok[ns];
+          const uint8_t* a_src = anc + (pp * kFL + sr) * anc_ld;
+          uint8_t* a_dst = anc + ((pp ^ 1) * kFL + ns) * anc_ld;
+          for (int t = lane; t <= step; t += 32) a_dst[t] = a_src[t];
+          if (rank == 0) {
+            const size_t nsl = static_cast<size_t>(gridDim.x / CS) * kFL;      // physical slots of the launch
+            const int* q_src = A.seqbuf + (static_cast<size_t>(pp) * nsl + b0 + sr) * A.Lmax;
+            int* q_dst = A.seqbuf + (static_cast<size_t>(pp ^ 1) * nsl + b0 + ns) * A.Lmax;
+            const float* l_src = A.lpbuf + (static_cast<size_t>(pp) * nsl + b0 + sr) * A.Lmax;
+            float* l_dst = A.lpbuf + (static_cast<size_t>(pp ^ 1) * nsl + b0 + ns) * A.Lmax;
+            for (int t = lane; t < ol; t += 32) { q_dst[t] = q_src[t]; l_dst[t] = l_src[t]; }
+            if (lane == 0 && tk >= 0) { q_dst[ol] = tk; l_dst[ol] = bs->new_v[ns]; }
+          }
+          all_done &= (bs->state[ns] == 2);
+        }
+        const bool ldone = all_done || (step + 1 >= st->max_steps[s0]);
+        __syncwarp();
+        if (ldone) {
+          if (lane == 0) bs->line_done[li] = 1;
+          for (int r = 0; r < BEAM; ++r) st->finished[s0 + r] = 1;
+          if (rank == 0) {
+            // the line is complete: publish its hypotheses (score, length, ids, log-probs)
+            const int b = st->line[s0];
+            const size_t nsl = static_cast<size_t>(gridDim.x / CS) * kFL;
+            for (int r = 0; r < BEAM; ++r) {
+              const int ns = s0 + r;
+              const int len = r < nb ? st->n_tok[ns] - 1 : 0;
+              if (lane == 0) {
+                A.bm_state[b * BEAM + r] = r < nb ? bs->state[ns] : 0;
+                A.bm_score[b * BEAM + r] = r < nb ? bs->score[ns] : 0.0;
+                A.bm_len[b * BEAM + r] = len;
+              }
+              const int* q_src = A.seqbuf + (static_cast<size_t>(pp ^ 1) * nsl + b0 + ns) * A.Lmax;
+              const float* l_src = A.lpbuf + (static_cast<size_t>(pp ^ 1) * nsl + b0 + ns) * A.Lmax;
+              for (int t = lane; t < len; t += 32) {
+                A.bm_ids[(static_cast<size_t>(b) * BEAM + r) * A.Lmax + t] = q_src[t];
+                A.bm_logp[(static_cast<size_t>(b) * BEAM + r) * A.Lmax + t] = l_src[t];
+              }
+            }
+          }
+        }
+      }
+      pp ^= 1;
     }
     // the next heads-GEMM writes `logits` remotely only after 18 more cluster barriers, and
     // `st` is CTA-local: a block barrier is enough here
@@ -724,7 +925,7 @@ void fused_decoder_free(KiriHandle* h) {
 
 template <int CS>
 static int launch_fused(const FusedArgs& a, int n_clusters, cudaStream_t stream) {
-  const FusedSmem L = fused_smem_plan(a.ff, a.Vp, CS, a.layers);
+  const FusedSmem L = fused_smem_plan(a.ff, a.Vp, CS, a.layers, a.bmode ? a.beam : 0, a.Lmax);
   auto kern = dec_fused_kernel<CS>;
   static int configured = 0;
   if (configured < L.total) {
@@ -750,7 +951,7 @@ int fused_decoder_run(KiriHandle* h, const __nv_bfloat16* crosskv, int crosskv_l
                       int T, __nv_bfloat16* self_k, __nv_bfloat16* self_v, const int* len_est, const int* forced,
                       const int* line_perm, int B, int Lmax, const KiriDecodeParams* p, int* ids, int* n_out,
                       float* sum_logp, float* step_logp, float* step_prob, int* steps_max_dev, int cluster_size,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, const FusedBeam* beam) {
   FusedPacked* fp = reinterpret_cast<FusedPacked*>(h->fused);
   KIRI_REQUIRE(fp, "fused decoder: handle was created without decoder weights");
   FusedArgs a = fp->args;
@@ -759,7 +960,16 @@ int fused_decoder_run(KiriHandle* h, const __nv_bfloat16* crosskv, int crosskv_l
   a.ids = ids; a.n_out = n_out; a.sum_logp = sum_logp; a.step_logp = step_logp; a.step_prob = step_prob;
   a.steps_max = steps_max_dev;
   a.timing = getenv("KIRI_DEC_TIMING") != nullptr;
-  const int n_clusters = (B + kFL - 1) / kFL;
+  a.beam = 1; a.bmode = 0; a.lenp = 0.0;
+  if (beam) {
+    a.bmode = 1;
+    KIRI_REQUIRE(beam->beam >= 1 && beam->beam <= 5, "fused decoder: beam width %d not in 1..5", beam->beam);
+    KIRI_REQUIRE(cluster_size > 1 || Lmax <= 160, "fused decoder: beam search needs a cluster size > 1 for Lmax=%d", Lmax);
+    a.beam = beam->beam; a.lenp = beam->lenp; a.seqbuf = beam->seqbuf; a.lpbuf = beam->lpbuf;
+    a.bm_score = beam->score; a.bm_len = beam->len; a.bm_state = beam->state; a.bm_ids = beam->ids; a.bm_logp = beam->logp;
+  }
+  const int lpc = kFL / a.beam;
+  const int n_clusters = (B + lpc - 1) / lpc;
   switch (cluster_size) {
     case 1: return launch_fused<1>(a, n_clusters, stream);
     case 2: return launch_fused<2>(a, n_clusters, stream);

@@ -18,13 +18,19 @@ int gemm_call(const void* a, const void* w, const float* bias, int M, int N, int
               const float* resid, const float* ln_g, const float* ln_b, void* out2, cudaStream_t stream);
 
 // decoder_fused.cu: whole-decode persistent cluster kernel
+struct FusedBeam {           // beam-search mode of the fused decoder (nullptr = greedy)
+  int beam; double lenp;
+  int* seqbuf; float* lpbuf; // [2][n_slots][Lmax] scratch, n_slots = fused_decoder_slots(B, beam)
+  double* score; int* len; int* state; int* ids; float* logp;   // outputs [B, beam(, Lmax)]
+};
+inline int fused_decoder_slots(int B, int beam) { const int lpc = 16 / beam; return (B + lpc - 1) / lpc * 16; }
 int fused_decoder_build(KiriHandle* h);
 void fused_decoder_free(KiriHandle* h);
 int fused_decoder_run(KiriHandle* h, const __nv_bfloat16* crosskv, int crosskv_ld, const int* mem_row0, const int* mem_len,
                       int T, __nv_bfloat16* self_k, __nv_bfloat16* self_v, const int* len_est, const int* forced,
                       const int* line_perm, int B, int Lmax, const KiriDecodeParams* p, int* ids, int* n_out,
                       float* sum_logp, float* step_logp, float* step_prob, int* steps_max_dev, int cluster_size,
-                      cudaStream_t stream);
+                      cudaStream_t stream, const FusedBeam* beam = nullptr);
 }  // namespace kiri
 
 namespace kiri {

@@ -423,8 +423,8 @@ class BatchedRecognizer:
                          streaming: bool = False) -> List[Optional[LineResult]]:
         """``src``: uint8 buffer (pinned host or device) holding pages/crops; ``entries[n,4]`` =
         (byte offset, pitch, w, h) of every crop after the reference's clamp-pad."""
-        if method not in ("ctc", "decoder"):
-            raise ValueError("method must be 'ctc' or 'decoder'")
+        if method not in ("ctc", "decoder", "beam"):
+            raise ValueError("method must be 'ctc', 'decoder' or 'beam'")
         caller = torch.cuda.current_stream(self.device)
         if caller != self.stream:
             self.stream.wait_stream(caller)
@@ -515,8 +515,11 @@ class BatchedRecognizer:
                                                    frame_prob=None if p_h is None else p_h[j], len_est=int(n_h[k]))
                 pos += B
             return results
-        # ---- greedy attention decoder over all lines at once
         len_h = n_h                                                  # length estimates bound the loop
+        if method == "beam":
+            return self._beam_finish(enc, dmeta[r0o:r0o + n_lines], dmeta[mlo:mlo + n_lines], n_all, len_h, c_h, order,
+                                     results)
+        # ---- greedy attention decoder over all lines at once
         Lmax = self.max_steps_bound(int(len_h.max()), max(T for _, _, T in enc["rows"]))
         dec_words = n_lines * Lmax * 3 + 2 * n_lines
         ddec = self._device("_ddec", dec_words, torch.int32)
@@ -545,6 +548,76 @@ class BatchedRecognizer:
             results[li] = LineResult("".join([tab[i] for i in text_ids.tolist()]), 0.6 * dec_conf + 0.4 * float(c_h[j]),
                                      float(c_h[j]), row, step_logp=slp_h[j, :nj], step_prob=spr_h[j, :nj],
                                      len_est=int(len_h[j]))
+        return results
+
+    def _beam_finish(self, enc, mem_row0, mem_len, len_est, len_h, ctc_conf_h, order, results):
+        """decode_method="beam" (model.py:390-600 with cfg.BEAM > 1): device beam search + device CTC
+        forward scores, then the reference's final ranking (model.py:562-598) in Python floats."""
+        cfg, tok = self.cfg, self.tok
+        beam = int(cfg.BEAM)
+        if not 1 <= beam <= 5:
+            raise ValueError(f"cfg.BEAM={beam}: the B200 beam decoder supports widths 1..5")
+        n_lines, M = len(order), int(enc["mem_bf16"].shape[0])
+        T_max = max(T for _, _, T in enc["rows"])
+        Lmax = self.max_steps_bound(int(len_h.max()), T_max)
+        p = self.decode_params(False)
+        need = self.lib.kiri_decode_beam_workspace_bytes(self.handle, n_lines, M, Lmax, beam)
+        ws = self._workspace(need, "_dws")
+        nb = n_lines * beam
+        # packed outputs: score f64[nb] | len i32[nb] | state i32[nb] | align f32[nb] | ids i32[nb*Lmax] | logp f32[nb*Lmax]
+        words = 2 * nb + 3 * nb + 2 * nb * Lmax
+        dout = self._device("_dbeam", words, torch.int32)
+        dout[:5 * nb].zero_()
+        score = dout[:2 * nb].view(torch.float64)
+        blen, bstate = dout[2 * nb:3 * nb], dout[3 * nb:4 * nb]
+        align = dout[4 * nb:5 * nb].view(torch.float32)
+        bids = dout[5 * nb:5 * nb + nb * Lmax]
+        blp = dout[5 * nb + nb * Lmax:5 * nb + 2 * nb * Lmax].view(torch.float32)
+        perm = torch.argsort(len_est, descending=True, stable=True).to(torch.int32)
+        _lib.check(self.lib.kiri_decode_beam_multi(self.handle, enc["mem_bf16"].data_ptr(), M, mem_row0.data_ptr(),
+                                                   mem_len.data_ptr(), len_est.data_ptr(), perm.data_ptr(), n_lines, Lmax,
+                                                   beam, float(cfg.BEAM_LENP), C.byref(p), ws.data_ptr(), need,
+                                                   score.data_ptr(), blen.data_ptr(), bstate.data_ptr(), bids.data_ptr(),
+                                                   blp.data_ptr(), _lib.stream_ptr()), "kiri_decode_beam_multi")
+        fuse_ctc = cfg.USE_CTC and cfg.CTC_FUSION_ALPHA > 0
+        if fuse_ctc:
+            _lib.check(self.lib.kiri_ctc_align_score(enc["logits"].data_ptr(), self.pw.Cp, self.pw.C, mem_row0.data_ptr(),
+                                                     mem_len.data_ptr(), n_lines, beam, Lmax, bids.data_ptr(),
+                                                     blen.data_ptr(), bstate.data_ptr(), tok.vocab_size,
+                                                     tok.unk_id + tok.ctc_offset, T_max, align.data_ptr(),
+                                                     _lib.stream_ptr()), "kiri_ctc_align_score")
+        self.launches += 3
+        hout = self._pinned("_hbeam", words, torch.int32)
+        hout[:words].copy_(dout[:words], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        h = hout.numpy()[:words].copy()
+        sc_h = h[:2 * nb].view(np.float64).reshape(n_lines, beam)
+        ln_h = h[2 * nb:3 * nb].reshape(n_lines, beam)
+        st_h = h[3 * nb:4 * nb].reshape(n_lines, beam)
+        al_h = h[4 * nb:5 * nb].view(np.float32).reshape(n_lines, beam)
+        id_h = h[5 * nb:5 * nb + nb * Lmax].reshape(n_lines, beam, Lmax)
+        lp_h = h[5 * nb + nb * Lmax:].view(np.float32).reshape(n_lines, beam, Lmax)
+        tab, eos = self._dec_table, tok.dec_eos
+        for j, li in enumerate(order):
+            best, best_key = None, None
+            for r in range(beam):                                   # hypotheses are in pruned (normed) order
+                if st_h[j, r] == 0:
+                    continue
+                n = int(ln_h[j, r])
+                length = max(1, n)
+                dec_score = float(sc_h[j, r]) / (length ** cfg.BEAM_LENP if length > 0 else 1.0)
+                key = dec_score + cfg.CTC_FUSION_ALPHA * float(al_h[j, r]) if fuse_ctc else dec_score
+                if best is None or key > best_key:                  # stable: ties keep the earlier hypothesis
+                    best, best_key = r, key
+            n = int(ln_h[j, best])
+            row = id_h[j, best, :n]
+            lps = lp_h[j, best, :n].astype(np.float64)
+            dec_conf = min(1.0, max(0.0, math.exp(float(lps.sum()) / n))) if n else 0.0
+            hit = np.nonzero(row == eos)[0]
+            text_ids = row[:hit[0]] if len(hit) else row
+            cc = float(ctc_conf_h[j])
+            results[li] = LineResult("".join([tab[i] for i in text_ids.tolist()]), 0.6 * dec_conf + 0.4 * cc, cc, row,
+                                     step_logp=lp_h[j, best, :n], step_prob=np.exp(lp_h[j, best, :n]), len_est=int(len_h[j]))
         return results
 
     def recognize_crops(self, crops: Sequence[np.ndarray], method: str = "ctc", streaming: bool = False):

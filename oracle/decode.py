@@ -8,6 +8,8 @@ Restates
   * ``greedy_ctc_decode_streaming``      — kiri_ocr/model.py:689-775
   * ``greedy_decode_streaming``          — kiri_ocr/model.py:779-946
   * ``OCR.recognize_region`` dispatch    — kiri_ocr/core.py:530-575
+  * ``beam_decode_one_batched`` at BEAM>1 ("beam") — kiri_ocr/model.py:390-600
+  * ``compute_ctc_alignment_score``      — kiri_ocr/model.py:603-668
 """
 from __future__ import annotations
 
@@ -127,6 +129,124 @@ def sequence_confidence(log_probs: List[float]) -> float:
     return min(1.0, max(0.0, math.exp(sum(log_probs) / len(log_probs))))
 
 
+# --------------------------------------------------------------------------- beam search
+def ctc_alignment_score(ctc_logits: torch.Tensor, dec_seq: List[int], tok) -> float:
+    """model.py:603-668.  The reference evaluates one ``torch.logsumexp`` per (t, s); here the 1/2/3
+    candidate rule is vectorised over s with -inf for the absent candidates, which gives the same
+    fp32 values (a zero term does not change the 3-way sum)."""
+    if ctc_logits.dim() == 3:
+        ctc_logits = ctc_logits.squeeze(0)
+    log_probs = F.log_softmax(ctc_logits.float(), dim=-1)
+    labels = []
+    for x in dec_seq[1:]:
+        if x == tok.dec_eos:
+            break
+        if x in (tok.dec_pad, tok.dec_bos):
+            continue
+        labels.append(tok.dec_to_ctc_id(x))
+    if not labels:
+        return log_probs[:, tok.blank_id].sum().item() / max(1, log_probs.size(0))
+    T, blank = log_probs.size(0), tok.blank_id
+    ext = [blank]
+    for lid in labels:
+        ext += [lid, blank]
+    S = len(ext)
+    ext_t = torch.tensor(ext)
+    ninf = float("-inf")
+    skip_ok = torch.zeros(S, dtype=torch.bool)
+    for s_ in range(2, S):
+        skip_ok[s_] = ext[s_] != blank and ext[s_] != ext[s_ - 2]
+    alpha = log_probs.new_full((S,), ninf)
+    alpha[0] = log_probs[0, blank]
+    if S > 1:
+        alpha[1] = log_probs[0, ext[1]]
+    for t in range(1, T):
+        a1 = torch.cat([alpha.new_full((1,), ninf), alpha[:-1]])
+        a2 = torch.cat([alpha.new_full((2,), ninf), alpha[:-2]])
+        a2 = torch.where(skip_ok, a2, alpha.new_full((S,), ninf))
+        stacked = torch.stack([alpha, a1, a2])
+        m = stacked.max(dim=0).values
+        lse = torch.where(torch.isinf(m), m, m + torch.log(torch.exp(stacked - m).sum(dim=0)))
+        alpha = lse + log_probs[t, ext_t]
+    if S == 1:
+        total = alpha[0]
+    else:
+        total = torch.logsumexp(torch.stack([alpha[S - 1], alpha[S - 2]]), dim=0)
+    return total.item() / max(1, len(labels))
+
+
+def _fork_state(st: "M.DecoderState", parents: List[int]) -> "M.DecoderState":
+    """KV caches of the hypotheses that descend from ``parents`` (rows of the previous step)."""
+    import copy
+    idx = torch.tensor(parents, dtype=torch.long)
+    new = copy.copy(st)
+    new.self_k = [None if k is None else k.index_select(0, idx) for k in st.self_k]
+    new.self_v = [None if v is None else v.index_select(0, idx) for v in st.self_v]
+    new.cross_k = [c[:1].expand(len(parents), -1, -1).contiguous() for c in st.cross_k]
+    new.cross_v = [c[:1].expand(len(parents), -1, -1).contiguous() for c in st.cross_v]
+    return new
+
+
+@torch.inference_mode()
+def beam_decode(sd, memp_1: torch.Tensor, ctc_logits_1: torch.Tensor, tok, cfg, heads: int = 8):
+    """``beam_decode_one_batched`` (model.py:390-600) with a KV cache instead of the full-prefix
+    re-run.  Returns (text, confidence, info) where info carries every surviving hypothesis."""
+    _, collapsed, ctc_conf, target_len = ctc_greedy(ctc_logits_1.reshape(-1, ctc_logits_1.shape[-1]).numpy())
+    max_steps = max_steps_for(cfg, target_len, memp_1.shape[1])
+    unk = tok.unk_id + tok.dec_offset
+    beams = [(0.0, [tok.dec_bos], [], False)]
+    st = M.DecoderState(sd, memp_1, heads)
+    alive_rows: List[int] = [0]                       # cache row of every alive hypothesis
+    for step in range(max_steps):
+        if all(b[3] for b in beams):
+            break
+        alive = [b for b in beams if not b[3]]
+        done = [b for b in beams if b[3]]
+        if not alive:
+            beams = done
+            break
+        st = _fork_state(st, alive_rows)
+        dec, lm = M.decoder_step(st, torch.tensor([b[1][-1] for b in alive]))
+        logp = fused_logp(dec, lm, cfg).clone()
+        for i, (_, seq, _, _) in enumerate(alive):
+            apply_penalties(logp[i], seq, cfg, unk, target_len)
+        topv, topi = torch.topk(logp, k=cfg.BEAM, dim=-1)
+        new_beams = [(b, -1) for b in done]
+        for bi, (base, seq, lps, _) in enumerate(alive):
+            for v, tid in zip(topv[bi].tolist(), topi[bi].tolist()):
+                new_beams.append(((base + float(v), seq + [int(tid)], lps + [float(v)], int(tid) == tok.dec_eos), bi))
+
+        def normed(entry):
+            score, seq, _, _ = entry[0]
+            L = max(1, len(seq) - 1)
+            return score / (((5 + L) ** cfg.BEAM_LENP) / ((5 + 1) ** cfg.BEAM_LENP))
+
+        new_beams.sort(key=normed, reverse=True)
+        kept = new_beams[: cfg.BEAM]
+        beams = [b for b, _ in kept]
+        alive_rows = [row for b, row in kept if not b[3]]
+
+    def final(entry):
+        score, seq, lps, _ = entry
+        length = max(1, len(seq) - 1)
+        dec_score = score / (length ** cfg.BEAM_LENP if length > 0 else 1.0)
+        conf = sequence_confidence(lps)
+        if cfg.CTC_FUSION_ALPHA > 0:
+            return dec_score + cfg.CTC_FUSION_ALPHA * ctc_alignment_score(ctc_logits_1, seq, tok), conf
+        return dec_score, conf
+
+    scored = [(final(b), b) for b in beams]
+    scored.sort(key=lambda x: x[0][0], reverse=True)
+    (_, best_conf), (_, best_seq, _, _) = scored[0]
+    ids = []
+    for x in best_seq[1:]:
+        if x == tok.dec_eos:
+            break
+        ids.append(x)
+    info = {"beams": beams, "scored": [(sc, b[1]) for (sc, _), b in scored], "len_est": target_len, "ctc_conf": ctc_conf}
+    return tok.decode_dec(ids), 0.6 * best_conf + 0.4 * ctc_conf, info
+
+
 # --------------------------------------------------------------------------- line level
 @torch.inference_mode()
 def recognize_plane(sd, tok, cfg, plane_u8: np.ndarray, method: str = "ctc",
@@ -143,6 +263,10 @@ def recognize_plane(sd, tok, cfg, plane_u8: np.ndarray, method: str = "ctc",
     if method == "ctc":
         return tok.decode_ctc(best.tolist()), ctc_conf, info
     memp = M.mem_proj(sd, mem)
+    if method == "beam":
+        text, conf, binfo = beam_decode(sd, memp, logits, tok, cfg, heads)
+        info.update(binfo)
+        return text, conf, info
     ids, lps = greedy_decode(sd, memp, cfg, tok.unk_id + tok.dec_offset, length, heads)
     text_ids = []
     for t in ids:

@@ -108,10 +108,17 @@ def test_stream_chars_schema(setup, method):
     assert len(stream) == 3 and "cumulative_text" in stream[-1] and stream[-1]["total_regions"] == 3
 
 
-def test_beam_is_explicitly_unbuilt(setup):
+def test_beam_extract_text(setup):
+    """decode_method="beam" (BASELINE config 4) through the document API: same result schema."""
     from kiri_ocr_b200 import OCR
     path, img, page, boxes, sd = setup
     ocr = OCR(model_path=path, decode_method="beam")
-    ocr._detector = FakeDetector(boxes[:1])
-    with pytest.raises(NotImplementedError):
-        ocr.extract_text(img)
+    ocr.cfg.BEAM = 5
+    ocr._detector = FakeDetector(boxes[:2])
+    text, results = ocr.extract_text(img)
+    assert len(results) == 2 and isinstance(text, str)
+    for r in results:
+        assert set(r) >= {"box", "text", "confidence", "det_confidence", "line_number"}
+        assert 0.0 <= r["confidence"] <= 1.0
+    chunks = list(ocr.extract_text_stream_chars(img))
+    assert chunks and {c["region_number"] for c in chunks} == {1, 2}

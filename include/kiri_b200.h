@@ -59,20 +59,22 @@ int kiri_profile_end(double* ms_by_stage_host, int* count_by_stage_host, int n);
  * done per line on the CPU by the reference.  Bit-exact with Pillow's fixed-point resample. */
 typedef struct {
   int64_t src_offset; /* byte offset of the crop's top-left pixel inside `src`            */
+  int64_t out_offset; /* ELEMENT offset of the crop's [img_h, Wb] plane inside the outputs */
   int32_t pitch;      /* bytes between source rows                                         */
   int32_t w, h;       /* crop size after the reference's clamp-pad (core.py:510-515)       */
   int32_t nw;         /* max(1, round(w * img_h / h)) — Python round (model.py:321-322)    */
-  int32_t out_index;  /* line slot in the output batch                                     */
+  int32_t Wb;         /* batch width of the crop's group: the plane is cropped/padded to it */
   int32_t strip_w;    /* output columns resampled by one CTA (fits the shared-memory budget)  */
 } KiriCropDesc;
 
 /* shared memory needed by one crop for a given strip width (host helper, no GPU call) */
 int kiri_preprocess_smem_bytes(int w, int h, int nw, int img_h, int Wb, int strip_w);
 
-/* planes_u8: [n_slots, img_h, Wb] uint8; norm_bf16 (nullable): same shape, (v/255-0.5)/0.5.
+/* planes_u8: uint8 buffer holding every crop's [img_h, Wb] plane at its out_offset (all width
+ * groups of a batch go in ONE launch); norm_bf16 (nullable): same offsets, (v/255-0.5)/0.5.
  * One CTA resamples one strip of strip_w output columns of one crop; max_strips >= the largest
  * ceil(min(nw, Wb) / strip_w) over the crops (grid = n_crops x max_strips). */
-int kiri_preprocess_pack(const uint8_t* src, const KiriCropDesc* descs, int n_crops, int img_h, int Wb,
+int kiri_preprocess_pack(const uint8_t* src, const KiriCropDesc* descs, int n_crops, int img_h,
                          int smem_bytes, int max_strips, uint8_t* planes_u8, void* norm_bf16, cudaStream_t stream);
 
 /* ---------------------------------------------------------------- K2: stem layer 1
@@ -123,6 +125,12 @@ int kiri_encoder_attention(const void* qkv_bf16, void* out_bf16, int n_lines, in
  * probability.  frame_ids / frame_prob ([n_lines, T], nullable) serve the streaming API. */
 int kiri_ctc_greedy(const void* logits, int logits_dtype, int n_lines, int T, int C, int ld, int* ids,
                     int* n_ids, float* conf, int* frame_ids, float* frame_prob, cudaStream_t stream);
+
+/* The same over a concatenated token stream: line b owns logits rows [row0[b], row0[b] + len[b])
+ * (device int arrays); ids / frame_ids / frame_prob are flat [M_total] and line b writes at row0[b]. */
+int kiri_ctc_greedy_multi(const void* logits, int logits_dtype, int n_lines, const int* row0, const int* len,
+                          int max_T, int C, int ld, int* ids, int* n_ids, float* conf, int* frame_ids,
+                          float* frame_prob, cudaStream_t stream);
 
 /* ---------------------------------------------------------------- model-level handle
  * Packed weights (produced once per checkpoint by kiri_ocr_b200/weights.py): BN folded into the conv

@@ -23,8 +23,8 @@ vp, fp, ip = C.c_void_p, C.c_void_p, C.c_void_p      # all device pointers trave
 
 
 class KiriCropDesc(C.Structure):
-    _fields_ = [("src_offset", C.c_int64), ("pitch", C.c_int32), ("w", C.c_int32), ("h", C.c_int32),
-                ("nw", C.c_int32), ("out_index", C.c_int32), ("strip_w", C.c_int32)]
+    _fields_ = [("src_offset", C.c_int64), ("out_offset", C.c_int64), ("pitch", C.c_int32), ("w", C.c_int32),
+                ("h", C.c_int32), ("nw", C.c_int32), ("Wb", C.c_int32), ("strip_w", C.c_int32)]
 
 
 class KiriDims(C.Structure):
@@ -72,7 +72,7 @@ _SIGS = {
     "kiri_profile_begin": (C.c_int, []),
     "kiri_profile_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]),
     "kiri_preprocess_smem_bytes": (C.c_int, [C.c_int] * 6),
-    "kiri_preprocess_pack": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
+    "kiri_preprocess_pack": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
     "kiri_conv1": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]),
     "kiri_conv3x3_bf16": (C.c_int, [vp, vp, vp] + [C.c_int] * 7 + [vp, vp]),
     "kiri_gemm_bf16": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),
@@ -81,6 +81,7 @@ _SIGS = {
     "kiri_layernorm": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]),
     "kiri_encoder_attention": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
     "kiri_ctc_greedy": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),
+    "kiri_ctc_greedy_multi": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),
     "kiri_create": (C.c_int, [C.POINTER(KiriDims), C.POINTER(KiriWeights), C.POINTER(vp)]),
     "kiri_destroy": (None, [vp]),
     "kiri_encode_workspace_bytes": (C.c_size_t, [vp, C.c_int, C.c_int, C.c_int]),

@@ -28,13 +28,16 @@ template <typename T>
 __global__ void __launch_bounds__(kCtcThreads)
 ctc_greedy_kernel(const T* __restrict__ logits, int Tn, int C, int ld, int* __restrict__ ids,
                   int* __restrict__ n_ids, float* __restrict__ conf, int* __restrict__ frame_ids,
-                  float* __restrict__ frame_prob) {
+                  float* __restrict__ frame_prob, const int* __restrict__ row0, const int* __restrict__ lens) {
   __shared__ int s_id[kCtcMaxT];
   __shared__ float s_psum[kCtcThreads / 32];
   __shared__ int s_cnt[kCtcThreads / 32];
   const int line = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = kCtcThreads >> 5;
-  const T* base = logits + static_cast<size_t>(line) * Tn * ld;
+  // fixed-shape batch: line i owns rows [i*Tn, (i+1)*Tn); token-stream form: rows [row0[i], +lens[i])
+  const size_t r0 = row0 ? static_cast<size_t>(row0[line]) : static_cast<size_t>(line) * Tn;
+  if (lens) Tn = lens[line];
+  const T* base = logits + r0 * ld;
 
   float psum = 0.f;
   for (int t = warp; t < Tn; t += nwarps) {
@@ -60,8 +63,8 @@ ctc_greedy_kernel(const T* __restrict__ logits, int Tn, int C, int ld, int* __re
     if (lane == 0) {
       s_id[t] = am;
       psum += p;
-      if (frame_ids) frame_ids[static_cast<size_t>(line) * Tn + t] = am;
-      if (frame_prob) frame_prob[static_cast<size_t>(line) * Tn + t] = p;
+      if (frame_ids) frame_ids[r0 + t] = am;
+      if (frame_prob) frame_prob[r0 + t] = p;
     }
   }
   if (lane == 0) s_psum[warp] = psum;
@@ -85,7 +88,7 @@ ctc_greedy_kernel(const T* __restrict__ logits, int Tn, int C, int ld, int* __re
       if (wi < warp) woff += s_cnt[wi];
       total += s_cnt[wi];
     }
-    if (keep) ids[static_cast<size_t>(line) * Tn + base_out + woff + __popc(bal & ((1u << lane) - 1))] = id;
+    if (keep) ids[r0 + base_out + woff + __popc(bal & ((1u << lane) - 1))] = id;
     base_out += total;
     __syncthreads();
   }
@@ -109,12 +112,25 @@ extern "C" int kiri_ctc_greedy(const void* logits, int logits_dtype, int n_lines
   if (n_lines == 0) return 0;
   if (logits_dtype == KIRI_DTYPE_F32)
     ctc_greedy_kernel<float><<<n_lines, kCtcThreads, 0, stream>>>(
-        reinterpret_cast<const float*>(logits), T, C, ld, ids, n_ids, conf, frame_ids, frame_prob);
+        reinterpret_cast<const float*>(logits), T, C, ld, ids, n_ids, conf, frame_ids, frame_prob, nullptr, nullptr);
   else if (logits_dtype == KIRI_DTYPE_BF16)
     ctc_greedy_kernel<__nv_bfloat16><<<n_lines, kCtcThreads, 0, stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(logits), T, C, ld, ids, n_ids, conf, frame_ids, frame_prob);
+        reinterpret_cast<const __nv_bfloat16*>(logits), T, C, ld, ids, n_ids, conf, frame_ids, frame_prob, nullptr, nullptr);
   else
     KIRI_REQUIRE(false, "kiri_ctc_greedy: unknown dtype %d", logits_dtype);
+  KIRI_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int kiri_ctc_greedy_multi(const void* logits, int logits_dtype, int n_lines, const int* row0, const int* len,
+                                     int max_T, int C, int ld, int* ids, int* n_ids, float* conf, int* frame_ids,
+                                     float* frame_prob, cudaStream_t stream) {
+  KIRI_REQUIRE(logits && row0 && len && ids && n_ids && conf, "kiri_ctc_greedy_multi: null pointer");
+  KIRI_REQUIRE(max_T > 0 && max_T <= kCtcMaxT && C > 0 && ld >= C, "kiri_ctc_greedy_multi: bad shape T=%d C=%d ld=%d", max_T, C, ld);
+  KIRI_REQUIRE(logits_dtype == KIRI_DTYPE_F32, "kiri_ctc_greedy_multi: fp32 logits only");
+  if (n_lines == 0) return 0;
+  ctc_greedy_kernel<float><<<n_lines, kCtcThreads, 0, stream>>>(reinterpret_cast<const float*>(logits), max_T, C, ld, ids,
+                                                                n_ids, conf, frame_ids, frame_prob, row0, len);
   KIRI_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -72,19 +72,19 @@ __device__ __forceinline__ uint8_t clip8(int acc) {
 
 __global__ void __launch_bounds__(kPreThreads)
 preprocess_pack_kernel(const uint8_t* __restrict__ src, const KiriCropDesc* __restrict__ descs,
-                       int img_h, int Wb, uint8_t* __restrict__ planes,
+                       int img_h, uint8_t* __restrict__ planes,
                        __nv_bfloat16* __restrict__ norm_out, int smem_bytes) {
   extern __shared__ __align__(16) uint8_t sm[];
   __shared__ unsigned long long s_sum;
   const KiriCropDesc d = descs[blockIdx.x];
   const int tid = threadIdx.x;
-  const int w = d.w, h = d.h, nw = d.nw;
+  const int w = d.w, h = d.h, nw = d.nw, Wb = d.Wb;
   const int Wout = nw < Wb ? nw : Wb;
   const int strip0 = static_cast<int>(blockIdx.y) * d.strip_w;   // first output column of this CTA
   if (strip0 >= Wout) return;                                    // (whole CTA: no barrier is skipped)
   const uint8_t* crop = src + d.src_offset;
-  uint8_t* plane = planes + static_cast<size_t>(d.out_index) * img_h * Wb;
-  __nv_bfloat16* nplane = norm_out ? norm_out + static_cast<size_t>(d.out_index) * img_h * Wb : nullptr;
+  uint8_t* plane = planes + d.out_offset;                       // the crop's [img_h, Wb] plane
+  __nv_bfloat16* nplane = norm_out ? norm_out + d.out_offset : nullptr;
 
   // ---------------- pass 0: sum of the crop -> invert decision (core.py:524) ----------------
   if (tid == 0) s_sum = 0ull;
@@ -248,10 +248,10 @@ extern "C" int kiri_preprocess_smem_bytes(int w, int h, int nw, int img_h, int W
 }
 
 extern "C" int kiri_preprocess_pack(const uint8_t* src, const KiriCropDesc* descs_dev, int n_crops,
-                                    int img_h, int Wb, int smem_bytes, int max_strips, uint8_t* planes_u8,
+                                    int img_h, int smem_bytes, int max_strips, uint8_t* planes_u8,
                                     void* norm_bf16, cudaStream_t stream) {
   KIRI_REQUIRE(src && descs_dev && planes_u8, "kiri_preprocess_pack: null pointer");
-  KIRI_REQUIRE(n_crops >= 0 && img_h > 0 && Wb > 0 && max_strips >= 1 && max_strips <= 65535, "kiri_preprocess_pack: bad sizes");
+  KIRI_REQUIRE(n_crops >= 0 && img_h > 0 && max_strips >= 1 && max_strips <= 65535, "kiri_preprocess_pack: bad sizes");
   if (n_crops == 0) return 0;
   static int max_optin = 0;
   if (!max_optin) {
@@ -269,7 +269,7 @@ extern "C" int kiri_preprocess_pack(const uint8_t* src, const KiriCropDesc* desc
   KIRI_REQUIRE(smem_bytes <= max_optin, "kiri_preprocess_pack: %d bytes of shared memory requested, %d available",
                smem_bytes, max_optin);
   preprocess_pack_kernel<<<dim3(n_crops, max_strips), kPreThreads, smem_bytes, stream>>>(
-      src, descs_dev, img_h, Wb, planes_u8, reinterpret_cast<__nv_bfloat16*>(norm_bf16), smem_bytes);
+      src, descs_dev, img_h, planes_u8, reinterpret_cast<__nv_bfloat16*>(norm_bf16), smem_bytes);
   KIRI_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -27,8 +27,8 @@ from .config import CFG, CharTokenizer
 from .weights import PackedWeights
 
 BUCKETS = (128, 256, 384, 512, 640)
-DESC_DTYPE = np.dtype([("src_offset", "<i8"), ("pitch", "<i4"), ("w", "<i4"), ("h", "<i4"),
-                       ("nw", "<i4"), ("out_index", "<i4"), ("strip_w", "<i4")])
+DESC_DTYPE = np.dtype([("src_offset", "<i8"), ("out_offset", "<i8"), ("pitch", "<i4"), ("w", "<i4"), ("h", "<i4"),
+                       ("nw", "<i4"), ("Wb", "<i4"), ("strip_w", "<i4")])
 assert DESC_DTYPE.itemsize == C.sizeof(_lib.KiriCropDesc)
 PRE_SMEM_CAP = 56 * 1024           # four preprocessing CTAs per SM
 PRE_STRIP = 128                    # output columns per preprocessing CTA
@@ -93,7 +93,7 @@ def plan_groups(entries: np.ndarray, cfg: CFG, width_mode: str = "parity"
     nstr = (wout + strip - 1) // strip
     d_all = np.zeros(len(entries), DESC_DTYPE)
     d_all["src_offset"], d_all["pitch"], d_all["w"], d_all["h"] = entries[:, 0], entries[:, 1], w, h
-    d_all["nw"], d_all["strip_w"] = nw, strip
+    d_all["nw"], d_all["strip_w"], d_all["Wb"] = nw, strip, wb
     order = np.argsort(wb, kind="stable")
     wbs = wb[order]
     cuts = np.nonzero(np.diff(wbs))[0] + 1
@@ -101,7 +101,7 @@ def plan_groups(entries: np.ndarray, cfg: CFG, width_mode: str = "parity"
     for lo, hi in zip(np.concatenate([[0], cuts]), np.concatenate([cuts, [len(order)]])):
         idx = order[lo:hi]
         d = d_all[idx]
-        d["out_index"] = np.arange(hi - lo)
+        d["out_offset"] = np.arange(hi - lo, dtype=np.int64) * (img_h * int(wbs[lo]))   # inside the group's planes
         groups[int(wbs[lo])] = (idx, d, int(need[idx].max()), int(nstr[idx].max()))
     return groups
 
@@ -222,7 +222,7 @@ class BatchedRecognizer:
         dd = torch.from_numpy(descs.view(np.uint8).reshape(-1)).pin_memory().to(self.device, non_blocking=True)
         planes = torch.empty((n, self.cfg.IMG_H, Wb), dtype=torch.uint8, device=self.device)
         norm = torch.empty((n, self.cfg.IMG_H, Wb), dtype=torch.bfloat16, device=self.device) if want_norm else None
-        _lib.check(self.lib.kiri_preprocess_pack(src_dev.data_ptr(), dd.data_ptr(), n, self.cfg.IMG_H, Wb, smem, n_strips,
+        _lib.check(self.lib.kiri_preprocess_pack(src_dev.data_ptr(), dd.data_ptr(), n, self.cfg.IMG_H, smem, n_strips,
                                                  planes.data_ptr(), _lib.ptr(norm), _lib.stream_ptr()),
                    "kiri_preprocess_pack")
         self.launches += 1
@@ -365,20 +365,30 @@ class BatchedRecognizer:
         ``step_resident`` replays with no host<->device traffic."""
         src_dev = src if src.is_cuda else src.to(self.device)
         plan = []
-        row0 = 0
-        mem_row0, mem_len, kv = [], [], []
-        for Wb, (idx, descs, smem, n_strips) in self.plan(entries).items():
-            dd = torch.from_numpy(descs.view(np.uint8).reshape(-1).copy()).to(self.device)
-            planes = torch.empty((len(idx), self.cfg.IMG_H, Wb), dtype=torch.uint8, device=self.device)
+        row0, p0 = 0, 0
+        mem_row0, mem_len, kv, dall = [], [], [], []
+        groups = self.plan(entries)
+        total_planes = sum(len(g[0]) * self.cfg.IMG_H * Wb for Wb, g in groups.items())
+        planes_all = torch.empty(total_planes, dtype=torch.uint8, device=self.device)
+        smem_max = n_strips_max = 0
+        for Wb, (idx, descs, smem, n_strips) in groups.items():
+            descs = descs.copy()
+            descs["out_offset"] += p0                                   # absolute inside planes_all
+            dall.append(descs)
+            nb = len(idx) * self.cfg.IMG_H * Wb
+            planes = planes_all[p0:p0 + nb].view(len(idx), self.cfg.IMG_H, Wb)
+            p0 += nb
+            smem_max, n_strips_max = max(smem_max, smem), max(n_strips_max, n_strips)
             T = Wb // 4
             mem_row0.append(row0 + np.arange(len(idx), dtype=np.int32) * T)
             mem_len.append(np.full(len(idx), T, np.int32))
             kv.append(np.minimum((descs["nw"] + 3) // 4, T).astype(np.int32))
             row0 += len(idx) * T
-            plan.append({"Wb": Wb, "idx": idx, "descs": dd, "n": len(idx), "smem": smem, "planes": planes,
-                         "n_strips": n_strips})
+            plan.append({"Wb": Wb, "idx": idx, "n": len(idx), "planes": planes})
+        dd = torch.from_numpy(np.concatenate(dall).view(np.uint8).reshape(-1).copy()).to(self.device)
         kv_len = torch.from_numpy(np.concatenate(kv)).to(self.device) if self.width_mode == "masked" else None
-        out = {"src": src_dev, "groups": plan, "kv_len": kv_len,
+        out = {"src": src_dev, "groups": plan, "kv_len": kv_len, "descs": dd, "n_crops": len(entries), "smem": smem_max,
+               "n_strips": n_strips_max, "planes_all": planes_all, "M": row0, "n_lines": len(entries),
                "mem_row0": torch.from_numpy(np.concatenate(mem_row0)).to(self.device),
                "mem_len": torch.from_numpy(np.concatenate(mem_len)).to(self.device),
                "T_max": max(g["Wb"] for g in plan) // 4}
@@ -389,15 +399,21 @@ class BatchedRecognizer:
         """One pass of the hot path over the prepared batch, inputs already in HBM.  Returns the
         device outputs (no synchronisation in "ctc" mode; the decoder needs the CTC length
         estimates on the host once to bound its loop)."""
-        for g in prep["groups"]:
-            _lib.check(self.lib.kiri_preprocess_pack(prep["src"].data_ptr(), g["descs"].data_ptr(), g["n"],
-                                                     self.cfg.IMG_H, g["Wb"], g["smem"], g["n_strips"],
-                                                     g["planes"].data_ptr(), 0, _lib.stream_ptr()), "kiri_preprocess_pack")
-            self.launches += 1
+        _lib.check(self.lib.kiri_preprocess_pack(prep["src"].data_ptr(), prep["descs"].data_ptr(), prep["n_crops"],
+                                                 self.cfg.IMG_H, prep["smem"], prep["n_strips"],
+                                                 prep["planes_all"].data_ptr(), 0, _lib.stream_ptr()), "kiri_preprocess_pack")
+        self.launches += 1
         enc = self.encode_multi([g["planes"] for g in prep["groups"]], kv_len=prep["kv_len"])
-        outs = []
-        for (row0, B, T) in enc["rows"]:
-            outs.append(self.ctc_greedy(enc["logits"][row0:row0 + B * T].view(B, T, self.pw.Cp))[:3])
+        M, L = prep["M"], prep["n_lines"]
+        ids = torch.empty(M, dtype=torch.int32, device=self.device)
+        n_ids = torch.empty(L, dtype=torch.int32, device=self.device)
+        conf = torch.empty(L, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.kiri_ctc_greedy_multi(enc["logits"].data_ptr(), _lib.DTYPE_F32, L, prep["mem_row0"].data_ptr(),
+                                                  prep["mem_len"].data_ptr(), prep["T_max"], self.pw.C, self.pw.Cp,
+                                                  ids.data_ptr(), n_ids.data_ptr(), conf.data_ptr(), 0, 0, _lib.stream_ptr()),
+                   "kiri_ctc_greedy_multi")
+        self.launches += 1
+        outs = [(ids, n_ids, conf)]
         if method != "decoder":
             return outs
         len_est = torch.cat([o[1] for o in outs]) if len(outs) > 1 else outs[0][1]
@@ -449,30 +465,30 @@ class BatchedRecognizer:
         off, line0, row0 = 0, 0, 0
         desc_off = []
         kvo, r0o, mlo = desc_bytes // 4, desc_bytes // 4 + n_lines, desc_bytes // 4 + 2 * n_lines
+        p0 = 0
+        planes_list = []
+        planes_all = self._device("_planes", M * 4 * IMG_H, torch.uint8)
+        smem_max = n_strips_max = 0
         for Wb, (idx, descs, smem, n_strips) in groups:
             nb, T = descs.nbytes // 4, Wb // 4
+            descs["out_offset"] += p0                                   # absolute inside planes_all
             hm[off:off + nb] = descs.view(np.int32).reshape(-1)
-            desc_off.append(off)
             hm[kvo + line0:kvo + line0 + len(idx)] = np.minimum((descs["nw"] + 3) // 4, T)
             hm[r0o + line0:r0o + line0 + len(idx)] = row0 + np.arange(len(idx), dtype=np.int32) * T
             hm[mlo + line0:mlo + line0 + len(idx)] = T
+            npl = len(idx) * IMG_H * Wb
+            planes_list.append(planes_all[p0:p0 + npl].view(len(idx), IMG_H, Wb))
+            p0 += npl
+            smem_max, n_strips_max = max(smem_max, smem), max(n_strips_max, n_strips)
             off += nb
             line0 += len(idx)
             row0 += len(idx) * T
         dmeta = self._device("_dmeta", meta_words, torch.int32)
         dmeta[:meta_words].copy_(hmeta[:meta_words], non_blocking=True)
-        # ---- preprocess per group, one encoder pass over all groups
-        planes_all = self._device("_planes", M * 4 * IMG_H, torch.uint8)
-        planes_list, p0 = [], 0
-        for gi, (Wb, (idx, descs, smem, n_strips)) in enumerate(groups):
-            nb = len(idx) * IMG_H * Wb
-            planes = planes_all[p0:p0 + nb].view(len(idx), IMG_H, Wb)
-            p0 += nb
-            _lib.check(self.lib.kiri_preprocess_pack(src_dev.data_ptr(), dmeta[desc_off[gi]:].data_ptr(), len(idx), IMG_H, Wb,
-                                                     smem, n_strips, planes.data_ptr(), 0, _lib.stream_ptr()),
-                       "kiri_preprocess_pack")
-            self.launches += 1
-            planes_list.append(planes)
+        # ---- ONE preprocess launch for every width group, one encoder pass over all groups
+        _lib.check(self.lib.kiri_preprocess_pack(src_dev.data_ptr(), dmeta.data_ptr(), n_lines, IMG_H, smem_max, n_strips_max,
+                                                 planes_all.data_ptr(), 0, _lib.stream_ptr()), "kiri_preprocess_pack")
+        self.launches += 1
         kv_len = dmeta[kvo:kvo + n_lines] if self.width_mode == "masked" else None
         enc = self.encode_multi(planes_list, kv_len=kv_len)
         # ---- CTC greedy per group into ONE packed result buffer: ids[M] | n_ids[L] | conf[L] | frames
@@ -483,15 +499,13 @@ class BatchedRecognizer:
         conf_all = dres[M + n_lines:M + 2 * n_lines].view(torch.float32)
         fid_all = dres[M + 2 * n_lines:2 * M + 2 * n_lines] if want_frames else None
         fpr_all = dres[2 * M + 2 * n_lines:3 * M + 2 * n_lines].view(torch.float32) if want_frames else None
-        line0 = 0
-        for (r0, B, T) in enc["rows"]:
-            _lib.check(self.lib.kiri_ctc_greedy(enc["logits"][r0:].data_ptr(), _lib.DTYPE_F32, B, T, self.pw.C, Cp,
-                                                ids_all[r0:].data_ptr(), n_all[line0:].data_ptr(), conf_all[line0:].data_ptr(),
-                                                _lib.ptr(fid_all[r0:] if want_frames else None),
-                                                _lib.ptr(fpr_all[r0:] if want_frames else None), _lib.stream_ptr()),
-                       "kiri_ctc_greedy")
-            self.launches += 1
-            line0 += B
+        _lib.check(self.lib.kiri_ctc_greedy_multi(enc["logits"].data_ptr(), _lib.DTYPE_F32, n_lines,
+                                                  dmeta[r0o:].data_ptr(), dmeta[mlo:].data_ptr(),
+                                                  max(T for _, _, T in enc["rows"]), self.pw.C, Cp, ids_all.data_ptr(),
+                                                  n_all.data_ptr(), conf_all.data_ptr(),
+                                                  _lib.ptr(fid_all), _lib.ptr(fpr_all), _lib.stream_ptr()),
+                   "kiri_ctc_greedy_multi")
+        self.launches += 1
         order = np.concatenate([g[1][0] for g in groups])          # line index of every concatenated slot
         hres = self._pinned("_hres", res_words, torch.int32)
         hres[:res_words].copy_(dres[:res_words], non_blocking=True)

@@ -89,12 +89,13 @@ def run_preprocess(lib, crops_or_pages, boxes, Wb, img_h=48, want_norm=False, sm
         max_strips = max(max_strips, (wout + strip - 1) // strip)
         d = descs[i]
         d.src_offset = offs[pi] + y * page.shape[1] + x
-        d.pitch, d.w, d.h, d.nw, d.out_index, d.strip_w = page.shape[1], w, h, nw, i, strip
+        d.pitch, d.w, d.h, d.nw, d.Wb, d.strip_w = page.shape[1], w, h, nw, Wb, strip
+        d.out_offset = i * img_h * Wb
     src = torch.from_numpy(buf).cuda()
     dd = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8).cuda()
     planes = torch.zeros((len(boxes), img_h, Wb), dtype=torch.uint8, device="cuda")
     norm = torch.zeros((len(boxes), img_h, Wb), dtype=torch.bfloat16, device="cuda") if want_norm else None
-    _lib.check(lib.kiri_preprocess_pack(src.data_ptr(), dd.data_ptr(), len(boxes), img_h, Wb, smem, max_strips,
+    _lib.check(lib.kiri_preprocess_pack(src.data_ptr(), dd.data_ptr(), len(boxes), img_h, smem, max_strips,
                                         planes.data_ptr(), _lib.ptr(norm), _lib.stream_ptr()))
     sync()
     return planes.cpu().numpy(), (norm.float().cpu().numpy() if want_norm else None)

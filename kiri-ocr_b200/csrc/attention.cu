@@ -45,6 +45,8 @@ encoder_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* _
   __shared__ __align__(128) uint8_t s_v[T * 64];
   const int head = blockIdx.x, line = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_trigger();
+  pdl_wait();                                       // qkv comes from the previous kernel
   const size_t ld = static_cast<size_t>(3) * D;
   const __nv_bfloat16* base = qkv + static_cast<size_t>(line) * T * ld + head * kHd;
 
@@ -162,11 +164,11 @@ extern "C" int kiri_encoder_attention(const void* qkv_bf16, void* out_bf16, int 
   const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(qkv_bf16);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_bf16);
   switch (T) {
-    case 32:  encoder_attention_kernel<32><<<grid, 64, 0, stream>>>(q, o, D, kv_len); break;
-    case 64:  encoder_attention_kernel<64><<<grid, 128, 0, stream>>>(q, o, D, kv_len); break;
-    case 96:  encoder_attention_kernel<96><<<grid, 192, 0, stream>>>(q, o, D, kv_len); break;
-    case 128: encoder_attention_kernel<128><<<grid, 256, 0, stream>>>(q, o, D, kv_len); break;
-    case 160: encoder_attention_kernel<160><<<grid, 320, 0, stream>>>(q, o, D, kv_len); break;
+    case 32:  KIRI_CHECK_CUDA(launch_pdl(encoder_attention_kernel<32>, grid, dim3(64), 0, stream, q, o, D, kv_len)); break;
+    case 64:  KIRI_CHECK_CUDA(launch_pdl(encoder_attention_kernel<64>, grid, dim3(128), 0, stream, q, o, D, kv_len)); break;
+    case 96:  KIRI_CHECK_CUDA(launch_pdl(encoder_attention_kernel<96>, grid, dim3(192), 0, stream, q, o, D, kv_len)); break;
+    case 128: KIRI_CHECK_CUDA(launch_pdl(encoder_attention_kernel<128>, grid, dim3(256), 0, stream, q, o, D, kv_len)); break;
+    case 160: KIRI_CHECK_CUDA(launch_pdl(encoder_attention_kernel<160>, grid, dim3(320), 0, stream, q, o, D, kv_len)); break;
     default: KIRI_REQUIRE(false, "kiri_encoder_attention: T=%d not in {32,64,96,128,160}", T);
   }
   KIRI_CHECK_CUDA(cudaGetLastError());

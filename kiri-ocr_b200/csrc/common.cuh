@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace kiri {
 
@@ -25,6 +26,25 @@ void set_last_error(const char* fmt, ...);
       return -2;                                                                           \
     }                                                                                      \
   } while (0)
+// host: kernel launch with programmatic stream serialization (falls back to plain ordering when
+// the previous kernel in the stream never triggers)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  static const bool off = getenv("KIRI_NO_PDL") != nullptr;
+  cfg.attrs = at;
+  cfg.numAttrs = off ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 #define KIRI_REQUIRE(cond, ...)                                                            \
   do {                                                                                     \
     if (!(cond)) {                                                                         \
@@ -91,6 +111,16 @@ __device__ __forceinline__ float gelu_erf_fast(float v) {
   const float er = 1.0f - p * __expf(-z * z);
   return 0.5f * v * (1.0f + copysignf(er, v));
 }
+
+// ------------------------------------------------------------------ programmatic dependent launch
+// Every kernel of the step is launched with cudaLaunchAttributeProgrammaticStreamSerialization
+// (launch_pdl below): a CTA slot that frees up while the previous kernel's last wave is still
+// running starts this kernel's prologue (barrier init, TMEM alloc, tensor-map prefetch, smem
+// staging of constants) instead of idling.  pdl_wait() is the point past which data written by the
+// previous kernel may be touched; pdl_trigger() lets the NEXT kernel's CTAs be scheduled as early
+// as resources allow (they stop at their own pdl_wait()).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

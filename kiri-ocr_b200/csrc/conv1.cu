@@ -30,6 +30,8 @@ conv1_bn_silu_kernel(const uint8_t* __restrict__ planes, __nv_bfloat16* __restri
   for (int v = tid; v < 256; v += kConv1Threads)
     s_norm[v] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(v), 255.0f), 0.5f), 0.5f);
   __syncthreads();
+  pdl_trigger();
+  pdl_wait();                                       // the planes come from the previous kernel
 
   const int tiles_per_row = W / kConv1Threads;
   const int tile = blockIdx.x;
@@ -94,8 +96,7 @@ extern "C" int kiri_conv1(const uint8_t* planes_u8, const float* w_host, const f
   for (int i = 0; i < kC1; ++i) p.b[i] = b_host[i];
   const long long tiles = static_cast<long long>(n_lines) * H * (W / kConv1Threads);
   KIRI_REQUIRE(tiles < 0x7fffffffll, "kiri_conv1: grid too large");
-  conv1_bn_silu_kernel<<<static_cast<unsigned>(tiles), kConv1Threads, 0, stream>>>(
-      planes_u8, reinterpret_cast<__nv_bfloat16*>(out_bf16_nhwc64), H, W, p);
-  KIRI_CHECK_CUDA(cudaGetLastError());
+  KIRI_CHECK_CUDA(launch_pdl(conv1_bn_silu_kernel, dim3(static_cast<unsigned>(tiles)), dim3(kConv1Threads), 0, stream,
+                             planes_u8, reinterpret_cast<__nv_bfloat16*>(out_bf16_nhwc64), H, W, p));
   return 0;
 }

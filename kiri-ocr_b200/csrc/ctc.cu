@@ -34,6 +34,8 @@ ctc_greedy_kernel(const T* __restrict__ logits, int Tn, int C, int ld, int* __re
   __shared__ int s_cnt[kCtcThreads / 32];
   const int line = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = kCtcThreads >> 5;
+  pdl_trigger();
+  pdl_wait();                                       // the logits come from the previous kernel
   // fixed-shape batch: line i owns rows [i*Tn, (i+1)*Tn); token-stream form: rows [row0[i], +lens[i])
   const size_t r0 = row0 ? static_cast<size_t>(row0[line]) : static_cast<size_t>(line) * Tn;
   if (lens) Tn = lens[line];
@@ -129,9 +131,9 @@ extern "C" int kiri_ctc_greedy_multi(const void* logits, int logits_dtype, int n
   KIRI_REQUIRE(max_T > 0 && max_T <= kCtcMaxT && C > 0 && ld >= C, "kiri_ctc_greedy_multi: bad shape T=%d C=%d ld=%d", max_T, C, ld);
   KIRI_REQUIRE(logits_dtype == KIRI_DTYPE_F32, "kiri_ctc_greedy_multi: fp32 logits only");
   if (n_lines == 0) return 0;
-  ctc_greedy_kernel<float><<<n_lines, kCtcThreads, 0, stream>>>(reinterpret_cast<const float*>(logits), max_T, C, ld, ids,
-                                                                n_ids, conf, frame_ids, frame_prob, row0, len);
-  KIRI_CHECK_CUDA(cudaGetLastError());
+  KIRI_CHECK_CUDA(launch_pdl(ctc_greedy_kernel<float>, dim3(n_lines), dim3(kCtcThreads), 0, stream,
+                             reinterpret_cast<const float*>(logits), max_T, C, ld, ids, n_ids, conf, frame_ids, frame_prob,
+                             row0, len));
   return 0;
 }
 

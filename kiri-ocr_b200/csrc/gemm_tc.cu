@@ -140,6 +140,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  pdl_trigger();                                   // the next kernel may start its prologue
+  pdl_wait();                                      // A / residual come from the previous kernel
 
   if (warp == kTmaWarp) {
     // ============================ TMA producer ============================
@@ -616,8 +618,8 @@ static int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   }
   int grid = num_m_tiles * num_n_tiles;
   if (grid > g_num_sms) grid = g_num_sms;
-  kern<<<grid, kNumThreads, smem, stream>>>(tmA, tmB, tmOut, tmRes, tmOut2, g, e, bn, num_m_tiles, num_n_tiles, stages, CPS);
-  KIRI_CHECK_CUDA(cudaGetLastError());
+  KIRI_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kNumThreads), smem, stream, tmA, tmB, tmOut, tmRes, tmOut2, g, e, bn,
+                             num_m_tiles, num_n_tiles, stages, CPS));
   return 0;
 }
 

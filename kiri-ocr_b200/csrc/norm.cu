@@ -21,6 +21,8 @@ pool_pos_ln_kernel(const __nv_bfloat16* __restrict__ act, const float* __restric
                    float* __restrict__ x_f32, __nv_bfloat16* __restrict__ a_bf16) {
   const int lane = threadIdx.x & 31;
   const int tok = blockIdx.x * (kLnThreads / 32) + (threadIdx.x >> 5);
+  pdl_trigger();
+  pdl_wait();                                       // the stem output comes from the previous kernel
   if (tok >= n_tok) return;
   const int b = tok / T, t = tok - b * T;
   float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -50,6 +52,8 @@ ln_chain_kernel(const float* __restrict__ x, int n_tok, const float* g0, const f
                 const float* b1, __nv_bfloat16* __restrict__ z_bf16) {
   const int lane = threadIdx.x & 31;
   const int tok = blockIdx.x * (kLnThreads / 32) + (threadIdx.x >> 5);
+  pdl_trigger();
+  pdl_wait();
   if (tok >= n_tok) return;
   const float4 x0 = *reinterpret_cast<const float4*>(x + static_cast<size_t>(tok) * kD + lane * 8);
   const float4 x1 = *reinterpret_cast<const float4*>(x + static_cast<size_t>(tok) * kD + lane * 8 + 4);
@@ -76,10 +80,9 @@ extern "C" int kiri_pool_pos_ln(const void* act_bf16, const float* pos_table, in
   const int n_tok = n_lines * T;
   if (n_tok == 0) return 0;
   const int per = kLnThreads / 32;
-  pool_pos_ln_kernel<<<(n_tok + per - 1) / per, kLnThreads, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(act_bf16), pos_table, n_tok, RH, T, g0, b0, g1, b1, x_f32,
-      reinterpret_cast<__nv_bfloat16*>(a_bf16));
-  KIRI_CHECK_CUDA(cudaGetLastError());
+  KIRI_CHECK_CUDA(launch_pdl(pool_pos_ln_kernel, dim3((n_tok + per - 1) / per), dim3(kLnThreads), 0, stream,
+                             reinterpret_cast<const __nv_bfloat16*>(act_bf16), pos_table, n_tok, RH, T, g0, b0, g1, b1, x_f32,
+                             reinterpret_cast<__nv_bfloat16*>(a_bf16)));
   return 0;
 }
 
@@ -91,9 +94,8 @@ extern "C" int kiri_layernorm(const float* x, int n_tok, int D, const float* g0,
   KIRI_REQUIRE(!z_bf16 || (g1 && b1), "kiri_layernorm: second LayerNorm needs its affine");
   if (n_tok == 0) return 0;
   const int per = kLnThreads / 32;
-  ln_chain_kernel<<<(n_tok + per - 1) / per, kLnThreads, 0, stream>>>(
-      x, n_tok, g0, b0, y_f32, reinterpret_cast<__nv_bfloat16*>(y_bf16), g1, b1,
-      reinterpret_cast<__nv_bfloat16*>(z_bf16));
-  KIRI_CHECK_CUDA(cudaGetLastError());
+  KIRI_CHECK_CUDA(launch_pdl(ln_chain_kernel, dim3((n_tok + per - 1) / per), dim3(kLnThreads), 0, stream,
+                             x, n_tok, g0, b0, y_f32, reinterpret_cast<__nv_bfloat16*>(y_bf16), g1, b1,
+                             reinterpret_cast<__nv_bfloat16*>(z_bf16)));
   return 0;
 }

@@ -76,6 +76,8 @@ preprocess_pack_kernel(const uint8_t* __restrict__ src, const KiriCropDesc* __re
                        __nv_bfloat16* __restrict__ norm_out, int smem_bytes) {
   extern __shared__ __align__(16) uint8_t sm[];
   __shared__ unsigned long long s_sum;
+  pdl_trigger();
+  pdl_wait();                                       // descriptors / source may come from a copy kernel
   const KiriCropDesc d = descs[blockIdx.x];
   const int tid = threadIdx.x;
   const int w = d.w, h = d.h, nw = d.nw, Wb = d.Wb;
@@ -268,8 +270,7 @@ extern "C" int kiri_preprocess_pack(const uint8_t* src, const KiriCropDesc* desc
   }
   KIRI_REQUIRE(smem_bytes <= max_optin, "kiri_preprocess_pack: %d bytes of shared memory requested, %d available",
                smem_bytes, max_optin);
-  preprocess_pack_kernel<<<dim3(n_crops, max_strips), kPreThreads, smem_bytes, stream>>>(
-      src, descs_dev, img_h, planes_u8, reinterpret_cast<__nv_bfloat16*>(norm_bf16), smem_bytes);
-  KIRI_CHECK_CUDA(cudaGetLastError());
+  KIRI_CHECK_CUDA(launch_pdl(preprocess_pack_kernel, dim3(n_crops, max_strips), dim3(kPreThreads), smem_bytes, stream,
+                             src, descs_dev, img_h, planes_u8, reinterpret_cast<__nv_bfloat16*>(norm_bf16), smem_bytes));
   return 0;
 }

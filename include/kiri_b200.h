@@ -254,13 +254,15 @@ int kiri_decode_greedy(KiriHandle* h, const void* mem_bf16, const int* len_est, 
                        int* n_out, float* sum_logp, float* step_logp, float* step_prob,
                        const int* forced_ids, int* steps_run_host, int poll_every, cudaStream_t stream);
 /* The same over the concatenated token stream of kiri_encode_multi: line b attends to the memory
- * rows [mem_row0[b], mem_row0[b] + mem_len[b]) of mem_bf16 [M_total, D] (device int arrays).
+ * rows [mem_row0[b], mem_row0[b] + mem_len[b]) of mem_bf16 [M_total, D] (device int arrays;
+ * max_T >= every mem_len).  The cross K/V of a line are re-laid head-major once per batch so the
+ * per-step single-query attention reads contiguous [t][32] runs.
  * line_perm (nullable, device int[B]): decode slot -> line.  Sixteen consecutive slots share one
  * thread-block cluster, so listing the lines by decreasing len_est lets every cluster stop early
  * and lets the clusters that do not fit in the first wave hide behind the longest ones. */
 size_t kiri_decode_multi_workspace_bytes(const KiriHandle* h, int B, long long M_total, int Lmax);
 int kiri_decode_greedy_multi(KiriHandle* h, const void* mem_bf16, long long M_total, const int* mem_row0,
-                             const int* mem_len, const int* len_est, const int* line_perm, int B, int Lmax,
+                             const int* mem_len, int max_T, const int* len_est, const int* line_perm, int B, int Lmax,
                              const KiriDecodeParams* p,
                              void* workspace, size_t workspace_bytes, int* ids, int* n_out, float* sum_logp,
                              float* step_logp, float* step_prob, const int* forced_ids, int* steps_run_host,
@@ -277,7 +279,7 @@ int kiri_decode_greedy_multi(KiriHandle* h, const void* mem_bf16, long long M_to
  * ranking (model.py:562-579) is done by the caller with kiri_ctc_align_score. */
 size_t kiri_decode_beam_workspace_bytes(const KiriHandle* h, int B, long long M_total, int Lmax, int beam);
 int kiri_decode_beam_multi(KiriHandle* h, const void* mem_bf16, long long M_total, const int* mem_row0,
-                           const int* mem_len, const int* len_est, const int* line_perm, int B, int Lmax, int beam,
+                           const int* mem_len, int max_T, const int* len_est, const int* line_perm, int B, int Lmax, int beam,
                            double lenp, const KiriDecodeParams* p, void* workspace, size_t workspace_bytes,
                            double* bm_score, int* bm_len, int* bm_state, int* bm_ids, float* bm_logp,
                            cudaStream_t stream);

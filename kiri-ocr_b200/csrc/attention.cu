@@ -35,8 +35,11 @@ __device__ __forceinline__ uint32_t tile_off(int row, int chunk) {
   return static_cast<uint32_t>(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
 }
 
+// Two CTAs per (line, head), each owning half of the query rows (T/32 warps of 16 rows): with one
+// 10-warp CTA the 106 registers per thread allowed a single resident CTA per SM, so the global-load
+// phase of one (line, head) never overlapped the MMA phase of another; 5-warp CTAs fit three per SM.
 template <int T>
-__global__ void __launch_bounds__(T * 2)
+__global__ void __launch_bounds__(T)
 encoder_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int D,
                          const int* __restrict__ kv_len) {
   constexpr int NB = T / 8;          // key blocks of 8
@@ -50,17 +53,18 @@ encoder_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* _
   const size_t ld = static_cast<size_t>(3) * D;
   const __nv_bfloat16* base = qkv + static_cast<size_t>(line) * T * ld + head * kHd;
 
-  for (int idx = tid; idx < 3 * T * 4; idx += T * 2) {
-    const int which = idx / (T * 4);
-    const int rem = idx - which * (T * 4);
-    const int r = rem >> 2, c = rem & 3;
+  const int q0 = static_cast<int>(blockIdx.z) * (T / 2);       // first query row of this CTA
+  for (int idx = tid; idx < 2 * T * 4 + (T / 2) * 4; idx += T) {
+    int which, r, c;
+    if (idx < 2 * T * 4) { which = 1 + idx / (T * 4); const int rem = idx % (T * 4); r = rem >> 2; c = rem & 3; }
+    else { which = 0; const int rem = idx - 2 * T * 4; r = q0 + (rem >> 2); c = rem & 3; }
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + r * ld + which * D + c * 8));
     uint8_t* dst = which == 0 ? s_q : (which == 1 ? s_k : s_v);
     *reinterpret_cast<uint4*>(dst + tile_off(r, c)) = v;
   }
   __syncthreads();
 
-  const int m0 = warp * 16;
+  const int m0 = q0 + warp * 16;
   const uint32_t q_base = smem_u32(s_q), k_base = smem_u32(s_k), v_base = smem_u32(s_v);
 
   // Q fragments for the two k16 steps of head_dim 32
@@ -160,15 +164,26 @@ extern "C" int kiri_encoder_attention(const void* qkv_bf16, void* out_bf16, int 
   KIRI_REQUIRE(qkv_bf16 && out_bf16, "kiri_encoder_attention: null pointer");
   KIRI_REQUIRE(D == heads * kHd, "kiri_encoder_attention: head_dim must be 32 (D=%d, heads=%d)", D, heads);
   if (n_lines == 0) return 0;
-  dim3 grid(heads, n_lines);
+  dim3 grid(heads, n_lines, 2);
+  static bool carveout_set = false;
+  if (!carveout_set) {
+    // several CTAs per SM need the large shared-memory carve-out (the driver's default for a
+    // 30 KB static kernel was a 32 KB configuration = one resident CTA)
+    cudaFuncSetAttribute(encoder_attention_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(encoder_attention_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(encoder_attention_kernel<96>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(encoder_attention_kernel<128>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(encoder_attention_kernel<160>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    carveout_set = true;
+  }
   const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(qkv_bf16);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_bf16);
   switch (T) {
-    case 32:  KIRI_CHECK_CUDA(launch_pdl(encoder_attention_kernel<32>, grid, dim3(64), 0, stream, q, o, D, kv_len)); break;
-    case 64:  KIRI_CHECK_CUDA(launch_pdl(encoder_attention_kernel<64>, grid, dim3(128), 0, stream, q, o, D, kv_len)); break;
-    case 96:  KIRI_CHECK_CUDA(launch_pdl(encoder_attention_kernel<96>, grid, dim3(192), 0, stream, q, o, D, kv_len)); break;
-    case 128: KIRI_CHECK_CUDA(launch_pdl(encoder_attention_kernel<128>, grid, dim3(256), 0, stream, q, o, D, kv_len)); break;
-    case 160: KIRI_CHECK_CUDA(launch_pdl(encoder_attention_kernel<160>, grid, dim3(320), 0, stream, q, o, D, kv_len)); break;
+    case 32:  KIRI_CHECK_CUDA(launch_pdl(encoder_attention_kernel<32>, grid, dim3(32), 0, stream, q, o, D, kv_len)); break;
+    case 64:  KIRI_CHECK_CUDA(launch_pdl(encoder_attention_kernel<64>, grid, dim3(64), 0, stream, q, o, D, kv_len)); break;
+    case 96:  KIRI_CHECK_CUDA(launch_pdl(encoder_attention_kernel<96>, grid, dim3(96), 0, stream, q, o, D, kv_len)); break;
+    case 128: KIRI_CHECK_CUDA(launch_pdl(encoder_attention_kernel<128>, grid, dim3(128), 0, stream, q, o, D, kv_len)); break;
+    case 160: KIRI_CHECK_CUDA(launch_pdl(encoder_attention_kernel<160>, grid, dim3(160), 0, stream, q, o, D, kv_len)); break;
     default: KIRI_REQUIRE(false, "kiri_encoder_attention: T=%d not in {32,64,96,128,160}", T);
   }
   KIRI_CHECK_CUDA(cudaGetLastError());

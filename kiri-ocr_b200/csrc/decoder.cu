@@ -458,11 +458,11 @@ extern "C" int kiri_decode_greedy(KiriHandle* h, const void* mem_bf16, const int
 extern "C" size_t kiri_decode_multi_workspace_bytes(const KiriHandle* h, int B, long long M_total, int Lmax) {
   if (!h || B <= 0 || M_total <= 0 || Lmax <= 0) return 0;
   const size_t L = h->d.dec_layers, D = h->d.dec_dim;
-  return al256(static_cast<size_t>(M_total) * L * 2 * D * 2) + 2 * al256(L * B * Lmax * D * 2) + 256;
+  return 2 * al256(static_cast<size_t>(M_total) * L * 2 * D * 2) + 2 * al256(L * B * Lmax * D * 2) + 256;
 }
 
 extern "C" int kiri_decode_greedy_multi(KiriHandle* h, const void* mem_bf16, long long M_total, const int* mem_row0,
-                                        const int* mem_len, const int* len_est, const int* line_perm, int B, int Lmax,
+                                        const int* mem_len, int max_T, const int* len_est, const int* line_perm, int B, int Lmax,
                                         const KiriDecodeParams* p, void* workspace, size_t workspace_bytes, int* ids,
                                         int* n_out, float* sum_logp, float* step_logp, float* step_prob,
                                         const int* forced_ids, int* steps_run_host, cudaStream_t stream) {
@@ -478,18 +478,21 @@ extern "C" int kiri_decode_greedy_multi(KiriHandle* h, const void* mem_bf16, lon
   uint8_t* base = reinterpret_cast<uint8_t*>(workspace);
   __nv_bfloat16* crosskv = reinterpret_cast<__nv_bfloat16*>(base);
   size_t off = al256(static_cast<size_t>(M_total) * L * 2 * D * 2);
+  __nv_bfloat16* crosskv_hm = reinterpret_cast<__nv_bfloat16*>(base + off); off += al256(static_cast<size_t>(M_total) * L * 2 * D * 2);
   __nv_bfloat16* self_k = reinterpret_cast<__nv_bfloat16*>(base + off); off += al256(L * B * Lmax * D * 2);
   __nv_bfloat16* self_v = reinterpret_cast<__nv_bfloat16*>(base + off); off += al256(L * B * Lmax * D * 2);
   int* steps_dev = reinterpret_cast<int*>(base + off);
   { ProfScope ps(PS_DEC_CROSSKV, stream);
     KIRI_TRY(gemm_call(mem_bf16, w.crosskv_w, w.crosskv_b, static_cast<int>(M_total), static_cast<int>(L * 2 * D), d.enc_dim,
-                       EPI_BIAS_BF16, crosskv, nullptr, nullptr, nullptr, nullptr, stream)); }
+                       EPI_BIAS_BF16, crosskv, nullptr, nullptr, nullptr, nullptr, stream));
+    KIRI_TRY(crosskv_headmajor(crosskv, crosskv_hm, static_cast<int>(L * 2 * D), mem_row0, mem_len, 0, max_T, B, stream)); }
   KIRI_CHECK_CUDA(cudaMemsetAsync(steps_dev, 0, sizeof(int), stream));
   int cs = 8;
   if (const char* e = getenv("KIRI_DEC_CLUSTER")) cs = atoi(e);
   { ProfScope ps_step(PS_DEC_STEP, stream);
-    KIRI_TRY(fused_decoder_run(h, crosskv, static_cast<int>(L * 2 * D), mem_row0, mem_len, 0, self_k, self_v, len_est,
-                               forced_ids, line_perm, B, Lmax, p, ids, n_out, sum_logp, step_logp, step_prob, steps_dev, cs, stream)); }
+    KIRI_TRY(fused_decoder_run(h, crosskv_hm, static_cast<int>(L * 2 * D), mem_row0, mem_len, 0, self_k, self_v, len_est,
+                               forced_ids, line_perm, B, Lmax, p, ids, n_out, sum_logp, step_logp, step_prob, steps_dev, cs, stream,
+                               nullptr, 1)); }
   if (steps_run_host) {
     static int* steps_host = nullptr;
     if (!steps_host) KIRI_CHECK_CUDA(cudaMallocHost(&steps_host, sizeof(int)));
@@ -504,12 +507,12 @@ extern "C" int kiri_decode_greedy_multi(KiriHandle* h, const void* mem_bf16, lon
 extern "C" size_t kiri_decode_beam_workspace_bytes(const KiriHandle* h, int B, long long M_total, int Lmax, int beam) {
   if (!h || B <= 0 || M_total <= 0 || Lmax <= 0 || beam < 1 || beam > 5) return 0;
   const size_t L = h->d.dec_layers, D = h->d.dec_dim, ns = fused_decoder_slots(B, beam);
-  return al256(static_cast<size_t>(M_total) * L * 2 * D * 2) + 2 * al256(L * ns * Lmax * D * 2) +
+  return 2 * al256(static_cast<size_t>(M_total) * L * 2 * D * 2) + 2 * al256(L * ns * Lmax * D * 2) +
          2 * al256(2 * ns * static_cast<size_t>(Lmax) * 4) + 256;
 }
 
 extern "C" int kiri_decode_beam_multi(KiriHandle* h, const void* mem_bf16, long long M_total, const int* mem_row0,
-                                      const int* mem_len, const int* len_est, const int* line_perm, int B, int Lmax,
+                                      const int* mem_len, int max_T, const int* len_est, const int* line_perm, int B, int Lmax,
                                       int beam, double lenp, const KiriDecodeParams* p, void* workspace,
                                       size_t workspace_bytes, double* bm_score, int* bm_len, int* bm_state,
                                       int* bm_ids, float* bm_logp, cudaStream_t stream) {
@@ -526,6 +529,7 @@ extern "C" int kiri_decode_beam_multi(KiriHandle* h, const void* mem_bf16, long 
   uint8_t* base = reinterpret_cast<uint8_t*>(workspace);
   size_t off = 0;
   __nv_bfloat16* crosskv = reinterpret_cast<__nv_bfloat16*>(base); off += al256(static_cast<size_t>(M_total) * L * 2 * D * 2);
+  __nv_bfloat16* crosskv_hm = reinterpret_cast<__nv_bfloat16*>(base + off); off += al256(static_cast<size_t>(M_total) * L * 2 * D * 2);
   __nv_bfloat16* self_k = reinterpret_cast<__nv_bfloat16*>(base + off); off += al256(L * ns * Lmax * D * 2);
   __nv_bfloat16* self_v = reinterpret_cast<__nv_bfloat16*>(base + off); off += al256(L * ns * Lmax * D * 2);
   FusedBeam fb;
@@ -536,12 +540,13 @@ extern "C" int kiri_decode_beam_multi(KiriHandle* h, const void* mem_bf16, long 
   fb.score = bm_score; fb.len = bm_len; fb.state = bm_state; fb.ids = bm_ids; fb.logp = bm_logp;
   { ProfScope ps(PS_DEC_CROSSKV, stream);
     KIRI_TRY(gemm_call(mem_bf16, w.crosskv_w, w.crosskv_b, static_cast<int>(M_total), static_cast<int>(L * 2 * D), d.enc_dim,
-                       EPI_BIAS_BF16, crosskv, nullptr, nullptr, nullptr, nullptr, stream)); }
+                       EPI_BIAS_BF16, crosskv, nullptr, nullptr, nullptr, nullptr, stream));
+    KIRI_TRY(crosskv_headmajor(crosskv, crosskv_hm, static_cast<int>(L * 2 * D), mem_row0, mem_len, 0, max_T, B, stream)); }
   KIRI_CHECK_CUDA(cudaMemsetAsync(steps_dev, 0, sizeof(int), stream));
   int cs = 8;
   if (const char* e = getenv("KIRI_DEC_CLUSTER")) cs = atoi(e);
   ProfScope ps_step(PS_DEC_STEP, stream);
   // the self-attention cache is indexed by physical slot: B of the run function = decode slots in use
-  return fused_decoder_run(h, crosskv, static_cast<int>(L * 2 * D), mem_row0, mem_len, 0, self_k, self_v, len_est, nullptr,
-                           line_perm, B, Lmax, p, nullptr, nullptr, nullptr, nullptr, nullptr, steps_dev, cs, stream, &fb);
+  return fused_decoder_run(h, crosskv_hm, static_cast<int>(L * 2 * D), mem_row0, mem_len, 0, self_k, self_v, len_est, nullptr,
+                           line_perm, B, Lmax, p, nullptr, nullptr, nullptr, nullptr, nullptr, steps_dev, cs, stream, &fb, 1);
 }

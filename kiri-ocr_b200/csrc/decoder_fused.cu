@@ -47,7 +47,8 @@ struct FusedArgs {
   const uint4* wheads; const float* bheads;
   const float *dec_ln_g, *dec_ln_b, *emb, *pe;
   int layers, ff, Vd, Vp, has_pos;
-  const __nv_bfloat16* crosskv; int crosskv_ld;       // [rows, layers*2*D]
+  const __nv_bfloat16* crosskv; int crosskv_ld;       // [rows, layers*2*D], or head-major per line (kv_hm)
+  int kv_hm;                                          // 1: line block = [layer][K|V][head][t][32] (crosskv_headmajor)
   const int* mem_row0; const int* mem_len;            // per line (nullable -> b*T, T)
   int T;
   __nv_bfloat16 *self_k, *self_v;                     // [layers][B][Lmax][D]
@@ -545,9 +546,19 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
         const int i = pidx % kFL, hl = pidx / kFL, head = rank * HPC + hl;
         float o = 0.f;
         if (st->valid[i] && !st->finished[i]) {
-          const __nv_bfloat16* kb = A.crosskv + static_cast<size_t>(st->row0[i]) * A.crosskv_ld + l * 2 * D + head * kHd;
-          const size_t ldk = A.crosskv_ld;
-          o = attend_warp<true>(qloc + i * DC + hl * kHd, kb, kb + D, [&](int j) { return j * ldk; }, st->mlen[i], vst, lane);
+          const int Tm = st->mlen[i];
+          if (A.kv_hm) {
+            // head-major block of the line: K of (layer, head) is Tm contiguous 64-byte rows -> a warp's
+            // 32 key loads are one contiguous 2 KB run instead of 32 rows 3 KB apart
+            const __nv_bfloat16* kb = A.crosskv + static_cast<size_t>(st->row0[i]) * A.crosskv_ld +
+                                      (static_cast<size_t>(l) * 2 * kHeads + head) * Tm * kHd;
+            o = attend_warp<true>(qloc + i * DC + hl * kHd, kb, kb + static_cast<size_t>(kHeads) * Tm * kHd,
+                                  [&](int j) { return static_cast<size_t>(j) * kHd; }, Tm, vst, lane);
+          } else {
+            const __nv_bfloat16* kb = A.crosskv + static_cast<size_t>(st->row0[i]) * A.crosskv_ld + l * 2 * D + head * kHd;
+            const size_t ldk = A.crosskv_ld;
+            o = attend_warp<true>(qloc + i * DC + hl * kHd, kb, kb + D, [&](int j) { return j * ldk; }, Tm, vst, lane);
+          }
         }
         const float on = __shfl_down_sync(0xffffffffu, o, 1);
         if ((lane & 1) == 0) {
@@ -868,6 +879,35 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
   csync();                                          // no CTA may exit while peers can still write its smem
 }
 
+// ---------------------------------------------------------------- cross K/V relayout
+// src: the cross-K/V GEMM output [M, ld = layers*2*256] (token-major).  dst: per line the block
+// [layer][K|V][head][t][32]; one CTA moves one token row (ld/8 16-byte chunks).
+__global__ void __launch_bounds__(256)
+crosskv_headmajor_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int ld, const int* __restrict__ mem_row0,
+                         const int* __restrict__ mem_len, int T_uniform) {
+  const int b = blockIdx.y, t = blockIdx.x;
+  const int T = mem_len ? mem_len[b] : T_uniform;
+  if (t >= T) return;
+  const size_t row0 = mem_row0 ? static_cast<size_t>(mem_row0[b]) : static_cast<size_t>(b) * T_uniform;
+  const int chunks = ld / 8;                         // 16-byte chunks per row
+  const uint4* s_row = src + (row0 + t) * chunks;
+  uint4* d_line = dst + row0 * chunks;
+  for (int c = threadIdx.x; c < chunks; c += blockDim.x) {
+    const int col = c * 8, sec = col >> 8, head = (col & 255) >> 5, d0 = col & 31;
+    d_line[((static_cast<size_t>(sec) * kHeads + head) * T + t) * 4 + (d0 >> 3)] = __ldg(s_row + c);
+  }
+}
+
+int crosskv_headmajor(const __nv_bfloat16* src, __nv_bfloat16* dst, int ld, const int* mem_row0, const int* mem_len,
+                      int T_uniform, int max_T, int n_lines, cudaStream_t stream) {
+  KIRI_REQUIRE(ld % 256 == 0, "crosskv_headmajor: row length %d must be a multiple of 256", ld);
+  if (n_lines == 0) return 0;
+  crosskv_headmajor_kernel<<<dim3(max_T, n_lines), 192, 0, stream>>>(reinterpret_cast<const uint4*>(src),
+                                                                    reinterpret_cast<uint4*>(dst), ld, mem_row0, mem_len, T_uniform);
+  KIRI_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // ---------------------------------------------------------------- host side
 struct FusedPacked {
   void* blob = nullptr;
@@ -951,11 +991,11 @@ int fused_decoder_run(KiriHandle* h, const __nv_bfloat16* crosskv, int crosskv_l
                       int T, __nv_bfloat16* self_k, __nv_bfloat16* self_v, const int* len_est, const int* forced,
                       const int* line_perm, int B, int Lmax, const KiriDecodeParams* p, int* ids, int* n_out,
                       float* sum_logp, float* step_logp, float* step_prob, int* steps_max_dev, int cluster_size,
-                      cudaStream_t stream, const FusedBeam* beam) {
+                      cudaStream_t stream, const FusedBeam* beam, int kv_headmajor) {
   FusedPacked* fp = reinterpret_cast<FusedPacked*>(h->fused);
   KIRI_REQUIRE(fp, "fused decoder: handle was created without decoder weights");
   FusedArgs a = fp->args;
-  a.crosskv = crosskv; a.crosskv_ld = crosskv_ld; a.mem_row0 = mem_row0; a.mem_len = mem_len; a.T = T;
+  a.crosskv = crosskv; a.crosskv_ld = crosskv_ld; a.kv_hm = kv_headmajor; a.mem_row0 = mem_row0; a.mem_len = mem_len; a.T = T;
   a.self_k = self_k; a.self_v = self_v; a.len_est = len_est; a.forced = forced; a.line_perm = line_perm; a.B = B; a.Lmax = Lmax; a.p = *p;
   a.ids = ids; a.n_out = n_out; a.sum_logp = sum_logp; a.step_logp = step_logp; a.step_prob = step_prob;
   a.steps_max = steps_max_dev;

@@ -644,11 +644,19 @@ int launch_gemm_tc(const GemmLaunch& L_in, cudaStream_t stream) {
     KIRI_REQUIRE(L.Cin % 64 == 0, "gemm_tc: GEMM K=%d must be a multiple of 64", L.Cin);
     CPS = 1;
   } else {
-    if (L.OW % 128 == 0) { g.R = 1; g.SEG = 128; }
-    else if (L.OW % 64 == 0 && L.OH % 2 == 0) { g.R = 2; g.SEG = 64; }
-    else if (L.OW % 32 == 0 && L.OH % 4 == 0) { g.R = 4; g.SEG = 32; }
-    else if (L.OW % 32 == 0) { g.R = 1; g.SEG = 32; NSEG = 4; }
-    else { KIRI_REQUIRE(false, "gemm_tc: conv output width %d must be a multiple of 32", L.OW); }
+    // A tile is 128 output pixels = R rows x SEG columns fetched by ONE TMA box per K chunk.  Partial
+    // tiles (zero-filled by TMA, skipped by the epilogue per 32-row warp) are accepted up to 25 %
+    // padding because one big box beats four 32-pixel boxes (the NSEG = 4 form, no padding).
+    KIRI_REQUIRE(L.OW % 32 == 0, "gemm_tc: conv output width %d must be a multiple of 32", L.OW);
+    const int cand[3][2] = {{1, 128}, {2, 64}, {4, 32}};
+    double best = 1e9;
+    for (int i = 0; i < 3; ++i) {
+      const int R = cand[i][0], SEG = cand[i][1];
+      const double padded = static_cast<double>((L.OW + SEG - 1) / SEG * SEG) * ((L.OH + R - 1) / R * R);
+      const double waste = padded / (static_cast<double>(L.OW) * L.OH);
+      if (waste < best - 1e-9) { best = waste; g.R = R; g.SEG = SEG; }
+    }
+    if (best > 1.25) { g.R = 1; g.SEG = 32; NSEG = 4; }
     if (KC == 64) CPS = 1;
     else CPS = (NSEG == 1 && chunks <= 3) ? chunks : 1;
     KIRI_REQUIRE(L.epi == EPI_BIAS_SILU_BF16, "gemm_tc: conv path is built with the SiLU epilogue only");

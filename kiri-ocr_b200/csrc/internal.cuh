@@ -30,7 +30,10 @@ int fused_decoder_run(KiriHandle* h, const __nv_bfloat16* crosskv, int crosskv_l
                       int T, __nv_bfloat16* self_k, __nv_bfloat16* self_v, const int* len_est, const int* forced,
                       const int* line_perm, int B, int Lmax, const KiriDecodeParams* p, int* ids, int* n_out,
                       float* sum_logp, float* step_logp, float* step_prob, int* steps_max_dev, int cluster_size,
-                      cudaStream_t stream, const FusedBeam* beam = nullptr);
+                      cudaStream_t stream, const FusedBeam* beam = nullptr, int kv_headmajor = 0);
+// token-major cross K/V [M, ld] -> per-line head-major blocks [layer][K|V][head][t][32]
+int crosskv_headmajor(const __nv_bfloat16* src, __nv_bfloat16* dst, int ld, const int* mem_row0, const int* mem_len,
+                      int T_uniform, int max_T, int n_lines, cudaStream_t stream);
 }  // namespace kiri
 
 namespace kiri {

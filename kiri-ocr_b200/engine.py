@@ -284,7 +284,7 @@ class BatchedRecognizer:
         return out
 
     def decode_greedy_multi(self, mem_bf16: torch.Tensor, mem_row0: torch.Tensor, mem_len: torch.Tensor,
-                            len_est: torch.Tensor, Lmax: int, select_raw: bool = False,
+                            len_est: torch.Tensor, Lmax: int, max_T: int, select_raw: bool = False,
                             forced: Optional[torch.Tensor] = None, want_steps: bool = False, out=None):
         """One persistent decode over every line of every group (concatenated token stream)."""
         p = self.decode_params(select_raw)
@@ -302,7 +302,8 @@ class BatchedRecognizer:
             slp = torch.zeros((B, Lmax), dtype=torch.float32, device=self.device) if want_steps else None
             spr = torch.zeros((B, Lmax), dtype=torch.float32, device=self.device) if want_steps else None
         _lib.check(self.lib.kiri_decode_greedy_multi(self.handle, mem_bf16.data_ptr(), M, mem_row0.data_ptr(),
-                                                     mem_len.data_ptr(), len_est.data_ptr(), perm.data_ptr(), B, Lmax, C.byref(p),
+                                                     mem_len.data_ptr(), max_T, len_est.data_ptr(), perm.data_ptr(), B, Lmax,
+                                                     C.byref(p),
                                                      ws.data_ptr(), need, ids.data_ptr(), n_out.data_ptr(),
                                                      sum_lp.data_ptr(), _lib.ptr(slp), _lib.ptr(spr), _lib.ptr(forced),
                                                      None, _lib.stream_ptr()), "kiri_decode_greedy_multi")
@@ -356,7 +357,7 @@ class BatchedRecognizer:
                                                C.byref(p), ws.data_ptr(), need, ids.data_ptr(), n_out.data_ptr(),
                                                sum_lp.data_ptr(), _lib.ptr(slp), _lib.ptr(spr), _lib.ptr(forced),
                                                C.byref(steps), poll_every, _lib.stream_ptr()), "kiri_decode_greedy")
-        self.launches += 2          # cross-K/V GEMM + the persistent decode kernel
+        self.launches += 3          # cross-K/V GEMM, head-major relayout, the persistent decode kernel
         return ids, n_out, sum_lp, slp, spr, steps.value
 
     # ------------------------------------------------------------------ device-resident stepping (bench)
@@ -419,7 +420,8 @@ class BatchedRecognizer:
         len_est = torch.cat([o[1] for o in outs]) if len(outs) > 1 else outs[0][1]
         conf = torch.cat([o[2] for o in outs]) if len(outs) > 1 else outs[0][2]
         Lmax = self.max_steps_bound(int(len_est.max().item()), prep["T_max"])
-        d_ids, n_out, sum_lp, _, _ = self.decode_greedy_multi(enc["mem_bf16"], prep["mem_row0"], prep["mem_len"], len_est, Lmax)
+        d_ids, n_out, sum_lp, _, _ = self.decode_greedy_multi(enc["mem_bf16"], prep["mem_row0"], prep["mem_len"], len_est, Lmax,
+                                                              prep["T_max"])
         return [(d_ids, n_out, sum_lp, conf)]
 
     def profile(self, fn):
@@ -543,7 +545,7 @@ class BatchedRecognizer:
         slp = ddec[LL + 2 * n_lines:2 * LL + 2 * n_lines].view(torch.float32).view(n_lines, Lmax)
         spr = ddec[2 * LL + 2 * n_lines:3 * LL + 2 * n_lines].view(torch.float32).view(n_lines, Lmax)
         self.decode_greedy_multi(enc["mem_bf16"], dmeta[r0o:r0o + n_lines], dmeta[mlo:mlo + n_lines], n_all, Lmax,
-                                 select_raw=streaming, out=(d_ids, n_out, sum_lp, slp, spr))
+                                 max(T for _, _, T in enc["rows"]), select_raw=streaming, out=(d_ids, n_out, sum_lp, slp, spr))
         hdec = self._pinned("_hdec", dec_words, torch.int32)
         hdec[:dec_words].copy_(ddec[:dec_words], non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -589,7 +591,7 @@ class BatchedRecognizer:
         blp = dout[5 * nb + nb * Lmax:5 * nb + 2 * nb * Lmax].view(torch.float32)
         perm = torch.argsort(len_est, descending=True, stable=True).to(torch.int32)
         _lib.check(self.lib.kiri_decode_beam_multi(self.handle, enc["mem_bf16"].data_ptr(), M, mem_row0.data_ptr(),
-                                                   mem_len.data_ptr(), len_est.data_ptr(), perm.data_ptr(), n_lines, Lmax,
+                                                   mem_len.data_ptr(), T_max, len_est.data_ptr(), perm.data_ptr(), n_lines, Lmax,
                                                    beam, float(cfg.BEAM_LENP), C.byref(p), ws.data_ptr(), need,
                                                    score.data_ptr(), blen.data_ptr(), bstate.data_ptr(), bids.data_ptr(),
                                                    blp.data_ptr(), _lib.stream_ptr()), "kiri_decode_beam_multi")

@@ -123,6 +123,9 @@ class BatchedRecognizer:
         self.handle = h
         # the engine runs on its own (capturable) stream; public calls fence it against the caller's stream
         self.stream = torch.cuda.Stream(device=self.device)
+        self._copy_stream = torch.cuda.Stream(device=self.device)     # uploads overlap the previous batch
+        self._slot = 0                                                # ping-pong staging slot of submit()
+        self._src_free = [None, None]
         self._ws: Optional[torch.Tensor] = None
         self._dws: Optional[torch.Tensor] = None
         self._build_tables()
@@ -437,9 +440,12 @@ class BatchedRecognizer:
 
     # ------------------------------------------------------------------ public API
     @torch.no_grad()
-    def recognize_packed(self, src: torch.Tensor, entries: np.ndarray, method: str = "ctc",
-                         streaming: bool = False) -> List[Optional[LineResult]]:
-        """``src``: uint8 buffer (pinned host or device) holding pages/crops; ``entries[n,4]`` =
+    def submit(self, src: torch.Tensor, entries: np.ndarray, method: str = "ctc", streaming: bool = False):
+        """Enqueue one batch (H2D of the source on the copy stream, preprocess, encoder, CTC greedy, async
+        D2H of the packed CTC results) and return a ticket without synchronising the host.  Two
+        tickets may be in flight: ``t2 = submit(...); r1 = collect(t1)`` overlaps batch i's host-side
+        string decoding and batch i+1's upload with the kernels of the other batch.
+        ``src``: uint8 buffer (pinned host or device) holding pages/crops; ``entries[n,4]`` =
         (byte offset, pitch, w, h) of every crop after the reference's clamp-pad."""
         if method not in ("ctc", "decoder", "beam"):
             raise ValueError("method must be 'ctc', 'decoder' or 'beam'")
@@ -447,14 +453,22 @@ class BatchedRecognizer:
         if caller != self.stream:
             self.stream.wait_stream(caller)
             with torch.cuda.stream(self.stream):
-                out = self.recognize_packed(src, entries, method, streaming)
-            caller.wait_stream(self.stream)
-            return out
+                return self.submit(src, entries, method, streaming)
         n = len(entries)
-        results: List[Optional[LineResult]] = [None] * n
+        tk = {"method": method, "streaming": streaming, "n": n}
         if n == 0:
-            return results
-        src_dev = src if src.is_cuda else src.to(self.device, non_blocking=True)
+            return tk
+        self._slot ^= 1
+        sl = f"_{self._slot}"
+        if src.is_cuda:
+            src_dev = src
+        else:
+            # upload on the copy stream: it overlaps the kernels of the batch submitted before
+            src_dev = self._device("_src" + sl, src.numel(), torch.uint8)
+            if self._src_free[self._slot] is not None:              # the preprocess launch that last read this slot
+                self._copy_stream.wait_event(self._src_free[self._slot])
+            with torch.cuda.stream(self._copy_stream):
+                src_dev[:src.numel()].copy_(src, non_blocking=True)
         groups = list(self.plan(entries).items())
         IMG_H, Cp = self.cfg.IMG_H, self.pw.Cp
         n_lines = sum(len(g[1][0]) for g in groups)
@@ -462,14 +476,12 @@ class BatchedRecognizer:
         # ---- ONE pinned staging buffer -> ONE H2D copy for every descriptor / per-line table
         desc_bytes = sum(g[1][1].nbytes for g in groups)
         meta_words = desc_bytes // 4 + 3 * n_lines                       # descs | kv_len | mem_row0 | mem_len
-        hmeta = self._pinned("_hmeta", meta_words, torch.int32)
+        hmeta = self._pinned("_hmeta" + sl, meta_words, torch.int32)
         hm = hmeta.numpy()
-        off, line0, row0 = 0, 0, 0
-        desc_off = []
+        off, line0, row0, p0 = 0, 0, 0, 0
         kvo, r0o, mlo = desc_bytes // 4, desc_bytes // 4 + n_lines, desc_bytes // 4 + 2 * n_lines
-        p0 = 0
         planes_list = []
-        planes_all = self._device("_planes", M * 4 * IMG_H, torch.uint8)
+        planes_all = self._device("_planes" + sl, M * 4 * IMG_H, torch.uint8)
         smem_max = n_strips_max = 0
         for Wb, (idx, descs, smem, n_strips) in groups:
             nb, T = descs.nbytes // 4, Wb // 4
@@ -485,40 +497,69 @@ class BatchedRecognizer:
             off += nb
             line0 += len(idx)
             row0 += len(idx) * T
-        dmeta = self._device("_dmeta", meta_words, torch.int32)
+        dmeta = self._device("_dmeta" + sl, meta_words, torch.int32)
         dmeta[:meta_words].copy_(hmeta[:meta_words], non_blocking=True)
+        if not src.is_cuda:
+            self.stream.wait_stream(self._copy_stream)
         # ---- ONE preprocess launch for every width group, one encoder pass over all groups
         _lib.check(self.lib.kiri_preprocess_pack(src_dev.data_ptr(), dmeta.data_ptr(), n_lines, IMG_H, smem_max, n_strips_max,
                                                  planes_all.data_ptr(), 0, _lib.stream_ptr()), "kiri_preprocess_pack")
         self.launches += 1
+        if not src.is_cuda:
+            self._src_free[self._slot] = torch.cuda.Event()
+            self._src_free[self._slot].record()
         kv_len = dmeta[kvo:kvo + n_lines] if self.width_mode == "masked" else None
         enc = self.encode_multi(planes_list, kv_len=kv_len)
-        # ---- CTC greedy per group into ONE packed result buffer: ids[M] | n_ids[L] | conf[L] | frames
+        # ---- CTC greedy into ONE packed result buffer: ids[M] | n_ids[L] | conf[L] | frames
         want_frames = streaming and method == "ctc"
         res_words = M + 2 * n_lines + (2 * M if want_frames else 0)
-        dres = self._device("_dres", res_words, torch.int32)
+        dres = self._device("_dres" + sl, res_words, torch.int32)
         ids_all, n_all = dres[:M], dres[M:M + n_lines]
         conf_all = dres[M + n_lines:M + 2 * n_lines].view(torch.float32)
         fid_all = dres[M + 2 * n_lines:2 * M + 2 * n_lines] if want_frames else None
         fpr_all = dres[2 * M + 2 * n_lines:3 * M + 2 * n_lines].view(torch.float32) if want_frames else None
+        T_max = max(T for _, _, T in enc["rows"])
         _lib.check(self.lib.kiri_ctc_greedy_multi(enc["logits"].data_ptr(), _lib.DTYPE_F32, n_lines,
-                                                  dmeta[r0o:].data_ptr(), dmeta[mlo:].data_ptr(),
-                                                  max(T for _, _, T in enc["rows"]), self.pw.C, Cp, ids_all.data_ptr(),
-                                                  n_all.data_ptr(), conf_all.data_ptr(),
+                                                  dmeta[r0o:].data_ptr(), dmeta[mlo:].data_ptr(), T_max, self.pw.C, Cp,
+                                                  ids_all.data_ptr(), n_all.data_ptr(), conf_all.data_ptr(),
                                                   _lib.ptr(fid_all), _lib.ptr(fpr_all), _lib.stream_ptr()),
                    "kiri_ctc_greedy_multi")
         self.launches += 1
-        order = np.concatenate([g[1][0] for g in groups])          # line index of every concatenated slot
-        hres = self._pinned("_hres", res_words, torch.int32)
+        hres = self._pinned("_hres" + sl, res_words, torch.int32)
         hres[:res_words].copy_(dres[:res_words], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        hr = hres.numpy()[:res_words].copy()                        # the pinned buffer is reused by the next call
+        done = torch.cuda.Event()
+        done.record()
+        tk.update(done=done, hres=hres, res_words=res_words, M=M, n_lines=n_lines, rows=enc["rows"], T_max=T_max,
+                  order=np.concatenate([g[1][0] for g in groups]),     # line index of every concatenated slot
+                  want_frames=want_frames, enc=enc, n_all=n_all, mem_row0=dmeta[r0o:r0o + n_lines],
+                  mem_len=dmeta[mlo:mlo + n_lines], keep=(src_dev, planes_all, dmeta, dres), sl=sl)
+        return tk
+
+    @torch.no_grad()
+    def collect(self, tk) -> List[Optional[LineResult]]:
+        """Wait for a ticket; "ctc" is finished on the host, "decoder" / "beam" run their decode stage
+        now (they need the CTC length estimates on the host to bound the loop)."""
+        n = tk["n"]
+        results: List[Optional[LineResult]] = [None] * n
+        if n == 0:
+            return results
+        caller = torch.cuda.current_stream(self.device)
+        if caller != self.stream:
+            with torch.cuda.stream(self.stream):
+                out = self.collect(tk)
+            caller.wait_stream(self.stream)
+            return out
+        method, streaming = tk["method"], tk["streaming"]
+        tk["done"].synchronize()
+        res_words, M, n_lines, order, enc = tk["res_words"], tk["M"], tk["n_lines"], tk["order"], tk["enc"]
+        hr = tk["hres"].numpy()[:res_words].copy()                  # the pinned buffer is reused two batches later
         n_h = hr[M:M + n_lines]
         c_h = hr[M + n_lines:M + 2 * n_lines].view(np.float32)
         if method == "ctc":
+            want_frames = tk["want_frames"]
             tab = self._ctc_table
             pos = 0
-            for (r0, B, T) in enc["rows"]:
+            for (r0, B, T) in tk["rows"]:
                 ids_h = hr[r0:r0 + B * T].reshape(B, T)
                 f_h = hr[M + 2 * n_lines + r0:M + 2 * n_lines + r0 + B * T].reshape(B, T) if want_frames else None
                 p_h = hr[2 * M + 2 * n_lines + r0:2 * M + 2 * n_lines + r0 + B * T].view(np.float32).reshape(B, T) if want_frames else None
@@ -533,10 +574,10 @@ class BatchedRecognizer:
             return results
         len_h = n_h                                                  # length estimates bound the loop
         if method == "beam":
-            return self._beam_finish(enc, dmeta[r0o:r0o + n_lines], dmeta[mlo:mlo + n_lines], n_all, len_h, c_h, order,
-                                     results)
+            return self._beam_finish(enc, tk["mem_row0"], tk["mem_len"], tk["n_all"], len_h, c_h, order, results)
         # ---- greedy attention decoder over all lines at once
-        Lmax = self.max_steps_bound(int(len_h.max()), max(T for _, _, T in enc["rows"]))
+        T_max = tk["T_max"]
+        Lmax = self.max_steps_bound(int(len_h.max()), T_max)
         dec_words = n_lines * Lmax * 3 + 2 * n_lines
         ddec = self._device("_ddec", dec_words, torch.int32)
         LL = n_lines * Lmax
@@ -544,8 +585,8 @@ class BatchedRecognizer:
         sum_lp = ddec[LL + n_lines:LL + 2 * n_lines].view(torch.float32)
         slp = ddec[LL + 2 * n_lines:2 * LL + 2 * n_lines].view(torch.float32).view(n_lines, Lmax)
         spr = ddec[2 * LL + 2 * n_lines:3 * LL + 2 * n_lines].view(torch.float32).view(n_lines, Lmax)
-        self.decode_greedy_multi(enc["mem_bf16"], dmeta[r0o:r0o + n_lines], dmeta[mlo:mlo + n_lines], n_all, Lmax,
-                                 max(T for _, _, T in enc["rows"]), select_raw=streaming, out=(d_ids, n_out, sum_lp, slp, spr))
+        self.decode_greedy_multi(enc["mem_bf16"], tk["mem_row0"], tk["mem_len"], tk["n_all"], Lmax, T_max,
+                                 select_raw=streaming, out=(d_ids, n_out, sum_lp, slp, spr))
         hdec = self._pinned("_hdec", dec_words, torch.int32)
         hdec[:dec_words].copy_(ddec[:dec_words], non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -565,6 +606,11 @@ class BatchedRecognizer:
                                      float(c_h[j]), row, step_logp=slp_h[j, :nj], step_prob=spr_h[j, :nj],
                                      len_est=int(len_h[j]))
         return results
+
+    def recognize_packed(self, src: torch.Tensor, entries: np.ndarray, method: str = "ctc",
+                         streaming: bool = False) -> List[Optional[LineResult]]:
+        """One synchronous batch = ``collect(submit(...))``."""
+        return self.collect(self.submit(src, entries, method, streaming))
 
     def _beam_finish(self, enc, mem_row0, mem_len, len_est, len_h, ctc_conf_h, order, results):
         """decode_method="beam" (model.py:390-600 with cfg.BEAM > 1): device beam search + device CTC

@@ -47,8 +47,9 @@ STAGE_FLOPS_PER_LINE = {           # algorithmic (unpadded) FLOPs of one line at
     "attention": lambda Wb: 4 * 2.0 * 2 * 256 * (Wb // 4) ** 2,
     "ctc_head": lambda Wb: 2.0 * (Wb // 4) * 204 * 256,
 }
-STAGE_BYTES_PER_LINE = {           # algorithmic bytes for the CUDA-core / HBM-bound stages
+STAGE_BYTES_PER_LINE = {           # algorithmic bytes for the CUDA-core / HBM-bound stages (SURVEY.md section 8d)
     "conv1": lambda Wb: 48 * Wb + 48 * Wb * 48 * 2,
+    "ctc_greedy": lambda Wb: (Wb // 4) * 204 * 4 + 4 * (Wb // 4) + 12,      # fp32 logits in, ids + stats out
 }
 
 
@@ -310,6 +311,10 @@ def run_ours(args):
             fl = sum(STAGE_FLOPS_PER_LINE[name](wb) * n for wb, n in widths.items())
             ent_["tflops"] = fl / (sms / reps / 1e3) / 1e12
             ent_["frac_of_peak"] = ent_["tflops"] / pk["bf16_tflops_sustained"]
+        if name == "preprocess":
+            by = float(sum(c.size for c in crops) + sum(48 * wb * n for wb, n in widths.items()))   # h*w in, 48*Wb u8 out
+            ent_["gbs"] = by / (sms / reps / 1e3) / 1e9
+            ent_["frac_of_peak"] = ent_["gbs"] / pk["hbm_gbs"]
         if name in STAGE_BYTES_PER_LINE:
             by = sum(STAGE_BYTES_PER_LINE[name](wb) * n for wb, n in widths.items())
             ent_["gbs"] = by / (sms / reps / 1e3) / 1e9
@@ -318,9 +323,17 @@ def run_ours(args):
     top = max((n for n in stages if n in STAGE_FLOPS_PER_LINE), key=lambda n: stages[n]["ms_per_step"])
     st = stages[top]
     flops_launch = sum(STAGE_FLOPS_PER_LINE[top](wb) * n for wb, n in widths.items()) / max(1, st["launches_per_step"])
+    traffic, traffic_note = None, None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+        if top in tr:
+            traffic, traffic_note = tr[top]["dram_bytes_per_launch"], tr[top]["note"]
+    except Exception:
+        pass
     roof = {"bound": "tensor", "kernel": f"gemm_tc_kernel ({top})", "achieved": st["tflops"],
             "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": st["tflops"] / pk["bf16_tflops_sustained"],
-            "traffic": None, "peak_source": f"{pk['src']} sustained bf16 (kernel timed inside the step)",
+            "traffic": traffic, "traffic_note": traffic_note,
+            "peak_source": f"{pk['src']} sustained bf16 (kernel timed inside the step)",
             "flops_per_launch": flops_launch, "ms_per_launch": st["ms_per_step"] / max(1, st["launches_per_step"]),
             "share_of_step": st["share"]}
     whole = sum(flops_per_line(wb) * n for wb, n in widths.items()) * world

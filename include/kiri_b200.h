@@ -49,7 +49,7 @@ int kiri_device_ok(void);
  * numbers).  kiri_profile_begin() starts recording and returns the number of stages;
  * kiri_profile_end() synchronises the device and returns, per stage, the summed milliseconds and
  * the number of timed intervals.  Stage order: conv1, conv2, conv3, conv4, pool_ln, qkv, attention,
- * out_proj, ff1, ff2, ln_final, ctc_head, dec_crosskv, dec_step. */
+ * out_proj, ff1, ff2, ln_final, ctc_head, dec_crosskv, dec_step, preprocess, ctc_greedy. */
 int kiri_profile_begin(void);
 int kiri_profile_end(double* ms_by_stage_host, int* count_by_stage_host, int n);
 
@@ -73,9 +73,13 @@ int kiri_preprocess_smem_bytes(int w, int h, int nw, int img_h, int Wb, int stri
 /* planes_u8: uint8 buffer holding every crop's [img_h, Wb] plane at its out_offset (all width
  * groups of a batch go in ONE launch); norm_bf16 (nullable): same offsets, (v/255-0.5)/0.5.
  * One CTA resamples one strip of strip_w output columns of one crop; max_strips >= the largest
- * ceil(min(nw, Wb) / strip_w) over the crops (grid = n_crops x max_strips). */
+ * ceil(min(nw, Wb) / strip_w) over the crops (grid = n_crops x max_strips).  smem_bytes >= the
+ * largest kiri_preprocess_smem_bytes() of the crops; anything above lets a CTA stage more source
+ * rows per phase (all of them for ordinary lines).  A first small launch sums every crop for the
+ * reference's dark-background inversion test (core.py:524). */
 int kiri_preprocess_pack(const uint8_t* src, const KiriCropDesc* descs, int n_crops, int img_h,
-                         int smem_bytes, int max_strips, uint8_t* planes_u8, void* norm_bf16, cudaStream_t stream);
+                         int smem_bytes, int max_strips, uint8_t* planes_u8, void* norm_bf16,
+                         unsigned long long* crop_sums_scratch /* device, n_crops entries */, cudaStream_t stream);
 
 /* ---------------------------------------------------------------- K2: stem layer 1
  * Replaces ConvStem.net[0:3] (kiri_ocr/model.py:215-217).  w_host[48*9], b_host[48]: BN-folded

@@ -72,7 +72,7 @@ _SIGS = {
     "kiri_profile_begin": (C.c_int, []),
     "kiri_profile_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]),
     "kiri_preprocess_smem_bytes": (C.c_int, [C.c_int] * 6),
-    "kiri_preprocess_pack": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
+    "kiri_preprocess_pack": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]),
     "kiri_conv1": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]),
     "kiri_conv3x3_bf16": (C.c_int, [vp, vp, vp] + [C.c_int] * 7 + [vp, vp]),
     "kiri_gemm_bf16": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),
@@ -154,7 +154,7 @@ def require_device() -> None:
 
 
 PROFILE_STAGES = ("conv1", "conv2", "conv3", "conv4", "pool_ln", "qkv", "attention", "out_proj", "ff1", "ff2",
-                  "ln_final", "ctc_head", "dec_crosskv", "dec_step")
+                  "ln_final", "ctc_head", "dec_crosskv", "dec_step", "preprocess", "ctc_greedy")
 
 
 def ptr(t) -> int:

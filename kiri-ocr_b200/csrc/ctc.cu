@@ -10,8 +10,7 @@
 // coalesced loads, reduce (max, first arg-max) and sum(exp) with shuffles.  Collapse is a
 // ballot/popcount compaction over the T frame ids.  HBM-bound: T*C*sizeof(logit) bytes in,
 // ~4*T bytes out per line.
-#include "common.cuh"
-#include "kiri_b200.h"
+#include "internal.cuh"
 
 namespace kiri {
 
@@ -22,6 +21,72 @@ template <typename T> __device__ __forceinline__ float ld_logit(const T* p);
 template <> __device__ __forceinline__ float ld_logit<float>(const float* p) { return __ldg(p); }
 template <> __device__ __forceinline__ float ld_logit<__nv_bfloat16>(const __nv_bfloat16* p) {
   return __bfloat162float(*p);
+}
+
+// one frame row held by a warp: lane l owns float4 chunks l and l+32 (C <= 256 classes), or scalar
+// strided elements for other element types / unaligned rows
+// 16-byte loads, the whole row in a warp's registers: ONE pass over the logits (the scalar version
+// read every row twice and issued 4-byte loads)
+__device__ __forceinline__ void ctc_load_row(const float* __restrict__ row, int C, int lane, float (&v)[8]) {
+  const float4* r4 = reinterpret_cast<const float4*>(row);
+  const int nch = C >> 2;                                      // full float4 chunks
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int ch = lane + 32 * h;
+    float4 t = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    if (ch < nch) t = __ldg(r4 + ch);
+    else if (ch == nch && (C & 3)) {                           // ragged tail (C not a multiple of 4)
+      const float* rs = row + 4 * ch;
+      const int nv = C & 3;
+      t.x = __ldg(rs); if (nv > 1) t.y = __ldg(rs + 1); if (nv > 2) t.z = __ldg(rs + 2);
+    }
+    v[4 * h] = t.x; v[4 * h + 1] = t.y; v[4 * h + 2] = t.z; v[4 * h + 3] = t.w;
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void ctc_frame(const T* __restrict__ row, int C, bool vec, int lane, int& am_out, float& p_out,
+                                          const float* v) {
+  if (vec) {
+    float m = -INFINITY;
+    int am = 0x7fffffff;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float x = v[4 * h + k];
+        if (x > m) { m = x; am = 4 * (lane + 32 * h) + k; }     // ascending class index per lane: first max wins
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, m, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, am, o);
+      if (om > m || (om == m && oa < am)) { m = om; am = oa; }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += __expf(v[k] - m);          // exp(-inf) = 0 for the padding
+    s = warp_sum(s);
+    am_out = am; p_out = 1.0f / s;
+    return;
+  }
+  // scalar path: max and FIRST arg-max (torch.argmax tie rule), then sum exp(x - max)
+  float m = -INFINITY;
+  int am = 0x7fffffff;
+  for (int c = lane; c < C; c += 32) {
+    const float x = ld_logit<T>(row + c);
+    if (x > m) { m = x; am = c; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, am, o);
+    if (om > m || (om == m && oa < am)) { m = om; am = oa; }
+  }
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += __expf(ld_logit<T>(row + c) - m);
+  s = warp_sum(s);
+  am_out = am; p_out = 1.0f / s;
 }
 
 template <typename T>
@@ -40,33 +105,37 @@ ctc_greedy_kernel(const T* __restrict__ logits, int Tn, int C, int ld, int* __re
   const size_t r0 = row0 ? static_cast<size_t>(row0[line]) : static_cast<size_t>(line) * Tn;
   if (lens) Tn = lens[line];
   const T* base = logits + r0 * ld;
+  const bool vec = (sizeof(T) == 4) && (C <= 256) && ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
 
   float psum = 0.f;
-  for (int t = warp; t < Tn; t += nwarps) {
-    const T* row = base + static_cast<size_t>(t) * ld;
-    // pass 1: max and FIRST arg-max (torch.argmax tie rule)
-    float m = -INFINITY;
-    int am = 0x7fffffff;
-    for (int c = lane; c < C; c += 32) {
-      const float v = ld_logit<T>(row + c);
-      if (v > m) { m = v; am = c; }
+  // four frames per iteration: their loads are independent, which quadruples the bytes in flight per warp
+  constexpr int kFr = 4;
+  for (int t = warp; t < Tn; t += kFr * nwarps) {
+    int am[kFr];
+    float pr[kFr];
+    float vals[kFr][8];                               // all loads of the iteration are issued before any reduction
+#pragma unroll
+    for (int f = 0; f < kFr; ++f) {
+      am[f] = 0; pr[f] = 0.f;
+      const int tf = t + f * nwarps;
+      if (vec && tf < Tn) ctc_load_row(reinterpret_cast<const float*>(base + static_cast<size_t>(tf) * ld), C, lane, vals[f]);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float om = __shfl_xor_sync(0xffffffffu, m, o);
-      const int oa = __shfl_xor_sync(0xffffffffu, am, o);
-      if (om > m || (om == m && oa < am)) { m = om; am = oa; }
+    for (int f = 0; f < kFr; ++f) {
+      const int tf = t + f * nwarps;
+      if (tf < Tn) ctc_frame<T>(base + static_cast<size_t>(tf) * ld, C, vec, lane, am[f], pr[f], vals[f]);
     }
-    // pass 2 (row is L1-resident): sum exp(x - max); max prob = 1 / sum
-    float s = 0.f;
-    for (int c = lane; c < C; c += 32) s += __expf(ld_logit<T>(row + c) - m);
-    s = warp_sum(s);
-    const float p = 1.0f / s;
     if (lane == 0) {
-      s_id[t] = am;
-      psum += p;
-      if (frame_ids) frame_ids[r0 + t] = am;
-      if (frame_prob) frame_prob[r0 + t] = p;
+#pragma unroll
+      for (int f = 0; f < kFr; ++f) {
+        const int tf = t + f * nwarps;
+        if (tf < Tn) {
+          s_id[tf] = am[f];
+          psum += pr[f];
+          if (frame_ids) frame_ids[r0 + tf] = am[f];
+          if (frame_prob) frame_prob[r0 + tf] = pr[f];
+        }
+      }
     }
   }
   if (lane == 0) s_psum[warp] = psum;
@@ -131,6 +200,7 @@ extern "C" int kiri_ctc_greedy_multi(const void* logits, int logits_dtype, int n
   KIRI_REQUIRE(max_T > 0 && max_T <= kCtcMaxT && C > 0 && ld >= C, "kiri_ctc_greedy_multi: bad shape T=%d C=%d ld=%d", max_T, C, ld);
   KIRI_REQUIRE(logits_dtype == KIRI_DTYPE_F32, "kiri_ctc_greedy_multi: fp32 logits only");
   if (n_lines == 0) return 0;
+  ProfScope ps(PS_CTC_GREEDY, stream);
   KIRI_CHECK_CUDA(launch_pdl(ctc_greedy_kernel<float>, dim3(n_lines), dim3(kCtcThreads), 0, stream,
                              reinterpret_cast<const float*>(logits), max_T, C, ld, ids, n_ids, conf, frame_ids, frame_prob,
                              row0, len));

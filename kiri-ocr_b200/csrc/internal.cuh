@@ -41,7 +41,7 @@ namespace kiri {
 // launching stream around each stage while profiling is on.
 enum ProfStage : int {
   PS_CONV1 = 0, PS_CONV2, PS_CONV3, PS_CONV4, PS_POOL_LN, PS_QKV, PS_ATTN, PS_OUTPROJ, PS_FF1, PS_FF2,
-  PS_LN_FINAL, PS_CTC_HEAD, PS_DEC_CROSSKV, PS_DEC_STEP, PS_COUNT
+  PS_LN_FINAL, PS_CTC_HEAD, PS_DEC_CROSSKV, PS_DEC_STEP, PS_PREPROCESS, PS_CTC_GREEDY, PS_COUNT
 };
 void prof_begin(int stage, cudaStream_t s);
 void prof_end(int stage, cudaStream_t s);

@@ -13,8 +13,7 @@
 // explicitly rounded operations (no FMA contraction), which reproduces the host bit for bit.
 // Horizontal pass first (source rows staged through shared memory with 32-bit loads), the
 // intermediate lives in shared memory, then the vertical pass writes coalesced rows.
-#include "common.cuh"
-#include "kiri_b200.h"
+#include "internal.cuh"
 
 namespace kiri {
 
@@ -70,12 +69,45 @@ __device__ __forceinline__ uint8_t clip8(int acc) {
   return static_cast<uint8_t>(acc < 0 ? 0 : (acc > 255 ? 255 : acc));
 }
 
+// Pass 0 as its own launch: sum of every crop -> invert decision (core.py:524).  grid = (crops, 8):
+// block y takes rows y, y+8, ...; one 64-bit atomic per warp.  Each source byte is read once here
+// and once by the strip that resamples it (the old per-strip pass re-read the whole crop per strip).
+__global__ void __launch_bounds__(kPreThreads)
+crop_sum_kernel(const uint8_t* __restrict__ src, const KiriCropDesc* __restrict__ descs,
+                unsigned long long* __restrict__ sums) {
+  pdl_trigger();
+  pdl_wait();
+  const KiriCropDesc d = descs[blockIdx.x];
+  const uint8_t* crop = src + d.src_offset;
+  const int w = d.w, h = d.h;
+  unsigned int local = 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = kPreThreads >> 5;
+  for (int r = blockIdx.y * nwarps + warp; r < h; r += gridDim.y * nwarps) {
+    const uint8_t* row = crop + static_cast<size_t>(r) * d.pitch;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(row);
+    const int head = static_cast<int>(a & 3);          // bytes before `row` in its first word
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(a - head);
+    const int nwords = (head + w + 3) >> 2;
+    for (int i = lane; i < nwords; i += 32) {
+      uint32_t v = __ldg(wp + i);
+      const int lo = i * 4 - head;                     // crop column of byte 0 of this word
+      uint32_t mask = 0xffffffffu;
+      if (lo < 0) mask &= 0xffffffffu << (8 * (-lo));
+      if (lo + 4 > w) mask &= 0xffffffffu >> (8 * (lo + 4 - w));
+      local = __dp4a(v & mask, 0x01010101u, local);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if (lane == 0 && local) atomicAdd(&sums[blockIdx.x], static_cast<unsigned long long>(local));
+}
+
 __global__ void __launch_bounds__(kPreThreads)
 preprocess_pack_kernel(const uint8_t* __restrict__ src, const KiriCropDesc* __restrict__ descs,
                        int img_h, uint8_t* __restrict__ planes,
-                       __nv_bfloat16* __restrict__ norm_out, int smem_bytes) {
+                       __nv_bfloat16* __restrict__ norm_out, int smem_bytes,
+                       const unsigned long long* __restrict__ sums) {
   extern __shared__ __align__(16) uint8_t sm[];
-  __shared__ unsigned long long s_sum;
   pdl_trigger();
   pdl_wait();                                       // descriptors / source may come from a copy kernel
   const KiriCropDesc d = descs[blockIdx.x];
@@ -88,33 +120,8 @@ preprocess_pack_kernel(const uint8_t* __restrict__ src, const KiriCropDesc* __re
   uint8_t* plane = planes + d.out_offset;                       // the crop's [img_h, Wb] plane
   __nv_bfloat16* nplane = norm_out ? norm_out + d.out_offset : nullptr;
 
-  // ---------------- pass 0: sum of the crop -> invert decision (core.py:524) ----------------
-  if (tid == 0) s_sum = 0ull;
-  __syncthreads();
-  {
-    unsigned int local = 0;
-    const int warp = tid >> 5, lane = tid & 31, nwarps = kPreThreads >> 5;
-    for (int r = warp; r < h; r += nwarps) {
-      const uint8_t* row = crop + static_cast<size_t>(r) * d.pitch;
-      const uintptr_t a = reinterpret_cast<uintptr_t>(row);
-      const int head = static_cast<int>(a & 3);          // bytes before `row` in its first word
-      const uint32_t* wp = reinterpret_cast<const uint32_t*>(a - head);
-      const int nwords = (head + w + 3) >> 2;
-      for (int i = lane; i < nwords; i += 32) {
-        uint32_t v = __ldg(wp + i);
-        const int lo = i * 4 - head;                     // crop column of byte 0 of this word
-        uint32_t mask = 0xffffffffu;
-        if (lo < 0) mask &= 0xffffffffu << (8 * (-lo));
-        if (lo + 4 > w) mask &= 0xffffffffu >> (8 * (lo + 4 - w));
-        local = __dp4a(v & mask, 0x01010101u, local);
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
-    if (lane == 0) atomicAdd(&s_sum, static_cast<unsigned long long>(local));
-  }
-  __syncthreads();
-  const bool invert = s_sum < 127ull * static_cast<unsigned long long>(w) * h;
+  // invert decision (core.py:524) from the crop sum of crop_sum_kernel
+  const bool invert = sums[blockIdx.x] < 127ull * static_cast<unsigned long long>(w) * h;
   const uint32_t inv_mask = invert ? 0xffffffffu : 0u;
 
   // ---------------- coefficient geometry ----------------
@@ -133,8 +140,7 @@ preprocess_pack_kernel(const uint8_t* __restrict__ src, const KiriCropDesc* __re
   int* kh = reinterpret_cast<int*>(sm + off);      off += ((Ws * ksize_h * 4 + 15) & ~15);
   int* xmin = reinterpret_cast<int*>(sm + off);    off += ((Ws * 4 + 15) & ~15);
   uint8_t* inter = sm + off;                       off += ((h * Ws + 15) & ~15);
-  uint8_t* srow = sm + off;                        // kRowBlock rows of staged source
-  const int srow_cap = (smem_bytes - off) / kRowBlock & ~15;
+  uint8_t* srow = sm + off;                        // staged source rows: as many as the budget holds
 
   if (do_v) {
     for (int y = tid; y < img_h; y += kPreThreads) ymin[y] = fill_coefs(y, h, img_h, ksize_v, kv + y * ksize_v, 1);
@@ -154,62 +160,85 @@ preprocess_pack_kernel(const uint8_t* __restrict__ src, const KiriCropDesc* __re
     const int sx0 = xmin[0];                                  // first source column needed
     const int sx1 = do_h ? (xmin[cw - 1] + ksize_h) : (c0 + cw);
     const int span = (sx1 < w ? sx1 : w) - sx0;               // source columns to stage
+    // all rows of the strip in ONE staging phase when they fit (typical lines: 3 barriers per CTA
+    // instead of 2 per 8 rows, and every load of the strip in flight at once)
+    const int srow_cap = (span + 4 + 3 + 15) & ~15;           // bytes per staged row (4-byte alignment head + tail)
+    int rows_blk = (smem_bytes - off) / srow_cap;
+    if (rows_blk > h) rows_blk = h;
+    if (rows_blk < 1) rows_blk = 1;
 
-    for (int r0 = 0; r0 < h; r0 += kRowBlock) {
-      const int nr = (h - r0) < kRowBlock ? (h - r0) : kRowBlock;
+    for (int r0 = 0; r0 < h; r0 += rows_blk) {
+      const int nr = (h - r0) < rows_blk ? (h - r0) : rows_blk;
       // stage rows r0..r0+nr, columns sx0..sx0+span, inverted if needed, with 32-bit loads
-      for (int rr = 0; rr < nr; ++rr) {
-        const uint8_t* row = crop + static_cast<size_t>(r0 + rr) * d.pitch + sx0;
-        const uintptr_t a = reinterpret_cast<uintptr_t>(row);
-        const int head = static_cast<int>(a & 3);
-        const uint32_t* wp = reinterpret_cast<const uint32_t*>(a - head);
-        const int nwords = (head + span + 3) >> 2;
-        uint32_t* dst = reinterpret_cast<uint32_t*>(srow + rr * srow_cap);
-        for (int i = tid; i < nwords; i += kPreThreads) dst[i] = __ldg(wp + i) ^ inv_mask;
+      {
+        const int wpr = srow_cap >> 2;                          // word slots per staged row
+        for (int idx = tid; idx < nr * wpr; idx += kPreThreads) {
+          const int rr = idx / wpr, i = idx - rr * wpr;
+          const uint8_t* row = crop + static_cast<size_t>(r0 + rr) * d.pitch + sx0;
+          const uintptr_t a = reinterpret_cast<uintptr_t>(row);
+          const int head = static_cast<int>(a & 3);
+          if (i < ((head + span + 3) >> 2))
+            reinterpret_cast<uint32_t*>(srow + rr * srow_cap)[i] = __ldg(reinterpret_cast<const uint32_t*>(a - head) + i) ^ inv_mask;
+        }
       }
       __syncthreads();
-      // horizontal pass -> inter[r][x]
-      for (int idx = tid; idx < nr * cw; idx += kPreThreads) {
-        const int rr = idx / cw, x = idx - rr * cw;
-        const uint8_t* row = crop + static_cast<size_t>(r0 + rr) * d.pitch + sx0;
-        const int head = static_cast<int>(reinterpret_cast<uintptr_t>(row) & 3);
-        const uint8_t* s = srow + rr * srow_cap + head + (xmin[x] - sx0);
-        uint8_t o;
-        if (do_h) {
-          int acc = 1 << (kPrecisionBits - 1);
-          const int avail = w - xmin[x];                      // taps beyond the row carry weight 0
-          for (int k = 0; k < ksize_h; ++k) {
-            const int kk = kh[k * Ws + x];
-            if (k < avail) acc += static_cast<int>(s[k]) * kk;
+      // horizontal pass -> inter[r][x].  A thread owns ONE output column (x = tid mod 128) and walks
+      // the rows: xmin / tap count / up to 8 coefficients live in registers, no per-pixel division.
+      {
+        const int x = tid & 127, rg = tid >> 7;                // strips are <= 128 columns wide
+        if (x < cw) {
+          const int xm = xmin[x];
+          const int kmax = do_h ? (ksize_h < w - xm ? ksize_h : w - xm) : 1;   // taps beyond the row carry weight 0
+          int kc[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) kc[k] = (do_h && k < kmax) ? kh[k * Ws + x] : 0;
+          const uintptr_t a0 = reinterpret_cast<uintptr_t>(crop + sx0);
+          for (int rr = rg; rr < nr; rr += kPreThreads / 128) {
+            const int head = static_cast<int>((a0 + static_cast<uintptr_t>(r0 + rr) * d.pitch) & 3);
+            const uint8_t* s = srow + rr * srow_cap + head + (xm - sx0);
+            uint8_t o;
+            if (do_h) {
+              int acc = 1 << (kPrecisionBits - 1);
+              if (kmax <= 8) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                  if (k < kmax) acc += static_cast<int>(s[k]) * kc[k];
+              } else {
+                for (int k = 0; k < kmax; ++k) acc += static_cast<int>(s[k]) * kh[k * Ws + x];
+              }
+              o = clip8(acc);
+            } else {
+              o = s[0];
+            }
+            inter[(r0 + rr) * Ws + x] = o;
           }
-          o = clip8(acc);
-        } else {
-          o = s[0];
         }
-        inter[(r0 + rr) * Ws + x] = o;
       }
       __syncthreads();
     }
-    // vertical pass -> plane rows
-    for (int idx = tid; idx < img_h * cw; idx += kPreThreads) {
-      const int y = idx / cw, x = idx - y * cw;
-      uint8_t o;
-      if (do_v) {
-        int acc = 1 << (kPrecisionBits - 1);
-        const int y0 = ymin[y];
-        const int avail = h - y0;
-        for (int k = 0; k < ksize_v; ++k) {
-          const int kk = kv[y * ksize_v + k];
-          if (k < avail) acc += static_cast<int>(inter[(y0 + k) * Ws + x]) * kk;
+    // vertical pass -> plane rows: same column ownership, the row's coefficients are a warp broadcast
+    {
+      const int x = tid & 127, rg = tid >> 7;
+      if (x < cw) {
+        for (int y = rg; y < img_h; y += kPreThreads / 128) {
+          uint8_t o;
+          if (do_v) {
+            int acc = 1 << (kPrecisionBits - 1);
+            const int y0 = ymin[y];
+            const int kmax = ksize_v < h - y0 ? ksize_v : h - y0;
+            const int* kr = kv + y * ksize_v;
+            const uint8_t* col = inter + y0 * Ws + x;
+            for (int k = 0; k < kmax; ++k) acc += static_cast<int>(col[k * Ws]) * kr[k];
+            o = clip8(acc);
+          } else {
+            o = inter[y * Ws + x];
+          }
+          plane[y * Wb + c0 + x] = o;
+          if (nplane) {
+            const float f = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(o), 255.0f), 0.5f), 0.5f);
+            nplane[y * Wb + c0 + x] = __float2bfloat16_rn(f);
+          }
         }
-        o = clip8(acc);
-      } else {
-        o = inter[y * Ws + x];
-      }
-      plane[y * Wb + c0 + x] = o;
-      if (nplane) {
-        const float f = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(o), 255.0f), 0.5f), 0.5f);
-        nplane[y * Wb + c0 + x] = __float2bfloat16_rn(f);
       }
     }
   }
@@ -251,8 +280,8 @@ extern "C" int kiri_preprocess_smem_bytes(int w, int h, int nw, int img_h, int W
 
 extern "C" int kiri_preprocess_pack(const uint8_t* src, const KiriCropDesc* descs_dev, int n_crops,
                                     int img_h, int smem_bytes, int max_strips, uint8_t* planes_u8,
-                                    void* norm_bf16, cudaStream_t stream) {
-  KIRI_REQUIRE(src && descs_dev && planes_u8, "kiri_preprocess_pack: null pointer");
+                                    void* norm_bf16, unsigned long long* crop_sums, cudaStream_t stream) {
+  KIRI_REQUIRE(src && descs_dev && planes_u8 && crop_sums, "kiri_preprocess_pack: null pointer");
   KIRI_REQUIRE(n_crops >= 0 && img_h > 0 && max_strips >= 1 && max_strips <= 65535, "kiri_preprocess_pack: bad sizes");
   if (n_crops == 0) return 0;
   static int max_optin = 0;
@@ -270,7 +299,11 @@ extern "C" int kiri_preprocess_pack(const uint8_t* src, const KiriCropDesc* desc
   }
   KIRI_REQUIRE(smem_bytes <= max_optin, "kiri_preprocess_pack: %d bytes of shared memory requested, %d available",
                smem_bytes, max_optin);
+  ProfScope ps(PS_PREPROCESS, stream);
+  KIRI_CHECK_CUDA(cudaMemsetAsync(crop_sums, 0, sizeof(unsigned long long) * n_crops, stream));
+  KIRI_CHECK_CUDA(launch_pdl(crop_sum_kernel, dim3(n_crops, 8), dim3(kPreThreads), 0, stream, src, descs_dev, crop_sums));
   KIRI_CHECK_CUDA(launch_pdl(preprocess_pack_kernel, dim3(n_crops, max_strips), dim3(kPreThreads), smem_bytes, stream,
-                             src, descs_dev, img_h, planes_u8, reinterpret_cast<__nv_bfloat16*>(norm_bf16), smem_bytes));
+                             src, descs_dev, img_h, planes_u8, reinterpret_cast<__nv_bfloat16*>(norm_bf16), smem_bytes,
+                             static_cast<const unsigned long long*>(crop_sums)));
   return 0;
 }

@@ -54,8 +54,9 @@ def target_widths(w: np.ndarray, h: np.ndarray, img_h: int) -> np.ndarray:
     return np.maximum(1, np.rint(w.astype(np.float64) * scale)).astype(np.int64)
 
 
-def _pre_smem(w, h, nw, img_h, Wb, strip):
-    """numpy mirror of kiri_preprocess_smem_bytes (csrc/preprocess.cu)."""
+def _pre_smem(w, h, nw, img_h, Wb, strip, rows=8):
+    """numpy mirror of kiri_preprocess_smem_bytes (csrc/preprocess.cu) for ``rows`` staged source rows
+    (8 = the minimum the C helper reports)."""
     wout = np.minimum(nw, Wb)
     ws = np.minimum(strip, wout)
     hs = w / nw
@@ -66,7 +67,7 @@ def _pre_smem(w, h, nw, img_h, Wb, strip):
     off = a16(img_h * ksv * 4) + a16(np.full_like(ksv, img_h * 4)) + a16(ws * ksh * 4) + a16(ws * 4) + a16(h * ws)
     span = np.ceil(np.maximum(hs, 1.0) * ws).astype(np.int64) + 2 * ksh + 8
     per_row = a16(span + 4)
-    return off + per_row * 8 + 16 * 8
+    return off + (per_row + 16) * rows
 
 
 def plan_groups(entries: np.ndarray, cfg: CFG, width_mode: str = "parity"
@@ -90,6 +91,8 @@ def plan_groups(entries: np.ndarray, cfg: CFG, width_mode: str = "parity"
             break
         strip = np.where(big & (strip > 32), np.maximum(32, (strip // 2 + 31) // 32 * 32), strip)
         need = _pre_smem(w, h, nw, img_h, wb, strip)
+    # more shared memory than the minimum lets a CTA stage every source row of its strip at once
+    need = np.maximum(need, np.minimum(_pre_smem(w, h, nw, img_h, wb, strip, rows=h), PRE_SMEM_CAP))
     nstr = (wout + strip - 1) // strip
     d_all = np.zeros(len(entries), DESC_DTYPE)
     d_all["src_offset"], d_all["pitch"], d_all["w"], d_all["h"] = entries[:, 0], entries[:, 1], w, h
@@ -225,10 +228,11 @@ class BatchedRecognizer:
         dd = torch.from_numpy(descs.view(np.uint8).reshape(-1)).pin_memory().to(self.device, non_blocking=True)
         planes = torch.empty((n, self.cfg.IMG_H, Wb), dtype=torch.uint8, device=self.device)
         norm = torch.empty((n, self.cfg.IMG_H, Wb), dtype=torch.bfloat16, device=self.device) if want_norm else None
+        sums = torch.empty(2 * n, dtype=torch.int32, device=self.device)
         _lib.check(self.lib.kiri_preprocess_pack(src_dev.data_ptr(), dd.data_ptr(), n, self.cfg.IMG_H, smem, n_strips,
-                                                 planes.data_ptr(), _lib.ptr(norm), _lib.stream_ptr()),
+                                                 planes.data_ptr(), _lib.ptr(norm), sums.data_ptr(), _lib.stream_ptr()),
                    "kiri_preprocess_pack")
-        self.launches += 1
+        self.launches += 2
         return planes, norm
 
     def encode(self, planes: torch.Tensor, want_mem_f32: bool = False, want_tokens: bool = False,
@@ -391,7 +395,8 @@ class BatchedRecognizer:
             plan.append({"Wb": Wb, "idx": idx, "n": len(idx), "planes": planes})
         dd = torch.from_numpy(np.concatenate(dall).view(np.uint8).reshape(-1).copy()).to(self.device)
         kv_len = torch.from_numpy(np.concatenate(kv)).to(self.device) if self.width_mode == "masked" else None
-        out = {"src": src_dev, "groups": plan, "kv_len": kv_len, "descs": dd, "n_crops": len(entries), "smem": smem_max,
+        out = {"src": src_dev, "groups": plan, "kv_len": kv_len, "descs": dd,
+               "sums": torch.empty(2 * len(entries), dtype=torch.int32, device=self.device), "n_crops": len(entries), "smem": smem_max,
                "n_strips": n_strips_max, "planes_all": planes_all, "M": row0, "n_lines": len(entries),
                "mem_row0": torch.from_numpy(np.concatenate(mem_row0)).to(self.device),
                "mem_len": torch.from_numpy(np.concatenate(mem_len)).to(self.device),
@@ -405,8 +410,9 @@ class BatchedRecognizer:
         estimates on the host once to bound its loop)."""
         _lib.check(self.lib.kiri_preprocess_pack(prep["src"].data_ptr(), prep["descs"].data_ptr(), prep["n_crops"],
                                                  self.cfg.IMG_H, prep["smem"], prep["n_strips"],
-                                                 prep["planes_all"].data_ptr(), 0, _lib.stream_ptr()), "kiri_preprocess_pack")
-        self.launches += 1
+                                                 prep["planes_all"].data_ptr(), 0, prep["sums"].data_ptr(), _lib.stream_ptr()),
+                   "kiri_preprocess_pack")
+        self.launches += 2
         enc = self.encode_multi([g["planes"] for g in prep["groups"]], kv_len=prep["kv_len"])
         M, L = prep["M"], prep["n_lines"]
         ids = torch.empty(M, dtype=torch.int32, device=self.device)
@@ -502,9 +508,11 @@ class BatchedRecognizer:
         if not src.is_cuda:
             self.stream.wait_stream(self._copy_stream)
         # ---- ONE preprocess launch for every width group, one encoder pass over all groups
+        sums = self._device("_sums" + sl, 2 * n_lines, torch.int32)
         _lib.check(self.lib.kiri_preprocess_pack(src_dev.data_ptr(), dmeta.data_ptr(), n_lines, IMG_H, smem_max, n_strips_max,
-                                                 planes_all.data_ptr(), 0, _lib.stream_ptr()), "kiri_preprocess_pack")
-        self.launches += 1
+                                                 planes_all.data_ptr(), 0, sums.data_ptr(), _lib.stream_ptr()),
+                   "kiri_preprocess_pack")
+        self.launches += 2
         if not src.is_cuda:
             self._src_free[self._slot] = torch.cuda.Event()
             self._src_free[self._slot].record()

@@ -95,8 +95,9 @@ def run_preprocess(lib, crops_or_pages, boxes, Wb, img_h=48, want_norm=False, sm
     dd = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8).cuda()
     planes = torch.zeros((len(boxes), img_h, Wb), dtype=torch.uint8, device="cuda")
     norm = torch.zeros((len(boxes), img_h, Wb), dtype=torch.bfloat16, device="cuda") if want_norm else None
+    sums = torch.zeros(len(boxes), dtype=torch.int64, device="cuda")
     _lib.check(lib.kiri_preprocess_pack(src.data_ptr(), dd.data_ptr(), len(boxes), img_h, smem, max_strips,
-                                        planes.data_ptr(), _lib.ptr(norm), _lib.stream_ptr()))
+                                        planes.data_ptr(), _lib.ptr(norm), sums.data_ptr(), _lib.stream_ptr()))
     sync()
     return planes.cpu().numpy(), (norm.float().cpu().numpy() if want_norm else None)
 

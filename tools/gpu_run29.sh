@@ -1,0 +1,10 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_all.log 2>&1
+echo "== all rc=$?"; grep -E "passed|failed|FAILED|Error" gpurun_out/pytest_all.log | tail -5
+timeout 300 python tools/bench_hbm_kernels.py > gpurun_out/hbm_kernels.json 2> gpurun_out/hbm_kernels.err; echo "rc=$?"
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/hbm_kernels.json'))
+for k,v in d.items(): print(k, round(v['ms'],4),'ms', round(v['GBps']),'GB/s', round(v['frac_of_hbm_peak'],3))
+PY

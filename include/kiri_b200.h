@@ -88,6 +88,12 @@ int kiri_preprocess_pack(const uint8_t* src, const KiriCropDesc* descs, int n_cr
 int kiri_conv1(const uint8_t* planes_u8, const float* w_host, const float* b_host, int n_lines, int H,
                int W, void* out_bf16_nhwc64, cudaStream_t stream);
 
+/* K2+K3 fused: stem layers 1 and 2 in one kernel (ConvStem.net[0:6], kiri_ocr/model.py:215-220): the
+ * 48-channel activation never leaves the SM.  planes_u8 [n, H, W] (H % 4 == 0, W % 128 == 0),
+ * conv2_w48 bf16 [96, 9*48] ordered (ky, kx, cin), out NHWC bf16 [n, H/2, W/2, 96]. */
+int kiri_stem12(const uint8_t* planes_u8, const float* conv1_w_host, const float* conv1_b_host, const void* conv2_w48,
+                const float* conv2_bias, int n_lines, int H, int W, void* out_nhwc96, cudaStream_t stream);
+
 /* ---------------------------------------------------------------- K3-K5, K8, K9, K11: tcgen05 GEMMs
  * 3x3 conv as implicit GEMM (replaces ConvStem.net[3:12], kiri_ocr/model.py:218-226): input NHWC
  * bf16 [n, IH, IW, Cin] (Cin % 32 == 0), weights bf16 [N, 9*Cin] ordered (ky, kx, cin), pad 1,
@@ -190,6 +196,7 @@ typedef struct {
   KiriDecLayerWeights dec[KIRI_MAX_LAYERS];
   const float* dec_ln_g; const float* dec_ln_b;
   const void* heads_w; const float* heads_b;               /* [2*Vp, D], [2*Vp]: dec_head rows then lm_head rows, Vp = roundup(Vd, 16) */
+  const void* conv2_w48;                                   /* [96, 9*48] (ky, kx, cin) unpadded: the fused conv1+conv2 kernel (nullable) */
 } KiriWeights;
 
 typedef struct KiriHandle KiriHandle;

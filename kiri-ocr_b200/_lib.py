@@ -50,7 +50,7 @@ class KiriWeights(C.Structure):
                 + [(n, vp) for n in ("enc_ln_g", "enc_ln_b", "ctc_ln_g", "ctc_ln_b", "ctc_w", "ctc_b",
                                      "crosskv_w", "crosskv_b", "dec_emb", "dec_pe")]
                 + [("dec", KiriDecLayerWeights * KIRI_MAX_LAYERS)]
-                + [(n, vp) for n in ("dec_ln_g", "dec_ln_b", "heads_w", "heads_b")])
+                + [(n, vp) for n in ("dec_ln_g", "dec_ln_b", "heads_w", "heads_b", "conv2_w48")])
 
 
 class KiriGroup(C.Structure):
@@ -74,6 +74,7 @@ _SIGS = {
     "kiri_preprocess_smem_bytes": (C.c_int, [C.c_int] * 6),
     "kiri_preprocess_pack": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]),
     "kiri_conv1": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]),
+    "kiri_stem12": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]),
     "kiri_conv3x3_bf16": (C.c_int, [vp, vp, vp] + [C.c_int] * 7 + [vp, vp]),
     "kiri_gemm_bf16": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),
     "kiri_gemm_ref": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]),

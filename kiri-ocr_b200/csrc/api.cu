@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -139,6 +140,11 @@ static int conv_call(const void* in, const void* w, const float* bias, int n, in
   return launch_gemm_tc(L, stream);
 }
 
+extern "C" int kiri_stem12(const uint8_t* planes_u8, const float* conv1_w_host, const float* conv1_b_host, const void* conv2_w48,
+                           const float* conv2_bias, int n_lines, int H, int W, void* out_nhwc96, cudaStream_t stream) {
+  return launch_stem12(planes_u8, conv1_w_host, conv1_b_host, conv2_w48, conv2_bias, n_lines, H, W, out_nhwc96, stream);
+}
+
 extern "C" int kiri_conv3x3_bf16(const void* in_nhwc, const void* w, const float* bias, int n, int IH, int IW,
                                  int Cin, int N, int sh, int sw, void* out_nhwc, cudaStream_t stream) {
   KIRI_REQUIRE(in_nhwc && w && bias && out_nhwc, "kiri_conv3x3_bf16: null pointer");
@@ -259,6 +265,11 @@ extern "C" int kiri_encode_multi(KiriHandle* h, const KiriGroup* groups, int n_g
   float* x = reinterpret_cast<float*>(base + ws.x);
   uint8_t* a = base + ws.a;
 
+  // conv1 fused into conv2 (stem12_kernel) is correct and tested but measured SLOWER than the two
+  // kernels (0.99 vs 0.81 ms per 256 lines at 640 px): conv1 costs ~8.7 k cycles of CUDA-core work per
+  // 128-output tile even on 16 producer warps and cannot overlap anything but 1.3 k cycles of MMA,
+  // while the standalone conv1 runs at 64 warps/SM (profiles/README.md).  Opt-in for experiments.
+  static const bool no_stem12 = getenv("KIRI_STEM12") == nullptr;
   // ---- per group: stem (in sub-batches), then pool + positional table + enc_ln_in (+ norm1 of layer 0)
   // written at the group's row offset of the concatenated token stream
   size_t row0 = 0;
@@ -267,11 +278,18 @@ extern "C" int kiri_encode_multi(KiriHandle* h, const KiriGroup* groups, int n_g
     const int sc = (stem_chunk <= 0 || stem_chunk > B) ? B : stem_chunk;
     for (int b0 = 0; b0 < B; b0 += sc) {
       const int nb = (B - b0) < sc ? (B - b0) : sc;
-      { ProfScope ps(PS_CONV1, stream);
-        KIRI_TRY(kiri_conv1(groups[g].planes + static_cast<size_t>(b0) * H * Wb, w.conv1_w_host, w.conv1_b_host, nb, H, Wb,
-                            base + ws.act1, stream)); }
-      { ProfScope ps(PS_CONV2, stream);
-        KIRI_TRY(conv_call(base + ws.act1, w.conv2_w, w.conv2_b, nb, H, Wb, 64, 96, 2, 2, base + ws.act2, stream)); }
+      if (w.conv2_w48 && !no_stem12) {
+        // layers 1+2 fused: the 48-channel activation never reaches HBM
+        ProfScope ps(PS_CONV2, stream);
+        KIRI_TRY(launch_stem12(groups[g].planes + static_cast<size_t>(b0) * H * Wb, w.conv1_w_host, w.conv1_b_host, w.conv2_w48,
+                               w.conv2_b, nb, H, Wb, base + ws.act2, stream));
+      } else {
+        { ProfScope ps(PS_CONV1, stream);
+          KIRI_TRY(kiri_conv1(groups[g].planes + static_cast<size_t>(b0) * H * Wb, w.conv1_w_host, w.conv1_b_host, nb, H, Wb,
+                              base + ws.act1, stream)); }
+        { ProfScope ps(PS_CONV2, stream);
+          KIRI_TRY(conv_call(base + ws.act1, w.conv2_w, w.conv2_b, nb, H, Wb, 64, 96, 2, 2, base + ws.act2, stream)); }
+      }
       { ProfScope ps(PS_CONV3, stream);
         KIRI_TRY(conv_call(base + ws.act2, w.conv3_w, w.conv3_b, nb, H / 2, Wb / 2, 96, 160, 2, 2, base + ws.act3, stream)); }
       { ProfScope ps(PS_CONV4, stream);

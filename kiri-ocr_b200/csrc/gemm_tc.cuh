@@ -67,6 +67,9 @@ struct GemmLaunch {
   EpiParams e;
 };
 int launch_gemm_tc(const GemmLaunch& L, cudaStream_t stream);
+// conv1 fused into conv2 (gemm_tc.cu, stem12_kernel)
+int launch_stem12(const uint8_t* planes, const float* conv1_w_host, const float* conv1_b_host, const void* w48,
+                  const float* bias2, int n, int H, int W, void* out, cudaStream_t stream);
 int gemm_tc_num_sms();
 
 }  // namespace kiri

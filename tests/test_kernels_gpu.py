@@ -255,6 +255,43 @@ def test_conv1_vs_torch(lib):
     assert float(o[..., 48:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("n,W", [(2, 128), (3, 384), (5, 640)])
+def test_stem12_fused_vs_torch_and_unfused(lib, n, W):
+    """conv1 fused into conv2 (stem12_kernel): against torch fp32 with the bf16 rounding of the
+    intermediate, and bit-for-bit against the unfused conv1 -> conv2 kernels (same arithmetic)."""
+    torch.manual_seed(n + W)
+    H = 48
+    planes = torch.randint(0, 256, (n, H, W), dtype=torch.uint8)
+    w1 = torch.randn(48, 9) / 3
+    b1 = torch.randn(48) * 0.1
+    w2 = (torch.randn(96, 48, 3, 3) / (3 * 48 ** 0.5)).to(torch.bfloat16)
+    b2 = dev(torch.randn(96) * 0.2)
+    w48 = dev(w2.permute(0, 2, 3, 1).reshape(96, 9 * 48).contiguous())
+    out = torch.full((n, H // 2, W // 2, 96), float("nan"), dtype=torch.bfloat16, device="cuda")
+    pl = dev(planes)
+    _lib.check(lib.kiri_stem12(pl.data_ptr(), w1.data_ptr(), b1.data_ptr(), w48.data_ptr(), b2.data_ptr(), n, H, W,
+                               out.data_ptr(), _lib.stream_ptr()), "kiri_stem12")
+    sync()
+    assert not torch.isnan(out.float()).any()
+    # torch reference with the same rounding points
+    x = (planes.float() / 255.0 - 0.5) / 0.5
+    a1 = F.silu(F.conv2d(x[:, None], w1.view(48, 1, 3, 3), b1, 1, 1)).to(torch.bfloat16).float()
+    ref = F.silu(F.conv2d(a1, w2.float(), b2.cpu(), 2, 1)).permute(0, 2, 3, 1)
+    err = (out.float().cpu() - ref).abs()
+    assert float(err.max()) < 0.05, f"max err {float(err.max())} at {torch.nonzero(err == err.max())[0].tolist()}"
+    # unfused device path: conv1 (64-channel NHWC) -> conv3x3 with the 64-channel padded weights
+    act1 = torch.empty((n, H, W, 64), dtype=torch.bfloat16, device="cuda")
+    _lib.check(lib.kiri_conv1(pl.data_ptr(), w1.data_ptr(), b1.data_ptr(), n, H, W, act1.data_ptr(), _lib.stream_ptr()))
+    w64 = torch.zeros(96, 3, 3, 64, dtype=torch.bfloat16)
+    w64[..., :48] = w2.permute(0, 2, 3, 1)
+    out2 = torch.empty_like(out)
+    _lib.check(lib.kiri_conv3x3_bf16(act1.data_ptr(), dev(w64.reshape(96, 9 * 64)).data_ptr(), b2.data_ptr(), n, H, W, 64, 96,
+                                     2, 2, out2.data_ptr(), _lib.stream_ptr()))
+    sync()
+    d = (out.float() - out2.float()).abs().max()
+    assert float(d) < 0.02, float(d)          # same products; only the fp32 accumulation order differs
+
+
 # --------------------------------------------------------------------------- norms / attention
 def test_pool_pos_ln_and_layernorm(lib):
     torch.manual_seed(1)

@@ -194,7 +194,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("KIRI_BENCH_NO_SAMPLER"):
         sampler.start()                                     # nvidia-smi needs a while to come up
     cfg, tok, sd = make_model()
     eng = BatchedRecognizer(sd, cfg, tok, device="cuda", width_mode=args.width_mode, stem_chunk=args.stem_chunk)
@@ -269,12 +269,15 @@ def run_ours(args):
     sync_dt = time.perf_counter() - t0
     barrier()
     t0 = time.perf_counter()
+    iter_s = []
     tk = eng.submit(buf, ent, method)
     for _ in range(args.steps - 1):
+        ti = time.perf_counter()
         tk2 = eng.submit(buf, ent, method)
         res = eng.collect(tk)
         gather([])
         tk = tk2
+        iter_s.append(time.perf_counter() - ti)
     res = eng.collect(tk)
     gather([])
     barrier()
@@ -368,7 +371,8 @@ def run_ours(args):
                    "weights": "random-init (seed 0), reference state_dict layout"},
         "e2e": {"value": e2e_value, "unit": "lines/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_dt / args.steps * 1e3, "api": "submit()/collect(), two batches in flight",
-                "sync_value": e2e_sync_value, "sync_api": "recognize_packed(), one blocking call per batch"},
+                "sync_value": e2e_sync_value, "sync_api": "recognize_packed(), one blocking call per batch",
+                "iter_ms_p50_p95_max": [round(float(np.percentile(np.array(iter_s or [0.0]) * 1e3, q)), 3) for q in (50, 95, 100)]},
         "gpu_launches": int(launches), "clocks": clocks,
         "roofline": roof, "whole_step_tensor_frac": tensor_frac, "stages": stages, "other_method": other,
         "cpu_baseline": {"value": cb_v, "unit": "lines/s", "cores": torch.get_num_threads(), "kind": "port",

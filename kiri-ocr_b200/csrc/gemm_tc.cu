@@ -100,7 +100,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* staging = pipe + (size_t)stages * stage_bytes;
   PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(staging + kEpiWarps * kNBuf * kBufBytes);
 
-  const int warp = threadIdx.x >> 5;
+  // the shuffle makes the warp index (and everything derived from it: role, staging slot, rows) provably
+  // warp-uniform for the compiler, so TMA / tcgen05 operands live in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int total_tiles = num_m_tiles * num_n_tiles;
   // contiguous, n-major tile range of this CTA: B changes at most twice per CTA
@@ -109,7 +111,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int num_kb = g.taps * g.cgs;
   const bool timing = e.timing != 0 && blockIdx.x == 0;
 
-  if (threadIdx.x == kTmaWarp * 32) {
+  if (warp == kTmaWarp && lane == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(&bars->full[s], 1);
       mbar_init(&bars->empty[s], 1);
@@ -145,7 +147,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == kTmaWarp) {
     // ============================ TMA producer ============================
-    if (lane == 0) {
+    // The WHOLE warp walks the loop (uniform control flow, coordinates in uniform registers) and one
+    // elected lane issues.  With a single divergent lane running the loop every UTMALDG was wrapped in
+    // an ELECT / R2UR.BROADCAST waterfall: ~640 cycles per stage, the bound of every GEMM of the model
+    // (tools/tma_stream.cu, profiles/README.md).
+    {
       // one TMA box = one KC-channel chunk of one segment: R*SEG rows x (KC*2) B
       const uint32_t box_bytes = g.R * g.SEG * kChunkBytes;
       int stage = 0;
@@ -158,9 +164,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int m_tile = tile - n_tile * num_m_tiles;
         if (BSTAT && n_tile != cur_n) {
           if (b_loads > 0) mbar_wait(&bars->b_empty, (b_loads - 1) & 1);   // MMAs on the old B retired
-          mbar_arrive_expect_tx(&bars->b_full, num_chunks * b_chunk_bytes);
-          for (int ck = 0; ck < num_chunks; ++ck)
-            tma_load_3d(bres + (size_t)ck * b_chunk_bytes, &tmB, &bars->b_full, 0, ck, n_tile * bn);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&bars->b_full, num_chunks * b_chunk_bytes);
+            for (int ck = 0; ck < num_chunks; ++ck)
+              tma_load_3d(bres + (size_t)ck * b_chunk_bytes, &tmB, &bars->b_full, 0, ck, n_tile * bn);
+          }
+          __syncwarp();
           cur_n = n_tile;
           ++b_loads;
         }
@@ -183,44 +192,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         const uint32_t tx_bytes = nvalid * CPS * box_bytes + b_stage_bytes;
+        int ky = 0, kx = 0, cg = 0;                 // k-block = (tap, channel group), walked without divisions
         for (int kb = 0; kb < num_kb; ++kb) {
-          const int tap = kb / g.cgs;
-          const int cg = kb - tap * g.cgs;
-          const int ky = tap / g.kw;
-          const int kx = tap - ky * g.kw;
           if (timing) tt0 = clock64();
           mbar_wait(&bars->empty[stage], phase ^ 1);
           GT_ACC(acc_we, tt0);
-          uint8_t* a_dst = pipe + (size_t)stage * stage_bytes;
-          uint8_t* b_dst = a_dst + a_stage_bytes;
-          mbar_arrive_expect_tx(&bars->full[stage], tx_bytes);
-          for (int c = 0; c < CPS; ++c) {
+          if (elect_one()) {
+            uint8_t* a_dst = pipe + (size_t)stage * stage_bytes;
+            uint8_t* b_dst = a_dst + a_stage_bytes;
+            mbar_arrive_expect_tx(&bars->full[stage], tx_bytes);
+            for (int c = 0; c < CPS; ++c) {
 #pragma unroll
-            for (int j = 0; j < NSEG; ++j) {
-              if (seg_b[j] >= 0)
-                tma_load_5d(a_dst + (size_t)c * kATileBytes + (size_t)j * box_bytes, &tmA,
-                            &bars->full[stage], 0, cg * CPS + c, seg_x[j] + kx, seg_y[j] + ky,
-                            seg_b[j]);
+              for (int j = 0; j < NSEG; ++j) {
+                if (seg_b[j] >= 0)
+                  tma_load_5d(a_dst + (size_t)c * kATileBytes + (size_t)j * box_bytes, &tmA,
+                              &bars->full[stage], 0, cg * CPS + c, seg_x[j] + kx, seg_y[j] + ky,
+                              seg_b[j]);
+              }
+              if (!BSTAT)
+                tma_load_3d(b_dst + (size_t)c * b_chunk_bytes, &tmB, &bars->full[stage], 0,
+                            (ky * g.kw + kx) * g.chunks_per_tap + cg * CPS + c, n_tile * bn);
             }
-            if (!BSTAT)
-              tma_load_3d(b_dst + (size_t)c * b_chunk_bytes, &tmB, &bars->full[stage], 0,
-                          tap * g.chunks_per_tap + cg * CPS + c, n_tile * bn);
           }
+          __syncwarp();
+          if (++cg == g.cgs) { cg = 0; if (++kx == g.kw) { kx = 0; ++ky; } }
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
       GT_ACC(acc_tt, tt_all);
-      GT_FLUSH(0, acc_we); GT_FLUSH(1, acc_tt);
+      if (lane == 0) { GT_FLUSH(0, acc_we); GT_FLUSH(1, acc_tt); }
     }
   } else if (warp == kMmaWarp) {
     // ============================ MMA issuer ============================
-    if (lane == 0) {
+    // whole warp in the loop, one elected lane issues: descriptors are built in uniform registers
+    {
       const uint32_t idesc = umma_idesc_bf16(kTileM, bn);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       int cur_n = -1, b_loads = 0;
       const uint32_t bres_addr = smem_u32(bres);
+      const uint32_t pipe_addr = smem_u32(pipe);
       GT_BEGIN(tm0);
       long long tm_all = tm0, acc_wf = 0, acc_wt = 0, acc_mt = 0;
       for (int tile = t_begin; tile < t_end; ++tile, ++it) {
@@ -237,31 +249,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         GT_ACC(acc_wt, tm0);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kAccStride;
+        const bool last_of_b = BSTAT && (tile + 1 == t_end || (tile + 1) / num_m_tiles != n_tile);
         for (int kb = 0; kb < num_kb; ++kb) {
           if (timing) tm0 = clock64();
           mbar_wait(&bars->full[stage], phase);
           GT_ACC(acc_wf, tm0);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(pipe + (size_t)stage * stage_bytes);
+          const uint32_t a_addr = pipe_addr + static_cast<uint32_t>(stage) * stage_bytes;
           const uint32_t b_addr = BSTAT ? bres_addr + (uint32_t)(kb * CPS) * b_chunk_bytes : a_addr + a_stage_bytes;
-          for (int c = 0; c < CPS; ++c) {
+          if (elect_one()) {
+            for (int c = 0; c < CPS; ++c) {
 #pragma unroll
-            for (int h = 0; h < KC / 16; ++h) {
-              const uint64_t ad = umma_desc_kmajor(a_addr + c * kATileBytes + h * 32, kSBO, kLayout);
-              const uint64_t bd = umma_desc_kmajor(b_addr + c * b_chunk_bytes + h * 32, kSBO, kLayout);
-              umma_bf16(d_tmem, ad, bd, idesc, (kb | c | h) != 0 ? 1u : 0u);
+              for (int h = 0; h < KC / 16; ++h) {
+                const uint64_t ad = umma_desc_kmajor(a_addr + c * kATileBytes + h * 32, kSBO, kLayout);
+                const uint64_t bd = umma_desc_kmajor(b_addr + c * b_chunk_bytes + h * 32, kSBO, kLayout);
+                umma_bf16(d_tmem, ad, bd, idesc, (kb | c | h) != 0 ? 1u : 0u);
+              }
+            }
+            umma_commit(&bars->empty[stage]);       // frees the smem stage when the MMAs retire
+            if (kb + 1 == num_kb) {
+              umma_commit(&bars->tmem_full[acc]);   // accumulator complete -> epilogue
+              if (last_of_b) umma_commit(&bars->b_empty);   // last MMAs that read this B
             }
           }
-          umma_commit(&bars->empty[stage]);       // frees the smem stage when the MMAs retire
+          __syncwarp();
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&bars->tmem_full[acc]);       // accumulator complete -> epilogue
-        if (BSTAT && (tile + 1 == t_end || (tile + 1) / num_m_tiles != n_tile))
-          umma_commit(&bars->b_empty);            // last MMAs that read this B
       }
       GT_ACC(acc_mt, tm_all);
-      GT_FLUSH(2, acc_wf); GT_FLUSH(3, acc_wt); GT_FLUSH(4, acc_mt);
-      if (timing) g_gemm_prof[9] += t_end - t_begin;
+      if (lane == 0) {
+        GT_FLUSH(2, acc_wf); GT_FLUSH(3, acc_wt); GT_FLUSH(4, acc_mt);
+        if (timing) g_gemm_prof[9] += t_end - t_begin;
+      }
     }
   } else {
     // ============================ epilogue warps ============================

@@ -192,6 +192,18 @@ struct EncodeWs {          // byte offsets into the caller's workspace
 };
 inline size_t al(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
 
+// Lines per stem sub-batch of a width group.  `stem_chunk` is a budget in 640-px lines (the stem's
+// activations scale with the width), and the sub-batches of a group are balanced: 66 lines at 512 px
+// run as one launch chain instead of 64 + 2 (a 2-line chain is all fixed cost).
+inline int stem_sub_batch(int B, int Wb, int stem_chunk) {
+  if (stem_chunk <= 0) return B;
+  long long cap = static_cast<long long>(stem_chunk) * 640 / Wb;
+  if (cap < stem_chunk) cap = stem_chunk;
+  if (cap >= B) return B;
+  const int n_chunks = static_cast<int>((B + cap - 1) / cap);
+  return (B + n_chunks - 1) / n_chunks;
+}
+
 // Workspace of a multi-group encode: the stem buffers are sized for the largest sub-batch of any
 // group, the token-stream buffers for the concatenation of all groups.
 EncodeWs plan_encode(const KiriDims& d, const KiriGroup* groups, int n_groups, int stem_chunk) {
@@ -200,7 +212,7 @@ EncodeWs plan_encode(const KiriDims& d, const KiriGroup* groups, int n_groups, i
   long long M = 0;
   for (int g = 0; g < n_groups; ++g) {
     const int B = groups[g].n_lines, Wb = groups[g].Wb;
-    const int sc = (stem_chunk <= 0 || stem_chunk > B) ? B : stem_chunk;
+    const int sc = stem_sub_batch(B, Wb, stem_chunk);
     const size_t T = Wb / 4;
     a1 = std::max(a1, static_cast<size_t>(sc) * H * Wb * 64 * 2);
     a2 = std::max(a2, static_cast<size_t>(sc) * (H / 2) * (Wb / 2) * 96 * 2);
@@ -275,7 +287,7 @@ extern "C" int kiri_encode_multi(KiriHandle* h, const KiriGroup* groups, int n_g
   size_t row0 = 0;
   for (int g = 0; g < n_groups; ++g) {
     const int B = groups[g].n_lines, Wb = groups[g].Wb, T = Wb / 4;
-    const int sc = (stem_chunk <= 0 || stem_chunk > B) ? B : stem_chunk;
+    const int sc = stem_sub_batch(B, Wb, stem_chunk);
     for (int b0 = 0; b0 < B; b0 += sc) {
       const int nb = (B - b0) < sc ? (B - b0) : sc;
       if (w.conv2_w48 && !no_stem12) {

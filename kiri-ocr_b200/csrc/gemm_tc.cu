@@ -16,8 +16,11 @@ static constexpr int kTmemCols = 512;
 static constexpr int kEpiWarps = 8;                     // two per TMEM lane quarter (column halves)
 // Epilogue warps take the LOW warp ids: the SM sub-partition arbiter favours the highest warp id, and
 // the single-lane TMA / MMA issuers (warps 8, 9) must never be starved by epilogue arithmetic.
-static constexpr int kTmaWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
-static constexpr int kNumThreads = 64 + kEpiWarps * 32;
+// Two TMA producer warps take alternate k-blocks: one thread cannot issue a box faster than every
+// ~450 cycles (tools/tma_stream.cu: 1 issuer 51 B/clk/SM, 2 issuers 101 B/clk/SM).
+static constexpr int kTmaWarps = 2;
+static constexpr int kTmaWarp = kEpiWarps, kMmaWarp = kEpiWarps + kTmaWarps;
+static constexpr int kNumThreads = (kEpiWarps + kTmaWarps + 1) * 32;
 static constexpr int kMaxStages = 8;
 static constexpr int kBufBytes = 4096;                  // 32 rows x 128 B epilogue staging tile
 static constexpr int kMaxBResident = 128 * 1024;        // weights kept in shared memory when they fit
@@ -145,8 +148,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   pdl_trigger();                                   // the next kernel may start its prologue
   pdl_wait();                                      // A / residual come from the previous kernel
 
-  if (warp == kTmaWarp) {
-    // ============================ TMA producer ============================
+  if (warp >= kTmaWarp && warp < kTmaWarp + kTmaWarps) {
+    // ============================ TMA producers ============================
     // The WHOLE warp walks the loop (uniform control flow, coordinates in uniform registers) and one
     // elected lane issues.  With a single divergent lane running the loop every UTMALDG was wrapped in
     // an ELECT / R2UR.BROADCAST waterfall: ~640 cycles per stage, the bound of every GEMM of the model
@@ -157,12 +160,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       int cur_n = -1, b_loads = 0;
+      const int pw = warp - kTmaWarp;              // this producer owns k-blocks pw, pw + kTmaWarps, ... of the CTA's stream
+      int turn = 0;
       GT_BEGIN(tt0);
       long long tt_all = tt0, acc_we = 0, acc_tt = 0;
       for (int tile = t_begin; tile < t_end; ++tile) {
         const int n_tile = tile / num_m_tiles;
         const int m_tile = tile - n_tile * num_m_tiles;
-        if (BSTAT && n_tile != cur_n) {
+        if (BSTAT && pw == 0 && n_tile != cur_n) {
           if (b_loads > 0) mbar_wait(&bars->b_empty, (b_loads - 1) & 1);   // MMAs on the old B retired
           if (elect_one()) {
             mbar_arrive_expect_tx(&bars->b_full, num_chunks * b_chunk_bytes);
@@ -194,6 +199,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t tx_bytes = nvalid * CPS * box_bytes + b_stage_bytes;
         int ky = 0, kx = 0, cg = 0;                 // k-block = (tap, channel group), walked without divisions
         for (int kb = 0; kb < num_kb; ++kb) {
+          if (turn == pw) {
           if (timing) tt0 = clock64();
           mbar_wait(&bars->empty[stage], phase ^ 1);
           GT_ACC(acc_we, tt0);
@@ -215,12 +221,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           __syncwarp();
+          }
+          if (++turn == kTmaWarps) turn = 0;
           if (++cg == g.cgs) { cg = 0; if (++kx == g.kw) { kx = 0; ++ky; } }
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
       GT_ACC(acc_tt, tt_all);
-      if (lane == 0) { GT_FLUSH(0, acc_we); GT_FLUSH(1, acc_tt); }
+      if (lane == 0 && pw == 0) { GT_FLUSH(0, acc_we); GT_FLUSH(1, acc_tt); }
     }
   } else if (warp == kMmaWarp) {
     // ============================ MMA issuer ============================

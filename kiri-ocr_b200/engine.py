@@ -253,9 +253,20 @@ class BatchedRecognizer:
                                         _lib.ptr(out.get("mem_f32")), out["mem_bf16"].data_ptr(),
                                         _lib.ptr(out.get("logits")), _lib.ptr(out.get("tokens")), _lib.ptr(kv_len),
                                         _lib.stream_ptr()), "kiri_encode")
-        n_chunks = math.ceil(B / (self.stem_chunk if 0 < self.stem_chunk <= B else B))
+        n_chunks = math.ceil(B / self._stem_sub_batch(B, Wb))
         self.launches += 4 * n_chunks + 1 + 4 * self.pw.enc_layers + 1 + (1 if want_logits else 0)
         return out
+
+    def _stem_sub_batch(self, B: int, Wb: int) -> int:
+        """Mirror of stem_sub_batch() in csrc/api.cu (only used to count launches)."""
+        sc = self.stem_chunk
+        if sc <= 0:
+            return B
+        cap = max(sc, sc * 640 // Wb)
+        if cap >= B:
+            return B
+        n = -(-B // cap)
+        return -(-B // n)
 
     def encode_multi(self, planes_list: Sequence[torch.Tensor], want_mem_f32: bool = False, want_tokens: bool = False,
                      kv_len: Optional[torch.Tensor] = None, want_logits: bool = True):
@@ -284,8 +295,8 @@ class BatchedRecognizer:
                                               _lib.ptr(out.get("mem_f32")), out["mem_bf16"].data_ptr(),
                                               _lib.ptr(out.get("logits")), _lib.ptr(out.get("tokens")), _lib.ptr(kv_len),
                                               _lib.stream_ptr()), "kiri_encode_multi")
-        for _, B, _ in rows:
-            n_chunks = math.ceil(B / (self.stem_chunk if 0 < self.stem_chunk <= B else B))
+        for _, B, T in rows:
+            n_chunks = math.ceil(B / self._stem_sub_batch(B, 4 * T))
             self.launches += 4 * n_chunks + 1 + self.pw.enc_layers          # stem, pool, attention per group
         self.launches += 4 * self.pw.enc_layers + 1 + (1 if want_logits else 0)
         return out

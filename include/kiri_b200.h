@@ -126,6 +126,11 @@ int kiri_layernorm(const float* x, int n_tok, int D, const float* g0, const floa
  * T in {32,64,96,128,160}; kv_len (nullable): per-line number of valid keys. */
 int kiri_encoder_attention(const void* qkv_bf16, void* out_bf16, int n_lines, int T, int heads, int D,
                            const int* kv_len, cudaStream_t stream);
+/* The same for a concatenated token stream of several width groups in ONE launch: group g owns
+ * group_lines[g] lines of group_T[g] tokens, rows and kv_len entries in group order (host arrays,
+ * at most 8 groups). */
+int kiri_encoder_attention_multi(const void* qkv_bf16, void* out_bf16, const int* group_lines, const int* group_T,
+                                 int n_groups, int heads, int D, const int* kv_len, cudaStream_t stream);
 
 /* ---------------------------------------------------------------- K10: fused CTC greedy
  * Replaces compute_ctc_confidence + the id-level part of CharTokenizer.decode_ctc

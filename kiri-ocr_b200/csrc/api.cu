@@ -320,14 +320,10 @@ extern "C" int kiri_encode_multi(KiriHandle* h, const KiriGroup* groups, int n_g
     { ProfScope ps(PS_QKV, stream);
       KIRI_TRY(gemm_call(a, lw.wqkv, lw.bqkv, M, 3 * D, D, EPI_BIAS_BF16, base + ws.qkv, nullptr, nullptr, nullptr, nullptr, stream)); }
     { ProfScope ps(PS_ATTN, stream);
-      size_t r0 = 0, l0 = 0;
-      for (int g = 0; g < n_groups; ++g) {
-        const int B = groups[g].n_lines, T = groups[g].Wb / 4;
-        KIRI_TRY(kiri_encoder_attention(base + ws.qkv + r0 * 3 * D * 2, base + ws.o + r0 * D * 2, B, T, d.enc_heads, D,
-                                        kv_len ? kv_len + l0 : nullptr, stream));
-        r0 += static_cast<size_t>(B) * T;
-        l0 += B;
-      } }
+      int g_lines[8], g_T[8];
+      KIRI_REQUIRE(n_groups <= 8, "kiri_encode_multi: at most 8 width groups");
+      for (int g = 0; g < n_groups; ++g) { g_lines[g] = groups[g].n_lines; g_T[g] = groups[g].Wb / 4; }
+      KIRI_TRY(kiri_encoder_attention_multi(base + ws.qkv, base + ws.o, g_lines, g_T, n_groups, d.enc_heads, D, kv_len, stream)); }
     // x += out_proj(o); a = norm2(x)
     { ProfScope ps(PS_OUTPROJ, stream);
       KIRI_TRY(gemm_call(base + ws.o, lw.wo, lw.bo, M, D, D, EPI_BIAS_RESID_LN, x, x, lw.ln2_g, lw.ln2_b, a, stream)); }

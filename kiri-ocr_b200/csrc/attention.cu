@@ -10,6 +10,8 @@
 #include "common.cuh"
 #include "kiri_b200.h"
 
+#include <cstring>
+
 namespace kiri {
 
 static constexpr int kHd = 32;
@@ -35,43 +37,49 @@ __device__ __forceinline__ uint32_t tile_off(int row, int chunk) {
   return static_cast<uint32_t>(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
 }
 
-// Two CTAs per (line, head), each owning half of the query rows (T/32 warps of 16 rows): with one
-// 10-warp CTA the 106 registers per thread allowed a single resident CTA per SM, so the global-load
-// phase of one (line, head) never overlapped the MMA phase of another; 5-warp CTAs fit three per SM.
-template <int T>
-__global__ void __launch_bounds__(T)
-encoder_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int D,
-                         const int* __restrict__ kv_len) {
-  constexpr int NB = T / 8;          // key blocks of 8
-  __shared__ __align__(128) uint8_t s_q[T * 64];
-  __shared__ __align__(128) uint8_t s_k[T * 64];
-  __shared__ __align__(128) uint8_t s_v[T * 64];
-  const int head = blockIdx.x, line = blockIdx.y;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  pdl_trigger();
-  pdl_wait();                                       // qkv comes from the previous kernel
-  const size_t ld = static_cast<size_t>(3) * D;
-  const __nv_bfloat16* base = qkv + static_cast<size_t>(line) * T * ld + head * kHd;
+// One launch covers every width group of the batch (the token stream is the concatenation of the
+// groups): a CTA finds its group in a small grid-constant table and then its
+// (line, head, half).  Lines of up to 96 tokens are handled by one CTA per (line, head) (T/16 warps of
+// 16 query rows); longer lines by two CTAs that each own half of the query rows, because with one
+// 10-warp CTA the 106 registers per thread allowed a single resident CTA per SM and the global-load
+// phase of one (line, head) never overlapped the MMA phase of another.  Groups are ordered longest
+// first so the short CTAs fill the tail.
+static constexpr int kAttnThreads = 192;
+static constexpr int kAttnMaxGroups = 8;
+struct AttnGroups {
+  int n;
+  int cta_begin[kAttnMaxGroups + 1];
+  int row0[kAttnMaxGroups];      // first token row of the group
+  int line0[kAttnMaxGroups];     // first line of the group (kv_len index)
+  int T[kAttnMaxGroups];
+};
 
-  const int q0 = static_cast<int>(blockIdx.z) * (T / 2);       // first query row of this CTA
-  for (int idx = tid; idx < 2 * T * 4 + (T / 2) * 4; idx += T) {
-    int which, r, c;
-    if (idx < 2 * T * 4) { which = 1 + idx / (T * 4); const int rem = idx % (T * 4); r = rem >> 2; c = rem & 3; }
-    else { which = 0; const int rem = idx - 2 * T * 4; r = q0 + (rem >> 2); c = rem & 3; }
+template <int T, int QR>
+__device__ __forceinline__ void attn_tile(const __nv_bfloat16* __restrict__ base, __nv_bfloat16* __restrict__ obase, const int q0,
+                                          const int D, const int klen, const bool masked, uint8_t* s_q, uint8_t* s_k,
+                                          uint8_t* s_v) {
+  constexpr int NB = T / 8;          // key blocks of 8
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t ld = static_cast<size_t>(3) * D;
+  for (int idx = tid; idx < 2 * T * 4 + QR * 4; idx += kAttnThreads) {
+    int which, r, rl, c;
+    if (idx < 2 * T * 4) { which = 1 + idx / (T * 4); const int rem = idx % (T * 4); r = rem >> 2; rl = r; c = rem & 3; }
+    else { which = 0; const int rem = idx - 2 * T * 4; rl = rem >> 2; r = q0 + rl; c = rem & 3; }
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + r * ld + which * D + c * 8));
     uint8_t* dst = which == 0 ? s_q : (which == 1 ? s_k : s_v);
-    *reinterpret_cast<uint4*>(dst + tile_off(r, c)) = v;
+    *reinterpret_cast<uint4*>(dst + tile_off(rl, c)) = v;
   }
   __syncthreads();
+  if (warp >= QR / 16) return;
 
-  const int m0 = q0 + warp * 16;
+  const int ml = warp * 16;                       // first query row of this warp inside s_q
   const uint32_t q_base = smem_u32(s_q), k_base = smem_u32(s_k), v_base = smem_u32(s_v);
 
   // Q fragments for the two k16 steps of head_dim 32
   uint32_t qa[2][4];
 #pragma unroll
   for (int ks = 0; ks < 2; ++ks)
-    ldsm_x4(q_base + tile_off(m0 + (lane & 15), ks * 2 + (lane >> 4)), qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
+    ldsm_x4(q_base + tile_off(ml + (lane & 15), ks * 2 + (lane >> 4)), qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
 
   float s[NB][4];
 #pragma unroll
@@ -91,12 +99,11 @@ encoder_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* _
 
   // soft-max over keys for rows g = lane/4 (regs 0,1) and g+8 (regs 2,3)
   const float sl2 = 0.17677669529663687f * 1.4426950408889634f;   // 1/sqrt(32) * log2(e)
-  const int klen = kv_len ? kv_len[line] : T;
   const int t2 = (lane & 3) * 2;
   float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
   for (int nb = 0; nb < NB; ++nb) {
-    if (kv_len) {
+    if (masked) {
       const int key = nb * 8 + t2;
       if (key >= klen) { s[nb][0] = -INFINITY; s[nb][2] = -INFINITY; }
       if (key + 1 >= klen) { s[nb][1] = -INFINITY; s[nb][3] = -INFINITY; }
@@ -146,7 +153,7 @@ encoder_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* _
   }
   const float r0 = 1.0f / sum0, r1 = 1.0f / sum1;
   const int g = lane >> 2;
-  __nv_bfloat16* orow0 = out + (static_cast<size_t>(line) * T + m0 + g) * D + head * kHd + t2;
+  __nv_bfloat16* orow0 = obase + static_cast<size_t>(q0 + ml + g) * D + t2;
   __nv_bfloat16* orow1 = orow0 + static_cast<size_t>(8) * D;
 #pragma unroll
   for (int nb = 0; nb < 4; ++nb) {
@@ -155,37 +162,94 @@ encoder_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* _
   }
 }
 
+__global__ void __launch_bounds__(kAttnThreads, 3)
+encoder_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, const int D, const int heads,
+                         const int* __restrict__ kv_len, const __grid_constant__ AttnGroups G) {
+  __shared__ __align__(128) uint8_t s_q[96 * 64];
+  __shared__ __align__(128) uint8_t s_k[160 * 64];
+  __shared__ __align__(128) uint8_t s_v[160 * 64];
+  int gi = 0;
+#pragma unroll
+  for (int i = 1; i < kAttnMaxGroups; ++i)
+    if (i < G.n && static_cast<int>(blockIdx.x) >= G.cta_begin[i]) gi = i;
+  const int T = G.T[gi];
+  const int halves = T > 96 ? 2 : 1;
+  int local = static_cast<int>(blockIdx.x) - G.cta_begin[gi];
+  const int half = local % halves;
+  local /= halves;
+  const int head = local % heads;
+  const int line = local / heads;
+  pdl_trigger();
+  pdl_wait();                                       // qkv comes from the previous kernel
+  const size_t row0 = static_cast<size_t>(G.row0[gi]) + static_cast<size_t>(line) * T;
+  const __nv_bfloat16* base = qkv + row0 * 3 * D + head * kHd;
+  __nv_bfloat16* obase = out + row0 * D + head * kHd;
+  const bool masked = kv_len != nullptr;
+  const int klen = masked ? kv_len[G.line0[gi] + line] : T;
+  switch (T) {
+    case 32:  attn_tile<32, 32>(base, obase, 0, D, klen, masked, s_q, s_k, s_v); break;
+    case 64:  attn_tile<64, 64>(base, obase, 0, D, klen, masked, s_q, s_k, s_v); break;
+    case 96:  attn_tile<96, 96>(base, obase, 0, D, klen, masked, s_q, s_k, s_v); break;
+    case 128: attn_tile<128, 64>(base, obase, half * 64, D, klen, masked, s_q, s_k, s_v); break;
+    default:  attn_tile<160, 80>(base, obase, half * 80, D, klen, masked, s_q, s_k, s_v); break;
+  }
+}
+
 }  // namespace kiri
 
 using namespace kiri;
 
-extern "C" int kiri_encoder_attention(const void* qkv_bf16, void* out_bf16, int n_lines, int T, int heads,
-                                      int D, const int* kv_len, cudaStream_t stream) {
-  KIRI_REQUIRE(qkv_bf16 && out_bf16, "kiri_encoder_attention: null pointer");
+extern "C" int kiri_encoder_attention_multi(const void* qkv_bf16, void* out_bf16, const int* group_lines, const int* group_T,
+                                            int n_groups, int heads, int D, const int* kv_len, cudaStream_t stream) {
+  KIRI_REQUIRE(qkv_bf16 && out_bf16 && group_lines && group_T, "kiri_encoder_attention_multi: null pointer");
   KIRI_REQUIRE(D == heads * kHd, "kiri_encoder_attention: head_dim must be 32 (D=%d, heads=%d)", D, heads);
-  if (n_lines == 0) return 0;
-  dim3 grid(heads, n_lines, 2);
+  KIRI_REQUIRE(n_groups >= 0 && n_groups <= kAttnMaxGroups, "kiri_encoder_attention_multi: at most %d groups", kAttnMaxGroups);
+  // token rows / line indices follow the caller's group order; CTAs are dealt longest group first
+  int row0[kAttnMaxGroups], line0[kAttnMaxGroups], order[kAttnMaxGroups];
+  long long r = 0;
+  int l = 0, n_used = 0;
+  for (int g = 0; g < n_groups; ++g) {
+    const int T = group_T[g];
+    KIRI_REQUIRE(T == 32 || T == 64 || T == 96 || T == 128 || T == 160, "kiri_encoder_attention: T=%d not in {32,64,96,128,160}", T);
+    KIRI_REQUIRE(group_lines[g] >= 0 && r < (1ll << 31), "kiri_encoder_attention_multi: bad group %d", g);
+    row0[g] = static_cast<int>(r);
+    line0[g] = l;
+    r += static_cast<long long>(group_lines[g]) * T;
+    l += group_lines[g];
+    if (group_lines[g] > 0) order[n_used++] = g;
+  }
+  if (n_used == 0) return 0;
+  for (int i = 1; i < n_used; ++i)                  // insertion sort by T, descending
+    for (int j = i; j > 0 && group_T[order[j]] > group_T[order[j - 1]]; --j) { const int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t; }
+  AttnGroups G;
+  memset(&G, 0, sizeof(G));
+  G.n = n_used;
+  long long ctas = 0;
+  for (int i = 0; i < n_used; ++i) {
+    const int g = order[i];
+    G.cta_begin[i] = static_cast<int>(ctas);
+    G.row0[i] = row0[g];
+    G.line0[i] = line0[g];
+    G.T[i] = group_T[g];
+    ctas += static_cast<long long>(group_lines[g]) * heads * (group_T[g] > 96 ? 2 : 1);
+    KIRI_REQUIRE(ctas < 0x7fffffffll, "kiri_encoder_attention_multi: grid too large");
+  }
+  for (int i = n_used; i <= kAttnMaxGroups; ++i) G.cta_begin[i] = static_cast<int>(ctas);
   static bool carveout_set = false;
   if (!carveout_set) {
     // several CTAs per SM need the large shared-memory carve-out (the driver's default for a
-    // 30 KB static kernel was a 32 KB configuration = one resident CTA)
-    cudaFuncSetAttribute(encoder_attention_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(encoder_attention_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(encoder_attention_kernel<96>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(encoder_attention_kernel<128>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(encoder_attention_kernel<160>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    // 26 KB static kernel was a 32 KB configuration = one resident CTA)
+    cudaFuncSetAttribute(encoder_attention_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     carveout_set = true;
   }
-  const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(qkv_bf16);
-  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_bf16);
-  switch (T) {
-    case 32:  KIRI_CHECK_CUDA(launch_pdl(encoder_attention_kernel<32>, grid, dim3(32), 0, stream, q, o, D, kv_len)); break;
-    case 64:  KIRI_CHECK_CUDA(launch_pdl(encoder_attention_kernel<64>, grid, dim3(64), 0, stream, q, o, D, kv_len)); break;
-    case 96:  KIRI_CHECK_CUDA(launch_pdl(encoder_attention_kernel<96>, grid, dim3(96), 0, stream, q, o, D, kv_len)); break;
-    case 128: KIRI_CHECK_CUDA(launch_pdl(encoder_attention_kernel<128>, grid, dim3(128), 0, stream, q, o, D, kv_len)); break;
-    case 160: KIRI_CHECK_CUDA(launch_pdl(encoder_attention_kernel<160>, grid, dim3(160), 0, stream, q, o, D, kv_len)); break;
-    default: KIRI_REQUIRE(false, "kiri_encoder_attention: T=%d not in {32,64,96,128,160}", T);
-  }
+  KIRI_CHECK_CUDA(launch_pdl(encoder_attention_kernel, dim3(static_cast<unsigned>(ctas)), dim3(kAttnThreads), 0, stream,
+                             reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), reinterpret_cast<__nv_bfloat16*>(out_bf16), D, heads,
+                             kv_len, G));
   KIRI_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int kiri_encoder_attention(const void* qkv_bf16, void* out_bf16, int n_lines, int T, int heads,
+                                      int D, const int* kv_len, cudaStream_t stream) {
+  return kiri_encoder_attention_multi(qkv_bf16, out_bf16, &n_lines, &T, 1, heads, D, kv_len, stream);
 }

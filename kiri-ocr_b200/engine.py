@@ -297,8 +297,8 @@ class BatchedRecognizer:
                                               _lib.stream_ptr()), "kiri_encode_multi")
         for _, B, T in rows:
             n_chunks = math.ceil(B / self._stem_sub_batch(B, 4 * T))
-            self.launches += 4 * n_chunks + 1 + self.pw.enc_layers          # stem, pool, attention per group
-        self.launches += 4 * self.pw.enc_layers + 1 + (1 if want_logits else 0)
+            self.launches += 4 * n_chunks + 1                               # stem, pool per group
+        self.launches += 5 * self.pw.enc_layers + 1 + (1 if want_logits else 0)
         return out
 
     def decode_greedy_multi(self, mem_bf16: torch.Tensor, mem_row0: torch.Tensor, mem_len: torch.Tensor,

@@ -338,3 +338,34 @@ def test_encoder_attention_vs_torch(lib, T):
     for i, L in enumerate(kv_len.tolist()):
         r = F.scaled_dot_product_attention(q[i:i + 1], k[i:i + 1, :, :L], v[i:i + 1, :, :L]).transpose(1, 2).reshape(T, D)
         assert float((out[i * T:(i + 1) * T].float() - r).abs().max()) < 0.03
+
+
+def test_encoder_attention_multi_group_one_launch(lib):
+    """All width groups of a concatenated token stream in ONE launch (group order != length order)."""
+    import ctypes as C
+    torch.manual_seed(7)
+    heads, D = 8, 256
+    lines, Ts = [2, 3, 0, 1, 4, 2], [64, 160, 96, 32, 128, 96]
+    M = sum(n * T for n, T in zip(lines, Ts))
+    qkv = dev(torch.randn(M, 3 * D).to(torch.bfloat16))
+    kv = []
+    for n, T in zip(lines, Ts):
+        kv += [max(1, T - 7 * i) for i in range(n)]
+    kv_len = torch.tensor(kv, dtype=torch.int32, device="cuda")
+    gl, gt = (C.c_int * len(lines))(*lines), (C.c_int * len(Ts))(*Ts)
+    for masked in (False, True):
+        out = torch.full((M, D), float("nan"), dtype=torch.bfloat16, device="cuda")
+        _lib.check(lib.kiri_encoder_attention_multi(qkv.data_ptr(), out.data_ptr(), gl, gt, len(lines), heads, D,
+                                                    kv_len.data_ptr() if masked else 0, _lib.stream_ptr()))
+        sync()
+        r0, li = 0, 0
+        for n, T in zip(lines, Ts):
+            for i in range(n):
+                blk = qkv[r0:r0 + T].float()
+                q, k, v = (t.reshape(1, T, heads, 32).transpose(1, 2) for t in blk.split(D, dim=1))
+                L = kv[li] if masked else T
+                ref = F.scaled_dot_product_attention(q, k[:, :, :L], v[:, :, :L]).transpose(1, 2).reshape(T, D)
+                assert float((out[r0:r0 + T].float() - ref).abs().max()) < 0.03, (T, i, masked)
+                r0 += T
+                li += 1
+        assert not torch.isnan(out.float()).any()

@@ -132,6 +132,18 @@ int kiri_encoder_attention(const void* qkv_bf16, void* out_bf16, int n_lines, in
 int kiri_encoder_attention_multi(const void* qkv_bf16, void* out_bf16, const int* group_lines, const int* group_T,
                                  int n_groups, int heads, int D, const int* kv_len, cudaStream_t stream);
 
+/* ---------------------------------------------------------------- K8b: fused encoder-layer tail
+ * Replaces out_proj + residual, norm2, linear1 + GELU, linear2 + residual and the next layer's norm1
+ * of nn.TransformerEncoderLayer (kiri_ocr/model.py:246-261, norm_first=True, activation="gelu") in
+ * ONE kernel; the 1024-wide hidden activation and norm2's output never reach HBM.
+ *   x[M,256] fp32 (in/out) += o[M,256] @ wo[256,256]^T + bo;  a2 = LN(x; ln_mid);
+ *   x += gelu(a2 @ w1[FF,256]^T + b1) @ w2[256,FF]^T + b2;    a_out[M,256] bf16 = LN(x; ln_out)
+ * ln_out_g/ln_out_b/a_out may be NULL together (last layer).  M % 32 == 0, FF % 128 == 0. */
+int kiri_encoder_block(const void* o_bf16, float* x_f32, void* a_out_bf16, const void* wo, const float* bo,
+                       const void* w1, const float* b1, const void* w2, const float* b2, const float* ln_mid_g,
+                       const float* ln_mid_b, const float* ln_out_g, const float* ln_out_b, int M, int FF,
+                       cudaStream_t stream);
+
 /* ---------------------------------------------------------------- K10: fused CTC greedy
  * Replaces compute_ctc_confidence + the id-level part of CharTokenizer.decode_ctc
  * (kiri_ocr/model.py:343-373, 109-119).  logits: [n_lines, T, ld] (first C columns valid).

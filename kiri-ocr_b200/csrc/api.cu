@@ -324,6 +324,15 @@ extern "C" int kiri_encode_multi(KiriHandle* h, const KiriGroup* groups, int n_g
       KIRI_REQUIRE(n_groups <= 8, "kiri_encode_multi: at most 8 width groups");
       for (int g = 0; g < n_groups; ++g) { g_lines[g] = groups[g].n_lines; g_T[g] = groups[g].Wb / 4; }
       KIRI_TRY(kiri_encoder_attention_multi(base + ws.qkv, base + ws.o, g_lines, g_T, n_groups, d.enc_heads, D, kv_len, stream)); }
+    static const bool fused_tail = getenv("KIRI_NO_FUSED_BLOCK") == nullptr;
+    if (fused_tail && d.enc_ff % 128 == 0 && M % 32 == 0) {
+      // x += out_proj(o); x += FFN(norm2(x)); a = next layer's norm1(x) — one kernel (encoder_block.cu)
+      ProfScope ps(PS_FF2, stream);
+      const bool last = l + 1 == d.enc_layers;
+      KIRI_TRY(launch_encoder_block(base + ws.o, x, last ? nullptr : a, lw.wo, lw.bo, lw.w1, lw.b1, lw.w2, lw.b2, lw.ln2_g, lw.ln2_b,
+                                    last ? nullptr : w.enc[l + 1].ln1_g, last ? nullptr : w.enc[l + 1].ln1_b, M, d.enc_ff, stream));
+      continue;
+    }
     // x += out_proj(o); a = norm2(x)
     { ProfScope ps(PS_OUTPROJ, stream);
       KIRI_TRY(gemm_call(base + ws.o, lw.wo, lw.bo, M, D, D, EPI_BIAS_RESID_LN, x, x, lw.ln2_g, lw.ln2_b, a, stream)); }

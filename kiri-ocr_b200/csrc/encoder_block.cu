@@ -1,0 +1,510 @@
+// Fused second half of a pre-LN encoder layer — ONE persistent tcgen05 kernel per layer:
+//
+//     x   += o @ Wo^T + bo                      (attention out-projection + residual)
+//     a2   = LayerNorm_2(x)                     (bf16, never leaves shared memory)
+//     h    = gelu(a2 @ W1^T + b1)               (bf16, 64 hidden columns at a time, never leaves shared memory)
+//     x   += h @ W2^T + b2                      (second residual: the accumulator is PRE-LOADED with x + b2)
+//     a    = LayerNorm_next(x)                  (bf16 A operand of the next layer's QKV GEMM)
+//
+// Replaces, per layer, the out_proj / linear1 / linear2 GEMMs of nn.TransformerEncoderLayer
+// (kiri_ocr/model.py:246-261, norm_first) which as three launches moved 420 MB per 40 960 tokens
+// through HBM (the 1024-wide hidden activation twice, the fp32 residual stream twice, LN output twice);
+// fused, a 128-token tile reads o (64 KB) + x (128 KB) and writes x + a (192 KB), and the 1.15 MB of
+// layer weights stream from L2 through a 3 x 32 KB TMA ring fed by two producer warps.
+//
+// Roles (352 threads): warps 0-7 epilogue (thread = one tile row x one column half), warps 8-9 TMA
+// producers (alternate ring units), warp 10 MMA issuer + TMEM owner.
+// TMEM: X = columns [0,256) (out-proj accumulator, then x + b2 + FFN), H[2] = 2 x 64 columns (hidden chunk).
+// Shared memory (227 KB): ring 96 KB | A2 64 KB | hidden chunk 2 x 16 KB | staging 32 KB; the last three
+// double as the per-warp 16 KB landing zone of the fp32 residual tile / staging of the x and a stores.
+#include "gemm_tc.cuh"
+#include "internal.cuh"
+
+namespace kiri {
+namespace {
+
+constexpr int kEbEpiWarps = 8, kEbProdWarps = 2;
+constexpr int kEbProdWarp0 = kEbEpiWarps, kEbMmaWarp = kEbEpiWarps + kEbProdWarps;
+constexpr int kEbThreads = (kEbEpiWarps + kEbProdWarps + 1) * 32;
+constexpr int kSlotBytes = 32768, kSlots = 3;
+constexpr int kA2Bytes = 65536, kHBytes = 16384, kStgBytes = 32768;
+constexpr int kScratchOff = kSlots * kSlotBytes;                 // A2 | H[2] | staging = 128 KB
+constexpr int kHOff = kScratchOff + kA2Bytes;
+constexpr int kBarOff = kScratchOff + 131072;
+constexpr int kXCol = 0, kHCol = 256;
+
+struct __align__(16) EbBars {
+  uint64_t full[kSlots], empty[kSlots];
+  uint64_t g1_full, a2_ready, x_full, x_empty;
+  uint64_t acc2_full[2], acc2_empty[2], h_full[2], h_empty[2];
+  uint64_t res_full[kEbEpiWarps][4];
+  uint32_t tmem_base;
+  uint32_t pad[3];
+  float xch[2][2][128];              // LayerNorm partial sums: [stat][column half][tile row]
+};
+
+struct EbParams {
+  const float* bo; const float* b1; const float* b2;
+  const float* ln_mid_g; const float* ln_mid_b;
+  const float* ln_out_g; const float* ln_out_b;     // null: no LayerNorm output (last layer)
+  int M, n_tiles, nC;                                // tokens, 128-token tiles, hidden chunks of 64
+};
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+__global__ void __launch_bounds__(kEbThreads, 1)
+encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmWo,
+                     const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+                     const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmA, const EbParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // no static shared memory in this kernel: the dynamic window starts 1024-byte aligned (checked), and
+  // the layout needs all but 600 bytes of the 227 KB
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  uint8_t* ring = smem;
+  uint8_t* scratch = smem + kScratchOff;
+  uint8_t* sA2 = scratch;
+  uint8_t* sH = smem + kHOff;
+  EbBars* bars = reinterpret_cast<EbBars*>(smem + kBarOff);
+
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int nC = p.nC;
+
+  if (warp == kEbProdWarp0 && lane == 0) {
+    for (int s = 0; s < kSlots; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+    mbar_init(&bars->g1_full, 1);
+    mbar_init(&bars->a2_ready, kEbEpiWarps);
+    mbar_init(&bars->x_full, 1);
+    mbar_init(&bars->x_empty, kEbEpiWarps);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bars->acc2_full[b], 1);
+      mbar_init(&bars->acc2_empty[b], kEbEpiWarps);
+      mbar_init(&bars->h_full[b], kEbEpiWarps);
+      mbar_init(&bars->h_empty[b], 1);
+    }
+    for (int w = 0; w < kEbEpiWarps; ++w)
+      for (int c = 0; c < 4; ++c) mbar_init(&bars->res_full[w][c], 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmO); tma_prefetch_desc(&tmWo); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
+    tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmA);
+  }
+  if (warp == kEbMmaWarp) {
+    tmem_alloc(&bars->tmem_base, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+  pdl_trigger();
+  pdl_wait();                                        // o and x come from the previous kernels
+
+  if (warp >= kEbProdWarp0 && warp < kEbProdWarp0 + kEbProdWarps) {
+    // ============================ TMA producers ============================
+    // Ring units per tile, in the order the MMA warp consumes them:
+    //   o_0 Wo_0 o_1 Wo_1 o_2 Wo_2 o_3 Wo_3 | W1_0 W1_1 W2_0 W1_2 W2_1 ... W1_{nC-1} W2_{nC-2} W2_{nC-1}
+    const int pw = warp - kEbProdWarp0;
+    const int units = 8 + 2 * nC;
+    int slot = 0, turn = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      for (int n = 0; n < units; ++n) {
+        if (turn == pw) {
+          mbar_wait(&bars->empty[slot], phase ^ 1);
+          if (elect_one()) {
+            uint8_t* dst = ring + slot * kSlotBytes;
+            uint64_t* fb = &bars->full[slot];
+            if (n < 8) {
+              const int j = n >> 1;
+              if ((n & 1) == 0) {
+                mbar_arrive_expect_tx(fb, 16384);
+                tma_load_3d(dst, &tmO, fb, 0, j, tile * 128);
+              } else {
+                mbar_arrive_expect_tx(fb, 32768);
+                tma_load_3d(dst, &tmWo, fb, 0, j, 0);
+              }
+            } else {
+              const int m = n - 8;
+              int c;
+              bool is_w1;
+              if (m < 2) { is_w1 = true; c = m; }
+              else if (m == 2 * nC - 1) { is_w1 = false; c = nC - 1; }
+              else if (m & 1) { is_w1 = true; c = (m + 1) >> 1; }
+              else { is_w1 = false; c = (m - 2) >> 1; }
+              mbar_arrive_expect_tx(fb, 32768);
+              if (is_w1) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) tma_load_3d(dst + kk * 8192, &tmW1, fb, 0, kk, 64 * c);
+              } else {
+                tma_load_3d(dst, &tmW2, fb, 0, c, 0);
+              }
+            }
+          }
+          __syncwarp();
+        }
+        if (++turn == kEbProdWarps) turn = 0;
+        if (++slot == kSlots) { slot = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == kEbMmaWarp) {
+    // ============================ MMA issuer ============================
+    const uint32_t idesc256 = umma_idesc_bf16(128, 256), idesc64 = umma_idesc_bf16(128, 64);
+    const uint32_t ring_addr = smem_u32(ring), a2_addr = smem_u32(sA2), h_addr = smem_u32(sH);
+    const uint32_t x_tmem = tmem_base + kXCol;
+    int slot = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    auto next_slot = [&]() { if (++slot == kSlots) { slot = 0; phase ^= 1; } };
+    // hidden chunk c: H[c&1] = A2 @ W1[64c:64c+64, :]^T   (K = 256: four 64-wide K chunks of four k16 steps)
+    auto issue_ff1 = [&](int c) {
+      const int b = c & 1, u = c >> 1;
+      mbar_wait(&bars->acc2_empty[b], (u & 1) ^ 1);              // GELU of chunk c-2 has drained H[b]
+      mbar_wait(&bars->full[slot], phase);
+      tc_fence_after();
+      const uint32_t w_addr = ring_addr + slot * kSlotBytes;
+      const uint32_t d_tmem = tmem_base + kHCol + 64 * b;
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const uint64_t ad = umma_desc_kmajor(a2_addr + kk * 16384 + h * 32, 1024, UMMA_LAYOUT_SW128);
+            const uint64_t bd = umma_desc_kmajor(w_addr + kk * 8192 + h * 32, 1024, UMMA_LAYOUT_SW128);
+            umma_bf16(d_tmem, ad, bd, idesc64, (kk | h) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(&bars->empty[slot]);
+        umma_commit(&bars->acc2_full[b]);
+      }
+      __syncwarp();
+      next_slot();
+    };
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      if (it > 0) mbar_wait(&bars->x_empty, (it - 1) & 1);       // the previous tile's x has been read out of TMEM
+      tc_fence_after();
+      // ---- X = o @ Wo^T
+      for (int j = 0; j < 4; ++j) {
+        const int s0 = slot;
+        const uint32_t ph0 = phase;
+        next_slot();
+        const int s1 = slot;
+        const uint32_t ph1 = phase;
+        next_slot();
+        mbar_wait(&bars->full[s0], ph0);
+        mbar_wait(&bars->full[s1], ph1);
+        tc_fence_after();
+        const uint32_t a_addr = ring_addr + s0 * kSlotBytes, b_addr = ring_addr + s1 * kSlotBytes;
+        if (elect_one()) {
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const uint64_t ad = umma_desc_kmajor(a_addr + h * 32, 1024, UMMA_LAYOUT_SW128);
+            const uint64_t bd = umma_desc_kmajor(b_addr + h * 32, 1024, UMMA_LAYOUT_SW128);
+            umma_bf16(x_tmem, ad, bd, idesc256, (j | h) != 0 ? 1u : 0u);
+          }
+          umma_commit(&bars->empty[s0]);
+          umma_commit(&bars->empty[s1]);
+          if (j == 3) umma_commit(&bars->g1_full);
+        }
+        __syncwarp();
+      }
+      // ---- FFN: the epilogue warps have written A2 = LN(x) to shared memory and x + b2 back into X
+      mbar_wait(&bars->a2_ready, it & 1);
+      tc_fence_after();
+      issue_ff1(0);
+      for (int c = 0; c < nC; ++c) {
+        if (c + 1 < nC) issue_ff1(c + 1);
+        const int b = c & 1, u = c >> 1;
+        mbar_wait(&bars->h_full[b], u & 1);                      // gelu(H chunk c) is in shared memory
+        mbar_wait(&bars->full[slot], phase);
+        tc_fence_after();
+        const uint32_t w_addr = ring_addr + slot * kSlotBytes;
+        const uint32_t hb_addr = h_addr + b * kHBytes;
+        if (elect_one()) {
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const uint64_t ad = umma_desc_kmajor(hb_addr + h * 32, 1024, UMMA_LAYOUT_SW128);
+            const uint64_t bd = umma_desc_kmajor(w_addr + h * 32, 1024, UMMA_LAYOUT_SW128);
+            umma_bf16(x_tmem, ad, bd, idesc256, 1u);
+          }
+          umma_commit(&bars->empty[slot]);
+          umma_commit(&bars->h_empty[b]);
+          if (c + 1 == nC) umma_commit(&bars->x_full);
+        }
+        __syncwarp();
+        next_slot();
+      }
+    }
+  } else {
+    // ============================ epilogue warps ============================
+    const int q = warp & 3, half = warp >> 2, ew = warp;
+    const int cb = half * 128;
+    const int trow = q * 32 + lane;
+    auto buf = [&](int c) -> uint8_t* { return scratch + (c * kEbEpiWarps + ew) * 4096; };
+    const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    uint32_t res_cnt = 0;
+    auto load_resid = [&](int tile) {                 // lane 0: this warp's 32 x 128 fp32 residual slice
+      const int row0 = tile * 128 + q * 32;
+      if (row0 < p.M) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          mbar_arrive_expect_tx(&bars->res_full[ew][c], 4096);
+          tma_load_2d(buf(c), &tmX, &bars->res_full[ew][c], cb + c * 32, row0);
+        }
+      }
+    };
+    if (lane == 0 && static_cast<int>(blockIdx.x) < p.n_tiles) load_resid(blockIdx.x);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const int row0 = tile * 128 + q * 32;
+      const bool valid = row0 < p.M;
+      uint32_t v[128];
+      // ================= E1: x_mid = X + bo + x;  X <- x_mid + b2;  A2 <- LN_mid(x_mid)
+      mbar_wait(&bars->g1_full, it & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld32(lane_taddr + kXCol + cb + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
+      tmem_ld_wait();
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (valid) mbar_wait(&bars->res_full[ew][c], res_cnt & 1);
+        const uint8_t* rb = buf(c);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const float4 b = ldg4(p.bo + cb + c * 32 + 4 * t);
+          float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (valid) r4 = *reinterpret_cast<const float4*>(rb + stg_off(lane, t));
+          const float o0 = __uint_as_float(v[c * 32 + 4 * t]) + b.x + r4.x;
+          const float o1 = __uint_as_float(v[c * 32 + 4 * t + 1]) + b.y + r4.y;
+          const float o2 = __uint_as_float(v[c * 32 + 4 * t + 2]) + b.z + r4.z;
+          const float o3 = __uint_as_float(v[c * 32 + 4 * t + 3]) + b.w + r4.w;
+          sum += (o0 + o1) + (o2 + o3);
+          v[c * 32 + 4 * t] = __float_as_uint(o0); v[c * 32 + 4 * t + 1] = __float_as_uint(o1);
+          v[c * 32 + 4 * t + 2] = __float_as_uint(o2); v[c * 32 + 4 * t + 3] = __float_as_uint(o3);
+        }
+      }
+      if (valid) ++res_cnt;
+      // X <- x_mid + b2: the FFN's second GEMM accumulates on top of it (the second residual costs nothing)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t w[32];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const float4 b = ldg4(p.b2 + cb + c * 32 + 4 * t);
+          w[4 * t] = __float_as_uint(__uint_as_float(v[c * 32 + 4 * t]) + b.x);
+          w[4 * t + 1] = __float_as_uint(__uint_as_float(v[c * 32 + 4 * t + 1]) + b.y);
+          w[4 * t + 2] = __float_as_uint(__uint_as_float(v[c * 32 + 4 * t + 2]) + b.z);
+          w[4 * t + 3] = __float_as_uint(__uint_as_float(v[c * 32 + 4 * t + 3]) + b.w);
+        }
+        tmem_st32(lane_taddr + kXCol + cb + c * 32, w);
+      }
+      bars->xch[0][half][trow] = sum;
+      asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+      const float mean = (sum + bars->xch[0][half ^ 1][trow]) * (1.0f / 256.0f);
+      float sq = 0.f;
+#pragma unroll
+      for (int t = 0; t < 128; ++t) { const float d = __uint_as_float(v[t]) - mean; sq = fmaf(d, d, sq); }
+      bars->xch[1][half][trow] = sq;
+      asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+      const float rstd = 1.0f / sqrtf((sq + bars->xch[1][half ^ 1][trow]) * (1.0f / 256.0f) + 1e-5f);
+      tmem_st_wait();
+      // every warp has consumed its residual slice: A2 (which overlays them) may be written
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+      for (int c2 = 0; c2 < 2; ++c2) {               // K chunk 2*half + c2 of A2: [128 rows][64 bf16], 128-byte swizzle
+        uint8_t* ob = sA2 + (2 * half + c2) * 16384 + q * 4096;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const int col = cb + c2 * 64 + t * 8;
+          const float4 g0 = ldg4(p.ln_mid_g + col), g1 = ldg4(p.ln_mid_g + col + 4);
+          const float4 h0 = ldg4(p.ln_mid_b + col), h1 = ldg4(p.ln_mid_b + col + 4);
+          const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+          const float hh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+          float y[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) y[u] = (__uint_as_float(v[c2 * 64 + t * 8 + u]) - mean) * rstd * gg[u] + hh[u];
+          uint4 pk;
+          pk.x = pack_bf16x2(y[0], y[1]); pk.y = pack_bf16x2(y[2], y[3]);
+          pk.z = pack_bf16x2(y[4], y[5]); pk.w = pack_bf16x2(y[6], y[7]);
+          *reinterpret_cast<uint4*>(ob + stg_off(lane, t)) = pk;
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->a2_ready);
+
+      // ================= hidden chunks: gelu(H + b1) -> bf16 A operand of the second GEMM
+      for (int c = 0; c < nC; ++c) {
+        const int b = c & 1, u = c >> 1;
+        uint32_t r[32];
+        mbar_wait(&bars->acc2_full[b], u & 1);
+        tc_fence_after();
+        tmem_ld32(lane_taddr + kHCol + 64 * b + 32 * half, r);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->acc2_empty[b]);
+        uint4 pk[4];
+        const float* b1 = p.b1 + c * 64 + half * 32;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float4 b0 = ldg4(b1 + t * 8), b4 = ldg4(b1 + t * 8 + 4);
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b4.x, b4.y, b4.z, b4.w};
+          float y[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) y[k] = gelu_tanh_erf(__uint_as_float(r[t * 8 + k]) + bb[k]);
+          pk[t].x = pack_bf16x2(y[0], y[1]); pk[t].y = pack_bf16x2(y[2], y[3]);
+          pk[t].z = pack_bf16x2(y[4], y[5]); pk[t].w = pack_bf16x2(y[6], y[7]);
+        }
+        mbar_wait(&bars->h_empty[b], (u & 1) ^ 1);               // the MMAs of chunk c-2 have read H[b]
+        uint8_t* hb = sH + b * kHBytes + q * 4096;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) *reinterpret_cast<uint4*>(hb + stg_off(lane, 4 * half + t)) = pk[t];
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->h_full[b]);
+      }
+
+      // ================= E2: x = X (all FFN MMAs retired) -> global; a = LN_out(x) -> global
+      mbar_wait(&bars->x_full, it & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld32(lane_taddr + kXCol + cb + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->x_empty);
+      sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint8_t* rb = buf(c);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const float4 o = make_float4(__uint_as_float(v[c * 32 + 4 * t]), __uint_as_float(v[c * 32 + 4 * t + 1]),
+                                       __uint_as_float(v[c * 32 + 4 * t + 2]), __uint_as_float(v[c * 32 + 4 * t + 3]));
+          *reinterpret_cast<float4*>(rb + stg_off(lane, t)) = o;
+          sum += (o.x + o.y) + (o.z + o.w);
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0 && valid) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tma_store_2d(&tmX, buf(c), cb + c * 32, row0);
+        bulk_commit_group();
+      }
+      if (p.ln_out_g != nullptr) {
+        bars->xch[0][half][trow] = sum;
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+        const float mean2 = (sum + bars->xch[0][half ^ 1][trow]) * (1.0f / 256.0f);
+        float sq2 = 0.f;
+#pragma unroll
+        for (int t = 0; t < 128; ++t) { const float d = __uint_as_float(v[t]) - mean2; sq2 = fmaf(d, d, sq2); }
+        bars->xch[1][half][trow] = sq2;
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+        const float rstd2 = 1.0f / sqrtf((sq2 + bars->xch[1][half ^ 1][trow]) * (1.0f / 256.0f) + 1e-5f);
+        if (lane == 0) bulk_wait_group_read<0>();                // the x stores have read their tiles
+        __syncwarp();
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2) {
+          uint8_t* ob = buf(c2);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const int col = cb + c2 * 64 + t * 8;
+            const float4 g0 = ldg4(p.ln_out_g + col), g1 = ldg4(p.ln_out_g + col + 4);
+            const float4 h0 = ldg4(p.ln_out_b + col), h1 = ldg4(p.ln_out_b + col + 4);
+            const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const float hh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+            float y[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) y[u] = (__uint_as_float(v[c2 * 64 + t * 8 + u]) - mean2) * rstd2 * gg[u] + hh[u];
+            uint4 pk;
+            pk.x = pack_bf16x2(y[0], y[1]); pk.y = pack_bf16x2(y[2], y[3]);
+            pk.z = pack_bf16x2(y[4], y[5]); pk.w = pack_bf16x2(y[6], y[7]);
+            *reinterpret_cast<uint4*>(ob + stg_off(lane, t)) = pk;
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && valid) {
+          tma_store_2d(&tmA, buf(0), cb, row0);
+          tma_store_2d(&tmA, buf(1), cb + 64, row0);
+          bulk_commit_group();
+        }
+      }
+      // the next tile's residual slice lands in the same buffers once the stores have read them
+      if (lane == 0) {
+        const int nt = tile + gridDim.x;
+        if (nt < p.n_tiles) {
+          bulk_wait_group_read<0>();
+          load_resid(nt);
+        }
+      }
+      __syncwarp();
+    }
+    if (lane == 0) bulk_wait_group<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kEbMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int encode_kchunk_map(CUtensorMap* m, const void* base, int rows, int K, int box_rows) {
+  // bf16 [rows, K] (K contiguous) fetched as [box_rows x 64] boxes that land as 128-byte-swizzled K-major tiles
+  cuuint64_t dims[3] = {64, (cuuint64_t)(K / 64), (cuuint64_t)rows};
+  cuuint64_t str[2] = {128, (cuuint64_t)K * 2};
+  cuuint32_t box[3] = {64, 1, (cuuint32_t)box_rows};
+  cuuint32_t es[3] = {1, 1, 1};
+  return encode_map(m, base, 3, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+}  // namespace
+
+int launch_encoder_block(const void* o, float* x, void* a_out, const void* wo, const float* bo, const void* w1, const float* b1,
+                         const void* w2, const float* b2, const float* ln_mid_g, const float* ln_mid_b, const float* ln_out_g,
+                         const float* ln_out_b, int M, int FF, cudaStream_t stream) {
+  KIRI_REQUIRE(o && x && wo && bo && w1 && b1 && w2 && b2 && ln_mid_g && ln_mid_b, "encoder_block: null pointer");
+  KIRI_REQUIRE((ln_out_g == nullptr) == (ln_out_b == nullptr) && (ln_out_g == nullptr || a_out != nullptr),
+               "encoder_block: ln_out_g, ln_out_b and a_out go together");
+  KIRI_REQUIRE(M % 32 == 0, "encoder_block: token count %d must be a multiple of 32", M);
+  KIRI_REQUIRE(FF % 128 == 0 && FF >= 128, "encoder_block: FF width %d must be a multiple of 128", FF);
+  if (M == 0) return 0;
+  const int sms = gemm_tc_num_sms();
+  CUtensorMap tmO, tmWo, tmW1, tmW2, tmX, tmA;
+  if (encode_kchunk_map(&tmO, o, M, 256, 128)) return -1;
+  if (encode_kchunk_map(&tmWo, wo, 256, 256, 256)) return -1;
+  if (encode_kchunk_map(&tmW1, w1, FF, 256, 64)) return -1;
+  if (encode_kchunk_map(&tmW2, w2, 256, FF, 256)) return -1;
+  if (encode_rowtile_map(&tmX, x, M, 256, 256, true)) return -1;
+  tmA = tmX;
+  if (ln_out_g && encode_rowtile_map(&tmA, a_out, M, 256, 256, false)) return -1;
+  EbParams p;
+  p.bo = bo; p.b1 = b1; p.b2 = b2; p.ln_mid_g = ln_mid_g; p.ln_mid_b = ln_mid_b; p.ln_out_g = ln_out_g; p.ln_out_b = ln_out_b;
+  p.M = M; p.n_tiles = (M + 127) / 128; p.nC = FF / 64;
+  const int smem = kBarOff + static_cast<int>(sizeof(EbBars));
+  KIRI_REQUIRE(smem <= gemm_tc_max_smem(), "encoder_block: %d bytes of shared memory needed, %d available", smem, gemm_tc_max_smem());
+  static bool configured = false;
+  if (!configured) {
+    KIRI_CHECK_CUDA(cudaFuncSetAttribute(encoder_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int grid = p.n_tiles < sms ? p.n_tiles : sms;
+  KIRI_CHECK_CUDA(launch_pdl(encoder_block_kernel, dim3(grid), dim3(kEbThreads), smem, stream, tmO, tmWo, tmW1, tmW2, tmX, tmA, p));
+  return 0;
+}
+
+}  // namespace kiri
+
+extern "C" int kiri_encoder_block(const void* o_bf16, float* x_f32, void* a_out_bf16, const void* wo, const float* bo,
+                                  const void* w1, const float* b1, const void* w2, const float* b2, const float* ln_mid_g,
+                                  const float* ln_mid_b, const float* ln_out_g, const float* ln_out_b, int M, int FF,
+                                  cudaStream_t stream) {
+  return kiri::launch_encoder_block(o_bf16, x_f32, a_out_bf16, wo, bo, w1, b1, w2, b2, ln_mid_g, ln_mid_b, ln_out_g, ln_out_b, M,
+                                    FF, stream);
+}

@@ -39,25 +39,6 @@ struct __align__(16) PipeBarriers {
   float xch[2][2][128];              // LayerNorm partial sums: [stat][column half][tile row]
 };
 
-// 16-byte chunk j of row `lane` inside a 32 x 128 B tile laid out with the 128-byte swizzle that the
-// TMA tensor maps of the epilogue use: conflict-free for "one thread = one row" accesses.
-__device__ __forceinline__ uint32_t stg_off(int lane, int j) {
-  return static_cast<uint32_t>(lane * 128 + ((j ^ (lane & 7)) << 4));
-}
-
-// erf-GELU with erf(z) ~ tanh(z (a + b z^2 + c z^4)), |err| < 4.1e-5 on the clamped range: ONE MUFU
-// per element (the FFN epilogue is MUFU/issue-bound: 32 K activations per 128 x 256 tile).
-__device__ __forceinline__ float gelu_tanh_erf(float v) {
-  const float u = fminf(fmaxf(v * 0.70710678118654752440f, -4.5f), 4.5f);
-  const float u2 = u * u;
-  float p = fmaf(-0.00181363f, u2, 0.10414107f);
-  p = fmaf(p, u2, 1.12812423f);
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u * p));
-  const float h = 0.5f * v;
-  return fmaf(h, t, h);
-}
-
 template <int EPI>
 __device__ __forceinline__ float epi_act(float v) {
   if (EPI == EPI_BIAS_SILU_BF16) return silu_fast(v);
@@ -554,6 +535,8 @@ static EncodeTiledFn get_encode_fn() {
 
 static int g_num_sms = 0;
 static int g_max_smem = 0;
+int gemm_tc_num_sms();
+int gemm_tc_max_smem() { gemm_tc_num_sms(); return g_max_smem; }
 int gemm_tc_num_sms() {
   if (g_num_sms == 0) {
     int dev = 0;
@@ -584,9 +567,9 @@ struct MapKeyHash {
 static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
 static std::mutex g_map_mutex;
 
-static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims,
-                      const cuuint64_t* strides, const cuuint32_t* box, const cuuint32_t* estr,
-                      CUtensorMapSwizzle swz, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
+int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims,
+               const cuuint64_t* strides, const cuuint32_t* box, const cuuint32_t* estr,
+               CUtensorMapSwizzle swz, CUtensorMapDataType dtype) {
   MapKey key;
   memset(&key, 0, sizeof(key));
   key.base = base; key.rank = rank; key.swz = static_cast<int>(swz) | (static_cast<int>(dtype) << 8);
@@ -613,7 +596,7 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64
 }
 
 // 2-D row-major [rows, cols] view moved in 32-row x 128-byte tiles (epilogue stores / residual loads)
-static int encode_rowtile_map(CUtensorMap* m, const void* base, long long rows, int cols, int ld, bool f32) {
+int encode_rowtile_map(CUtensorMap* m, const void* base, long long rows, int cols, int ld, bool f32) {
   const int esz = f32 ? 4 : 2;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t str[1] = {(cuuint64_t)ld * esz};

@@ -71,5 +71,33 @@ int launch_gemm_tc(const GemmLaunch& L, cudaStream_t stream);
 int launch_stem12(const uint8_t* planes, const float* conv1_w_host, const float* conv1_b_host, const void* w48,
                   const float* bias2, int n, int H, int W, void* out, cudaStream_t stream);
 int gemm_tc_num_sms();
+int gemm_tc_max_smem();
+
+// cached cuTensorMapEncodeTiled (gemm_tc.cu)
+int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+               const cuuint32_t* box, const cuuint32_t* estr, CUtensorMapSwizzle swz,
+               CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+// 2-D row-major [rows, cols] view moved in 32-row x 128-byte tiles (epilogue stores / residual loads)
+int encode_rowtile_map(CUtensorMap* m, const void* base, long long rows, int cols, int ld, bool f32);
+
+// 16-byte chunk j of row `lane` inside a 32 x 128 B tile laid out with the 128-byte swizzle that the
+// TMA tensor maps of the epilogue use: conflict-free for "one thread = one row" accesses.
+__device__ __forceinline__ uint32_t stg_off(int lane, int j) {
+  return static_cast<uint32_t>(lane * 128 + ((j ^ (lane & 7)) << 4));
+}
+
+// erf-GELU with erf(z) ~ tanh(z (a + b z^2 + c z^4)), |err| < 4.1e-5 on the clamped range: ONE MUFU
+// per element (the FFN epilogue is MUFU/issue-bound: 32 K activations per 128 x 256 tile).
+__device__ __forceinline__ float gelu_tanh_erf(float v) {
+  const float u = fminf(fmaxf(v * 0.70710678118654752440f, -4.5f), 4.5f);
+  const float u2 = u * u;
+  float p = fmaf(-0.00181363f, u2, 0.10414107f);
+  p = fmaf(p, u2, 1.12812423f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u * p));
+  const float h = 0.5f * v;
+  return fmaf(h, t, h);
+}
+
 
 }  // namespace kiri

@@ -17,6 +17,11 @@ namespace kiri {
 int gemm_call(const void* a, const void* w, const float* bias, int M, int N, int K, int epi, void* out,
               const float* resid, const float* ln_g, const float* ln_b, void* out2, cudaStream_t stream);
 
+// encoder_block.cu: out_proj + LN + FFN + LN of one encoder layer in one kernel
+int launch_encoder_block(const void* o, float* x, void* a_out, const void* wo, const float* bo, const void* w1, const float* b1,
+                         const void* w2, const float* b2, const float* ln_mid_g, const float* ln_mid_b, const float* ln_out_g,
+                         const float* ln_out_b, int M, int FF, cudaStream_t stream);
+
 // decoder_fused.cu: whole-decode persistent cluster kernel
 struct FusedBeam {           // beam-search mode of the fused decoder (nullptr = greedy)
   int beam; double lenp;

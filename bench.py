@@ -12,6 +12,7 @@ Every rank works on its own crops (weak scaling); the only collective is one NCC
 the fixed-stride result records per step.  One JSON line is printed by rank 0.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -260,6 +261,11 @@ def run_ours(args):
     # `e2e_sync` is the same through the blocking one-call form recognize_packed().
     for _ in range(2):
         eng.recognize_packed(buf, ent, method)
+    # a serving process freezes its start-up heap: without this, one generation-2 collection (torch keeps
+    # ~10^6 objects alive) lands in some timed iteration and costs 40 ms (seen as e2e between 22 k and 130 k
+    # lines/s from run to run; iter_ms_p50_p95_max in the line shows the spread)
+    gc.collect()
+    gc.freeze()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -370,7 +376,7 @@ def run_ours(args):
                    "l2": "256 MiB buffer written between timed iterations", "stem_chunk": args.stem_chunk,
                    "weights": "random-init (seed 0), reference state_dict layout"},
         "e2e": {"value": e2e_value, "unit": "lines/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_dt / args.steps * 1e3, "api": "submit()/collect(), two batches in flight",
+                "ms_per_step": e2e_dt / args.steps * 1e3, "api": "submit()/collect(), two batches in flight, gc.freeze() after warm-up",
                 "sync_value": e2e_sync_value, "sync_api": "recognize_packed(), one blocking call per batch",
                 "iter_ms_p50_p95_max": [round(float(np.percentile(np.array(iter_s or [0.0]) * 1e3, q)), 3) for q in (50, 95, 100)]},
         "gpu_launches": int(launches), "clocks": clocks,

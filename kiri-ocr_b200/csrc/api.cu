@@ -172,6 +172,19 @@ extern "C" int kiri_create(const KiriDims* dims, const KiriWeights* weights, Kir
   h->w.conv1_w_host = h->conv1_w;
   h->w.conv1_b_host = h->conv1_b;
   h->fused = nullptr;
+  h->enc_consts = nullptr;
+  if (dims->enc_ff % 128 == 0 && dims->enc_ff <= 1024 && dims->enc_layers > 0 && weights->enc[0].wo) {
+    h->enc_consts = new (std::nothrow) EbConst[dims->enc_layers];
+    KIRI_REQUIRE(h->enc_consts, "kiri_create: out of host memory");
+    for (int l = 0; l < dims->enc_layers; ++l) {
+      const KiriEncLayerWeights& lw = weights->enc[l];
+      const bool last = l + 1 == dims->enc_layers;
+      const int rc = encoder_block_consts(&h->enc_consts[l], lw.bo, lw.b1, lw.b2, lw.ln2_g, lw.ln2_b,
+                                          last ? nullptr : weights->enc[l + 1].ln1_g, last ? nullptr : weights->enc[l + 1].ln1_b,
+                                          dims->enc_ff);
+      if (rc != 0) { delete[] h->enc_consts; delete h; return rc; }
+    }
+  }
   if (dims->dec_layers > 0 && weights->heads_w && weights->dec[0].wqkv) {
     const int rc = fused_decoder_build(h);
     if (rc != 0) { delete h; return rc; }
@@ -182,6 +195,7 @@ extern "C" int kiri_create(const KiriDims* dims, const KiriWeights* weights, Kir
 extern "C" void kiri_destroy(KiriHandle* h) {
   if (!h) return;
   fused_decoder_free(h);
+  delete[] h->enc_consts;
   delete h;
 }
 
@@ -325,12 +339,12 @@ extern "C" int kiri_encode_multi(KiriHandle* h, const KiriGroup* groups, int n_g
       for (int g = 0; g < n_groups; ++g) { g_lines[g] = groups[g].n_lines; g_T[g] = groups[g].Wb / 4; }
       KIRI_TRY(kiri_encoder_attention_multi(base + ws.qkv, base + ws.o, g_lines, g_T, n_groups, d.enc_heads, D, kv_len, stream)); }
     static const bool fused_tail = getenv("KIRI_NO_FUSED_BLOCK") == nullptr;
-    if (fused_tail && d.enc_ff % 128 == 0 && M % 32 == 0) {
+    if (fused_tail && h->enc_consts && M % 32 == 0) {
       // x += out_proj(o); x += FFN(norm2(x)); a = next layer's norm1(x) — one kernel (encoder_block.cu)
       ProfScope ps(PS_FF2, stream);
       const bool last = l + 1 == d.enc_layers;
-      KIRI_TRY(launch_encoder_block(base + ws.o, x, last ? nullptr : a, lw.wo, lw.bo, lw.w1, lw.b1, lw.w2, lw.b2, lw.ln2_g, lw.ln2_b,
-                                    last ? nullptr : w.enc[l + 1].ln1_g, last ? nullptr : w.enc[l + 1].ln1_b, M, d.enc_ff, stream));
+      KIRI_TRY(launch_encoder_block(base + ws.o, x, last ? nullptr : a, lw.wo, lw.w1, lw.w2, &h->enc_consts[l], !last, M, d.enc_ff,
+                                    stream));
       continue;
     }
     // x += out_proj(o); a = norm2(x)

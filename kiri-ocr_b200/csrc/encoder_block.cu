@@ -12,18 +12,20 @@
 // fused, a 128-token tile reads o (64 KB) + x (128 KB) and writes x + a (192 KB), and the 1.15 MB of
 // layer weights stream from L2 through a 3 x 32 KB TMA ring fed by two producer warps.
 //
-// Roles (352 threads): warps 0-7 epilogue (thread = one tile row x one column half), warps 8-9 TMA
-// producers (alternate ring units), warp 10 MMA issuer + TMEM owner.
+// Roles (608 threads): warps 0-15 epilogue (thread = one tile row x one column quarter), warps 16-17 TMA
+// producers (alternate ring units), warp 18 MMA issuer + TMEM owner.
 // TMEM: X = columns [0,256) (out-proj accumulator, then x + b2 + FFN), H[2] = 2 x 64 columns (hidden chunk).
 // Shared memory (227 KB): ring 96 KB | A2 64 KB | hidden chunk 2 x 16 KB | staging 32 KB; the last three
-// double as the per-warp 16 KB landing zone of the fp32 residual tile / staging of the x and a stores.
+// double as the per-warp 8 KB landing zone of the fp32 residual tile / staging of the x and a stores.
 #include "gemm_tc.cuh"
 #include "internal.cuh"
+
+#include <cstring>
 
 namespace kiri {
 namespace {
 
-constexpr int kEbEpiWarps = 8, kEbProdWarps = 2;
+constexpr int kEbEpiWarps = 16, kEbProdWarps = 2;
 constexpr int kEbProdWarp0 = kEbEpiWarps, kEbMmaWarp = kEbEpiWarps + kEbProdWarps;
 constexpr int kEbThreads = (kEbEpiWarps + kEbProdWarps + 1) * 32;
 constexpr int kSlotBytes = 32768, kSlots = 3;
@@ -37,25 +39,34 @@ struct __align__(16) EbBars {
   uint64_t full[kSlots], empty[kSlots];
   uint64_t g1_full, a2_ready, x_full, x_empty;
   uint64_t acc2_full[2], acc2_empty[2], h_full[2], h_empty[2];
-  uint64_t res_full[kEbEpiWarps][4];
+  uint64_t res_full[kEbEpiWarps][2];
   uint32_t tmem_base;
   uint32_t pad[3];
-  float xch[2][2][128];              // LayerNorm partial sums: [stat][column half][tile row]
+  float xch[4][128];                 // LayerNorm partial sums: [column quarter][tile row]
 };
 
+// Biases and LayerNorm affines travel BY VALUE in the kernel parameters (constant bank): the epilogue threads
+// of a warp all want the same element, and as 128-bit global/shared broadcast loads those cost the full
+// 512-byte register write-back each (1024 of them per LayerNorm pass = 4-8 k cycles per tile, measured).
 struct EbParams {
-  const float* bo; const float* b1; const float* b2;
-  const float* ln_mid_g; const float* ln_mid_b;
-  const float* ln_out_g; const float* ln_out_b;     // null: no LayerNorm output (last layer)
+  EbConst c;
+  int has_ln_out;                                    // 0: no LayerNorm output (last layer)
   int M, n_tiles, nC;                                // tokens, 128-token tiles, hidden chunks of 64
+  int timing;
 };
 
-__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// KIRI_GEMM_TIMING=1: phase cycles of CTA 0 (epilogue warp 0 lane 0 / MMA warp), read by kiri_debug_eb_timing():
+// [0] E1 wait g1 [1] E1 wait resid [2] E1 work [3] FF wait acc2_full [4] FF wait h_empty [5] FF work [6] E2 wait x_full
+// [7] E2 work [8] tiles [9] MMA wait ring [10] MMA wait a2_ready [11] MMA wait h_full [12] MMA wait acc2_empty [13] MMA total
+__device__ long long g_eb_prof[16];
+#define EB_T(acc) do { if (timing) { const long long _t = clock64(); acc += _t - tq; tq = _t; } } while (0)
+
 
 __global__ void __launch_bounds__(kEbThreads, 1)
 encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmWo,
                      const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
-                     const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmA, const EbParams p) {
+                     const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmA,
+                     const __grid_constant__ EbParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // no static shared memory in this kernel: the dynamic window starts 1024-byte aligned (checked), and
   // the layout needs all but 600 bytes of the 227 KB
@@ -84,7 +95,7 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
       mbar_init(&bars->h_empty[b], 1);
     }
     for (int w = 0; w < kEbEpiWarps; ++w)
-      for (int c = 0; c < 4; ++c) mbar_init(&bars->res_full[w][c], 1);
+      for (int c = 0; c < 2; ++c) mbar_init(&bars->res_full[w][c], 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmO); tma_prefetch_desc(&tmWo); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
     tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmA);
@@ -155,12 +166,18 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
     int slot = 0;
     uint32_t phase = 0;
     int it = 0;
+    const bool timing = p.timing != 0 && blockIdx.x == 0;
+    long long tq = timing ? clock64() : 0, m_ring = 0, m_a2 = 0, m_hf = 0, m_ae = 0, m_other = 0;
+    const long long m_t0 = tq;
     auto next_slot = [&]() { if (++slot == kSlots) { slot = 0; phase ^= 1; } };
     // hidden chunk c: H[c&1] = A2 @ W1[64c:64c+64, :]^T   (K = 256: four 64-wide K chunks of four k16 steps)
     auto issue_ff1 = [&](int c) {
       const int b = c & 1, u = c >> 1;
+      EB_T(m_other);
       mbar_wait(&bars->acc2_empty[b], (u & 1) ^ 1);              // GELU of chunk c-2 has drained H[b]
+      EB_T(m_ae);
       mbar_wait(&bars->full[slot], phase);
+      EB_T(m_ring);
       tc_fence_after();
       const uint32_t w_addr = ring_addr + slot * kSlotBytes;
       const uint32_t d_tmem = tmem_base + kHCol + 64 * b;
@@ -191,8 +208,10 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
         const int s1 = slot;
         const uint32_t ph1 = phase;
         next_slot();
+        EB_T(m_other);
         mbar_wait(&bars->full[s0], ph0);
         mbar_wait(&bars->full[s1], ph1);
+        EB_T(m_ring);
         tc_fence_after();
         const uint32_t a_addr = ring_addr + s0 * kSlotBytes, b_addr = ring_addr + s1 * kSlotBytes;
         if (elect_one()) {
@@ -209,14 +228,19 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
         __syncwarp();
       }
       // ---- FFN: the epilogue warps have written A2 = LN(x) to shared memory and x + b2 back into X
+      EB_T(m_other);
       mbar_wait(&bars->a2_ready, it & 1);
+      EB_T(m_a2);
       tc_fence_after();
       issue_ff1(0);
       for (int c = 0; c < nC; ++c) {
         if (c + 1 < nC) issue_ff1(c + 1);
         const int b = c & 1, u = c >> 1;
+        EB_T(m_other);
         mbar_wait(&bars->h_full[b], u & 1);                      // gelu(H chunk c) is in shared memory
+        EB_T(m_hf);
         mbar_wait(&bars->full[slot], phase);
+        EB_T(m_ring);
         tc_fence_after();
         const uint32_t w_addr = ring_addr + slot * kSlotBytes;
         const uint32_t hb_addr = h_addr + b * kHBytes;
@@ -235,44 +259,66 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
         next_slot();
       }
     }
+    if (timing && lane == 0) {
+      g_eb_prof[9] += m_ring; g_eb_prof[10] += m_a2; g_eb_prof[11] += m_hf; g_eb_prof[12] += m_ae;
+      g_eb_prof[13] += clock64() - m_t0;
+    }
   } else {
     // ============================ epilogue warps ============================
-    const int q = warp & 3, half = warp >> 2, ew = warp;
-    const int cb = half * 128;
+    // 16 warps: warp w reads TMEM lane quarter q = w & 3 (hardware rule) and owns column quarter cq = w >> 2,
+    // i.e. thread = one tile row x 64 columns.  (With 8 warps of 128 columns per thread the two LayerNorm
+    // passes and the GELU were latency-bound at 2 warps per scheduler: 13 k + 11 k + 26 k cycles per tile.)
+    const int q = warp & 3, cq = warp >> 2, ew = warp;
+    const int cb = cq * 64;
     const int trow = q * 32 + lane;
     auto buf = [&](int c) -> uint8_t* { return scratch + (c * kEbEpiWarps + ew) * 4096; };
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     uint32_t res_cnt = 0;
-    auto load_resid = [&](int tile) {                 // lane 0: this warp's 32 x 128 fp32 residual slice
+    auto load_resid = [&](int tile) {                 // lane 0: this warp's 32 x 64 fp32 residual slice
       const int row0 = tile * 128 + q * 32;
       if (row0 < p.M) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
           mbar_arrive_expect_tx(&bars->res_full[ew][c], 4096);
           tma_load_2d(buf(c), &tmX, &bars->res_full[ew][c], cb + c * 32, row0);
         }
       }
     };
+    // LayerNorm statistics of a row are spread over the four warps of its lane quarter
+    auto row_total = [&](float part) -> float {
+      bars->xch[cq][trow] = part;
+      asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory");
+      const float tot = (bars->xch[0][trow] + bars->xch[1][trow]) + (bars->xch[2][trow] + bars->xch[3][trow]);
+      asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory");       // everyone has read: xch may be rewritten
+      return tot;
+    };
     if (lane == 0 && static_cast<int>(blockIdx.x) < p.n_tiles) load_resid(blockIdx.x);
     int it = 0;
+    const bool timing = p.timing != 0 && blockIdx.x == 0 && warp == 0;
+    long long tq = timing ? clock64() : 0, e_g1 = 0, e_res = 0, e_w1 = 0, e_af = 0, e_he = 0, e_ff = 0, e_xf = 0, e_w2 = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int row0 = tile * 128 + q * 32;
       const bool valid = row0 < p.M;
-      uint32_t v[128];
+      uint32_t v[64];
+      if (timing) tq = clock64();
       // ================= E1: x_mid = X + bo + x;  X <- x_mid + b2;  A2 <- LN_mid(x_mid)
       mbar_wait(&bars->g1_full, it & 1);
+      EB_T(e_g1);
       tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld32(lane_taddr + kXCol + cb + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
+      for (int c = 0; c < 2; ++c) tmem_ld32(lane_taddr + kXCol + cb + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
       tmem_ld_wait();
       float sum = 0.f;
+      if (valid) mbar_wait(&bars->res_full[ew][1], res_cnt & 1);
+      EB_T(e_res);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         if (valid) mbar_wait(&bars->res_full[ew][c], res_cnt & 1);
         const uint8_t* rb = buf(c);
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
-          const float4 b = ldg4(p.bo + cb + c * 32 + 4 * t);
+          const float* bp = p.c.bo + cb + c * 32 + 4 * t;
+          const float4 b = make_float4(bp[0], bp[1], bp[2], bp[3]);
           float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (valid) r4 = *reinterpret_cast<const float4*>(rb + stg_off(lane, t));
           const float o0 = __uint_as_float(v[c * 32 + 4 * t]) + b.x + r4.x;
@@ -287,11 +333,12 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
       if (valid) ++res_cnt;
       // X <- x_mid + b2: the FFN's second GEMM accumulates on top of it (the second residual costs nothing)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t w[32];
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
-          const float4 b = ldg4(p.b2 + cb + c * 32 + 4 * t);
+          const float* bp = p.c.b2 + cb + c * 32 + 4 * t;
+          const float4 b = make_float4(bp[0], bp[1], bp[2], bp[3]);
           w[4 * t] = __float_as_uint(__uint_as_float(v[c * 32 + 4 * t]) + b.x);
           w[4 * t + 1] = __float_as_uint(__uint_as_float(v[c * 32 + 4 * t + 1]) + b.y);
           w[4 * t + 2] = __float_as_uint(__uint_as_float(v[c * 32 + 4 * t + 2]) + b.z);
@@ -299,31 +346,24 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
         }
         tmem_st32(lane_taddr + kXCol + cb + c * 32, w);
       }
-      bars->xch[0][half][trow] = sum;
-      asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
-      const float mean = (sum + bars->xch[0][half ^ 1][trow]) * (1.0f / 256.0f);
+      const float mean = row_total(sum) * (1.0f / 256.0f);
       float sq = 0.f;
 #pragma unroll
-      for (int t = 0; t < 128; ++t) { const float d = __uint_as_float(v[t]) - mean; sq = fmaf(d, d, sq); }
-      bars->xch[1][half][trow] = sq;
-      asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
-      const float rstd = 1.0f / sqrtf((sq + bars->xch[1][half ^ 1][trow]) * (1.0f / 256.0f) + 1e-5f);
+      for (int t = 0; t < 64; ++t) { const float d = __uint_as_float(v[t]) - mean; sq = fmaf(d, d, sq); }
+      const float rstd = 1.0f / sqrtf(row_total(sq) * (1.0f / 256.0f) + 1e-5f);
       tmem_st_wait();
       // every warp has consumed its residual slice: A2 (which overlays them) may be written
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-#pragma unroll
-      for (int c2 = 0; c2 < 2; ++c2) {               // K chunk 2*half + c2 of A2: [128 rows][64 bf16], 128-byte swizzle
-        uint8_t* ob = sA2 + (2 * half + c2) * 16384 + q * 4096;
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      {                                              // K chunk cq of A2: [128 rows][64 bf16], 128-byte swizzle
+        uint8_t* ob = sA2 + cq * 16384 + q * 4096;
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
-          const int col = cb + c2 * 64 + t * 8;
-          const float4 g0 = ldg4(p.ln_mid_g + col), g1 = ldg4(p.ln_mid_g + col + 4);
-          const float4 h0 = ldg4(p.ln_mid_b + col), h1 = ldg4(p.ln_mid_b + col + 4);
-          const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-          const float hh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+          const int col = cb + t * 8;
+          const float* gg = p.c.ln_mid_g + col;
+          const float* hh = p.c.ln_mid_b + col;
           float y[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) y[u] = (__uint_as_float(v[c2 * 64 + t * 8 + u]) - mean) * rstd * gg[u] + hh[u];
+          for (int u = 0; u < 8; ++u) y[u] = (__uint_as_float(v[t * 8 + u]) - mean) * rstd * gg[u] + hh[u];
           uint4 pk;
           pk.x = pack_bf16x2(y[0], y[1]); pk.y = pack_bf16x2(y[2], y[3]);
           pk.z = pack_bf16x2(y[4], y[5]); pk.w = pack_bf16x2(y[6], y[7]);
@@ -334,51 +374,56 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->a2_ready);
+      EB_T(e_w1);
 
       // ================= hidden chunks: gelu(H + b1) -> bf16 A operand of the second GEMM
       for (int c = 0; c < nC; ++c) {
         const int b = c & 1, u = c >> 1;
-        uint32_t r[32];
+        uint32_t r[16];
         mbar_wait(&bars->acc2_full[b], u & 1);
+        EB_T(e_af);
         tc_fence_after();
-        tmem_ld32(lane_taddr + kHCol + 64 * b + 32 * half, r);
+        tmem_ld16(lane_taddr + kHCol + 64 * b + 16 * cq, r);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->acc2_empty[b]);
-        uint4 pk[4];
-        const float* b1 = p.b1 + c * 64 + half * 32;
+        uint4 pk[2];
+        const float* b1 = p.c.b1 + c * 64 + cq * 16;
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const float4 b0 = ldg4(b1 + t * 8), b4 = ldg4(b1 + t * 8 + 4);
-          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b4.x, b4.y, b4.z, b4.w};
+        for (int t = 0; t < 2; ++t) {
+          const float* bb = b1 + t * 8;
           float y[8];
 #pragma unroll
           for (int k = 0; k < 8; ++k) y[k] = gelu_tanh_erf(__uint_as_float(r[t * 8 + k]) + bb[k]);
           pk[t].x = pack_bf16x2(y[0], y[1]); pk[t].y = pack_bf16x2(y[2], y[3]);
           pk[t].z = pack_bf16x2(y[4], y[5]); pk[t].w = pack_bf16x2(y[6], y[7]);
         }
+        EB_T(e_ff);
         mbar_wait(&bars->h_empty[b], (u & 1) ^ 1);               // the MMAs of chunk c-2 have read H[b]
+        EB_T(e_he);
         uint8_t* hb = sH + b * kHBytes + q * 4096;
 #pragma unroll
-        for (int t = 0; t < 4; ++t) *reinterpret_cast<uint4*>(hb + stg_off(lane, 4 * half + t)) = pk[t];
+        for (int t = 0; t < 2; ++t) *reinterpret_cast<uint4*>(hb + stg_off(lane, 2 * cq + t)) = pk[t];
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->h_full[b]);
+        EB_T(e_ff);
       }
 
       // ================= E2: x = X (all FFN MMAs retired) -> global; a = LN_out(x) -> global
       mbar_wait(&bars->x_full, it & 1);
+      EB_T(e_xf);
       tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld32(lane_taddr + kXCol + cb + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
+      for (int c = 0; c < 2; ++c) tmem_ld32(lane_taddr + kXCol + cb + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->x_empty);
       sum = 0.f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint8_t* rb = buf(c);
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
@@ -391,46 +436,36 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
       fence_proxy_async();
       __syncwarp();
       if (lane == 0 && valid) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tma_store_2d(&tmX, buf(c), cb + c * 32, row0);
+        tma_store_2d(&tmX, buf(0), cb, row0);
+        tma_store_2d(&tmX, buf(1), cb + 32, row0);
         bulk_commit_group();
       }
-      if (p.ln_out_g != nullptr) {
-        bars->xch[0][half][trow] = sum;
-        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
-        const float mean2 = (sum + bars->xch[0][half ^ 1][trow]) * (1.0f / 256.0f);
+      if (p.has_ln_out) {
+        const float mean2 = row_total(sum) * (1.0f / 256.0f);
         float sq2 = 0.f;
 #pragma unroll
-        for (int t = 0; t < 128; ++t) { const float d = __uint_as_float(v[t]) - mean2; sq2 = fmaf(d, d, sq2); }
-        bars->xch[1][half][trow] = sq2;
-        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
-        const float rstd2 = 1.0f / sqrtf((sq2 + bars->xch[1][half ^ 1][trow]) * (1.0f / 256.0f) + 1e-5f);
+        for (int t = 0; t < 64; ++t) { const float d = __uint_as_float(v[t]) - mean2; sq2 = fmaf(d, d, sq2); }
+        const float rstd2 = 1.0f / sqrtf(row_total(sq2) * (1.0f / 256.0f) + 1e-5f);
         if (lane == 0) bulk_wait_group_read<0>();                // the x stores have read their tiles
         __syncwarp();
+        uint8_t* ob = buf(0);
 #pragma unroll
-        for (int c2 = 0; c2 < 2; ++c2) {
-          uint8_t* ob = buf(c2);
+        for (int t = 0; t < 8; ++t) {
+          const int col = cb + t * 8;
+          const float* gg = p.c.ln_out_g + col;
+          const float* hh = p.c.ln_out_b + col;
+          float y[8];
 #pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            const int col = cb + c2 * 64 + t * 8;
-            const float4 g0 = ldg4(p.ln_out_g + col), g1 = ldg4(p.ln_out_g + col + 4);
-            const float4 h0 = ldg4(p.ln_out_b + col), h1 = ldg4(p.ln_out_b + col + 4);
-            const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-            const float hh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-            float y[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) y[u] = (__uint_as_float(v[c2 * 64 + t * 8 + u]) - mean2) * rstd2 * gg[u] + hh[u];
-            uint4 pk;
-            pk.x = pack_bf16x2(y[0], y[1]); pk.y = pack_bf16x2(y[2], y[3]);
-            pk.z = pack_bf16x2(y[4], y[5]); pk.w = pack_bf16x2(y[6], y[7]);
-            *reinterpret_cast<uint4*>(ob + stg_off(lane, t)) = pk;
-          }
+          for (int u = 0; u < 8; ++u) y[u] = (__uint_as_float(v[t * 8 + u]) - mean2) * rstd2 * gg[u] + hh[u];
+          uint4 pk;
+          pk.x = pack_bf16x2(y[0], y[1]); pk.y = pack_bf16x2(y[2], y[3]);
+          pk.z = pack_bf16x2(y[4], y[5]); pk.w = pack_bf16x2(y[6], y[7]);
+          *reinterpret_cast<uint4*>(ob + stg_off(lane, t)) = pk;
         }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0 && valid) {
           tma_store_2d(&tmA, buf(0), cb, row0);
-          tma_store_2d(&tmA, buf(1), cb + 64, row0);
           bulk_commit_group();
         }
       }
@@ -443,6 +478,11 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
         }
       }
       __syncwarp();
+      EB_T(e_w2);
+    }
+    if (timing && lane == 0) {
+      g_eb_prof[0] += e_g1; g_eb_prof[1] += e_res; g_eb_prof[2] += e_w1; g_eb_prof[3] += e_af; g_eb_prof[4] += e_he;
+      g_eb_prof[5] += e_ff; g_eb_prof[6] += e_xf; g_eb_prof[7] += e_w2; g_eb_prof[8] += it;
     }
     if (lane == 0) bulk_wait_group<0>();
   }
@@ -466,14 +506,12 @@ int encode_kchunk_map(CUtensorMap* m, const void* base, int rows, int K, int box
 
 }  // namespace
 
-int launch_encoder_block(const void* o, float* x, void* a_out, const void* wo, const float* bo, const void* w1, const float* b1,
-                         const void* w2, const float* b2, const float* ln_mid_g, const float* ln_mid_b, const float* ln_out_g,
-                         const float* ln_out_b, int M, int FF, cudaStream_t stream) {
-  KIRI_REQUIRE(o && x && wo && bo && w1 && b1 && w2 && b2 && ln_mid_g && ln_mid_b, "encoder_block: null pointer");
-  KIRI_REQUIRE((ln_out_g == nullptr) == (ln_out_b == nullptr) && (ln_out_g == nullptr || a_out != nullptr),
-               "encoder_block: ln_out_g, ln_out_b and a_out go together");
+int launch_encoder_block(const void* o, float* x, void* a_out, const void* wo, const void* w1, const void* w2,
+                         const EbConst* consts_host, bool has_ln_out, int M, int FF, cudaStream_t stream) {
+  KIRI_REQUIRE(o && x && wo && w1 && w2 && consts_host, "encoder_block: null pointer");
+  KIRI_REQUIRE(!has_ln_out || a_out != nullptr, "encoder_block: LayerNorm output without a_out");
   KIRI_REQUIRE(M % 32 == 0, "encoder_block: token count %d must be a multiple of 32", M);
-  KIRI_REQUIRE(FF % 128 == 0 && FF >= 128, "encoder_block: FF width %d must be a multiple of 128", FF);
+  KIRI_REQUIRE(FF % 128 == 0 && FF >= 128 && FF <= 1024, "encoder_block: FF width %d must be a multiple of 128, at most 1024", FF);
   if (M == 0) return 0;
   const int sms = gemm_tc_num_sms();
   CUtensorMap tmO, tmWo, tmW1, tmW2, tmX, tmA;
@@ -483,10 +521,13 @@ int launch_encoder_block(const void* o, float* x, void* a_out, const void* wo, c
   if (encode_kchunk_map(&tmW2, w2, 256, FF, 256)) return -1;
   if (encode_rowtile_map(&tmX, x, M, 256, 256, true)) return -1;
   tmA = tmX;
-  if (ln_out_g && encode_rowtile_map(&tmA, a_out, M, 256, 256, false)) return -1;
+  if (has_ln_out && encode_rowtile_map(&tmA, a_out, M, 256, 256, false)) return -1;
   EbParams p;
-  p.bo = bo; p.b1 = b1; p.b2 = b2; p.ln_mid_g = ln_mid_g; p.ln_mid_b = ln_mid_b; p.ln_out_g = ln_out_g; p.ln_out_b = ln_out_b;
+  p.c = *consts_host;
+  p.has_ln_out = has_ln_out ? 1 : 0;
   p.M = M; p.n_tiles = (M + 127) / 128; p.nC = FF / 64;
+  static const int timing_on = getenv("KIRI_GEMM_TIMING") != nullptr;
+  p.timing = timing_on;
   const int smem = kBarOff + static_cast<int>(sizeof(EbBars));
   KIRI_REQUIRE(smem <= gemm_tc_max_smem(), "encoder_block: %d bytes of shared memory needed, %d available", smem, gemm_tc_max_smem());
   static bool configured = false;
@@ -499,12 +540,45 @@ int launch_encoder_block(const void* o, float* x, void* a_out, const void* wo, c
   return 0;
 }
 
+// host copy of the per-layer constants (device pointers -> EbConst); synchronous, done once per model
+int encoder_block_consts(EbConst* out, const float* bo, const float* b1, const float* b2, const float* ln_mid_g,
+                         const float* ln_mid_b, const float* ln_out_g, const float* ln_out_b, int FF) {
+  KIRI_REQUIRE(out && bo && b1 && b2 && ln_mid_g && ln_mid_b, "encoder_block_consts: null pointer");
+  KIRI_REQUIRE(FF > 0 && FF <= 1024, "encoder_block_consts: FF width %d exceeds 1024", FF);
+  memset(out, 0, sizeof(*out));
+  KIRI_CHECK_CUDA(cudaMemcpy(out->bo, bo, 256 * 4, cudaMemcpyDeviceToHost));
+  KIRI_CHECK_CUDA(cudaMemcpy(out->b2, b2, 256 * 4, cudaMemcpyDeviceToHost));
+  KIRI_CHECK_CUDA(cudaMemcpy(out->ln_mid_g, ln_mid_g, 256 * 4, cudaMemcpyDeviceToHost));
+  KIRI_CHECK_CUDA(cudaMemcpy(out->ln_mid_b, ln_mid_b, 256 * 4, cudaMemcpyDeviceToHost));
+  KIRI_CHECK_CUDA(cudaMemcpy(out->b1, b1, static_cast<size_t>(FF) * 4, cudaMemcpyDeviceToHost));
+  if (ln_out_g && ln_out_b) {
+    KIRI_CHECK_CUDA(cudaMemcpy(out->ln_out_g, ln_out_g, 256 * 4, cudaMemcpyDeviceToHost));
+    KIRI_CHECK_CUDA(cudaMemcpy(out->ln_out_b, ln_out_b, 256 * 4, cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+
 }  // namespace kiri
 
 extern "C" int kiri_encoder_block(const void* o_bf16, float* x_f32, void* a_out_bf16, const void* wo, const float* bo,
                                   const void* w1, const float* b1, const void* w2, const float* b2, const float* ln_mid_g,
                                   const float* ln_mid_b, const float* ln_out_g, const float* ln_out_b, int M, int FF,
                                   cudaStream_t stream) {
-  return kiri::launch_encoder_block(o_bf16, x_f32, a_out_bf16, wo, bo, w1, b1, w2, b2, ln_mid_g, ln_mid_b, ln_out_g, ln_out_b, M,
-                                    FF, stream);
+  // stand-alone entry (tests, tools): the constants are fetched from the device on every call (synchronous);
+  // kiri_encode uses the copies made once by kiri_create
+  KIRI_REQUIRE((ln_out_g == nullptr) == (ln_out_b == nullptr), "kiri_encoder_block: ln_out_g and ln_out_b go together");
+  kiri::EbConst c;
+  KIRI_TRY(kiri::encoder_block_consts(&c, bo, b1, b2, ln_mid_g, ln_mid_b, ln_out_g, ln_out_b, FF));
+  return kiri::launch_encoder_block(o_bf16, x_f32, a_out_bf16, wo, w1, w2, &c, ln_out_g != nullptr, M, FF, stream);
+}
+
+// Debug: phase cycles of CTA 0 accumulated since the last call (KIRI_GEMM_TIMING=1).
+extern "C" int kiri_debug_eb_timing(long long* out_host, int n) {
+  long long buf[16];
+  if (cudaDeviceSynchronize() != cudaSuccess) return -2;
+  if (cudaMemcpyFromSymbol(buf, kiri::g_eb_prof, sizeof(buf)) != cudaSuccess) return -2;
+  for (int i = 0; i < n && i < 16; ++i) out_host[i] = buf[i];
+  long long zero[16] = {0};
+  if (cudaMemcpyToSymbol(kiri::g_eb_prof, zero, sizeof(zero)) != cudaSuccess) return -2;
+  return 0;
 }

@@ -4,12 +4,14 @@
 #include "gemm_tc.cuh"
 #include "kiri_b200.h"
 
+namespace kiri { struct EbConst; }
 struct KiriHandle {
   KiriDims d;
   KiriWeights w;
   float conv1_w[48 * 9];
   float conv1_b[48];
   void* fused;          // fragment-packed decoder weights of the fused decode kernel (decoder_fused.cu)
+  kiri::EbConst* enc_consts;   // [enc_layers] host copies of the encoder-tail constants (encoder_block.cu), or null
 };
 
 namespace kiri {
@@ -18,9 +20,13 @@ int gemm_call(const void* a, const void* w, const float* bias, int M, int N, int
               const float* resid, const float* ln_g, const float* ln_b, void* out2, cudaStream_t stream);
 
 // encoder_block.cu: out_proj + LN + FFN + LN of one encoder layer in one kernel
-int launch_encoder_block(const void* o, float* x, void* a_out, const void* wo, const float* bo, const void* w1, const float* b1,
-                         const void* w2, const float* b2, const float* ln_mid_g, const float* ln_mid_b, const float* ln_out_g,
-                         const float* ln_out_b, int M, int FF, cudaStream_t stream);
+struct EbConst {             // per-layer biases / LayerNorm affines, passed by value in the kernel parameters
+  float bo[256], b2[256], ln_mid_g[256], ln_mid_b[256], ln_out_g[256], ln_out_b[256], b1[1024];
+};
+int encoder_block_consts(EbConst* out, const float* bo, const float* b1, const float* b2, const float* ln_mid_g,
+                         const float* ln_mid_b, const float* ln_out_g, const float* ln_out_b, int FF);
+int launch_encoder_block(const void* o, float* x, void* a_out, const void* wo, const void* w1, const void* w2,
+                         const EbConst* consts_host, bool has_ln_out, int M, int FF, cudaStream_t stream);
 
 // decoder_fused.cu: whole-decode persistent cluster kernel
 struct FusedBeam {           // beam-search mode of the fused decoder (nullptr = greedy)

@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_kernels_gpu.py -m gpu -q -x -k "encoder_block" > gpurun_out/pytest_eb.log 2>&1
+echo "== encoder_block rc=$?"; grep -E "passed|failed|FAILED|Error|assert|timeout|kiri:" gpurun_out/pytest_eb.log | tail -12
+timeout 200 python tools/eb_timing.py > gpurun_out/eb_timing.log 2>&1; echo rc=$?; cat gpurun_out/eb_timing.log

@@ -87,6 +87,12 @@ int kiri_preprocess_pack(const uint8_t* src, const KiriCropDesc* descs, int n_cr
  * (48 + 16 zero).  W must be a multiple of 128. */
 int kiri_conv1(const uint8_t* planes_u8, const float* w_host, const float* b_host, int n_lines, int H,
                int W, void* out_bf16_nhwc64, cudaStream_t stream);
+/* The two forms of the layer by name: fp32 FMAs on the CUDA cores (the default of kiri_conv1) and warp-level
+ * tensor-core MMAs on exact bf16 operands (u = v - 128, split weights; opt-in with KIRI_CONV1_TC=1, measured slower). */
+int kiri_conv1_tc(const uint8_t* planes_u8, const float* w_host, const float* b_host, int n_lines, int H,
+                  int W, void* out_bf16_nhwc64, cudaStream_t stream);
+int kiri_conv1_ffma(const uint8_t* planes_u8, const float* w_host, const float* b_host, int n_lines, int H,
+                    int W, void* out_bf16_nhwc64, cudaStream_t stream);
 
 /* K2+K3 fused: stem layers 1 and 2 in one kernel (ConvStem.net[0:6], kiri_ocr/model.py:215-220): the
  * 48-channel activation never leaves the SM.  planes_u8 [n, H, W] (H % 4 == 0, W % 128 == 0),

@@ -10,6 +10,8 @@
 #include "common.cuh"
 #include "kiri_b200.h"
 
+#include <cstring>
+
 namespace kiri {
 
 static constexpr int kC1 = 48;
@@ -82,12 +84,134 @@ conv1_bn_silu_kernel(const uint8_t* __restrict__ planes, __nv_bfloat16* __restri
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Tensor-core form (opt-in, KIRI_CONV1_TC=1; measured 11 % SLOWER than the FFMA kernel above, see kiri_conv1).
+// The 9-tap products run on warp-level mma.sync m16n8k16; what remains is the SiLU epilogue and the
+// 128 B/pixel store, which also bound the FFMA form.  Exactness is kept without fp32
+// operands: with u = v - 128 for in-image taps and u = -0.5 for padded taps (both exact in bf16),
+//     (v/255 - 0.5)/0.5 = (u + 0.5)/127.5      and the conv padding value 0 <-> u = -0.5,
+// so  out[c] = b[c] + 0.5*sum_k w'[c][k] + sum_k w'[c][k]*u_k,   w' = w/127.5 = w'_hi + w'_lo (two bf16).
+// A = [16 pixels x 16 taps (9 used)], B = [taps x 8 channels]; two k-steps (hi, lo weights) per n-tile.
+// Products of two bf16 are exact in the fp32 accumulator, the weight split leaves 2^-17 relative error.
+struct Conv1TcParams {
+  uint32_t bfrag[6][2][32][2];   // B fragments in mma register order: [n-tile][hi|lo][lane][reg]
+  float bias[kC1];               // b[c] + 0.5 * sum_k w'[c][k]
+};
+
+__device__ __forceinline__ void mma16816_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                              uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+static constexpr int kPatchPitch = 136;     // 128 + 2 halo columns, padded
+
+__global__ void __launch_bounds__(kConv1Threads, 8)
+conv1_tc_kernel(const uint8_t* __restrict__ planes, __nv_bfloat16* __restrict__ out, int H, int W, int total_tiles,
+                const __grid_constant__ Conv1TcParams p) {
+  __shared__ __align__(16) unsigned short s_patch[3 * kPatchPitch];          // bf16 bits of u
+  __shared__ __align__(16) uint8_t s_out[kConv1Threads * kC1Pad * 2];        // 16 KiB staging tile [pixel][128 B]
+  __shared__ __align__(8) uint32_t s_bfrag[6 * 2 * 32 * 2];                  // B fragments, lane-contiguous
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  for (int i = tid; i < 6 * 2 * 32 * 2; i += kConv1Threads) s_bfrag[i] = (&p.bfrag[0][0][0][0])[i];
+  float bs[6][2];                                   // biases of this thread's channels 8j + 2t, 8j + 2t + 1
+#pragma unroll
+  for (int j = 0; j < 6; ++j) { bs[j][0] = p.bias[8 * j + 2 * t]; bs[j][1] = p.bias[8 * j + 2 * t + 1]; }
+  // the 16 zero channels (chunks 6, 7 of every pixel row) are written once: no other store touches them
+  for (int i = tid; i < kConv1Threads * 2; i += kConv1Threads) {
+    const int px = i >> 1, j = 6 + (i & 1);
+    reinterpret_cast<uint4*>(s_out)[px * 8 + (j ^ (px & 7))] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  // taps 2t, 2t+1 of the 3x3 window as patch offsets (tap k = ky*3 + kx); tap 8 belongs to t == 0
+  const int k0 = 2 * t, k1 = 2 * t + 1;
+  const int o0 = (k0 / 3) * kPatchPitch + (k0 % 3), o1 = (k1 / 3) * kPatchPitch + (k1 % 3);
+  const int o8 = 2 * kPatchPitch + 2;
+  pdl_trigger();
+  pdl_wait();                                       // the planes come from the previous kernel
+  const int tiles_per_row = W / kConv1Threads;
+  const unsigned short kPad = 0xBF00;               // bf16(-0.5): the reference's zero padding
+  // the 3 x 130 patch of a tile is fetched into registers one tile ahead (4 pixels per thread)
+  unsigned short nxt[4];
+  auto fetch = [&](int tile) {
+    const int xt = tile % tiles_per_row, by = tile / tiles_per_row;
+    const int y = by % H, b = by / H, x0 = xt * kConv1Threads;
+    const uint8_t* img = planes + static_cast<size_t>(b) * H * W;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = tid + r * kConv1Threads;
+      const int ky = i / 130, c = i - ky * 130;
+      const int yy = y + ky - 1, xx = x0 - 1 + c;
+      const bool ok = (i < 3 * 130) && (yy >= 0) && (yy < H) && (xx >= 0) && (xx < W);
+      nxt[r] = ok ? __bfloat16_as_ushort(__float2bfloat16(static_cast<float>(__ldg(img + yy * W + xx)) - 128.0f)) : kPad;   // exact
+    }
+  };
+  if (static_cast<int>(blockIdx.x) < total_tiles) fetch(blockIdx.x);
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int xt = tile % tiles_per_row;
+    const int by = tile / tiles_per_row;            // b * H + y
+    const int x0 = xt * kConv1Threads;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = tid + r * kConv1Threads;
+      if (i < 3 * 130) { const int ky = i / 130; s_patch[ky * kPatchPitch + (i - ky * 130)] = nxt[r]; }
+    }
+    __syncthreads();                                // patch complete; the previous tile's copy-out has read s_out
+    if (tile + static_cast<int>(gridDim.x) < total_tiles) fetch(tile + gridDim.x);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const int pa = warp * 32 + mt * 16 + g, pb = pa + 8;      // this thread's two pixels of the m-tile
+      const uint32_t a0 = static_cast<uint32_t>(s_patch[pa + o0]) | (static_cast<uint32_t>(s_patch[pa + o1]) << 16);
+      const uint32_t a1 = static_cast<uint32_t>(s_patch[pb + o0]) | (static_cast<uint32_t>(s_patch[pb + o1]) << 16);
+      const uint32_t a2 = t == 0 ? static_cast<uint32_t>(s_patch[pa + o8]) : 0u;
+      const uint32_t a3 = t == 0 ? static_cast<uint32_t>(s_patch[pb + o8]) : 0u;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const uint2 bh = *reinterpret_cast<const uint2*>(&s_bfrag[((j * 2 + 0) * 32 + lane) * 2]);
+        const uint2 bl = *reinterpret_cast<const uint2*>(&s_bfrag[((j * 2 + 1) * 32 + lane) * 2]);
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+        mma16816_bf16(c, a0, a1, a2, a3, bl.x, bl.y);           // low weight halves first
+        mma16816_bf16(c, a0, a1, a2, a3, bh.x, bh.y);
+        const uint32_t va = pack_bf16x2(silu_fast(c[0] + bs[j][0]), silu_fast(c[1] + bs[j][1]));
+        const uint32_t vb = pack_bf16x2(silu_fast(c[2] + bs[j][0]), silu_fast(c[3] + bs[j][1]));
+        *reinterpret_cast<uint32_t*>(s_out + pa * 128 + ((j ^ (pa & 7)) << 4) + t * 4) = va;
+        *reinterpret_cast<uint32_t*>(s_out + pb * 128 + ((j ^ (pb & 7)) << 4) + t * 4) = vb;
+      }
+    }
+    __syncthreads();                                // staging tile complete; everyone is done with s_patch
+    const uint4* so = reinterpret_cast<const uint4*>(s_out);
+    uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(by) * W + x0) * kC1Pad);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int q = i * kConv1Threads + tid;
+      const int px = q >> 3, j = q & 7;
+      dst[q] = so[px * 8 + (j ^ (px & 7))];
+    }
+  }
+}
+
+static uint16_t host_bf16_rn(float f) {            // round-to-nearest-even fp32 -> bf16 bits
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>(u >> 16);
+}
+static float host_bf16_to_f(uint16_t h) {
+  const uint32_t u = static_cast<uint32_t>(h) << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
 }  // namespace kiri
 
 using namespace kiri;
 
-extern "C" int kiri_conv1(const uint8_t* planes_u8, const float* w_host, const float* b_host, int n_lines,
-                          int H, int W, void* out_bf16_nhwc64, cudaStream_t stream) {
+extern "C" int kiri_conv1_ffma(const uint8_t* planes_u8, const float* w_host, const float* b_host, int n_lines,
+                               int H, int W, void* out_bf16_nhwc64, cudaStream_t stream) {
   KIRI_REQUIRE(planes_u8 && w_host && b_host && out_bf16_nhwc64, "kiri_conv1: null pointer");
   KIRI_REQUIRE(W % kConv1Threads == 0, "kiri_conv1: width %d must be a multiple of %d", W, kConv1Threads);
   if (n_lines == 0) return 0;
@@ -98,5 +222,65 @@ extern "C" int kiri_conv1(const uint8_t* planes_u8, const float* w_host, const f
   KIRI_REQUIRE(tiles < 0x7fffffffll, "kiri_conv1: grid too large");
   KIRI_CHECK_CUDA(launch_pdl(conv1_bn_silu_kernel, dim3(static_cast<unsigned>(tiles)), dim3(kConv1Threads), 0, stream,
                              planes_u8, reinterpret_cast<__nv_bfloat16*>(out_bf16_nhwc64), H, W, p));
+  return 0;
+}
+
+extern "C" int kiri_conv1_tc(const uint8_t* planes_u8, const float* w_host, const float* b_host, int n_lines,
+                             int H, int W, void* out_bf16_nhwc64, cudaStream_t stream);
+
+extern "C" int kiri_conv1(const uint8_t* planes_u8, const float* w_host, const float* b_host, int n_lines,
+                          int H, int W, void* out_bf16_nhwc64, cudaStream_t stream) {
+  // Measured on the B200 (256 bucketed lines): FFMA form 0.211 ms, tensor-core form 0.235 ms — the layer is bound
+  // by the 48 SiLUs + the 128-byte store per pixel, not by the 432 FMAs, and the FFMA kernel keeps more warps
+  // resident (56 vs 63 registers, no per-tile fragment traffic).  The tensor-core form stays as an opt-in.
+  static const bool use_tc = getenv("KIRI_CONV1_TC") != nullptr;
+  if (!use_tc) return kiri_conv1_ffma(planes_u8, w_host, b_host, n_lines, H, W, out_bf16_nhwc64, stream);
+  return kiri_conv1_tc(planes_u8, w_host, b_host, n_lines, H, W, out_bf16_nhwc64, stream);
+}
+
+extern "C" int kiri_conv1_tc(const uint8_t* planes_u8, const float* w_host, const float* b_host, int n_lines,
+                             int H, int W, void* out_bf16_nhwc64, cudaStream_t stream) {
+  KIRI_REQUIRE(planes_u8 && w_host && b_host && out_bf16_nhwc64, "kiri_conv1: null pointer");
+  KIRI_REQUIRE(W % kConv1Threads == 0, "kiri_conv1: width %d must be a multiple of %d", W, kConv1Threads);
+  if (n_lines == 0) return 0;
+  // fragment table: a few thousand flops on the host, cached for the (single) weight set of a process
+  static Conv1TcParams cached;
+  static const float* cached_w = nullptr;
+  static float cached_w0 = 0.f, cached_b0 = 0.f;
+  if (cached_w != w_host || cached_w0 != w_host[0] || cached_b0 != b_host[0]) {
+    uint16_t hi[kC1][16], lo[kC1][16];
+    for (int c = 0; c < kC1; ++c) {
+      double half_sum = 0.0;
+      for (int k = 0; k < 16; ++k) {
+        const float wp = k < 9 ? w_host[c * 9 + k] / 127.5f : 0.f;
+        hi[c][k] = host_bf16_rn(wp);
+        lo[c][k] = host_bf16_rn(wp - host_bf16_to_f(hi[c][k]));
+        half_sum += 0.5 * (static_cast<double>(host_bf16_to_f(hi[c][k])) + static_cast<double>(host_bf16_to_f(lo[c][k])));
+      }
+      cached.bias[c] = static_cast<float>(static_cast<double>(b_host[c]) + half_sum);
+    }
+    for (int j = 0; j < 6; ++j)
+      for (int h = 0; h < 2; ++h)
+        for (int lane = 0; lane < 32; ++lane) {
+          const int g = lane >> 2, t = lane & 3, c = 8 * j + g;
+          const uint16_t(*w)[16] = h == 0 ? hi : lo;
+          cached.bfrag[j][h][lane][0] = static_cast<uint32_t>(w[c][2 * t]) | (static_cast<uint32_t>(w[c][2 * t + 1]) << 16);
+          cached.bfrag[j][h][lane][1] = static_cast<uint32_t>(w[c][2 * t + 8]) | (static_cast<uint32_t>(w[c][2 * t + 9]) << 16);
+        }
+    cached_w = w_host; cached_w0 = w_host[0]; cached_b0 = b_host[0];
+  }
+  const long long tiles = static_cast<long long>(n_lines) * H * (W / kConv1Threads);
+  KIRI_REQUIRE(tiles < 0x7fffffffll, "kiri_conv1: grid too large");
+  static int sms = 0;
+  if (sms == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  static bool carveout_set = false;
+  if (!carveout_set) {
+    cudaFuncSetAttribute(conv1_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    carveout_set = true;
+  }
+  const long long cap = static_cast<long long>(sms) * 8;           // 8 resident CTAs per SM, each walks its tiles
+  const unsigned grid = static_cast<unsigned>(tiles < cap ? tiles : cap);
+  KIRI_CHECK_CUDA(launch_pdl(conv1_tc_kernel, dim3(grid), dim3(kConv1Threads), 0, stream, planes_u8,
+                             reinterpret_cast<__nv_bfloat16*>(out_bf16_nhwc64), H, W, static_cast<int>(tiles), cached));
   return 0;
 }

@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_kernels_gpu.py tests/test_engine_gpu.py -m gpu -q -x > gpurun_out/pytest_k.log 2>&1
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_k.log 2>&1
 echo "== kernels+engine rc=$?"; grep -E "passed|failed|FAILED|Error" gpurun_out/pytest_k.log | tail -8
 KIRI_GEMM_TIMING=1 timeout 300 python tools/gemm_timing.py > gpurun_out/gemm_timing.log 2>&1; echo "rc=$?"; cat gpurun_out/gemm_timing.log
 timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "== bench rc=$?"

@@ -145,8 +145,9 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
               else { is_w1 = false; c = (m - 2) >> 1; }
               mbar_arrive_expect_tx(fb, 32768);
               if (is_w1) {
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) tma_load_3d(dst + kk * 8192, &tmW1, fb, 0, kk, 64 * c);
+                // ONE box {64 k, 64 rows, 4 K-chunks}: lands as four [64 x 128 B] K-major tiles.  (Four separate
+                // boxes cost the issuing thread ~350 cycles each and made this producer the FFN's bottleneck.)
+                tma_load_3d(dst, &tmW1, fb, 0, 64 * c, 0);
               } else {
                 tma_load_3d(dst, &tmW2, fb, 0, c, 0);
               }
@@ -517,7 +518,13 @@ int launch_encoder_block(const void* o, float* x, void* a_out, const void* wo, c
   CUtensorMap tmO, tmWo, tmW1, tmW2, tmX, tmA;
   if (encode_kchunk_map(&tmO, o, M, 256, 128)) return -1;
   if (encode_kchunk_map(&tmWo, wo, 256, 256, 256)) return -1;
-  if (encode_kchunk_map(&tmW1, w1, FF, 256, 64)) return -1;
+  {  // W1 [FF, 256]: dims (k 64, row, K-chunk) so that a {64, 64, 4} box is four consecutive K-major tiles
+    cuuint64_t dims[3] = {64, (cuuint64_t)FF, 4};
+    cuuint64_t str[2] = {512, 128};
+    cuuint32_t box[3] = {64, 64, 4};
+    cuuint32_t es[3] = {1, 1, 1};
+    if (encode_map(&tmW1, w1, 3, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
+  }
   if (encode_kchunk_map(&tmW2, w2, 256, FF, 256)) return -1;
   if (encode_rowtile_map(&tmX, x, M, 256, 256, true)) return -1;
   tmA = tmX;

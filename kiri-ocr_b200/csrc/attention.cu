@@ -32,6 +32,13 @@ __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+// 2^x in one MUFU (arguments are <= 0 here; results below 2^-126 flush to zero, which a soft-max wants anyway)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // shared tile [rows][32 bf16] = 4 x 16-byte chunks per row, chunk index XOR-swizzled by row
 __device__ __forceinline__ uint32_t tile_off(int row, int chunk) {
   return static_cast<uint32_t>(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
@@ -55,21 +62,10 @@ struct AttnGroups {
 };
 
 template <int T, int QR>
-__device__ __forceinline__ void attn_tile(const __nv_bfloat16* __restrict__ base, __nv_bfloat16* __restrict__ obase, const int q0,
-                                          const int D, const int klen, const bool masked, uint8_t* s_q, uint8_t* s_k,
-                                          uint8_t* s_v) {
+__device__ __forceinline__ void attn_tile(__nv_bfloat16* __restrict__ obase, const int q0, const int D, const int klen,
+                                          const bool masked, const uint8_t* s_q, const uint8_t* s_k, const uint8_t* s_v) {
   constexpr int NB = T / 8;          // key blocks of 8
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const size_t ld = static_cast<size_t>(3) * D;
-  for (int idx = tid; idx < 2 * T * 4 + QR * 4; idx += kAttnThreads) {
-    int which, r, rl, c;
-    if (idx < 2 * T * 4) { which = 1 + idx / (T * 4); const int rem = idx % (T * 4); r = rem >> 2; rl = r; c = rem & 3; }
-    else { which = 0; const int rem = idx - 2 * T * 4; rl = rem >> 2; r = q0 + rl; c = rem & 3; }
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + r * ld + which * D + c * 8));
-    uint8_t* dst = which == 0 ? s_q : (which == 1 ? s_k : s_v);
-    *reinterpret_cast<uint4*>(dst + tile_off(rl, c)) = v;
-  }
-  __syncthreads();
   if (warp >= QR / 16) return;
 
   const int ml = warp * 16;                       // first query row of this warp inside s_q
@@ -119,10 +115,10 @@ __device__ __forceinline__ void attn_tile(const __nv_bfloat16* __restrict__ base
   float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
   for (int nb = 0; nb < NB; ++nb) {
-    s[nb][0] = exp2f(fmaf(s[nb][0], sl2, -o0));
-    s[nb][1] = exp2f(fmaf(s[nb][1], sl2, -o0));
-    s[nb][2] = exp2f(fmaf(s[nb][2], sl2, -o1));
-    s[nb][3] = exp2f(fmaf(s[nb][3], sl2, -o1));
+    s[nb][0] = ex2_approx(fmaf(s[nb][0], sl2, -o0));
+    s[nb][1] = ex2_approx(fmaf(s[nb][1], sl2, -o0));
+    s[nb][2] = ex2_approx(fmaf(s[nb][2], sl2, -o1));
+    s[nb][3] = ex2_approx(fmaf(s[nb][3], sl2, -o1));
     sum0 += s[nb][0] + s[nb][1];
     sum1 += s[nb][2] + s[nb][3];
   }
@@ -162,36 +158,88 @@ __device__ __forceinline__ void attn_tile(const __nv_bfloat16* __restrict__ base
   }
 }
 
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+static constexpr int kAttnBufBytes = (96 + 2 * 160) * 64;     // Q (<= 96 rows) | K | V of one work item
+
+struct AttnItem { int T, q0, qr, klen; const __nv_bfloat16* base; __nv_bfloat16* obase; };
+
+// Persistent CTAs: the Q/K/V slices of the NEXT (line, head, half) stream into the other shared-memory
+// buffer with cp.async while the current one is computed (the one-shot form spent 48 % of its issue slots
+// in long-scoreboard stalls on these loads at 25 % occupancy, profiles/r01_ncu_full_summary_v2.json).
 __global__ void __launch_bounds__(kAttnThreads, 3)
 encoder_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, const int D, const int heads,
-                         const int* __restrict__ kv_len, const __grid_constant__ AttnGroups G) {
-  __shared__ __align__(128) uint8_t s_q[96 * 64];
-  __shared__ __align__(128) uint8_t s_k[160 * 64];
-  __shared__ __align__(128) uint8_t s_v[160 * 64];
-  int gi = 0;
+                         const int* __restrict__ kv_len, const int total_items, const __grid_constant__ AttnGroups G) {
+  extern __shared__ __align__(128) uint8_t s_attn[];
+  const int tid = threadIdx.x;
+  const bool masked = kv_len != nullptr;
+  auto decode = [&](int item) -> AttnItem {
+    int gi = 0;
 #pragma unroll
-  for (int i = 1; i < kAttnMaxGroups; ++i)
-    if (i < G.n && static_cast<int>(blockIdx.x) >= G.cta_begin[i]) gi = i;
-  const int T = G.T[gi];
-  const int halves = T > 96 ? 2 : 1;
-  int local = static_cast<int>(blockIdx.x) - G.cta_begin[gi];
-  const int half = local % halves;
-  local /= halves;
-  const int head = local % heads;
-  const int line = local / heads;
+    for (int i = 1; i < kAttnMaxGroups; ++i)
+      if (i < G.n && item >= G.cta_begin[i]) gi = i;
+    AttnItem w;
+    w.T = G.T[gi];
+    const int halves = w.T > 96 ? 2 : 1;
+    int local = item - G.cta_begin[gi];
+    const int half = local % halves;
+    local /= halves;
+    const int head = local % heads;
+    const int line = local / heads;
+    w.qr = w.T / halves;
+    w.q0 = half * w.qr;
+    const size_t row0 = static_cast<size_t>(G.row0[gi]) + static_cast<size_t>(line) * w.T;
+    w.base = qkv + row0 * 3 * D + head * kHd;
+    w.obase = out + row0 * D + head * kHd;
+    w.klen = masked ? kv_len[G.line0[gi] + line] : w.T;
+    return w;
+  };
+  auto issue_load = [&](const AttnItem& w, uint8_t* bufp) {
+    const uint32_t sq = smem_u32(bufp), sk = sq + 96 * 64, sv = sk + 160 * 64;
+    const size_t ld = static_cast<size_t>(3) * D;
+    const int nkv = 2 * w.T * 4, total = nkv + w.qr * 4;
+    for (int idx = tid; idx < total; idx += kAttnThreads) {
+      int which, r, rl;
+      const int c = idx & 3;
+      if (idx < nkv) { const int rr = idx >> 2; which = rr >= w.T ? 2 : 1; r = rr - (which - 1) * w.T; rl = r; }
+      else { which = 0; rl = (idx - nkv) >> 2; r = w.q0 + rl; }
+      const uint32_t dst = (which == 0 ? sq : (which == 1 ? sk : sv)) + tile_off(rl, c);
+      cp_async16(dst, w.base + r * ld + which * D + c * 8);
+    }
+  };
   pdl_trigger();
   pdl_wait();                                       // qkv comes from the previous kernel
-  const size_t row0 = static_cast<size_t>(G.row0[gi]) + static_cast<size_t>(line) * T;
-  const __nv_bfloat16* base = qkv + row0 * 3 * D + head * kHd;
-  __nv_bfloat16* obase = out + row0 * D + head * kHd;
-  const bool masked = kv_len != nullptr;
-  const int klen = masked ? kv_len[G.line0[gi] + line] : T;
-  switch (T) {
-    case 32:  attn_tile<32, 32>(base, obase, 0, D, klen, masked, s_q, s_k, s_v); break;
-    case 64:  attn_tile<64, 64>(base, obase, 0, D, klen, masked, s_q, s_k, s_v); break;
-    case 96:  attn_tile<96, 96>(base, obase, 0, D, klen, masked, s_q, s_k, s_v); break;
-    case 128: attn_tile<128, 64>(base, obase, half * 64, D, klen, masked, s_q, s_k, s_v); break;
-    default:  attn_tile<160, 80>(base, obase, half * 80, D, klen, masked, s_q, s_k, s_v); break;
+  int item = blockIdx.x;
+  int b = 0;
+  AttnItem cur = {};
+  if (item < total_items) { cur = decode(item); issue_load(cur, s_attn); }
+  cp_async_commit();
+  while (item < total_items) {
+    const int nxt_item = item + gridDim.x;
+    AttnItem nxt = {};
+    if (nxt_item < total_items) { nxt = decode(nxt_item); issue_load(nxt, s_attn + (b ^ 1) * kAttnBufBytes); }
+    cp_async_commit();
+    cp_async_wait<1>();                             // everything but the newest group has landed
+    __syncthreads();
+    const uint8_t* s_q = s_attn + b * kAttnBufBytes;
+    const uint8_t* s_k = s_q + 96 * 64;
+    const uint8_t* s_v = s_k + 160 * 64;
+    switch (cur.T) {
+      case 32:  attn_tile<32, 32>(cur.obase, cur.q0, D, cur.klen, masked, s_q, s_k, s_v); break;
+      case 64:  attn_tile<64, 64>(cur.obase, cur.q0, D, cur.klen, masked, s_q, s_k, s_v); break;
+      case 96:  attn_tile<96, 96>(cur.obase, cur.q0, D, cur.klen, masked, s_q, s_k, s_v); break;
+      case 128: attn_tile<128, 64>(cur.obase, cur.q0, D, cur.klen, masked, s_q, s_k, s_v); break;
+      default:  attn_tile<160, 80>(cur.obase, cur.q0, D, cur.klen, masked, s_q, s_k, s_v); break;
+    }
+    __syncthreads();                                // buffer b is refilled by the next iteration's loads
+    cur = nxt;
+    item = nxt_item;
+    b ^= 1;
   }
 }
 
@@ -235,16 +283,19 @@ extern "C" int kiri_encoder_attention_multi(const void* qkv_bf16, void* out_bf16
     KIRI_REQUIRE(ctas < 0x7fffffffll, "kiri_encoder_attention_multi: grid too large");
   }
   for (int i = n_used; i <= kAttnMaxGroups; ++i) G.cta_begin[i] = static_cast<int>(ctas);
-  static bool carveout_set = false;
-  if (!carveout_set) {
-    // several CTAs per SM need the large shared-memory carve-out (the driver's default for a
-    // 26 KB static kernel was a 32 KB configuration = one resident CTA)
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    KIRI_CHECK_CUDA(cudaFuncSetAttribute(encoder_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kAttnBufBytes));
     cudaFuncSetAttribute(encoder_attention_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    carveout_set = true;
   }
-  KIRI_CHECK_CUDA(launch_pdl(encoder_attention_kernel, dim3(static_cast<unsigned>(ctas)), dim3(kAttnThreads), 0, stream,
+  const long long cap = static_cast<long long>(sms) * 3;          // three resident CTAs per SM walk the work items
+  const unsigned grid = static_cast<unsigned>(ctas < cap ? ctas : cap);
+  KIRI_CHECK_CUDA(launch_pdl(encoder_attention_kernel, dim3(grid), dim3(kAttnThreads), 2 * kAttnBufBytes, stream,
                              reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), reinterpret_cast<__nv_bfloat16*>(out_bf16), D, heads,
-                             kv_len, G));
+                             kv_len, static_cast<int>(ctas), G));
   KIRI_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

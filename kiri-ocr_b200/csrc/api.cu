@@ -126,9 +126,8 @@ extern "C" int kiri_gemm_bf16(const void* a, const void* w, const float* bias, i
   return gemm_call(a, w, bias, M, N, K, epi, out, resid, ln_g, ln_b, out2, stream);
 }
 
-static int conv_call(const void* in, const void* w, const float* bias, int n, int IH, int IW, int Cin, int N,
-                     int sh, int sw, void* out, cudaStream_t stream) {
-  if (n == 0) return 0;
+static GemmLaunch conv_launch(const void* in, const void* w, const float* bias, int n, int IH, int IW, int Cin, int N,
+                              int sh, int sw, void* out) {
   GemmLaunch L;
   memset(&L, 0, sizeof(L));
   L.a = in; L.w = w;
@@ -137,7 +136,12 @@ static int conv_call(const void* in, const void* w, const float* bias, int n, in
   L.sw = sw; L.sh = sh; L.pad = 1; L.kw = 3; L.kh = 3;
   L.N = N; L.epi = EPI_BIAS_SILU_BF16;
   L.e.out = out; L.e.bias = bias; L.e.resid = nullptr; L.e.ldc = N; L.e.n_valid = N;
-  return launch_gemm_tc(L, stream);
+  return L;
+}
+static int conv_call(const void* in, const void* w, const float* bias, int n, int IH, int IW, int Cin, int N,
+                     int sh, int sw, void* out, cudaStream_t stream) {
+  if (n == 0) return 0;
+  return launch_gemm_tc(conv_launch(in, w, bias, n, IH, IW, Cin, N, sh, sw, out), stream);
 }
 
 extern "C" int kiri_stem12(const uint8_t* planes_u8, const float* conv1_w_host, const float* conv1_b_host, const void* conv2_w48,
@@ -202,6 +206,8 @@ extern "C" void kiri_destroy(KiriHandle* h) {
 namespace {
 struct EncodeWs {          // byte offsets into the caller's workspace
   size_t act1, act2, act3, act4, x, a, qkv, o, hbuf, total;
+  size_t g1[8], g2[8], g3[8], g4[8];   // per-group offsets inside act1..act4 (sub-batch buffers / whole-group act4)
+  int sc[8];                           // lines per stem sub-batch of each group
   long long m_total;       // tokens of all groups
 };
 inline size_t al(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
@@ -218,23 +224,25 @@ inline int stem_sub_batch(int B, int Wb, int stem_chunk) {
   return (B + n_chunks - 1) / n_chunks;
 }
 
-// Workspace of a multi-group encode: the stem buffers are sized for the largest sub-batch of any
-// group, the token-stream buffers for the concatenation of all groups.
+// Workspace of a multi-group encode: every group has its own stem buffers (one sub-batch each — the
+// conv layers of all groups share launches), the token-stream buffers hold the concatenation of all groups.
 EncodeWs plan_encode(const KiriDims& d, const KiriGroup* groups, int n_groups, int stem_chunk) {
   const int H = d.img_h;
   size_t a1 = 0, a2 = 0, a3 = 0, a4 = 0;
   long long M = 0;
-  for (int g = 0; g < n_groups; ++g) {
+  EncodeWs w;
+  memset(&w, 0, sizeof(w));
+  for (int g = 0; g < n_groups && g < 8; ++g) {
     const int B = groups[g].n_lines, Wb = groups[g].Wb;
     const int sc = stem_sub_batch(B, Wb, stem_chunk);
     const size_t T = Wb / 4;
-    a1 = std::max(a1, static_cast<size_t>(sc) * H * Wb * 64 * 2);
-    a2 = std::max(a2, static_cast<size_t>(sc) * (H / 2) * (Wb / 2) * 96 * 2);
-    a3 = std::max(a3, static_cast<size_t>(sc) * (H / 4) * (Wb / 4) * 160 * 2);
-    a4 = std::max(a4, static_cast<size_t>(B) * (H / 8) * T * 256 * 2);
+    w.sc[g] = sc;
+    w.g1[g] = a1; a1 += al(static_cast<size_t>(sc) * H * Wb * 64 * 2);
+    w.g2[g] = a2; a2 += al(static_cast<size_t>(sc) * (H / 2) * (Wb / 2) * 96 * 2);
+    w.g3[g] = a3; a3 += al(static_cast<size_t>(sc) * (H / 4) * (Wb / 4) * 160 * 2);
+    w.g4[g] = a4; a4 += al(static_cast<size_t>(B) * (H / 8) * T * 256 * 2);
     M += static_cast<long long>(B) * T;
   }
-  EncodeWs w;
   size_t off = 0;
   w.act1 = off; off += al(a1);
   w.act2 = off; off += al(a2);
@@ -291,39 +299,54 @@ extern "C" int kiri_encode_multi(KiriHandle* h, const KiriGroup* groups, int n_g
   float* x = reinterpret_cast<float*>(base + ws.x);
   uint8_t* a = base + ws.a;
 
+  KIRI_REQUIRE(n_groups <= 8, "kiri_encode_multi: at most 8 width groups");
   // conv1 fused into conv2 (stem12_kernel) is correct and tested but measured SLOWER than the two
   // kernels (0.99 vs 0.81 ms per 256 lines at 640 px): conv1 costs ~8.7 k cycles of CUDA-core work per
   // 128-output tile even on 16 producer warps and cannot overlap anything but 1.3 k cycles of MMA,
   // while the standalone conv1 runs at 64 warps/SM (profiles/README.md).  Opt-in for experiments.
   static const bool no_stem12 = getenv("KIRI_STEM12") == nullptr;
-  // ---- per group: stem (in sub-batches), then pool + positional table + enc_ln_in (+ norm1 of layer 0)
-  // written at the group's row offset of the concatenated token stream
-  size_t row0 = 0;
-  for (int g = 0; g < n_groups; ++g) {
-    const int B = groups[g].n_lines, Wb = groups[g].Wb, T = Wb / 4;
-    const int sc = stem_sub_batch(B, Wb, stem_chunk);
-    for (int b0 = 0; b0 < B; b0 += sc) {
-      const int nb = (B - b0) < sc ? (B - b0) : sc;
+  // ---- stem: the sub-batches of all groups advance together, and every conv layer runs as ONE launch over
+  // the groups (per-group launches paid ~20 us each of prologue, tail and wave quantisation: 15 launches)
+  int rounds = 0;
+  for (int g = 0; g < n_groups; ++g) rounds = std::max(rounds, (groups[g].n_lines + ws.sc[g] - 1) / ws.sc[g]);
+  for (int r = 0; r < rounds; ++r) {
+    GemmLaunch L2[8], L3[8], L4[8];
+    int np = 0;
+    for (int g = 0; g < n_groups; ++g) {
+      const int B = groups[g].n_lines, Wb = groups[g].Wb, T = Wb / 4;
+      const int b0 = r * ws.sc[g];
+      if (b0 >= B) continue;
+      const int nb = std::min(ws.sc[g], B - b0);
+      uint8_t* a1 = base + ws.act1 + ws.g1[g];
+      uint8_t* a2 = base + ws.act2 + ws.g2[g];
+      uint8_t* a3 = base + ws.act3 + ws.g3[g];
+      uint8_t* a4 = base + ws.act4 + ws.g4[g] + static_cast<size_t>(b0) * (H / 8) * T * 256 * 2;
+      const uint8_t* planes = groups[g].planes + static_cast<size_t>(b0) * H * Wb;
       if (w.conv2_w48 && !no_stem12) {
         // layers 1+2 fused: the 48-channel activation never reaches HBM
         ProfScope ps(PS_CONV2, stream);
-        KIRI_TRY(launch_stem12(groups[g].planes + static_cast<size_t>(b0) * H * Wb, w.conv1_w_host, w.conv1_b_host, w.conv2_w48,
-                               w.conv2_b, nb, H, Wb, base + ws.act2, stream));
+        KIRI_TRY(launch_stem12(planes, w.conv1_w_host, w.conv1_b_host, w.conv2_w48, w.conv2_b, nb, H, Wb, a2, stream));
       } else {
-        { ProfScope ps(PS_CONV1, stream);
-          KIRI_TRY(kiri_conv1(groups[g].planes + static_cast<size_t>(b0) * H * Wb, w.conv1_w_host, w.conv1_b_host, nb, H, Wb,
-                              base + ws.act1, stream)); }
-        { ProfScope ps(PS_CONV2, stream);
-          KIRI_TRY(conv_call(base + ws.act1, w.conv2_w, w.conv2_b, nb, H, Wb, 64, 96, 2, 2, base + ws.act2, stream)); }
+        ProfScope ps(PS_CONV1, stream);
+        KIRI_TRY(kiri_conv1(planes, w.conv1_w_host, w.conv1_b_host, nb, H, Wb, a1, stream));
       }
-      { ProfScope ps(PS_CONV3, stream);
-        KIRI_TRY(conv_call(base + ws.act2, w.conv3_w, w.conv3_b, nb, H / 2, Wb / 2, 96, 160, 2, 2, base + ws.act3, stream)); }
-      { ProfScope ps(PS_CONV4, stream);
-        KIRI_TRY(conv_call(base + ws.act3, w.conv4_w, w.conv4_b, nb, H / 4, Wb / 4, 160, 256, 2, 1,
-                           base + ws.act4 + static_cast<size_t>(b0) * (H / 8) * T * 256 * 2, stream)); }
+      L2[np] = conv_launch(a1, w.conv2_w, w.conv2_b, nb, H, Wb, 64, 96, 2, 2, a2);
+      L3[np] = conv_launch(a2, w.conv3_w, w.conv3_b, nb, H / 2, Wb / 2, 96, 160, 2, 2, a3);
+      L4[np] = conv_launch(a3, w.conv4_w, w.conv4_b, nb, H / 4, Wb / 4, 160, 256, 2, 1, a4);
+      ++np;
     }
+    if (np == 0) continue;
+    if (!(w.conv2_w48 && !no_stem12)) { ProfScope ps(PS_CONV2, stream); KIRI_TRY(launch_gemm_tc_multi(L2, np, stream)); }
+    { ProfScope ps(PS_CONV3, stream); KIRI_TRY(launch_gemm_tc_multi(L3, np, stream)); }
+    { ProfScope ps(PS_CONV4, stream); KIRI_TRY(launch_gemm_tc_multi(L4, np, stream)); }
+  }
+  // ---- per group: pool + positional table + enc_ln_in (+ norm1 of layer 0), written at the group's row
+  // offset of the concatenated token stream
+  size_t row0 = 0;
+  for (int g = 0; g < n_groups; ++g) {
+    const int B = groups[g].n_lines, T = groups[g].Wb / 4;
     { ProfScope ps(PS_POOL_LN, stream);
-      KIRI_TRY(kiri_pool_pos_ln(base + ws.act4, w.pos_table, B, H / 8, T, D, w.enc_ln_in_g, w.enc_ln_in_b,
+      KIRI_TRY(kiri_pool_pos_ln(base + ws.act4 + ws.g4[g], w.pos_table, B, H / 8, T, D, w.enc_ln_in_g, w.enc_ln_in_b,
                                 w.enc[0].ln1_g, w.enc[0].ln1_b, x + row0 * D, a + row0 * D * 2, stream)); }
     row0 += static_cast<size_t>(B) * T;
   }

@@ -58,9 +58,8 @@ __device__ long long g_gemm_prof[16];
 
 template <int KC, int NSEG, int EPI, bool BSTAT>
 __global__ void __launch_bounds__(kNumThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
-               const __grid_constant__ CUtensorMap tmOut2, const ConvGeom g, const EpiParams e,
+gemm_tc_kernel(const __grid_constant__ ProblemSet P, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmOut2, const EpiParams e,
                const int bn, const int num_m_tiles, const int num_n_tiles, const int stages, const int CPS) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int kChunkBytes = KC * 2;
@@ -73,7 +72,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // carve: [resident B] | [stages][A: CPS chunk tiles][B: CPS chunk tiles] | staging | barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  const int num_chunks = g.taps * g.chunks_per_tap;          // K / KC
+  // Several problems of ONE layer (the width groups of a batch: same weights, kernel, strides, N) share a
+  // launch: the m-tiles of all problems form one range, a tile looks its problem up in P.mtile_begin.
+  // Fields that do not depend on the problem are read from problem 0.
+  const ConvGeom& g0 = P.g[0];
+  const int num_chunks = g0.taps * g0.chunks_per_tap;        // K / KC
   const uint32_t b_chunk_bytes = bn * kChunkBytes;
   const uint32_t b_res_bytes = BSTAT ? ((num_chunks * b_chunk_bytes + 1023u) & ~1023u) : 0u;
   const uint32_t a_stage_bytes = CPS * kATileBytes;
@@ -92,7 +95,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // contiguous, n-major tile range of this CTA: B changes at most twice per CTA
   const int t_begin = static_cast<int>(static_cast<long long>(blockIdx.x) * total_tiles / gridDim.x);
   const int t_end = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * total_tiles / gridDim.x);
-  const int num_kb = g.taps * g.cgs;
+  const int num_kb = g0.taps * g0.cgs;
   const bool timing = e.timing != 0 && blockIdx.x == 0;
 
   if (warp == kTmaWarp && lane == 0) {
@@ -109,9 +112,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int wq = 0; wq < kEpiWarps; ++wq)
       for (int r = 0; r < 4; ++r) mbar_init(&bars->res_full[wq][r], 1);
     fence_mbar_init();
-    tma_prefetch_desc(&tmA);
+    for (int i = 0; i < P.n; ++i) { tma_prefetch_desc(&P.tmA[i]); tma_prefetch_desc(&P.tmOut[i]); }
     tma_prefetch_desc(&tmB);
-    tma_prefetch_desc(&tmOut);
   }
   if (warp == kMmaWarp) {
     tmem_alloc(&bars->tmem_base, kTmemCols);
@@ -136,8 +138,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // an ELECT / R2UR.BROADCAST waterfall: ~640 cycles per stage, the bound of every GEMM of the model
     // (tools/tma_stream.cu, profiles/README.md).
     {
-      // one TMA box = one KC-channel chunk of one segment: R*SEG rows x (KC*2) B
-      const uint32_t box_bytes = g.R * g.SEG * kChunkBytes;
       int stage = 0;
       uint32_t phase = 0;
       int cur_n = -1, b_loads = 0;
@@ -147,7 +147,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       long long tt_all = tt0, acc_we = 0, acc_tt = 0;
       for (int tile = t_begin; tile < t_end; ++tile) {
         const int n_tile = tile / num_m_tiles;
-        const int m_tile = tile - n_tile * num_m_tiles;
+        const int gm_tile = tile - n_tile * num_m_tiles;
+        int pi = 0;
+#pragma unroll
+        for (int i = 1; i < kMaxProblems; ++i)
+          if (i < P.n && gm_tile >= P.mtile_begin[i]) pi = i;
+        const int m_tile = gm_tile - P.mtile_begin[pi];
+        const ConvGeom& g = P.g[pi];
+        const CUtensorMap* tmA = &P.tmA[pi];
+        // one TMA box = one KC-channel chunk of one segment: R*SEG rows x (KC*2) B
+        const uint32_t box_bytes = g.R * g.SEG * kChunkBytes;
         if (BSTAT && pw == 0 && n_tile != cur_n) {
           if (b_loads > 0) mbar_wait(&bars->b_empty, (b_loads - 1) & 1);   // MMAs on the old B retired
           if (elect_one()) {
@@ -192,7 +201,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int j = 0; j < NSEG; ++j) {
                 if (seg_b[j] >= 0)
-                  tma_load_5d(a_dst + (size_t)c * kATileBytes + (size_t)j * box_bytes, &tmA,
+                  tma_load_5d(a_dst + (size_t)c * kATileBytes + (size_t)j * box_bytes, tmA,
                               &bars->full[stage], 0, cg * CPS + c, seg_x[j] + kx, seg_y[j] + ky,
                               seg_b[j]);
               }
@@ -281,15 +290,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int half = ew >> 2;                      // column half (chunks are dealt round-robin)
     uint8_t* bufs = staging + ew * kNBuf * kBufBytes;
     uint32_t stg_cnt = 0;                          // staging tiles issued (for buffer rotation)
-    // first row of this warp inside the tile and its decomposition
+    // first row of this warp inside the tile and its decomposition (per problem)
     const int m0 = q * 32;
-    const int j = m0 / (g.R * g.SEG);
-    const int within = m0 - j * (g.R * g.SEG);
-    const int jj = within / g.SEG;
-    const int ii = within - jj * g.SEG;
-    auto tile_rows = [&](int tile, int& row0) -> bool {
+    auto tile_rows = [&](int tile, int& row0, int& pi) -> bool {
       const int n_tile = tile / num_m_tiles;
-      const int m_tile = tile - n_tile * num_m_tiles;
+      const int gm_tile = tile - n_tile * num_m_tiles;
+      pi = 0;
+#pragma unroll
+      for (int i = 1; i < kMaxProblems; ++i)
+        if (i < P.n && gm_tile >= P.mtile_begin[i]) pi = i;
+      const int m_tile = gm_tile - P.mtile_begin[pi];
+      const ConvGeom& g = P.g[pi];
+      const int j = m0 / (g.R * g.SEG);
+      const int within = m0 - j * (g.R * g.SEG);
+      const int jj = within / g.SEG;
+      const int ii = within - jj * g.SEG;
       const int s = m_tile * NSEG + j;
       row0 = 0;
       if (s >= g.n_seg_total) return false;
@@ -303,8 +318,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       return (oy < g.OH) && (ox < g.OW);
     };
     if (kResid && lane == 0 && t_begin < t_end) {
-      int row0;
-      if (tile_rows(t_begin, row0)) {
+      int row0, pi0;
+      if (tile_rows(t_begin, row0, pi0)) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           mbar_arrive_expect_tx(&bars->res_full[ew][c], kBufBytes);
@@ -321,8 +336,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n_tile = tile / num_m_tiles;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      int row0;
-      const bool valid = tile_rows(tile, row0);
+      int row0, pi;
+      const bool valid = tile_rows(tile, row0, pi);
+      const CUtensorMap* tmOut = &P.tmOut[pi];
       const int col_base = n_tile * bn;
       // stage this tile's bias slice in shared memory (overlaps the wait for the accumulator)
       float* sbias = bars->bias[acc];
@@ -376,7 +392,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
         if (lane == 0 && valid) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) tma_store_2d(&tmOut, bufs + c * kBufBytes, cb + c * 32, row0);
+          for (int c = 0; c < 4; ++c) tma_store_2d(tmOut, bufs + c * kBufBytes, cb + c * 32, row0);
           bulk_commit_group();
         }
         if (valid) ++res_tiles;
@@ -426,8 +442,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         // the residual of the next tile can land as soon as the stores have read the tiles
         if (lane == 0 && tile + 1 < t_end) {
-          int nrow0;
-          if (tile_rows(tile + 1, nrow0)) {
+          int nrow0, npi;
+          if (tile_rows(tile + 1, nrow0, npi)) {
             bulk_wait_group_read<0>();
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -484,7 +500,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           fence_proxy_async();
           __syncwarp();
           if (lane == 0 && valid) {
-            tma_store_2d(&tmOut, ob, col_base + c0, row0);
+            tma_store_2d(tmOut, ob, col_base + c0, row0);
             bulk_commit_group();
           }
           ++stg_cnt;
@@ -607,11 +623,11 @@ int encode_rowtile_map(CUtensorMap* m, const void* base, long long rows, int col
 }
 
 template <int KC, int NSEG, int EPI, bool BSTAT>
-static int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
-                       const CUtensorMap& tmRes, const CUtensorMap& tmOut2, const ConvGeom& g,
+static int launch_inst(const ProblemSet& P, const CUtensorMap& tmB, const CUtensorMap& tmRes, const CUtensorMap& tmOut2,
                        const EpiParams& e, int bn, int num_m_tiles, int num_n_tiles, int CPS, cudaStream_t stream) {
   constexpr bool kResid = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_RESID_LN);
   constexpr int kNBuf = kResid ? 4 : (BSTAT ? 1 : 2);
+  const ConvGeom& g = P.g[0];
   const int num_chunks = g.taps * g.chunks_per_tap;
   const int b_res = BSTAT ? ((num_chunks * bn * KC * 2 + 1023) & ~1023) : 0;
   const int stage_bytes = (CPS * kTileM * KC * 2 + (BSTAT ? 0 : CPS * bn * KC * 2) + 1023) & ~1023;
@@ -628,25 +644,17 @@ static int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   }
   int grid = num_m_tiles * num_n_tiles;
   if (grid > g_num_sms) grid = g_num_sms;
-  KIRI_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kNumThreads), smem, stream, tmA, tmB, tmOut, tmRes, tmOut2, g, e, bn,
-                             num_m_tiles, num_n_tiles, stages, CPS));
+  KIRI_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kNumThreads), smem, stream, P, tmB, tmRes, tmOut2, e, bn, num_m_tiles,
+                             num_n_tiles, stages, CPS));
   return 0;
 }
 
-int launch_gemm_tc(const GemmLaunch& L_in, cudaStream_t stream) {
-  GemmLaunch L = L_in;
-  static const int timing_on = getenv("KIRI_GEMM_TIMING") != nullptr;
-  L.e.timing = timing_on;
-  gemm_tc_num_sms();
-  KIRI_REQUIRE(L.Cin % 32 == 0, "gemm_tc: Cin=%d must be a multiple of 32", L.Cin);
-  KIRI_REQUIRE(L.e.bias != nullptr && L.e.out != nullptr, "gemm_tc: bias/out must not be null");
-  const bool is_gemm = (L.kw == 1 && L.kh == 1);
-  // 128-byte K rows whenever the channels allow; the residual/LayerNorm epilogues keep 128 KB of
-  // staging tiles, so their pipeline uses the half-size (64-byte) stages to still be 3 deep
-  const bool resid_epi = (L.epi == EPI_BIAS_RESID_F32 || L.epi == EPI_BIAS_RESID_LN);
-  const int KC = (L.Cin % 64 == 0 && !resid_epi) ? 64 : 32;
+// Geometry + tensor maps of one problem.  KC / NSEG / CPS are decided here and must agree between the
+// problems of one launch (the caller groups by NSEG).
+static int prep_problem(const GemmLaunch& L, bool is_gemm, int KC, ConvGeom* gp, int* nseg, int* cps, CUtensorMap* tmA,
+                        CUtensorMap* tmOut, int* num_m_tiles) {
+  ConvGeom& g = *gp;
   const int chunks = L.Cin / KC;
-  ConvGeom g;
   int NSEG = 1, CPS = 1;
   if (is_gemm) {
     KIRI_REQUIRE(L.IH == 1 && L.NB == 1 && L.OH == 1 && L.OW == L.IW, "gemm_tc: plain GEMM wants [1,1,M,K]");
@@ -678,21 +686,17 @@ int launch_gemm_tc(const GemmLaunch& L_in, cudaStream_t stream) {
   g.segs_per_row = (L.OW + g.SEG - 1) / g.SEG;
   g.segs_per_img = ((L.OH + g.R - 1) / g.R) * g.segs_per_row;
   g.n_seg_total = L.NB * g.segs_per_img;
-  const int num_m_tiles = (g.n_seg_total + NSEG - 1) / NSEG;
-  int bn = (L.N + 15) / 16 * 16;
-  if (bn > 256) bn = 256;
-  const int num_n_tiles = (L.N + bn - 1) / bn;
+  *num_m_tiles = (g.n_seg_total + NSEG - 1) / NSEG;
+  *nseg = NSEG;
+  *cps = CPS;
   KIRI_REQUIRE(g.SEG * g.sw <= 256 && g.R * g.sh <= 256, "gemm_tc: TMA box too large");
   KIRI_REQUIRE(L.e.n_valid == L.N, "gemm_tc: n_valid must equal N");
   const bool f32_out = (L.epi == EPI_BIAS_F32 || L.epi == EPI_BIAS_RESID_F32 || L.epi == EPI_BIAS_RESID_LN);
   KIRI_REQUIRE((static_cast<long long>(L.e.ldc) * (f32_out ? 4 : 2)) % 16 == 0,
                "gemm_tc: output row pitch must be a multiple of 16 bytes (ldc=%d)", L.e.ldc);
   KIRI_REQUIRE((reinterpret_cast<uintptr_t>(L.e.out) & 15) == 0, "gemm_tc: output must be 16-byte aligned");
-
-  // Tensor maps keep global strides ascending; a box covers ONE KC-channel chunk, so a box lands
-  // in shared memory as [rows][KC*2 B] — exactly the K-major swizzled operand tile.
-  // A: (cKC, chunk, W, H, image)
-  CUtensorMap tmA, tmB, tmOut, tmRes, tmOut2;
+  // Tensor maps: a box covers ONE KC-channel chunk, so a box lands in shared memory as [rows][KC*2 B] —
+  // exactly the K-major swizzled operand tile.  A: (cKC, chunk, W, H, image)
   const CUtensorMapSwizzle swz = (KC == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   {
     cuuint64_t dims[5] = {(cuuint64_t)KC, (cuuint64_t)chunks, (cuuint64_t)L.IW, (cuuint64_t)L.IH, (cuuint64_t)L.NB};
@@ -700,59 +704,117 @@ int launch_gemm_tc(const GemmLaunch& L_in, cudaStream_t stream) {
                          (cuuint64_t)L.IH * L.IW * L.Cin * 2};
     cuuint32_t box[5] = {(cuuint32_t)KC, 1, (cuuint32_t)(g.SEG * g.sw), (cuuint32_t)(g.R * g.sh), 1};
     cuuint32_t es[5] = {1, 1, (cuuint32_t)g.sw, (cuuint32_t)g.sh, 1};
-    if (encode_map(&tmA, L.a, 5, dims, str, box, es, swz)) return -1;
+    if (encode_map(tmA, L.a, 5, dims, str, box, es, swz)) return -1;
   }
+  const long long rows_total = static_cast<long long>(L.NB) * L.OH * L.OW;
+  if (encode_rowtile_map(tmOut, L.e.out, rows_total, L.N, L.e.ldc, f32_out)) return -1;
+  return 0;
+}
+
+int launch_gemm_tc(const GemmLaunch& L, cudaStream_t stream) { return launch_gemm_tc_multi(&L, 1, stream); }
+
+// n problems of one layer (same weights, bias, epilogue, kernel, strides, channel counts; different
+// activations / geometry).  Problems that need different tile forms (NSEG) go to separate launches.
+int launch_gemm_tc_multi(const GemmLaunch* Ls, int n, cudaStream_t stream) {
+  KIRI_REQUIRE(Ls && n >= 1 && n <= kMaxProblems, "gemm_tc: 1..%d problems per call", kMaxProblems);
+  GemmLaunch L = Ls[0];
+  static const int timing_on = getenv("KIRI_GEMM_TIMING") != nullptr;
+  L.e.timing = timing_on;
+  gemm_tc_num_sms();
+  KIRI_REQUIRE(L.Cin % 32 == 0, "gemm_tc: Cin=%d must be a multiple of 32", L.Cin);
+  const bool is_gemm = (L.kw == 1 && L.kh == 1);
+  KIRI_REQUIRE(n == 1 || !is_gemm, "gemm_tc: only conv problems can share a launch");
+  for (int i = 0; i < n; ++i) {
+    const GemmLaunch& Q = Ls[i];
+    KIRI_REQUIRE(Q.e.bias != nullptr && Q.e.out != nullptr && Q.a != nullptr, "gemm_tc: a/bias/out must not be null");
+    KIRI_REQUIRE(Q.w == L.w && Q.e.bias == L.e.bias && Q.N == L.N && Q.Cin == L.Cin && Q.epi == L.epi && Q.kw == L.kw &&
+                     Q.kh == L.kh && Q.sw == L.sw && Q.sh == L.sh && Q.pad == L.pad && Q.e.ldc == L.e.ldc,
+                 "gemm_tc: problem %d is not the same layer as problem 0", i);
+  }
+  // 128-byte K rows whenever the channels allow; the residual/LayerNorm epilogues keep 128 KB of
+  // staging tiles, so their pipeline uses the half-size (64-byte) stages to still be 3 deep
+  const bool resid_epi = (L.epi == EPI_BIAS_RESID_F32 || L.epi == EPI_BIAS_RESID_LN);
+  const int KC = (L.Cin % 64 == 0 && !resid_epi) ? 64 : 32;
+  int bn = (L.N + 15) / 16 * 16;
+  if (bn > 256) bn = 256;
+  const int num_n_tiles = (L.N + bn - 1) / bn;
+
+  CUtensorMap tmB, tmRes, tmOut2;
+  const CUtensorMapSwizzle swz = (KC == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  const int taps = L.kw * L.kh;
   {  // B: (cKC, chunk, N)
-    const int ktot = g.taps * L.Cin;
+    const int ktot = taps * L.Cin;
     cuuint64_t dims[3] = {(cuuint64_t)KC, (cuuint64_t)(ktot / KC), (cuuint64_t)L.N};
     cuuint64_t str[2] = {(cuuint64_t)KC * 2, (cuuint64_t)ktot * 2};
     cuuint32_t box[3] = {(cuuint32_t)KC, 1, (cuuint32_t)bn};
     cuuint32_t es[3] = {1, 1, 1};
     if (encode_map(&tmB, L.w, 3, dims, str, box, es, swz)) return -1;
   }
-  const long long rows_total = static_cast<long long>(L.NB) * L.OH * L.OW;
-  if (encode_rowtile_map(&tmOut, L.e.out, rows_total, L.N, L.e.ldc, f32_out)) return -1;
-  tmRes = tmOut;
-  tmOut2 = tmOut;
-  if (L.epi == EPI_BIAS_RESID_F32 || L.epi == EPI_BIAS_RESID_LN) {
-    KIRI_REQUIRE(L.N == 256 && L.e.ldc == 256 && L.e.resid, "gemm_tc: residual epilogues need N = ldc = 256 and resid");
-    if (encode_rowtile_map(&tmRes, L.e.resid, rows_total, 256, 256, true)) return -1;
-  }
-  if (L.epi == EPI_BIAS_RESID_LN) {
-    KIRI_REQUIRE(L.e.ln_g && L.e.ln_b && L.e.out2, "gemm_tc: LayerNorm epilogue needs ln_g, ln_b, out2");
-    if (encode_rowtile_map(&tmOut2, L.e.out2, rows_total, 256, 256, false)) return -1;
-  }
-
   // weights stay resident in shared memory for the whole CTA when they fit beside >= 3 A stages
-  const int b_total = g.taps * L.Cin * bn * 2;
-  const bool bstat = !resid_epi && b_total <= kMaxBResident && getenv("KIRI_GEMM_NO_BSTAT") == nullptr &&
-                     (g_max_smem - 1024 - (int)sizeof(PipeBarriers) - kEpiWarps * kBufBytes - b_total) >= 3 * CPS * kTileM * KC * 2;
-#define KIRI_LAUNCH(K, S, E)                                                                                          \
-  do {                                                                                                                 \
-    if (bstat) return launch_inst<K, S, E, true>(tmA, tmB, tmOut, tmRes, tmOut2, g, L.e, bn, num_m_tiles, num_n_tiles, CPS, stream); \
-    return launch_inst<K, S, E, false>(tmA, tmB, tmOut, tmRes, tmOut2, g, L.e, bn, num_m_tiles, num_n_tiles, CPS, stream);           \
-  } while (0)
-#define KIRI_LAUNCH_NB(K, S, E) \
-  return launch_inst<K, S, E, false>(tmA, tmB, tmOut, tmRes, tmOut2, g, L.e, bn, num_m_tiles, num_n_tiles, CPS, stream)
-  if (!is_gemm) {
-    if (KC == 64 && NSEG == 1) KIRI_LAUNCH(64, 1, EPI_BIAS_SILU_BF16);
-    if (KC == 64 && NSEG == 4) KIRI_LAUNCH(64, 4, EPI_BIAS_SILU_BF16);
-    if (KC == 32 && NSEG == 1) KIRI_LAUNCH_NB(32, 1, EPI_BIAS_SILU_BF16);
-    if (KC == 32 && NSEG == 4) KIRI_LAUNCH_NB(32, 4, EPI_BIAS_SILU_BF16);
-  } else {
-    switch (L.epi) {
-      case EPI_BIAS_BF16: KIRI_LAUNCH(64, 1, EPI_BIAS_BF16);
-      case EPI_BIAS_SILU_BF16: KIRI_LAUNCH(64, 1, EPI_BIAS_SILU_BF16);
-      case EPI_BIAS_GELU_BF16: KIRI_LAUNCH(64, 1, EPI_BIAS_GELU_BF16);
-      case EPI_BIAS_RESID_F32: KIRI_LAUNCH_NB(32, 1, EPI_BIAS_RESID_F32);
-      case EPI_BIAS_F32: KIRI_LAUNCH(64, 1, EPI_BIAS_F32);
-      case EPI_BIAS_RESID_LN: KIRI_LAUNCH_NB(32, 1, EPI_BIAS_RESID_LN);
-      default: break;
+  const int b_total = taps * L.Cin * bn * 2;
+
+  // group the problems by tile form
+  bool done[kMaxProblems] = {false};
+  for (int first = 0; first < n; ++first) {
+    if (done[first]) continue;
+    ProblemSet P;
+    memset(&P, 0, sizeof(P));
+    int nseg0 = 0, cps0 = 0, m_total = 0;
+    for (int i = first; i < n; ++i) {
+      if (done[i]) continue;
+      ConvGeom g;
+      CUtensorMap ta, to;
+      int nseg, cps, mt;
+      if (prep_problem(Ls[i], is_gemm, KC, &g, &nseg, &cps, &ta, &to, &mt)) return -1;
+      if (P.n == 0) { nseg0 = nseg; cps0 = cps; }
+      if (nseg != nseg0 || cps != cps0) continue;
+      P.g[P.n] = g; P.tmA[P.n] = ta; P.tmOut[P.n] = to;
+      P.mtile_begin[P.n] = m_total;
+      m_total += mt;
+      ++P.n;
+      done[i] = true;
     }
-  }
+    for (int i = P.n; i <= kMaxProblems; ++i) P.mtile_begin[i] = m_total;
+    const int NSEG = nseg0, CPS = cps0;
+    tmRes = P.tmOut[0];
+    tmOut2 = P.tmOut[0];
+    if (resid_epi) {
+      const long long rows_total = static_cast<long long>(L.NB) * L.OH * L.OW;
+      KIRI_REQUIRE(L.N == 256 && L.e.ldc == 256 && L.e.resid, "gemm_tc: residual epilogues need N = ldc = 256 and resid");
+      if (encode_rowtile_map(&tmRes, L.e.resid, rows_total, 256, 256, true)) return -1;
+      if (L.epi == EPI_BIAS_RESID_LN) {
+        KIRI_REQUIRE(L.e.ln_g && L.e.ln_b && L.e.out2, "gemm_tc: LayerNorm epilogue needs ln_g, ln_b, out2");
+        if (encode_rowtile_map(&tmOut2, L.e.out2, rows_total, 256, 256, false)) return -1;
+      }
+    }
+    const bool bstat = !resid_epi && b_total <= kMaxBResident && getenv("KIRI_GEMM_NO_BSTAT") == nullptr &&
+                       (g_max_smem - 1024 - (int)sizeof(PipeBarriers) - kEpiWarps * kBufBytes - b_total) >= 3 * CPS * kTileM * KC * 2;
+    int rc = -1;
+#define KIRI_LAUNCH(K, S, E)                                                                                          \
+  rc = bstat ? launch_inst<K, S, E, true>(P, tmB, tmRes, tmOut2, L.e, bn, m_total, num_n_tiles, CPS, stream)            \
+             : launch_inst<K, S, E, false>(P, tmB, tmRes, tmOut2, L.e, bn, m_total, num_n_tiles, CPS, stream)
+#define KIRI_LAUNCH_NB(K, S, E) rc = launch_inst<K, S, E, false>(P, tmB, tmRes, tmOut2, L.e, bn, m_total, num_n_tiles, CPS, stream)
+    if (!is_gemm) {
+      if (KC == 64 && NSEG == 1) KIRI_LAUNCH(64, 1, EPI_BIAS_SILU_BF16);
+      else if (KC == 64 && NSEG == 4) KIRI_LAUNCH(64, 4, EPI_BIAS_SILU_BF16);
+      else if (KC == 32 && NSEG == 1) KIRI_LAUNCH_NB(32, 1, EPI_BIAS_SILU_BF16);
+      else if (KC == 32 && NSEG == 4) KIRI_LAUNCH_NB(32, 4, EPI_BIAS_SILU_BF16);
+    } else {
+      switch (L.epi) {
+        case EPI_BIAS_BF16: KIRI_LAUNCH(64, 1, EPI_BIAS_BF16); break;
+        case EPI_BIAS_SILU_BF16: KIRI_LAUNCH(64, 1, EPI_BIAS_SILU_BF16); break;
+        case EPI_BIAS_GELU_BF16: KIRI_LAUNCH(64, 1, EPI_BIAS_GELU_BF16); break;
+        case EPI_BIAS_RESID_F32: KIRI_LAUNCH_NB(32, 1, EPI_BIAS_RESID_F32); break;
+        case EPI_BIAS_F32: KIRI_LAUNCH(64, 1, EPI_BIAS_F32); break;
+        case EPI_BIAS_RESID_LN: KIRI_LAUNCH_NB(32, 1, EPI_BIAS_RESID_LN); break;
+        default: KIRI_REQUIRE(false, "gemm_tc: unknown epilogue %d", L.epi);
+      }
+    }
 #undef KIRI_LAUNCH_NB
 #undef KIRI_LAUNCH
-  KIRI_REQUIRE(false, "gemm_tc: no kernel instance for KC=%d CPS=%d NSEG=%d epi=%d", KC, CPS, NSEG, L.epi);
+    if (rc != 0) return rc;
+  }
+  return 0;
 }
 
 

@@ -67,6 +67,17 @@ struct GemmLaunch {
   EpiParams e;
 };
 int launch_gemm_tc(const GemmLaunch& L, cudaStream_t stream);
+// Up to kMaxProblems conv problems of ONE layer (the width groups of a batch) in one launch (two when the
+// groups need different tile forms): one prologue / tail and one wave-quantisation loss instead of five.
+constexpr int kMaxProblems = 8;
+int launch_gemm_tc_multi(const GemmLaunch* Ls, int n, cudaStream_t stream);
+struct ProblemSet {              // grid-constant kernel parameter
+  CUtensorMap tmA[kMaxProblems];
+  CUtensorMap tmOut[kMaxProblems];
+  ConvGeom g[kMaxProblems];
+  int mtile_begin[kMaxProblems + 1];
+  int n;
+};
 // conv1 fused into conv2 (gemm_tc.cu, stem12_kernel)
 int launch_stem12(const uint8_t* planes, const float* conv1_w_host, const float* conv1_b_host, const void* w48,
                   const float* bias2, int n, int H, int W, void* out, cudaStream_t stream);

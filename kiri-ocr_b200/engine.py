@@ -253,8 +253,7 @@ class BatchedRecognizer:
                                         _lib.ptr(out.get("mem_f32")), out["mem_bf16"].data_ptr(),
                                         _lib.ptr(out.get("logits")), _lib.ptr(out.get("tokens")), _lib.ptr(kv_len),
                                         _lib.stream_ptr()), "kiri_encode")
-        n_chunks = math.ceil(B / self._stem_sub_batch(B, Wb))
-        self.launches += 4 * n_chunks + 1 + 4 * self.pw.enc_layers + 1 + (1 if want_logits else 0)
+        self.launches += self._stem_launches([(B, Wb)]) + 1 + 5 * self.pw.enc_layers + 1 + (1 if want_logits else 0)
         return out
 
     def _stem_sub_batch(self, B: int, Wb: int) -> int:
@@ -267,6 +266,26 @@ class BatchedRecognizer:
             return B
         n = -(-B // cap)
         return -(-B // n)
+
+    @staticmethod
+    def _conv_nseg(OH: int, OW: int) -> int:
+        """Tile form of a conv problem (mirror of prep_problem in csrc/gemm_tc.cu): 4 = four 32-pixel segments."""
+        best = min(((OW + S - 1) // S * S) * ((OH + R - 1) // R * R) / (OW * OH) for R, S in ((1, 128), (2, 64), (4, 32)))
+        return 4 if best > 1.25 else 1
+
+    def _stem_launches(self, groups) -> int:
+        """Kernel launches of the stem for width groups [(lines, Wb)]: conv1 per (group, round), one launch per conv
+        layer and tile form per round (csrc/api.cu; only used for the bench's launch count)."""
+        H = self.cfg.IMG_H
+        subs = [self._stem_sub_batch(B, Wb) for B, Wb in groups]
+        rounds = max(-(-B // sc) for (B, _), sc in zip(groups, subs))
+        n = 0
+        for r in range(rounds):
+            live = [Wb for (B, Wb), sc in zip(groups, subs) if r * sc < B]
+            n += len(live)
+            for OH, div in ((H // 2, 2), (H // 4, 4), (H // 8, 4)):
+                n += len({self._conv_nseg(OH, Wb // div) for Wb in live})
+        return n
 
     def encode_multi(self, planes_list: Sequence[torch.Tensor], want_mem_f32: bool = False, want_tokens: bool = False,
                      kv_len: Optional[torch.Tensor] = None, want_logits: bool = True):
@@ -295,9 +314,7 @@ class BatchedRecognizer:
                                               _lib.ptr(out.get("mem_f32")), out["mem_bf16"].data_ptr(),
                                               _lib.ptr(out.get("logits")), _lib.ptr(out.get("tokens")), _lib.ptr(kv_len),
                                               _lib.stream_ptr()), "kiri_encode_multi")
-        for _, B, T in rows:
-            n_chunks = math.ceil(B / self._stem_sub_batch(B, 4 * T))
-            self.launches += 4 * n_chunks + 1                               # stem, pool per group
+        self.launches += self._stem_launches([(B, 4 * T) for _, B, T in rows]) + len(rows)     # stem + pool per group
         self.launches += 5 * self.pw.enc_layers + 1 + (1 if want_logits else 0)
         return out
 

@@ -93,6 +93,10 @@ int kiri_conv1_tc(const uint8_t* planes_u8, const float* w_host, const float* b_
                   int W, void* out_bf16_nhwc64, cudaStream_t stream);
 int kiri_conv1_ffma(const uint8_t* planes_u8, const float* w_host, const float* b_host, int n_lines, int H,
                     int W, void* out_bf16_nhwc64, cudaStream_t stream);
+/* The default (FFMA) form for several width groups in ONE launch: planes / out / lines / W per group (host arrays). */
+int kiri_conv1_multi(const uint8_t* const* planes_u8, void* const* out_bf16_nhwc64, const int* group_lines,
+                     const int* group_W, int n_groups, const float* w_host, const float* b_host, int H,
+                     cudaStream_t stream);
 
 /* K2+K3 fused: stem layers 1 and 2 in one kernel (ConvStem.net[0:6], kiri_ocr/model.py:215-220): the
  * 48-channel activation never leaves the SM.  planes_u8 [n, H, W] (H % 4 == 0, W % 128 == 0),
@@ -122,6 +126,10 @@ int kiri_gemm_ref(const void* a, const void* w, int M, int N, int K, float* out_
 int kiri_pool_pos_ln(const void* act_bf16, const float* pos_table, int n_lines, int RH, int T, int D,
                      const float* g0, const float* b0, const float* g1, const float* b1, float* x_f32,
                      void* a_bf16, cudaStream_t stream);
+/* The same for several width groups of one token stream in ONE launch (group order = token order). */
+int kiri_pool_pos_ln_multi(const void* const* act_bf16, const int* group_lines, const int* group_T, int n_groups,
+                           const float* pos_table, int RH, int D, const float* g0, const float* b0, const float* g1,
+                           const float* b1, float* x_f32, void* a_bf16, cudaStream_t stream);
 /* y = LN0(x) -> y_f32 / y_bf16 (nullable); z_bf16 = LN1(y) (nullable).  D must be 256. */
 int kiri_layernorm(const float* x, int n_tok, int D, const float* g0, const float* b0, float* y_f32,
                    void* y_bf16, const float* g1, const float* b1, void* z_bf16, cudaStream_t stream);

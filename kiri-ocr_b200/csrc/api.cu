@@ -311,6 +311,10 @@ extern "C" int kiri_encode_multi(KiriHandle* h, const KiriGroup* groups, int n_g
   for (int g = 0; g < n_groups; ++g) rounds = std::max(rounds, (groups[g].n_lines + ws.sc[g] - 1) / ws.sc[g]);
   for (int r = 0; r < rounds; ++r) {
     GemmLaunch L2[8], L3[8], L4[8];
+    const uint8_t* c1_in[8];
+    void* c1_out[8];
+    int c1_lines[8], c1_W[8];
+    static const bool conv1_tc = getenv("KIRI_CONV1_TC") != nullptr;
     int np = 0;
     for (int g = 0; g < n_groups; ++g) {
       const int B = groups[g].n_lines, Wb = groups[g].Wb, T = Wb / 4;
@@ -326,29 +330,38 @@ extern "C" int kiri_encode_multi(KiriHandle* h, const KiriGroup* groups, int n_g
         // layers 1+2 fused: the 48-channel activation never reaches HBM
         ProfScope ps(PS_CONV2, stream);
         KIRI_TRY(launch_stem12(planes, w.conv1_w_host, w.conv1_b_host, w.conv2_w48, w.conv2_b, nb, H, Wb, a2, stream));
-      } else {
+      } else if (conv1_tc) {
         ProfScope ps(PS_CONV1, stream);
-        KIRI_TRY(kiri_conv1(planes, w.conv1_w_host, w.conv1_b_host, nb, H, Wb, a1, stream));
+        KIRI_TRY(kiri_conv1_tc(planes, w.conv1_w_host, w.conv1_b_host, nb, H, Wb, a1, stream));
       }
+      c1_in[np] = planes; c1_out[np] = a1; c1_lines[np] = nb; c1_W[np] = Wb;
       L2[np] = conv_launch(a1, w.conv2_w, w.conv2_b, nb, H, Wb, 64, 96, 2, 2, a2);
       L3[np] = conv_launch(a2, w.conv3_w, w.conv3_b, nb, H / 2, Wb / 2, 96, 160, 2, 2, a3);
       L4[np] = conv_launch(a3, w.conv4_w, w.conv4_b, nb, H / 4, Wb / 4, 160, 256, 2, 1, a4);
       ++np;
     }
     if (np == 0) continue;
+    if (!(w.conv2_w48 && !no_stem12) && !conv1_tc) {
+      ProfScope ps(PS_CONV1, stream);
+      KIRI_TRY(kiri_conv1_multi(c1_in, c1_out, c1_lines, c1_W, np, w.conv1_w_host, w.conv1_b_host, H, stream));
+    }
     if (!(w.conv2_w48 && !no_stem12)) { ProfScope ps(PS_CONV2, stream); KIRI_TRY(launch_gemm_tc_multi(L2, np, stream)); }
     { ProfScope ps(PS_CONV3, stream); KIRI_TRY(launch_gemm_tc_multi(L3, np, stream)); }
     { ProfScope ps(PS_CONV4, stream); KIRI_TRY(launch_gemm_tc_multi(L4, np, stream)); }
   }
-  // ---- per group: pool + positional table + enc_ln_in (+ norm1 of layer 0), written at the group's row
-  // offset of the concatenated token stream
-  size_t row0 = 0;
-  for (int g = 0; g < n_groups; ++g) {
-    const int B = groups[g].n_lines, T = groups[g].Wb / 4;
-    { ProfScope ps(PS_POOL_LN, stream);
-      KIRI_TRY(kiri_pool_pos_ln(base + ws.act4 + ws.g4[g], w.pos_table, B, H / 8, T, D, w.enc_ln_in_g, w.enc_ln_in_b,
-                                w.enc[0].ln1_g, w.enc[0].ln1_b, x + row0 * D, a + row0 * D * 2, stream)); }
-    row0 += static_cast<size_t>(B) * T;
+  // ---- pool + positional table + enc_ln_in (+ norm1 of layer 0) of every group, written as the concatenated
+  // token stream (one launch)
+  {
+    const void* p_act[8];
+    int p_lines[8], p_T[8];
+    for (int g = 0; g < n_groups; ++g) {
+      p_act[g] = base + ws.act4 + ws.g4[g];
+      p_lines[g] = groups[g].n_lines;
+      p_T[g] = groups[g].Wb / 4;
+    }
+    ProfScope ps(PS_POOL_LN, stream);
+    KIRI_TRY(kiri_pool_pos_ln_multi(p_act, p_lines, p_T, n_groups, w.pos_table, H / 8, D, w.enc_ln_in_g, w.enc_ln_in_b,
+                                    w.enc[0].ln1_g, w.enc[0].ln1_b, x, a, stream));
   }
   if (tok_f32) KIRI_CHECK_CUDA(cudaMemcpyAsync(tok_f32, x, static_cast<size_t>(M) * D * 4, cudaMemcpyDeviceToDevice, stream));
   // ---- encoder layers over the concatenated token stream (the GEMMs do not see line boundaries)

@@ -23,9 +23,17 @@ struct Conv1Params {
   float b[kC1];
 };
 
+// Width groups of one batch: group i owns tiles [tile_begin[i], tile_begin[i+1]) (one tile = 128 pixels of a row).
+struct Conv1Groups {
+  int n;
+  int tile_begin[9];
+  const uint8_t* planes[8];
+  __nv_bfloat16* out[8];
+  int W[8];
+};
+
 __global__ void __launch_bounds__(kConv1Threads)
-conv1_bn_silu_kernel(const uint8_t* __restrict__ planes, __nv_bfloat16* __restrict__ out, int H,
-                     int W, const __grid_constant__ Conv1Params p) {
+conv1_bn_silu_kernel(const __grid_constant__ Conv1Groups G, int H, const __grid_constant__ Conv1Params p) {
   __shared__ float s_norm[256];
   __shared__ __align__(16) uint8_t s_out[kConv1Threads * kC1Pad * 2];   // 16 KiB staging tile
   const int tid = threadIdx.x;
@@ -35,8 +43,15 @@ conv1_bn_silu_kernel(const uint8_t* __restrict__ planes, __nv_bfloat16* __restri
   pdl_trigger();
   pdl_wait();                                       // the planes come from the previous kernel
 
+  int gi = 0;
+#pragma unroll
+  for (int i = 1; i < 8; ++i)
+    if (i < G.n && static_cast<int>(blockIdx.x) >= G.tile_begin[i]) gi = i;
+  const int W = G.W[gi];
+  const uint8_t* __restrict__ planes = G.planes[gi];
+  __nv_bfloat16* __restrict__ out = G.out[gi];
   const int tiles_per_row = W / kConv1Threads;
-  const int tile = blockIdx.x;
+  const int tile = static_cast<int>(blockIdx.x) - G.tile_begin[gi];
   const int xt = tile % tiles_per_row;
   const int by = tile / tiles_per_row;            // b * H + y
   const int y = by % H;
@@ -210,19 +225,39 @@ static float host_bf16_to_f(uint16_t h) {
 
 using namespace kiri;
 
-extern "C" int kiri_conv1_ffma(const uint8_t* planes_u8, const float* w_host, const float* b_host, int n_lines,
-                               int H, int W, void* out_bf16_nhwc64, cudaStream_t stream) {
-  KIRI_REQUIRE(planes_u8 && w_host && b_host && out_bf16_nhwc64, "kiri_conv1: null pointer");
-  KIRI_REQUIRE(W % kConv1Threads == 0, "kiri_conv1: width %d must be a multiple of %d", W, kConv1Threads);
-  if (n_lines == 0) return 0;
+extern "C" int kiri_conv1_multi(const uint8_t* const* planes_u8, void* const* out_bf16_nhwc64, const int* group_lines,
+                                const int* group_W, int n_groups, const float* w_host, const float* b_host, int H,
+                                cudaStream_t stream) {
+  KIRI_REQUIRE(planes_u8 && out_bf16_nhwc64 && group_lines && group_W && w_host && b_host, "kiri_conv1: null pointer");
+  KIRI_REQUIRE(n_groups >= 0 && n_groups <= 8, "kiri_conv1_multi: at most 8 groups");
+  Conv1Groups G;
+  memset(&G, 0, sizeof(G));
+  long long tiles = 0;
+  for (int g = 0; g < n_groups; ++g) {
+    if (group_lines[g] <= 0) continue;
+    KIRI_REQUIRE(planes_u8[g] && out_bf16_nhwc64[g], "kiri_conv1_multi: null pointer in group %d", g);
+    KIRI_REQUIRE(group_W[g] % kConv1Threads == 0, "kiri_conv1: width %d must be a multiple of %d", group_W[g], kConv1Threads);
+    G.tile_begin[G.n] = static_cast<int>(tiles);
+    G.planes[G.n] = planes_u8[g];
+    G.out[G.n] = reinterpret_cast<__nv_bfloat16*>(out_bf16_nhwc64[g]);
+    G.W[G.n] = group_W[g];
+    tiles += static_cast<long long>(group_lines[g]) * H * (group_W[g] / kConv1Threads);
+    KIRI_REQUIRE(tiles < 0x7fffffffll, "kiri_conv1: grid too large");
+    ++G.n;
+  }
+  for (int i = G.n; i < 9; ++i) G.tile_begin[i] = static_cast<int>(tiles);
+  if (tiles == 0) return 0;
   Conv1Params p;
   for (int i = 0; i < kC1 * 9; ++i) p.w[i] = w_host[i];
   for (int i = 0; i < kC1; ++i) p.b[i] = b_host[i];
-  const long long tiles = static_cast<long long>(n_lines) * H * (W / kConv1Threads);
-  KIRI_REQUIRE(tiles < 0x7fffffffll, "kiri_conv1: grid too large");
-  KIRI_CHECK_CUDA(launch_pdl(conv1_bn_silu_kernel, dim3(static_cast<unsigned>(tiles)), dim3(kConv1Threads), 0, stream,
-                             planes_u8, reinterpret_cast<__nv_bfloat16*>(out_bf16_nhwc64), H, W, p));
+  KIRI_CHECK_CUDA(launch_pdl(conv1_bn_silu_kernel, dim3(static_cast<unsigned>(tiles)), dim3(kConv1Threads), 0, stream, G, H, p));
   return 0;
+}
+
+extern "C" int kiri_conv1_ffma(const uint8_t* planes_u8, const float* w_host, const float* b_host, int n_lines,
+                               int H, int W, void* out_bf16_nhwc64, cudaStream_t stream) {
+  KIRI_REQUIRE(planes_u8 && w_host && b_host && out_bf16_nhwc64, "kiri_conv1: null pointer");
+  return kiri_conv1_multi(&planes_u8, &out_bf16_nhwc64, &n_lines, &W, 1, w_host, b_host, H, stream);
 }
 
 extern "C" int kiri_conv1_tc(const uint8_t* planes_u8, const float* w_host, const float* b_host, int n_lines,

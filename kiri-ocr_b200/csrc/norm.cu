@@ -10,21 +10,38 @@
 #include "kiri_b200.h"
 #include "ln_utils.cuh"
 
+#include <cstring>
+
 namespace kiri {
 
 static constexpr int kLnThreads = 256;    // 8 tokens per CTA
 
-// act: bf16 [B, RH, T, 256] (NHWC stem output); pos: fp32 [T, 256]
+// Width groups of one token stream: group i owns tokens [tok_begin[i], tok_begin[i+1]) and its own stem output.
+struct PoolGroups {
+  int n;
+  int tok_begin[9];
+  const __nv_bfloat16* act[8];
+  int T[8];
+};
+
+// act: bf16 [B, RH, T, 256] per group (NHWC stem output); pos: fp32 [T, 256]
 __global__ void __launch_bounds__(kLnThreads)
-pool_pos_ln_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ pos, int n_tok,
-                   int RH, int T, const float* g0, const float* b0, const float* g1, const float* b1,
+pool_pos_ln_kernel(const __grid_constant__ PoolGroups G, const float* __restrict__ pos, int n_tok,
+                   int RH, const float* g0, const float* b0, const float* g1, const float* b1,
                    float* __restrict__ x_f32, __nv_bfloat16* __restrict__ a_bf16) {
   const int lane = threadIdx.x & 31;
   const int tok = blockIdx.x * (kLnThreads / 32) + (threadIdx.x >> 5);
   pdl_trigger();
   pdl_wait();                                       // the stem output comes from the previous kernel
   if (tok >= n_tok) return;
-  const int b = tok / T, t = tok - b * T;
+  int gi = 0;
+#pragma unroll
+  for (int i = 1; i < 8; ++i)
+    if (i < G.n && tok >= G.tok_begin[i]) gi = i;
+  const int T = G.T[gi];
+  const __nv_bfloat16* __restrict__ act = G.act[gi];
+  const int ltok = tok - G.tok_begin[gi];
+  const int b = ltok / T, t = ltok - b * T;
   float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (int r = 0; r < RH; ++r) {
     const uint4 pk = __ldg(reinterpret_cast<const uint4*>(
@@ -71,19 +88,39 @@ ln_chain_kernel(const float* __restrict__ x, int n_tok, const float* g0, const f
 
 using namespace kiri;
 
+extern "C" int kiri_pool_pos_ln_multi(const void* const* act_bf16, const int* group_lines, const int* group_T, int n_groups,
+                                      const float* pos_table, int RH, int D, const float* g0, const float* b0, const float* g1,
+                                      const float* b1, float* x_f32, void* a_bf16, cudaStream_t stream) {
+  KIRI_REQUIRE(D == kD, "kiri_pool_pos_ln: model width %d unsupported (kernels are built for 256)", D);
+  KIRI_REQUIRE(act_bf16 && group_lines && group_T && pos_table && g0 && b0 && x_f32, "kiri_pool_pos_ln: null pointer");
+  KIRI_REQUIRE(!a_bf16 || (g1 && b1), "kiri_pool_pos_ln: second LayerNorm needs its affine");
+  KIRI_REQUIRE(n_groups >= 0 && n_groups <= 8, "kiri_pool_pos_ln_multi: at most 8 groups");
+  PoolGroups G;
+  memset(&G, 0, sizeof(G));
+  long long tok = 0;
+  for (int g = 0; g < n_groups; ++g) {
+    if (group_lines[g] <= 0) continue;
+    KIRI_REQUIRE(act_bf16[g] && group_T[g] > 0, "kiri_pool_pos_ln_multi: bad group %d", g);
+    G.tok_begin[G.n] = static_cast<int>(tok);
+    G.act[G.n] = reinterpret_cast<const __nv_bfloat16*>(act_bf16[g]);
+    G.T[G.n] = group_T[g];
+    tok += static_cast<long long>(group_lines[g]) * group_T[g];
+    KIRI_REQUIRE(tok < 0x7fffffffll, "kiri_pool_pos_ln_multi: too many tokens");
+    ++G.n;
+  }
+  for (int i = G.n; i < 9; ++i) G.tok_begin[i] = static_cast<int>(tok);
+  const int n_tok = static_cast<int>(tok);
+  if (n_tok == 0) return 0;
+  const int per = kLnThreads / 32;
+  KIRI_CHECK_CUDA(launch_pdl(pool_pos_ln_kernel, dim3((n_tok + per - 1) / per), dim3(kLnThreads), 0, stream, G, pos_table, n_tok,
+                             RH, g0, b0, g1, b1, x_f32, reinterpret_cast<__nv_bfloat16*>(a_bf16)));
+  return 0;
+}
+
 extern "C" int kiri_pool_pos_ln(const void* act_bf16, const float* pos_table, int n_lines, int RH, int T,
                                 int D, const float* g0, const float* b0, const float* g1, const float* b1,
                                 float* x_f32, void* a_bf16, cudaStream_t stream) {
-  KIRI_REQUIRE(D == kD, "kiri_pool_pos_ln: model width %d unsupported (kernels are built for 256)", D);
-  KIRI_REQUIRE(act_bf16 && pos_table && g0 && b0 && x_f32, "kiri_pool_pos_ln: null pointer");
-  KIRI_REQUIRE(!a_bf16 || (g1 && b1), "kiri_pool_pos_ln: second LayerNorm needs its affine");
-  const int n_tok = n_lines * T;
-  if (n_tok == 0) return 0;
-  const int per = kLnThreads / 32;
-  KIRI_CHECK_CUDA(launch_pdl(pool_pos_ln_kernel, dim3((n_tok + per - 1) / per), dim3(kLnThreads), 0, stream,
-                             reinterpret_cast<const __nv_bfloat16*>(act_bf16), pos_table, n_tok, RH, T, g0, b0, g1, b1, x_f32,
-                             reinterpret_cast<__nv_bfloat16*>(a_bf16)));
-  return 0;
+  return kiri_pool_pos_ln_multi(&act_bf16, &n_lines, &T, 1, pos_table, RH, D, g0, b0, g1, b1, x_f32, a_bf16, stream);
 }
 
 extern "C" int kiri_layernorm(const float* x, int n_tok, int D, const float* g0, const float* b0, float* y_f32,

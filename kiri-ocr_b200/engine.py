@@ -274,15 +274,15 @@ class BatchedRecognizer:
         return 4 if best > 1.25 else 1
 
     def _stem_launches(self, groups) -> int:
-        """Kernel launches of the stem for width groups [(lines, Wb)]: conv1 per (group, round), one launch per conv
-        layer and tile form per round (csrc/api.cu; only used for the bench's launch count)."""
+        """Kernel launches of the stem for width groups [(lines, Wb)]: per round one conv1 and one launch per conv
+        layer and tile form (csrc/api.cu; only used for the bench's launch count)."""
         H = self.cfg.IMG_H
         subs = [self._stem_sub_batch(B, Wb) for B, Wb in groups]
         rounds = max(-(-B // sc) for (B, _), sc in zip(groups, subs))
         n = 0
         for r in range(rounds):
             live = [Wb for (B, Wb), sc in zip(groups, subs) if r * sc < B]
-            n += len(live)
+            n += 1                                            # conv1 of all groups
             for OH, div in ((H // 2, 2), (H // 4, 4), (H // 8, 4)):
                 n += len({self._conv_nseg(OH, Wb // div) for Wb in live})
         return n
@@ -314,7 +314,7 @@ class BatchedRecognizer:
                                               _lib.ptr(out.get("mem_f32")), out["mem_bf16"].data_ptr(),
                                               _lib.ptr(out.get("logits")), _lib.ptr(out.get("tokens")), _lib.ptr(kv_len),
                                               _lib.stream_ptr()), "kiri_encode_multi")
-        self.launches += self._stem_launches([(B, 4 * T) for _, B, T in rows]) + len(rows)     # stem + pool per group
+        self.launches += self._stem_launches([(B, 4 * T) for _, B, T in rows]) + 1             # stem + pool
         self.launches += 5 * self.pw.enc_layers + 1 + (1 if want_logits else 0)
         return out
 

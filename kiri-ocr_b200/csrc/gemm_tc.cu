@@ -16,9 +16,10 @@ static constexpr int kTmemCols = 512;
 static constexpr int kEpiWarps = 8;                     // two per TMEM lane quarter (column halves)
 // Epilogue warps take the LOW warp ids: the SM sub-partition arbiter favours the highest warp id, and
 // the single-lane TMA / MMA issuers (warps 8, 9) must never be starved by epilogue arithmetic.
-// Two TMA producer warps take alternate k-blocks: one thread cannot issue a box faster than every
-// ~450 cycles (tools/tma_stream.cu: 1 issuer 51 B/clk/SM, 2 issuers 101 B/clk/SM).
-static constexpr int kTmaWarps = 2;
+// Three TMA producer warps take k-blocks in turn: one thread cannot issue a box faster than every
+// ~350-450 cycles (tools/tma_stream.cu: 1 issuer 51 B/clk/SM, 2 issuers 101, 3 issuers 119), and a
+// conv4 tile is 45 k-blocks of two boxes.  A k-block's CPS channel chunks travel in ONE box per operand.
+static constexpr int kTmaWarps = 3;
 static constexpr int kTmaWarp = kEpiWarps, kMmaWarp = kEpiWarps + kTmaWarps;
 static constexpr int kNumThreads = (kEpiWarps + kTmaWarps + 1) * 32;
 static constexpr int kMaxStages = 8;
@@ -60,7 +61,8 @@ template <int KC, int NSEG, int EPI, bool BSTAT>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc_kernel(const __grid_constant__ ProblemSet P, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmOut2, const EpiParams e,
-               const int bn, const int num_m_tiles, const int num_n_tiles, const int stages, const int CPS) {
+               const int bn, const int num_m_tiles, const int num_n_tiles, const int stages, const int CPS, const int abox,
+               const int bbox) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int kChunkBytes = KC * 2;
   constexpr int kATileBytes = kTileM * kChunkBytes;
@@ -141,7 +143,10 @@ gemm_tc_kernel(const __grid_constant__ ProblemSet P, const __grid_constant__ CUt
       int stage = 0;
       uint32_t phase = 0;
       int cur_n = -1, b_loads = 0;
-      const int pw = warp - kTmaWarp;              // this producer owns k-blocks pw, pw + kTmaWarps, ... of the CTA's stream
+      const int pw = warp - kTmaWarp;              // this producer owns k-blocks pw, pw + n_prod, ... of the CTA's stream
+      // A producer may not run more than one ring revolution ahead of a stage's empty barrier (parity waits
+      // alias two phases apart): no more active producers than stages.
+      const int n_prod = stages < kTmaWarps ? stages : kTmaWarps;
       int turn = 0;
       GT_BEGIN(tt0);
       long long tt_all = tt0, acc_we = 0, acc_tt = 0;
@@ -162,7 +167,7 @@ gemm_tc_kernel(const __grid_constant__ ProblemSet P, const __grid_constant__ CUt
           if (elect_one()) {
             mbar_arrive_expect_tx(&bars->b_full, num_chunks * b_chunk_bytes);
             for (int ck = 0; ck < num_chunks; ++ck)
-              tma_load_3d(bres + (size_t)ck * b_chunk_bytes, &tmB, &bars->b_full, 0, ck, n_tile * bn);
+              tma_load_3d(bres + (size_t)ck * b_chunk_bytes, &tmB, &bars->b_full, 0, n_tile * bn, ck);
           }
           __syncwarp();
           cur_n = n_tile;
@@ -197,22 +202,26 @@ gemm_tc_kernel(const __grid_constant__ ProblemSet P, const __grid_constant__ CUt
             uint8_t* a_dst = pipe + (size_t)stage * stage_bytes;
             uint8_t* b_dst = a_dst + a_stage_bytes;
             mbar_arrive_expect_tx(&bars->full[stage], tx_bytes);
-            for (int c = 0; c < CPS; ++c) {
+            // the CPS chunks of the k-block are the slowest box dimension: they land as CPS consecutive
+            // K-major tiles (CPS > 1 only with NSEG == 1, i.e. one 128-row segment per tile)
+            // (abox / bbox = chunks per A / B box: CPS, or 1 with one box per chunk)
+            for (int c = 0; c < CPS; c += abox) {
 #pragma unroll
               for (int j = 0; j < NSEG; ++j) {
                 if (seg_b[j] >= 0)
-                  tma_load_5d(a_dst + (size_t)c * kATileBytes + (size_t)j * box_bytes, tmA,
-                              &bars->full[stage], 0, cg * CPS + c, seg_x[j] + kx, seg_y[j] + ky,
-                              seg_b[j]);
+                  tma_load_5d(a_dst + (size_t)c * kATileBytes + (size_t)j * box_bytes, tmA, &bars->full[stage], 0, seg_x[j] + kx,
+                              seg_y[j] + ky, cg * CPS + c, seg_b[j]);
               }
-              if (!BSTAT)
-                tma_load_3d(b_dst + (size_t)c * b_chunk_bytes, &tmB, &bars->full[stage], 0,
-                            (ky * g.kw + kx) * g.chunks_per_tap + cg * CPS + c, n_tile * bn);
+            }
+            if (!BSTAT) {
+              for (int c = 0; c < CPS; c += bbox)
+                tma_load_3d(b_dst + (size_t)c * b_chunk_bytes, &tmB, &bars->full[stage], 0, n_tile * bn,
+                            (ky * g.kw + kx) * g.chunks_per_tap + cg * CPS + c);
             }
           }
           __syncwarp();
           }
-          if (++turn == kTmaWarps) turn = 0;
+          if (++turn == n_prod) turn = 0;
           if (++cg == g.cgs) { cg = 0; if (++kx == g.kw) { kx = 0; ++ky; } }
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
@@ -624,7 +633,8 @@ int encode_rowtile_map(CUtensorMap* m, const void* base, long long rows, int col
 
 template <int KC, int NSEG, int EPI, bool BSTAT>
 static int launch_inst(const ProblemSet& P, const CUtensorMap& tmB, const CUtensorMap& tmRes, const CUtensorMap& tmOut2,
-                       const EpiParams& e, int bn, int num_m_tiles, int num_n_tiles, int CPS, cudaStream_t stream) {
+                       const EpiParams& e, int bn, int num_m_tiles, int num_n_tiles, int CPS, int abox, int bbox,
+                       cudaStream_t stream) {
   constexpr bool kResid = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_RESID_LN);
   constexpr int kNBuf = kResid ? 4 : (BSTAT ? 1 : 2);
   const ConvGeom& g = P.g[0];
@@ -645,14 +655,14 @@ static int launch_inst(const ProblemSet& P, const CUtensorMap& tmB, const CUtens
   int grid = num_m_tiles * num_n_tiles;
   if (grid > g_num_sms) grid = g_num_sms;
   KIRI_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kNumThreads), smem, stream, P, tmB, tmRes, tmOut2, e, bn, num_m_tiles,
-                             num_n_tiles, stages, CPS));
+                             num_n_tiles, stages, CPS, abox, bbox));
   return 0;
 }
 
 // Geometry + tensor maps of one problem.  KC / NSEG / CPS are decided here and must agree between the
 // problems of one launch (the caller groups by NSEG).
-static int prep_problem(const GemmLaunch& L, bool is_gemm, int KC, ConvGeom* gp, int* nseg, int* cps, CUtensorMap* tmA,
-                        CUtensorMap* tmOut, int* num_m_tiles) {
+static int prep_problem(const GemmLaunch& L, bool is_gemm, int KC, bool a_multi, ConvGeom* gp, int* nseg, int* cps,
+                        CUtensorMap* tmA, CUtensorMap* tmOut, int* num_m_tiles) {
   ConvGeom& g = *gp;
   const int chunks = L.Cin / KC;
   int NSEG = 1, CPS = 1;
@@ -699,11 +709,13 @@ static int prep_problem(const GemmLaunch& L, bool is_gemm, int KC, ConvGeom* gp,
   // exactly the K-major swizzled operand tile.  A: (cKC, chunk, W, H, image)
   const CUtensorMapSwizzle swz = (KC == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   {
-    cuuint64_t dims[5] = {(cuuint64_t)KC, (cuuint64_t)chunks, (cuuint64_t)L.IW, (cuuint64_t)L.IH, (cuuint64_t)L.NB};
-    cuuint64_t str[4] = {(cuuint64_t)KC * 2, (cuuint64_t)L.Cin * 2, (cuuint64_t)L.IW * L.Cin * 2,
+    // (cKC, W, H, chunk, image): the chunk dimension has the SMALLEST stride but sits after W / H, so a box of
+    // CPS chunks lands as [chunk][pixel][KC*2 B] = CPS consecutive operand tiles
+    cuuint64_t dims[5] = {(cuuint64_t)KC, (cuuint64_t)L.IW, (cuuint64_t)L.IH, (cuuint64_t)chunks, (cuuint64_t)L.NB};
+    cuuint64_t str[4] = {(cuuint64_t)L.Cin * 2, (cuuint64_t)L.IW * L.Cin * 2, (cuuint64_t)KC * 2,
                          (cuuint64_t)L.IH * L.IW * L.Cin * 2};
-    cuuint32_t box[5] = {(cuuint32_t)KC, 1, (cuuint32_t)(g.SEG * g.sw), (cuuint32_t)(g.R * g.sh), 1};
-    cuuint32_t es[5] = {1, 1, (cuuint32_t)g.sw, (cuuint32_t)g.sh, 1};
+    cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)(g.SEG * g.sw), (cuuint32_t)(g.R * g.sh), (cuuint32_t)(a_multi ? CPS : 1), 1};
+    cuuint32_t es[5] = {1, (cuuint32_t)g.sw, (cuuint32_t)g.sh, 1, 1};
     if (encode_map(tmA, L.a, 5, dims, str, box, es, swz)) return -1;
   }
   const long long rows_total = static_cast<long long>(L.NB) * L.OH * L.OW;
@@ -742,17 +754,11 @@ int launch_gemm_tc_multi(const GemmLaunch* Ls, int n, cudaStream_t stream) {
   CUtensorMap tmB, tmRes, tmOut2;
   const CUtensorMapSwizzle swz = (KC == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   const int taps = L.kw * L.kh;
-  {  // B: (cKC, chunk, N)
-    const int ktot = taps * L.Cin;
-    cuuint64_t dims[3] = {(cuuint64_t)KC, (cuuint64_t)(ktot / KC), (cuuint64_t)L.N};
-    cuuint64_t str[2] = {(cuuint64_t)KC * 2, (cuuint64_t)ktot * 2};
-    cuuint32_t box[3] = {(cuuint32_t)KC, 1, (cuuint32_t)bn};
-    cuuint32_t es[3] = {1, 1, 1};
-    if (encode_map(&tmB, L.w, 3, dims, str, box, es, swz)) return -1;
-  }
   // weights stay resident in shared memory for the whole CTA when they fit beside >= 3 A stages
   const int b_total = taps * L.Cin * bn * 2;
 
+  // one box per k-block and operand (all CPS chunks) unless switched off for A/B experiments
+  static const bool a_multi = getenv("KIRI_GEMM_ABOX1") == nullptr, b_multi = getenv("KIRI_GEMM_BBOX1") == nullptr;
   // group the problems by tile form
   bool done[kMaxProblems] = {false};
   for (int first = 0; first < n; ++first) {
@@ -765,7 +771,7 @@ int launch_gemm_tc_multi(const GemmLaunch* Ls, int n, cudaStream_t stream) {
       ConvGeom g;
       CUtensorMap ta, to;
       int nseg, cps, mt;
-      if (prep_problem(Ls[i], is_gemm, KC, &g, &nseg, &cps, &ta, &to, &mt)) return -1;
+      if (prep_problem(Ls[i], is_gemm, KC, a_multi, &g, &nseg, &cps, &ta, &to, &mt)) return -1;
       if (P.n == 0) { nseg0 = nseg; cps0 = cps; }
       if (nseg != nseg0 || cps != cps0) continue;
       P.g[P.n] = g; P.tmA[P.n] = ta; P.tmOut[P.n] = to;
@@ -776,6 +782,14 @@ int launch_gemm_tc_multi(const GemmLaunch* Ls, int n, cudaStream_t stream) {
     }
     for (int i = P.n; i <= kMaxProblems; ++i) P.mtile_begin[i] = m_total;
     const int NSEG = nseg0, CPS = cps0;
+    {  // B: (cKC, N, chunk) — a box holds the CPS chunks of one k-block for bn output channels
+      const int ktot = taps * L.Cin;
+      cuuint64_t dims[3] = {(cuuint64_t)KC, (cuuint64_t)L.N, (cuuint64_t)(ktot / KC)};
+      cuuint64_t str[2] = {(cuuint64_t)ktot * 2, (cuuint64_t)KC * 2};
+      cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)bn, (cuuint32_t)(b_multi ? CPS : 1)};
+      cuuint32_t es[3] = {1, 1, 1};
+      if (encode_map(&tmB, L.w, 3, dims, str, box, es, swz)) return -1;
+    }
     tmRes = P.tmOut[0];
     tmOut2 = P.tmOut[0];
     if (resid_epi) {
@@ -787,13 +801,13 @@ int launch_gemm_tc_multi(const GemmLaunch* Ls, int n, cudaStream_t stream) {
         if (encode_rowtile_map(&tmOut2, L.e.out2, rows_total, 256, 256, false)) return -1;
       }
     }
-    const bool bstat = !resid_epi && b_total <= kMaxBResident && getenv("KIRI_GEMM_NO_BSTAT") == nullptr &&
+    const bool bstat = !resid_epi && CPS == 1 && b_total <= kMaxBResident && getenv("KIRI_GEMM_NO_BSTAT") == nullptr &&
                        (g_max_smem - 1024 - (int)sizeof(PipeBarriers) - kEpiWarps * kBufBytes - b_total) >= 3 * CPS * kTileM * KC * 2;
     int rc = -1;
 #define KIRI_LAUNCH(K, S, E)                                                                                          \
-  rc = bstat ? launch_inst<K, S, E, true>(P, tmB, tmRes, tmOut2, L.e, bn, m_total, num_n_tiles, CPS, stream)            \
-             : launch_inst<K, S, E, false>(P, tmB, tmRes, tmOut2, L.e, bn, m_total, num_n_tiles, CPS, stream)
-#define KIRI_LAUNCH_NB(K, S, E) rc = launch_inst<K, S, E, false>(P, tmB, tmRes, tmOut2, L.e, bn, m_total, num_n_tiles, CPS, stream)
+  rc = bstat ? launch_inst<K, S, E, true>(P, tmB, tmRes, tmOut2, L.e, bn, m_total, num_n_tiles, CPS, a_multi ? CPS : 1, b_multi ? CPS : 1, stream)            \
+             : launch_inst<K, S, E, false>(P, tmB, tmRes, tmOut2, L.e, bn, m_total, num_n_tiles, CPS, a_multi ? CPS : 1, b_multi ? CPS : 1, stream)
+#define KIRI_LAUNCH_NB(K, S, E) rc = launch_inst<K, S, E, false>(P, tmB, tmRes, tmOut2, L.e, bn, m_total, num_n_tiles, CPS, a_multi ? CPS : 1, b_multi ? CPS : 1, stream)
     if (!is_gemm) {
       if (KC == 64 && NSEG == 1) KIRI_LAUNCH(64, 1, EPI_BIAS_SILU_BF16);
       else if (KC == 64 && NSEG == 4) KIRI_LAUNCH(64, 4, EPI_BIAS_SILU_BF16);

@@ -70,7 +70,7 @@ gemm_tc_kernel(const __grid_constant__ ProblemSet P, const __grid_constant__ CUt
   constexpr uint64_t kLayout = (KC == 64) ? UMMA_LAYOUT_SW128 : UMMA_LAYOUT_SW64;
   constexpr bool kF32Out = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_F32 || EPI == EPI_BIAS_RESID_LN);
   constexpr bool kResid = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_RESID_LN);
-  constexpr int kNBuf = kResid ? 4 : (BSTAT ? 1 : 2);        // staging tiles per epilogue warp
+  constexpr int kNBuf = kResid ? 4 : ((BSTAT || KC == 32) ? 1 : 2);   // staging tiles per epilogue warp (KC = 32: a third 54 KB stage instead)
   // carve: [resident B] | [stages][A: CPS chunk tiles][B: CPS chunk tiles] | staging | barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -636,7 +636,7 @@ static int launch_inst(const ProblemSet& P, const CUtensorMap& tmB, const CUtens
                        const EpiParams& e, int bn, int num_m_tiles, int num_n_tiles, int CPS, int abox, int bbox,
                        cudaStream_t stream) {
   constexpr bool kResid = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_RESID_LN);
-  constexpr int kNBuf = kResid ? 4 : (BSTAT ? 1 : 2);
+  constexpr int kNBuf = kResid ? 4 : ((BSTAT || KC == 32) ? 1 : 2);
   const ConvGeom& g = P.g[0];
   const int num_chunks = g.taps * g.chunks_per_tap;
   const int b_res = BSTAT ? ((num_chunks * bn * KC * 2 + 1023) & ~1023) : 0;

@@ -299,7 +299,7 @@ def run_ours(args):
         tk = tk2
         tc = time.perf_counter()
         iter_s.append(tc - ti)
-        iter_parts.append((ta - ti, tb - ta, tc - tb))
+        iter_parts.append((ta - ti, tb - ta, tc - tb, [b - a for a, b in zip(tk2["marks"][:-1], tk2["marks"][1:])]))
     res = eng.collect(tk)
     gather([])
     barrier()
@@ -398,7 +398,9 @@ def run_ours(args):
                 "ms_per_step": e2e_dt / args.steps * 1e3, "api": "submit()/collect(), two batches in flight, gc.freeze() after warm-up",
                 "sync_value": e2e_sync_value, "sync_api": "recognize_packed(), one blocking call per batch",
                 "iter_ms_p50_p95_max": [round(float(np.percentile(np.array(iter_s or [0.0]) * 1e3, q)), 3) for q in (50, 95, 100)],
-                "worst_iter_ms_submit_wait_collect": [round(v * 1e3, 3) for v in (iter_parts[int(np.argmax(iter_s))] if iter_s else (0, 0, 0))],
+                "worst_iter_ms_submit_wait_collect": [round(v * 1e3, 3) for v in (iter_parts[int(np.argmax(iter_s))][:3] if iter_s else (0, 0, 0))],
+                "worst_iter_submit_phases_ms": [round(v * 1e3, 3) for v in (iter_parts[int(np.argmax(iter_s))][3] if iter_s else [])],
+                "submit_phases": "upload enqueue | plan | staging + descriptor copy | preprocess launch | encoder launches | CTC + download enqueue",
                 "median_iter_ms_submit_wait_collect": [round(float(np.median([p[k] for p in iter_parts] or [0.0])) * 1e3, 3) for k in range(3)]},
         "gpu_launches": int(launches), "clocks": clocks,
         "roofline": roof, "whole_step_tensor_frac": tensor_frac, "stages": stages, "other_method": other,

@@ -133,6 +133,11 @@ class BatchedRecognizer:
         self._dws: Optional[torch.Tensor] = None
         self._build_tables()
         self.launches = 0           # kernels launched by this engine (for bench's gpu_launches)
+        # per encoder layer: QKV GEMM, attention, fused tail (csrc/encoder_block.cu) — or QKV, attention and the
+        # three GEMMs the tail replaces when it is switched off / not applicable
+        import os as _os
+        fused = _os.environ.get("KIRI_NO_FUSED_BLOCK") is None and cfg.ENC_FF % 128 == 0 and cfg.ENC_FF <= 1024
+        self._layer_launches = 3 if fused else 5
 
     def __del__(self):
         try:
@@ -253,7 +258,7 @@ class BatchedRecognizer:
                                         _lib.ptr(out.get("mem_f32")), out["mem_bf16"].data_ptr(),
                                         _lib.ptr(out.get("logits")), _lib.ptr(out.get("tokens")), _lib.ptr(kv_len),
                                         _lib.stream_ptr()), "kiri_encode")
-        self.launches += self._stem_launches([(B, Wb)]) + 1 + 5 * self.pw.enc_layers + 1 + (1 if want_logits else 0)
+        self.launches += self._stem_launches([(B, Wb)]) + 1 + self._layer_launches * self.pw.enc_layers + 1 + (1 if want_logits else 0)
         return out
 
     def _stem_sub_batch(self, B: int, Wb: int) -> int:
@@ -288,7 +293,7 @@ class BatchedRecognizer:
         return n
 
     def encode_multi(self, planes_list: Sequence[torch.Tensor], want_mem_f32: bool = False, want_tokens: bool = False,
-                     kv_len: Optional[torch.Tensor] = None, want_logits: bool = True):
+                     kv_len: Optional[torch.Tensor] = None, want_logits: bool = True, slot: Optional[str] = None):
         """Several width groups ([B_g, IMG_H, Wb_g] uint8 each) in one call: per-group stems, ONE pass
         of the encoder / CTC head over the concatenated token stream.  Returns the outputs token-major
         ([M, ...], M = sum B_g * Wb_g / 4) plus ``rows`` = [(row0, B_g, T_g)] per group."""
@@ -303,9 +308,15 @@ class BatchedRecognizer:
             M += B * (Wb // 4)
         need = self.lib.kiri_encode_multi_workspace_bytes(self.handle, garr, n, self.stem_chunk)
         ws = self._workspace(need)
-        out = {"mem_bf16": torch.empty((M, D), dtype=torch.bfloat16, device=self.device), "rows": rows}
-        if want_logits:
-            out["logits"] = torch.empty((M, self.pw.Cp), dtype=torch.float32, device=self.device)
+        if slot is None:
+            out = {"mem_bf16": torch.empty((M, D), dtype=torch.bfloat16, device=self.device), "rows": rows}
+            if want_logits:
+                out["logits"] = torch.empty((M, self.pw.Cp), dtype=torch.float32, device=self.device)
+        else:
+            # submit(): outputs live in the ticket's ping-pong slot (no allocator / tensor-map-cache churn per call)
+            out = {"mem_bf16": self._device("_mem" + slot, M * D, torch.bfloat16)[:M * D].view(M, D), "rows": rows}
+            if want_logits:
+                out["logits"] = self._device("_logits" + slot, M * self.pw.Cp, torch.float32)[:M * self.pw.Cp].view(M, self.pw.Cp)
         if want_mem_f32:
             out["mem_f32"] = torch.empty((M, D), dtype=torch.float32, device=self.device)
         if want_tokens:
@@ -315,7 +326,7 @@ class BatchedRecognizer:
                                               _lib.ptr(out.get("logits")), _lib.ptr(out.get("tokens")), _lib.ptr(kv_len),
                                               _lib.stream_ptr()), "kiri_encode_multi")
         self.launches += self._stem_launches([(B, 4 * T) for _, B, T in rows]) + 1             # stem + pool
-        self.launches += 5 * self.pw.enc_layers + 1 + (1 if want_logits else 0)
+        self.launches += self._layer_launches * self.pw.enc_layers + 1 + (1 if want_logits else 0)
         return out
 
     def decode_greedy_multi(self, mem_bf16: torch.Tensor, mem_row0: torch.Tensor, mem_len: torch.Tensor,
@@ -492,6 +503,8 @@ class BatchedRecognizer:
         tk = {"method": method, "streaming": streaming, "n": n}
         if n == 0:
             return tk
+        import time as _time
+        marks = [_time.perf_counter()]                       # host-side phase marks of this call (tk["marks"])
         self._slot ^= 1
         sl = f"_{self._slot}"
         if src.is_cuda:
@@ -503,7 +516,9 @@ class BatchedRecognizer:
                 self._copy_stream.wait_event(self._src_free[self._slot])
             with torch.cuda.stream(self._copy_stream):
                 src_dev[:src.numel()].copy_(src, non_blocking=True)
+        marks.append(_time.perf_counter())                   # [1] upload enqueued
         groups = list(self.plan(entries).items())
+        marks.append(_time.perf_counter())                   # [2] planned
         IMG_H, Cp = self.cfg.IMG_H, self.pw.Cp
         n_lines = sum(len(g[1][0]) for g in groups)
         M = sum(len(g[0]) * (Wb // 4) for Wb, g in groups)
@@ -535,6 +550,7 @@ class BatchedRecognizer:
         dmeta[:meta_words].copy_(hmeta[:meta_words], non_blocking=True)
         if not src.is_cuda:
             self.stream.wait_stream(self._copy_stream)
+        marks.append(_time.perf_counter())                   # [3] staging filled, descriptors enqueued
         # ---- ONE preprocess launch for every width group, one encoder pass over all groups
         sums = self._device("_sums" + sl, 2 * n_lines, torch.int32)
         _lib.check(self.lib.kiri_preprocess_pack(src_dev.data_ptr(), dmeta.data_ptr(), n_lines, IMG_H, smem_max, n_strips_max,
@@ -545,7 +561,9 @@ class BatchedRecognizer:
             self._src_free[self._slot] = torch.cuda.Event()
             self._src_free[self._slot].record()
         kv_len = dmeta[kvo:kvo + n_lines] if self.width_mode == "masked" else None
-        enc = self.encode_multi(planes_list, kv_len=kv_len)
+        marks.append(_time.perf_counter())                   # [4] preprocess launched
+        enc = self.encode_multi(planes_list, kv_len=kv_len, slot=sl)
+        marks.append(_time.perf_counter())                   # [5] encoder launched
         # ---- CTC greedy into ONE packed result buffer: ids[M] | n_ids[L] | conf[L] | frames
         want_frames = streaming and method == "ctc"
         res_words = M + 2 * n_lines + (2 * M if want_frames else 0)
@@ -565,7 +583,8 @@ class BatchedRecognizer:
         hres[:res_words].copy_(dres[:res_words], non_blocking=True)
         done = torch.cuda.Event()
         done.record()
-        tk.update(done=done, hres=hres, res_words=res_words, M=M, n_lines=n_lines, rows=enc["rows"], T_max=T_max,
+        marks.append(_time.perf_counter())                   # [6] CTC + download enqueued
+        tk.update(marks=marks, done=done, hres=hres, res_words=res_words, M=M, n_lines=n_lines, rows=enc["rows"], T_max=T_max,
                   order=np.concatenate([g[1][0] for g in groups]),     # line index of every concatenated slot
                   want_frames=want_frames, enc=enc, n_all=n_all, mem_row0=dmeta[r0o:r0o + n_lines],
                   mem_len=dmeta[mlo:mlo + n_lines], keep=(src_dev, planes_all, dmeta, dres), sl=sl)

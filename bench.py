@@ -210,6 +210,7 @@ def run_ours(args):
     T = cfg.IMG_W // 4
     rec_w = 2 + T
     gathered = torch.empty((world * BATCH, rec_w), dtype=torch.int32, device="cuda") if world > 1 else None
+    gather_cols = torch.arange(T, device="cuda")
 
     def gather(outs):
         """The path's one exchange step: fixed-stride records {n, conf bits, ids[T]} to every rank."""
@@ -219,10 +220,16 @@ def run_ours(args):
         r0 = 0
         for o in outs:
             ids, n, conf = o[0], o[1], o[-1]
-            k = ids.shape[0]
+            k = n.shape[0]
             rec[r0:r0 + k, 0] = n
             rec[r0:r0 + k, 1] = conf.view(torch.int32)
-            rec[r0:r0 + k, 2:2 + min(T, ids.shape[1])] = ids[:, :T]
+            if ids.dim() == 1:
+                # CTC: collapsed ids of all lines in one token-major array; line b owns [row0[b], row0[b] + len[b])
+                pos = prep["mem_row0"][:, None].long() + gather_cols[None, :]
+                ok = gather_cols[None, :] < prep["mem_len"][:, None]
+                rec[r0:r0 + k, 2:2 + T] = torch.where(ok, ids[pos.clamp_(max=ids.numel() - 1)], 0)
+            else:
+                rec[r0:r0 + k, 2:2 + min(T, ids.shape[1])] = ids[:, :T]
             r0 += k
         dist.all_gather_into_tensor(gathered, rec)
 

@@ -187,7 +187,7 @@ def workload_name(args):
 
 def run_ours(args):
     import torch.distributed as dist
-    from kiri_ocr_b200 import fixtures as FX
+    from kiri_ocr_b200 import _lib, fixtures as FX
     from kiri_ocr_b200.engine import BatchedRecognizer
 
     rank = int(os.environ.get("RANK", "0"))
@@ -210,11 +210,19 @@ def run_ours(args):
     T = cfg.IMG_W // 4
     rec_w = 2 + T
     gathered = torch.empty((world * BATCH, rec_w), dtype=torch.int32, device="cuda") if world > 1 else None
-    gather_cols = torch.arange(T, device="cuda")
+    rec_buf = torch.zeros((BATCH, rec_w), dtype=torch.int32, device="cuda")
 
     def gather(outs):
         """The path's one exchange step: fixed-stride records {n, conf bits, ids[T]} to every rank."""
         if world == 1:
+            return
+        if len(outs) == 1 and outs[0][0].dim() == 1:
+            # CTC: one kernel turns the token-major ids into the fixed-stride records
+            ids, n, conf = outs[0]
+            _lib.check(eng.lib.kiri_pack_records(ids.data_ptr(), n.data_ptr(), conf.data_ptr(), prep["mem_row0"].data_ptr(),
+                                                 BATCH, T, rec_buf.data_ptr(), _lib.stream_ptr()), "kiri_pack_records")
+            eng.launches += 1
+            dist.all_gather_into_tensor(gathered, rec_buf)
             return
         rec = torch.zeros((BATCH, rec_w), dtype=torch.int32, device="cuda")
         r0 = 0
@@ -224,10 +232,7 @@ def run_ours(args):
             rec[r0:r0 + k, 0] = n
             rec[r0:r0 + k, 1] = conf.view(torch.int32)
             if ids.dim() == 1:
-                # CTC: collapsed ids of all lines in one token-major array; line b owns [row0[b], row0[b] + len[b])
-                pos = prep["mem_row0"][:, None].long() + gather_cols[None, :]
-                ok = gather_cols[None, :] < prep["mem_len"][:, None]
-                rec[r0:r0 + k, 2:2 + T] = torch.where(ok, ids[pos.clamp_(max=ids.numel() - 1)], 0)
+                continue                                     # CTC: packed by kiri_pack_records above
             else:
                 rec[r0:r0 + k, 2:2 + min(T, ids.shape[1])] = ids[:, :T]
             r0 += k

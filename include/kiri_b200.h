@@ -173,6 +173,12 @@ int kiri_ctc_greedy_multi(const void* logits, int logits_dtype, int n_lines, con
                           int max_T, int C, int ld, int* ids, int* n_ids, float* conf, int* frame_ids,
                           float* frame_prob, cudaStream_t stream);
 
+/* Multi-GPU exchange payload (the one collective of the path): fixed-stride int32 records
+ * {n_ids, confidence bits, ids[T]} per line, built from the token-major output of kiri_ctc_greedy_multi
+ * (line b's ids start at ids[mem_row0[b]]; entries beyond n_ids are zero).  records: [n_lines, 2 + T]. */
+int kiri_pack_records(const int* ids, const int* n_ids, const float* conf, const int* mem_row0, int n_lines, int T,
+                      int* records, cudaStream_t stream);
+
 /* ---------------------------------------------------------------- model-level handle
  * Packed weights (produced once per checkpoint by kiri_ocr_b200/weights.py): BN folded into the conv
  * weights, Linear weights [out, in] in bf16, biases / LayerNorm affines in fp32. */

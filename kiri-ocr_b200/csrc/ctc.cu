@@ -330,3 +330,32 @@ extern "C" int kiri_ctc_align_score(const float* logits, int ld, int C, const in
   KIRI_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// The exchange step's payload: fixed-stride int32 records
+// {n_ids, confidence bits, ids[T]} per line from the token-major CTC output, so that one all-gather moves
+// the results of every rank (ids beyond n_ids are zero).
+namespace kiri {
+__global__ void __launch_bounds__(128)
+pack_records_kernel(const int* __restrict__ ids, const int* __restrict__ n_ids, const float* __restrict__ conf,
+                    const int* __restrict__ row0, int T, int* __restrict__ rec) {
+  pdl_trigger();
+  pdl_wait();
+  const int b = blockIdx.x;
+  const int n = n_ids[b];
+  int* r = rec + static_cast<size_t>(b) * (2 + T);
+  if (threadIdx.x == 0) { r[0] = n; r[1] = __float_as_int(conf[b]); }
+  const int* src = ids + row0[b];
+  for (int t = threadIdx.x; t < T; t += blockDim.x) r[2 + t] = t < n ? src[t] : 0;
+}
+}  // namespace kiri
+
+extern "C" int kiri_pack_records(const int* ids, const int* n_ids, const float* conf, const int* mem_row0, int n_lines, int T,
+                                 int* records, cudaStream_t stream) {
+  KIRI_REQUIRE(ids && n_ids && conf && mem_row0 && records, "kiri_pack_records: null pointer");
+  KIRI_REQUIRE(T > 0, "kiri_pack_records: T must be positive");
+  if (n_lines == 0) return 0;
+  KIRI_CHECK_CUDA(kiri::launch_pdl(kiri::pack_records_kernel, dim3(n_lines), dim3(128), 0, stream, ids, n_ids, conf, mem_row0, T,
+                                   records));
+  return 0;
+}

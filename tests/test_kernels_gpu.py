@@ -447,3 +447,26 @@ def test_encoder_block_fused_vs_three_gemms_and_torch(lib, M, FF, with_ln):
         ea_3 = float((a.float() - a_fin.float()).abs().max())
         assert ea_ref < 0.06, ea_ref
         assert ea_3 < 0.05, ea_3
+
+
+def test_pack_records_matches_numpy(lib):
+    """Fixed-stride exchange records {n_ids, conf bits, ids[T]} from the token-major CTC output."""
+    rng = np.random.default_rng(3)
+    T = 160
+    lens = np.array([160, 32, 96, 64, 128], np.int32)
+    row0 = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int32)
+    ids = rng.integers(2, 200, int(lens.sum())).astype(np.int32)
+    n_ids = np.array([0, 32, 17, 5, 100], np.int32)
+    conf = rng.random(5).astype(np.float32)
+    rec = torch.full((5, 2 + T), -7, dtype=torch.int32, device="cuda")
+    d = lambda a: torch.from_numpy(a).cuda()
+    t_ids, t_n, t_c, t_r = d(ids), d(n_ids), d(conf), d(row0)
+    _lib.check(lib.kiri_pack_records(t_ids.data_ptr(), t_n.data_ptr(), t_c.data_ptr(), t_r.data_ptr(), 5, T, rec.data_ptr(),
+                                     _lib.stream_ptr()))
+    sync()
+    got = rec.cpu().numpy()
+    for b in range(5):
+        assert got[b, 0] == n_ids[b] and got[b, 1:2].view(np.float32)[0] == conf[b]
+        want = np.zeros(T, np.int32)
+        want[:n_ids[b]] = ids[row0[b]:row0[b] + n_ids[b]]
+        assert np.array_equal(got[b, 2:], want)

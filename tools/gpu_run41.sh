@@ -1,5 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_kernels_gpu.py -m gpu -q -k pack_records 2>&1 | tail -1
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 40 --warmup 3 > gpurun_out/bench_2gpu.json 2> gpurun_out/bench_2gpu.err; echo "== 2gpu rc=$?"
 tail -3 gpurun_out/bench_2gpu.err
 python - <<PY

@@ -178,3 +178,26 @@ def test_page_boxes_and_empty_crop(engines):
     res = eng.recognize_boxes(page, boxes, "ctc")
     assert len(res) == len(boxes)
     assert res[-1] is None and all(r is not None for r in res[:-1])
+
+
+@pytest.mark.gpu
+def test_multi_group_launches_equal_per_group_runs(engines):
+    """encode_multi (one launch per conv layer / conv1 / pool / attention for ALL width groups, one token stream)
+    must reproduce the per-group encode() bit for bit: every line is independent of its batch."""
+    eng, sd = engines("hard", "bucketed")
+    crops = FX.make_line_crops(40, seed=23)
+    buf, ent = eng.pack_crops(crops)
+    groups = eng.plan(ent)
+    assert len(groups) >= 3
+    planes_list, singles = [], []
+    for Wb, (idx, descs, smem, n_strips) in groups.items():
+        planes, _ = eng.preprocess(buf.cuda(), descs, Wb, smem, n_strips)
+        planes_list.append(planes)
+        e = eng.encode(planes)
+        torch.cuda.synchronize()
+        singles.append((e["logits"].clone(), e["mem_bf16"].clone()))
+    multi = eng.encode_multi(planes_list)
+    torch.cuda.synchronize()
+    for (r0, B, T), (lg, mem) in zip(multi["rows"], singles):
+        assert torch.equal(multi["logits"][r0:r0 + B * T].view(B, T, -1), lg)
+        assert torch.equal(multi["mem_bf16"][r0:r0 + B * T], mem.view(B * T, -1))

@@ -14,7 +14,7 @@
 //
 // Roles (608 threads): warps 0-15 epilogue (thread = one tile row x one column quarter), warps 16-17 TMA
 // producers (alternate ring units), warp 18 MMA issuer + TMEM owner.
-// TMEM: X = columns [0,256) (out-proj accumulator, then x + b2 + FFN), H[2] = 2 x 64 columns (hidden chunk).
+// TMEM: X = columns [0,256) (out-proj accumulator, then x + b2 + FFN), H[2] = 2 x 128 columns (a pair of hidden chunks).
 // Shared memory (227 KB): ring 96 KB | A2 64 KB | hidden chunk 2 x 16 KB | staging 32 KB; the last three
 // double as the per-warp 8 KB landing zone of the fp32 residual tile / staging of the x and a stores.
 #include "gemm_tc.cuh"
@@ -90,7 +90,7 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
     mbar_init(&bars->x_empty, kEbEpiWarps);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&bars->acc2_full[b], 1);
-      mbar_init(&bars->acc2_empty[b], kEbEpiWarps);
+      mbar_init(&bars->acc2_empty[b], 2 * kEbEpiWarps);      // every warp arrives once per hidden chunk of the pair
       mbar_init(&bars->h_full[b], kEbEpiWarps);
       mbar_init(&bars->h_empty[b], 1);
     }
@@ -136,20 +136,24 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
                 tma_load_3d(dst, &tmWo, fb, 0, j, 0);
               }
             } else {
-              const int m = n - 8;
-              int c;
+              // FFN units: W1a_0 W1b_0 | W1a_1 W1b_1 W2_0 W2_1 | W1a_2 W1b_2 W2_2 W2_3 | ... | W2_{nC-2} W2_{nC-1}
+              //   W1a_p / W1b_p = rows [128p, 128p+128) of W1, K halves (two 64-wide K chunks each): the first GEMM runs
+              //   in PAIRS of hidden chunks (N = 128: an N = 64 MMA re-reads its 4 KB A slice for half the columns)
+              const int m = n - 8, nP = nC >> 1;
+              int idx;
               bool is_w1;
-              if (m < 2) { is_w1 = true; c = m; }
-              else if (m == 2 * nC - 1) { is_w1 = false; c = nC - 1; }
-              else if (m & 1) { is_w1 = true; c = (m + 1) >> 1; }
-              else { is_w1 = false; c = (m - 2) >> 1; }
+              if (m < 2) { is_w1 = true; idx = m; }
+              else {
+                const int q = m - 2, pp = q >> 2, r = q & 3;
+                if (pp < nP - 1 && r < 2) { is_w1 = true; idx = 2 * (pp + 1) + r; }
+                else { is_w1 = false; idx = 2 * pp + (pp < nP - 1 ? r - 2 : r); }
+              }
               mbar_arrive_expect_tx(fb, 32768);
               if (is_w1) {
-                // ONE box {64 k, 64 rows, 4 K-chunks}: lands as four [64 x 128 B] K-major tiles.  (Four separate
-                // boxes cost the issuing thread ~350 cycles each and made this producer the FFN's bottleneck.)
-                tma_load_3d(dst, &tmW1, fb, 0, 64 * c, 0);
+                // ONE box {64 k, 128 rows, 2 K-chunks}: lands as two [128 x 128 B] K-major tiles
+                tma_load_3d(dst, &tmW1, fb, 0, 128 * (idx >> 1), 2 * (idx & 1));
               } else {
-                tma_load_3d(dst, &tmW2, fb, 0, c, 0);
+                tma_load_3d(dst, &tmW2, fb, 0, idx, 0);
               }
             }
           }
@@ -161,7 +165,7 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
     }
   } else if (warp == kEbMmaWarp) {
     // ============================ MMA issuer ============================
-    const uint32_t idesc256 = umma_idesc_bf16(128, 256), idesc64 = umma_idesc_bf16(128, 64);
+    const uint32_t idesc256 = umma_idesc_bf16(128, 256);
     const uint32_t ring_addr = smem_u32(ring), a2_addr = smem_u32(sA2), h_addr = smem_u32(sH);
     const uint32_t x_tmem = tmem_base + kXCol;
     int slot = 0;
@@ -171,32 +175,36 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
     long long tq = timing ? clock64() : 0, m_ring = 0, m_a2 = 0, m_hf = 0, m_ae = 0, m_other = 0;
     const long long m_t0 = tq;
     auto next_slot = [&]() { if (++slot == kSlots) { slot = 0; phase ^= 1; } };
-    // hidden chunk c: H[c&1] = A2 @ W1[64c:64c+64, :]^T   (K = 256: four 64-wide K chunks of four k16 steps)
-    auto issue_ff1 = [&](int c) {
-      const int b = c & 1, u = c >> 1;
+    // hidden chunk pair pp: H[pp&1] (128 TMEM columns) = A2 @ W1[128pp:128pp+128, :]^T; K = 256 arrives as two ring
+    // units of two 64-wide K chunks
+    const uint32_t idesc128 = umma_idesc_bf16(128, 128);
+    auto issue_ff1_pair = [&](int pp) {
+      const int b = pp & 1, u = pp >> 1;
       EB_T(m_other);
-      mbar_wait(&bars->acc2_empty[b], (u & 1) ^ 1);              // GELU of chunk c-2 has drained H[b]
+      mbar_wait(&bars->acc2_empty[b], (u & 1) ^ 1);              // GELU of pair pp-2 has drained H[b]
       EB_T(m_ae);
-      mbar_wait(&bars->full[slot], phase);
-      EB_T(m_ring);
-      tc_fence_after();
-      const uint32_t w_addr = ring_addr + slot * kSlotBytes;
-      const uint32_t d_tmem = tmem_base + kHCol + 64 * b;
-      if (elect_one()) {
+      const uint32_t d_tmem = tmem_base + kHCol + 128 * b;
+      for (int kh = 0; kh < 2; ++kh) {
+        mbar_wait(&bars->full[slot], phase);
+        EB_T(m_ring);
+        tc_fence_after();
+        const uint32_t w_addr = ring_addr + slot * kSlotBytes;
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
+          for (int kk = 0; kk < 2; ++kk) {
 #pragma unroll
-          for (int h = 0; h < 4; ++h) {
-            const uint64_t ad = umma_desc_kmajor(a2_addr + kk * 16384 + h * 32, 1024, UMMA_LAYOUT_SW128);
-            const uint64_t bd = umma_desc_kmajor(w_addr + kk * 8192 + h * 32, 1024, UMMA_LAYOUT_SW128);
-            umma_bf16(d_tmem, ad, bd, idesc64, (kk | h) != 0 ? 1u : 0u);
+            for (int h = 0; h < 4; ++h) {
+              const uint64_t ad = umma_desc_kmajor(a2_addr + (2 * kh + kk) * 16384 + h * 32, 1024, UMMA_LAYOUT_SW128);
+              const uint64_t bd = umma_desc_kmajor(w_addr + kk * 16384 + h * 32, 1024, UMMA_LAYOUT_SW128);
+              umma_bf16(d_tmem, ad, bd, idesc128, (kh | kk | h) != 0 ? 1u : 0u);
+            }
           }
+          umma_commit(&bars->empty[slot]);
+          if (kh == 1) umma_commit(&bars->acc2_full[b]);
         }
-        umma_commit(&bars->empty[slot]);
-        umma_commit(&bars->acc2_full[b]);
+        __syncwarp();
+        next_slot();
       }
-      __syncwarp();
-      next_slot();
     };
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       if (it > 0) mbar_wait(&bars->x_empty, (it - 1) & 1);       // the previous tile's x has been read out of TMEM
@@ -233,9 +241,9 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
       mbar_wait(&bars->a2_ready, it & 1);
       EB_T(m_a2);
       tc_fence_after();
-      issue_ff1(0);
+      issue_ff1_pair(0);
       for (int c = 0; c < nC; ++c) {
-        if (c + 1 < nC) issue_ff1(c + 1);
+        if ((c & 1) == 0 && c + 2 < nC) issue_ff1_pair((c >> 1) + 1);
         const int b = c & 1, u = c >> 1;
         EB_T(m_other);
         mbar_wait(&bars->h_full[b], u & 1);                      // gelu(H chunk c) is in shared memory
@@ -380,15 +388,16 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
       // ================= hidden chunks: gelu(H + b1) -> bf16 A operand of the second GEMM
       for (int c = 0; c < nC; ++c) {
         const int b = c & 1, u = c >> 1;
+        const int tb = (c >> 1) & 1;                             // TMEM buffer of this chunk's pair
         uint32_t r[16];
-        mbar_wait(&bars->acc2_full[b], u & 1);
+        mbar_wait(&bars->acc2_full[tb], (c >> 2) & 1);
         EB_T(e_af);
         tc_fence_after();
-        tmem_ld16(lane_taddr + kHCol + 64 * b + 16 * cq, r);
+        tmem_ld16(lane_taddr + kHCol + 128 * tb + 64 * b + 16 * cq, r);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->acc2_empty[b]);
+        if (lane == 0) mbar_arrive(&bars->acc2_empty[tb]);
         uint4 pk[2];
         const float* b1 = p.c.b1 + c * 64 + cq * 16;
 #pragma unroll
@@ -512,16 +521,16 @@ int launch_encoder_block(const void* o, float* x, void* a_out, const void* wo, c
   KIRI_REQUIRE(o && x && wo && w1 && w2 && consts_host, "encoder_block: null pointer");
   KIRI_REQUIRE(!has_ln_out || a_out != nullptr, "encoder_block: LayerNorm output without a_out");
   KIRI_REQUIRE(M % 32 == 0, "encoder_block: token count %d must be a multiple of 32", M);
-  KIRI_REQUIRE(FF % 128 == 0 && FF >= 128 && FF <= 1024, "encoder_block: FF width %d must be a multiple of 128, at most 1024", FF);
+  KIRI_REQUIRE(FF % 128 == 0 && FF >= 256 && FF <= 1024, "encoder_block: FF width %d must be a multiple of 128 in [256, 1024]", FF);
   if (M == 0) return 0;
   const int sms = gemm_tc_num_sms();
   CUtensorMap tmO, tmWo, tmW1, tmW2, tmX, tmA;
   if (encode_kchunk_map(&tmO, o, M, 256, 128)) return -1;
   if (encode_kchunk_map(&tmWo, wo, 256, 256, 256)) return -1;
-  {  // W1 [FF, 256]: dims (k 64, row, K-chunk) so that a {64, 64, 4} box is four consecutive K-major tiles
+  {  // W1 [FF, 256]: dims (k 64, row, K-chunk) so that a {64, 128, 2} box is two consecutive K-major tiles
     cuuint64_t dims[3] = {64, (cuuint64_t)FF, 4};
     cuuint64_t str[2] = {512, 128};
-    cuuint32_t box[3] = {64, 64, 4};
+    cuuint32_t box[3] = {64, 128, 2};
     cuuint32_t es[3] = {1, 1, 1};
     if (encode_map(&tmW1, w1, 3, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
   }

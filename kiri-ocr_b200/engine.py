@@ -16,6 +16,8 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os as _os
+import time as _time
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -135,7 +137,6 @@ class BatchedRecognizer:
         self.launches = 0           # kernels launched by this engine (for bench's gpu_launches)
         # per encoder layer: QKV GEMM, attention, fused tail (csrc/encoder_block.cu) — or QKV, attention and the
         # three GEMMs the tail replaces when it is switched off / not applicable
-        import os as _os
         fused = _os.environ.get("KIRI_NO_FUSED_BLOCK") is None and cfg.ENC_FF % 128 == 0 and cfg.ENC_FF <= 1024
         self._layer_launches = 3 if fused else 5
 
@@ -503,7 +504,6 @@ class BatchedRecognizer:
         tk = {"method": method, "streaming": streaming, "n": n}
         if n == 0:
             return tk
-        import time as _time
         marks = [_time.perf_counter()]                       # host-side phase marks of this call (tk["marks"])
         self._slot ^= 1
         sl = f"_{self._slot}"

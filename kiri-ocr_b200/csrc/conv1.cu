@@ -101,6 +101,120 @@ conv1_bn_silu_kernel(const __grid_constant__ Conv1Groups G, int H, const __grid_
 
 
 // ------------------------------------------------------------------------------------------------
+// Packed-fp32 form (default): Blackwell's FFMA2 does two IEEE fp32 FMAs per instruction, but its weight
+// operand must sit in (uniform) registers instead of the constant bank.  A thread therefore computes TWO
+// vertically adjacent pixels for a PAIR of output channels at a time: one weight-pair load feeds two
+// FFMA2s, the 432 FMAs per pixel become 216 FFMA2 + 108 loads, and the SiLU runs on pairs too
+// (mul2, 2 x tanh, fma2, mul2).  Results are bit-identical to the scalar kernel (same fp32 operations).
+struct Conv1PairParams {
+  float2 w[(kC1 / 2) * 9];     // [channel pair][tap] = {w[2c][k], w[2c+1][k]}, BN folded
+  float2 b[kC1 / 2];
+};
+
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)),
+        "l"(reinterpret_cast<unsigned long long&>(c)));
+  return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  float2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+  return d;
+}
+// silu_fast on a pair, the same operations in the same order: x * fma(0.5, tanh(0.5 x), 0.5)
+__device__ __forceinline__ float2 silu_fast2(float2 x) {
+  const float2 half2 = make_float2(0.5f, 0.5f);
+  const float2 h = fmul2(half2, x);
+  float2 t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(h.x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(h.y));
+  return fmul2(x, ffma2(half2, t, half2));
+}
+
+// tile = 2 image rows x 128 columns; thread = one column, both rows
+__global__ void __launch_bounds__(kConv1Threads)
+conv1_pair_kernel(const __grid_constant__ Conv1Groups G, int H, const __grid_constant__ Conv1PairParams p) {
+  __shared__ float s_norm[256];
+  __shared__ __align__(16) uint8_t s_out[2 * kConv1Threads * kC1Pad * 2];   // 2 x 16 KiB staging tiles
+  const int tid = threadIdx.x;
+  for (int v = tid; v < 256; v += kConv1Threads)
+    s_norm[v] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(v), 255.0f), 0.5f), 0.5f);
+  __syncthreads();
+  pdl_trigger();
+  pdl_wait();                                       // the planes come from the previous kernel
+
+  int gi = 0;
+#pragma unroll
+  for (int i = 1; i < 8; ++i)
+    if (i < G.n && static_cast<int>(blockIdx.x) >= G.tile_begin[i]) gi = i;
+  const int W = G.W[gi];
+  const uint8_t* __restrict__ planes = G.planes[gi];
+  __nv_bfloat16* __restrict__ out = G.out[gi];
+  const int tiles_per_row = W / kConv1Threads;
+  const int tile = static_cast<int>(blockIdx.x) - G.tile_begin[gi];
+  const int xt = tile % tiles_per_row;
+  const int bp = tile / tiles_per_row;            // b * (H/2) + y/2
+  const int y = (bp % (H / 2)) * 2;
+  const int b = bp / (H / 2);
+  const int x = xt * kConv1Threads + tid;
+  const uint8_t* img = planes + static_cast<size_t>(b) * H * W;
+
+  float in[4][3];                                  // rows y-1 .. y+2, columns x-1 .. x+1
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int yy = y + r - 1;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int xx = x + kx - 1;
+      const bool ok = (yy >= 0) && (yy < H) && (xx >= 0) && (xx < W);
+      in[r][kx] = ok ? s_norm[img[yy * W + xx]] : 0.0f;            // conv zero padding
+    }
+  }
+  uint4* so = reinterpret_cast<uint4*>(s_out);
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {                    // 8 channels (four pairs) per 16-byte chunk
+    uint32_t pk0[4], pk1[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int cp = j * 4 + q;
+      float2 a0 = p.b[cp], a1 = a0;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const float2 wv = p.w[cp * 9 + ky * 3 + kx];
+          a0 = ffma2(make_float2(in[ky][kx], in[ky][kx]), wv, a0);
+          a1 = ffma2(make_float2(in[ky + 1][kx], in[ky + 1][kx]), wv, a1);
+        }
+      const float2 s0 = silu_fast2(a0), s1 = silu_fast2(a1);
+      pk0[q] = pack_bf16x2(s0.x, s0.y);
+      pk1[q] = pack_bf16x2(s1.x, s1.y);
+    }
+    so[tid * 8 + (j ^ (tid & 7))] = make_uint4(pk0[0], pk0[1], pk0[2], pk0[3]);
+    so[kConv1Threads * 8 + tid * 8 + (j ^ (tid & 7))] = make_uint4(pk1[0], pk1[1], pk1[2], pk1[3]);
+  }
+#pragma unroll
+  for (int j = 6; j < 8; ++j) {                    // the 16 zero channels
+    so[tid * 8 + (j ^ (tid & 7))] = make_uint4(0u, 0u, 0u, 0u);
+    so[kConv1Threads * 8 + tid * 8 + (j ^ (tid & 7))] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    uint4* dst = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * H + y + r) * W + xt * kConv1Threads) * kC1Pad);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int q = i * kConv1Threads + tid;
+      const int px = q >> 3, j = q & 7;
+      dst[q] = so[r * kConv1Threads * 8 + px * 8 + (j ^ (px & 7))];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Tensor-core form (opt-in, KIRI_CONV1_TC=1; measured 11 % SLOWER than the FFMA kernel above, see kiri_conv1).
 // The 9-tap products run on warp-level mma.sync m16n8k16; what remains is the SiLU epilogue and the
 // 128 B/pixel store, which also bound the FFMA form.  Exactness is kept without fp32
@@ -247,6 +361,18 @@ extern "C" int kiri_conv1_multi(const uint8_t* const* planes_u8, void* const* ou
   }
   for (int i = G.n; i < 9; ++i) G.tile_begin[i] = static_cast<int>(tiles);
   if (tiles == 0) return 0;
+  static const bool scalar_form = getenv("KIRI_CONV1_SCALAR") != nullptr;
+  if (!scalar_form && H % 2 == 0) {
+    // tiles of the pair kernel cover two rows: half as many, same per-group order
+    Conv1PairParams pp;
+    for (int c = 0; c < kC1 / 2; ++c) {
+      for (int k = 0; k < 9; ++k) pp.w[c * 9 + k] = make_float2(w_host[(2 * c) * 9 + k], w_host[(2 * c + 1) * 9 + k]);
+      pp.b[c] = make_float2(b_host[2 * c], b_host[2 * c + 1]);
+    }
+    for (int i = 0; i <= 8; ++i) G.tile_begin[i] /= 2;
+    KIRI_CHECK_CUDA(launch_pdl(conv1_pair_kernel, dim3(static_cast<unsigned>(tiles / 2)), dim3(kConv1Threads), 0, stream, G, H, pp));
+    return 0;
+  }
   Conv1Params p;
   for (int i = 0; i < kC1 * 9; ++i) p.w[i] = w_host[i];
   for (int i = 0; i < kC1; ++i) p.b[i] = b_host[i];

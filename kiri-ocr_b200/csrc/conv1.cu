@@ -111,29 +111,6 @@ struct Conv1PairParams {
   float2 b[kC1 / 2];
 };
 
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-  float2 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(reinterpret_cast<unsigned long long&>(d))
-      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)),
-        "l"(reinterpret_cast<unsigned long long&>(c)));
-  return d;
-}
-__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
-  float2 d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<unsigned long long&>(d))
-      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
-  return d;
-}
-// silu_fast on a pair, the same operations in the same order: x * fma(0.5, tanh(0.5 x), 0.5)
-__device__ __forceinline__ float2 silu_fast2(float2 x) {
-  const float2 half2 = make_float2(0.5f, 0.5f);
-  const float2 h = fmul2(half2, x);
-  float2 t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(h.x));
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(h.y));
-  return fmul2(x, ffma2(half2, t, half2));
-}
-
 // tile = 2 image rows x 128 columns; thread = one column, both rows
 __global__ void __launch_bounds__(kConv1Threads)
 conv1_pair_kernel(const __grid_constant__ Conv1Groups G, int H, const __grid_constant__ Conv1PairParams p) {

@@ -360,6 +360,7 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
 #pragma unroll
       for (int t = 0; t < 64; ++t) { const float d = __uint_as_float(v[t]) - mean; sq = fmaf(d, d, sq); }
       const float rstd = 1.0f / sqrtf(row_total(sq) * (1.0f / 256.0f) + 1e-5f);
+      const float2 nmean2 = make_float2(-mean, -mean), rstd2v = make_float2(rstd, rstd);
       tmem_st_wait();
       // every warp has consumed its residual slice: A2 (which overlays them) may be written
       asm volatile("bar.sync 1, 512;" ::: "memory");
@@ -370,12 +371,15 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
           const int col = cb + t * 8;
           const float* gg = p.c.ln_mid_g + col;
           const float* hh = p.c.ln_mid_b + col;
-          float y[8];
+          float2 y[4];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) y[u] = (__uint_as_float(v[t * 8 + u]) - mean) * rstd * gg[u] + hh[u];
+          for (int u = 0; u < 4; ++u) {
+            const float2 dd = fadd2(make_float2(__uint_as_float(v[t * 8 + 2 * u]), __uint_as_float(v[t * 8 + 2 * u + 1])), nmean2);
+            y[u] = ffma2(fmul2(dd, rstd2v), make_float2(gg[2 * u], gg[2 * u + 1]), make_float2(hh[2 * u], hh[2 * u + 1]));
+          }
           uint4 pk;
-          pk.x = pack_bf16x2(y[0], y[1]); pk.y = pack_bf16x2(y[2], y[3]);
-          pk.z = pack_bf16x2(y[4], y[5]); pk.w = pack_bf16x2(y[6], y[7]);
+          pk.x = pack_bf16x2(y[0].x, y[0].y); pk.y = pack_bf16x2(y[1].x, y[1].y);
+          pk.z = pack_bf16x2(y[2].x, y[2].y); pk.w = pack_bf16x2(y[3].x, y[3].y);
           *reinterpret_cast<uint4*>(ob + stg_off(lane, t)) = pk;
         }
       }
@@ -403,11 +407,13 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           const float* bb = b1 + t * 8;
-          float y[8];
+          float2 y[4];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) y[k] = gelu_tanh_erf(__uint_as_float(r[t * 8 + k]) + bb[k]);
-          pk[t].x = pack_bf16x2(y[0], y[1]); pk[t].y = pack_bf16x2(y[2], y[3]);
-          pk[t].z = pack_bf16x2(y[4], y[5]); pk[t].w = pack_bf16x2(y[6], y[7]);
+          for (int k = 0; k < 4; ++k)
+            y[k] = gelu_tanh_erf2(fadd2(make_float2(__uint_as_float(r[t * 8 + 2 * k]), __uint_as_float(r[t * 8 + 2 * k + 1])),
+                                        make_float2(bb[2 * k], bb[2 * k + 1])));
+          pk[t].x = pack_bf16x2(y[0].x, y[0].y); pk[t].y = pack_bf16x2(y[1].x, y[1].y);
+          pk[t].z = pack_bf16x2(y[2].x, y[2].y); pk[t].w = pack_bf16x2(y[3].x, y[3].y);
         }
         EB_T(e_ff);
         mbar_wait(&bars->h_empty[b], (u & 1) ^ 1);               // the MMAs of chunk c-2 have read H[b]
@@ -456,6 +462,7 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
 #pragma unroll
         for (int t = 0; t < 64; ++t) { const float d = __uint_as_float(v[t]) - mean2; sq2 = fmaf(d, d, sq2); }
         const float rstd2 = 1.0f / sqrtf(row_total(sq2) * (1.0f / 256.0f) + 1e-5f);
+        const float2 nmean2b = make_float2(-mean2, -mean2), rstd2vb = make_float2(rstd2, rstd2);
         if (lane == 0) bulk_wait_group_read<0>();                // the x stores have read their tiles
         __syncwarp();
         uint8_t* ob = buf(0);
@@ -464,12 +471,15 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
           const int col = cb + t * 8;
           const float* gg = p.c.ln_out_g + col;
           const float* hh = p.c.ln_out_b + col;
-          float y[8];
+          float2 y[4];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) y[u] = (__uint_as_float(v[t * 8 + u]) - mean2) * rstd2 * gg[u] + hh[u];
+          for (int u = 0; u < 4; ++u) {
+            const float2 dd = fadd2(make_float2(__uint_as_float(v[t * 8 + 2 * u]), __uint_as_float(v[t * 8 + 2 * u + 1])), nmean2b);
+            y[u] = ffma2(fmul2(dd, rstd2vb), make_float2(gg[2 * u], gg[2 * u + 1]), make_float2(hh[2 * u], hh[2 * u + 1]));
+          }
           uint4 pk;
-          pk.x = pack_bf16x2(y[0], y[1]); pk.y = pack_bf16x2(y[2], y[3]);
-          pk.z = pack_bf16x2(y[4], y[5]); pk.w = pack_bf16x2(y[6], y[7]);
+          pk.x = pack_bf16x2(y[0].x, y[0].y); pk.y = pack_bf16x2(y[1].x, y[1].y);
+          pk.z = pack_bf16x2(y[2].x, y[2].y); pk.w = pack_bf16x2(y[3].x, y[3].y);
           *reinterpret_cast<uint4*>(ob + stg_off(lane, t)) = pk;
         }
         fence_proxy_async();

@@ -46,6 +46,12 @@ __device__ __forceinline__ float epi_act(float v) {
   if (EPI == EPI_BIAS_GELU_BF16) return gelu_tanh_erf(v);
   return v;
 }
+template <int EPI>
+__device__ __forceinline__ float2 epi_act2(float2 v) {       // a pair per instruction (packed fp32 math)
+  if (EPI == EPI_BIAS_SILU_BF16) return silu_fast2(v);
+  if (EPI == EPI_BIAS_GELU_BF16) return gelu_tanh_erf2(v);
+  return v;
+}
 
 // Role-level cycle accounting of CTA 0 (KIRI_GEMM_TIMING=1 -> EpiParams::timing), read back with
 // kiri_debug_gemm_timing(): [0] TMA wait-empty [1] TMA total [2] MMA wait-full [3] MMA wait-tmem-empty
@@ -497,12 +503,14 @@ gemm_tc_kernel(const __grid_constant__ ProblemSet P, const __grid_constant__ CUt
               const float4 b0 = *reinterpret_cast<const float4*>(sbias + c0 + t * 8);
               const float4 b1 = *reinterpret_cast<const float4*>(sbias + c0 + t * 8 + 4);
               const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-              float y[8];
+              float2 y[4];
 #pragma unroll
-              for (int u = 0; u < 8; ++u) y[u] = epi_act<EPI>(__uint_as_float(src[o8 + u]) + bb[u]);
+              for (int u = 0; u < 4; ++u)
+                y[u] = epi_act2<EPI>(fadd2(make_float2(__uint_as_float(src[o8 + 2 * u]), __uint_as_float(src[o8 + 2 * u + 1])),
+                                           make_float2(bb[2 * u], bb[2 * u + 1])));
               uint4 pk;
-              pk.x = pack_bf16x2(y[0], y[1]); pk.y = pack_bf16x2(y[2], y[3]);
-              pk.z = pack_bf16x2(y[4], y[5]); pk.w = pack_bf16x2(y[6], y[7]);
+              pk.x = pack_bf16x2(y[0].x, y[0].y); pk.y = pack_bf16x2(y[1].x, y[1].y);
+              pk.z = pack_bf16x2(y[2].x, y[2].y); pk.w = pack_bf16x2(y[3].x, y[3].y);
               *reinterpret_cast<uint4*>(ob + stg_off(lane, t)) = pk;
             }
           }

@@ -109,6 +109,21 @@ __device__ __forceinline__ float gelu_tanh_erf(float v) {
   const float h = 0.5f * v;
   return fmaf(h, t, h);
 }
+// the same on a pair (packed fp32 multiplies / FMAs; min, max and tanh stay scalar)
+__device__ __forceinline__ float2 gelu_tanh_erf2(float2 v) {
+  float2 u = fmul2(v, make_float2(0.70710678118654752440f, 0.70710678118654752440f));
+  u.x = fminf(fmaxf(u.x, -4.5f), 4.5f);
+  u.y = fminf(fmaxf(u.y, -4.5f), 4.5f);
+  const float2 u2 = fmul2(u, u);
+  float2 p = ffma2(make_float2(-0.00181363f, -0.00181363f), u2, make_float2(0.10414107f, 0.10414107f));
+  p = ffma2(p, u2, make_float2(1.12812423f, 1.12812423f));
+  const float2 a = fmul2(u, p);
+  float2 t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(a.x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(a.y));
+  const float2 h = fmul2(make_float2(0.5f, 0.5f), v);
+  return ffma2(h, t, h);
+}
 
 
 }  // namespace kiri

@@ -112,15 +112,22 @@ __device__ __forceinline__ void attn_tile(__nv_bfloat16* __restrict__ obase, con
   mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
   mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
   const float o0 = mx0 * sl2, o1 = mx1 * sl2;
-  float sum0 = 0.f, sum1 = 0.f;
+  float sum0, sum1;
+  {
+    // packed fp32 math: one FFMA2 scales and shifts two scores, one FADD2 accumulates two probabilities
+    const float2 sc = make_float2(sl2, sl2), n0 = make_float2(-o0, -o0), n1 = make_float2(-o1, -o1);
+    float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
 #pragma unroll
-  for (int nb = 0; nb < NB; ++nb) {
-    s[nb][0] = ex2_approx(fmaf(s[nb][0], sl2, -o0));
-    s[nb][1] = ex2_approx(fmaf(s[nb][1], sl2, -o0));
-    s[nb][2] = ex2_approx(fmaf(s[nb][2], sl2, -o1));
-    s[nb][3] = ex2_approx(fmaf(s[nb][3], sl2, -o1));
-    sum0 += s[nb][0] + s[nb][1];
-    sum1 += s[nb][2] + s[nb][3];
+    for (int nb = 0; nb < NB; ++nb) {
+      const float2 a = ffma2(make_float2(s[nb][0], s[nb][1]), sc, n0);
+      const float2 b = ffma2(make_float2(s[nb][2], s[nb][3]), sc, n1);
+      s[nb][0] = ex2_approx(a.x); s[nb][1] = ex2_approx(a.y);
+      s[nb][2] = ex2_approx(b.x); s[nb][3] = ex2_approx(b.y);
+      acc0 = fadd2(acc0, make_float2(s[nb][0], s[nb][1]));
+      acc1 = fadd2(acc1, make_float2(s[nb][2], s[nb][3]));
+    }
+    sum0 = acc0.x + acc0.y;
+    sum1 = acc1.x + acc1.y;
   }
   sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
   sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);

@@ -317,7 +317,7 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
 #pragma unroll
       for (int c = 0; c < 2; ++c) tmem_ld32(lane_taddr + kXCol + cb + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
       tmem_ld_wait();
-      float sum = 0.f;
+      float2 sum2 = make_float2(0.f, 0.f);
       if (valid) mbar_wait(&bars->res_full[ew][1], res_cnt & 1);
       EB_T(e_res);
 #pragma unroll
@@ -327,16 +327,15 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
           const float* bp = p.c.bo + cb + c * 32 + 4 * t;
-          const float4 b = make_float4(bp[0], bp[1], bp[2], bp[3]);
           float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (valid) r4 = *reinterpret_cast<const float4*>(rb + stg_off(lane, t));
-          const float o0 = __uint_as_float(v[c * 32 + 4 * t]) + b.x + r4.x;
-          const float o1 = __uint_as_float(v[c * 32 + 4 * t + 1]) + b.y + r4.y;
-          const float o2 = __uint_as_float(v[c * 32 + 4 * t + 2]) + b.z + r4.z;
-          const float o3 = __uint_as_float(v[c * 32 + 4 * t + 3]) + b.w + r4.w;
-          sum += (o0 + o1) + (o2 + o3);
-          v[c * 32 + 4 * t] = __float_as_uint(o0); v[c * 32 + 4 * t + 1] = __float_as_uint(o1);
-          v[c * 32 + 4 * t + 2] = __float_as_uint(o2); v[c * 32 + 4 * t + 3] = __float_as_uint(o3);
+          const float2 o01 = fadd2(fadd2(make_float2(__uint_as_float(v[c * 32 + 4 * t]), __uint_as_float(v[c * 32 + 4 * t + 1])),
+                                         make_float2(bp[0], bp[1])), make_float2(r4.x, r4.y));
+          const float2 o23 = fadd2(fadd2(make_float2(__uint_as_float(v[c * 32 + 4 * t + 2]), __uint_as_float(v[c * 32 + 4 * t + 3])),
+                                         make_float2(bp[2], bp[3])), make_float2(r4.z, r4.w));
+          sum2 = fadd2(sum2, fadd2(o01, o23));
+          v[c * 32 + 4 * t] = __float_as_uint(o01.x); v[c * 32 + 4 * t + 1] = __float_as_uint(o01.y);
+          v[c * 32 + 4 * t + 2] = __float_as_uint(o23.x); v[c * 32 + 4 * t + 3] = __float_as_uint(o23.y);
         }
       }
       if (valid) ++res_cnt;
@@ -347,19 +346,26 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
           const float* bp = p.c.b2 + cb + c * 32 + 4 * t;
-          const float4 b = make_float4(bp[0], bp[1], bp[2], bp[3]);
-          w[4 * t] = __float_as_uint(__uint_as_float(v[c * 32 + 4 * t]) + b.x);
-          w[4 * t + 1] = __float_as_uint(__uint_as_float(v[c * 32 + 4 * t + 1]) + b.y);
-          w[4 * t + 2] = __float_as_uint(__uint_as_float(v[c * 32 + 4 * t + 2]) + b.z);
-          w[4 * t + 3] = __float_as_uint(__uint_as_float(v[c * 32 + 4 * t + 3]) + b.w);
+          const float2 w01 = fadd2(make_float2(__uint_as_float(v[c * 32 + 4 * t]), __uint_as_float(v[c * 32 + 4 * t + 1])),
+                                   make_float2(bp[0], bp[1]));
+          const float2 w23 = fadd2(make_float2(__uint_as_float(v[c * 32 + 4 * t + 2]), __uint_as_float(v[c * 32 + 4 * t + 3])),
+                                   make_float2(bp[2], bp[3]));
+          w[4 * t] = __float_as_uint(w01.x); w[4 * t + 1] = __float_as_uint(w01.y);
+          w[4 * t + 2] = __float_as_uint(w23.x); w[4 * t + 3] = __float_as_uint(w23.y);
         }
         tmem_st32(lane_taddr + kXCol + cb + c * 32, w);
       }
-      const float mean = row_total(sum) * (1.0f / 256.0f);
-      float sq = 0.f;
+      const float mean = row_total(sum2.x + sum2.y) * (1.0f / 256.0f);
+      float2 sq2v = make_float2(0.f, 0.f);
+      {
+        const float2 nm = make_float2(-mean, -mean);
 #pragma unroll
-      for (int t = 0; t < 64; ++t) { const float d = __uint_as_float(v[t]) - mean; sq = fmaf(d, d, sq); }
-      const float rstd = 1.0f / sqrtf(row_total(sq) * (1.0f / 256.0f) + 1e-5f);
+        for (int t = 0; t < 64; t += 2) {
+          const float2 d = fadd2(make_float2(__uint_as_float(v[t]), __uint_as_float(v[t + 1])), nm);
+          sq2v = ffma2(d, d, sq2v);
+        }
+      }
+      const float rstd = 1.0f / sqrtf(row_total(sq2v.x + sq2v.y) * (1.0f / 256.0f) + 1e-5f);
       const float2 nmean2 = make_float2(-mean, -mean), rstd2v = make_float2(rstd, rstd);
       tmem_st_wait();
       // every warp has consumed its residual slice: A2 (which overlays them) may be written
@@ -437,7 +443,7 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->x_empty);
-      sum = 0.f;
+      sum2 = make_float2(0.f, 0.f);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint8_t* rb = buf(c);
@@ -446,7 +452,7 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
           const float4 o = make_float4(__uint_as_float(v[c * 32 + 4 * t]), __uint_as_float(v[c * 32 + 4 * t + 1]),
                                        __uint_as_float(v[c * 32 + 4 * t + 2]), __uint_as_float(v[c * 32 + 4 * t + 3]));
           *reinterpret_cast<float4*>(rb + stg_off(lane, t)) = o;
-          sum += (o.x + o.y) + (o.z + o.w);
+          sum2 = fadd2(sum2, fadd2(make_float2(o.x, o.y), make_float2(o.z, o.w)));
         }
       }
       fence_proxy_async();
@@ -457,11 +463,17 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
         bulk_commit_group();
       }
       if (p.has_ln_out) {
-        const float mean2 = row_total(sum) * (1.0f / 256.0f);
-        float sq2 = 0.f;
+        const float mean2 = row_total(sum2.x + sum2.y) * (1.0f / 256.0f);
+        float2 sqb = make_float2(0.f, 0.f);
+        {
+          const float2 nm = make_float2(-mean2, -mean2);
 #pragma unroll
-        for (int t = 0; t < 64; ++t) { const float d = __uint_as_float(v[t]) - mean2; sq2 = fmaf(d, d, sq2); }
-        const float rstd2 = 1.0f / sqrtf(row_total(sq2) * (1.0f / 256.0f) + 1e-5f);
+          for (int t = 0; t < 64; t += 2) {
+            const float2 d = fadd2(make_float2(__uint_as_float(v[t]), __uint_as_float(v[t + 1])), nm);
+            sqb = ffma2(d, d, sqb);
+          }
+        }
+        const float rstd2 = 1.0f / sqrtf(row_total(sqb.x + sqb.y) * (1.0f / 256.0f) + 1e-5f);
         const float2 nmean2b = make_float2(-mean2, -mean2), rstd2vb = make_float2(rstd2, rstd2);
         if (lane == 0) bulk_wait_group_read<0>();                // the x stores have read their tiles
         __syncwarp();

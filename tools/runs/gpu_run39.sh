@@ -13,8 +13,8 @@ print({k:round(v['ms_per_step'],3) for k,v in d['stages'].items()})
 PY
 done
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "== reference rc=$?"; cut -c1-200 gpurun_out/bench_reference.json
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 230 -c 100 --csv --log-file gpurun_out/launches_fast_v7.csv \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 230 -c 100 --csv --log-file gpurun_out/launches_fast_v8.csv \
     python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_launch.log 2>&1; echo "launch list rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"encoder_block_kernel|gemm_tc_kernel|encoder_attention_kernel|conv1_bn_silu_kernel|preprocess_pack_kernel|ctc_greedy|pool_pos_ln" -s 23 -c 23 -f -o gpurun_out/ncu_step_v7 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"encoder_block_kernel|gemm_tc_kernel|encoder_attention_kernel|conv1_pair_kernel|preprocess_pack_kernel|ctc_greedy|pool_pos_ln" -s 23 -c 23 -f -o gpurun_out/ncu_step_v8 \
     python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_full.log 2>&1; echo "full rc=$?"
 ls -la gpurun_out/*.ncu-rep

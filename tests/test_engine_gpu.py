@@ -201,3 +201,19 @@ def test_multi_group_launches_equal_per_group_runs(engines):
     for (r0, B, T), (lg, mem) in zip(multi["rows"], singles):
         assert torch.equal(multi["logits"][r0:r0 + B * T].view(B, T, -1), lg)
         assert torch.equal(multi["mem_bf16"][r0:r0 + B * T], mem.view(B * T, -1))
+
+
+@pytest.mark.gpu
+def test_full_size_batch_is_deterministic_and_composition_independent(engines):
+    """BASELINE configs[1] size (256 bucketed lines): the same batch twice gives identical ids / confidences, and a
+    line's result does not depend on which other lines share its batch (every fourth line alone == inside)."""
+    eng, sd = engines("hard", "bucketed")
+    crops = FX.make_line_crops(256, seed=1234)
+    a = eng.recognize_crops(crops, "ctc")
+    b = eng.recognize_crops(crops, "ctc")
+    sub = eng.recognize_crops(crops[::4], "ctc")
+    assert len(a) == 256 and all(r is not None for r in a)
+    for ra, rb in zip(a, b):
+        assert np.array_equal(ra.ids, rb.ids) and ra.confidence == rb.confidence and ra.text == rb.text
+    for rs, ra in zip(sub, a[::4]):
+        assert np.array_equal(rs.ids, ra.ids) and rs.confidence == ra.confidence

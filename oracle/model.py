@@ -157,8 +157,9 @@ def _attend(q, k, v, heads: int):
 
 
 @torch.inference_mode()
-def decoder_step(st: DecoderState, token_ids: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-    """One token per line: returns (dec_head logits, lm_head logits), each [B, Vd].
+def decoder_hidden(st: DecoderState, token_ids: torch.Tensor) -> torch.Tensor:
+    """One token per line through the decoder stack: returns ``dec_ln`` output [B, D] (the input of
+    ``dec_head`` / ``lm_head``) and advances the KV cache.
 
     Input embedding is ``dec_emb[id] + pe[pos]`` with no sqrt(d) scale (model.py:465-470); old
     checkpoints without ``dec_pos_enc.pe`` skip the positional term (core.py:255-263)."""
@@ -188,7 +189,14 @@ def decoder_step(st: DecoderState, token_ids: torch.Tensor) -> Tuple[torch.Tenso
                      sd[f"{p}.linear2.weight"], sd[f"{p}.linear2.bias"])
         x = x + h
     st.pos += 1
-    out = _ln(x, sd, "dec_ln")[:, 0, :]
+    return _ln(x, sd, "dec_ln")[:, 0, :]
+
+
+@torch.inference_mode()
+def decoder_step(st: DecoderState, token_ids: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """One token per line: returns (dec_head logits, lm_head logits), each [B, Vd] (model.py:478-484)."""
+    sd = st.sd
+    out = decoder_hidden(st, token_ids)
     dec = F.linear(out, sd["dec_head.weight"], sd["dec_head.bias"])
     lm = F.linear(out, sd["lm_head.weight"], sd["lm_head.bias"]) if "lm_head.weight" in sd else None
     return dec, lm

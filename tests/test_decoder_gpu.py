@@ -2,7 +2,8 @@
 
 Free-running greedy decode is chaotic after the first divergent token, so parity is checked
 two ways: (1) teacher-forced — the oracle's token sequence is fed and the
-per-step penalised log-prob of each fed token must match within DEC_LOGP_ATOL; (2) free-running
+per-step penalised log-prob of each fed token must match within dec_tol(sd) (tests/tolerances.py: 0.10 on
+the "hard" fixture, 2x the measured 0.042); (2) free-running
 — ids / text / confidence against the reference goldens, required identical on the fixtures
 whose steps are all margin-safe, reported otherwise (gpurun_out/parity_report.json).
 """
@@ -17,7 +18,7 @@ from kiri_ocr_b200.config import CFG  # noqa: E402
 from tests.golden.cases import VARIANTS, golden_crops, lines_for  # noqa: E402
 from tests.test_engine_gpu import _report, engines  # noqa: E402,F401
 
-DEC_LOGP_ATOL = 0.35
+from tests.tolerances import dec_tol  # noqa: E402
 
 
 def _encode(eng, crops):
@@ -34,6 +35,7 @@ def test_teacher_forced_step_logp(engines, golden, tok_cfg, name):
     from oracle import decode as OD, model as OM, preprocess as OP
     tok, cfg = tok_cfg
     eng, sd = engines(name)
+    DEC_LOGP_ATOL = dec_tol(sd)
     n = min(4, lines_for(name))
     crops = golden_crops()[:n]
     enc, n_ids, conf = _encode(eng, crops)
@@ -73,6 +75,7 @@ def test_free_running_accurate_vs_goldens(engines, golden, tok_cfg, name):
     from oracle import decode as OD, model as OM, preprocess as OP
     tok, cfg = tok_cfg
     eng, sd = engines(name)
+    DEC_LOGP_ATOL = dec_tol(sd)
     n = lines_for(name)
     crops = golden_crops()[:n]
     res = eng.recognize_crops(crops, "decoder")
@@ -134,4 +137,8 @@ def test_streaming_rule_raw_argmax(engines, golden, tok_cfg):
         m = min(len(want), len(got))
         agree = sum(int(a == b) for a, b in zip(want[:m], got[:m]))
         _report(f"decoder_stream/hard/{i}", {"steps": m, "agree_prefix": agree})
-        assert got[:5] == want[:5]
+        # the full streamed sequence, unless the oracle itself is at a near tie (2 x tolerance) at the first
+        # differing step; on this fixture every step agrees (67/67 and 52/52 in profiles/r01_parity_report.json)
+        assert got[:m] == want[:m], (i, agree, m)
+        if res[i].len_est == length:                            # same CTC length estimate -> same step bound
+            assert len(got) == len(want), (i, len(got), len(want))

@@ -1,10 +1,12 @@
 """End-to-end parity of the B200 path against the CPU oracle and the reference goldens (-m gpu).
 
-Floating-point tolerance (stated, bf16 operands with fp32 accumulation and an fp32 residual
-stream): encoder memory  max-abs <= MEM_ATOL  and relative L2 <= MEM_RTOL;  CTC logits
-max-abs <= LOGIT_ATOL.  Token ids must be identical on every frame whose oracle top-1 margin
-exceeds 2 * LOGIT_ATOL ("margin-safe"); collapsed ids / text must be identical for lines whose
-frames are all margin-safe.  Measured values are written to gpurun_out/parity_report.json.
+Floating-point tolerance (stated in tests/tolerances.py: 2x the measured error of bf16 operands with fp32
+accumulation and an fp32 residual stream): encoder memory max-abs <= MEM_ATOL (0.03) and relative L2 <= MEM_RTOL
+(0.006); CTC logits max-abs <= logit_tol(sd) = 0.033 x the head's row norm (0.12 on the "hard" fixture).  Token ids
+must be identical on every frame whose oracle top-1 margin exceeds 2 * tolerance ("margin-safe"); collapsed ids /
+text must be identical for lines whose frames are all margin-safe (tests/test_wide_gpu.py has fixtures where that
+is every line; tests/test_baseline_gpu.py applies the rule to the 256-line bench workloads).  Measured values are
+written to gpurun_out/parity_report.json.
 """
 import json
 import os
@@ -19,7 +21,7 @@ from kiri_ocr_b200 import _lib, fixtures as FX  # noqa: E402
 from kiri_ocr_b200.config import CFG  # noqa: E402
 from tests.golden.cases import VARIANTS, golden_crops, lines_for  # noqa: E402
 
-MEM_ATOL, MEM_RTOL, LOGIT_ATOL = 0.12, 0.02, 0.35
+from tests.tolerances import MEM_ATOL, MEM_RTOL, logit_tol  # noqa: E402
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REPORT = {}
 
@@ -63,6 +65,7 @@ def oracle_line(sd, plane):
 def test_encoder_and_ctc_parity(engines, golden, name):
     from oracle import decode as OD, preprocess as OP
     eng, sd = engines(name)
+    LOGIT_ATOL = logit_tol(sd)
     crops = golden_crops()[: lines_for(name)]
     buf, ent = eng.pack_crops(crops)
     groups = eng.plan(ent)
@@ -99,7 +102,8 @@ def test_encoder_and_ctc_parity(engines, golden, name):
             assert np.array_equal(ids[i, :n].cpu().numpy(), collapsed), i
         text = eng.tok.decode_collapsed_ctc(ids[i, :n].cpu().tolist())
         stats["lines_text_equal"] += int(text == str(golden[f"{name}/{i}/fast_text"]))
-        assert abs(float(conf[i]) - cf) < 0.05
+        assert abs(float(conf[i]) - cf) < 0.01
+    stats["logit_tol"] = LOGIT_ATOL
     _report(f"encoder_ctc/{name}", stats)
     assert stats["mem_maxabs"] <= MEM_ATOL, stats
     assert stats["mem_rel_l2"] <= MEM_RTOL, stats
@@ -114,6 +118,7 @@ def test_recognize_crops_fast_matches_goldens(engines, golden):
     EXACTLY collapse(device frame ids) (integer work); text of all-safe lines equals the golden."""
     from oracle import decode as OD, preprocess as OP
     eng, sd = engines("hard")
+    LOGIT_ATOL = logit_tol(sd)
     crops = golden_crops()
     res = eng.recognize_crops(crops, "ctc", streaming=True)
     same = safe_lines = safe_lines_equal = near_tie_flips = 0
@@ -143,7 +148,7 @@ def test_recognize_crops_fast_matches_goldens(engines, golden):
     _report("fast_text/hard", {"lines": len(crops), "equal": same, "max_conf_diff": confd,
                                "all_safe_lines": safe_lines, "all_safe_lines_equal": safe_lines_equal,
                                "near_tie_frames_flipped": near_tie_flips})
-    assert confd < 0.05
+    assert confd < 0.01
     assert safe_lines_equal == safe_lines
 
 
@@ -151,6 +156,7 @@ def test_bucketed_equals_reference_with_img_w(engines):
     """width_mode='bucketed': a line in bucket Wb must equal the oracle run with IMG_W = Wb."""
     from oracle import decode as OD, model as OM, preprocess as OP
     eng, sd = engines("hard", "bucketed")
+    LOGIT_ATOL = logit_tol(sd)
     crops = FX.make_line_crops(24, seed=11)
     buf, ent = eng.pack_crops(crops)
     groups = eng.plan(ent)

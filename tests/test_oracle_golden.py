@@ -86,3 +86,29 @@ def test_blank_fixture_takes_memory_length_branch(golden):
     for i in range(4):
         assert int(golden[f"blank/{i}/len_est"]) == 0
         assert len(golden[f"blank/{i}/dec_ids"]) == 170      # min(512, int(160*1)+10) (model.py:421-425)
+
+
+@pytest.mark.parametrize("name", ["wide", "wide_b"])
+def test_wide_margin_fixture_matches_reference(tok_cfg, name):
+    """The fitted-head fixtures (tests/golden/wide.py): the oracle reproduces what the unmodified reference produced
+    on the stored checkpoint (text for fast / accurate, ids, confidences) and the stored margins are real."""
+    import os
+    from tests.golden.wide import MARGIN, wide_crops, wide_state_dict
+    tok, cfg = tok_cfg
+    gw = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_wide_v1.npz"), allow_pickle=False)
+    sd = wide_state_dict(gw, name)
+    crops, wbs = wide_crops(name)
+    for i, (c, Wb) in enumerate(zip(crops, wbs)):
+        key = f"{name}/{i}"
+        assert Wb == int(gw[f"{key}/Wb"])
+        plane = OP.preprocess_crop(c, 48, Wb)
+        text, conf, info = OD.recognize_plane(sd, tok, cfg, plane, "ctc")
+        assert text == str(gw[f"{key}/text"]) and abs(conf - float(gw[f"{key}/fast_conf"])) < 1e-5
+        assert info["ctc_ids"].tolist() == gw[f"{key}/ctc_ids"].astype(np.int64).tolist()
+        lg = OM.ctc_logits(sd, OM.encode(sd, torch.from_numpy(OP.normalise(plane))[None, None]))[0].numpy()
+        srt = np.sort(lg, axis=1)
+        assert float((srt[:, -1] - srt[:, -2]).min()) > 0.9 * MARGIN
+        if i == 0:                                              # one decoder run per case keeps the CPU suite short
+            text, conf, info = OD.recognize_plane(sd, tok, cfg, plane, "decoder")
+            assert text == str(gw[f"{key}/text"]) and abs(conf - float(gw[f"{key}/acc_conf"])) < 1e-5
+            assert info["dec_ids"].tolist() == gw[f"{key}/dec_ids"].astype(np.int64).tolist()

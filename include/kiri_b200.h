@@ -157,6 +157,11 @@ int kiri_encoder_block(const void* o_bf16, float* x_f32, void* a_out_bf16, const
                        const void* w1, const float* b1, const void* w2, const float* b2, const float* ln_mid_g,
                        const float* ln_mid_b, const float* ln_out_g, const float* ln_out_b, int M, int FF,
                        cudaStream_t stream);
+/* The same, `iters` launches back to back on x in place (constants fetched once; soak / timing tool). */
+int kiri_encoder_block_soak(const void* o_bf16, float* x_f32, void* a_out_bf16, const void* wo, const float* bo,
+                            const void* w1, const float* b1, const void* w2, const float* b2, const float* ln_mid_g,
+                            const float* ln_mid_b, const float* ln_out_g, const float* ln_out_b, int M, int FF,
+                            int iters, cudaStream_t stream);
 
 /* ---------------------------------------------------------------- K10: fused CTC greedy
  * Replaces compute_ctc_confidence + the id-level part of CharTokenizer.decode_ctc

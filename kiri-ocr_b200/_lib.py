@@ -89,6 +89,7 @@ _SIGS = {
     "kiri_encoder_attention": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
     "kiri_pack_records": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, vp, vp]),
     "kiri_encoder_block": (C.c_int, [vp] * 13 + [C.c_int, C.c_int, vp]),
+    "kiri_encoder_block_soak": (C.c_int, [vp] * 13 + [C.c_int, C.c_int, C.c_int, vp]),
     "kiri_encoder_attention_multi": (C.c_int, [vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, vp, vp]),
     "kiri_ctc_greedy": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),
     "kiri_ctc_greedy_multi": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),

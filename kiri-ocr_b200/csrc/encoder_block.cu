@@ -610,6 +610,21 @@ extern "C" int kiri_encoder_block(const void* o_bf16, float* x_f32, void* a_out_
   return kiri::launch_encoder_block(o_bf16, x_f32, a_out_bf16, wo, w1, w2, &c, ln_out_g != nullptr, M, FF, stream);
 }
 
+// Soak form of the stand-alone entry: the constants are fetched once, then `iters` launches go out back to back
+// (programmatic dependent launch on, no host synchronisation between them) on x in place.
+extern "C" int kiri_encoder_block_soak(const void* o_bf16, float* x_f32, void* a_out_bf16, const void* wo, const float* bo,
+                                       const void* w1, const float* b1, const void* w2, const float* b2, const float* ln_mid_g,
+                                       const float* ln_mid_b, const float* ln_out_g, const float* ln_out_b, int M, int FF,
+                                       int iters, cudaStream_t stream) {
+  KIRI_REQUIRE((ln_out_g == nullptr) == (ln_out_b == nullptr), "kiri_encoder_block_soak: ln_out_g and ln_out_b go together");
+  KIRI_REQUIRE(iters >= 1, "kiri_encoder_block_soak: iters must be positive");
+  kiri::EbConst c;
+  KIRI_TRY(kiri::encoder_block_consts(&c, bo, b1, b2, ln_mid_g, ln_mid_b, ln_out_g, ln_out_b, FF));
+  for (int i = 0; i < iters; ++i)
+    KIRI_TRY(kiri::launch_encoder_block(o_bf16, x_f32, a_out_bf16, wo, w1, w2, &c, ln_out_g != nullptr, M, FF, stream));
+  return 0;
+}
+
 // Debug: phase cycles of CTA 0 accumulated since the last call (KIRI_GEMM_TIMING=1).
 extern "C" int kiri_debug_eb_timing(long long* out_host, int n) {
   long long buf[16];

@@ -4,6 +4,7 @@ Checkers: the CPU oracle (oracle/), torch fp32 ops for floating-point kernels, a
 own CUDA-core reference GEMM.  Tolerances are stated per test; integer outputs are bit-exact.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -470,3 +471,24 @@ def test_pack_records_matches_numpy(lib):
         want = np.zeros(T, np.int32)
         want[:n_ids[b]] = ids[row0[b]:row0[b] + n_ids[b]]
         assert np.array_equal(got[b, 2:], want)
+
+
+def test_encoder_block_soak_back_to_back():
+    """1000 back-to-back launches (PDL on) of the fused encoder tail at the token counts of the bench (26 080 bucketed,
+    40 960 parity), one full wave (18 944) and a single tile, each twice from the same input: finite and bit-identical.
+    A second process repeats it with the clock64 phase accounting on (KIRI_GEMM_TIMING=1), the configuration of the
+    crash log that round 1 committed as profiles/r01_encoder_block_phase_cycles_v2.txt."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    import eb_soak
+    lib = _lib.load()
+    for M in (128, 18944, 26080, 40960):
+        eb_soak.soak(lib, M, 1000)
+    eb_soak.soak(lib, 26080, 300, with_ln=False)
+    env = dict(os.environ, KIRI_GEMM_TIMING="1")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "eb_soak.py"), "300"], env=env, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("soak ok") == 8

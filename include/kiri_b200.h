@@ -42,6 +42,9 @@ typedef struct CUstream_st* cudaStream_t;
 
 const char* kiri_last_error(void);
 int kiri_version(void);
+/* sizeof of {KiriCropDesc, KiriDims, KiriWeights, KiriGroup, KiriDecodeParams, KiriEncLayerWeights} as this library
+ * was built: a binding compares them with its own struct layouts before the first call (returns 6). */
+int kiri_abi_sizes(int* out, int n);
 /* 1 when the current device is compute capability 10.x (the kernels are sm_100a-only). */
 int kiri_device_ok(void);
 
@@ -65,7 +68,11 @@ typedef struct {
   int32_t nw;         /* max(1, round(w * img_h / h)) — Python round (model.py:321-322)    */
   int32_t Wb;         /* batch width of the crop's group: the plane is cropped/padded to it */
   int32_t strip_w;    /* output columns resampled by one CTA (fits the shared-memory budget)  */
+  int32_t flags;      /* KIRI_CROP_NO_INVERT: skip the dark-background inversion test (the input is an already
+                         preprocessed plane: OCR.recognize_region never inverts, core.py:530-568)            */
+  int32_t reserved;
 } KiriCropDesc;
+#define KIRI_CROP_NO_INVERT 1
 
 /* shared memory needed by one crop for a given strip width (host helper, no GPU call) */
 int kiri_preprocess_smem_bytes(int w, int h, int nw, int img_h, int Wb, int strip_w);

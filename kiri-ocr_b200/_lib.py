@@ -24,7 +24,11 @@ vp, fp, ip = C.c_void_p, C.c_void_p, C.c_void_p      # all device pointers trave
 
 class KiriCropDesc(C.Structure):
     _fields_ = [("src_offset", C.c_int64), ("out_offset", C.c_int64), ("pitch", C.c_int32), ("w", C.c_int32),
-                ("h", C.c_int32), ("nw", C.c_int32), ("Wb", C.c_int32), ("strip_w", C.c_int32)]
+                ("h", C.c_int32), ("nw", C.c_int32), ("Wb", C.c_int32), ("strip_w", C.c_int32), ("flags", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+CROP_NO_INVERT = 1
 
 
 class KiriDims(C.Structure):
@@ -68,6 +72,7 @@ class KiriDecodeParams(C.Structure):
 _SIGS = {
     "kiri_last_error": (C.c_char_p, []),
     "kiri_version": (C.c_int, []),
+    "kiri_abi_sizes": (C.c_int, [C.POINTER(C.c_int), C.c_int]),
     "kiri_device_ok": (C.c_int, []),
     "kiri_profile_begin": (C.c_int, []),
     "kiri_profile_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]),
@@ -145,6 +150,12 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    sizes = (C.c_int * 6)()
+    lib.kiri_abi_sizes(sizes, 6)
+    mine = [C.sizeof(t) for t in (KiriCropDesc, KiriDims, KiriWeights, KiriGroup, KiriDecodeParams, KiriEncLayerWeights)]
+    if list(sizes) != mine:
+        raise KiriError(f"{LIB_PATH} was built against another include/kiri_b200.h (struct sizes {list(sizes)} != {mine}): "
+                        f"rebuild it with `make -C {CSRC_DIR}`")
     _lib = lib
     return lib
 

@@ -68,82 +68,54 @@ META_CONFIG_KEYS = (
 
 
 class CharTokenizer:
-    """Character vocabulary with the reference's three id spaces (model.py:83-144).
+    """Character vocabulary with the reference's three id spaces (contract of kiri_ocr/model.py:83-144: same
+    constructor, attribute names and method results; the implementation here is table-driven).
 
     raw id r in [0, V); CTC id = r + 2 (0 blank, 1 pad); decoder id = r + 3 (0 pad, 1 bos, 2 eos).
+    ``vocab.json`` maps token -> stored id; tokens are re-numbered densely in the order of their stored ids and
+    ``<unk>`` is appended when the file has none.
     """
+
+    blank_id, pad_id, ctc_offset = 0, 1, 2
+    dec_pad, dec_bos, dec_eos, dec_offset = 0, 1, 2, 3
 
     def __init__(self, vocab_path: str, cfg: CFG):
         with open(vocab_path, "r", encoding="utf-8") as f:
-            vocab_raw: Dict[str, int] = json.load(f)
-        if cfg.UNK_TOKEN not in vocab_raw:
-            vocab_raw[cfg.UNK_TOKEN] = max(vocab_raw.values(), default=-1) + 1
-        # ids are re-densified in order of their stored value (model.py:91-93)
-        items = sorted(vocab_raw.items(), key=lambda kv: kv[1])
-        self.token_to_id = {tok: i for i, (tok, _) in enumerate(items)}
-        self.id_to_token = {i: tok for i, (tok, _) in enumerate(items)}
-
+            stored: Dict[str, int] = json.load(f)
         self.unk_token = cfg.UNK_TOKEN
-        self.unk_id = self.token_to_id[cfg.UNK_TOKEN]
-        self.blank_id = 0
-        self.pad_id = 1
-        self.ctc_offset = 2
-        self.vocab_size = len(self.token_to_id)
+        if self.unk_token not in stored:
+            stored[self.unk_token] = 1 + max(stored.values(), default=-1)
+        ordered = [tok for tok, _ in sorted(stored.items(), key=lambda item: item[1])]     # stable, like the reference
+        self.token_to_id = {tok: raw for raw, tok in enumerate(ordered)}
+        self.id_to_token = dict(enumerate(ordered))
+        self.unk_id = self.token_to_id[self.unk_token]
+        self.vocab_size = len(ordered)
         self.ctc_classes = self.vocab_size + self.ctc_offset
-
-        self.dec_pad = 0
-        self.dec_bos = 1
-        self.dec_eos = 2
-        self.dec_offset = 3
         self.dec_vocab = self.vocab_size + self.dec_offset
+        # what every id of each id space contributes to the text: '' for specials and <unk>
+        emitted = ["" if tok == self.unk_token else tok for tok in ordered]
+        self.ctc_text = [""] * self.ctc_offset + emitted
+        self.dec_text = [""] * self.dec_offset + emitted
 
     def decode_ctc(self, ids: List[int]) -> str:
-        """Collapse repeats, then drop blank/pad and <unk> (model.py:109-124)."""
-        chars = []
-        prev_id = None
-        for idx in ids:
-            if idx == prev_id:
-                continue
-            prev_id = idx
-            if idx < self.ctc_offset:
-                continue
-            raw_id = idx - self.ctc_offset
-            if 0 <= raw_id < self.vocab_size:
-                ch = self.id_to_token.get(raw_id, "")
-                if ch != self.unk_token:
-                    chars.append(ch)
-        return "".join(chars)
+        """Frame ids -> text: runs of equal ids count once, then blank / pad / <unk> / out-of-range ids vanish."""
+        from itertools import groupby
+        table, n = self.ctc_text, self.ctc_classes
+        return "".join(table[i] for i, _ in groupby(ids) if 0 <= i < n)
 
     def decode_collapsed_ctc(self, ids: List[int]) -> str:
-        """Text for ids that the device already collapsed (repeats removed, ids >= 2 kept).
-
-        Equivalent to ``decode_ctc`` on the un-collapsed frame ids: the device kernel applies
-        the ``idx == prev`` and ``idx < 2`` rules, this applies the range and <unk> rules.
-        """
-        chars = []
-        for idx in ids:
-            raw_id = idx - self.ctc_offset
-            if 0 <= raw_id < self.vocab_size:
-                ch = self.id_to_token.get(raw_id, "")
-                if ch != self.unk_token:
-                    chars.append(ch)
-        return "".join(chars)
+        """Text for ids the device already collapsed (repeats removed, ids >= 2 kept) — the tail of ``decode_ctc``."""
+        table, n = self.ctc_text, self.ctc_classes
+        return "".join(table[i] for i in ids if 0 <= i < n)
 
     def decode_dec(self, ids: List[int]) -> str:
-        out = []
-        for x in ids:
-            if x in (self.dec_pad, self.dec_bos, self.dec_eos):
-                continue
-            y = x - self.dec_offset
-            if 0 <= y < self.vocab_size:
-                t = self.id_to_token.get(y, self.unk_token)
-                out.append("" if t == self.unk_token else t)
-        return "".join(out)
+        table, n = self.dec_text, self.dec_vocab
+        return "".join(table[i] for i in ids if 0 <= i < n)
 
     def dec_to_ctc_id(self, dec_id: int) -> int:
-        if dec_id in (self.dec_pad, self.dec_bos, self.dec_eos):
-            return self.blank_id
-        raw_id = dec_id - self.dec_offset
-        if 0 <= raw_id < self.vocab_size:
-            return raw_id + self.ctc_offset
+        """Decoder id -> CTC id: specials map to blank, anything outside the vocabulary to <unk>'s CTC id."""
+        if dec_id < self.dec_offset:
+            return self.blank_id if dec_id >= 0 else self.unk_id + self.ctc_offset
+        if dec_id < self.dec_vocab:
+            return dec_id - self.dec_offset + self.ctc_offset
         return self.unk_id + self.ctc_offset

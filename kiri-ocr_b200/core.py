@@ -252,12 +252,12 @@ class OCR:
         if not valid[0]:
             return None
         page = np.ascontiguousarray(img)
-        buf = torch.empty(page.size + 16, dtype=torch.uint8).pin_memory()
-        buf.numpy()[:page.size] = page.reshape(-1)
         from .engine import plan_groups
         (idx, descs, smem, n_strips), = plan_groups(ent, self.cfg, "parity").values()
-        planes, _ = eng.preprocess(buf.to(eng.device), descs, self.cfg.IMG_W, smem, n_strips)
-        t = planes[0].float().cpu() / 255.0
+        with torch.cuda.stream(eng.stream):
+            src = eng._stage_host([page], 0)                     # persistent pinned staging, no per-call cudaHostAlloc
+            planes, _ = eng.preprocess(src.to(eng.device, non_blocking=True), descs, self.cfg.IMG_W, smem, n_strips)
+            t = planes[0].float().cpu() / 255.0                  # (synchronises: the staging buffer is free again)
         return ((t - 0.5) / 0.5).unsqueeze(0).unsqueeze(0)
 
     @staticmethod
@@ -266,12 +266,13 @@ class OCR:
         return torch.round((t * 0.5 + 0.5) * 255.0).clamp(0, 255).to(torch.uint8)
 
     def _recognize_planes(self, planes: torch.Tensor, method: str, streaming: bool = False) -> List[LineResult]:
+        """Already preprocessed uint8 planes [n, IMG_H, W]: they pass through the resample kernel as the identity and
+        are NEVER inverted (OCR.recognize_region takes the tensor as it is, core.py:530-568; the dark-background
+        test belongs to ``_preprocess_region`` only)."""
         eng = self.model
         n, H, W = planes.shape
-        ent = np.array([(i * H * W, W, W, H) for i in range(n)], np.int64)
-        buf = torch.empty(n * H * W + 16, dtype=torch.uint8).pin_memory()
-        buf[: n * H * W] = planes.reshape(-1)
-        return eng.recognize_packed(buf, ent, method, streaming)
+        ent = np.array([(i * H * W, W, W, H, _lib.CROP_NO_INVERT) for i in range(n)], np.int64)
+        return eng.recognize_packed([planes.numpy().reshape(-1)], ent, method, streaming)
 
     def recognize_region(self, image_tensor: torch.Tensor) -> Tuple[str, float]:
         r = self._recognize_planes(self._tensor_to_plane(image_tensor)[None], self._method())[0]
@@ -342,37 +343,74 @@ class OCR:
         res = self.model.recognize_boxes(img_gray, boxes, method, streaming) if len(boxes) else []
         return boxes, det_confs, res
 
+    @staticmethod
+    def _box_list(box):
+        try:
+            return [int(v) for v in box]
+        except Exception:                                          # noqa: BLE001 - a malformed detector box
+            return list(box) if isinstance(box, (list, tuple)) else [box]
+
+    def _results(self, boxes, det_confs, res, total: Optional[int] = None, keep_errors: bool = False):
+        """Per-region result dicts (core.py:778-784).  Empty crops are skipped (core.py:773-774); a region that
+        failed is dropped like the reference's swallowed per-region exception (core.py:789-791) or, for the
+        streaming form, reported with an ``error`` key (core.py:873-885)."""
+        from .engine import LineError
+        for i, (box, dc, r) in enumerate(zip(boxes, det_confs, res), 1):
+            if r is None:
+                continue
+            if isinstance(r, LineError):
+                if keep_errors:
+                    yield {"box": self._box_list(box), "text": "", "confidence": 0.0, "det_confidence": float(dc),
+                           "line_number": i, "total_regions": total, "error": r.message}
+                elif self.verbose:
+                    print(f"  {i:2d}. [Error: {r.message}]")
+                continue
+            d = {"box": [int(v) for v in box], "text": r.text, "confidence": float(r.confidence),
+                 "det_confidence": float(dc), "line_number": i}
+            if total is not None:
+                d["total_regions"] = total
+            yield d
+
     def process_document(self, image_path: Union[str, Path], mode: str = "lines", verbose: bool = False) -> List[Dict]:
         boxes, det_confs, res = self._recognize_document(image_path, mode, self._method())
-        out = []
-        for i, (box, dc, r) in enumerate(zip(boxes, det_confs, res), 1):
-            if r is None:                                          # empty crop: skipped (core.py:773-774)
-                continue
-            out.append({"box": [int(v) for v in box], "text": r.text, "confidence": float(r.confidence),
-                        "det_confidence": float(dc), "line_number": i})
-            if verbose:
-                print(f"  {i:2d}. {r.text[:50]:50s} ({r.confidence * 100:.1f}%)")
+        out = list(self._results(boxes, det_confs, res))
+        if verbose:
+            for d in out:
+                print(f"  {d['line_number']:2d}. {d['text'][:50]:50s} ({d['confidence'] * 100:.1f}%)")
         return out
+
+    def process_documents(self, image_paths: List[Union[str, Path]], mode: str = "lines") -> List[List[Dict]]:
+        """Several pages at once (an extension; the reference has only the per-page call): detection and image
+        decoding stay per page on the host, recognition runs through ``recognize_pages`` — whole pages per batch,
+        each uploaded once, two batches in flight.  Returns ``process_document``'s list for every page."""
+        method = self._method()
+        det, pages = [], []
+        for path in image_paths:
+            det.append(self._detect(path, mode))
+            pages.append(self._read_gray(path))
+        res = self.model.recognize_pages(pages, [d[0] for d in det], method)
+        return [list(self._results(b, c, r)) for (b, c), r in zip(det, res)]
 
     def process_document_streaming(self, image_path: Union[str, Path], mode: str = "lines", verbose: bool = False
                                    ) -> Generator[Dict, None, None]:
         boxes, det_confs, res = self._recognize_document(image_path, mode, self._method())
-        total = len(boxes)
-        for i, (box, dc, r) in enumerate(zip(boxes, det_confs, res), 1):
-            if r is None:
-                continue
-            yield {"box": [int(v) for v in box], "text": r.text, "confidence": float(r.confidence),
-                   "det_confidence": float(dc), "line_number": i, "total_regions": total}
+        yield from self._results(boxes, det_confs, res, total=len(boxes), keep_errors=True)
 
     def extract_text_stream_chars(self, image_path: Union[str, Path], mode: str = "lines",
                                   decode_method: Optional[str] = None, verbose: bool = False
                                   ) -> Generator[Dict, None, None]:
+        from .engine import LineError
         method = self._method(decode_method)
         boxes, det_confs, res = self._recognize_document(image_path, mode, method, streaming=True)
         total = len(boxes)
         done: List[str] = []
         for num, (box, dc, r) in enumerate(zip(boxes, det_confs, res), 1):
             if r is None:
+                continue
+            if isinstance(r, LineError):                           # core.py:1011-1026
+                yield {"token": "", "text": "", "cumulative_text": "\n".join(done), "region_number": num,
+                       "total_regions": total, "step": 0, "region_finished": True, "document_finished": num == total,
+                       "region_start": True, "box": self._box_list(box), "error": r.message}
                 continue
             b = [int(v) for v in box]
             yield {"token": "", "text": "", "cumulative_text": "\n".join(done), "region_number": num,

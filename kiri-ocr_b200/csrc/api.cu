@@ -59,7 +59,14 @@ __global__ void gemm_ref_kernel(const __nv_bfloat16* __restrict__ a, const __nv_
 using namespace kiri;
 
 extern "C" const char* kiri_last_error(void) { return g_err; }
-extern "C" int kiri_version(void) { return 100; }
+extern "C" int kiri_version(void) { return 200; }
+// ABI handshake for the ctypes binding: sizes of the structs that cross the boundary
+extern "C" int kiri_abi_sizes(int* out, int n) {
+  const int v[6] = {(int)sizeof(KiriCropDesc), (int)sizeof(KiriDims), (int)sizeof(KiriWeights), (int)sizeof(KiriGroup),
+                    (int)sizeof(KiriDecodeParams), (int)sizeof(KiriEncLayerWeights)};
+  for (int i = 0; i < n && i < 6; ++i) out[i] = v[i];
+  return 6;
+}
 extern "C" int kiri_device_ok(void) {
   int dev = 0, major = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;

@@ -121,7 +121,7 @@ preprocess_pack_kernel(const uint8_t* __restrict__ src, const KiriCropDesc* __re
   __nv_bfloat16* nplane = norm_out ? norm_out + d.out_offset : nullptr;
 
   // invert decision (core.py:524) from the crop sum of crop_sum_kernel
-  const bool invert = sums[blockIdx.x] < 127ull * static_cast<unsigned long long>(w) * h;
+  const bool invert = !(d.flags & KIRI_CROP_NO_INVERT) && sums[blockIdx.x] < 127ull * static_cast<unsigned long long>(w) * h;
   const uint32_t inv_mask = invert ? 0xffffffffu : 0u;
 
   // ---------------- coefficient geometry ----------------

@@ -59,15 +59,90 @@ def all_gather_records(rec: torch.Tensor, group=None) -> torch.Tensor:
 
 
 def unpack_records(rec: torch.Tensor, n_total: int):
-    """-> (ids per line, confidence per line) in global line order; missing lines give None."""
+    """-> (ids per line, confidence per line) in global line order; missing lines give None, lines that failed
+    on their rank (n_ids == -1) give ids None and confidence NaN."""
     r = rec.cpu().numpy()
     ids: List[Optional[np.ndarray]] = [None] * n_total
     conf: List[Optional[float]] = [None] * n_total
     for row in r:
         li, k = int(row[0]), int(row[1])
+        if k < 0:
+            conf[li] = float("nan")
+            continue
         ids[li] = row[3:3 + k].copy()
         conf[li] = float(row[2:3].view(np.float32)[0])
     return ids, conf
+
+
+def _record_width(engine, method: str) -> int:
+    """ids per record: T_max for CTC, the decode loop's static capacity for the decoders."""
+    T = engine.cfg.IMG_W // 4
+    if method == "ctc":
+        return T
+    cap = getattr(engine, "static_step_cap", None)
+    return cap(T) if cap else engine.cfg.MAX_DEC_LEN
+
+
+def _texts(engine, ids, conf, method):
+    tok = engine.tok
+    out = []
+    for row, c in zip(ids, conf):
+        if row is None:
+            out.append(None if c is None else LineFailed())
+        elif method == "ctc":
+            out.append((tok.decode_collapsed_ctc(row.tolist()), c))
+        else:
+            cut = row.tolist()
+            if tok.dec_eos in cut:
+                cut = cut[: cut.index(tok.dec_eos)]
+            out.append((tok.decode_dec(cut), c))
+    return out
+
+
+class LineFailed:
+    """Placeholder of a region that failed on the rank that owned it (see engine.LineError)."""
+
+    def __repr__(self):
+        return "LineFailed()"
+
+    def __eq__(self, other):
+        return isinstance(other, LineFailed)
+
+
+def recognize_pages_sharded(engine, pages, boxes_list, method: str = "ctc", group=None, batch_lines: int = 384):
+    """configs[4]: detector boxes of many pages, recognition sharded PAGE-MAJOR over the ranks (contiguous page
+    ranges balanced by line count, so every rank uploads only its own pages), the engine's pipelined multi-page
+    path on every rank, then the path's ONE exchange step: an all-gather of the fixed-stride records.  Every rank
+    returns, per page and box, ``(text, confidence)`` / ``None`` (empty crop) / ``LineFailed()``, identical on all
+    ranks and identical to a single-rank run.  ``pages[p]`` is only touched on the rank that owns page p (the others
+    may pass ``None`` there); ``pages`` may also be a pinned uint8 tensor [n, H, W] (zero-copy uploads)."""
+    import torch.distributed as dist
+    from .engine import LineError
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n_lines = np.array([len(b) for b in boxes_list], np.int64)
+    lo, hi = shard_bounds(n_lines, world)[rank]
+    local = engine.recognize_pages(pages[lo:hi], boxes_list[lo:hi], method, batch_lines=batch_lines)
+    start = np.concatenate([[0], np.cumsum(n_lines)])
+    idx, ids, conf = [], [], []
+    for p, page_res in zip(range(lo, hi), local):
+        for i, r in enumerate(page_res):
+            if r is None:
+                continue
+            idx.append(int(start[p]) + i)
+            if isinstance(r, LineError):
+                ids.append(None); conf.append(0.0)
+            else:
+                ids.append(r.ids); conf.append(r.confidence)
+    lmax = _record_width(engine, method)
+    rec = pack_records(np.asarray(idx, np.int64), [np.zeros(0, np.int32) if r is None else r for r in ids], conf, lmax)
+    for k, r in enumerate(ids):
+        if r is None:
+            rec[k, 1] = -1
+    dev = getattr(engine, "device", torch.device("cpu"))
+    allrec = all_gather_records(rec.to(dev) if dist.get_backend(group) == "nccl" else rec, group)
+    g_ids, g_conf = unpack_records(allrec, int(start[-1]))
+    flat = _texts(engine, g_ids, g_conf, method)
+    return [flat[int(start[p]):int(start[p + 1])] for p in range(len(boxes_list))]
 
 
 def recognize_sharded(engine, src: torch.Tensor, entries: np.ndarray, method: str = "ctc", group=None):
@@ -79,21 +154,9 @@ def recognize_sharded(engine, src: torch.Tensor, entries: np.ndarray, method: st
     nw = np.minimum(target_widths(entries[:, 2], entries[:, 3], engine.cfg.IMG_H), engine.cfg.IMG_W)
     lo, hi = shard_bounds(nw, world)[rank]
     local = engine.recognize_packed(src, entries[lo:hi], method)
-    lmax = engine.cfg.IMG_W // 4 if method == "ctc" else engine.cfg.MAX_DEC_LEN
+    lmax = _record_width(engine, method)
     rec = pack_records(np.arange(lo, hi), [r.ids for r in local], [r.confidence for r in local], lmax)
     dev = getattr(engine, "device", torch.device("cpu"))
     allrec = all_gather_records(rec.to(dev) if dist.get_backend(group) == "nccl" else rec, group)
     ids, conf = unpack_records(allrec, len(entries))
-    tok = engine.tok
-    out = []
-    for row, c in zip(ids, conf):
-        if row is None:
-            out.append(None)
-        elif method == "ctc":
-            out.append((tok.decode_collapsed_ctc(row.tolist()), c))
-        else:
-            cut = row.tolist()
-            if tok.dec_eos in cut:
-                cut = cut[: cut.index(tok.dec_eos)]
-            out.append((tok.decode_dec(cut), c))
-    return out
+    return _texts(engine, ids, conf, method)

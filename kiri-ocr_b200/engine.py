@@ -30,7 +30,7 @@ from .weights import PackedWeights
 
 BUCKETS = (128, 256, 384, 512, 640)
 DESC_DTYPE = np.dtype([("src_offset", "<i8"), ("out_offset", "<i8"), ("pitch", "<i4"), ("w", "<i4"), ("h", "<i4"),
-                       ("nw", "<i4"), ("Wb", "<i4"), ("strip_w", "<i4")])
+                       ("nw", "<i4"), ("Wb", "<i4"), ("strip_w", "<i4"), ("flags", "<i4"), ("reserved", "<i4")])
 assert DESC_DTYPE.itemsize == C.sizeof(_lib.KiriCropDesc)
 PRE_SMEM_CAP = 56 * 1024           # four preprocessing CTAs per SM
 PRE_STRIP = 128                    # output columns per preprocessing CTA
@@ -47,6 +47,19 @@ class LineResult:
     frame_ids: Optional[np.ndarray] = None
     frame_prob: Optional[np.ndarray] = None
     len_est: int = 0                # CTC length estimate that bounds the decoder (model.py:416-425)
+
+
+class LineError:
+    """A region that could not be recognised (malformed box, per-line failure): the document loops drop it or
+    report it as an ``error`` result / chunk like the reference's per-region ``try/except``
+    (kiri_ocr/core.py:771-791, 873-885, 1011-1026)."""
+    __slots__ = ("message",)
+
+    def __init__(self, message: str):
+        self.message = message
+
+    def __repr__(self):
+        return f"LineError({self.message!r})"
 
 
 def target_widths(w: np.ndarray, h: np.ndarray, img_h: int) -> np.ndarray:
@@ -99,6 +112,8 @@ def plan_groups(entries: np.ndarray, cfg: CFG, width_mode: str = "parity"
     d_all = np.zeros(len(entries), DESC_DTYPE)
     d_all["src_offset"], d_all["pitch"], d_all["w"], d_all["h"] = entries[:, 0], entries[:, 1], w, h
     d_all["nw"], d_all["strip_w"], d_all["Wb"] = nw, strip, wb
+    if entries.shape[1] > 4:                                 # optional 5th column: KiriCropDesc.flags (CROP_NO_INVERT)
+        d_all["flags"] = entries[:, 4]
     order = np.argsort(wb, kind="stable")
     wbs = wb[order]
     cuts = np.nonzero(np.diff(wbs))[0] + 1
@@ -118,6 +133,14 @@ class BatchedRecognizer:
         self.lib = _lib.load()
         self.cfg, self.tok = cfg, tokenizer
         self.device = torch.device(device if device != "cuda" else f"cuda:{torch.cuda.current_device()}")
+        if self.device.index is None:
+            self.device = torch.device(f"cuda:{torch.cuda.current_device()}")
+        if self.device.index != torch.cuda.current_device():
+            # the C ABI works on the CURRENT device (handle creation, cudaMalloc of the packed decoder weights,
+            # every launch); silently mixing devices would read another GPU's pointers
+            raise _lib.KiriError(f"BatchedRecognizer(device={device!r}): make it the current device first "
+                                 f"(torch.cuda.set_device({self.device.index})); the current device is "
+                                 f"cuda:{torch.cuda.current_device()}")
         if width_mode not in ("parity", "bucketed", "masked"):
             raise ValueError(f"unknown width_mode {width_mode!r}")
         self.width_mode = width_mode
@@ -131,6 +154,7 @@ class BatchedRecognizer:
         self._copy_stream = torch.cuda.Stream(device=self.device)     # uploads overlap the previous batch
         self._slot = 0                                                # ping-pong staging slot of submit()
         self._src_free = [None, None]
+        self._h2d_done = [None, None]                                 # H2D of the slot's pinned source buffer
         self._ws: Optional[torch.Tensor] = None
         self._dws: Optional[torch.Tensor] = None
         self._build_tables()
@@ -209,29 +233,16 @@ class BatchedRecognizer:
         return cur
 
     def _build_tables(self):
-        """id -> text lookup tables (object arrays) equivalent to CharTokenizer.decode_collapsed_ctc /
-        decode_dec (model.py:109-135): out-of-range ids, specials and <unk> map to ''."""
+        """id -> text lookup lists (the tokenizer's tables padded to the device's class counts, so ids of the zero
+        padded head columns map to '')."""
         tok = self.tok
-        ctc = np.empty(self.pw.Cp + 1, dtype=object)
-        ctc[:] = ""
-        for i in range(self.pw.C):
-            raw = i - tok.ctc_offset
-            if 0 <= raw < tok.vocab_size:
-                ch = tok.id_to_token.get(raw, "")
-                ctc[i] = "" if ch == tok.unk_token else ch
-        dec = np.empty(self.pw.Vp + 1, dtype=object)
-        dec[:] = ""
-        for i in range(self.pw.Vd):
-            raw = i - tok.dec_offset
-            if i not in (tok.dec_pad, tok.dec_bos, tok.dec_eos) and 0 <= raw < tok.vocab_size:
-                ch = tok.id_to_token.get(raw, tok.unk_token)
-                dec[i] = "" if ch == tok.unk_token else ch
-        self._ctc_table, self._dec_table = ctc.tolist(), dec.tolist()     # plain lists: fastest per-id lookup
+        self._ctc_table = list(tok.ctc_text) + [""] * (self.pw.Cp + 1 - len(tok.ctc_text))
+        self._dec_table = list(tok.dec_text) + [""] * (self.pw.Vp + 1 - len(tok.dec_text))
 
     def preprocess(self, src_dev: torch.Tensor, descs: np.ndarray, Wb: int, smem: int, n_strips: int,
                    want_norm: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
         n = len(descs)
-        dd = torch.from_numpy(descs.view(np.uint8).reshape(-1)).pin_memory().to(self.device, non_blocking=True)
+        dd = torch.from_numpy(descs.view(np.uint8).reshape(-1).copy()).to(self.device)
         planes = torch.empty((n, self.cfg.IMG_H, Wb), dtype=torch.uint8, device=self.device)
         norm = torch.empty((n, self.cfg.IMG_H, Wb), dtype=torch.bfloat16, device=self.device) if want_norm else None
         sums = torch.empty(2 * n, dtype=torch.int32, device=self.device)
@@ -446,8 +457,7 @@ class BatchedRecognizer:
 
     def step_resident(self, prep, method: str = "ctc"):
         """One pass of the hot path over the prepared batch, inputs already in HBM.  Returns the
-        device outputs (no synchronisation in "ctc" mode; the decoder needs the CTC length
-        estimates on the host once to bound its loop)."""
+        device outputs; nothing synchronises with the host ("ctc" and "decoder")."""
         _lib.check(self.lib.kiri_preprocess_pack(prep["src"].data_ptr(), prep["descs"].data_ptr(), prep["n_crops"],
                                                  self.cfg.IMG_H, prep["smem"], prep["n_strips"],
                                                  prep["planes_all"].data_ptr(), 0, prep["sums"].data_ptr(), _lib.stream_ptr()),
@@ -466,10 +476,10 @@ class BatchedRecognizer:
         outs = [(ids, n_ids, conf)]
         if method != "decoder":
             return outs
-        len_est = torch.cat([o[1] for o in outs]) if len(outs) > 1 else outs[0][1]
-        conf = torch.cat([o[2] for o in outs]) if len(outs) > 1 else outs[0][2]
-        Lmax = self.max_steps_bound(int(len_est.max().item()), prep["T_max"])
-        d_ids, n_out, sum_lp, _, _ = self.decode_greedy_multi(enc["mem_bf16"], prep["mem_row0"], prep["mem_len"], len_est, Lmax,
+        # the decode loop's capacity is a static bound and every line's own step budget is derived on the device from
+        # its length estimate: no host synchronisation between the encoder and the decoder
+        Lmax = self.static_step_cap(prep["T_max"])
+        d_ids, n_out, sum_lp, _, _ = self.decode_greedy_multi(enc["mem_bf16"], prep["mem_row0"], prep["mem_len"], n_ids, Lmax,
                                                               prep["T_max"])
         return [(d_ids, n_out, sum_lp, conf)]
 
@@ -485,16 +495,49 @@ class BatchedRecognizer:
         return {name: (ms[i], cnt[i]) for i, name in enumerate(_lib.PROFILE_STAGES[:n])}
 
     # ------------------------------------------------------------------ public API
+    def _check_device(self):
+        if torch.cuda.current_device() != self.device.index:
+            raise _lib.KiriError(f"this engine lives on {self.device}; the current device is cuda:{torch.cuda.current_device()} "
+                                 f"(wrap the call in torch.cuda.device({self.device.index}))")
+
+    def static_step_cap(self, T_max: int) -> int:
+        """Capacity of the decode loop that needs no host round trip: the CTC length estimate is at most T_max
+        (one new id per frame), so max_steps (model.py:416-425) is at most this.  The kernel derives every line's own
+        max_steps from its device-resident length estimate and clusters exit as soon as their lines are done."""
+        return self.max_steps_bound(T_max, T_max)
+
+    def _stage_host(self, arrays: Sequence[np.ndarray], slot: int) -> torch.Tensor:
+        """Concatenate host arrays into the slot's PERSISTENT pinned buffer (no per-call cudaHostAlloc)."""
+        total = int(sum(a.size for a in arrays))
+        name = f"_hsrc_{slot}"
+        cur = getattr(self, name, None)
+        if cur is None or cur.numel() < total + 16:
+            cur = torch.empty(int((total + 16) * 1.25) + 4096, dtype=torch.uint8).pin_memory()
+            setattr(self, name, cur)
+        elif self._h2d_done[slot] is not None:
+            self._h2d_done[slot].synchronize()              # the upload that last read this buffer has finished
+        nb = cur.numpy()
+        off = 0
+        for a in arrays:
+            if a.dtype != np.uint8:
+                raise ValueError("source arrays must be uint8")
+            nb[off:off + a.size] = a.reshape(-1)
+            off += a.size
+        return cur[:total + 16]
+
     @torch.no_grad()
-    def submit(self, src: torch.Tensor, entries: np.ndarray, method: str = "ctc", streaming: bool = False):
-        """Enqueue one batch (H2D of the source on the copy stream, preprocess, encoder, CTC greedy, async
-        D2H of the packed CTC results) and return a ticket without synchronising the host.  Two
-        tickets may be in flight: ``t2 = submit(...); r1 = collect(t1)`` overlaps batch i's host-side
+    def submit(self, src, entries: np.ndarray, method: str = "ctc", streaming: bool = False):
+        """Enqueue one batch (H2D of the source on the copy stream, preprocess, encoder, CTC greedy, for "decoder"
+        the whole greedy decode, async D2H of the packed results) and return a ticket without synchronising the
+        host.  Two tickets may be in flight: ``t2 = submit(...); r1 = collect(t1)`` overlaps batch i's host-side
         string decoding and batch i+1's upload with the kernels of the other batch.
-        ``src``: uint8 buffer (pinned host or device) holding pages/crops; ``entries[n,4]`` =
-        (byte offset, pitch, w, h) of every crop after the reference's clamp-pad."""
+        ``src``: uint8 buffer (pinned host or device) holding pages/crops, or a list of uint8 numpy arrays that are
+        concatenated into the engine's persistent pinned staging; ``entries[n,4]`` = (byte offset, pitch, w, h)
+        of every crop after the reference's clamp-pad; an optional fifth column carries ``KiriCropDesc.flags``
+        (``_lib.CROP_NO_INVERT`` for inputs that are already preprocessed planes)."""
         if method not in ("ctc", "decoder", "beam"):
             raise ValueError("method must be 'ctc', 'decoder' or 'beam'")
+        self._check_device()
         caller = torch.cuda.current_stream(self.device)
         if caller != self.stream:
             self.stream.wait_stream(caller)
@@ -506,16 +549,25 @@ class BatchedRecognizer:
             return tk
         marks = [_time.perf_counter()]                       # host-side phase marks of this call (tk["marks"])
         self._slot ^= 1
-        sl = f"_{self._slot}"
+        slot, sl = self._slot, f"_{self._slot}"
+        if isinstance(src, (list, tuple)):
+            src = self._stage_host(src, slot)
         if src.is_cuda:
             src_dev = src
         else:
             # upload on the copy stream: it overlaps the kernels of the batch submitted before
+            had = getattr(self, "_src" + sl, None)
             src_dev = self._device("_src" + sl, src.numel(), torch.uint8)
-            if self._src_free[self._slot] is not None:              # the preprocess launch that last read this slot
-                self._copy_stream.wait_event(self._src_free[self._slot])
+            if had is not src_dev:
+                # a fresh block from the caching allocator may have been freed on the engine stream a moment ago
+                # (e.g. a workspace that grew) while kernels that read it are still queued there
+                self._copy_stream.wait_stream(self.stream)
+            if self._src_free[slot] is not None:              # the preprocess launch that last read this slot
+                self._copy_stream.wait_event(self._src_free[slot])
             with torch.cuda.stream(self._copy_stream):
                 src_dev[:src.numel()].copy_(src, non_blocking=True)
+                self._h2d_done[slot] = torch.cuda.Event()
+                self._h2d_done[slot].record()
         marks.append(_time.perf_counter())                   # [1] upload enqueued
         groups = list(self.plan(entries).items())
         marks.append(_time.perf_counter())                   # [2] planned
@@ -558,46 +610,63 @@ class BatchedRecognizer:
                    "kiri_preprocess_pack")
         self.launches += 2
         if not src.is_cuda:
-            self._src_free[self._slot] = torch.cuda.Event()
-            self._src_free[self._slot].record()
+            self._src_free[slot] = torch.cuda.Event()
+            self._src_free[slot].record()
         kv_len = dmeta[kvo:kvo + n_lines] if self.width_mode == "masked" else None
         marks.append(_time.perf_counter())                   # [4] preprocess launched
         enc = self.encode_multi(planes_list, kv_len=kv_len, slot=sl)
         marks.append(_time.perf_counter())                   # [5] encoder launched
-        # ---- CTC greedy into ONE packed result buffer: ids[M] | n_ids[L] | conf[L] | frames
+        # ---- CTC greedy into ONE packed result buffer: ids[M] | n_ids[L] | conf[L] | frames | decoder block
         want_frames = streaming and method == "ctc"
-        res_words = M + 2 * n_lines + (2 * M if want_frames else 0)
+        T_max = max(T for _, _, T in enc["rows"])
+        Lcap = self.static_step_cap(T_max) if method == "decoder" else 0
+        LL = n_lines * Lcap
+        dec_words = (3 * LL if streaming else 2 * LL) + 2 * n_lines if method == "decoder" else 0
+        ctc_words = M + 2 * n_lines + (2 * M if want_frames else 0)
+        res_words = ctc_words + dec_words
         dres = self._device("_dres" + sl, res_words, torch.int32)
         ids_all, n_all = dres[:M], dres[M:M + n_lines]
         conf_all = dres[M + n_lines:M + 2 * n_lines].view(torch.float32)
         fid_all = dres[M + 2 * n_lines:2 * M + 2 * n_lines] if want_frames else None
         fpr_all = dres[2 * M + 2 * n_lines:3 * M + 2 * n_lines].view(torch.float32) if want_frames else None
-        T_max = max(T for _, _, T in enc["rows"])
         _lib.check(self.lib.kiri_ctc_greedy_multi(enc["logits"].data_ptr(), _lib.DTYPE_F32, n_lines,
                                                   dmeta[r0o:].data_ptr(), dmeta[mlo:].data_ptr(), T_max, self.pw.C, Cp,
                                                   ids_all.data_ptr(), n_all.data_ptr(), conf_all.data_ptr(),
                                                   _lib.ptr(fid_all), _lib.ptr(fpr_all), _lib.stream_ptr()),
                    "kiri_ctc_greedy_multi")
         self.launches += 1
+        mem_row0, mem_len = dmeta[r0o:r0o + n_lines], dmeta[mlo:mlo + n_lines]
+        if method == "decoder":
+            # the greedy decode is enqueued right behind the CTC kernel: its step bounds come from the device-resident
+            # length estimates, so no host round trip separates the encoder from the decoder
+            dd = dres[ctc_words:]
+            d_ids, n_out = dd[:LL].view(n_lines, Lcap), dd[LL:LL + n_lines]
+            sum_lp = dd[LL + n_lines:LL + 2 * n_lines].view(torch.float32)
+            slp = dd[LL + 2 * n_lines:2 * LL + 2 * n_lines].view(torch.float32).view(n_lines, Lcap)
+            spr = dd[2 * LL + 2 * n_lines:3 * LL + 2 * n_lines].view(torch.float32).view(n_lines, Lcap) if streaming else None
+            self.decode_greedy_multi(enc["mem_bf16"], mem_row0, mem_len, n_all, Lcap, T_max, select_raw=streaming,
+                                     out=(d_ids, n_out, sum_lp, slp, spr))
         hres = self._pinned("_hres" + sl, res_words, torch.int32)
         hres[:res_words].copy_(dres[:res_words], non_blocking=True)
         done = torch.cuda.Event()
         done.record()
-        marks.append(_time.perf_counter())                   # [6] CTC + download enqueued
-        tk.update(marks=marks, done=done, hres=hres, res_words=res_words, M=M, n_lines=n_lines, rows=enc["rows"], T_max=T_max,
+        marks.append(_time.perf_counter())                   # [6] CTC (+ decode) + download enqueued
+        tk.update(marks=marks, done=done, hres=hres, res_words=res_words, ctc_words=ctc_words, Lcap=Lcap, M=M, n_lines=n_lines,
+                  rows=enc["rows"], T_max=T_max,
                   order=np.concatenate([g[1][0] for g in groups]),     # line index of every concatenated slot
-                  want_frames=want_frames, enc=enc, n_all=n_all, mem_row0=dmeta[r0o:r0o + n_lines],
-                  mem_len=dmeta[mlo:mlo + n_lines], keep=(src_dev, planes_all, dmeta, dres), sl=sl)
+                  want_frames=want_frames, enc=enc, n_all=n_all, mem_row0=mem_row0, mem_len=mem_len,
+                  keep=(src_dev, planes_all, dmeta, dres), sl=sl)
         return tk
 
     @torch.no_grad()
     def collect(self, tk) -> List[Optional[LineResult]]:
-        """Wait for a ticket; "ctc" is finished on the host, "decoder" / "beam" run their decode stage
-        now (they need the CTC length estimates on the host to bound the loop)."""
+        """Wait for a ticket and build the per-line results on the host ("beam" runs its search now: its Python-side
+        final ranking needs the CTC length estimates for the buffer sizes)."""
         n = tk["n"]
         results: List[Optional[LineResult]] = [None] * n
         if n == 0:
             return results
+        self._check_device()
         caller = torch.cuda.current_stream(self.device)
         if caller != self.stream:
             with torch.cuda.stream(self.stream):
@@ -630,25 +699,12 @@ class BatchedRecognizer:
         len_h = n_h                                                  # length estimates bound the loop
         if method == "beam":
             return self._beam_finish(enc, tk["mem_row0"], tk["mem_len"], tk["n_all"], len_h, c_h, order, results)
-        # ---- greedy attention decoder over all lines at once
-        T_max = tk["T_max"]
-        Lmax = self.max_steps_bound(int(len_h.max()), T_max)
-        dec_words = n_lines * Lmax * 3 + 2 * n_lines
-        ddec = self._device("_ddec", dec_words, torch.int32)
-        LL = n_lines * Lmax
-        d_ids, n_out = ddec[:LL].view(n_lines, Lmax), ddec[LL:LL + n_lines]
-        sum_lp = ddec[LL + n_lines:LL + 2 * n_lines].view(torch.float32)
-        slp = ddec[LL + 2 * n_lines:2 * LL + 2 * n_lines].view(torch.float32).view(n_lines, Lmax)
-        spr = ddec[2 * LL + 2 * n_lines:3 * LL + 2 * n_lines].view(torch.float32).view(n_lines, Lmax)
-        self.decode_greedy_multi(enc["mem_bf16"], tk["mem_row0"], tk["mem_len"], tk["n_all"], Lmax, T_max,
-                                 select_raw=streaming, out=(d_ids, n_out, sum_lp, slp, spr))
-        hdec = self._pinned("_hdec", dec_words, torch.int32)
-        hdec[:dec_words].copy_(ddec[:dec_words], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        hd = hdec.numpy()[:dec_words].copy()
-        ids_h, no_h = hd[:LL].reshape(n_lines, Lmax), hd[LL:LL + n_lines]
-        slp_h = hd[LL + 2 * n_lines:2 * LL + 2 * n_lines].view(np.float32).reshape(n_lines, Lmax)
-        spr_h = hd[2 * LL + 2 * n_lines:3 * LL + 2 * n_lines].view(np.float32).reshape(n_lines, Lmax)
+        # ---- greedy attention decoder: everything is already on the host
+        Lcap, LL = tk["Lcap"], n_lines * tk["Lcap"]
+        hd = hr[tk["ctc_words"]:]
+        ids_h, no_h = hd[:LL].reshape(n_lines, Lcap), hd[LL:LL + n_lines]
+        slp_h = hd[LL + 2 * n_lines:2 * LL + 2 * n_lines].view(np.float32).reshape(n_lines, Lcap)
+        spr_h = hd[2 * LL + 2 * n_lines:3 * LL + 2 * n_lines].view(np.float32).reshape(n_lines, Lcap) if streaming else None
         tab, eos = self._dec_table, self.tok.dec_eos
         for j, li in enumerate(order):
             nj = int(no_h[j])
@@ -658,9 +714,31 @@ class BatchedRecognizer:
             lps = slp_h[j, :nj].astype(np.float64)
             dec_conf = min(1.0, max(0.0, math.exp(float(lps.sum()) / nj))) if nj else 0.0
             results[li] = LineResult("".join([tab[i] for i in text_ids.tolist()]), 0.6 * dec_conf + 0.4 * float(c_h[j]),
-                                     float(c_h[j]), row, step_logp=slp_h[j, :nj], step_prob=spr_h[j, :nj],
-                                     len_est=int(len_h[j]))
+                                     float(c_h[j]), row, step_logp=slp_h[j, :nj],
+                                     step_prob=None if spr_h is None else spr_h[j, :nj], len_est=int(len_h[j]))
         return results
+
+    def ticket_records(self, tk, T: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The exchange records of a submitted batch, built ON THE DEVICE from the ticket's outputs (stream-ordered
+        behind its kernels, no host involvement): int32 [n_lines, 2 + T] = {n_ids, confidence bits, ids[T]} in the
+        batch's slot order ("ctc": collapsed CTC ids + CTC confidence; "decoder": decoder ids + sum of log-probs)."""
+        n, M = tk["n_lines"], tk["M"]
+        rec = out if out is not None else torch.zeros((n, 2 + T), dtype=torch.int32, device=self.device)
+        dres = tk["keep"][3]
+        if tk["method"] == "decoder":
+            Lcap, LL = tk["Lcap"], n * tk["Lcap"]
+            dd = dres[tk["ctc_words"]:]
+            k = min(T, Lcap)
+            rec[:n, 0] = dd[LL:LL + n]
+            rec[:n, 1] = dd[LL + n:LL + 2 * n]
+            rec[:n, 2:2 + k] = dd[:LL].view(n, Lcap)[:, :k]
+            self.launches += 3
+        else:
+            _lib.check(self.lib.kiri_pack_records(dres[:M].data_ptr(), dres[M:M + n].data_ptr(), dres[M + n:M + 2 * n].data_ptr(),
+                                                  tk["mem_row0"].data_ptr(), n, T, rec.data_ptr(), _lib.stream_ptr()),
+                       "kiri_pack_records")
+            self.launches += 1
+        return rec
 
     def recognize_packed(self, src: torch.Tensor, entries: np.ndarray, method: str = "ctc",
                          streaming: bool = False) -> List[Optional[LineResult]]:
@@ -738,21 +816,128 @@ class BatchedRecognizer:
         return results
 
     def recognize_crops(self, crops: Sequence[np.ndarray], method: str = "ctc", streaming: bool = False):
-        buf, ent = self.pack_crops(crops)
-        return self.recognize_packed(buf, ent, method, streaming)
+        """Line crops (2-D uint8 arrays) -> results, through the engine's persistent pinned staging."""
+        ent = np.zeros((len(crops), 4), np.int64)
+        off = 0
+        arrs = []
+        for i, c in enumerate(crops):
+            if c.dtype != np.uint8 or c.ndim != 2:
+                raise ValueError("crops must be 2-D uint8 arrays")
+            ent[i] = (off, c.shape[1], c.shape[1], c.shape[0])
+            off += c.size
+            arrs.append(np.ascontiguousarray(c))
+        return self.collect(self.submit(arrs, ent, method, streaming))
+
+    @staticmethod
+    def _page_entries(page_shape, boxes, page_offset: int = 0):
+        """Clamp-padded entries of one page's boxes.  A box that cannot be interpreted (wrong arity, non-numeric)
+        becomes a LineError instead of failing the page (per-region isolation, core.py:771-791); returns
+        (entries of the usable boxes, their indices, {index: LineError})."""
+        errors = {}
+        good, rows = [], []
+        for i, b in enumerate(boxes):
+            try:
+                x, y, w, h = (int(v) for v in b)
+                rows.append((x, y, w, h))
+                good.append(i)
+            except Exception as e:                              # noqa: BLE001 - mirrored from the reference's bare except
+                errors[i] = LineError(f"invalid box {b!r}: {e}")
+        if not rows:
+            return np.zeros((0, 4), np.int64), np.zeros(0, np.int64), errors
+        ent, valid = BatchedRecognizer.boxes_to_entries(page_shape, rows, page_offset)
+        return ent[valid], np.asarray(good, np.int64)[valid], errors
+
+    def _isolate(self, arrays, ent, method, streaming, exc):
+        """The batch failed as a whole: recognise its lines one by one so that a single bad region cannot take the
+        others down (the reference's per-region try/except); a line that fails alone becomes a LineError."""
+        out = []
+        for k in range(len(ent)):
+            try:
+                out.append(self.collect(self.submit(arrays, ent[k:k + 1], method, streaming))[0])
+            except Exception as e:                              # noqa: BLE001
+                out.append(LineError(str(e)))
+        if all(isinstance(r, LineError) for r in out):
+            raise exc                                           # nothing works: a device/library problem, not a bad line
+        return out
 
     def recognize_boxes(self, page_gray: np.ndarray, boxes: Sequence[Sequence[int]], method: str = "ctc",
                         streaming: bool = False) -> List[Optional[LineResult]]:
         """All boxes of one grayscale page; boxes whose clamped crop is empty give ``None``
-        (the reference skips them, core.py:516-517 / 773-774)."""
-        page = np.ascontiguousarray(page_gray)
-        if page.dtype != np.uint8 or page.ndim != 2:
-            raise ValueError("page must be a 2-D uint8 array")
-        ent, valid = self.boxes_to_entries(page.shape, boxes)
-        buf = torch.empty(page.size + 16, dtype=torch.uint8).pin_memory()
-        buf.numpy()[:page.size] = page.reshape(-1)
-        res = self.recognize_packed(buf, ent[valid], method, streaming)
-        out: List[Optional[LineResult]] = [None] * len(boxes)
-        for k, i in enumerate(np.nonzero(valid)[0]):
-            out[i] = res[k]
+        (the reference skips them, core.py:516-517 / 773-774), malformed boxes a ``LineError``."""
+        return self.recognize_pages([page_gray], [boxes], method, streaming)[0]
+
+    def recognize_pages(self, pages: Sequence[np.ndarray], boxes_list: Sequence[Sequence[Sequence[int]]],
+                        method: str = "ctc", streaming: bool = False, batch_lines: int = 384):
+        """Several pages with their detector boxes: whole pages are grouped into batches of about ``batch_lines``
+        lines, every page is uploaded ONCE (crops are taken on the device), and two batches are kept in flight so
+        the upload and the host-side string work of one batch overlap the kernels of the other.  Returns one list
+        per page, aligned with its boxes (``None`` = empty crop, ``LineError`` = unusable region).  ``pages`` may be
+        a uint8 tensor [n, H, W] in pinned host memory: its pages are then uploaded in place (no staging copy)."""
+        n_pages = len(pages)
+        out: List[List] = [[None] * len(b) for b in boxes_list]
+        # ---- batches of whole pages
+        batches, cur, cur_lines = [], [], 0
+        for p in range(n_pages):
+            if len(boxes_list[p]) == 0:
+                continue
+            cur.append(p)
+            cur_lines += len(boxes_list[p])
+            if cur_lines >= batch_lines:
+                batches.append(cur)
+                cur, cur_lines = [], 0
+        if cur:
+            batches.append(cur)
+
+        as_tensor = isinstance(pages, torch.Tensor)
+        if as_tensor and (pages.dtype != torch.uint8 or pages.dim() != 3):
+            raise ValueError("a page tensor must be uint8 [n, H, W]")
+
+        def launch(batch):
+            arrays, ents, where, off = [], [], [], 0
+            p_first = batch[0]
+            for p in batch:
+                if as_tensor:
+                    shape = tuple(pages.shape[1:])
+                    off = (p - p_first) * shape[0] * shape[1]   # the batch uploads pages[p_first .. p_last] as one block
+                else:
+                    page = np.ascontiguousarray(pages[p])
+                    if page.dtype != np.uint8 or page.ndim != 2:
+                        raise ValueError("page must be a 2-D uint8 array")
+                    shape = page.shape
+                    arrays.append(page)
+                ent, idx, errors = self._page_entries(shape, boxes_list[p], off)
+                for i, e in errors.items():
+                    out[p][i] = e
+                if not as_tensor:
+                    off += page.size
+                ents.append(ent)
+                where += [(p, int(i)) for i in idx]
+            if as_tensor:
+                # zero-copy: the H2D runs straight out of the caller's (pinned) tensor
+                arrays = pages[p_first:batch[-1] + 1].reshape(-1)
+            ent = np.concatenate(ents) if ents else np.zeros((0, 4), np.int64)
+            try:
+                return (self.submit(arrays, ent, method, streaming), where, arrays, ent)
+            except _lib.KiriError as e:
+                return (e, where, arrays, ent)
+
+        def finish(item):
+            tk, where, arrays, ent = item
+            try:
+                if isinstance(tk, Exception):
+                    raise tk
+                res = self.collect(tk)
+            except _lib.KiriError as e:
+                res = self._isolate(arrays, ent, method, streaming, e)
+            for (p, i), r in zip(where, res):
+                out[p][i] = r
+
+        pending = None
+        for batch in batches:
+            item = launch(batch)
+            if pending is not None:
+                finish(pending)
+            pending = item
+        if pending is not None:
+            finish(pending)
         return out

@@ -122,3 +122,80 @@ def test_beam_extract_text(setup):
         assert 0.0 <= r["confidence"] <= 1.0
     chunks = list(ocr.extract_text_stream_chars(img))
     assert chunks and {c["region_number"] for c in chunks} == {1, 2}
+
+
+def test_recognize_region_never_inverts(setup, tok_cfg):
+    """A caller tensor with a DARK background (e.g. straight from preprocess_pil) must be recognised as it is:
+    the reference's recognize_region never inverts (core.py:530-568); only _preprocess_region does."""
+    from kiri_ocr_b200 import OCR, _lib
+    from oracle import decode as OD, model as OM, preprocess as OP
+    from tests.tolerances import logit_tol
+    path, img, page, boxes, sd = setup
+    tok, cfg = tok_cfg
+    ocr = OCR(model_path=path, decode_method="fast")
+    light = ocr._preprocess_region(page, boxes[0])
+    dark = -light                                                  # 255 - v in plane space
+    plane_dark = ocr._tensor_to_plane(dark).numpy()
+    assert plane_dark.mean() < 127
+    assert np.array_equal(plane_dark, 255 - OP.preprocess_region(page, boxes[0]))
+    t_dark, c_dark = ocr.recognize_region(dark)
+    o_text, o_conf, _ = OD.recognize_plane(sd, tok, cfg, plane_dark, "ctc")
+    assert abs(c_dark - o_conf) < 0.01
+    # frame level, under the margin rule
+    eng = ocr.model
+    ent = np.array([(0, 640, 640, 48, _lib.CROP_NO_INVERT)], np.int64)
+    r = eng.recognize_packed([plane_dark.reshape(-1)], ent, "ctc", streaming=True)[0]
+    lg = OM.ctc_logits(sd, OM.encode(sd, torch.from_numpy(OP.normalise(plane_dark))[None, None]))[0].numpy()
+    srt = np.sort(lg, axis=1)
+    safe = (srt[:, -1] - srt[:, -2]) > 2 * logit_tol(sd)
+    assert safe.sum() > 40 and np.array_equal(np.asarray(r.frame_ids)[safe], lg.argmax(1)[safe])
+    # and WITHOUT the flag the same bytes are treated as a crop and inverted (the _preprocess_region rule)
+    r_inv = eng.recognize_packed([plane_dark.reshape(-1)], ent[:, :4], "ctc", streaming=True)[0]
+    t_light, c_light = ocr.recognize_region(light)
+    assert abs(r_inv.confidence - c_light) < 1e-6 and r_inv.text == t_light
+
+
+def test_malformed_region_is_isolated(setup):
+    """Per-region isolation (core.py:771-791, 873-885, 1011-1026): a region that cannot be processed is dropped by
+    process_document, reported with an ``error`` key by the streaming forms; the other regions are unaffected."""
+    from kiri_ocr_b200 import OCR
+    path, img, page, boxes, sd = setup
+    ocr = OCR(model_path=path, decode_method="fast")
+    ocr._detector = FakeDetector([boxes[0], ("a", "b", 3, 4), boxes[1], (1, 2, 3)])
+    res = ocr.process_document(img)
+    assert [r["line_number"] for r in res] == [1, 3]
+    ocr._detector = FakeDetector([boxes[0], boxes[1]])
+    clean = ocr.process_document(img)
+    assert [r["text"] for r in res] == [r["text"] for r in clean]
+    ocr._detector = FakeDetector([boxes[0], ("a", "b", 3, 4), boxes[1], (1, 2, 3)])
+    st = list(ocr.process_document_streaming(img))
+    assert [("error" in r) for r in st] == [False, True, False, True] and st[1]["text"] == "" and st[1]["total_regions"] == 4
+    chunks = list(ocr.extract_text_stream_chars(img))
+    errs = [c for c in chunks if "error" in c]
+    assert [c["region_number"] for c in errs] == [2, 4] and errs[-1]["document_finished"] is True
+    assert all(c["region_finished"] and c["region_start"] for c in errs)
+
+
+def test_recognize_pages_equals_per_page(setup):
+    """The pipelined multi-page path (whole pages per batch, two batches in flight) returns exactly what the
+    per-page call returns, page by page and box by box, for fast and accurate."""
+    from kiri_ocr_b200 import OCR
+    path, img, page, boxes, sd = setup
+    ocr = OCR(model_path=path, decode_method="fast")
+    eng = ocr.model
+    pages, bl = [], []
+    for s in range(5):
+        p, b = FX.make_page(6, seed=20 + s, page_hw=(420, 760))
+        pages.append(p)
+        bl.append(list(b) + ([(750, 410, 30, 30), (900, 900, 5, 5)] if s == 2 else []))   # a clamped and an empty box
+    bl[3] = []                                                     # a page without boxes
+    for method in ("ctc", "decoder"):
+        multi = eng.recognize_pages(pages, bl, method, batch_lines=12)
+        assert [len(m) for m in multi] == [len(b) for b in bl]
+        for p, b, m in zip(pages, bl, multi):
+            single = eng.recognize_boxes(p, b, method) if b else []
+            for x, y in zip(single, m):
+                assert (x is None) == (y is None)
+                if x is not None:
+                    assert x.text == y.text and x.confidence == y.confidence and np.array_equal(x.ids, y.ids)
+    assert multi[2][-1] is None

@@ -28,7 +28,7 @@ def test_library_loads_and_exports_every_declared_symbol():
 
 def test_struct_sizes_match_header_layout():
     import ctypes as C
-    assert C.sizeof(_lib.KiriCropDesc) == 40
+    assert C.sizeof(_lib.KiriCropDesc) == 48
     assert C.sizeof(_lib.KiriDims) == 14 * 4
     assert C.sizeof(_lib.KiriEncLayerWeights) == 12 * 8
     assert C.sizeof(_lib.KiriDecLayerWeights) == 18 * 8

@@ -9,7 +9,7 @@
 Workload "lines" (default): a "step" is one pass of the hot path (preprocess -> stem -> encoder -> CTC head -> CTC greedy
 [-> greedy / beam decoder]) over one batch of 256 synthetic line crops per GPU.  ``value`` is timed with CUDA events with
 the packed source crops already in HBM; ``e2e`` goes through the public submit()/collect() pair from pinned host memory
-to Python strings.  Every rank works on its own crops (weak scaling); the path's exchange (fixed-stride result records,
+to Python strings.  Every rank works on its own copy of that batch (weak scaling: identical per-GPU work); the path's exchange (fixed-stride result records,
 all-gather over NCCL) runs on a side stream so that it overlaps the next step, still inside the timed region.
 Workload "pages": 10 000 lines on 250 synthetic pages, page-major sharded over the ranks (strong scaling), ONE all-gather
 at the end, and an ordered-equality check of the N-GPU result against a single-GPU run.  One JSON line is printed by rank 0.
@@ -238,25 +238,29 @@ class Exchange:
         self.out = [torch.empty((world * BATCH, 2 + T), dtype=torch.int32, device=device) for _ in range(2)] if world > 1 else None
         self.i = 0
         self.work = [None, None]
+        self.packed = None
 
-    def buffer(self):
-        """The record buffer of the next step; the gather that last read it has been waited for on the main stream."""
-        b = self.i & 1
-        if self.work[b] is not None:
-            self.work[b].wait()                                  # stream-side wait (no host block) on gather i-2
-            self.work[b] = None
-        return self.rec[b]
-
-    def gather(self):
-        """Called on the main stream right after the kernel that filled buffer(): fence, then all-gather on the side."""
+    def exchange(self, fill, inputs=()):
+        """Called on the main stream right after the step's last kernel: the side stream waits for it (event fence),
+        `fill(rec)` builds the step's records there (so the main stream goes straight on to the next step), then the
+        all-gather runs on NCCL's stream.  Buffer b is reused two steps later, after its gather."""
         b = self.i & 1
         self.i += 1
-        if self.world == 1:
-            return
         main = torch.cuda.current_stream()
-        self.side.wait_stream(main)
+        if self.packed is not None:
+            main.wait_event(self.packed)                         # the previous step's records are built (long done): buffers
+        self.side.wait_stream(main)                              # they read (ping-pong result slots) may be overwritten
         with torch.cuda.stream(self.side):
-            self.work[b] = self.dist.all_gather_into_tensor(self.out[b], self.rec[b], async_op=True)
+            for t in inputs:
+                t.record_stream(self.side)                       # allocated on the main stream, read on the side stream
+            if self.work[b] is not None:
+                self.work[b].wait()                              # side stream waits for gather i-2 of this buffer
+                self.work[b] = None
+            fill(self.rec[b])
+            self.packed = torch.cuda.Event()
+            self.packed.record()
+            if self.world > 1:
+                self.work[b] = self.dist.all_gather_into_tensor(self.out[b], self.rec[b], async_op=True)
 
     def finish(self):
         for b in (0, 1):
@@ -283,7 +287,7 @@ def run_lines(args):
     cfg, tok, sd = make_model(5 if args.method == "beam" else 0)
     eng = BatchedRecognizer(sd, cfg, tok, device="cuda", width_mode=args.width_mode, stem_chunk=args.stem_chunk)
     method = METHODS[args.method]
-    crops = FX.make_line_crops(BATCH, seed=1234 + rank)
+    crops = FX.make_line_crops(BATCH, seed=1234)          # the SAME synthetic batch on every rank: identical per-GPU work
     buf, ent = eng.pack_crops(crops)
     prep = eng.prepare_resident(buf, ent)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")       # > 126 MB L2
@@ -297,25 +301,27 @@ def run_lines(args):
         if method == "beam":
             tk = eng.submit(prep["src"], ent, "beam")
             res = eng.collect(tk)
-            if world > 1:
-                eng.ticket_records(tk, T, out=xch.buffer())
-                xch.gather()
+            xch.exchange(lambda rec: eng.ticket_records(tk, T, out=rec), tk["keep"])
             return res
         outs = eng.step_resident(prep, method)
-        rec = xch.buffer()
         if method == "ctc":
             ids, n, conf = outs[0]
-            _lib.check(eng.lib.kiri_pack_records(ids.data_ptr(), n.data_ptr(), conf.data_ptr(), prep["mem_row0"].data_ptr(),
-                                                 BATCH, T, rec.data_ptr(), _lib.stream_ptr()), "kiri_pack_records")
-            eng.launches += 1
+
+            def fill(rec):
+                _lib.check(eng.lib.kiri_pack_records(ids.data_ptr(), n.data_ptr(), conf.data_ptr(), prep["mem_row0"].data_ptr(),
+                                                     BATCH, T, rec.data_ptr(), _lib.stream_ptr()), "kiri_pack_records")
+                eng.launches += 1
+            xch.exchange(fill, (ids, n, conf))
         else:
             d_ids, n_out, sum_lp, _ = outs[0]
-            k = min(T, d_ids.shape[1])
-            rec[:, 0] = n_out
-            rec[:, 1] = sum_lp.view(torch.int32)
-            rec[:, 2:2 + k] = d_ids[:, :k]
-            eng.launches += 3
-        xch.gather()
+
+            def fill(rec):
+                k = min(T, d_ids.shape[1])
+                rec[:, 0] = n_out
+                rec[:, 1] = sum_lp.view(torch.int32)
+                rec[:, 2:2 + k] = d_ids[:, :k]
+                eng.launches += 3
+            xch.exchange(fill, (d_ids, n_out, sum_lp))
         return outs
 
     def barrier():
@@ -371,9 +377,8 @@ def run_lines(args):
     t0 = time.perf_counter()
     for _ in range(args.steps):
         tk = eng.submit(buf, ent, method)
-        if world > 1 and method != "beam":
-            eng.ticket_records(tk, T, out=xch.buffer())
-            xch.gather()
+        if method != "beam":
+            xch.exchange(lambda rec, tk=tk: eng.ticket_records(tk, T, out=rec), tk["keep"])
         res = eng.collect(tk)
     xch.finish()
     barrier()
@@ -391,9 +396,8 @@ def run_lines(args):
 
     def sub():
         t = eng.submit(buf, ent, method)
-        if world > 1 and method != "beam":
-            eng.ticket_records(t, T, out=xch.buffer())
-            xch.gather()
+        if method != "beam":
+            xch.exchange(lambda rec, t=t: eng.ticket_records(t, T, out=rec), t["keep"])
         return t
     tk = sub()
     for _ in range(args.steps - 1):

@@ -33,12 +33,13 @@ def shard_bounds(weights: Sequence[float], world: int) -> List[Tuple[int, int]]:
 
 
 def pack_records(line_idx: np.ndarray, ids: List[np.ndarray], conf: Sequence[float], lmax: int) -> torch.Tensor:
-    rec = np.zeros((len(line_idx), 3 + lmax), np.int32)
+    n = len(line_idx)
+    rec = np.zeros((n, 3 + lmax), np.int32)
     rec[:, 0] = line_idx
-    for i, row in enumerate(ids):
-        k = min(len(row), lmax)
-        rec[i, 1] = k
-        rec[i, 3:3 + k] = row[:k]
+    lens = np.fromiter((min(len(r), lmax) for r in ids), np.int64, n)
+    rec[:, 1] = lens
+    if n and lens.sum():
+        rec[:, 3:][np.arange(lmax)[None, :] < lens[:, None]] = np.concatenate([np.asarray(r[:lmax], np.int32) for r in ids])
     rec[:, 2] = np.asarray(conf, np.float32).view(np.int32)
     return torch.from_numpy(rec)
 
@@ -64,13 +65,13 @@ def unpack_records(rec: torch.Tensor, n_total: int):
     r = rec.cpu().numpy()
     ids: List[Optional[np.ndarray]] = [None] * n_total
     conf: List[Optional[float]] = [None] * n_total
-    for row in r:
-        li, k = int(row[0]), int(row[1])
+    cf = r[:, 2].copy().view(np.float32)
+    for row, li, k, c in zip(r, r[:, 0].tolist(), r[:, 1].tolist(), cf.tolist()):
         if k < 0:
             conf[li] = float("nan")
             continue
-        ids[li] = row[3:3 + k].copy()
-        conf[li] = float(row[2:3].view(np.float32)[0])
+        ids[li] = row[3:3 + k]
+        conf[li] = c
     return ids, conf
 
 
@@ -84,18 +85,25 @@ def _record_width(engine, method: str) -> int:
 
 
 def _texts(engine, ids, conf, method):
+    """(text, confidence) per line from the gathered ids; the texts of all lines in one vectorised pass when the
+    tokenizer offers ``decode_batch``."""
     tok = engine.tok
+    rows = [r for r in ids if r is not None]
+    if method != "ctc":
+        rows = [r[: int(np.argmax(r == tok.dec_eos))] if (r == tok.dec_eos).any() else r for r in rows]
+    if hasattr(tok, "decode_batch"):
+        flat = np.concatenate(rows) if rows else np.zeros(0, np.int64)
+        texts = iter(tok.decode_batch(flat, [len(r) for r in rows], "ctc" if method == "ctc" else "dec"))
+    elif method == "ctc":
+        texts = iter(tok.decode_collapsed_ctc(r.tolist()) for r in rows)
+    else:
+        texts = iter(tok.decode_dec(r.tolist()) for r in rows)
     out = []
     for row, c in zip(ids, conf):
         if row is None:
             out.append(None if c is None else LineFailed())
-        elif method == "ctc":
-            out.append((tok.decode_collapsed_ctc(row.tolist()), c))
         else:
-            cut = row.tolist()
-            if tok.dec_eos in cut:
-                cut = cut[: cut.index(tok.dec_eos)]
-            out.append((tok.decode_dec(cut), c))
+            out.append((next(texts), c))
     return out
 
 

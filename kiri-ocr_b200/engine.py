@@ -681,7 +681,10 @@ class BatchedRecognizer:
         c_h = hr[M + n_lines:M + 2 * n_lines].view(np.float32)
         if method == "ctc":
             want_frames = tk["want_frames"]
-            tab = self._ctc_table
+            # texts of the whole batch in one vectorised pass (CharTokenizer.decode_batch)
+            flat = [hr[r0:r0 + B * T].reshape(B, T)[np.arange(T)[None, :] < n_h[p0:p0 + B, None]]
+                    for (r0, B, T), p0 in zip(tk["rows"], np.cumsum([0] + [b for _, b, _ in tk["rows"]])[:-1])]
+            texts = self.tok.decode_batch(np.concatenate(flat), n_h, "ctc")
             pos = 0
             for (r0, B, T) in tk["rows"]:
                 ids_h = hr[r0:r0 + B * T].reshape(B, T)
@@ -689,9 +692,8 @@ class BatchedRecognizer:
                 p_h = hr[2 * M + 2 * n_lines + r0:2 * M + 2 * n_lines + r0 + B * T].view(np.float32).reshape(B, T) if want_frames else None
                 for j in range(B):
                     k = pos + j
-                    row = ids_h[j, :n_h[k]]
                     cf = float(c_h[k])
-                    results[order[k]] = LineResult("".join([tab[i] for i in row.tolist()]), cf, cf, row,
+                    results[order[k]] = LineResult(texts[k], cf, cf, ids_h[j, :n_h[k]],
                                                    frame_ids=None if f_h is None else f_h[j],
                                                    frame_prob=None if p_h is None else p_h[j], len_est=int(n_h[k]))
                 pos += B
@@ -705,17 +707,19 @@ class BatchedRecognizer:
         ids_h, no_h = hd[:LL].reshape(n_lines, Lcap), hd[LL:LL + n_lines]
         slp_h = hd[LL + 2 * n_lines:2 * LL + 2 * n_lines].view(np.float32).reshape(n_lines, Lcap)
         spr_h = hd[2 * LL + 2 * n_lines:3 * LL + 2 * n_lines].view(np.float32).reshape(n_lines, Lcap) if streaming else None
-        tab, eos = self._dec_table, self.tok.dec_eos
+        eos = self.tok.dec_eos
+        col = np.arange(Lcap)[None, :]
+        valid = col < no_h[:, None]
+        is_eos = (ids_h == eos) & valid
+        cut = np.where(is_eos.any(1), is_eos.argmax(1), no_h)            # ids before the first EOS make the text
+        texts = self.tok.decode_batch(ids_h[col < cut[:, None]], cut, "dec")
+        lp_sum = np.where(valid, slp_h, 0.0).astype(np.float64).sum(1)
         for j, li in enumerate(order):
             nj = int(no_h[j])
-            row = ids_h[j, :nj]
-            hit = np.nonzero(row == eos)[0]
-            text_ids = row[:hit[0]] if len(hit) else row
-            lps = slp_h[j, :nj].astype(np.float64)
-            dec_conf = min(1.0, max(0.0, math.exp(float(lps.sum()) / nj))) if nj else 0.0
-            results[li] = LineResult("".join([tab[i] for i in text_ids.tolist()]), 0.6 * dec_conf + 0.4 * float(c_h[j]),
-                                     float(c_h[j]), row, step_logp=slp_h[j, :nj],
-                                     step_prob=None if spr_h is None else spr_h[j, :nj], len_est=int(len_h[j]))
+            dec_conf = min(1.0, max(0.0, math.exp(float(lp_sum[j]) / nj))) if nj else 0.0
+            results[li] = LineResult(texts[j], 0.6 * dec_conf + 0.4 * float(c_h[j]), float(c_h[j]), ids_h[j, :nj],
+                                     step_logp=slp_h[j, :nj], step_prob=None if spr_h is None else spr_h[j, :nj],
+                                     len_est=int(len_h[j]))
         return results
 
     def ticket_records(self, tk, T: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -88,35 +88,30 @@ int kiri_preprocess_pack(const uint8_t* src, const KiriCropDesc* descs, int n_cr
                          int smem_bytes, int max_strips, uint8_t* planes_u8, void* norm_bf16,
                          unsigned long long* crop_sums_scratch /* device, n_crops entries */, cudaStream_t stream);
 
+/* Page ingest on the device: interleaved BGR uint8 [n_pixels, 3] -> gray uint8 [n_pixels], bit-exact with
+ * cv2.cvtColor(img, cv2.COLOR_BGR2GRAY) (kiri_ocr/core.py:762-766; OpenCV's 15-bit fixed-point BT.601 weights:
+ * (B*3735 + G*19235 + R*9798 + 16384) >> 15).  Both buffers 4-byte aligned. */
+int kiri_bgr_to_gray(const uint8_t* bgr_u8, long long n_pixels, uint8_t* gray_u8, cudaStream_t stream);
+
 /* ---------------------------------------------------------------- K2: stem layer 1
  * Replaces ConvStem.net[0:3] (kiri_ocr/model.py:215-217).  w_host[48*9], b_host[48]: BN-folded
- * fp32 weights in HOST memory (they travel as kernel parameters).  out: NHWC bf16, 64 channels
- * (48 + 16 zero).  W must be a multiple of 128. */
+ * fp32 weights in HOST memory (they travel as kernel parameters).  out: DENSE NHWC bf16 with 48 channels
+ * (96 bytes per pixel).  W must be a multiple of 128, H even. */
 int kiri_conv1(const uint8_t* planes_u8, const float* w_host, const float* b_host, int n_lines, int H,
-               int W, void* out_bf16_nhwc64, cudaStream_t stream);
-/* The two forms of the layer by name: fp32 FMAs on the CUDA cores (the default of kiri_conv1) and warp-level
- * tensor-core MMAs on exact bf16 operands (u = v - 128, split weights; opt-in with KIRI_CONV1_TC=1, measured slower). */
-int kiri_conv1_tc(const uint8_t* planes_u8, const float* w_host, const float* b_host, int n_lines, int H,
-                  int W, void* out_bf16_nhwc64, cudaStream_t stream);
-int kiri_conv1_ffma(const uint8_t* planes_u8, const float* w_host, const float* b_host, int n_lines, int H,
-                    int W, void* out_bf16_nhwc64, cudaStream_t stream);
-/* The default (FFMA) form for several width groups in ONE launch: planes / out / lines / W per group (host arrays). */
-int kiri_conv1_multi(const uint8_t* const* planes_u8, void* const* out_bf16_nhwc64, const int* group_lines,
+               int W, void* out_bf16_nhwc48, cudaStream_t stream);
+/* The same for several width groups in ONE launch: planes / out / lines / W per group (host arrays). */
+int kiri_conv1_multi(const uint8_t* const* planes_u8, void* const* out_bf16_nhwc48, const int* group_lines,
                      const int* group_W, int n_groups, const float* w_host, const float* b_host, int H,
                      cudaStream_t stream);
 
-/* K2+K3 fused: stem layers 1 and 2 in one kernel (ConvStem.net[0:6], kiri_ocr/model.py:215-220): the
- * 48-channel activation never leaves the SM.  planes_u8 [n, H, W] (H % 4 == 0, W % 128 == 0),
- * conv2_w48 bf16 [96, 9*48] ordered (ky, kx, cin), out NHWC bf16 [n, H/2, W/2, 96]. */
-int kiri_stem12(const uint8_t* planes_u8, const float* conv1_w_host, const float* conv1_b_host, const void* conv2_w48,
-                const float* conv2_bias, int n_lines, int H, int W, void* out_nhwc96, cudaStream_t stream);
-
 /* ---------------------------------------------------------------- K3-K5, K8, K9, K11: tcgen05 GEMMs
  * 3x3 conv as implicit GEMM (replaces ConvStem.net[3:12], kiri_ocr/model.py:218-226): input NHWC
- * bf16 [n, IH, IW, Cin] (Cin % 32 == 0), weights bf16 [N, 9*Cin] ordered (ky, kx, cin), pad 1,
- * stride (sh, sw); output NHWC bf16 [n, OH, OW, N] = silu(conv + bias). */
+ * bf16 [n, IH, IW, cin_mem], weights bf16 [N, 9*Cin] ordered (ky, kx, cin) with Cin % 32 == 0, pad 1,
+ * stride (sh, sw); output NHWC bf16 [n, OH, OW, N] = silu(conv + bias).  cin_mem <= Cin is the number of channels
+ * actually stored per pixel (0 = Cin): the TMA unit zero-fills channels cin_mem..Cin-1 in shared memory
+ * (conv2 reads conv1's dense 48-channel output with Cin = 64). */
 int kiri_conv3x3_bf16(const void* in_nhwc, const void* w, const float* bias, int n, int IH, int IW,
-                      int Cin, int N, int sh, int sw, void* out_nhwc, cudaStream_t stream);
+                      int Cin, int N, int sh, int sw, void* out_nhwc, int cin_mem, cudaStream_t stream);
 /* out[M, N] = epilogue(a[M, K] @ w[N, K]^T + bias) — replaces the nn.Linear call sites of the
  * encoder / CTC head / decoder (kiri_ocr/model.py:246-297).  K % 64 == 0.  `resid` (fp32 [M, N])
  * may alias `out`.  For KIRI_EPI_BIAS_RESID_LN: N == 256, out2 = bf16 [M, 256]. */
@@ -245,7 +240,6 @@ typedef struct {
   KiriDecLayerWeights dec[KIRI_MAX_LAYERS];
   const float* dec_ln_g; const float* dec_ln_b;
   const void* heads_w; const float* heads_b;               /* [2*Vp, D], [2*Vp]: dec_head rows then lm_head rows, Vp = roundup(Vd, 16) */
-  const void* conv2_w48;                                   /* [96, 9*48] (ky, kx, cin) unpadded: the fused conv1+conv2 kernel (nullable) */
 } KiriWeights;
 
 typedef struct KiriHandle KiriHandle;
@@ -326,7 +320,11 @@ int kiri_decode_greedy_multi(KiriHandle* h, const void* mem_bf16, long long M_to
                              const KiriDecodeParams* p,
                              void* workspace, size_t workspace_bytes, int* ids, int* n_out, float* sum_logp,
                              float* step_logp, float* step_prob, const int* forced_ids, int* steps_run_host,
-                             cudaStream_t stream);
+                             int* progress, int publish, cudaStream_t stream);
+/* Live streaming (kiri_ocr/core.py:887-1026, model.py:779-946): `progress` (nullable, [B]) receives after EVERY decode
+ * step of a line   steps_available | (1 << 30 once the line has ended)   ; with publish = 1 the step's records (ids,
+ * step_logp, step_prob) are made visible system-wide first (__threadfence_system), so ids / step_* / progress may be
+ * MAPPED PINNED HOST memory that a host thread polls while the kernel is still decoding. */
 
 /* ---------------------------------------------------------------- beam search (decode_method="beam")
  * Replaces beam_decode_one_batched at BEAM > 1 (kiri_ocr/model.py:390-600): `beam` (<= 5) hypotheses
@@ -342,7 +340,12 @@ int kiri_decode_beam_multi(KiriHandle* h, const void* mem_bf16, long long M_tota
                            const int* mem_len, int max_T, const int* len_est, const int* line_perm, int B, int Lmax, int beam,
                            double lenp, const KiriDecodeParams* p, void* workspace, size_t workspace_bytes,
                            double* bm_score, int* bm_len, int* bm_state, int* bm_ids, float* bm_logp,
-                           cudaStream_t stream);
+                           int stream_rule, int* bm_trace, int* progress, int publish, cudaStream_t stream);
+/* stream_rule = 1 selects beam_decode_streaming's variant (kiri_ocr/model.py:949-1152): hypotheses are pruned by
+ * score / L^lenp and a line stops as soon as its BEST hypothesis has ended.  bm_trace (nullable, [B, Lmax, beam, 3]
+ * int32) records for every step and kept hypothesis, in rank order: {rank of its parent in the previous step, appended
+ * token (-1: a finished hypothesis carried over), bits of the token's penalised log-prob} (parent -1 = slot unused), from
+ * which the caller rebuilds the best partial hypothesis of every step; progress / publish as for the greedy decoder. */
 /* K13: CTC forward-algorithm score of every hypothesis = compute_ctc_alignment_score
  * (kiri_ocr/model.py:603-668).  logits: fp32 [M_total, ld] CTC logits (first C columns valid); line b
  * owns rows [mem_row0[b], +mem_len[b]); max_T >= every mem_len.  out: [n_lines, beam] fp32. */

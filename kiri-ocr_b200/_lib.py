@@ -54,7 +54,7 @@ class KiriWeights(C.Structure):
                 + [(n, vp) for n in ("enc_ln_g", "enc_ln_b", "ctc_ln_g", "ctc_ln_b", "ctc_w", "ctc_b",
                                      "crosskv_w", "crosskv_b", "dec_emb", "dec_pe")]
                 + [("dec", KiriDecLayerWeights * KIRI_MAX_LAYERS)]
-                + [(n, vp) for n in ("dec_ln_g", "dec_ln_b", "heads_w", "heads_b", "conv2_w48")])
+                + [(n, vp) for n in ("dec_ln_g", "dec_ln_b", "heads_w", "heads_b")])
 
 
 class KiriGroup(C.Structure):
@@ -78,15 +78,13 @@ _SIGS = {
     "kiri_profile_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]),
     "kiri_preprocess_smem_bytes": (C.c_int, [C.c_int] * 6),
     "kiri_preprocess_pack": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]),
+    "kiri_bgr_to_gray": (C.c_int, [vp, C.c_longlong, vp, vp]),
     "kiri_conv1": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]),
-    "kiri_conv1_ffma": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]),
-    "kiri_conv1_tc": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]),
     "kiri_conv1_multi": (C.c_int, [C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, vp, vp,
                                    C.c_int, vp]),
     "kiri_pool_pos_ln_multi": (C.c_int, [C.POINTER(vp), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, vp, C.c_int, C.c_int,
                                          vp, vp, vp, vp, vp, vp, vp]),
-    "kiri_stem12": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]),
-    "kiri_conv3x3_bf16": (C.c_int, [vp, vp, vp] + [C.c_int] * 7 + [vp, vp]),
+    "kiri_conv3x3_bf16": (C.c_int, [vp, vp, vp] + [C.c_int] * 7 + [vp, C.c_int, vp]),
     "kiri_gemm_bf16": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),
     "kiri_gemm_ref": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]),
     "kiri_pool_pos_ln": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp]),
@@ -107,10 +105,10 @@ _SIGS = {
     "kiri_decode_workspace_bytes": (C.c_size_t, [vp, C.c_int, C.c_int, C.c_int]),
     "kiri_decode_multi_workspace_bytes": (C.c_size_t, [vp, C.c_int, C.c_longlong, C.c_int]),
     "kiri_decode_greedy_multi": (C.c_int, [vp, vp, C.c_longlong, vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.POINTER(KiriDecodeParams),
-                                           vp, C.c_size_t, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int), vp]),
+                                           vp, C.c_size_t, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int), vp, C.c_int, vp]),
     "kiri_decode_beam_workspace_bytes": (C.c_size_t, [vp, C.c_int, C.c_longlong, C.c_int, C.c_int]),
     "kiri_decode_beam_multi": (C.c_int, [vp, vp, C.c_longlong, vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_double,
-                                         C.POINTER(KiriDecodeParams), vp, C.c_size_t, vp, vp, vp, vp, vp, vp]),
+                                         C.POINTER(KiriDecodeParams), vp, C.c_size_t, vp, vp, vp, vp, vp, C.c_int, vp, vp, C.c_int, vp]),
     "kiri_ctc_align_score": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, C.c_int,
                                        C.c_int, vp, vp]),
     "kiri_decode_greedy": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(KiriDecodeParams), vp,

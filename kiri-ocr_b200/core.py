@@ -8,7 +8,9 @@ plug-in boundary (core.py:469-485, 746-756: anything with ``detect_lines_objects
 ``_preprocess_region`` + ``recognize_region`` per box on the host, all boxes of a page go through
 ``BatchedRecognizer`` in one batch.  There is no CPU path: ``device`` must be a CUDA device.
 ``decode_method="beam"`` runs the device beam search (widths 1..5, ``ocr.cfg.BEAM``) and the device CTC
-forward rescoring; its streaming form replays the final best hypothesis.
+forward rescoring.  The streaming calls are LIVE for the decoders: the persistent decode kernel publishes every
+step into mapped host memory and chunks are yielded while it is still running (beam streaming follows
+``beam_decode_streaming``'s own rule: prune by ``score / L**0.8``, stop when the best hypothesis ended).
 """
 from __future__ import annotations
 
@@ -229,11 +231,18 @@ class OCR:
         return boxes, [1.0] * len(boxes)
 
     @staticmethod
-    def _read_gray(image_path) -> np.ndarray:
+    def _read_image(image_path) -> np.ndarray:
+        """cv2.imread as the reference does (core.py:762-764): BGR uint8 [H, W, 3] (or gray [H, W])."""
         import cv2
         img = cv2.imread(str(image_path))
         if img is None:
             raise ValueError(f"Could not load image: {image_path}")
+        return img
+
+    @classmethod
+    def _read_gray(cls, image_path) -> np.ndarray:
+        import cv2
+        img = cls._read_image(image_path)
         return cv2.cvtColor(img, cv2.COLOR_BGR2GRAY) if len(img.shape) == 3 else img
 
     # ==================== recognition ====================
@@ -255,7 +264,7 @@ class OCR:
         from .engine import plan_groups
         (idx, descs, smem, n_strips), = plan_groups(ent, self.cfg, "parity").values()
         with torch.cuda.stream(eng.stream):
-            src = eng._stage_host([page], 0)                     # persistent pinned staging, no per-call cudaHostAlloc
+            src, _ = eng._stage_host([page], 0)                  # persistent pinned staging, no per-call cudaHostAlloc
             planes, _ = eng.preprocess(src.to(eng.device, non_blocking=True), descs, self.cfg.IMG_W, smem, n_strips)
             t = planes[0].float().cpu() / 255.0                  # (synchronises: the staging buffer is free again)
         return ((t - 0.5) / 0.5).unsqueeze(0).unsqueeze(0)
@@ -280,9 +289,7 @@ class OCR:
 
     def recognize_region_streaming(self, image_tensor: torch.Tensor, decode_method: Optional[str] = None
                                    ) -> Generator[Dict, None, None]:
-        method = self._method(decode_method)
-        r = self._recognize_planes(self._tensor_to_plane(image_tensor)[None], method, streaming=True)[0]
-        yield from self._chunks(r, method)
+        yield from self._stream_planes(self._tensor_to_plane(image_tensor)[None], self._method(decode_method))
 
     def _chunks(self, r: LineResult, method: str) -> Generator[Dict, None, None]:
         """Replay a decoded line as the reference's streaming chunks (model.py:736-775, 845-946)."""
@@ -321,6 +328,45 @@ class OCR:
             if finished:
                 break
 
+    def _live_chunks(self, tk, line: int, method: str) -> Generator[Dict, None, None]:
+        """The reference's streaming chunks for one line of a LIVE ticket, produced while the device is still decoding
+        (greedy_decode_streaming model.py:845-946, beam_decode_streaming model.py:1117-1150)."""
+        tok, eng = self.tokenizer, self.model
+        if method == "decoder":
+            text = ""
+            for tid, prob, _, step, finished in eng.live_greedy(tk, line):
+                ch = ""
+                if not finished and tid not in (tok.dec_pad, tok.dec_bos, tok.dec_eos) and 0 <= tid < tok.dec_vocab:
+                    ch = tok.dec_text[tid]                       # '' for <unk> (model.py:927-929)
+                    text += ch
+                yield {"token": ch, "token_id": tid, "text": text, "confidence": prob, "step": step, "finished": finished}
+            return
+        import math
+        prev = ""
+        for ids, lps, step, finished in eng.live_beam(tk, line):
+            cut = ids[: ids.index(tok.dec_eos)] if tok.dec_eos in ids else ids
+            cur = tok.decode_dec(cut)
+            conf = min(1.0, max(0.0, math.exp(sum(lps) / len(lps)))) if lps else 0.0
+            yield {"token": cur[len(prev):] if len(cur) > len(prev) else "", "text": cur, "confidence": conf, "step": step,
+                   "finished": finished}
+            prev = cur
+
+    def _stream_planes(self, planes: torch.Tensor, method: str) -> Generator[Dict, None, None]:
+        """Character stream of ONE preprocessed plane: CTC replays the per-frame decisions of the fused kernel
+        (the whole line is one launch); the decoders stream live from the persistent kernel."""
+        eng = self.model
+        n, H, W = planes.shape
+        ent = np.array([(i * H * W, W, W, H, _lib.CROP_NO_INVERT) for i in range(n)], np.int64)
+        if method == "ctc":
+            yield from self._chunks(eng.recognize_packed([planes.numpy().reshape(-1)], ent, "ctc", True)[0], "ctc")
+            return
+        with torch.cuda.stream(eng.stream):
+            tk = eng.submit([planes.numpy().reshape(-1)], ent, method, streaming=True, live=True)
+        try:
+            yield from self._live_chunks(tk, 0, method)
+        finally:
+            eng.live_finish(tk)
+
     def _single_line_plane(self, image_path) -> torch.Tensor:
         img = self._read_gray(image_path)
         t = self._preprocess_region(img, (0, 0, img.shape[1], img.shape[0]), extra_padding=0)
@@ -332,15 +378,14 @@ class OCR:
 
     def recognize_streaming(self, image_path: Union[str, Path], decode_method: Optional[str] = None
                             ) -> Generator[Dict, None, None]:
-        method = self._method(decode_method)
-        r = self._recognize_planes(self._single_line_plane(image_path)[None], method, streaming=True)[0]
-        yield from self._chunks(r, method)
+        yield from self._stream_planes(self._single_line_plane(image_path)[None], self._method(decode_method))
 
     # ==================== documents ====================
     def _recognize_document(self, image_path, mode: str, method: str, streaming: bool = False):
         boxes, det_confs = self._detect(image_path, mode)
-        img_gray = self._read_gray(image_path)
-        res = self.model.recognize_boxes(img_gray, boxes, method, streaming) if len(boxes) else []
+        # the page travels to the device as cv2 decoded it; BGR -> gray (core.py:766) runs there, bit-exact with cv2
+        img = self._read_image(image_path)
+        res = self.model.recognize_boxes(img, boxes, method, streaming) if len(boxes) else []
         return boxes, det_confs, res
 
     @staticmethod
@@ -387,7 +432,7 @@ class OCR:
         det, pages = [], []
         for path in image_paths:
             det.append(self._detect(path, mode))
-            pages.append(self._read_gray(path))
+            pages.append(self._read_image(path))
         res = self.model.recognize_pages(pages, [d[0] for d in det], method)
         return [list(self._results(b, c, r)) for (b, c), r in zip(det, res)]
 
@@ -401,33 +446,57 @@ class OCR:
                                   ) -> Generator[Dict, None, None]:
         from .engine import LineError
         method = self._method(decode_method)
-        boxes, det_confs, res = self._recognize_document(image_path, mode, method, streaming=True)
+        eng = self.model
+        boxes, det_confs = self._detect(image_path, mode)
+        img = self._read_image(image_path)
         total = len(boxes)
+        tk, res = None, []
+        if total:
+            if method == "ctc":
+                res = eng.recognize_boxes(img, boxes, "ctc", True)
+            else:
+                # LIVE: all regions of the page are submitted as one batch; the decode kernel publishes every step into
+                # mapped host memory, and region k's characters are yielded while regions k+1.. are still decoding
+                ent, idx, errors = eng._page_entries(img.shape[:2], boxes, 0)
+                res = [None] * total
+                for i, e in errors.items():
+                    res[i] = e
+                if len(ent):
+                    bgr = [(0, 0, img.shape[0] * img.shape[1], True)] if img.ndim == 3 else None
+                    with torch.cuda.stream(eng.stream):
+                        tk = eng.submit([np.ascontiguousarray(img)], ent, method, streaming=True, bgr_pages=bgr, live=True)
+                    for k, i in enumerate(idx):
+                        res[int(i)] = k                          # line index inside the ticket
         done: List[str] = []
-        for num, (box, dc, r) in enumerate(zip(boxes, det_confs, res), 1):
-            if r is None:
-                continue
-            if isinstance(r, LineError):                           # core.py:1011-1026
+        try:
+            for num, (box, dc, r) in enumerate(zip(boxes, det_confs, res), 1):
+                if r is None:
+                    continue
+                if isinstance(r, LineError):                       # core.py:1011-1026
+                    yield {"token": "", "text": "", "cumulative_text": "\n".join(done), "region_number": num,
+                           "total_regions": total, "step": 0, "region_finished": True, "document_finished": num == total,
+                           "region_start": True, "box": self._box_list(box), "error": r.message}
+                    continue
+                b = [int(v) for v in box]
                 yield {"token": "", "text": "", "cumulative_text": "\n".join(done), "region_number": num,
-                       "total_regions": total, "step": 0, "region_finished": True, "document_finished": num == total,
-                       "region_start": True, "box": self._box_list(box), "error": r.message}
-                continue
-            b = [int(v) for v in box]
-            yield {"token": "", "text": "", "cumulative_text": "\n".join(done), "region_number": num,
-                   "total_regions": total, "step": 0, "region_finished": False, "document_finished": False,
-                   "region_start": True, "box": b, "det_confidence": float(dc)}
-            cur = ""
-            for ch in self._chunks(r, method):
-                cur = ch["text"]
-                yield {"token": ch["token"], "text": cur, "cumulative_text": "\n".join(done + ([cur] if cur else [])),
-                       "region_number": num, "total_regions": total, "step": ch["step"],
-                       "confidence": ch["confidence"], "region_finished": ch["finished"],
-                       "document_finished": ch["finished"] and num == total, "region_start": False, "box": b,
-                       "det_confidence": float(dc)}
-                if ch["finished"]:
-                    break
-            if cur:
-                done.append(cur)
+                       "total_regions": total, "step": 0, "region_finished": False, "document_finished": False,
+                       "region_start": True, "box": b, "det_confidence": float(dc)}
+                cur = ""
+                chunks = self._chunks(r, method) if method == "ctc" else self._live_chunks(tk, r, method)
+                for ch in chunks:
+                    cur = ch["text"]
+                    yield {"token": ch["token"], "text": cur, "cumulative_text": "\n".join(done + ([cur] if cur else [])),
+                           "region_number": num, "total_regions": total, "step": ch["step"],
+                           "confidence": ch["confidence"], "region_finished": ch["finished"],
+                           "document_finished": ch["finished"] and num == total, "region_start": False, "box": b,
+                           "det_confidence": float(dc)}
+                    if ch["finished"]:
+                        break
+                if cur:
+                    done.append(cur)
+        finally:
+            if tk is not None:
+                eng.live_finish(tk)
 
     @staticmethod
     def _group_lines(results: List[Dict]) -> List[str]:

@@ -134,32 +134,23 @@ extern "C" int kiri_gemm_bf16(const void* a, const void* w, const float* bias, i
 }
 
 static GemmLaunch conv_launch(const void* in, const void* w, const float* bias, int n, int IH, int IW, int Cin, int N,
-                              int sh, int sw, void* out) {
+                              int sh, int sw, void* out, int cin_mem = 0) {
   GemmLaunch L;
   memset(&L, 0, sizeof(L));
   L.a = in; L.w = w;
-  L.NB = n; L.IH = IH; L.IW = IW; L.Cin = Cin;
+  L.NB = n; L.IH = IH; L.IW = IW; L.Cin = Cin; L.Cin_mem = cin_mem;
   L.OH = (IH + 2 - 3) / sh + 1; L.OW = (IW + 2 - 3) / sw + 1;
   L.sw = sw; L.sh = sh; L.pad = 1; L.kw = 3; L.kh = 3;
   L.N = N; L.epi = EPI_BIAS_SILU_BF16;
   L.e.out = out; L.e.bias = bias; L.e.resid = nullptr; L.e.ldc = N; L.e.n_valid = N;
   return L;
 }
-static int conv_call(const void* in, const void* w, const float* bias, int n, int IH, int IW, int Cin, int N,
-                     int sh, int sw, void* out, cudaStream_t stream) {
-  if (n == 0) return 0;
-  return launch_gemm_tc(conv_launch(in, w, bias, n, IH, IW, Cin, N, sh, sw, out), stream);
-}
-
-extern "C" int kiri_stem12(const uint8_t* planes_u8, const float* conv1_w_host, const float* conv1_b_host, const void* conv2_w48,
-                           const float* conv2_bias, int n_lines, int H, int W, void* out_nhwc96, cudaStream_t stream) {
-  return launch_stem12(planes_u8, conv1_w_host, conv1_b_host, conv2_w48, conv2_bias, n_lines, H, W, out_nhwc96, stream);
-}
-
 extern "C" int kiri_conv3x3_bf16(const void* in_nhwc, const void* w, const float* bias, int n, int IH, int IW,
-                                 int Cin, int N, int sh, int sw, void* out_nhwc, cudaStream_t stream) {
+                                 int Cin, int N, int sh, int sw, void* out_nhwc, int cin_mem, cudaStream_t stream) {
   KIRI_REQUIRE(in_nhwc && w && bias && out_nhwc, "kiri_conv3x3_bf16: null pointer");
-  return conv_call(in_nhwc, w, bias, n, IH, IW, Cin, N, sh, sw, out_nhwc, stream);
+  KIRI_REQUIRE(cin_mem >= 0 && cin_mem <= Cin, "kiri_conv3x3_bf16: cin_mem=%d must be in [0, Cin=%d]", cin_mem, Cin);
+  if (n == 0) return 0;
+  return launch_gemm_tc(conv_launch(in_nhwc, w, bias, n, IH, IW, Cin, N, sh, sw, out_nhwc, cin_mem == Cin ? 0 : cin_mem), stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -244,7 +235,7 @@ EncodeWs plan_encode(const KiriDims& d, const KiriGroup* groups, int n_groups, i
     const int sc = stem_sub_batch(B, Wb, stem_chunk);
     const size_t T = Wb / 4;
     w.sc[g] = sc;
-    w.g1[g] = a1; a1 += al(static_cast<size_t>(sc) * H * Wb * 64 * 2);
+    w.g1[g] = a1; a1 += al(static_cast<size_t>(sc) * H * Wb * 48 * 2);          // conv1 output: dense 48 channels
     w.g2[g] = a2; a2 += al(static_cast<size_t>(sc) * (H / 2) * (Wb / 2) * 96 * 2);
     w.g3[g] = a3; a3 += al(static_cast<size_t>(sc) * (H / 4) * (Wb / 4) * 160 * 2);
     w.g4[g] = a4; a4 += al(static_cast<size_t>(B) * (H / 8) * T * 256 * 2);
@@ -307,11 +298,6 @@ extern "C" int kiri_encode_multi(KiriHandle* h, const KiriGroup* groups, int n_g
   uint8_t* a = base + ws.a;
 
   KIRI_REQUIRE(n_groups <= 8, "kiri_encode_multi: at most 8 width groups");
-  // conv1 fused into conv2 (stem12_kernel) is correct and tested but measured SLOWER than the two
-  // kernels (0.99 vs 0.81 ms per 256 lines at 640 px): conv1 costs ~8.7 k cycles of CUDA-core work per
-  // 128-output tile even on 16 producer warps and cannot overlap anything but 1.3 k cycles of MMA,
-  // while the standalone conv1 runs at 64 warps/SM (profiles/README.md).  Opt-in for experiments.
-  static const bool no_stem12 = getenv("KIRI_STEM12") == nullptr;
   // ---- stem: the sub-batches of all groups advance together, and every conv layer runs as ONE launch over
   // the groups (per-group launches paid ~20 us each of prologue, tail and wave quantisation: 15 launches)
   int rounds = 0;
@@ -321,7 +307,6 @@ extern "C" int kiri_encode_multi(KiriHandle* h, const KiriGroup* groups, int n_g
     const uint8_t* c1_in[8];
     void* c1_out[8];
     int c1_lines[8], c1_W[8];
-    static const bool conv1_tc = getenv("KIRI_CONV1_TC") != nullptr;
     int np = 0;
     for (int g = 0; g < n_groups; ++g) {
       const int B = groups[g].n_lines, Wb = groups[g].Wb, T = Wb / 4;
@@ -333,26 +318,16 @@ extern "C" int kiri_encode_multi(KiriHandle* h, const KiriGroup* groups, int n_g
       uint8_t* a3 = base + ws.act3 + ws.g3[g];
       uint8_t* a4 = base + ws.act4 + ws.g4[g] + static_cast<size_t>(b0) * (H / 8) * T * 256 * 2;
       const uint8_t* planes = groups[g].planes + static_cast<size_t>(b0) * H * Wb;
-      if (w.conv2_w48 && !no_stem12) {
-        // layers 1+2 fused: the 48-channel activation never reaches HBM
-        ProfScope ps(PS_CONV2, stream);
-        KIRI_TRY(launch_stem12(planes, w.conv1_w_host, w.conv1_b_host, w.conv2_w48, w.conv2_b, nb, H, Wb, a2, stream));
-      } else if (conv1_tc) {
-        ProfScope ps(PS_CONV1, stream);
-        KIRI_TRY(kiri_conv1_tc(planes, w.conv1_w_host, w.conv1_b_host, nb, H, Wb, a1, stream));
-      }
       c1_in[np] = planes; c1_out[np] = a1; c1_lines[np] = nb; c1_W[np] = Wb;
-      L2[np] = conv_launch(a1, w.conv2_w, w.conv2_b, nb, H, Wb, 64, 96, 2, 2, a2);
+      L2[np] = conv_launch(a1, w.conv2_w, w.conv2_b, nb, H, Wb, 64, 96, 2, 2, a2, 48);     // K = 64 per tap, 48 stored
       L3[np] = conv_launch(a2, w.conv3_w, w.conv3_b, nb, H / 2, Wb / 2, 96, 160, 2, 2, a3);
       L4[np] = conv_launch(a3, w.conv4_w, w.conv4_b, nb, H / 4, Wb / 4, 160, 256, 2, 1, a4);
       ++np;
     }
     if (np == 0) continue;
-    if (!(w.conv2_w48 && !no_stem12) && !conv1_tc) {
-      ProfScope ps(PS_CONV1, stream);
-      KIRI_TRY(kiri_conv1_multi(c1_in, c1_out, c1_lines, c1_W, np, w.conv1_w_host, w.conv1_b_host, H, stream));
-    }
-    if (!(w.conv2_w48 && !no_stem12)) { ProfScope ps(PS_CONV2, stream); KIRI_TRY(launch_gemm_tc_multi(L2, np, stream)); }
+    { ProfScope ps(PS_CONV1, stream);
+      KIRI_TRY(kiri_conv1_multi(c1_in, c1_out, c1_lines, c1_W, np, w.conv1_w_host, w.conv1_b_host, H, stream)); }
+    { ProfScope ps(PS_CONV2, stream); KIRI_TRY(launch_gemm_tc_multi(L2, np, stream)); }
     { ProfScope ps(PS_CONV3, stream); KIRI_TRY(launch_gemm_tc_multi(L3, np, stream)); }
     { ProfScope ps(PS_CONV4, stream); KIRI_TRY(launch_gemm_tc_multi(L4, np, stream)); }
   }

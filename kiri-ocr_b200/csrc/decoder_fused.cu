@@ -66,7 +66,16 @@ struct FusedArgs {
   double* bm_score; int* bm_len; int* bm_state;       // [B, beam]
   int* bm_ids; float* bm_logp;                        // [B, beam, Lmax]
   int timing;                                         // 1: accumulate phase cycles into g_dec_prof
+  // live streaming: outputs may live in mapped host memory; every step is published with
+  // system-scope fences so that a host thread polling `progress` sees the step's ids / log-probs
+  int publish;                                        // 1: fence before the progress words
+  int* progress;                                      // nullable [B]: steps available | (1 << 30) once the line is done
+  int stream_rule;                                    // beam: 1 = beam_decode_streaming's rule (prune by score / L^lenp, stop
+                                                      //       when the best hypothesis ended, model.py:1112-1150)
+  int* bm_trace;                                      // nullable [B, Lmax, beam, 3]: per step and kept hypothesis (rank
+                                                      //       order): parent rank | appended token (-1 carried) | logp bits
 };
+static constexpr int kDoneBit = 1 << 30;
 
 // ---------------------------------------------------------------- weight packing
 // dst word ((nt*K/32 + kt)*32 + lane)*4 + wd  =  W[nt*8 + lane/4][kt*32 + wd*8 + (lane%4)*2 .. +1]
@@ -400,6 +409,7 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
 #pragma unroll
     for (int k = 0; k < 8; ++k) st->hist[i][k] = -1 - k;
     st->hist[i][0] = kTokBOS;
+    if (ok && rank == 0 && bi == 0 && A.progress) A.progress[b] = ms <= 0 ? kDoneBit : 0;
     if (!BM) {
       if (ok && rank == 0) { A.n_out[b] = 0; A.sum_logp[b] = 0.f; }
     } else {
@@ -716,10 +726,12 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
           if (done) st->finished[i] = 1;
           if (rank == 0) {
             A.ids[static_cast<size_t>(b) * A.Lmax + step] = bid;
-            A.n_out[b] = step + 1;
             A.sum_logp[b] += lp;
             if (A.step_logp) A.step_logp[static_cast<size_t>(b) * A.Lmax + step] = lp;
             if (A.step_prob) A.step_prob[static_cast<size_t>(b) * A.Lmax + step] = expf(dec[bid] - lse_d);
+            if (A.publish) __threadfence_system();                 // the step's records first, then the counters
+            A.n_out[b] = step + 1;
+            if (A.progress) A.progress[b] = (step + 1) | (done ? kDoneBit : 0);
           }
         }
         } else {
@@ -782,7 +794,8 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
           }
         }
         const int Ln = ntok_new - 1 > 1 ? ntok_new - 1 : 1;
-        const double pen = pow(5.0 + static_cast<double>(Ln), A.lenp) / pow(6.0, A.lenp);
+        const double pen = A.stream_rule ? pow(static_cast<double>(Ln), A.lenp)                      // model.py:1112-1115
+                                         : pow(5.0 + static_cast<double>(Ln), A.lenp) / pow(6.0, A.lenp);   // model.py:550-555
         const double normed = has ? sc / pen : -1e300;
         int rk = 0;
         for (int j = 0; j < n_cand; ++j) {
@@ -834,8 +847,21 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
             if (lane == 0 && tk >= 0) { q_dst[ol] = tk; l_dst[ol] = bs->new_v[ns]; }
           }
           all_done &= (bs->state[ns] == 2);
+          if (rank == 0 && A.bm_trace && lane == 0) {
+            int* tr = A.bm_trace + ((static_cast<size_t>(st->line[s0]) * A.Lmax + step) * BEAM + r) * 3;
+            tr[0] = sr - s0; tr[1] = tk; tr[2] = __float_as_int(bs->new_v[ns]);
+          }
         }
-        const bool ldone = all_done || (step + 1 >= st->max_steps[s0]);
+        if (rank == 0 && A.bm_trace && lane == 0)
+          for (int r = nb; r < BEAM; ++r) A.bm_trace[((static_cast<size_t>(st->line[s0]) * A.Lmax + step) * BEAM + r) * 3] = -1;
+        // batch beam search runs until every hypothesis ended (model.py:444-452); the streaming form stops as soon as
+        // the BEST one ended (model.py:1148-1150)
+        const bool best_done = A.stream_rule && nb > 0 && bs->state[s0] == 2;
+        const bool ldone = all_done || best_done || (step + 1 >= st->max_steps[s0]);
+        if (rank == 0 && A.progress && lane == 0) {
+          if (A.publish) __threadfence_system();
+          A.progress[st->line[s0]] = (step + 1) | (ldone ? kDoneBit : 0);
+        }
         __syncwarp();
         if (ldone) {
           if (lane == 0) bs->line_done[li] = 1;
@@ -991,7 +1017,7 @@ int fused_decoder_run(KiriHandle* h, const __nv_bfloat16* crosskv, int crosskv_l
                       int T, __nv_bfloat16* self_k, __nv_bfloat16* self_v, const int* len_est, const int* forced,
                       const int* line_perm, int B, int Lmax, const KiriDecodeParams* p, int* ids, int* n_out,
                       float* sum_logp, float* step_logp, float* step_prob, int* steps_max_dev, int cluster_size,
-                      cudaStream_t stream, const FusedBeam* beam, int kv_headmajor) {
+                      cudaStream_t stream, const FusedBeam* beam, int kv_headmajor, const FusedLive* live) {
   FusedPacked* fp = reinterpret_cast<FusedPacked*>(h->fused);
   KIRI_REQUIRE(fp, "fused decoder: handle was created without decoder weights");
   FusedArgs a = fp->args;
@@ -1001,6 +1027,8 @@ int fused_decoder_run(KiriHandle* h, const __nv_bfloat16* crosskv, int crosskv_l
   a.steps_max = steps_max_dev;
   a.timing = getenv("KIRI_DEC_TIMING") != nullptr;
   a.beam = 1; a.bmode = 0; a.lenp = 0.0;
+  a.publish = 0; a.progress = nullptr; a.stream_rule = 0; a.bm_trace = nullptr;
+  if (live) { a.publish = live->publish; a.progress = live->progress; a.stream_rule = live->stream_rule; a.bm_trace = live->bm_trace; }
   if (beam) {
     a.bmode = 1;
     KIRI_REQUIRE(beam->beam >= 1 && beam->beam <= 5, "fused decoder: beam width %d not in 1..5", beam->beam);

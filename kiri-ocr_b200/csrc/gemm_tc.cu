@@ -719,9 +719,15 @@ static int prep_problem(const GemmLaunch& L, bool is_gemm, int KC, bool a_multi,
   {
     // (cKC, W, H, chunk, image): the chunk dimension has the SMALLEST stride but sits after W / H, so a box of
     // CPS chunks lands as [chunk][pixel][KC*2 B] = CPS consecutive operand tiles
-    cuuint64_t dims[5] = {(cuuint64_t)KC, (cuuint64_t)L.IW, (cuuint64_t)L.IH, (cuuint64_t)chunks, (cuuint64_t)L.NB};
-    cuuint64_t str[4] = {(cuuint64_t)L.Cin * 2, (cuuint64_t)L.IW * L.Cin * 2, (cuuint64_t)KC * 2,
-                         (cuuint64_t)L.IH * L.IW * L.Cin * 2};
+    // Cm = channels stored per pixel.  Cm < Cin (conv2 on conv1's dense 48 channels, K padded to 64): the inner
+    // EXTENT is Cm while the box stays KC wide, so the TMA unit zero-fills channels Cm..KC-1 of every row in shared
+    // memory (out-of-bounds elements of a tiled box read as zero) - the padding never exists in HBM
+    const int Cm = L.Cin_mem > 0 ? L.Cin_mem : L.Cin;
+    KIRI_REQUIRE(Cm == L.Cin || (chunks == 1 && Cm < L.Cin && (Cm * 2) % 16 == 0),
+                 "gemm_tc: %d stored channels for Cin=%d needs a single K chunk per tap and a 16-byte pixel pitch", Cm, L.Cin);
+    cuuint64_t dims[5] = {(cuuint64_t)(Cm < KC ? Cm : KC), (cuuint64_t)L.IW, (cuuint64_t)L.IH, (cuuint64_t)chunks, (cuuint64_t)L.NB};
+    cuuint64_t str[4] = {(cuuint64_t)Cm * 2, (cuuint64_t)L.IW * Cm * 2, (cuuint64_t)KC * 2,
+                         (cuuint64_t)L.IH * L.IW * Cm * 2};
     cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)(g.SEG * g.sw), (cuuint32_t)(g.R * g.sh), (cuuint32_t)(a_multi ? CPS : 1), 1};
     cuuint32_t es[5] = {1, (cuuint32_t)g.sw, (cuuint32_t)g.sh, 1, 1};
     if (encode_map(tmA, L.a, 5, dims, str, box, es, swz)) return -1;
@@ -747,7 +753,7 @@ int launch_gemm_tc_multi(const GemmLaunch* Ls, int n, cudaStream_t stream) {
   for (int i = 0; i < n; ++i) {
     const GemmLaunch& Q = Ls[i];
     KIRI_REQUIRE(Q.e.bias != nullptr && Q.e.out != nullptr && Q.a != nullptr, "gemm_tc: a/bias/out must not be null");
-    KIRI_REQUIRE(Q.w == L.w && Q.e.bias == L.e.bias && Q.N == L.N && Q.Cin == L.Cin && Q.epi == L.epi && Q.kw == L.kw &&
+    KIRI_REQUIRE(Q.w == L.w && Q.e.bias == L.e.bias && Q.N == L.N && Q.Cin == L.Cin && Q.Cin_mem == L.Cin_mem && Q.epi == L.epi && Q.kw == L.kw &&
                      Q.kh == L.kh && Q.sw == L.sw && Q.sh == L.sh && Q.pad == L.pad && Q.e.ldc == L.e.ldc,
                  "gemm_tc: problem %d is not the same layer as problem 0", i);
   }
@@ -839,267 +845,6 @@ int launch_gemm_tc_multi(const GemmLaunch* Ls, int n, cudaStream_t stream) {
   return 0;
 }
 
-
-// ================================================================================================
-// stem12: conv1 (1->48, CUDA cores) fused into conv2's (48->96, stride 2) tcgen05 implicit GEMM.
-//
-// Replaces ConvStem.net[0:6] (kiri_ocr/model.py:215-220).  The unfused pair writes a 64-channel bf16
-// activation of 3.9 MB per line to HBM and conv2 reads it back nine times (once per tap) through L2:
-// 41 % of the stem's L2 bytes (profiles/README.md).  Here a CTA owns 2 x 64 conv2 outputs; its 8
-// producer warps compute the 5 x 129 conv1 pixels the tile needs straight from the uint8 plane
-// (same fp32 arithmetic as conv1_bn_silu_kernel) and scatter them, already in bf16, into the im2col
-// A operand in shared memory: 27 K-major tiles [128 rows x 16 channels] with the 32-byte swizzle
-// (tap-major, three channel thirds per tap; a conv1 pixel lands in 1, 2 or 4 tiles because of the
-// stride-2 overlap).  conv2's weights (83 KB) stay resident in shared memory.  The same 8 warps
-// drain the previous tile's accumulator (bias + SiLU -> bf16 -> TMA store) while the MMAs of the
-// current tile run.
-static constexpr int kS12KT = 27;                    // k16 steps: 9 taps x 3 channel thirds
-static constexpr int kS12ATile = 128 * 32;           // bytes of one A k-tile
-static constexpr int kS12BTile = 96 * 32;            // bytes of one B k-tile
-static constexpr int kS12Prod = 512;                 // producer threads (warps 0-15; warps 0-7 also drain)
-static constexpr int kS12Threads = kS12Prod + 64;    // + warp 16 weights, warp 17 MMA
-constexpr uint64_t UMMA_LAYOUT_SW32 = 6;
-
-struct S12Params { float w[48 * 9]; float b[48]; };
-struct __align__(16) S12Bars {
-  uint64_t a_full, a_empty, b_full, tmem_full[2], tmem_empty[2];
-  uint32_t tmem_base;
-  uint32_t pad[3];
-  float bias[128];
-  float patch[7 * 132];              // normalised plane pixels the tile's conv1 needs (0 outside the plane)
-};
-
-// 16 conv1 output channels [THIRD*16, +16) of one pixel.  THIRD is a template parameter so that every
-// weight is a compile-time offset into the kernel-parameter (constant) bank: the FFMAs read their
-// weight operand directly; a run-time third costs one LDC per FMA.
-template <int THIRD>
-__device__ __forceinline__ void conv1_third(const float (&in)[9], const S12Params& p, uint32_t (&packed)[8]) {
-#pragma unroll
-  for (int c = 0; c < 16; c += 2) {
-    float a0 = p.b[THIRD * 16 + c], a1 = p.b[THIRD * 16 + c + 1];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      a0 = fmaf(in[k], p.w[(THIRD * 16 + c) * 9 + k], a0);
-      a1 = fmaf(in[k], p.w[(THIRD * 16 + c + 1) * 9 + k], a1);
-    }
-    packed[c / 2] = pack_bf16x2(silu_fast(a0), silu_fast(a1));
-  }
-}
-
-__global__ void __launch_bounds__(kS12Threads, 1)
-stem12_kernel(const uint8_t* __restrict__ planes, const __grid_constant__ CUtensorMap tmB,
-              const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ S12Params p,
-              const float* __restrict__ bias2, const int H, const int W, const int total_tiles, const int timing_on) {
-  const bool timing = timing_on != 0 && blockIdx.x == 0 && threadIdx.x == 0;     // producer thread 0 of CTA 0
-  long long tq = 0, acc_we = 0, acc_st = 0, acc_cp = 0, acc_dr = 0;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* sA = smem;
-  uint8_t* sB = sA + kS12KT * kS12ATile;
-  uint8_t* staging = sB + kS12KT * kS12BTile;        // one 4 KB tile per producer/epilogue warp
-  S12Bars* bars = reinterpret_cast<S12Bars*>(staging + 8 * kBufBytes);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
-  const int OW = W / 2, tiles_x = W / 128, tiles_per_img = (H / 4) * tiles_x;
-
-  if (tid == kS12Prod) {
-    mbar_init(&bars->a_full, kS12Prod);
-    mbar_init(&bars->a_empty, 1);
-    mbar_init(&bars->b_full, 1);
-    for (int a = 0; a < 2; ++a) { mbar_init(&bars->tmem_full[a], 1); mbar_init(&bars->tmem_empty[a], 8); }
-    fence_mbar_init();
-    tma_prefetch_desc(&tmB);
-    tma_prefetch_desc(&tmOut);
-  }
-  if (warp == kS12Prod / 32 + 1) { tmem_alloc(&bars->tmem_base, 256); tmem_relinquish(); }
-  if (tid < 128) bars->bias[tid] = tid < 96 ? __ldg(bias2 + tid) : 0.f;
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = bars->tmem_base;
-  pdl_trigger();
-  pdl_wait();                                        // the planes come from the preprocess kernel
-
-  // epilogue of one finished tile (producer warps): bias + SiLU -> bf16 -> swizzled staging -> TMA store
-  auto drain = [&](int tile, int it) {
-    const int q = warp & 3, half = warp >> 2;        // TMEM lane quarter, 64-column chunk
-    const int acc = it & 1;
-    const int img = tile / tiles_per_img, rem = tile - img * tiles_per_img;
-    const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
-    const int m0 = q * 32;
-    const int row0 = (img * (H / 2) + 2 * ty + (m0 >> 6)) * OW + 64 * tx + (m0 & 63);
-    mbar_wait(&bars->tmem_full[acc], (it >> 1) & 1);
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 128 + half * 64;
-    uint32_t ra[32], rb2[32];
-    tmem_ld32(taddr, ra);
-    tmem_ld32(taddr + 32, rb2);                      // half 1: columns 96..127 are not part of N = 96 (store clips)
-    tmem_ld_wait();
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
-    uint8_t* ob = staging + warp * kBufBytes;
-    if (lane == 0) bulk_wait_group_read<0>();
-    __syncwarp();
-    const float* sbias = bars->bias + half * 64;
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      const uint32_t* src = (t < 4) ? ra : rb2;
-      const int o8 = (t & 3) * 8;
-      float y[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) y[u] = silu_fast(__uint_as_float(src[o8 + u]) + sbias[t * 8 + u]);
-      uint4 pk;
-      pk.x = pack_bf16x2(y[0], y[1]); pk.y = pack_bf16x2(y[2], y[3]);
-      pk.z = pack_bf16x2(y[4], y[5]); pk.w = pack_bf16x2(y[6], y[7]);
-      *reinterpret_cast<uint4*>(ob + stg_off(lane, t)) = pk;
-    }
-    fence_proxy_async();
-    __syncwarp();
-    if (lane == 0) {
-      tma_store_2d(&tmOut, ob, half * 64, row0);
-      bulk_commit_group();
-    }
-  };
-
-  if (warp < kS12Prod / 32) {
-    // ============================ producers (conv1) + epilogue ============================
-    int it = 0, prev_tile = -1;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int img = tile / tiles_per_img, rem = tile - img * tiles_per_img;
-      const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
-      const uint8_t* plane = planes + static_cast<size_t>(img) * H * W;
-      // a_empty also means every producer has finished reading the previous patch
-      if (timing) tq = clock64();
-      if (it > 0) mbar_wait(&bars->a_empty, (it - 1) & 1);      // the previous tile's MMAs have read A
-      GT_ACC(acc_we, tq);
-      for (int idx = tid; idx < 7 * 131; idx += kS12Prod) {
-        const int r7 = idx / 131, c = idx - r7 * 131;
-        const int yy = 4 * ty - 2 + r7, xx = 128 * tx - 2 + c;
-        const bool ok = (yy >= 0) && (yy < H) && (xx >= 0) && (xx < W);
-        // the reference's normalisation (model.py:337-338) in the same fp32 operation order; 0 = conv1 padding
-        bars->patch[r7 * 132 + c] =
-            ok ? __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(plane[yy * W + xx]), 255.0f), 0.5f), 0.5f) : 0.0f;
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(kS12Prod) : "memory");
-      GT_ACC(acc_st, tq);
-      // work item = (channel third, conv1 pixel): consecutive lanes take consecutive pixels of one
-      // third, so a warp's 16-byte scatter stores spread over all bank groups
-      for (int item = tid; item < 3 * 5 * 129; item += kS12Prod) {
-        const int third = item / (5 * 129), pidx = item - third * (5 * 129);
-        const int py = pidx / 129, px = pidx - py * 129;
-        const int y1 = 4 * ty - 1 + py, x1 = 128 * tx - 1 + px;
-        uint32_t packed[8];
-        if (y1 >= 0 && y1 < H && x1 >= 0 && x1 < W) {
-          float in[9];
-#pragma unroll
-          for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) in[ky * 3 + kx] = bars->patch[(py + ky) * 132 + px + kx];
-          if (third == 0) conv1_third<0>(in, p, packed);
-          else if (third == 1) conv1_third<1>(in, p, packed);
-          else conv1_third<2>(in, p, packed);
-        } else {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) packed[c] = 0u;           // conv2's zero padding
-        }
-        // scatter into the taps that read this conv1 pixel: 2*r + ky = py, 2*i + kx = px
-        const int a = px >> 1;
-        for (int vy = 0; vy < 2; ++vy) {
-          int ky, r;
-          if (vy == 0) { ky = (py & 1) ? 1 : (py == 0 ? 0 : 2); r = (py - ky) >> 1; }
-          else { if (py != 2) break; ky = 0; r = 1; }
-          for (int vx = 0; vx < 2; ++vx) {
-            int kx, i;
-            if (px & 1) { if (vx) break; kx = 1; i = a; }
-            else if (vx == 0) { kx = 0; i = a; if (i > 63) continue; }
-            else { kx = 2; i = a - 1; if (i < 0) break; }
-            const int m = r * 64 + i, tap = ky * 3 + kx;
-            uint8_t* dst = sA + (tap * 3 + third) * kS12ATile + m * 32;
-            const int sw = (m >> 2) & 1;
-            *reinterpret_cast<uint4*>(dst + (sw << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-            *reinterpret_cast<uint4*>(dst + ((sw ^ 1) << 4)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-          }
-        }
-      }
-      fence_proxy_async();
-      mbar_arrive(&bars->a_full);
-      GT_ACC(acc_cp, tq);
-      if (warp < 8 && it > 0) drain(prev_tile, it - 1);
-      GT_ACC(acc_dr, tq);
-      prev_tile = tile;
-    }
-    if (timing) {
-      g_gemm_prof[10] += acc_we; g_gemm_prof[11] += acc_st; g_gemm_prof[12] += acc_cp; g_gemm_prof[13] += acc_dr;
-      g_gemm_prof[15] += it;
-    }
-    if (warp < 8 && it > 0) drain(prev_tile, it - 1);
-    if (warp < 8 && lane == 0) bulk_wait_group<0>();
-  } else if (warp == kS12Prod / 32) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(&bars->b_full, kS12KT * kS12BTile);
-      for (int kt = 0; kt < kS12KT; ++kt) tma_load_3d(sB + kt * kS12BTile, &tmB, &bars->b_full, 0, kt, 0);
-    }
-  } else {
-    // ============================ MMA issuer ============================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(kTileM, 96);
-      const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
-      mbar_wait(&bars->b_full, 0);
-      int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        mbar_wait(&bars->tmem_empty[acc], ((it >> 1) & 1) ^ 1);
-        mbar_wait(&bars->a_full, it & 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * 128;
-        for (int kt = 0; kt < kS12KT; ++kt) {
-          const uint64_t ad = umma_desc_kmajor(a_addr + kt * kS12ATile, 256, UMMA_LAYOUT_SW32);
-          const uint64_t bd = umma_desc_kmajor(b_addr + kt * kS12BTile, 256, UMMA_LAYOUT_SW32);
-          umma_bf16(d_tmem, ad, bd, idesc, kt != 0 ? 1u : 0u);
-        }
-        umma_commit(&bars->a_empty);
-        umma_commit(&bars->tmem_full[acc]);
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == kS12Prod / 32 + 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
-}
-
-// planes: uint8 [n, H, W]; w48: bf16 [96, 9*48] ordered (ky, kx, cin); out: NHWC bf16 [n, H/2, W/2, 96]
-int launch_stem12(const uint8_t* planes, const float* conv1_w_host, const float* conv1_b_host, const void* w48,
-                  const float* bias2, int n, int H, int W, void* out, cudaStream_t stream) {
-  gemm_tc_num_sms();
-  KIRI_REQUIRE(planes && conv1_w_host && conv1_b_host && w48 && bias2 && out, "stem12: null pointer");
-  KIRI_REQUIRE(H % 4 == 0 && W % 128 == 0, "stem12: plane %dx%d must be a multiple of 4 x 128", H, W);
-  if (n == 0) return 0;
-  CUtensorMap tmB, tmOut;
-  {
-    cuuint64_t dims[3] = {16, 27, 96};
-    cuuint64_t str[2] = {32, 27 * 32};
-    cuuint32_t box[3] = {16, 1, 96};
-    cuuint32_t es[3] = {1, 1, 1};
-    if (encode_map(&tmB, w48, 3, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_32B)) return -1;
-  }
-  const long long rows_total = static_cast<long long>(n) * (H / 2) * (W / 2);
-  if (encode_rowtile_map(&tmOut, out, rows_total, 96, 96, false)) return -1;
-  S12Params prm;
-  for (int i = 0; i < 48 * 9; ++i) prm.w[i] = conv1_w_host[i];
-  for (int i = 0; i < 48; ++i) prm.b[i] = conv1_b_host[i];
-  const int smem = 1024 + kS12KT * (kS12ATile + kS12BTile) + 8 * kBufBytes + (int)sizeof(S12Bars);
-  static bool configured = false;
-  if (!configured) {
-    KIRI_CHECK_CUDA(cudaFuncSetAttribute(stem12_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
-  const int total_tiles = n * (H / 4) * (W / 128);
-  const int grid = total_tiles < g_num_sms ? total_tiles : g_num_sms;
-  static const int timing_on = getenv("KIRI_GEMM_TIMING") != nullptr;
-  KIRI_CHECK_CUDA(launch_pdl(stem12_kernel, dim3(grid), dim3(kS12Threads), smem, stream, planes, tmB, tmOut, prm, bias2, H, W,
-                             total_tiles, timing_on));
-  return 0;
-}
 
 }  // namespace kiri
 

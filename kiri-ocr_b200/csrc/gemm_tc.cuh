@@ -59,7 +59,8 @@ struct EpiParams {
 struct GemmLaunch {
   const void* a;       // bf16 activations
   const void* w;       // bf16 weights [N, taps*Cin]
-  int NB, IH, IW, Cin; // input geometry
+  int NB, IH, IW, Cin; // input geometry (Cin = channels per tap in the weight matrix)
+  int Cin_mem;         // channels stored per pixel (0 = Cin); < Cin: the TMA box zero-fills the rest (one chunk per tap only)
   int OH, OW;          // output geometry
   int sw, sh, pad, kw, kh;
   int N;               // output channels
@@ -78,9 +79,6 @@ struct ProblemSet {              // grid-constant kernel parameter
   int mtile_begin[kMaxProblems + 1];
   int n;
 };
-// conv1 fused into conv2 (gemm_tc.cu, stem12_kernel)
-int launch_stem12(const uint8_t* planes, const float* conv1_w_host, const float* conv1_b_host, const void* w48,
-                  const float* bias2, int n, int H, int W, void* out, cudaStream_t stream);
 int gemm_tc_num_sms();
 int gemm_tc_max_smem();
 

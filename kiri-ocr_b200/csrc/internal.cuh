@@ -34,6 +34,9 @@ struct FusedBeam {           // beam-search mode of the fused decoder (nullptr =
   int* seqbuf; float* lpbuf; // [2][n_slots][Lmax] scratch, n_slots = fused_decoder_slots(B, beam)
   double* score; int* len; int* state; int* ids; float* logp;   // outputs [B, beam(, Lmax)]
 };
+struct FusedLive {           // live publication of decode steps / the streaming beam rule (nullptr = none)
+  int publish; int* progress; int stream_rule; int* bm_trace;
+};
 inline int fused_decoder_slots(int B, int beam) { const int lpc = 16 / beam; return (B + lpc - 1) / lpc * 16; }
 int fused_decoder_build(KiriHandle* h);
 void fused_decoder_free(KiriHandle* h);
@@ -41,7 +44,8 @@ int fused_decoder_run(KiriHandle* h, const __nv_bfloat16* crosskv, int crosskv_l
                       int T, __nv_bfloat16* self_k, __nv_bfloat16* self_v, const int* len_est, const int* forced,
                       const int* line_perm, int B, int Lmax, const KiriDecodeParams* p, int* ids, int* n_out,
                       float* sum_logp, float* step_logp, float* step_prob, int* steps_max_dev, int cluster_size,
-                      cudaStream_t stream, const FusedBeam* beam = nullptr, int kv_headmajor = 0);
+                      cudaStream_t stream, const FusedBeam* beam = nullptr, int kv_headmajor = 0,
+                      const FusedLive* live = nullptr);
 // token-major cross K/V [M, ld] -> per-line head-major blocks [layer][K|V][head][t][32]
 int crosskv_headmajor(const __nv_bfloat16* src, __nv_bfloat16* dst, int ld, const int* mem_row0, const int* mem_len,
                       int T_uniform, int max_T, int n_lines, cudaStream_t stream);

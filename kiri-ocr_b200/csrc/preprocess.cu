@@ -255,9 +255,52 @@ preprocess_pack_kernel(const uint8_t* __restrict__ src, const KiriCropDesc* __re
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Page ingest: BGR -> gray on the device, bit-exact with cv2.cvtColor(img, COLOR_BGR2GRAY) on uint8 (core.py:762-766).
+// OpenCV (imgproc/src/color_rgb.simd.hpp, RGB2Gray<uchar>; opencv-python is a third-party dependency of the reference,
+// 4.13.0 here) computes   gray = (B*3735 + G*19235 + R*9798 + (1 << 14)) >> 15   - 15-bit fixed-point BT.601 weights.
+// One thread = 4 pixels: three 32-bit loads (12 bytes of BGR), one 32-bit store.  HBM-bound: 3 B in + 1 B out per pixel.
+__global__ void __launch_bounds__(256)
+bgr_to_gray_kernel(const uint32_t* __restrict__ bgr, uint32_t* __restrict__ gray, long long n_quads, const uint8_t* bgr_tail,
+                   uint8_t* gray_tail, int tail_pixels) {
+  pdl_trigger();
+  pdl_wait();
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i < n_quads) {
+    const uint32_t w0 = __ldg(bgr + 3 * i), w1 = __ldg(bgr + 3 * i + 1), w2 = __ldg(bgr + 3 * i + 2);
+    // bytes: w0 = B0 G0 R0 B1 | w1 = G1 R1 B2 G2 | w2 = R2 B3 G3 R3  (little endian)
+    auto y = [](uint32_t b, uint32_t g, uint32_t r) { return (b * 3735u + g * 19235u + r * 9798u + 16384u) >> 15; };
+    const uint32_t p0 = y(w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u);
+    const uint32_t p1 = y(w0 >> 24, w1 & 255u, (w1 >> 8) & 255u);
+    const uint32_t p2 = y((w1 >> 16) & 255u, w1 >> 24, w2 & 255u);
+    const uint32_t p3 = y((w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24);
+    gray[i] = p0 | (p1 << 8) | (p2 << 16) | (p3 << 24);
+  }
+  if (i == 0) {
+    for (int t = 0; t < tail_pixels; ++t)
+      gray_tail[t] = static_cast<uint8_t>((bgr_tail[3 * t] * 3735u + bgr_tail[3 * t + 1] * 19235u + bgr_tail[3 * t + 2] * 9798u + 16384u) >> 15);
+  }
+}
+
 }  // namespace kiri
 
 using namespace kiri;
+
+extern "C" int kiri_bgr_to_gray(const uint8_t* bgr_u8, long long n_pixels, uint8_t* gray_u8, cudaStream_t stream) {
+  KIRI_REQUIRE(bgr_u8 && gray_u8, "kiri_bgr_to_gray: null pointer");
+  KIRI_REQUIRE(n_pixels >= 0, "kiri_bgr_to_gray: negative size");
+  KIRI_REQUIRE((reinterpret_cast<uintptr_t>(bgr_u8) & 3) == 0 && (reinterpret_cast<uintptr_t>(gray_u8) & 3) == 0,
+               "kiri_bgr_to_gray: buffers must be 4-byte aligned");
+  if (n_pixels == 0) return 0;
+  const long long quads = n_pixels / 4;
+  const int tail = static_cast<int>(n_pixels - quads * 4);
+  const long long blocks = (quads + 255) / 256;
+  KIRI_REQUIRE(blocks < 0x7fffffffll, "kiri_bgr_to_gray: image too large");
+  KIRI_CHECK_CUDA(launch_pdl(bgr_to_gray_kernel, dim3(static_cast<unsigned>(blocks > 0 ? blocks : 1)), dim3(256), 0, stream,
+                             reinterpret_cast<const uint32_t*>(bgr_u8), reinterpret_cast<uint32_t*>(gray_u8), quads,
+                             bgr_u8 + quads * 12, gray_u8 + quads * 4, tail));
+  return 0;
+}
 
 extern "C" int kiri_preprocess_smem_bytes(int w, int h, int nw, int img_h, int Wb, int strip_w) {
   const int Wout = nw < Wb ? nw : Wb;

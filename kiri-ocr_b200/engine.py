@@ -49,6 +49,17 @@ class LineResult:
     len_est: int = 0                # CTC length estimate that bounds the decoder (model.py:416-425)
 
 
+class _Raw:
+    """A raw (device-visible) address standing in for a tensor in the low-level calls."""
+    __slots__ = ("p",)
+
+    def __init__(self, p: int):
+        self.p = p
+
+    def data_ptr(self) -> int:
+        return self.p
+
+
 class LineError:
     """A region that could not be recognised (malformed box, per-line failure): the document loops drop it or
     report it as an ``error`` result / chunk like the reference's per-region ``try/except``
@@ -343,8 +354,11 @@ class BatchedRecognizer:
 
     def decode_greedy_multi(self, mem_bf16: torch.Tensor, mem_row0: torch.Tensor, mem_len: torch.Tensor,
                             len_est: torch.Tensor, Lmax: int, max_T: int, select_raw: bool = False,
-                            forced: Optional[torch.Tensor] = None, want_steps: bool = False, out=None):
-        """One persistent decode over every line of every group (concatenated token stream)."""
+                            forced: Optional[torch.Tensor] = None, want_steps: bool = False, out=None,
+                            progress_ptr: int = 0, publish: bool = False):
+        """One persistent decode over every line of every group (concatenated token stream).  ``out`` tensors (or
+        raw addresses, for mapped pinned host memory) receive the results; ``progress_ptr`` / ``publish``: see
+        kiri_decode_greedy_multi (live streaming)."""
         p = self.decode_params(select_raw)
         B, M = int(len_est.numel()), int(mem_bf16.shape[0])
         need = self.lib.kiri_decode_multi_workspace_bytes(self.handle, B, M, Lmax)
@@ -364,7 +378,8 @@ class BatchedRecognizer:
                                                      C.byref(p),
                                                      ws.data_ptr(), need, ids.data_ptr(), n_out.data_ptr(),
                                                      sum_lp.data_ptr(), _lib.ptr(slp), _lib.ptr(spr), _lib.ptr(forced),
-                                                     None, _lib.stream_ptr()), "kiri_decode_greedy_multi")
+                                                     None, progress_ptr, int(publish), _lib.stream_ptr()),
+                   "kiri_decode_greedy_multi")
         self.launches += 2          # cross-K/V GEMM + the persistent decode kernel
         return ids, n_out, sum_lp, slp, spr
 
@@ -506,9 +521,14 @@ class BatchedRecognizer:
         max_steps from its device-resident length estimate and clusters exit as soon as their lines are done."""
         return self.max_steps_bound(T_max, T_max)
 
-    def _stage_host(self, arrays: Sequence[np.ndarray], slot: int) -> torch.Tensor:
-        """Concatenate host arrays into the slot's PERSISTENT pinned buffer (no per-call cudaHostAlloc)."""
-        total = int(sum(a.size for a in arrays))
+    def _stage_host(self, arrays: Sequence[np.ndarray], slot: int, align: int = 1):
+        """Concatenate host arrays into the slot's PERSISTENT pinned buffer (no per-call cudaHostAlloc); with
+        ``align`` > 1 every array starts at a multiple of it.  Returns (buffer view, start offset of every array)."""
+        offs, total = [], 0
+        for a in arrays:
+            total = -(-total // align) * align
+            offs.append(total)
+            total += int(a.size)
         name = f"_hsrc_{slot}"
         cur = getattr(self, name, None)
         if cur is None or cur.numel() < total + 16:
@@ -517,16 +537,15 @@ class BatchedRecognizer:
         elif self._h2d_done[slot] is not None:
             self._h2d_done[slot].synchronize()              # the upload that last read this buffer has finished
         nb = cur.numpy()
-        off = 0
-        for a in arrays:
+        for a, off in zip(arrays, offs):
             if a.dtype != np.uint8:
                 raise ValueError("source arrays must be uint8")
             nb[off:off + a.size] = a.reshape(-1)
-            off += a.size
-        return cur[:total + 16]
+        return cur[:total + 16], offs
 
     @torch.no_grad()
-    def submit(self, src, entries: np.ndarray, method: str = "ctc", streaming: bool = False):
+    def submit(self, src, entries: np.ndarray, method: str = "ctc", streaming: bool = False, bgr_pages=None,
+               live: bool = False):
         """Enqueue one batch (H2D of the source on the copy stream, preprocess, encoder, CTC greedy, for "decoder"
         the whole greedy decode, async D2H of the packed results) and return a ticket without synchronising the
         host.  Two tickets may be in flight: ``t2 = submit(...); r1 = collect(t1)`` overlaps batch i's host-side
@@ -542,16 +561,17 @@ class BatchedRecognizer:
         if caller != self.stream:
             self.stream.wait_stream(caller)
             with torch.cuda.stream(self.stream):
-                return self.submit(src, entries, method, streaming)
+                return self.submit(src, entries, method, streaming, bgr_pages, live)
         n = len(entries)
-        tk = {"method": method, "streaming": streaming, "n": n}
+        live = live and method in ("decoder", "beam")
+        tk = {"method": method, "streaming": streaming, "n": n, "live": live}
         if n == 0:
             return tk
         marks = [_time.perf_counter()]                       # host-side phase marks of this call (tk["marks"])
         self._slot ^= 1
         slot, sl = self._slot, f"_{self._slot}"
         if isinstance(src, (list, tuple)):
-            src = self._stage_host(src, slot)
+            src, _ = self._stage_host(src, slot)
         if src.is_cuda:
             src_dev = src
         else:
@@ -568,6 +588,21 @@ class BatchedRecognizer:
                 src_dev[:src.numel()].copy_(src, non_blocking=True)
                 self._h2d_done[slot] = torch.cuda.Event()
                 self._h2d_done[slot].record()
+        if bgr_pages:
+            # GPU-side page ingest: `src` holds raw pages, some of them interleaved BGR; the
+            # gray pages the crops are cut from are produced on the device (cv2-exact kernel), entries address them
+            total_gray = max(g + n_px for _, g, n_px, _ in bgr_pages)
+            gsrc = self._device("_gsrc" + sl, total_gray + 16, torch.uint8)
+            if not src.is_cuda:
+                self.stream.wait_stream(self._copy_stream)
+            for raw_off, gray_off, n_px, is_bgr in bgr_pages:
+                if is_bgr:
+                    _lib.check(self.lib.kiri_bgr_to_gray(src_dev.data_ptr() + raw_off, n_px, gsrc.data_ptr() + gray_off,
+                                                         _lib.stream_ptr()), "kiri_bgr_to_gray")
+                    self.launches += 1
+                else:
+                    gsrc[gray_off:gray_off + n_px].copy_(src_dev[raw_off:raw_off + n_px], non_blocking=True)
+            src_dev = gsrc
         marks.append(_time.perf_counter())                   # [1] upload enqueued
         groups = list(self.plan(entries).items())
         marks.append(_time.perf_counter())                   # [2] planned
@@ -619,9 +654,9 @@ class BatchedRecognizer:
         # ---- CTC greedy into ONE packed result buffer: ids[M] | n_ids[L] | conf[L] | frames | decoder block
         want_frames = streaming and method == "ctc"
         T_max = max(T for _, _, T in enc["rows"])
-        Lcap = self.static_step_cap(T_max) if method == "decoder" else 0
+        Lcap = self.static_step_cap(T_max) if (method == "decoder" or live) else 0
         LL = n_lines * Lcap
-        dec_words = (3 * LL if streaming else 2 * LL) + 2 * n_lines if method == "decoder" else 0
+        dec_words = (3 * LL if streaming else 2 * LL) + 2 * n_lines if (method == "decoder" and not live) else 0
         ctc_words = M + 2 * n_lines + (2 * M if want_frames else 0)
         res_words = ctc_words + dec_words
         dres = self._device("_dres" + sl, res_words, torch.int32)
@@ -636,7 +671,9 @@ class BatchedRecognizer:
                    "kiri_ctc_greedy_multi")
         self.launches += 1
         mem_row0, mem_len = dmeta[r0o:r0o + n_lines], dmeta[mlo:mlo + n_lines]
-        if method == "decoder":
+        if live:
+            tk["live_out"] = self._launch_live(tk, enc, mem_row0, mem_len, n_all, n_lines, Lcap, T_max, method, sl)
+        elif method == "decoder":
             # the greedy decode is enqueued right behind the CTC kernel: its step bounds come from the device-resident
             # length estimates, so no host round trip separates the encoder from the decoder
             dd = dres[ctc_words:]
@@ -722,6 +759,113 @@ class BatchedRecognizer:
                                      len_est=int(len_h[j]))
         return results
 
+    # ------------------------------------------------------------------ live streaming
+    def _launch_live(self, tk, enc, mem_row0, mem_len, len_est, n_lines, Lcap, T_max, method, sl):
+        """Enqueue the decode with its outputs in MAPPED PINNED HOST memory and per-step publication: the host reads
+        tokens while the persistent kernel is still decoding (later regions decode ahead of the one being read)."""
+        LL = n_lines * Lcap
+        if method == "decoder":
+            words = 3 * LL + 3 * n_lines                     # ids | step_logp | step_prob | n_out | sum_lp | progress
+        else:
+            beam = int(self.cfg.BEAM)
+            if not 1 <= beam <= 5:
+                raise ValueError(f"cfg.BEAM={beam}: the B200 beam decoder supports widths 1..5")
+            words = 3 * LL * beam + n_lines                  # trace [n, Lcap, beam, 3] | progress
+        h = self._pinned("_hlive" + sl, words, torch.int32)
+        hv = h.numpy()
+        base = h.data_ptr()                                  # UVA: the device writes through the same address
+        if method == "decoder":
+            po = 3 * LL + 2 * n_lines
+            hv[po:po + n_lines] = 0
+            out = (_Raw(base), _Raw(base + 4 * (3 * LL)), _Raw(base + 4 * (3 * LL + n_lines)), _Raw(base + 4 * LL), _Raw(base + 8 * LL))
+            self.decode_greedy_multi(enc["mem_bf16"], mem_row0, mem_len, len_est, Lcap, T_max, select_raw=True, out=out,
+                                     progress_ptr=base + 4 * po, publish=True)
+            return {"ids": hv[:LL].reshape(n_lines, Lcap), "logp": hv[LL:2 * LL].view(np.float32).reshape(n_lines, Lcap),
+                    "prob": hv[2 * LL:3 * LL].view(np.float32).reshape(n_lines, Lcap), "progress": hv[po:po + n_lines]}
+        po = 3 * LL * beam
+        hv[po:po + n_lines] = 0
+        M = int(enc["mem_bf16"].shape[0])
+        p = self.decode_params(False)
+        need = self.lib.kiri_decode_beam_workspace_bytes(self.handle, n_lines, M, Lcap, beam)
+        ws = self._workspace(need, "_dws")
+        nb = n_lines * beam
+        dout = self._device("_dbeam", 5 * nb + 2 * nb * Lcap, torch.int32)
+        dout[:5 * nb].zero_()
+        perm = torch.argsort(len_est, descending=True, stable=True).to(torch.int32)
+        _lib.check(self.lib.kiri_decode_beam_multi(
+            self.handle, enc["mem_bf16"].data_ptr(), M, mem_row0.data_ptr(), mem_len.data_ptr(), T_max, len_est.data_ptr(),
+            perm.data_ptr(), n_lines, Lcap, beam, float(self.cfg.BEAM_LENP), C.byref(p), ws.data_ptr(), need,
+            dout[:2 * nb].data_ptr(), dout[2 * nb:].data_ptr(), dout[3 * nb:].data_ptr(), dout[5 * nb:].data_ptr(),
+            dout[5 * nb + nb * Lcap:].data_ptr(), 1, base, base + 4 * po, 1, _lib.stream_ptr()), "kiri_decode_beam_multi")
+        self.launches += 2
+        return {"trace": hv[:po].reshape(n_lines, Lcap, beam, 3), "progress": hv[po:po + n_lines], "beam": beam}
+
+    @staticmethod
+    def _poll(progress, k, seen, timeout_s=120.0):
+        """Wait until slot k has more than `seen` steps or has ended; returns (steps available, ended)."""
+        t0 = _time.perf_counter()
+        while True:
+            v = int(progress[k])
+            n, done = v & 0x3FFFFFFF, bool(v >> 30)
+            if n > seen or done:
+                return n, done
+            if _time.perf_counter() - t0 > timeout_s:
+                raise _lib.KiriError("live decode: no progress from the device (kernel fault?)")
+            _time.sleep(0)
+
+    def live_slot(self, tk, line: int) -> int:
+        """Decode slot of line `line` of a live ticket (results are stored in width-group order)."""
+        inv = tk.get("_inv")
+        if inv is None:
+            inv = np.empty(tk["n"], np.int64)
+            inv[tk["order"]] = np.arange(tk["n"])
+            tk["_inv"] = inv
+        return int(inv[line])
+
+    def live_greedy(self, tk, line: int):
+        """Generator over the tokens of one line AS THE DEVICE PRODUCES THEM: (token id, raw soft-max probability,
+        penalised log-prob, step, finished).  The streaming token rule applies (arg-max of the raw dec_head soft-max,
+        model.py:915-917)."""
+        lo, k, seen = tk["live_out"], self.live_slot(tk, line), 0
+        eos = self.tok.dec_eos
+        while True:
+            n, ended = self._poll(lo["progress"], k, seen)
+            for s in range(seen, n):
+                tid = int(lo["ids"][k, s])
+                yield tid, float(lo["prob"][k, s]), float(lo["logp"][k, s]), s + 1, tid == eos
+            seen = n
+            if ended:
+                return
+
+    def live_beam(self, tk, line: int):
+        """Generator over the decode steps of one line in beam-streaming mode (model.py:949-1152): after every step the
+        BEST partial hypothesis as (ids after BOS, their log-probs, step, finished), rebuilt from the device's trace."""
+        lo, k, seen = tk["live_out"], self.live_slot(tk, line), 0
+        beam, eos = lo["beam"], self.tok.dec_eos
+        hyps = [([], [])] + [None] * (beam - 1)
+        while True:
+            n, ended = self._poll(lo["progress"], k, seen)
+            for s in range(seen, n):
+                tr = lo["trace"][k, s]
+                new = [None] * beam
+                for r in range(beam):
+                    par, tokid, bits = int(tr[r, 0]), int(tr[r, 1]), tr[r, 2:3]
+                    if par < 0 or hyps[par] is None:
+                        continue
+                    ids, lps = hyps[par]
+                    new[r] = (ids + [tokid], lps + [float(bits.view(np.float32)[0])]) if tokid >= 0 else (ids, lps)
+                hyps = new
+                ids, lps = hyps[0]
+                yield ids, lps, s + 1, bool(ids) and ids[-1] == eos
+            seen = n
+            if ended:
+                return
+
+    def live_finish(self, tk):
+        """Wait for a live ticket's kernels (call when the consumer stops reading, so buffers can be reused)."""
+        if tk.get("n"):
+            tk["done"].synchronize()
+
     def ticket_records(self, tk, T: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """The exchange records of a submitted batch, built ON THE DEVICE from the ticket's outputs (stream-ordered
         behind its kernels, no host involvement): int32 [n_lines, 2 + T] = {n_ids, confidence bits, ids[T]} in the
@@ -777,7 +921,7 @@ class BatchedRecognizer:
                                                    mem_len.data_ptr(), T_max, len_est.data_ptr(), perm.data_ptr(), n_lines, Lmax,
                                                    beam, float(cfg.BEAM_LENP), C.byref(p), ws.data_ptr(), need,
                                                    score.data_ptr(), blen.data_ptr(), bstate.data_ptr(), bids.data_ptr(),
-                                                   blp.data_ptr(), _lib.stream_ptr()), "kiri_decode_beam_multi")
+                                                   blp.data_ptr(), 0, 0, 0, 0, _lib.stream_ptr()), "kiri_decode_beam_multi")
         fuse_ctc = cfg.USE_CTC and cfg.CTC_FUSION_ALPHA > 0
         if fuse_ctc:
             _lib.check(self.lib.kiri_ctc_align_score(enc["logits"].data_ptr(), self.pw.Cp, self.pw.C, mem_row0.data_ptr(),
@@ -851,13 +995,13 @@ class BatchedRecognizer:
         ent, valid = BatchedRecognizer.boxes_to_entries(page_shape, rows, page_offset)
         return ent[valid], np.asarray(good, np.int64)[valid], errors
 
-    def _isolate(self, arrays, ent, method, streaming, exc):
+    def _isolate(self, arrays, ent, method, streaming, exc, bgr=None):
         """The batch failed as a whole: recognise its lines one by one so that a single bad region cannot take the
         others down (the reference's per-region try/except); a line that fails alone becomes a LineError."""
         out = []
         for k in range(len(ent)):
             try:
-                out.append(self.collect(self.submit(arrays, ent[k:k + 1], method, streaming))[0])
+                out.append(self.collect(self.submit(arrays, ent[k:k + 1], method, streaming, bgr))[0])
             except Exception as e:                              # noqa: BLE001
                 out.append(LineError(str(e)))
         if all(isinstance(r, LineError) for r in out):
@@ -899,40 +1043,53 @@ class BatchedRecognizer:
         def launch(batch):
             arrays, ents, where, off = [], [], [], 0
             p_first = batch[0]
+            layout, any_bgr = [], False
             for p in batch:
                 if as_tensor:
                     shape = tuple(pages.shape[1:])
                     off = (p - p_first) * shape[0] * shape[1]   # the batch uploads pages[p_first .. p_last] as one block
                 else:
                     page = np.ascontiguousarray(pages[p])
-                    if page.dtype != np.uint8 or page.ndim != 2:
-                        raise ValueError("page must be a 2-D uint8 array")
-                    shape = page.shape
+                    if page.dtype != np.uint8 or not (page.ndim == 2 or (page.ndim == 3 and page.shape[2] == 3)):
+                        raise ValueError("page must be a uint8 array [H, W] (gray) or [H, W, 3] (BGR)")
+                    shape = page.shape[:2]
                     arrays.append(page)
+                    any_bgr |= page.ndim == 3
+                    layout.append([0, off, shape[0] * shape[1], page.ndim == 3])
                 ent, idx, errors = self._page_entries(shape, boxes_list[p], off)
                 for i, e in errors.items():
                     out[p][i] = e
                 if not as_tensor:
-                    off += page.size
+                    off += -(-(shape[0] * shape[1]) // 4) * 4   # gray pages start 4-byte aligned
                 ents.append(ent)
                 where += [(p, int(i)) for i in idx]
+            ent = np.concatenate(ents) if ents else np.zeros((0, 4), np.int64)
+            bgr = None
             if as_tensor:
                 # zero-copy: the H2D runs straight out of the caller's (pinned) tensor
                 arrays = pages[p_first:batch[-1] + 1].reshape(-1)
-            ent = np.concatenate(ents) if ents else np.zeros((0, 4), np.int64)
+            else:
+                # one pinned staging copy per batch; BGR pages travel as they are and become gray on the device
+                arrays, raw_offs = self._stage_host(arrays, self._slot ^ 1, align=4)
+                for item, ro in zip(layout, raw_offs):
+                    item[0] = ro
+                if any_bgr:
+                    bgr = [tuple(i) for i in layout]
+                else:
+                    assert all(i[0] == i[1] for i in layout)    # gray only: staged offsets == gray offsets
             try:
-                return (self.submit(arrays, ent, method, streaming), where, arrays, ent)
+                return (self.submit(arrays, ent, method, streaming, bgr), where, arrays, ent, bgr)
             except _lib.KiriError as e:
-                return (e, where, arrays, ent)
+                return (e, where, arrays, ent, bgr)
 
         def finish(item):
-            tk, where, arrays, ent = item
+            tk, where, arrays, ent, bgr = item
             try:
                 if isinstance(tk, Exception):
                     raise tk
                 res = self.collect(tk)
             except _lib.KiriError as e:
-                res = self._isolate(arrays, ent, method, streaming, e)
+                res = self._isolate(arrays, ent, method, streaming, e, bgr)
             for (p, i), r in zip(where, res):
                 out[p][i] = r
 

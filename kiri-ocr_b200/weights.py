@@ -95,8 +95,6 @@ class PackedWeights:
             w, b = fold_bn(sd, idx)
             setattr(W, f"{name}_w", dev_bf16(conv_gemm_weight(w)))
             setattr(W, f"{name}_b", dev_f32(b))
-            if name == "conv2":      # unpadded (ky, kx, cin) copy for the fused conv1+conv2 kernel
-                W.conv2_w48 = dev_bf16(w.permute(0, 2, 3, 1).reshape(w.shape[0], 9 * w.shape[1]).contiguous())
         W.pos_table = dev_f32(pos_table(cfg.IMG_H // 8, max_t, D))
         W.enc_ln_in_g, W.enc_ln_in_b = dev_f32(sd["enc_ln_in.weight"]), dev_f32(sd["enc_ln_in.bias"])
         for l in range(enc_layers):

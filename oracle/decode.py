@@ -10,6 +10,7 @@ Restates
   * ``OCR.recognize_region`` dispatch    — kiri_ocr/core.py:530-575
   * ``beam_decode_one_batched`` at BEAM>1 ("beam") — kiri_ocr/model.py:390-600
   * ``compute_ctc_alignment_score``      — kiri_ocr/model.py:603-668
+  * ``beam_decode_streaming``            — kiri_ocr/model.py:949-1152
 """
 from __future__ import annotations
 
@@ -245,6 +246,54 @@ def beam_decode(sd, memp_1: torch.Tensor, ctc_logits_1: torch.Tensor, tok, cfg, 
         ids.append(x)
     info = {"beams": beams, "scored": [(sc, b[1]) for (sc, _), b in scored], "len_est": target_len, "ctc_conf": ctc_conf}
     return tok.decode_dec(ids), 0.6 * best_conf + 0.4 * ctc_conf, info
+
+
+@torch.inference_mode()
+def beam_stream_chunks(sd, memp_1: torch.Tensor, ctc_logits_1: torch.Tensor, tok, cfg, heads: int = 8) -> Iterator[Dict]:
+    """``beam_decode_streaming`` (model.py:949-1152) with a KV cache: same expansion and penalties as ``beam_decode``
+    but hypotheses are pruned by ``score / L**BEAM_LENP`` (1112-1115), the best partial hypothesis is yielded after
+    every step and decoding stops as soon as the BEST hypothesis has ended (1148-1150); no CTC rescoring."""
+    _, _, _, target_len = ctc_greedy(ctc_logits_1.reshape(-1, ctc_logits_1.shape[-1]).numpy())
+    max_steps = max_steps_for(cfg, target_len, memp_1.shape[1])
+    unk = tok.unk_id + tok.dec_offset
+    beams = [(0.0, [tok.dec_bos], [], False)]
+    st = M.DecoderState(sd, memp_1, heads)
+    alive_rows: List[int] = [0]
+    prev = ""
+    for step in range(max_steps):
+        if all(b[3] for b in beams):
+            break
+        alive = [b for b in beams if not b[3]]
+        done = [b for b in beams if b[3]]
+        if not alive:
+            break
+        st = _fork_state(st, alive_rows)
+        dec, lm = M.decoder_step(st, torch.tensor([b[1][-1] for b in alive]))
+        logp = fused_logp(dec, lm, cfg).clone()
+        for i, (_, seq, _, _) in enumerate(alive):
+            apply_penalties(logp[i], seq, cfg, unk, target_len)
+        topv, topi = torch.topk(logp, k=cfg.BEAM, dim=-1)
+        new_beams = [(b, -1) for b in done]
+        for bi, (base, seq, lps, _) in enumerate(alive):
+            for v, tid in zip(topv[bi].tolist(), topi[bi].tolist()):
+                new_beams.append(((base + float(v), seq + [int(tid)], lps + [float(v)], int(tid) == tok.dec_eos), bi))
+        new_beams.sort(key=lambda e: e[0][0] / (max(1, len(e[0][1]) - 1) ** cfg.BEAM_LENP), reverse=True)
+        kept = new_beams[: cfg.BEAM]
+        beams = [b for b, _ in kept]
+        alive_rows = [row for b, row in kept if not b[3]]
+        _, best_seq, best_lps, best_fin = beams[0]
+        ids = []
+        for x in best_seq[1:]:
+            if x == tok.dec_eos:
+                break
+            ids.append(x)
+        cur = tok.decode_dec(ids)
+        yield {"token": cur[len(prev):] if len(cur) > len(prev) else "", "text": cur,
+               "confidence": sequence_confidence(best_lps) if best_lps else 0.0, "step": step + 1, "finished": best_fin,
+               "best_ids": list(best_seq[1:])}
+        prev = cur
+        if best_fin:
+            break
 
 
 # --------------------------------------------------------------------------- line level

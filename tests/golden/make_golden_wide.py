@@ -24,7 +24,7 @@ from kiri_ocr_b200 import fixtures as FX                      # noqa: E402
 from kiri_ocr_b200.config import CFG                           # noqa: E402
 from oracle import decode as OD, model as OM, preprocess as OP   # noqa: E402
 from kiri_ocr import OCR as RefOCR                             # noqa: E402
-from kiri_ocr.model import greedy_decode_streaming as ref_greedy_stream   # noqa: E402
+from kiri_ocr.model import beam_decode_streaming as ref_beam_stream, greedy_decode_streaming as ref_greedy_stream   # noqa: E402
 from tests.golden.wide import MARGIN, WIDE_CASES, fit_max_margin, frame_labels, wide_crops   # noqa: E402
 
 
@@ -121,6 +121,20 @@ def main():
                 mem_r = m.encode(t)
                 chunks = list(ref_greedy_stream(m, m.mem_proj(mem_r), tok, r["accurate"].cfg, m.ctc_head(mem_r)))
             stream_ids = [ch["token_id"] for ch in chunks if "token_id" in ch]
+            # beam streaming (model.py:949-1152), BEAM 3: per-step best text / confidence / finished, oracle pinned to it
+            with torch.inference_mode():
+                r["beam"].cfg.BEAM = 3
+                bchunks = list(ref_beam_stream(m, m.mem_proj(mem_r), tok, r["beam"].cfg, m.ctc_head(mem_r)))
+            ochunks = list(OD.beam_stream_chunks(sd, OM.mem_proj(sd, mems[i]), OM.ctc_logits(sd, mems[i])[0], tok, bcfg))
+            assert len(ochunks) == len(bchunks), (key, len(ochunks), len(bchunks))
+            for a, b_ in zip(ochunks, bchunks):
+                assert a["text"] == b_["text"] and a["token"] == b_["token"] and a["finished"] == b_["finished"] and \
+                    abs(a["confidence"] - b_["confidence"]) < 1e-5, (key, a, b_)
+            assert bchunks[-1]["finished"] and bchunks[-1]["text"] == want_text
+            out[f"{key}/bstream_texts"] = np.array("\x00".join(ch["text"] for ch in bchunks))
+            out[f"{key}/bstream_conf"] = np.asarray([ch["confidence"] for ch in bchunks], np.float64)
+            out[f"{key}/gstream_conf"] = np.asarray([ch["confidence"] for ch in chunks], np.float64)
+            out[f"{key}/gstream_texts"] = np.array("\x00".join(ch["text"] for ch in chunks))
             out[f"{key}/Wb"] = np.int32(Wb)
             out[f"{key}/frame_ids"] = best.astype(np.int16)
             out[f"{key}/ctc_ids"] = collapsed.astype(np.int16)

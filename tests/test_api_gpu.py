@@ -199,3 +199,29 @@ def test_recognize_pages_equals_per_page(setup):
                 if x is not None:
                     assert x.text == y.text and x.confidence == y.confidence and np.array_equal(x.ids, y.ids)
     assert multi[2][-1] is None
+
+
+def test_bgr_page_ingest_equals_host_gray(setup, tmp_path):
+    """A colour page decoded by cv2.imread goes to the device as BGR and is converted there: results must equal the
+    path that converts on the host with cv2 (the reference's own order of operations, core.py:762-766)."""
+    import cv2
+    from kiri_ocr_b200 import OCR
+    path, img, page, boxes, sd = setup
+    rng = np.random.default_rng(3)
+    colour = np.stack([page, np.clip(page.astype(np.int16) - 9, 0, 255).astype(np.uint8), rng.integers(200, 256, page.shape, dtype=np.uint8)], -1)
+    cpath = str(tmp_path / "colour.png")
+    cv2.imwrite(cpath, colour)
+    ocr = OCR(model_path=path, decode_method="fast")
+    ocr._detector = FakeDetector(boxes)
+    res = ocr.process_document(cpath)
+    bgr = cv2.imread(cpath)
+    assert bgr.ndim == 3
+    gray = cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY)
+    want = ocr.model.recognize_boxes(gray, boxes, "ctc")
+    assert len(res) == len(want)
+    for r, w in zip(res, want):
+        assert r["text"] == w.text and r["confidence"] == float(w.confidence)
+    # mixed batch: a BGR page and a gray page in one multi-page call
+    multi = ocr.model.recognize_pages([bgr, gray], [boxes, boxes], "ctc", batch_lines=1000)
+    for a, b, w in zip(multi[0], multi[1], want):
+        assert a.text == w.text == b.text and a.confidence == w.confidence == b.confidence

@@ -231,7 +231,7 @@ def test_conv3x3_vs_torch(lib, cin, cout, sh, sw, IH, IW, n):
     OH, OW = (IH - 1) // sh + 1, (IW - 1) // sw + 1
     out = torch.full((n, OH, OW, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
     _lib.check(lib.kiri_conv3x3_bf16(x.data_ptr(), wk.data_ptr(), bias.data_ptr(), n, IH, IW, cin, cout, sh, sw,
-                                     out.data_ptr(), _lib.stream_ptr()), "kiri_conv3x3_bf16")
+                                     out.data_ptr(), 0, _lib.stream_ptr()), "kiri_conv3x3_bf16")
     sync()
     ref = F.silu(F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, (sh, sw), 1)).permute(0, 2, 3, 1)
     err = (out.float() - ref).abs()
@@ -239,10 +239,38 @@ def test_conv3x3_vs_torch(lib, cin, cout, sh, sw, IH, IW, n):
     assert float(err.max()) < 0.03, f"max err {float(err.max())} at {torch.nonzero(err == err.max())[0].tolist()}"
 
 
-@pytest.mark.parametrize("entry", ["kiri_conv1_tc", "kiri_conv1_ffma"])
+@pytest.mark.parametrize("IW,n", [(640, 2), (128, 3), (384, 1)])
+def test_conv2_on_dense_48_channels_equals_padded_64(lib, IW, n):
+    """conv2 reads conv1's DENSE 48-channel activation: the tensor map's inner extent is 48, the box 64, and the TMA
+    unit zero-fills channels 48..63 in shared memory.  Must be bit-identical to the same conv on a 64-channel tensor
+    whose last 16 channels are stored zeros (the round-1 layout), and match torch."""
+    torch.manual_seed(IW + n)
+    IH, cout = 48, 96
+    x48 = dev(torch.randn(n, IH, IW, 48).to(torch.bfloat16))
+    x64 = torch.zeros(n, IH, IW, 64, dtype=torch.bfloat16, device="cuda")
+    x64[..., :48] = x48
+    w = (torch.randn(cout, 48, 3, 3) / (3 * 48 ** 0.5)).to(torch.bfloat16)
+    w64 = torch.zeros(cout, 3, 3, 64, dtype=torch.bfloat16)
+    w64[..., :48] = w.permute(0, 2, 3, 1)
+    # garbage in the padded weight columns must not matter either: the activations there are zero-filled
+    wk = dev(w64.reshape(cout, 9 * 64))
+    bias = dev(torch.randn(cout) * 0.2)
+    outs = []
+    for x, cm in ((x48, 48), (x64, 0)):
+        out = torch.full((n, IH // 2, IW // 2, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+        _lib.check(lib.kiri_conv3x3_bf16(x.data_ptr(), wk.data_ptr(), bias.data_ptr(), n, IH, IW, 64, cout, 2, 2, out.data_ptr(),
+                                         cm, _lib.stream_ptr()), "kiri_conv3x3_bf16")
+        sync()
+        outs.append(out)
+    assert not torch.isnan(outs[0].float()).any()
+    assert torch.equal(outs[0], outs[1])
+    ref = F.silu(F.conv2d(x48.float().permute(0, 3, 1, 2), dev(w).float(), bias, (2, 2), 1)).permute(0, 2, 3, 1)
+    assert float((outs[0].float() - ref).abs().max()) < 0.03
+
+
 @pytest.mark.parametrize("n,W", [(3, 256), (2, 640), (1, 128)])
-def test_conv1_vs_torch(lib, entry, n, W):
-    """Tensor-core conv1 (mma.sync on exact bf16 operands u = v - 128, split weights) and the fp32 FFMA form."""
+def test_conv1_vs_torch(lib, n, W):
+    """conv1 (packed fp32 FMAs, dense 48-channel NHWC output) against torch in float64."""
     torch.manual_seed(W)
     H = 48
     planes = torch.randint(0, 256, (n, H, W), dtype=torch.uint8)
@@ -250,72 +278,40 @@ def test_conv1_vs_torch(lib, entry, n, W):
     planes[0, 4:8] = 255
     w = torch.randn(48, 9) / 3
     b = torch.randn(48) * 0.1
-    out = torch.full((n, H, W, 64), float("nan"), dtype=torch.bfloat16, device="cuda")
-    _lib.check(getattr(lib, entry)(dev(planes).data_ptr(), w.data_ptr(), b.data_ptr(), n, H, W, out.data_ptr(),
-                                   _lib.stream_ptr()))
+    out = torch.full((n, H, W, 48), float("nan"), dtype=torch.bfloat16, device="cuda")
+    _lib.check(lib.kiri_conv1(dev(planes).data_ptr(), w.data_ptr(), b.data_ptr(), n, H, W, out.data_ptr(), _lib.stream_ptr()))
     sync()
     x = (planes.float() / 255.0 - 0.5) / 0.5
     ref = F.silu(F.conv2d(x[:, None].double(), w.view(48, 1, 3, 3).double(), b.double(), 1, 1)).permute(0, 2, 3, 1)
     o = out.float().cpu()
-    err = (o[..., :48].double() - ref).abs()
+    assert not torch.isnan(o).any()
+    err = (o.double() - ref).abs()
     # the only error left is the bf16 rounding of the output (2^-9 relative) and tanh.approx (2^-11)
     assert float((err / (ref.abs() + 0.05)).max()) < 6e-3, float((err / (ref.abs() + 0.05)).max())
     assert float(err.max()) < 0.03
-    assert float(o[..., 48:].abs().max()) == 0.0
 
 
-def test_conv1_tensor_core_matches_ffma(lib):
-    """Both forms see the reference's exact pixel values: they may differ by one bf16 rounding step at most."""
-    torch.manual_seed(11)
-    n, H, W = 2, 48, 384
-    planes = dev(torch.randint(0, 256, (n, H, W), dtype=torch.uint8))
+def test_conv1_multi_groups_equal_single_launches(lib):
+    """One launch for several width groups == one launch per group, bit for bit."""
+    torch.manual_seed(5)
+    H = 48
     w = torch.randn(48, 9) / 3
     b = torch.randn(48) * 0.1
-    o1 = torch.zeros((n, H, W, 64), dtype=torch.bfloat16, device="cuda")
-    o2 = torch.zeros_like(o1)
-    _lib.check(lib.kiri_conv1_tc(planes.data_ptr(), w.data_ptr(), b.data_ptr(), n, H, W, o1.data_ptr(), _lib.stream_ptr()))
-    _lib.check(lib.kiri_conv1_ffma(planes.data_ptr(), w.data_ptr(), b.data_ptr(), n, H, W, o2.data_ptr(), _lib.stream_ptr()))
+    shapes = [(2, 128), (3, 384), (1, 640)]
+    planes = [dev(torch.randint(0, 256, (n, H, W), dtype=torch.uint8)) for n, W in shapes]
+    single = []
+    for (n, W), pl in zip(shapes, planes):
+        o = torch.empty((n, H, W, 48), dtype=torch.bfloat16, device="cuda")
+        _lib.check(lib.kiri_conv1(pl.data_ptr(), w.data_ptr(), b.data_ptr(), n, H, W, o.data_ptr(), _lib.stream_ptr()))
+        single.append(o)
+    multi = [torch.full((n, H, W, 48), float("nan"), dtype=torch.bfloat16, device="cuda") for n, W in shapes]
+    k = len(shapes)
+    _lib.check(lib.kiri_conv1_multi((C.c_void_p * k)(*[p.data_ptr() for p in planes]), (C.c_void_p * k)(*[m.data_ptr() for m in multi]),
+                                    (C.c_int * k)(*[n for n, _ in shapes]), (C.c_int * k)(*[W for _, W in shapes]), k,
+                                    w.data_ptr(), b.data_ptr(), H, _lib.stream_ptr()))
     sync()
-    d = (o1.float() - o2.float()).abs()
-    assert float((d / (o2.float().abs() + 1e-3)).max()) < 1.0 / 64       # <= ~2 bf16 ulps (tanh.approx inputs differ by 1e-6)
-    assert float((d > 0).float().mean()) < 0.05                           # and only on rounding boundaries
-
-
-@pytest.mark.parametrize("n,W", [(2, 128), (3, 384), (5, 640)])
-def test_stem12_fused_vs_torch_and_unfused(lib, n, W):
-    """conv1 fused into conv2 (stem12_kernel): against torch fp32 with the bf16 rounding of the
-    intermediate, and bit-for-bit against the unfused conv1 -> conv2 kernels (same arithmetic)."""
-    torch.manual_seed(n + W)
-    H = 48
-    planes = torch.randint(0, 256, (n, H, W), dtype=torch.uint8)
-    w1 = torch.randn(48, 9) / 3
-    b1 = torch.randn(48) * 0.1
-    w2 = (torch.randn(96, 48, 3, 3) / (3 * 48 ** 0.5)).to(torch.bfloat16)
-    b2 = dev(torch.randn(96) * 0.2)
-    w48 = dev(w2.permute(0, 2, 3, 1).reshape(96, 9 * 48).contiguous())
-    out = torch.full((n, H // 2, W // 2, 96), float("nan"), dtype=torch.bfloat16, device="cuda")
-    pl = dev(planes)
-    _lib.check(lib.kiri_stem12(pl.data_ptr(), w1.data_ptr(), b1.data_ptr(), w48.data_ptr(), b2.data_ptr(), n, H, W,
-                               out.data_ptr(), _lib.stream_ptr()), "kiri_stem12")
-    sync()
-    assert not torch.isnan(out.float()).any()
-    # torch reference with the same rounding points
-    x = (planes.float() / 255.0 - 0.5) / 0.5
-    a1 = F.silu(F.conv2d(x[:, None], w1.view(48, 1, 3, 3), b1, 1, 1)).to(torch.bfloat16).float()
-    ref = F.silu(F.conv2d(a1, w2.float(), b2.cpu(), 2, 1)).permute(0, 2, 3, 1)
-    err = (out.float().cpu() - ref).abs()
-    assert float(err.max()) < 0.05, f"max err {float(err.max())} at {torch.nonzero(err == err.max())[0].tolist()}"
-    # unfused device path: conv1 (64-channel NHWC) -> conv3x3 with the 64-channel padded weights
-    act1 = torch.empty((n, H, W, 64), dtype=torch.bfloat16, device="cuda")
-    _lib.check(lib.kiri_conv1_ffma(pl.data_ptr(), w1.data_ptr(), b1.data_ptr(), n, H, W, act1.data_ptr(), _lib.stream_ptr()))
-    w64 = torch.zeros(96, 3, 3, 64, dtype=torch.bfloat16)
-    w64[..., :48] = w2.permute(0, 2, 3, 1)
-    out2 = torch.empty_like(out)
-    _lib.check(lib.kiri_conv3x3_bf16(act1.data_ptr(), dev(w64.reshape(96, 9 * 64)).data_ptr(), b2.data_ptr(), n, H, W, 64, 96,
-                                     2, 2, out2.data_ptr(), _lib.stream_ptr()))
-    sync()
-    d = (out.float() - out2.float()).abs().max()
-    assert float(d) < 0.02, float(d)          # same products; only the fp32 accumulation order differs
+    for a, m in zip(single, multi):
+        assert torch.equal(a, m)
 
 
 # --------------------------------------------------------------------------- norms / attention
@@ -492,3 +488,20 @@ def test_encoder_block_soak_back_to_back():
                        timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("soak ok") == 8
+
+
+def test_bgr_to_gray_bit_exact_vs_cv2(lib):
+    """GPU page ingest: the BGR -> gray kernel equals cv2.cvtColor(COLOR_BGR2GRAY) byte for byte (core.py:762-766)."""
+    import cv2
+    rng = np.random.default_rng(7)
+    for shape in ((37, 53), (480, 641), (2339, 1654), (1, 1), (3, 2)):
+        img = rng.integers(0, 256, shape + (3,), dtype=np.uint8)
+        img[0, : min(shape[1], 256), 0] = np.arange(min(shape[1], 256))
+        want = cv2.cvtColor(img, cv2.COLOR_BGR2GRAY)
+        src = dev(torch.from_numpy(img.reshape(-1)))
+        out = torch.zeros(shape[0] * shape[1] + 8, dtype=torch.uint8, device="cuda")
+        _lib.check(lib.kiri_bgr_to_gray(src.data_ptr(), shape[0] * shape[1], out.data_ptr(), _lib.stream_ptr()))
+        sync()
+        got = out.cpu().numpy()
+        assert np.array_equal(got[: want.size].reshape(shape), want), shape
+        assert not got[want.size:].any()                      # nothing written past the image

@@ -10,6 +10,6 @@ w = torch.randn(cout, 9 * cin, device="cuda").to(torch.bfloat16)
 bias = torch.zeros(cout, device="cuda")
 OH, OW = (IH + 2 - 3) // sh + 1, (IW + 2 - 3) // sw + 1
 out = torch.zeros((n, OH, OW, cout), dtype=torch.bfloat16, device="cuda")
-_lib.check(lib.kiri_conv3x3_bf16(x.data_ptr(), w.data_ptr(), bias.data_ptr(), n, IH, IW, cin, cout, sh, sw, out.data_ptr(), _lib.stream_ptr()))
+_lib.check(lib.kiri_conv3x3_bf16(x.data_ptr(), w.data_ptr(), bias.data_ptr(), n, IH, IW, cin, cout, sh, sw, out.data_ptr(), 0, _lib.stream_ptr()))
 torch.cuda.synchronize()
 print("ok", float(out.float().abs().mean()))

@@ -40,14 +40,14 @@ def gemm(M, N, K, epi):
     ms, reps = timeit(fn)
     report(f"gemm M={M} N={N} K={K} epi={epi}", ms, reps)
 
-def conv(n, IH, IW, cin, cout, sh, sw):
-    x = torch.randn(n, IH, IW, cin, device="cuda").to(torch.bfloat16)
+def conv(n, IH, IW, cin, cout, sh, sw, cin_mem=0):
+    x = torch.randn(n, IH, IW, cin_mem or cin, device="cuda").to(torch.bfloat16)
     w = torch.randn(cout, 9 * cin, device="cuda").to(torch.bfloat16)
     bias = torch.zeros(cout, device="cuda")
     OH, OW = (IH + 2 - 3) // sh + 1, (IW + 2 - 3) // sw + 1
     out = torch.zeros((n, OH, OW, cout), dtype=torch.bfloat16, device="cuda")
     fn = lambda: _lib.check(lib.kiri_conv3x3_bf16(x.data_ptr(), w.data_ptr(), bias.data_ptr(), n, IH, IW, cin, cout, sh, sw,
-                                                  out.data_ptr(), _lib.stream_ptr()))
+                                                  out.data_ptr(), cin_mem, _lib.stream_ptr()))
     ms, reps = timeit(fn)
     fl = 2.0 * n * OH * OW * cout * 9 * cin
     report(f"conv n={n} {IH}x{IW}x{cin}->{cout} s({sh},{sw}) [{fl/ms/1e9:.0f} TF/s padded]", ms, reps)
@@ -57,24 +57,7 @@ gemm(40960, 256, 256, 5)
 gemm(40960, 1024, 256, 2)
 gemm(40960, 256, 1024, 5)
 gemm(40960, 208, 256, 4)
-conv(16, 48, 640, 64, 96, 2, 2)
+conv(16, 48, 640, 64, 96, 2, 2, 48)
 conv(16, 24, 320, 96, 160, 2, 2)
 conv(16, 12, 160, 160, 256, 2, 1)
 
-
-def stem12(n, W):
-    H = 48
-    planes = torch.randint(0, 256, (n, H, W), dtype=torch.uint8, device="cuda")
-    w1 = torch.randn(48, 9) / 3; b1 = torch.randn(48) * 0.1
-    w48 = torch.randn(96, 432, device="cuda").to(torch.bfloat16); b2 = torch.zeros(96, device="cuda")
-    out = torch.zeros((n, H // 2, W // 2, 96), dtype=torch.bfloat16, device="cuda")
-    fn = lambda: _lib.check(lib.kiri_stem12(planes.data_ptr(), w1.data_ptr(), b1.data_ptr(), w48.data_ptr(), b2.data_ptr(), n, H, W,
-                                            out.data_ptr(), _lib.stream_ptr()))
-    ms, reps = timeit(fn)
-    lib.kiri_debug_gemm_timing(buf, 16)
-    tiles = max(1, buf[15])
-    print(f"stem12 n={n} W={W}: {ms*1e3:.1f} us/launch; CTA0 tiles/launch {tiles/reps:.1f}; cycles per tile: wait_a_empty={buf[10]/tiles:.0f} "
-          f"patch={buf[11]/tiles:.0f} conv1+scatter={buf[12]/tiles:.0f} drain={buf[13]/tiles:.0f}")
-
-stem12(64, 640)
-stem12(64, 256)

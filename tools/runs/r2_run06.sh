@@ -1,0 +1,12 @@
+#!/bin/bash
+# round 2, call 6: dense 48-channel conv1 output, conv2 with TMA zero-filled K padding
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_kernels_gpu.py -m gpu -q -x -k "conv" > gpurun_out/r2_06_conv.log 2>&1; echo "== conv tests rc=$?"; tail -5 gpurun_out/r2_06_conv.log
+timeout 1500 python -m pytest tests -m gpu -q -x > gpurun_out/r2_06_pytest.log 2>&1; echo "== pytest rc=$?"; tail -5 gpurun_out/r2_06_pytest.log
+timeout 600 python bench.py > gpurun_out/r2_06_bench_fast.json 2> gpurun_out/r2_06_bench_fast.err; echo "== bench rc=$?"; tail -3 gpurun_out/r2_06_bench_fast.err
+python - <<PY
+import json
+d=[json.loads(l) for l in open('gpurun_out/r2_06_bench_fast.json') if l.startswith('{')][0]
+print('value',round(d['value']),'ms',round(d['ms_per_step'],3),'e2e',round(d['e2e']['value']),'launches',d['gpu_launches'],'roof',round(d['roofline']['frac'],3))
+print({k:round(v['ms_per_step'],4) for k,v in d['stages'].items()})
+PY

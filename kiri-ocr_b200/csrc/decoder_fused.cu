@@ -68,6 +68,7 @@ struct FusedArgs {
   int timing;                                         // 1: accumulate phase cycles into g_dec_prof
   // live streaming: outputs may live in mapped host memory; every step is published with
   // system-scope fences so that a host thread polling `progress` sees the step's ids / log-probs
+  int prefetch;                                       // 1: L2 prefetch of the cross K/V blocks a layer ahead of their use
   int publish;                                        // 1: fence before the progress words
   int* progress;                                      // nullable [B]: steps available | (1 << 30) once the line is done
   int stream_rule;                                    // beam: 1 = beam_decode_streaming's rule (prune by score / L^lenp, stop
@@ -208,7 +209,7 @@ __host__ __device__ inline FusedSmem fused_smem_plan(int ff, int Vp, int cs, int
   s.qloc = take(kFL * (256 / cs) * 4);
   s.logits = take(kFL * 2 * Vp * 4);
   s.part = take(kFWarps * 512);
-  s.vstage = take(kFWarps * 32 * kHd * 2);
+  s.vstage = take(0);                                  // (round 1: V staging tiles of the attention; no longer used)
   s.state = take(static_cast<int>(sizeof(LineState)));
   s.params = take((layers * fused_layer_floats(ff) + 2 * Vp + 512) * 4);
   s.beam = take(beam >= 1 ? static_cast<int>(sizeof(BeamState)) : 0);       // beam = 0: greedy, no bookkeeping
@@ -217,68 +218,130 @@ __host__ __device__ inline FusedSmem fused_smem_plan(int ff, int Vp, int cs, int
   return s;
 }
 
-// single-query attention of one warp over n keys; K/V rows are 32 bf16 at base + j*ld.
-// q: 32 fp32 in shared memory; vst: this warp's 32x32 bf16 staging tile.  Returns o[lane].
-template <bool READONLY, class RowOff>
+// Single-query attention of one warp over n keys; K/V rows are 32 bf16 (64 B) at base + row_off(j) elements.
+// q: 32 fp32 in shared memory.  Returns o[lane] (output dimension = lane).
+//
+// Lane l OWNS keys l, l+32, ... of a group of kAttC*32 keys: it computes their scores with a 32-wide dot product on its
+// own K rows and accumulates its own V rows into a private 32-dim partial sum; one 31-step butterfly at the very end
+// moves dimension d to lane d.  (Round 1 gave every lane one output DIMENSION instead: per 32-key chunk the V rows went
+// through a shared-memory staging tile and every key cost a shuffle + a shared load + a convert + an FMA in a serial
+// chain - ~2000 warp instructions per (line, head) at T = 160, measured 11.4 us per layer; this form needs ~800 and its
+// 16 resident warps hide the row loads.)  Groups are merged with the running-max rule of online soft-max.
+static constexpr int kAttC = 5;          // 32-key chunks per group: one group covers T <= 160 (every cross-attention)
+
+// MULTI = false: n <= kAttC*32 (one group; the output partial sums are not live during the score pass);
+// MULTI = true: any n, groups merged with the running-max rule of online soft-max.
+// Row j of the K / V operand lives at base + j*stride (+ (slot0 + anc[j]) * slot_stride when `anc` is given: beam
+// hypotheses read position j from the physical cache slot their ancestor wrote, see the ancestor table below).
+// One row per lane is in flight at a time: with two or three (tried as explicit batches, inlined and as separate
+// functions) ptxas front-batches the loads of the whole unrolled loop and spills 1-5 KB at the kernel's 128-register cap.
+template <bool READONLY, bool MULTI>
 __device__ __forceinline__ float attend_warp(const float* q, const __nv_bfloat16* kbase, const __nv_bfloat16* vbase,
-                                             RowOff row_off, int n, __nv_bfloat16* vst, int lane) {
-  float qf[kHd];
-#pragma unroll
-  for (int i = 0; i < kHd; i += 4) {
-    const float4 t = *reinterpret_cast<const float4*>(q + i);
-    qf[i] = t.x; qf[i + 1] = t.y; qf[i + 2] = t.z; qf[i + 3] = t.w;
-  }
+                                          size_t stride, const uint8_t* anc, size_t slot_stride, int slot0, int n, int lane) {
+  auto row_off = [&](int j) -> size_t {
+    return static_cast<size_t>(j) * stride + (anc ? static_cast<size_t>(slot0 + anc[j]) * slot_stride : 0);
+  };
+  const float4* q4 = reinterpret_cast<const float4*>(q);       // broadcast LDS.128 per use: q stays out of the registers
   const float scale = 0.17677669529663687f;           // 1/sqrt(32)
-  float m_run = -INFINITY, l_run = 0.f, o = 0.f;
-  for (int c0 = 0; c0 < n; c0 += 32) {
-    const int j = c0 + lane;
-    float s = -INFINITY;
-    uint4 vv[4];
+  auto ld_row = [&](const __nv_bfloat16* base, int j, uint4 (&r)[4]) {
     if (j < n) {
-      const size_t ro = row_off(j);
-      const uint4* kp = reinterpret_cast<const uint4*>(kbase + ro);
-      const uint4* vp = reinterpret_cast<const uint4*>(vbase + ro);
-      uint4 kk[4];
+      const uint4* p = reinterpret_cast<const uint4*>(base + row_off(j));
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (READONLY) { kk[i] = __ldg(kp + i); vv[i] = __ldg(vp + i); }
-        else { kk[i] = kp[i]; vv[i] = vp[i]; }
-      }
-      float acc = 0.f;
+      for (int i = 0; i < 4; ++i) r[i] = READONLY ? __ldg(p + i) : p[i];
+    }
+  };
+  auto dot_row = [&](const uint4 (&r)[4]) -> float {
+    float acc = 0.f;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint4 u = kk[i];
-        acc = fmaf(qf[8 * i + 0], bf16_lo(u.x), acc); acc = fmaf(qf[8 * i + 1], bf16_hi(u.x), acc);
-        acc = fmaf(qf[8 * i + 2], bf16_lo(u.y), acc); acc = fmaf(qf[8 * i + 3], bf16_hi(u.y), acc);
-        acc = fmaf(qf[8 * i + 4], bf16_lo(u.z), acc); acc = fmaf(qf[8 * i + 5], bf16_hi(u.z), acc);
-        acc = fmaf(qf[8 * i + 6], bf16_lo(u.w), acc); acc = fmaf(qf[8 * i + 7], bf16_hi(u.w), acc);
+    for (int i = 0; i < 4; ++i) {
+      const uint4 u = r[i];
+      const float4 qa = q4[2 * i], qb = q4[2 * i + 1];
+      acc = fmaf(qa.x, bf16_lo(u.x), acc); acc = fmaf(qa.y, bf16_hi(u.x), acc);
+      acc = fmaf(qa.z, bf16_lo(u.y), acc); acc = fmaf(qa.w, bf16_hi(u.y), acc);
+      acc = fmaf(qb.x, bf16_lo(u.z), acc); acc = fmaf(qb.y, bf16_hi(u.z), acc);
+      acc = fmaf(qb.z, bf16_lo(u.w), acc); acc = fmaf(qb.w, bf16_hi(u.w), acc);
+    }
+    return acc;
+  };
+  constexpr int RBK = MULTI ? 1 : 1;                   // K rows in flight per lane
+  constexpr int RBV = 1;                               // V rows in flight per lane (32 partial sums are live)
+  float m_run = -INFINITY, l_run = 0.f;
+  float o[kHd];
+  if (MULTI) {
+#pragma unroll
+    for (int d = 0; d < kHd; ++d) o[d] = 0.f;
+  }
+  const int n_grp = MULTI ? n : 1;
+  for (int g0 = 0; g0 < n_grp; g0 += kAttC * 32) {
+    // ---- scores of this lane's keys (rows of a batch are loaded together: one memory latency per batch)
+    float sc[kAttC];
+#pragma unroll
+    for (int c0 = 0; c0 < kAttC; c0 += RBK) {
+      uint4 rr[RBK][4];
+#pragma unroll
+      for (int r = 0; r < RBK; ++r)
+        if (c0 + r < kAttC) ld_row(kbase, g0 + lane + 32 * (c0 + r), rr[r]);
+#pragma unroll
+      for (int r = 0; r < RBK; ++r)
+        if (c0 + r < kAttC) {
+          const int j = g0 + lane + 32 * (c0 + r);
+          sc[c0 + r] = (j < n) ? dot_row(rr[r]) * scale : -INFINITY;
+        }
+    }
+    // ---- soft-max bookkeeping (running max over groups)
+    float gm = sc[0];
+#pragma unroll
+    for (int c = 1; c < kAttC; ++c) gm = fmaxf(gm, sc[c]);
+    const float m_new = fmaxf(m_run, warp_max(gm));
+    const float corr = __expf(m_run - m_new);          // 0 for the first group (m_run = -inf)
+    float ps = 0.f;
+#pragma unroll
+    for (int c = 0; c < kAttC; ++c) { sc[c] = __expf(sc[c] - m_new); ps += sc[c]; }     // exp(-inf) = 0 past the end
+    l_run = l_run * corr + warp_sum(ps);
+    if (MULTI) {
+      if (g0 > 0) {
+#pragma unroll
+        for (int d = 0; d < kHd; ++d) o[d] *= corr;
       }
-      s = acc * scale;
     } else {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) vv[i] = make_uint4(0, 0, 0, 0);
+      for (int d = 0; d < kHd; ++d) o[d] = 0.f;
     }
-    // stage V rows (row = key, 64 B) with a 16-byte-chunk rotation so column reads are conflict-free
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      *reinterpret_cast<uint4*>(vst + lane * kHd + ((i + (lane >> 1)) & 3) * 8) = vv[i];
-    const float cm = warp_max(s);
-    const float m_new = fmaxf(m_run, cm);
-    const float corr = __expf(m_run - m_new);
-    const float p = (j < n) ? __expf(s - m_new) : 0.f;
-    l_run = l_run * corr + warp_sum(p);
-    o *= corr;
-    __syncwarp();
-    const int n_here = min(32, n - c0);
-    for (int jj = 0; jj < n_here; ++jj) {
-      const float pj = __shfl_sync(0xffffffffu, p, jj);
-      const int chunk = ((lane >> 3) + (jj >> 1)) & 3;
-      o = fmaf(pj, __bfloat162float(vst[jj * kHd + chunk * 8 + (lane & 7)]), o);
-    }
-    __syncwarp();
     m_run = m_new;
+    // ---- this lane's V rows into its private partial sum
+#pragma unroll
+    for (int c0 = 0; c0 < kAttC; c0 += RBV) {
+      uint4 rr[RBV][4];
+#pragma unroll
+      for (int r = 0; r < RBV; ++r)
+        if (c0 + r < kAttC) ld_row(vbase, g0 + lane + 32 * (c0 + r), rr[r]);
+#pragma unroll
+      for (int r = 0; r < RBV; ++r)
+        if (c0 + r < kAttC && g0 + lane + 32 * (c0 + r) < n) {
+          const float pj = sc[c0 + r];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 u = rr[r][i];
+            o[8 * i + 0] = fmaf(pj, bf16_lo(u.x), o[8 * i + 0]); o[8 * i + 1] = fmaf(pj, bf16_hi(u.x), o[8 * i + 1]);
+            o[8 * i + 2] = fmaf(pj, bf16_lo(u.y), o[8 * i + 2]); o[8 * i + 3] = fmaf(pj, bf16_hi(u.y), o[8 * i + 3]);
+            o[8 * i + 4] = fmaf(pj, bf16_lo(u.z), o[8 * i + 4]); o[8 * i + 5] = fmaf(pj, bf16_hi(u.z), o[8 * i + 5]);
+            o[8 * i + 6] = fmaf(pj, bf16_lo(u.w), o[8 * i + 6]); o[8 * i + 7] = fmaf(pj, bf16_hi(u.w), o[8 * i + 7]);
+          }
+        }
+    }
   }
-  return o / l_run;
+  // ---- butterfly: sum the 32 partial vectors over the lanes, dimension d ends up in lane d
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) {
+    const bool up = (lane & w) != 0;                   // this lane keeps the upper half of what it still holds
+#pragma unroll
+    for (int k = 0; k < w; ++k) {
+      const float keep = up ? o[k + w] : o[k];
+      const float send = up ? o[k] : o[k + w];
+      o[k] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+    }
+  }
+  return o[0] / l_run;
 }
 
 // ln8 (ln_utils.cuh) with the affine in shared memory (plain loads)
@@ -339,7 +402,6 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
   float* qloc = reinterpret_cast<float*>(sm + L.qloc);
   float* logits = reinterpret_cast<float*>(sm + L.logits);
   float* part = reinterpret_cast<float*>(sm + L.part);
-  __nv_bfloat16* vst = reinterpret_cast<__nv_bfloat16*>(sm + L.vstage) + warp * 32 * kHd;
   LineState* st = reinterpret_cast<LineState*>(sm + L.state);
   float* prm = reinterpret_cast<float*>(sm + L.params);
   const int lfl = fused_layer_floats(A.ff);
@@ -471,6 +533,28 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
     for (int l = 0; l < A.layers; ++l) {
       const FusedLayer& W = A.layer[l];
       const float* PB = prm + l * lfl;                 // this layer's biases
+      // The cross K/V blocks this CTA will read in phase F do not depend on the tokens: pull them from HBM into L2
+      // NOW (prefetch.global.L2 needs no registers), ~10 us of other phases ahead of their use.  The per-lane loads
+      // of phase F then pay an L2 hit instead of an HBM miss per 32-key chunk (the cross K/V of a 256-line batch,
+      // 80-126 MB, do not stay L2-resident from one step to the next).
+      if (A.kv_hm && A.prefetch) {
+        const int i = warp;
+        if (st->valid[i] && !st->finished[i]) {
+          const int Tm = st->mlen[i];
+          const int n128 = (Tm * kHd * 2 + 127) >> 7;              // 128-byte lines of one (head, K|V) block
+#pragma unroll
+          for (int hl = 0; hl < HPC; ++hl) {
+            const int head = rank * HPC + hl;
+            const char* kb = reinterpret_cast<const char*>(A.crosskv + static_cast<size_t>(st->row0[i]) * A.crosskv_ld +
+                                                           (static_cast<size_t>(l) * 2 * kHeads + head) * Tm * kHd);
+            const char* vb = kb + static_cast<size_t>(kHeads) * Tm * kHd * 2;
+            for (int c = lane; c < n128; c += 32) {
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(kb + (c << 7)));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(vb + (c << 7)));
+            }
+          }
+        }
+      }
       const float* PN = PB + 1792 + A.ff;              // ln1 g,b | ln2 g,b | ln3 g,b
       // the cache is indexed by PHYSICAL slot: B slots when greedy, 16 per cluster in beam mode
       const size_t cache_slots = !BM ? static_cast<size_t>(A.B) : static_cast<size_t>(gridDim.x / CS) * kFL;
@@ -499,14 +583,16 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
         if (st->valid[i] && !st->finished[i]) {
           if (!BM) {
             const size_t base = (static_cast<size_t>(b0 + i) * A.Lmax) * D + head * kHd;
-            o = attend_warp<false>(qloc + i * DC + hl * kHd, kc + base, vc + base,
-                                   [&](int j) { return static_cast<size_t>(j) * D; }, step + 1, vst, lane);
+            if (step < kAttC * 32)
+              o = attend_warp<false, false>(qloc + i * DC + hl * kHd, kc + base, vc + base, D, nullptr, 0, 0, step + 1, lane);
+            else
+              o = attend_warp<false, true>(qloc + i * DC + hl * kHd, kc + base, vc + base, D, nullptr, 0, 0, step + 1, lane);
           } else {
             // hypothesis i reads position j from the physical slot its ancestor wrote it to
             const uint8_t* ar = anc + (pp * kFL + i) * anc_ld;
             const size_t base = static_cast<size_t>(head) * kHd;
-            o = attend_warp<false>(qloc + i * DC + hl * kHd, kc + base, vc + base,
-                                   [&](int j) { return (static_cast<size_t>(b0 + ar[j]) * A.Lmax + j) * D; }, step + 1, vst, lane);
+            o = attend_warp<false, true>(qloc + i * DC + hl * kHd, kc + base, vc + base, D, ar,
+                                         static_cast<size_t>(A.Lmax) * D, b0, step + 1, lane);
           }
         }
         const float on = __shfl_down_sync(0xffffffffu, o, 1);
@@ -562,12 +648,16 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
             // 32 key loads are one contiguous 2 KB run instead of 32 rows 3 KB apart
             const __nv_bfloat16* kb = A.crosskv + static_cast<size_t>(st->row0[i]) * A.crosskv_ld +
                                       (static_cast<size_t>(l) * 2 * kHeads + head) * Tm * kHd;
-            o = attend_warp<true>(qloc + i * DC + hl * kHd, kb, kb + static_cast<size_t>(kHeads) * Tm * kHd,
-                                  [&](int j) { return static_cast<size_t>(j) * kHd; }, Tm, vst, lane);
+            if (Tm <= kAttC * 32)
+              o = attend_warp<true, false>(qloc + i * DC + hl * kHd, kb, kb + static_cast<size_t>(kHeads) * Tm * kHd, kHd, nullptr, 0, 0,
+                                           Tm, lane);
+            else
+              o = attend_warp<true, true>(qloc + i * DC + hl * kHd, kb, kb + static_cast<size_t>(kHeads) * Tm * kHd, kHd, nullptr, 0, 0,
+                                          Tm, lane);
           } else {
             const __nv_bfloat16* kb = A.crosskv + static_cast<size_t>(st->row0[i]) * A.crosskv_ld + l * 2 * D + head * kHd;
             const size_t ldk = A.crosskv_ld;
-            o = attend_warp<true>(qloc + i * DC + hl * kHd, kb, kb + D, [&](int j) { return j * ldk; }, Tm, vst, lane);
+            o = attend_warp<true, true>(qloc + i * DC + hl * kHd, kb, kb + D, ldk, nullptr, 0, 0, Tm, lane);
           }
         }
         const float on = __shfl_down_sync(0xffffffffu, o, 1);
@@ -1026,6 +1116,7 @@ int fused_decoder_run(KiriHandle* h, const __nv_bfloat16* crosskv, int crosskv_l
   a.ids = ids; a.n_out = n_out; a.sum_logp = sum_logp; a.step_logp = step_logp; a.step_prob = step_prob;
   a.steps_max = steps_max_dev;
   a.timing = getenv("KIRI_DEC_TIMING") != nullptr;
+  a.prefetch = getenv("KIRI_DEC_PREFETCH") != nullptr;       // measured: no net gain (profiles/README.md), off by default
   a.beam = 1; a.bmode = 0; a.lenp = 0.0;
   a.publish = 0; a.progress = nullptr; a.stream_rule = 0; a.bm_trace = nullptr;
   if (live) { a.publish = live->publish; a.progress = live->progress; a.stream_rule = live->stream_rule; a.bm_trace = live->bm_trace; }

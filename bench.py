@@ -58,7 +58,9 @@ STAGE_FLOPS_PER_LINE = {           # algorithmic (unpadded) FLOPs of one line at
 }
 STAGE_BYTES_PER_LINE = {           # algorithmic bytes for the CUDA-core / HBM-bound stages
     "conv1": lambda Wb: 48 * Wb + 48 * Wb * 48 * 2,
-    "ctc_greedy": lambda Wb: (Wb // 4) * 204 * 4 + 4 * (Wb // 4) + 12,      # fp32 logits in, ids + stats out
+    # the frame decisions are taken in the CTC head's epilogue (no logits in HBM): what is left is the collapse stage,
+    # 8 bytes per frame in (arg-max id + probability), ids + length + confidence out
+    "ctc_greedy": lambda Wb: (Wb // 4) * 8 + 4 * (Wb // 4) + 12,
 }
 
 

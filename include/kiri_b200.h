@@ -180,6 +180,12 @@ int kiri_ctc_greedy_multi(const void* logits, int logits_dtype, int n_lines, con
                           int max_T, int C, int ld, int* ids, int* n_ids, float* conf, int* frame_ids,
                           float* frame_prob, cudaStream_t stream);
 
+/* The collapse stage alone (kiri_ocr/model.py:109-124, 366-371) for frame decisions taken in the CTC head's GEMM epilogue
+ * (kiri_encode_multi with frame_ids / frame_prob: arg-max class and its soft-max probability per token, the logits stay
+ * on chip): line b owns tokens [row0[b], row0[b] + len[b]); outputs as kiri_ctc_greedy_multi. */
+int kiri_ctc_collapse_multi(const int* frame_ids, const float* frame_prob, int n_lines, const int* row0, const int* len,
+                            int* ids, int* n_ids, float* conf, cudaStream_t stream);
+
 /* Multi-GPU exchange payload (the one collective of the path): fixed-stride int32 records
  * {n_ids, confidence bits, ids[T]} per line, built from the token-major output of kiri_ctc_greedy_multi
  * (line b's ids start at ids[mem_row0[b]]; entries beyond n_ids are zero).  records: [n_lines, 2 + T]. */
@@ -277,7 +283,11 @@ size_t kiri_encode_multi_workspace_bytes(const KiriHandle* h, const KiriGroup* g
                                          int stem_chunk);
 int kiri_encode_multi(KiriHandle* h, const KiriGroup* groups_host, int n_groups, int stem_chunk, void* workspace,
                       size_t workspace_bytes, float* mem_f32, void* mem_bf16, float* logits, float* tok_f32,
-                      const int* kv_len, cudaStream_t stream);
+                      const int* kv_len, int* frame_ids, float* frame_prob, cudaStream_t stream);
+/* frame_ids / frame_prob (nullable together, [M_total]): the CTC head's GEMM epilogue takes the per-token arg-max class
+ * (first maximum over the C real classes) and its soft-max probability straight from the accumulator
+ * (compute_ctc_confidence, kiri_ocr/model.py:355-363); with logits == NULL the logits are never written to HBM
+ * (decode_method "fast" / "accurate" need only these two; "beam" also asks for the logits). */
 
 /* ---------------------------------------------------------------- greedy attention decoder
  * Replaces beam_decode_one_batched at BEAM=1 (kiri_ocr/model.py:390-600 via core.py:560-568)

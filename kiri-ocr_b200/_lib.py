@@ -17,7 +17,7 @@ CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 KIRI_MAX_LAYERS = 8
 
 DTYPE_F32, DTYPE_BF16 = 0, 1
-EPI_BIAS_BF16, EPI_BIAS_SILU_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32, EPI_BIAS_F32, EPI_BIAS_RESID_LN = range(6)
+EPI_BIAS_BF16, EPI_BIAS_SILU_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32, EPI_BIAS_F32, EPI_BIAS_RESID_LN, EPI_CTC_STATS = range(7)
 
 vp, fp, ip = C.c_void_p, C.c_void_p, C.c_void_p      # all device pointers travel as integers
 
@@ -101,7 +101,8 @@ _SIGS = {
     "kiri_encode_workspace_bytes": (C.c_size_t, [vp, C.c_int, C.c_int, C.c_int]),
     "kiri_encode": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, vp, vp, vp, vp, vp, vp]),
     "kiri_encode_multi_workspace_bytes": (C.c_size_t, [vp, C.POINTER(KiriGroup), C.c_int, C.c_int]),
-    "kiri_encode_multi": (C.c_int, [vp, C.POINTER(KiriGroup), C.c_int, C.c_int, vp, C.c_size_t, vp, vp, vp, vp, vp, vp]),
+    "kiri_encode_multi": (C.c_int, [vp, C.POINTER(KiriGroup), C.c_int, C.c_int, vp, C.c_size_t, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "kiri_ctc_collapse_multi": (C.c_int, [vp, vp, C.c_int, vp, vp, vp, vp, vp, vp]),
     "kiri_decode_workspace_bytes": (C.c_size_t, [vp, C.c_int, C.c_int, C.c_int]),
     "kiri_decode_multi_workspace_bytes": (C.c_size_t, [vp, C.c_int, C.c_longlong, C.c_int]),
     "kiri_decode_greedy_multi": (C.c_int, [vp, vp, C.c_longlong, vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.POINTER(KiriDecodeParams),

@@ -274,13 +274,15 @@ extern "C" int kiri_encode(KiriHandle* h, const uint8_t* planes_u8, int B, int W
   KIRI_REQUIRE(h && planes_u8 && workspace, "kiri_encode: null pointer");
   KiriGroup g = {planes_u8, B, Wb};
   return kiri_encode_multi(h, &g, 1, stem_chunk, workspace, workspace_bytes, mem_f32, mem_bf16, logits, tok_f32, kv_len,
-                           stream);
+                           nullptr, nullptr, stream);
 }
 
 extern "C" int kiri_encode_multi(KiriHandle* h, const KiriGroup* groups, int n_groups, int stem_chunk,
                                  void* workspace, size_t workspace_bytes, float* mem_f32, void* mem_bf16,
-                                 float* logits, float* tok_f32, const int* kv_len, cudaStream_t stream) {
+                                 float* logits, float* tok_f32, const int* kv_len, int* frame_ids, float* frame_prob,
+                                 cudaStream_t stream) {
   KIRI_REQUIRE(h && groups && workspace && n_groups > 0, "kiri_encode_multi: null pointer");
+  KIRI_REQUIRE((frame_ids == nullptr) == (frame_prob == nullptr), "kiri_encode_multi: frame_ids and frame_prob go together");
   const KiriDims& d = h->d;
   const KiriWeights& w = h->w;
   for (int g = 0; g < n_groups; ++g) {
@@ -384,8 +386,23 @@ extern "C" int kiri_encode_multi(KiriHandle* h, const KiriGroup* groups, int n_g
   { ProfScope ps(PS_LN_FINAL, stream);
     KIRI_TRY(kiri_layernorm(x, M, D, w.enc_ln_g, w.enc_ln_b, mem_f32, mem_b, w.ctc_ln_g, w.ctc_ln_b, a, stream)); }
   ProfScope ps_head(PS_CTC_HEAD, stream);
+  const int Cp = (d.ctc_classes + 15) / 16 * 16;
+  if (frame_ids && Cp <= 256) {
+    // frame decisions in the GEMM epilogue; the logits are stored only when the caller wants them (beam rescoring)
+    GemmLaunch L;
+    memset(&L, 0, sizeof(L));
+    L.a = a; L.w = w.ctc_w;
+    L.NB = 1; L.IH = 1; L.IW = M; L.Cin = D; L.OH = 1; L.OW = M;
+    L.sw = 1; L.sh = 1; L.pad = 0; L.kw = 1; L.kh = 1;
+    L.N = Cp; L.epi = EPI_CTC_STATS;
+    L.e.out = logits ? static_cast<void*>(logits) : static_cast<void*>(base);   // (any aligned base: the tensor map of a store that never happens)
+    L.e.bias = w.ctc_b; L.e.ldc = Cp; L.e.n_valid = Cp;
+    L.e.stat_id = frame_ids; L.e.stat_p = frame_prob; L.e.n_stat = d.ctc_classes; L.e.store_out = logits ? 1 : 0;
+    KIRI_TRY(launch_gemm_tc(L, stream));
+    return 0;
+  }
+  KIRI_REQUIRE(!frame_ids, "kiri_encode_multi: frame decisions in the head epilogue need at most 256 CTC classes (have %d)", Cp);
   if (logits)
-    KIRI_TRY(gemm_call(a, w.ctc_w, w.ctc_b, M, (d.ctc_classes + 15) / 16 * 16, D, EPI_BIAS_F32, logits, nullptr, nullptr, nullptr,
-                       nullptr, stream));
+    KIRI_TRY(gemm_call(a, w.ctc_w, w.ctc_b, M, Cp, D, EPI_BIAS_F32, logits, nullptr, nullptr, nullptr, nullptr, stream));
   return 0;
 }

@@ -171,9 +171,65 @@ ctc_greedy_kernel(const T* __restrict__ logits, int Tn, int C, int ld, int* __re
   }
 }
 
+// Collapse stage alone, for frame decisions that were taken in the CTC head's GEMM epilogue (EPI_CTC_STATS: the logits
+// never reach HBM in fast mode): per line keep frame t iff id[t] != id[t-1] and id[t] >= 2, confidence = mean of the
+// frames' arg-max probabilities in a fixed summation order.
+__global__ void __launch_bounds__(128)
+ctc_collapse_kernel(const int* __restrict__ frame_ids, const float* __restrict__ frame_prob, const int* __restrict__ row0,
+                    const int* __restrict__ lens, int* __restrict__ ids, int* __restrict__ n_ids, float* __restrict__ conf) {
+  __shared__ float s_psum[4];
+  __shared__ int s_cnt[4];
+  const int line = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
+  pdl_wait();
+  const size_t r0 = static_cast<size_t>(row0[line]);
+  const int Tn = lens[line];
+  float psum = 0.f;
+  int base_out = 0;
+  for (int t0 = 0; t0 < Tn; t0 += 128) {
+    const int t = t0 + threadIdx.x;
+    bool keep = false;
+    int id = 0;
+    if (t < Tn) {
+      id = __ldg(frame_ids + r0 + t);
+      psum += __ldg(frame_prob + r0 + t);
+      keep = (id >= 2) && (t == 0 || id != __ldg(frame_ids + r0 + t - 1));
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_cnt[warp] = __popc(bal);
+    __syncthreads();
+    int woff = 0, total = 0;
+#pragma unroll
+    for (int wi = 0; wi < 4; ++wi) {
+      if (wi < warp) woff += s_cnt[wi];
+      total += s_cnt[wi];
+    }
+    if (keep) ids[r0 + base_out + woff + __popc(bal & ((1u << lane) - 1))] = id;
+    base_out += total;
+    __syncthreads();
+  }
+  psum = warp_sum(psum);
+  if (lane == 0) s_psum[warp] = psum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    conf[line] = ((s_psum[0] + s_psum[1]) + (s_psum[2] + s_psum[3])) / static_cast<float>(Tn);
+    n_ids[line] = base_out;
+  }
+}
+
 }  // namespace kiri
 
 using namespace kiri;
+
+extern "C" int kiri_ctc_collapse_multi(const int* frame_ids, const float* frame_prob, int n_lines, const int* row0, const int* len,
+                                       int* ids, int* n_ids, float* conf, cudaStream_t stream) {
+  KIRI_REQUIRE(frame_ids && frame_prob && row0 && len && ids && n_ids && conf, "kiri_ctc_collapse_multi: null pointer");
+  if (n_lines <= 0) return 0;
+  ProfScope ps(PS_CTC_GREEDY, stream);
+  KIRI_CHECK_CUDA(launch_pdl(ctc_collapse_kernel, dim3(n_lines), dim3(128), 0, stream, frame_ids, frame_prob, row0, len, ids, n_ids, conf));
+  return 0;
+}
 
 extern "C" int kiri_ctc_greedy(const void* logits, int logits_dtype, int n_lines, int T, int C, int ld,
                                int* ids, int* n_ids, float* conf, int* frame_ids, float* frame_prob,

@@ -74,7 +74,7 @@ gemm_tc_kernel(const __grid_constant__ ProblemSet P, const __grid_constant__ CUt
   constexpr int kATileBytes = kTileM * kChunkBytes;
   constexpr uint32_t kSBO = 8 * kChunkBytes;                 // 8-row group pitch
   constexpr uint64_t kLayout = (KC == 64) ? UMMA_LAYOUT_SW128 : UMMA_LAYOUT_SW64;
-  constexpr bool kF32Out = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_F32 || EPI == EPI_BIAS_RESID_LN);
+  constexpr bool kF32Out = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_F32 || EPI == EPI_BIAS_RESID_LN || EPI == EPI_CTC_STATS);
   constexpr bool kResid = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_RESID_LN);
   constexpr int kNBuf = kResid ? 4 : ((BSTAT || KC == 32) ? 1 : 2);   // staging tiles per epilogue warp (KC = 32: a third 54 KB stage instead)
   // carve: [resident B] | [stages][A: CPS chunk tiles][B: CPS chunk tiles] | staging | barriers
@@ -471,6 +471,9 @@ gemm_tc_kernel(const __grid_constant__ ProblemSet P, const __grid_constant__ CUt
       } else {
         constexpr int kCols = kF32Out ? 32 : 64;                 // columns per 128-byte staging row
         const int nch = (bn + kCols - 1) / kCols;
+        // EPI_CTC_STATS: running (max, first arg-max, sum exp) of this thread's row over its column chunks
+        float st_m = -INFINITY, st_s = 0.f;
+        int st_a = 0x7fffffff;
         for (int ch = half; ch < nch; ch += 2) {
           const int c0 = ch * kCols;
           uint32_t ra[32], rb2[32];
@@ -481,6 +484,28 @@ gemm_tc_kernel(const __grid_constant__ ProblemSet P, const __grid_constant__ CUt
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
+          }
+          if (EPI == EPI_CTC_STATS) {
+            // logits of this chunk (the same fp32 values the store path writes); the head's padding columns take no part
+            float cm = -INFINITY;
+            int ca = 0x7fffffff;
+            float lv[32];
+#pragma unroll
+            for (int t = 0; t < 32; ++t) {
+              const int col = col_base + c0 + t;
+              lv[t] = (col < e.n_stat) ? __uint_as_float(ra[t]) + sbias[c0 + t] : -INFINITY;
+              if (lv[t] > cm) { cm = lv[t]; ca = col; }          // ascending columns: the first maximum wins
+            }
+            const float nm = fmaxf(st_m, cm);
+            if (nm > -INFINITY) {
+              float ssum = 0.f;
+#pragma unroll
+              for (int t = 0; t < 32; ++t) ssum += __expf(lv[t] - nm);      // exp(-inf) = 0 in the padding
+              st_s = st_s * __expf(st_m - nm) + ssum;
+              if (cm > st_m) st_a = ca;                          // strict: an earlier chunk keeps a tie
+              st_m = nm;
+            }
+            if (!e.store_out) { ++stg_cnt; continue; }
           }
           uint8_t* ob = bufs + (stg_cnt % kNBuf) * kBufBytes;
           if (etime) te0 = clock64();
@@ -526,6 +551,24 @@ gemm_tc_kernel(const __grid_constant__ ProblemSet P, const __grid_constant__ CUt
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
+        }
+        if (EPI == EPI_CTC_STATS) {
+          // merge the two warps that share a TMEM lane quarter (they took the 32-column chunks of the row in turn);
+          // on equal maxima the lower class index wins (torch.argmax returns the first maximum)
+          const int trow = q * 32 + lane;
+          bars->xch[0][half][trow] = st_m;
+          bars->xch[1][half][trow] = st_s;
+          reinterpret_cast<int*>(bars->ln_g)[half * 128 + trow] = st_a;
+          asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+          if (half == 0 && valid) {
+            const float om = bars->xch[0][1][trow], os = bars->xch[1][1][trow];
+            const int oa = reinterpret_cast<const int*>(bars->ln_g)[128 + trow];
+            const float m = fmaxf(st_m, om);
+            const float stot = st_s * __expf(st_m - m) + os * __expf(om - m);
+            e.stat_id[row0 + lane] = (om > st_m || (om == st_m && oa < st_a)) ? oa : st_a;
+            e.stat_p[row0 + lane] = 1.0f / stot;
+          }
+          asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");      // xch may be rewritten by the next tile
         }
       }
     }
@@ -709,7 +752,7 @@ static int prep_problem(const GemmLaunch& L, bool is_gemm, int KC, bool a_multi,
   *cps = CPS;
   KIRI_REQUIRE(g.SEG * g.sw <= 256 && g.R * g.sh <= 256, "gemm_tc: TMA box too large");
   KIRI_REQUIRE(L.e.n_valid == L.N, "gemm_tc: n_valid must equal N");
-  const bool f32_out = (L.epi == EPI_BIAS_F32 || L.epi == EPI_BIAS_RESID_F32 || L.epi == EPI_BIAS_RESID_LN);
+  const bool f32_out = (L.epi == EPI_BIAS_F32 || L.epi == EPI_BIAS_RESID_F32 || L.epi == EPI_BIAS_RESID_LN || L.epi == EPI_CTC_STATS);
   KIRI_REQUIRE((static_cast<long long>(L.e.ldc) * (f32_out ? 4 : 2)) % 16 == 0,
                "gemm_tc: output row pitch must be a multiple of 16 bytes (ldc=%d)", L.e.ldc);
   KIRI_REQUIRE((reinterpret_cast<uintptr_t>(L.e.out) & 15) == 0, "gemm_tc: output must be 16-byte aligned");
@@ -835,6 +878,10 @@ int launch_gemm_tc_multi(const GemmLaunch* Ls, int n, cudaStream_t stream) {
         case EPI_BIAS_RESID_F32: KIRI_LAUNCH_NB(32, 1, EPI_BIAS_RESID_F32); break;
         case EPI_BIAS_F32: KIRI_LAUNCH(64, 1, EPI_BIAS_F32); break;
         case EPI_BIAS_RESID_LN: KIRI_LAUNCH_NB(32, 1, EPI_BIAS_RESID_LN); break;
+        case EPI_CTC_STATS:
+          KIRI_REQUIRE(num_n_tiles == 1 && L.e.stat_id && L.e.stat_p && L.e.n_stat > 0 && L.e.n_stat <= L.N,
+                       "gemm_tc: the CTC statistics epilogue needs N <= 256, stat_id, stat_p and 0 < n_stat <= N");
+          KIRI_LAUNCH(64, 1, EPI_CTC_STATS); break;
         default: KIRI_REQUIRE(false, "gemm_tc: unknown epilogue %d", L.epi);
       }
     }

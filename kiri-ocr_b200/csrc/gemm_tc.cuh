@@ -27,6 +27,8 @@ enum EpiMode : int {
   EPI_BIAS_RESID_F32 = 3,  // out_f32  = resid_f32 + acc + bias    (attention out-proj, FFN second)
   EPI_BIAS_F32 = 4,        // out_f32  = acc + bias                (CTC / decoder heads)
   EPI_BIAS_RESID_LN = 5,   // out_f32  = resid + acc + bias; out2_bf16 = LayerNorm(out_f32), N == 256
+  EPI_CTC_STATS = 6,       // logits = acc + bias (fp32, stored only if out != null); per row: first arg-max over the
+                           // n_stat valid classes and 1 / sum exp(logit - max)  (the CTC head, N <= 256: one n-tile)
 };
 
 struct ConvGeom {
@@ -52,6 +54,10 @@ struct EpiParams {
   const float* ln_b;
   void* out2;          // EPI_BIAS_RESID_LN: bf16 [rows, 256]
   int timing;          // debug: accumulate role-level cycle counts of CTA 0 (set by the launcher)
+  int* stat_id;        // EPI_CTC_STATS: [rows] arg-max class per row
+  float* stat_p;       // EPI_CTC_STATS: [rows] soft-max probability of that class
+  int n_stat;          // EPI_CTC_STATS: classes that take part (columns >= n_stat are head padding)
+  int store_out;       // EPI_CTC_STATS: 1 = also store the logits
 };
 
 // Host launcher (gemm_tc.cu).  A is described by an NHWC activation [NB, IH, IW, Cin]

@@ -316,10 +316,13 @@ class BatchedRecognizer:
         return n
 
     def encode_multi(self, planes_list: Sequence[torch.Tensor], want_mem_f32: bool = False, want_tokens: bool = False,
-                     kv_len: Optional[torch.Tensor] = None, want_logits: bool = True, slot: Optional[str] = None):
+                     kv_len: Optional[torch.Tensor] = None, want_logits: bool = True, slot: Optional[str] = None,
+                     stats: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
         """Several width groups ([B_g, IMG_H, Wb_g] uint8 each) in one call: per-group stems, ONE pass
         of the encoder / CTC head over the concatenated token stream.  Returns the outputs token-major
-        ([M, ...], M = sum B_g * Wb_g / 4) plus ``rows`` = [(row0, B_g, T_g)] per group."""
+        ([M, ...], M = sum B_g * Wb_g / 4) plus ``rows`` = [(row0, B_g, T_g)] per group.  ``stats`` = (frame_ids int32
+        [M], frame_prob fp32 [M]): the CTC head's epilogue takes the per-token arg-max and its probability; with
+        ``want_logits=False`` the logits then never reach HBM."""
         D = self.cfg.ENC_DIM
         n = len(planes_list)
         garr = (_lib.KiriGroup * n)()
@@ -347,9 +350,10 @@ class BatchedRecognizer:
         _lib.check(self.lib.kiri_encode_multi(self.handle, garr, n, self.stem_chunk, ws.data_ptr(), need,
                                               _lib.ptr(out.get("mem_f32")), out["mem_bf16"].data_ptr(),
                                               _lib.ptr(out.get("logits")), _lib.ptr(out.get("tokens")), _lib.ptr(kv_len),
+                                              _lib.ptr(stats[0]) if stats else 0, _lib.ptr(stats[1]) if stats else 0,
                                               _lib.stream_ptr()), "kiri_encode_multi")
         self.launches += self._stem_launches([(B, 4 * T) for _, B, T in rows]) + 1             # stem + pool
-        self.launches += self._layer_launches * self.pw.enc_layers + 1 + (1 if want_logits else 0)
+        self.launches += self._layer_launches * self.pw.enc_layers + 1 + (1 if (want_logits or stats) else 0)
         return out
 
     def decode_greedy_multi(self, mem_bf16: torch.Tensor, mem_row0: torch.Tensor, mem_len: torch.Tensor,
@@ -478,15 +482,17 @@ class BatchedRecognizer:
                                                  prep["planes_all"].data_ptr(), 0, prep["sums"].data_ptr(), _lib.stream_ptr()),
                    "kiri_preprocess_pack")
         self.launches += 2
-        enc = self.encode_multi([g["planes"] for g in prep["groups"]], kv_len=prep["kv_len"])
         M, L = prep["M"], prep["n_lines"]
+        fid = torch.empty(M, dtype=torch.int32, device=self.device)
+        fpr = torch.empty(M, dtype=torch.float32, device=self.device)
+        # frame decisions come out of the CTC head's epilogue: no logits in HBM for "ctc" / "decoder"
+        enc = self.encode_multi([g["planes"] for g in prep["groups"]], kv_len=prep["kv_len"], want_logits=False, stats=(fid, fpr))
         ids = torch.empty(M, dtype=torch.int32, device=self.device)
         n_ids = torch.empty(L, dtype=torch.int32, device=self.device)
         conf = torch.empty(L, dtype=torch.float32, device=self.device)
-        _lib.check(self.lib.kiri_ctc_greedy_multi(enc["logits"].data_ptr(), _lib.DTYPE_F32, L, prep["mem_row0"].data_ptr(),
-                                                  prep["mem_len"].data_ptr(), prep["T_max"], self.pw.C, self.pw.Cp,
-                                                  ids.data_ptr(), n_ids.data_ptr(), conf.data_ptr(), 0, 0, _lib.stream_ptr()),
-                   "kiri_ctc_greedy_multi")
+        _lib.check(self.lib.kiri_ctc_collapse_multi(fid.data_ptr(), fpr.data_ptr(), L, prep["mem_row0"].data_ptr(),
+                                                    prep["mem_len"].data_ptr(), ids.data_ptr(), n_ids.data_ptr(), conf.data_ptr(),
+                                                    _lib.stream_ptr()), "kiri_ctc_collapse_multi")
         self.launches += 1
         outs = [(ids, n_ids, conf)]
         if method != "decoder":
@@ -649,26 +655,26 @@ class BatchedRecognizer:
             self._src_free[slot].record()
         kv_len = dmeta[kvo:kvo + n_lines] if self.width_mode == "masked" else None
         marks.append(_time.perf_counter())                   # [4] preprocess launched
-        enc = self.encode_multi(planes_list, kv_len=kv_len, slot=sl)
-        marks.append(_time.perf_counter())                   # [5] encoder launched
-        # ---- CTC greedy into ONE packed result buffer: ids[M] | n_ids[L] | conf[L] | frames | decoder block
+        # ---- ONE packed result buffer: ids[M] | n_ids[L] | conf[L] | decoder block | frame ids[M] | frame probs[M]
+        # (the frame decisions are taken in the CTC head's GEMM epilogue; they are downloaded only for CTC streaming)
         want_frames = streaming and method == "ctc"
-        T_max = max(T for _, _, T in enc["rows"])
+        T_max = max(Wb // 4 for Wb, _ in groups)
         Lcap = self.static_step_cap(T_max) if (method == "decoder" or live) else 0
         LL = n_lines * Lcap
         dec_words = (3 * LL if streaming else 2 * LL) + 2 * n_lines if (method == "decoder" and not live) else 0
-        ctc_words = M + 2 * n_lines + (2 * M if want_frames else 0)
-        res_words = ctc_words + dec_words
-        dres = self._device("_dres" + sl, res_words, torch.int32)
+        ctc_words = M + 2 * n_lines
+        head_words = ctc_words + dec_words
+        res_words = head_words + (2 * M if want_frames else 0)
+        dres = self._device("_dres" + sl, head_words + 2 * M, torch.int32)
         ids_all, n_all = dres[:M], dres[M:M + n_lines]
         conf_all = dres[M + n_lines:M + 2 * n_lines].view(torch.float32)
-        fid_all = dres[M + 2 * n_lines:2 * M + 2 * n_lines] if want_frames else None
-        fpr_all = dres[2 * M + 2 * n_lines:3 * M + 2 * n_lines].view(torch.float32) if want_frames else None
-        _lib.check(self.lib.kiri_ctc_greedy_multi(enc["logits"].data_ptr(), _lib.DTYPE_F32, n_lines,
-                                                  dmeta[r0o:].data_ptr(), dmeta[mlo:].data_ptr(), T_max, self.pw.C, Cp,
-                                                  ids_all.data_ptr(), n_all.data_ptr(), conf_all.data_ptr(),
-                                                  _lib.ptr(fid_all), _lib.ptr(fpr_all), _lib.stream_ptr()),
-                   "kiri_ctc_greedy_multi")
+        fid_all = dres[head_words:head_words + M]
+        fpr_all = dres[head_words + M:head_words + 2 * M].view(torch.float32)
+        enc = self.encode_multi(planes_list, kv_len=kv_len, slot=sl, want_logits=(method == "beam"), stats=(fid_all, fpr_all))
+        marks.append(_time.perf_counter())                   # [5] encoder launched
+        _lib.check(self.lib.kiri_ctc_collapse_multi(fid_all.data_ptr(), fpr_all.data_ptr(), n_lines, dmeta[r0o:].data_ptr(),
+                                                    dmeta[mlo:].data_ptr(), ids_all.data_ptr(), n_all.data_ptr(),
+                                                    conf_all.data_ptr(), _lib.stream_ptr()), "kiri_ctc_collapse_multi")
         self.launches += 1
         mem_row0, mem_len = dmeta[r0o:r0o + n_lines], dmeta[mlo:mlo + n_lines]
         if live:
@@ -676,7 +682,7 @@ class BatchedRecognizer:
         elif method == "decoder":
             # the greedy decode is enqueued right behind the CTC kernel: its step bounds come from the device-resident
             # length estimates, so no host round trip separates the encoder from the decoder
-            dd = dres[ctc_words:]
+            dd = dres[ctc_words:head_words]
             d_ids, n_out = dd[:LL].view(n_lines, Lcap), dd[LL:LL + n_lines]
             sum_lp = dd[LL + n_lines:LL + 2 * n_lines].view(torch.float32)
             slp = dd[LL + 2 * n_lines:2 * LL + 2 * n_lines].view(torch.float32).view(n_lines, Lcap)
@@ -688,7 +694,8 @@ class BatchedRecognizer:
         done = torch.cuda.Event()
         done.record()
         marks.append(_time.perf_counter())                   # [6] CTC (+ decode) + download enqueued
-        tk.update(marks=marks, done=done, hres=hres, res_words=res_words, ctc_words=ctc_words, Lcap=Lcap, M=M, n_lines=n_lines,
+        tk.update(marks=marks, done=done, hres=hres, res_words=res_words, ctc_words=ctc_words, head_words=head_words, Lcap=Lcap, M=M,
+                  n_lines=n_lines,
                   rows=enc["rows"], T_max=T_max,
                   order=np.concatenate([g[1][0] for g in groups]),     # line index of every concatenated slot
                   want_frames=want_frames, enc=enc, n_all=n_all, mem_row0=mem_row0, mem_len=mem_len,
@@ -725,8 +732,9 @@ class BatchedRecognizer:
             pos = 0
             for (r0, B, T) in tk["rows"]:
                 ids_h = hr[r0:r0 + B * T].reshape(B, T)
-                f_h = hr[M + 2 * n_lines + r0:M + 2 * n_lines + r0 + B * T].reshape(B, T) if want_frames else None
-                p_h = hr[2 * M + 2 * n_lines + r0:2 * M + 2 * n_lines + r0 + B * T].view(np.float32).reshape(B, T) if want_frames else None
+                hw = tk["head_words"]
+                f_h = hr[hw + r0:hw + r0 + B * T].reshape(B, T) if want_frames else None
+                p_h = hr[hw + M + r0:hw + M + r0 + B * T].view(np.float32).reshape(B, T) if want_frames else None
                 for j in range(B):
                     k = pos + j
                     cf = float(c_h[k])
@@ -740,7 +748,7 @@ class BatchedRecognizer:
             return self._beam_finish(enc, tk["mem_row0"], tk["mem_len"], tk["n_all"], len_h, c_h, order, results)
         # ---- greedy attention decoder: everything is already on the host
         Lcap, LL = tk["Lcap"], n_lines * tk["Lcap"]
-        hd = hr[tk["ctc_words"]:]
+        hd = hr[tk["ctc_words"]:tk["head_words"]]
         ids_h, no_h = hd[:LL].reshape(n_lines, Lcap), hd[LL:LL + n_lines]
         slp_h = hd[LL + 2 * n_lines:2 * LL + 2 * n_lines].view(np.float32).reshape(n_lines, Lcap)
         spr_h = hd[2 * LL + 2 * n_lines:3 * LL + 2 * n_lines].view(np.float32).reshape(n_lines, Lcap) if streaming else None
@@ -875,7 +883,7 @@ class BatchedRecognizer:
         dres = tk["keep"][3]
         if tk["method"] == "decoder":
             Lcap, LL = tk["Lcap"], n * tk["Lcap"]
-            dd = dres[tk["ctc_words"]:]
+            dd = dres[tk["ctc_words"]:tk["head_words"]]
             k = min(T, Lcap)
             rec[:n, 0] = dd[LL:LL + n]
             rec[:n, 1] = dd[LL + n:LL + 2 * n]

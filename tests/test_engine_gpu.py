@@ -223,3 +223,54 @@ def test_full_size_batch_is_deterministic_and_composition_independent(engines):
         assert np.array_equal(ra.ids, rb.ids) and ra.confidence == rb.confidence and ra.text == rb.text
     for rs, ra in zip(sub, a[::4]):
         assert np.array_equal(rs.ids, ra.ids) and rs.confidence == ra.confidence
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["hard", "blank"])
+def test_ctc_head_epilogue_statistics_equal_the_logits(engines, name):
+    """The CTC head's GEMM epilogue takes every token's arg-max class and its soft-max probability from the accumulator
+    (fast mode never writes the logits).  With the logits requested as well they must be the SAME fp32 values, so:
+    the arg-max is exactly torch's first maximum over the C real classes (the head's zero padding never wins), the
+    probability matches soft-max to fp32 rounding, the collapse stage equals the stand-alone fused CTC kernel, and
+    running without the logits changes nothing."""
+    eng, sd = engines(name, "bucketed")
+    crops = FX.make_line_crops(40, seed=31)
+    buf, ent = eng.pack_crops(crops)
+    planes_list = []
+    for Wb, (idx, descs, smem, n_strips) in eng.plan(ent).items():
+        planes_list.append(eng.preprocess(buf.cuda(), descs, Wb, smem, n_strips)[0])
+    M = sum(p.shape[0] * p.shape[2] // 4 for p in planes_list)
+    outs = []
+    for want_logits in (True, False):
+        fid = torch.full((M,), -1, dtype=torch.int32, device="cuda")
+        fpr = torch.full((M,), -1.0, dtype=torch.float32, device="cuda")
+        enc = eng.encode_multi(planes_list, want_logits=want_logits, stats=(fid, fpr))
+        torch.cuda.synchronize()
+        outs.append((fid.clone(), fpr.clone(), enc))
+    (fid, fpr, enc), (fid2, fpr2, _) = outs
+    assert torch.equal(fid, fid2) and torch.equal(fpr, fpr2)
+    lg = enc["logits"][:, :204]
+    assert torch.equal(fid.long(), lg.argmax(dim=1))
+    sm = torch.softmax(lg.double(), dim=1).max(dim=1).values
+    assert float((fpr.double() - sm).abs().max()) < 2e-6
+    assert float(enc["logits"][:, 204:].abs().max()) == 0.0           # head padding: zero weights and bias
+    # collapse stage vs the stand-alone fused kernel on the same logits
+    rows = enc["rows"]
+    r0 = torch.tensor([r + j * T for r, B, T in rows for j in range(B)], dtype=torch.int32, device="cuda")
+    ln = torch.tensor([T for r, B, T in rows for j in range(B)], dtype=torch.int32, device="cuda")
+    L = int(r0.numel())
+    ids_a, n_a, c_a = (torch.zeros(M, dtype=torch.int32, device="cuda"), torch.zeros(L, dtype=torch.int32, device="cuda"),
+                       torch.zeros(L, device="cuda"))
+    ids_b, n_b, c_b = torch.zeros_like(ids_a), torch.zeros_like(n_a), torch.zeros_like(c_a)
+    _lib.check(eng.lib.kiri_ctc_collapse_multi(fid.data_ptr(), fpr.data_ptr(), L, r0.data_ptr(), ln.data_ptr(), ids_a.data_ptr(),
+                                               n_a.data_ptr(), c_a.data_ptr(), _lib.stream_ptr()))
+    _lib.check(eng.lib.kiri_ctc_greedy_multi(enc["logits"].data_ptr(), _lib.DTYPE_F32, L, r0.data_ptr(), ln.data_ptr(), 160, 204,
+                                             eng.pw.Cp, ids_b.data_ptr(), n_b.data_ptr(), c_b.data_ptr(), 0, 0, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(n_a, n_b)
+    for i in range(L):
+        a, k = int(r0[i]), int(n_a[i])
+        assert torch.equal(ids_a[a:a + k], ids_b[a:a + k]), i
+    assert float((c_a - c_b).abs().max()) < 1e-6
+    if name == "blank":
+        assert int(n_a.max()) == 0

@@ -175,7 +175,7 @@ extern "C" int kiri_create(const KiriDims* dims, const KiriWeights* weights, Kir
   h->w.conv1_b_host = h->conv1_b;
   h->fused = nullptr;
   h->enc_consts = nullptr;
-  if (dims->enc_ff % 128 == 0 && dims->enc_ff <= 1024 && dims->enc_layers > 0 && weights->enc[0].wo) {
+  if (dims->enc_ff % 256 == 0 && dims->enc_ff <= 1024 && dims->enc_layers > 0 && weights->enc[0].wo) {
     h->enc_consts = new (std::nothrow) EbConst[dims->enc_layers];
     KIRI_REQUIRE(h->enc_consts, "kiri_create: out of host memory");
     for (int l = 0; l < dims->enc_layers; ++l) {

@@ -14,9 +14,13 @@
 //
 // Roles (608 threads): warps 0-15 epilogue (thread = one tile row x one column quarter), warps 16-17 TMA
 // producers (alternate ring units), warp 18 MMA issuer + TMEM owner.
-// TMEM: X = columns [0,256) (out-proj accumulator, then x + b2 + FFN), H[2] = 2 x 128 columns (a pair of hidden chunks).
-// Shared memory (227 KB): ring 96 KB | A2 64 KB | hidden chunk 2 x 16 KB | staging 32 KB; the last three
-// double as the per-warp 8 KB landing zone of the fp32 residual tile / staging of the x and a stores.
+// TMEM: X = columns [0,256) (out-proj accumulator, then x + b2 + FFN), H = columns [256,512): one GROUP of 256 hidden
+// columns.  Every MMA of the kernel is M = 128, N = 256: the tensor pipe's cost per instruction has a large part that
+// does not depend on N (tools/mma_rate.cu, profiles/r02_mma_rate.txt: 168 cycles at N = 256, 124 at N = 128, 117 at
+// N = 96 for K = 16), so round 1's pairs of 64-column hidden chunks (N = 128, 128 MMAs per tile for the first FFN GEMM)
+// cost 15.9 k tensor cycles per tile where 64 N = 256 instructions cost 10.7 k.
+// Shared memory (227 KB): ring 96 KB | A2 64 KB | hidden group 64 KB (bf16 A operand of the second GEMM); A2 and the
+// hidden group double as the per-warp 8 KB landing zone of the fp32 residual tile / staging of the x and a stores.
 #include "gemm_tc.cuh"
 #include "internal.cuh"
 
@@ -29,7 +33,7 @@ constexpr int kEbEpiWarps = 16, kEbProdWarps = 2;
 constexpr int kEbProdWarp0 = kEbEpiWarps, kEbMmaWarp = kEbEpiWarps + kEbProdWarps;
 constexpr int kEbThreads = (kEbEpiWarps + kEbProdWarps + 1) * 32;
 constexpr int kSlotBytes = 32768, kSlots = 3;
-constexpr int kA2Bytes = 65536, kHBytes = 16384, kStgBytes = 32768;
+constexpr int kA2Bytes = 65536, kHBytes = 65536;
 constexpr int kScratchOff = kSlots * kSlotBytes;                 // A2 | H[2] | staging = 128 KB
 constexpr int kHOff = kScratchOff + kA2Bytes;
 constexpr int kBarOff = kScratchOff + 131072;
@@ -38,11 +42,10 @@ constexpr int kXCol = 0, kHCol = 256;
 struct __align__(16) EbBars {
   uint64_t full[kSlots], empty[kSlots];
   uint64_t g1_full, a2_ready, x_full, x_empty;
-  uint64_t acc2_full[2], acc2_empty[2], h_full[2], h_empty[2];
+  uint64_t acc2_full, acc2_empty, h_full, h_empty;
   uint64_t res_full[kEbEpiWarps][2];
   uint32_t tmem_base;
   uint32_t pad[3];
-  float xch[4][128];                 // LayerNorm partial sums: [column quarter][tile row]
 };
 
 // Biases and LayerNorm affines travel BY VALUE in the kernel parameters (constant bank): the epilogue threads
@@ -51,7 +54,7 @@ struct __align__(16) EbBars {
 struct EbParams {
   EbConst c;
   int has_ln_out;                                    // 0: no LayerNorm output (last layer)
-  int M, n_tiles, nC;                                // tokens, 128-token tiles, hidden chunks of 64
+  int M, n_tiles, nG;                                // tokens, 128-token tiles, hidden GROUPS of 256
   int timing;
 };
 
@@ -80,7 +83,7 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const int nC = p.nC;
+  const int nG = p.nG;
 
   if (warp == kEbProdWarp0 && lane == 0) {
     for (int s = 0; s < kSlots; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
@@ -88,12 +91,10 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
     mbar_init(&bars->a2_ready, kEbEpiWarps);
     mbar_init(&bars->x_full, 1);
     mbar_init(&bars->x_empty, kEbEpiWarps);
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&bars->acc2_full[b], 1);
-      mbar_init(&bars->acc2_empty[b], 2 * kEbEpiWarps);      // every warp arrives once per hidden chunk of the pair
-      mbar_init(&bars->h_full[b], kEbEpiWarps);
-      mbar_init(&bars->h_empty[b], 1);
-    }
+    mbar_init(&bars->acc2_full, 1);
+    mbar_init(&bars->acc2_empty, kEbEpiWarps);
+    mbar_init(&bars->h_full, kEbEpiWarps);
+    mbar_init(&bars->h_empty, 1);
     for (int w = 0; w < kEbEpiWarps; ++w)
       for (int c = 0; c < 2; ++c) mbar_init(&bars->res_full[w][c], 1);
     fence_mbar_init();
@@ -113,10 +114,11 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
 
   if (warp >= kEbProdWarp0 && warp < kEbProdWarp0 + kEbProdWarps) {
     // ============================ TMA producers ============================
-    // Ring units per tile, in the order the MMA warp consumes them:
-    //   o_0 Wo_0 o_1 Wo_1 o_2 Wo_2 o_3 Wo_3 | W1_0 W1_1 W2_0 W1_2 W2_1 ... W1_{nC-1} W2_{nC-2} W2_{nC-1}
+    // Ring units per tile (32 KB each, except the 16 KB o chunks), in the order the MMA warp consumes them:
+    //   o_0 Wo_0 o_1 Wo_1 o_2 Wo_2 o_3 Wo_3 | W1(0,0..3) | W1(1,0..3) W2(0..3) | W1(2,0..3) W2(4..7) | ... | W2(4nG-4 .. 4nG-1)
+    //   W1(g,k) = rows [256g, 256g+256) of W1, K chunk k (64 wide);  W2(c) = all 256 rows of W2, K chunk c (64 hidden columns)
     const int pw = warp - kEbProdWarp0;
-    const int units = 8 + 2 * nC;
+    const int units = 8 + 8 * nG;
     int slot = 0, turn = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -136,25 +138,19 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
                 tma_load_3d(dst, &tmWo, fb, 0, j, 0);
               }
             } else {
-              // FFN units: W1a_0 W1b_0 | W1a_1 W1b_1 W2_0 W2_1 | W1a_2 W1b_2 W2_2 W2_3 | ... | W2_{nC-2} W2_{nC-1}
-              //   W1a_p / W1b_p = rows [128p, 128p+128) of W1, K halves (two 64-wide K chunks each): the first GEMM runs
-              //   in PAIRS of hidden chunks (N = 128: an N = 64 MMA re-reads its 4 KB A slice for half the columns)
-              const int m = n - 8, nP = nC >> 1;
-              int idx;
+              // m-th FFN unit: blocks of 8 = W1 group (g+1) then W2 group g, after the leading W1 group 0
+              const int m = n - 8;
               bool is_w1;
-              if (m < 2) { is_w1 = true; idx = m; }
+              int g, k;
+              if (m < 4) { is_w1 = true; g = 0; k = m; }
               else {
-                const int q = m - 2, pp = q >> 2, r = q & 3;
-                if (pp < nP - 1 && r < 2) { is_w1 = true; idx = 2 * (pp + 1) + r; }
-                else { is_w1 = false; idx = 2 * pp + (pp < nP - 1 ? r - 2 : r); }
+                const int q = m - 4, blk = q >> 3, r = q & 7;
+                if (blk < nG - 1) { is_w1 = r < 4; g = is_w1 ? blk + 1 : blk; k = r & 3; }
+                else { is_w1 = false; g = nG - 1; k = q - 8 * (nG - 1); }
               }
               mbar_arrive_expect_tx(fb, 32768);
-              if (is_w1) {
-                // ONE box {64 k, 128 rows, 2 K-chunks}: lands as two [128 x 128 B] K-major tiles
-                tma_load_3d(dst, &tmW1, fb, 0, 128 * (idx >> 1), 2 * (idx & 1));
-              } else {
-                tma_load_3d(dst, &tmW2, fb, 0, idx, 0);
-              }
+              if (is_w1) tma_load_3d(dst, &tmW1, fb, 0, k, 256 * g);
+              else tma_load_3d(dst, &tmW2, fb, 0, 4 * g + k, 0);
             }
           }
           __syncwarp();
@@ -175,36 +171,62 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
     long long tq = timing ? clock64() : 0, m_ring = 0, m_a2 = 0, m_hf = 0, m_ae = 0, m_other = 0;
     const long long m_t0 = tq;
     auto next_slot = [&]() { if (++slot == kSlots) { slot = 0; phase ^= 1; } };
-    // hidden chunk pair pp: H[pp&1] (128 TMEM columns) = A2 @ W1[128pp:128pp+128, :]^T; K = 256 arrives as two ring
-    // units of two 64-wide K chunks
-    const uint32_t idesc128 = umma_idesc_bf16(128, 128);
-    auto issue_ff1_pair = [&](int pp) {
-      const int b = pp & 1, u = pp >> 1;
+    // hidden group g: H (256 TMEM columns) = A2 @ W1[256g : 256g+256, :]^T; K = 256 arrives as four ring units
+    int n_ff1 = 0, n_ff2 = 0;                          // groups issued so far (barrier phases)
+    auto issue_ff1 = [&]() {
       EB_T(m_other);
-      mbar_wait(&bars->acc2_empty[b], (u & 1) ^ 1);              // GELU of pair pp-2 has drained H[b]
+      mbar_wait(&bars->acc2_empty, (n_ff1 & 1) ^ 1);             // the GELU warps have read the previous group out of H
       EB_T(m_ae);
-      const uint32_t d_tmem = tmem_base + kHCol + 128 * b;
-      for (int kh = 0; kh < 2; ++kh) {
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + kHCol;
+      for (int kc = 0; kc < 4; ++kc) {
         mbar_wait(&bars->full[slot], phase);
         EB_T(m_ring);
         tc_fence_after();
         const uint32_t w_addr = ring_addr + slot * kSlotBytes;
         if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 2; ++kk) {
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {
-              const uint64_t ad = umma_desc_kmajor(a2_addr + (2 * kh + kk) * 16384 + h * 32, 1024, UMMA_LAYOUT_SW128);
-              const uint64_t bd = umma_desc_kmajor(w_addr + kk * 16384 + h * 32, 1024, UMMA_LAYOUT_SW128);
-              umma_bf16(d_tmem, ad, bd, idesc128, (kh | kk | h) != 0 ? 1u : 0u);
-            }
+          for (int h = 0; h < 4; ++h) {
+            const uint64_t ad = umma_desc_kmajor(a2_addr + kc * 16384 + h * 32, 1024, UMMA_LAYOUT_SW128);
+            const uint64_t bd = umma_desc_kmajor(w_addr + h * 32, 1024, UMMA_LAYOUT_SW128);
+            umma_bf16(d_tmem, ad, bd, idesc256, (kc | h) != 0 ? 1u : 0u);
           }
           umma_commit(&bars->empty[slot]);
-          if (kh == 1) umma_commit(&bars->acc2_full[b]);
+          if (kc == 3) umma_commit(&bars->acc2_full);
         }
         __syncwarp();
         next_slot();
       }
+      ++n_ff1;
+    };
+    // X += gelu(H group g) @ W2[:, 256g : 256g+256]^T: four K chunks of 64 hidden columns
+    auto issue_ff2 = [&](bool last) {
+      EB_T(m_other);
+      mbar_wait(&bars->h_full, n_ff2 & 1);                       // gelu(H group) is in shared memory
+      EB_T(m_hf);
+      tc_fence_after();
+      for (int j = 0; j < 4; ++j) {
+        mbar_wait(&bars->full[slot], phase);
+        EB_T(m_ring);
+        tc_fence_after();
+        const uint32_t w_addr = ring_addr + slot * kSlotBytes;
+        if (elect_one()) {
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const uint64_t ad = umma_desc_kmajor(h_addr + j * 16384 + h * 32, 1024, UMMA_LAYOUT_SW128);
+            const uint64_t bd = umma_desc_kmajor(w_addr + h * 32, 1024, UMMA_LAYOUT_SW128);
+            umma_bf16(x_tmem, ad, bd, idesc256, 1u);
+          }
+          umma_commit(&bars->empty[slot]);
+          if (j == 3) {
+            umma_commit(&bars->h_empty);
+            if (last) umma_commit(&bars->x_full);
+          }
+        }
+        __syncwarp();
+        next_slot();
+      }
+      ++n_ff2;
     };
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       if (it > 0) mbar_wait(&bars->x_empty, (it - 1) & 1);       // the previous tile's x has been read out of TMEM
@@ -241,31 +263,11 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
       mbar_wait(&bars->a2_ready, it & 1);
       EB_T(m_a2);
       tc_fence_after();
-      issue_ff1_pair(0);
-      for (int c = 0; c < nC; ++c) {
-        if ((c & 1) == 0 && c + 2 < nC) issue_ff1_pair((c >> 1) + 1);
-        const int b = c & 1, u = c >> 1;
-        EB_T(m_other);
-        mbar_wait(&bars->h_full[b], u & 1);                      // gelu(H chunk c) is in shared memory
-        EB_T(m_hf);
-        mbar_wait(&bars->full[slot], phase);
-        EB_T(m_ring);
-        tc_fence_after();
-        const uint32_t w_addr = ring_addr + slot * kSlotBytes;
-        const uint32_t hb_addr = h_addr + b * kHBytes;
-        if (elect_one()) {
-#pragma unroll
-          for (int h = 0; h < 4; ++h) {
-            const uint64_t ad = umma_desc_kmajor(hb_addr + h * 32, 1024, UMMA_LAYOUT_SW128);
-            const uint64_t bd = umma_desc_kmajor(w_addr + h * 32, 1024, UMMA_LAYOUT_SW128);
-            umma_bf16(x_tmem, ad, bd, idesc256, 1u);
-          }
-          umma_commit(&bars->empty[slot]);
-          umma_commit(&bars->h_empty[b]);
-          if (c + 1 == nC) umma_commit(&bars->x_full);
-        }
-        __syncwarp();
-        next_slot();
+      // order: FF1(0) | FF1(1) FF2(0) | FF1(2) FF2(1) | ... | FF2(nG-1): the GELU of group g runs under FF1(g+1) / FF2(g-1)
+      issue_ff1();
+      for (int g = 0; g < nG; ++g) {
+        if (g + 1 < nG) issue_ff1();
+        issue_ff2(g + 1 == nG);
       }
     }
     if (timing && lane == 0) {
@@ -293,13 +295,22 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
         }
       }
     };
-    // LayerNorm statistics of a row are spread over the four warps of its lane quarter
-    auto row_total = [&](float part) -> float {
-      bars->xch[cq][trow] = part;
+    // LayerNorm statistics of a row are spread over the four warps of its lane quarter.  ONE exchange per LayerNorm:
+    // every thread contributes (sum, sum of squares) of its 64 columns through the head of its warp's own buf(0)
+    // (free at both call sites: the residual slice has been consumed / the x tile is not staged yet).  `release`:
+    // a second barrier before the caller overwrites buf(0) again (E1 has its all-warp barrier instead).
+    auto row_stats = [&](float2 part, float& mean, float& rstd, bool release) {
+      reinterpret_cast<float2*>(buf(0))[lane] = part;
       asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory");
-      const float tot = (bars->xch[0][trow] + bars->xch[1][trow]) + (bars->xch[2][trow] + bars->xch[3][trow]);
-      asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory");       // everyone has read: xch may be rewritten
-      return tot;
+      float sx = 0.f, sy = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 t = reinterpret_cast<const float2*>(scratch + (k * 4 + q) * 4096)[lane];
+        sx += t.x; sy += t.y;
+      }
+      if (release) asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory");
+      mean = sx * (1.0f / 256.0f);
+      rstd = rsqrtf(fmaxf(sy * (1.0f / 256.0f) - mean * mean, 0.f) + 1e-5f);
     };
     if (lane == 0 && static_cast<int>(blockIdx.x) < p.n_tiles) load_resid(blockIdx.x);
     int it = 0;
@@ -317,7 +328,7 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
 #pragma unroll
       for (int c = 0; c < 2; ++c) tmem_ld32(lane_taddr + kXCol + cb + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
       tmem_ld_wait();
-      float2 sum2 = make_float2(0.f, 0.f);
+      float2 sum2 = make_float2(0.f, 0.f), sq2 = make_float2(0.f, 0.f);
       if (valid) mbar_wait(&bars->res_full[ew][1], res_cnt & 1);
       EB_T(e_res);
 #pragma unroll
@@ -334,6 +345,8 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
           const float2 o23 = fadd2(fadd2(make_float2(__uint_as_float(v[c * 32 + 4 * t + 2]), __uint_as_float(v[c * 32 + 4 * t + 3])),
                                          make_float2(bp[2], bp[3])), make_float2(r4.z, r4.w));
           sum2 = fadd2(sum2, fadd2(o01, o23));
+          sq2 = ffma2(o01, o01, sq2);
+          sq2 = ffma2(o23, o23, sq2);
           v[c * 32 + 4 * t] = __float_as_uint(o01.x); v[c * 32 + 4 * t + 1] = __float_as_uint(o01.y);
           v[c * 32 + 4 * t + 2] = __float_as_uint(o23.x); v[c * 32 + 4 * t + 3] = __float_as_uint(o23.y);
         }
@@ -355,17 +368,8 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
         }
         tmem_st32(lane_taddr + kXCol + cb + c * 32, w);
       }
-      const float mean = row_total(sum2.x + sum2.y) * (1.0f / 256.0f);
-      float2 sq2v = make_float2(0.f, 0.f);
-      {
-        const float2 nm = make_float2(-mean, -mean);
-#pragma unroll
-        for (int t = 0; t < 64; t += 2) {
-          const float2 d = fadd2(make_float2(__uint_as_float(v[t]), __uint_as_float(v[t + 1])), nm);
-          sq2v = ffma2(d, d, sq2v);
-        }
-      }
-      const float rstd = 1.0f / sqrtf(row_total(sq2v.x + sq2v.y) * (1.0f / 256.0f) + 1e-5f);
+      float mean, rstd;
+      row_stats(make_float2(sum2.x + sum2.y, sq2.x + sq2.y), mean, rstd, false);
       const float2 nmean2 = make_float2(-mean, -mean), rstd2v = make_float2(rstd, rstd);
       tmem_st_wait();
       // every warp has consumed its residual slice: A2 (which overlays them) may be written
@@ -395,41 +399,45 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
       if (lane == 0) mbar_arrive(&bars->a2_ready);
       EB_T(e_w1);
 
-      // ================= hidden chunks: gelu(H + b1) -> bf16 A operand of the second GEMM
-      for (int c = 0; c < nC; ++c) {
-        const int b = c & 1, u = c >> 1;
-        const int tb = (c >> 1) & 1;                             // TMEM buffer of this chunk's pair
-        uint32_t r[16];
-        mbar_wait(&bars->acc2_full[tb], (c >> 2) & 1);
+      // ================= hidden groups: gelu(H + b1) -> bf16 A operand of the second GEMM (K chunk cq of the group)
+      for (int g = 0; g < nG; ++g) {
+        const int gi = it * nG + g;                              // groups processed by this CTA so far (barrier phases)
+        uint4 pk[8];
+        mbar_wait(&bars->acc2_full, gi & 1);
         EB_T(e_af);
         tc_fence_after();
-        tmem_ld16(lane_taddr + kHCol + 128 * tb + 64 * b + 16 * cq, r);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->acc2_empty[tb]);
-        uint4 pk[2];
-        const float* b1 = p.c.b1 + c * 64 + cq * 16;
+        const float* b1 = p.c.b1 + g * 256 + cq * 64;
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const float* bb = b1 + t * 8;
-          float2 y[4];
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t r[32];
+          tmem_ld32(lane_taddr + kHCol + cq * 64 + hh * 32, r);
+          tmem_ld_wait();
+          if (hh == 1) {                                         // both halves are in registers: H may be overwritten
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->acc2_empty);
+          }
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            y[k] = gelu_tanh_erf2(fadd2(make_float2(__uint_as_float(r[t * 8 + 2 * k]), __uint_as_float(r[t * 8 + 2 * k + 1])),
-                                        make_float2(bb[2 * k], bb[2 * k + 1])));
-          pk[t].x = pack_bf16x2(y[0].x, y[0].y); pk[t].y = pack_bf16x2(y[1].x, y[1].y);
-          pk[t].z = pack_bf16x2(y[2].x, y[2].y); pk[t].w = pack_bf16x2(y[3].x, y[3].y);
+          for (int t = 0; t < 4; ++t) {
+            const float* bb = b1 + hh * 32 + t * 8;
+            float2 y[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              y[k] = gelu_tanh_erf2(fadd2(make_float2(__uint_as_float(r[t * 8 + 2 * k]), __uint_as_float(r[t * 8 + 2 * k + 1])),
+                                          make_float2(bb[2 * k], bb[2 * k + 1])));
+            pk[hh * 4 + t].x = pack_bf16x2(y[0].x, y[0].y); pk[hh * 4 + t].y = pack_bf16x2(y[1].x, y[1].y);
+            pk[hh * 4 + t].z = pack_bf16x2(y[2].x, y[2].y); pk[hh * 4 + t].w = pack_bf16x2(y[3].x, y[3].y);
+          }
         }
         EB_T(e_ff);
-        mbar_wait(&bars->h_empty[b], (u & 1) ^ 1);               // the MMAs of chunk c-2 have read H[b]
+        if (gi > 0) mbar_wait(&bars->h_empty, (gi - 1) & 1);     // the MMAs of the previous group have read the hidden tile
         EB_T(e_he);
-        uint8_t* hb = sH + b * kHBytes + q * 4096;
+        uint8_t* hb = sH + cq * 16384 + q * 4096;                // K chunk cq of the group: [128 rows][64 bf16], 128-byte swizzle
 #pragma unroll
-        for (int t = 0; t < 2; ++t) *reinterpret_cast<uint4*>(hb + stg_off(lane, 2 * cq + t)) = pk[t];
+        for (int t = 0; t < 8; ++t) *reinterpret_cast<uint4*>(hb + stg_off(lane, t)) = pk[t];
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->h_full[b]);
+        if (lane == 0) mbar_arrive(&bars->h_full);
         EB_T(e_ff);
       }
 
@@ -443,17 +451,27 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->x_empty);
-      sum2 = make_float2(0.f, 0.f);
+      // row statistics first (the exchange goes through the head of buf(0), which the x tile is staged in afterwards)
+      float mean2 = 0.f, rstd2 = 0.f;
+      if (p.has_ln_out) {
+        sum2 = make_float2(0.f, 0.f);
+        sq2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int t = 0; t < 64; t += 2) {
+          const float2 o = make_float2(__uint_as_float(v[t]), __uint_as_float(v[t + 1]));
+          sum2 = fadd2(sum2, o);
+          sq2 = ffma2(o, o, sq2);
+        }
+        row_stats(make_float2(sum2.x + sum2.y, sq2.x + sq2.y), mean2, rstd2, true);
+      }
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint8_t* rb = buf(c);
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          const float4 o = make_float4(__uint_as_float(v[c * 32 + 4 * t]), __uint_as_float(v[c * 32 + 4 * t + 1]),
-                                       __uint_as_float(v[c * 32 + 4 * t + 2]), __uint_as_float(v[c * 32 + 4 * t + 3]));
-          *reinterpret_cast<float4*>(rb + stg_off(lane, t)) = o;
-          sum2 = fadd2(sum2, fadd2(make_float2(o.x, o.y), make_float2(o.z, o.w)));
-        }
+        for (int t = 0; t < 8; ++t)
+          *reinterpret_cast<float4*>(rb + stg_off(lane, t)) =
+              make_float4(__uint_as_float(v[c * 32 + 4 * t]), __uint_as_float(v[c * 32 + 4 * t + 1]),
+                          __uint_as_float(v[c * 32 + 4 * t + 2]), __uint_as_float(v[c * 32 + 4 * t + 3]));
       }
       fence_proxy_async();
       __syncwarp();
@@ -463,17 +481,6 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
         bulk_commit_group();
       }
       if (p.has_ln_out) {
-        const float mean2 = row_total(sum2.x + sum2.y) * (1.0f / 256.0f);
-        float2 sqb = make_float2(0.f, 0.f);
-        {
-          const float2 nm = make_float2(-mean2, -mean2);
-#pragma unroll
-          for (int t = 0; t < 64; t += 2) {
-            const float2 d = fadd2(make_float2(__uint_as_float(v[t]), __uint_as_float(v[t + 1])), nm);
-            sqb = ffma2(d, d, sqb);
-          }
-        }
-        const float rstd2 = 1.0f / sqrtf(row_total(sqb.x + sqb.y) * (1.0f / 256.0f) + 1e-5f);
         const float2 nmean2b = make_float2(-mean2, -mean2), rstd2vb = make_float2(rstd2, rstd2);
         if (lane == 0) bulk_wait_group_read<0>();                // the x stores have read their tiles
         __syncwarp();
@@ -543,19 +550,13 @@ int launch_encoder_block(const void* o, float* x, void* a_out, const void* wo, c
   KIRI_REQUIRE(o && x && wo && w1 && w2 && consts_host, "encoder_block: null pointer");
   KIRI_REQUIRE(!has_ln_out || a_out != nullptr, "encoder_block: LayerNorm output without a_out");
   KIRI_REQUIRE(M % 32 == 0, "encoder_block: token count %d must be a multiple of 32", M);
-  KIRI_REQUIRE(FF % 128 == 0 && FF >= 256 && FF <= 1024, "encoder_block: FF width %d must be a multiple of 128 in [256, 1024]", FF);
+  KIRI_REQUIRE(FF % 256 == 0 && FF >= 256 && FF <= 1024, "encoder_block: FF width %d must be a multiple of 256 in [256, 1024]", FF);
   if (M == 0) return 0;
   const int sms = gemm_tc_num_sms();
   CUtensorMap tmO, tmWo, tmW1, tmW2, tmX, tmA;
   if (encode_kchunk_map(&tmO, o, M, 256, 128)) return -1;
   if (encode_kchunk_map(&tmWo, wo, 256, 256, 256)) return -1;
-  {  // W1 [FF, 256]: dims (k 64, row, K-chunk) so that a {64, 128, 2} box is two consecutive K-major tiles
-    cuuint64_t dims[3] = {64, (cuuint64_t)FF, 4};
-    cuuint64_t str[2] = {512, 128};
-    cuuint32_t box[3] = {64, 128, 2};
-    cuuint32_t es[3] = {1, 1, 1};
-    if (encode_map(&tmW1, w1, 3, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
-  }
+  if (encode_kchunk_map(&tmW1, w1, FF, 256, 256)) return -1;           // unit = 256 rows of W1 x one 64-wide K chunk
   if (encode_kchunk_map(&tmW2, w2, 256, FF, 256)) return -1;
   if (encode_rowtile_map(&tmX, x, M, 256, 256, true)) return -1;
   tmA = tmX;
@@ -563,7 +564,7 @@ int launch_encoder_block(const void* o, float* x, void* a_out, const void* wo, c
   EbParams p;
   p.c = *consts_host;
   p.has_ln_out = has_ln_out ? 1 : 0;
-  p.M = M; p.n_tiles = (M + 127) / 128; p.nC = FF / 64;
+  p.M = M; p.n_tiles = (M + 127) / 128; p.nG = FF / 256;
   static const int timing_on = getenv("KIRI_GEMM_TIMING") != nullptr;
   p.timing = timing_on;
   const int smem = kBarOff + static_cast<int>(sizeof(EbBars));

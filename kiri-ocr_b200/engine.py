@@ -172,7 +172,7 @@ class BatchedRecognizer:
         self.launches = 0           # kernels launched by this engine (for bench's gpu_launches)
         # per encoder layer: QKV GEMM, attention, fused tail (csrc/encoder_block.cu) — or QKV, attention and the
         # three GEMMs the tail replaces when it is switched off / not applicable
-        fused = _os.environ.get("KIRI_NO_FUSED_BLOCK") is None and cfg.ENC_FF % 128 == 0 and cfg.ENC_FF <= 1024
+        fused = _os.environ.get("KIRI_NO_FUSED_BLOCK") is None and cfg.ENC_FF % 256 == 0 and cfg.ENC_FF <= 1024
         self._layer_launches = 3 if fused else 5
 
     def __del__(self):

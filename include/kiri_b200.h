@@ -154,7 +154,9 @@ int kiri_encoder_attention_multi(const void* qkv_bf16, void* out_bf16, const int
  * ONE kernel; the 1024-wide hidden activation and norm2's output never reach HBM.
  *   x[M,256] fp32 (in/out) += o[M,256] @ wo[256,256]^T + bo;  a2 = LN(x; ln_mid);
  *   x += gelu(a2 @ w1[FF,256]^T + b1) @ w2[256,FF]^T + b2;    a_out[M,256] bf16 = LN(x; ln_out)
- * ln_out_g/ln_out_b/a_out may be NULL together (last layer).  M % 32 == 0, FF % 256 == 0. */
+ * ln_out_g/ln_out_b/a_out may be NULL together (last layer).  M % 32 == 0, FF % 256 == 0.
+ * When every gain is exactly 1 and every shift exactly 0 the kernel variant without per-column LayerNorm parameters
+ * runs (~8 % faster): callers fold the affines into w1/b1 and into the consumer of a_out, as kiri-ocr_b200/weights.py does. */
 int kiri_encoder_block(const void* o_bf16, float* x_f32, void* a_out_bf16, const void* wo, const float* bo,
                        const void* w1, const float* b1, const void* w2, const float* b2, const float* ln_mid_g,
                        const float* ln_mid_b, const float* ln_out_g, const float* ln_out_b, int M, int FF,

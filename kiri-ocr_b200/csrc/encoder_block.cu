@@ -61,10 +61,147 @@ struct EbParams {
 // KIRI_GEMM_TIMING=1: phase cycles of CTA 0 (epilogue warp 0 lane 0 / MMA warp), read by kiri_debug_eb_timing():
 // [0] E1 wait g1 [1] E1 wait resid [2] E1 work [3] FF wait acc2_full [4] FF wait h_empty [5] FF work [6] E2 wait x_full
 // [7] E2 work [8] tiles [9] MMA wait ring [10] MMA wait a2_ready [11] MMA wait h_full [12] MMA wait acc2_empty [13] MMA total
-__device__ long long g_eb_prof[16];
+__device__ long long g_eb_prof[32];
 #define EB_T(acc) do { if (timing) { const long long _t = clock64(); acc += _t - tq; tq = _t; } } while (0)
 
 
+// ---- epilogue pieces.  CQ (the warp's column quarter) is a template parameter so that the biases / LayerNorm affines,
+// which travel by value in the kernel parameters, are addressed with COMPILE-TIME constant-bank offsets (operands of the
+// arithmetic instructions or immediate-addressed loads); with a run-time quarter every one of them was a register-indexed
+// LDC feeding one packed add (192 of them per thread and tile, ~37 cycles each when 16 warps queue on the constant port).
+// Everything works on 16 columns at a time so that a pass never holds more than ~48 values: the 64-column form spilled
+// (384 B of stack) and its loads were issued one by one.
+
+// E1, first pass: x_mid = (G1 + bo) + residual -> back into X; row partial sums.  tx = TMEM address of this thread's
+// 64 X columns, rb0 / rb1 = shared addresses of the warp's residual slices (32 rows x 32 fp32, 128-byte swizzle).
+__device__ __forceinline__ void eb_e1_resid(const int CQ, const EbParams& p, uint32_t tx, uint32_t rb0, uint32_t rb1, uint32_t rowb,
+                                            uint32_t sw, float2& sum2, float2& sq2) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t v[16];
+    tmem_ld16(tx + c * 16, v);
+    float4 r[4];
+    const uint32_t rb = ((c < 2) ? rb0 : rb1) + rowb;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) r[t] = lds128(rb + ((static_cast<uint32_t>((c & 1) * 4 + t) << 4) ^ sw));
+    tmem_ld_wait();
+    uint32_t w[16];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float* bp = p.c.bo + CQ * 64 + c * 16 + 4 * t;
+      const float2 o01 = fadd2(make_float2(__uint_as_float(v[4 * t]) + bp[0], __uint_as_float(v[4 * t + 1]) + bp[1]),
+                               make_float2(r[t].x, r[t].y));
+      const float2 o23 = fadd2(make_float2(__uint_as_float(v[4 * t + 2]) + bp[2], __uint_as_float(v[4 * t + 3]) + bp[3]),
+                               make_float2(r[t].z, r[t].w));
+      sum2 = fadd2(sum2, fadd2(o01, o23));
+      sq2 = ffma2(o01, o01, sq2);
+      sq2 = ffma2(o23, o23, sq2);
+      w[4 * t] = __float_as_uint(o01.x); w[4 * t + 1] = __float_as_uint(o01.y);
+      w[4 * t + 2] = __float_as_uint(o23.x); w[4 * t + 3] = __float_as_uint(o23.y);
+    }
+    tmem_st16(tx + c * 16, w);
+  }
+}
+
+// E1, second pass: x_mid comes back from TMEM; A2 = LN_mid(x_mid) (bf16, K chunk CQ of the FFN's A operand, written over
+// the warp's own first residual slice) and X <- x_mid + b2 (the second residual costs the FFN nothing).
+template <bool AFFINE>
+__device__ __forceinline__ void eb_e1_norm(const int CQ, const EbParams& p, uint32_t tx, uint32_t ob, uint32_t sw, float mean, float rstd) {
+  const float2 nmean2 = make_float2(-mean, -mean), rstd2v = make_float2(rstd, rstd);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t v[16], w[16], pk[8];
+    tmem_ld16(tx + c * 16, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int col = CQ * 64 + c * 16 + 2 * u;
+      const float x0 = __uint_as_float(v[2 * u]), x1 = __uint_as_float(v[2 * u + 1]);
+      const float2 dd = fadd2(make_float2(x0, x1), nmean2);
+      float2 y = fmul2(dd, rstd2v);
+      if (AFFINE) y = ffma2(y, make_float2(p.c.ln_mid_g[col], p.c.ln_mid_g[col + 1]), make_float2(p.c.ln_mid_b[col], p.c.ln_mid_b[col + 1]));
+      pk[u] = pack_bf16x2(y.x, y.y);
+      w[2 * u] = __float_as_uint(x0 + p.c.b2[col]);
+      w[2 * u + 1] = __float_as_uint(x1 + p.c.b2[col + 1]);
+    }
+    sts128(ob + ((static_cast<uint32_t>(2 * c) << 4) ^ sw), pk[0], pk[1], pk[2], pk[3]);
+    sts128(ob + ((static_cast<uint32_t>(2 * c + 1) << 4) ^ sw), pk[4], pk[5], pk[6], pk[7]);
+    tmem_st16(tx + c * 16, w);
+  }
+}
+
+// E2: the thread's 64 x values stay in registers (X is handed back to the MMA warp for the next tile's out-projection
+// straight after the read).  Staging of the fp32 tile + row partial sums:
+__device__ __forceinline__ void eb_e2_stage(const uint32_t (&v)[64], uint32_t rb0, uint32_t rb1, uint32_t rowb, uint32_t sw,
+                                            float2& sum2, float2& sq2) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+#pragma unroll
+    for (int t = 0; t < 16; t += 2) {
+      const float2 o = make_float2(__uint_as_float(v[c * 16 + t]), __uint_as_float(v[c * 16 + t + 1]));
+      sum2 = fadd2(sum2, o);
+      sq2 = ffma2(o, o, sq2);
+    }
+    const uint32_t rb = ((c < 2) ? rb0 : rb1) + rowb;
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      sts128(rb + ((static_cast<uint32_t>((c & 1) * 4 + t) << 4) ^ sw), v[c * 16 + 4 * t], v[c * 16 + 4 * t + 1],
+             v[c * 16 + 4 * t + 2], v[c * 16 + 4 * t + 3]);
+  }
+}
+
+// a = LN_out(x) as packed bf16, in place (pair u of the row lands in v[u]); staged once the x stores have read the tiles.
+template <bool AFFINE>
+__device__ __forceinline__ void eb_e2_norm(const int CQ, const EbParams& p, float mean, float rstd, uint32_t (&v)[64]) {
+  const float2 nmean2 = make_float2(-mean, -mean), rstd2v = make_float2(rstd, rstd);
+#pragma unroll
+  for (int u = 0; u < 32; ++u) {
+    const int col = CQ * 64 + 2 * u;
+    const float2 dd = fadd2(make_float2(__uint_as_float(v[2 * u]), __uint_as_float(v[2 * u + 1])), nmean2);
+    float2 y = fmul2(dd, rstd2v);
+    if (AFFINE) y = ffma2(y, make_float2(p.c.ln_out_g[col], p.c.ln_out_g[col + 1]), make_float2(p.c.ln_out_b[col], p.c.ln_out_b[col + 1]));
+    v[u] = pack_bf16x2(y.x, y.y);
+  }
+}
+
+// LayerNorm statistics of a row are spread over the four warps of its lane quarter (one column quarter each).  The four
+// warps may all address the same 32 TMEM lanes, so the exchange goes through eight spare TMEM columns of the (idle) hidden
+// accumulator: no shared memory (the staging tiles are all in use) and one 128-thread barrier.
+__device__ __forceinline__ void eb_row_stats(uint32_t th, int cq, int q, float2 part, float& mean, float& rstd) {
+  tmem_st2(th + cq * 2, __float_as_uint(part.x), __float_as_uint(part.y));
+  tmem_st_wait();
+  tc_fence_before();
+  asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory");
+  tc_fence_after();
+  uint32_t s[8];
+  tmem_ld8(th, s);
+  tmem_ld_wait();
+  float sx = 0.f, sy = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { sx += __uint_as_float(s[2 * k]); sy += __uint_as_float(s[2 * k + 1]); }
+  mean = sx * (1.0f / 256.0f);
+  rstd = rsqrtf(fmaxf(sy * (1.0f / 256.0f) - mean * mean, 0.f) + 1e-5f);
+}
+
+// ptxas list-schedules a basic block by critical path, and a barrier arrival has no dependants: left alone it sinks
+// below all the arithmetic that follows it in the block (the GELU warps then hand the hidden accumulator back ~1.5 k
+// cycles late, once per group).  A branch the compiler cannot resolve ends the block right after the arrival.
+#define EB_SCHED_FENCE() do { if (p.M < 0) __trap(); } while (0)
+
+#ifdef KIRI_EB_CQ_SWITCH
+#define EB_CQ_SWITCH(cq, CALL) \
+  switch (cq) { case 0: { constexpr int CQ = 0; CALL; } break; case 1: { constexpr int CQ = 1; CALL; } break; \
+                case 2: { constexpr int CQ = 2; CALL; } break; default: { constexpr int CQ = 3; CALL; } break; }
+#else
+#define EB_CQ_SWITCH(cq, CALL) { const int CQ = cq; CALL; }
+#endif
+
+
+// AFFINE = false: both LayerNorms are pure normalisations — their affines have been folded into the weights that consume
+// them (W1 / b1 and the next layer's Wqkv / bqkv: kiri-ocr_b200/weights.py), which takes 128 of the 192 per-column
+// parameter fetches per thread and tile out of the epilogues (a warp-wide LDC.64 costs ~4 cycles of the SM's constant
+// port: 16 warps x 96 of them were 5 k of E1's 8 k cycles).  AFFINE = true applies ln_mid / ln_out as given.
+template <bool AFFINE>
 __global__ void __launch_bounds__(kEbThreads, 1)
 encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmWo,
                      const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
@@ -279,124 +416,67 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
     // 16 warps: warp w reads TMEM lane quarter q = w & 3 (hardware rule) and owns column quarter cq = w >> 2,
     // i.e. thread = one tile row x 64 columns.  (With 8 warps of 128 columns per thread the two LayerNorm
     // passes and the GELU were latency-bound at 2 warps per scheduler: 13 k + 11 k + 26 k cycles per tile.)
+    // Per warp two 4 KB tiles, buf(0) inside the A2 region (it IS the warp's 32 rows of A2's K chunk cq) and buf(1)
+    // inside the hidden-group region: landing zone of the fp32 residual slice, then staging of the x and a stores.
     const int q = warp & 3, cq = warp >> 2, ew = warp;
     const int cb = cq * 64;
-    const int trow = q * 32 + lane;
     auto buf = [&](int c) -> uint8_t* { return scratch + (c * kEbEpiWarps + ew) * 4096; };
+    const uint32_t rb0 = smem_u32(buf(0)), rb1 = smem_u32(buf(1));
+    const uint32_t rowb = static_cast<uint32_t>(lane) * 128u, sw = static_cast<uint32_t>(lane & 7) << 4;
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t tx = lane_taddr + kXCol + cb;          // this thread's 64 columns of X
+    const uint32_t th = lane_taddr + kHCol;               // row-statistics exchange: columns [0,8) for E1, [8,16) for E2
     uint32_t res_cnt = 0;
-    auto load_resid = [&](int tile) {                 // lane 0: this warp's 32 x 64 fp32 residual slice
-      const int row0 = tile * 128 + q * 32;
-      if (row0 < p.M) {
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          mbar_arrive_expect_tx(&bars->res_full[ew][c], 4096);
-          tma_load_2d(buf(c), &tmX, &bars->res_full[ew][c], cb + c * 32, row0);
-        }
-      }
+    auto load_resid_c = [&](int tile, int c) {        // lane 0: half of this warp's 32 x 64 fp32 residual slice
+      mbar_arrive_expect_tx(&bars->res_full[ew][c], 4096);
+      tma_load_2d(buf(c), &tmX, &bars->res_full[ew][c], cb + c * 32, tile * 128 + q * 32);
     };
-    // LayerNorm statistics of a row are spread over the four warps of its lane quarter.  ONE exchange per LayerNorm:
-    // every thread contributes (sum, sum of squares) of its 64 columns through the head of its warp's own buf(0)
-    // (free at both call sites: the residual slice has been consumed / the x tile is not staged yet).  `release`:
-    // a second barrier before the caller overwrites buf(0) again (E1 has its all-warp barrier instead).
-    auto row_stats = [&](float2 part, float& mean, float& rstd, bool release) {
-      reinterpret_cast<float2*>(buf(0))[lane] = part;
-      asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory");
-      float sx = 0.f, sy = 0.f;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 t = reinterpret_cast<const float2*>(scratch + (k * 4 + q) * 4096)[lane];
-        sx += t.x; sy += t.y;
-      }
-      if (release) asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory");
-      mean = sx * (1.0f / 256.0f);
-      rstd = rsqrtf(fmaxf(sy * (1.0f / 256.0f) - mean * mean, 0.f) + 1e-5f);
-    };
-    if (lane == 0 && static_cast<int>(blockIdx.x) < p.n_tiles) load_resid(blockIdx.x);
+    if (lane == 0 && static_cast<int>(blockIdx.x) < p.n_tiles && static_cast<int>(blockIdx.x) * 128 + q * 32 < p.M) {
+      load_resid_c(blockIdx.x, 0);
+      load_resid_c(blockIdx.x, 1);
+    }
     int it = 0;
     const bool timing = p.timing != 0 && blockIdx.x == 0 && warp == 0;
     long long tq = timing ? clock64() : 0, e_g1 = 0, e_res = 0, e_w1 = 0, e_af = 0, e_he = 0, e_ff = 0, e_xf = 0, e_w2 = 0;
+#ifdef KIRI_EB_SUBPHASE
+    long long s1[7] = {0, 0, 0, 0, 0, 0, 0}, s2[6] = {0, 0, 0, 0, 0, 0}, ts = 0;   // sub-phases of E1 / E2
+#define EB_S(acc) do { if (timing) { const long long _t = clock64(); acc += _t - ts; ts = _t; } } while (0)
+#else
+#define EB_S(acc) do { } while (0)
+#endif
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int row0 = tile * 128 + q * 32;
-      const bool valid = row0 < p.M;
-      uint32_t v[64];
-      if (timing) tq = clock64();
-      // ================= E1: x_mid = X + bo + x;  X <- x_mid + b2;  A2 <- LN_mid(x_mid)
+      const bool valid = row0 < p.M;                  // warp-uniform (M % 32 == 0); rows past M compute on whatever the
+      if (timing) tq = clock64();                     // staging tiles hold and are never stored
+      // ================= E1: x_mid = X + bo + x;  A2 <- LN_mid(x_mid);  X <- x_mid + b2
       mbar_wait(&bars->g1_full, it & 1);
       EB_T(e_g1);
+#ifdef KIRI_EB_SUBPHASE
+      if (timing) ts = clock64();
+#endif
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) tmem_ld32(lane_taddr + kXCol + cb + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
-      tmem_ld_wait();
-      float2 sum2 = make_float2(0.f, 0.f), sq2 = make_float2(0.f, 0.f);
-      if (valid) mbar_wait(&bars->res_full[ew][1], res_cnt & 1);
+      if (valid) {
+        mbar_wait(&bars->res_full[ew][0], res_cnt & 1);
+        mbar_wait(&bars->res_full[ew][1], res_cnt & 1);
+        ++res_cnt;
+      }
       EB_T(e_res);
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        if (valid) mbar_wait(&bars->res_full[ew][c], res_cnt & 1);
-        const uint8_t* rb = buf(c);
-#pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          const float* bp = p.c.bo + cb + c * 32 + 4 * t;
-          float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (valid) r4 = *reinterpret_cast<const float4*>(rb + stg_off(lane, t));
-          const float2 o01 = fadd2(fadd2(make_float2(__uint_as_float(v[c * 32 + 4 * t]), __uint_as_float(v[c * 32 + 4 * t + 1])),
-                                         make_float2(bp[0], bp[1])), make_float2(r4.x, r4.y));
-          const float2 o23 = fadd2(fadd2(make_float2(__uint_as_float(v[c * 32 + 4 * t + 2]), __uint_as_float(v[c * 32 + 4 * t + 3])),
-                                         make_float2(bp[2], bp[3])), make_float2(r4.z, r4.w));
-          sum2 = fadd2(sum2, fadd2(o01, o23));
-          sq2 = ffma2(o01, o01, sq2);
-          sq2 = ffma2(o23, o23, sq2);
-          v[c * 32 + 4 * t] = __float_as_uint(o01.x); v[c * 32 + 4 * t + 1] = __float_as_uint(o01.y);
-          v[c * 32 + 4 * t + 2] = __float_as_uint(o23.x); v[c * 32 + 4 * t + 3] = __float_as_uint(o23.y);
-        }
-      }
-      if (valid) ++res_cnt;
-      // X <- x_mid + b2: the FFN's second GEMM accumulates on top of it (the second residual costs nothing)
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t w[32];
-#pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          const float* bp = p.c.b2 + cb + c * 32 + 4 * t;
-          const float2 w01 = fadd2(make_float2(__uint_as_float(v[c * 32 + 4 * t]), __uint_as_float(v[c * 32 + 4 * t + 1])),
-                                   make_float2(bp[0], bp[1]));
-          const float2 w23 = fadd2(make_float2(__uint_as_float(v[c * 32 + 4 * t + 2]), __uint_as_float(v[c * 32 + 4 * t + 3])),
-                                   make_float2(bp[2], bp[3]));
-          w[4 * t] = __float_as_uint(w01.x); w[4 * t + 1] = __float_as_uint(w01.y);
-          w[4 * t + 2] = __float_as_uint(w23.x); w[4 * t + 3] = __float_as_uint(w23.y);
-        }
-        tmem_st32(lane_taddr + kXCol + cb + c * 32, w);
-      }
+      EB_S(s1[0]);
+      float2 sum2 = make_float2(0.f, 0.f), sq2 = make_float2(0.f, 0.f);
+      EB_CQ_SWITCH(cq, eb_e1_resid(CQ, p, tx, rb0, rb1, rowb, sw, sum2, sq2));
+      EB_S(s1[1]);
       float mean, rstd;
-      row_stats(make_float2(sum2.x + sum2.y, sq2.x + sq2.y), mean, rstd, false);
-      const float2 nmean2 = make_float2(-mean, -mean), rstd2v = make_float2(rstd, rstd);
+      eb_row_stats(th, cq, q, make_float2(sum2.x + sum2.y, sq2.x + sq2.y), mean, rstd);
+      EB_S(s1[2]);
+      // K chunk cq of A2 ([128 rows][64 bf16], 128-byte swizzle): this warp's 32 rows are its own buf(0), consumed above
+      EB_CQ_SWITCH(cq, eb_e1_norm<AFFINE>(CQ, p, tx, rb0 + rowb, sw, mean, rstd));
+      EB_S(s1[3]);
       tmem_st_wait();
-      // every warp has consumed its residual slice: A2 (which overlays them) may be written
-      asm volatile("bar.sync 1, 512;" ::: "memory");
-      {                                              // K chunk cq of A2: [128 rows][64 bf16], 128-byte swizzle
-        uint8_t* ob = sA2 + cq * 16384 + q * 4096;
-#pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          const int col = cb + t * 8;
-          const float* gg = p.c.ln_mid_g + col;
-          const float* hh = p.c.ln_mid_b + col;
-          float2 y[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float2 dd = fadd2(make_float2(__uint_as_float(v[t * 8 + 2 * u]), __uint_as_float(v[t * 8 + 2 * u + 1])), nmean2);
-            y[u] = ffma2(fmul2(dd, rstd2v), make_float2(gg[2 * u], gg[2 * u + 1]), make_float2(hh[2 * u], hh[2 * u + 1]));
-          }
-          uint4 pk;
-          pk.x = pack_bf16x2(y[0].x, y[0].y); pk.y = pack_bf16x2(y[1].x, y[1].y);
-          pk.z = pack_bf16x2(y[2].x, y[2].y); pk.w = pack_bf16x2(y[3].x, y[3].y);
-          *reinterpret_cast<uint4*>(ob + stg_off(lane, t)) = pk;
-        }
-      }
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->a2_ready);
+      EB_S(s1[4]);
       EB_T(e_w1);
 
       // ================= hidden groups: gelu(H + b1) -> bf16 A operand of the second GEMM (K chunk cq of the group)
@@ -407,34 +487,39 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
         EB_T(e_af);
         tc_fence_after();
         const float* b1 = p.c.b1 + g * 256 + cq * 64;
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          uint32_t r[32];
-          tmem_ld32(lane_taddr + kHCol + cq * 64 + hh * 32, r);
+        {
+          // both halves are fetched before any arithmetic: H is handed back to the MMA warp (the next group's first GEMM
+          // waits for it) as soon as it is in registers, not after half of the GELUs
+          uint32_t r[2][32];
+          tmem_ld32(lane_taddr + kHCol + cq * 64, r[0]);
+          tmem_ld32(lane_taddr + kHCol + cq * 64 + 32, r[1]);
           tmem_ld_wait();
-          if (hh == 1) {                                         // both halves are in registers: H may be overwritten
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->acc2_empty);
-          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->acc2_empty);
+          EB_SCHED_FENCE();
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const float* bb = b1 + hh * 32 + t * 8;
-            float2 y[4];
+          for (int hh = 0; hh < 2; ++hh) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              y[k] = gelu_tanh_erf2(fadd2(make_float2(__uint_as_float(r[t * 8 + 2 * k]), __uint_as_float(r[t * 8 + 2 * k + 1])),
-                                          make_float2(bb[2 * k], bb[2 * k + 1])));
-            pk[hh * 4 + t].x = pack_bf16x2(y[0].x, y[0].y); pk[hh * 4 + t].y = pack_bf16x2(y[1].x, y[1].y);
-            pk[hh * 4 + t].z = pack_bf16x2(y[2].x, y[2].y); pk[hh * 4 + t].w = pack_bf16x2(y[3].x, y[3].y);
+            for (int t = 0; t < 4; ++t) {
+              const float* bb = b1 + hh * 32 + t * 8;
+              float2 y[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                y[k] = gelu_tanh_erf2(fadd2(make_float2(__uint_as_float(r[hh][t * 8 + 2 * k]), __uint_as_float(r[hh][t * 8 + 2 * k + 1])),
+                                            make_float2(bb[2 * k], bb[2 * k + 1])));
+              pk[hh * 4 + t].x = pack_bf16x2(y[0].x, y[0].y); pk[hh * 4 + t].y = pack_bf16x2(y[1].x, y[1].y);
+              pk[hh * 4 + t].z = pack_bf16x2(y[2].x, y[2].y); pk[hh * 4 + t].w = pack_bf16x2(y[3].x, y[3].y);
+            }
           }
         }
         EB_T(e_ff);
         if (gi > 0) mbar_wait(&bars->h_empty, (gi - 1) & 1);     // the MMAs of the previous group have read the hidden tile
         EB_T(e_he);
-        uint8_t* hb = sH + cq * 16384 + q * 4096;                // K chunk cq of the group: [128 rows][64 bf16], 128-byte swizzle
+        // K chunk cq of the group ([128 rows][64 bf16], 128-byte swizzle): this warp's rows are its own buf(1)
 #pragma unroll
-        for (int t = 0; t < 8; ++t) *reinterpret_cast<uint4*>(hb + stg_off(lane, t)) = pk[t];
+        for (int t = 0; t < 8; ++t)
+          sts128(rb1 + rowb + ((static_cast<uint32_t>(t) << 4) ^ sw), pk[t].x, pk[t].y, pk[t].z, pk[t].w);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->h_full);
@@ -444,84 +529,71 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
       // ================= E2: x = X (all FFN MMAs retired) -> global; a = LN_out(x) -> global
       mbar_wait(&bars->x_full, it & 1);
       EB_T(e_xf);
+#ifdef KIRI_EB_SUBPHASE
+      if (timing) ts = clock64();
+#endif
       tc_fence_after();
+      {
+        uint32_t v[64];
 #pragma unroll
-      for (int c = 0; c < 2; ++c) tmem_ld32(lane_taddr + kXCol + cb + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->x_empty);
-      // row statistics first (the exchange goes through the head of buf(0), which the x tile is staged in afterwards)
-      float mean2 = 0.f, rstd2 = 0.f;
-      if (p.has_ln_out) {
+        for (int c = 0; c < 4; ++c) tmem_ld16(tx + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[c * 16]));
+        tmem_ld_wait();
+        tc_fence_before();                                       // X goes back to the MMA warp (next tile's out-projection)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->x_empty);
+        EB_SCHED_FENCE();
         sum2 = make_float2(0.f, 0.f);
         sq2 = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int t = 0; t < 64; t += 2) {
-          const float2 o = make_float2(__uint_as_float(v[t]), __uint_as_float(v[t + 1]));
-          sum2 = fadd2(sum2, o);
-          sq2 = ffma2(o, o, sq2);
-        }
-        row_stats(make_float2(sum2.x + sum2.y, sq2.x + sq2.y), mean2, rstd2, true);
-      }
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint8_t* rb = buf(c);
-#pragma unroll
-        for (int t = 0; t < 8; ++t)
-          *reinterpret_cast<float4*>(rb + stg_off(lane, t)) =
-              make_float4(__uint_as_float(v[c * 32 + 4 * t]), __uint_as_float(v[c * 32 + 4 * t + 1]),
-                          __uint_as_float(v[c * 32 + 4 * t + 2]), __uint_as_float(v[c * 32 + 4 * t + 3]));
-      }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0 && valid) {
-        tma_store_2d(&tmX, buf(0), cb, row0);
-        tma_store_2d(&tmX, buf(1), cb + 32, row0);
-        bulk_commit_group();
-      }
-      if (p.has_ln_out) {
-        const float2 nmean2b = make_float2(-mean2, -mean2), rstd2vb = make_float2(rstd2, rstd2);
-        if (lane == 0) bulk_wait_group_read<0>();                // the x stores have read their tiles
-        __syncwarp();
-        uint8_t* ob = buf(0);
-#pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          const int col = cb + t * 8;
-          const float* gg = p.c.ln_out_g + col;
-          const float* hh = p.c.ln_out_b + col;
-          float2 y[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float2 dd = fadd2(make_float2(__uint_as_float(v[t * 8 + 2 * u]), __uint_as_float(v[t * 8 + 2 * u + 1])), nmean2b);
-            y[u] = ffma2(fmul2(dd, rstd2vb), make_float2(gg[2 * u], gg[2 * u + 1]), make_float2(hh[2 * u], hh[2 * u + 1]));
-          }
-          uint4 pk;
-          pk.x = pack_bf16x2(y[0].x, y[0].y); pk.y = pack_bf16x2(y[1].x, y[1].y);
-          pk.z = pack_bf16x2(y[2].x, y[2].y); pk.w = pack_bf16x2(y[3].x, y[3].y);
-          *reinterpret_cast<uint4*>(ob + stg_off(lane, t)) = pk;
-        }
+        eb_e2_stage(v, rb0, rb1, rowb, sw, sum2, sq2);
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0 && valid) {
-          tma_store_2d(&tmA, buf(0), cb, row0);
+        if (lane == 0 && valid) {                                // two bulk groups: buf(0) is reused first
+          tma_store_2d(&tmX, buf(0), cb, row0);
+          bulk_commit_group();
+          tma_store_2d(&tmX, buf(1), cb + 32, row0);
           bulk_commit_group();
         }
+        EB_S(s2[0]);
+        if (p.has_ln_out) {
+          float mean2, rstd2;
+          eb_row_stats(th + 8, cq, q, make_float2(sum2.x + sum2.y, sq2.x + sq2.y), mean2, rstd2);
+          EB_S(s2[1]);
+          EB_CQ_SWITCH(cq, eb_e2_norm<AFFINE>(CQ, p, mean2, rstd2, v));
+          EB_S(s2[2]);
+          if (lane == 0) bulk_wait_group_read<1>();              // the first x store has read buf(0)
+          __syncwarp();
+          EB_S(s2[3]);
+#pragma unroll
+          for (int t = 0; t < 8; ++t)
+            sts128(rb0 + rowb + ((static_cast<uint32_t>(t) << 4) ^ sw), v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && valid) {
+            tma_store_2d(&tmA, buf(0), cb, row0);
+            bulk_commit_group();
+          }
+          EB_S(s2[4]);
+        }
       }
-      // the next tile's residual slice lands in the same buffers once the stores have read them
+      // the next tile's residual slice lands in the same tiles once the stores have read them (buf(1) first)
       if (lane == 0) {
         const int nt = tile + gridDim.x;
-        if (nt < p.n_tiles) {
-          bulk_wait_group_read<0>();
-          load_resid(nt);
+        if (nt < p.n_tiles && nt * 128 + q * 32 < p.M) {
+          if (p.has_ln_out) { bulk_wait_group_read<1>(); load_resid_c(nt, 1); bulk_wait_group_read<0>(); load_resid_c(nt, 0); }
+          else { bulk_wait_group_read<0>(); load_resid_c(nt, 0); load_resid_c(nt, 1); }
         }
       }
       __syncwarp();
+      EB_S(s2[5]);
       EB_T(e_w2);
     }
     if (timing && lane == 0) {
       g_eb_prof[0] += e_g1; g_eb_prof[1] += e_res; g_eb_prof[2] += e_w1; g_eb_prof[3] += e_af; g_eb_prof[4] += e_he;
       g_eb_prof[5] += e_ff; g_eb_prof[6] += e_xf; g_eb_prof[7] += e_w2; g_eb_prof[8] += it;
+#ifdef KIRI_EB_SUBPHASE
+      for (int i = 0; i < 7; ++i) g_eb_prof[16 + i] += s1[i];
+      for (int i = 0; i < 6; ++i) g_eb_prof[23 + i] += s2[i];
+#endif
     }
     if (lane == 0) bulk_wait_group<0>();
   }
@@ -571,11 +643,15 @@ int launch_encoder_block(const void* o, float* x, void* a_out, const void* wo, c
   KIRI_REQUIRE(smem <= gemm_tc_max_smem(), "encoder_block: %d bytes of shared memory needed, %d available", smem, gemm_tc_max_smem());
   static bool configured = false;
   if (!configured) {
-    KIRI_CHECK_CUDA(cudaFuncSetAttribute(encoder_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    KIRI_CHECK_CUDA(cudaFuncSetAttribute(encoder_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    KIRI_CHECK_CUDA(cudaFuncSetAttribute(encoder_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   const int grid = p.n_tiles < sms ? p.n_tiles : sms;
-  KIRI_CHECK_CUDA(launch_pdl(encoder_block_kernel, dim3(grid), dim3(kEbThreads), smem, stream, tmO, tmWo, tmW1, tmW2, tmX, tmA, p));
+  if (consts_host->affine)
+    KIRI_CHECK_CUDA(launch_pdl(encoder_block_kernel<true>, dim3(grid), dim3(kEbThreads), smem, stream, tmO, tmWo, tmW1, tmW2, tmX, tmA, p));
+  else
+    KIRI_CHECK_CUDA(launch_pdl(encoder_block_kernel<false>, dim3(grid), dim3(kEbThreads), smem, stream, tmO, tmWo, tmW1, tmW2, tmX, tmA, p));
   return 0;
 }
 
@@ -593,6 +669,12 @@ int encoder_block_consts(EbConst* out, const float* bo, const float* b1, const f
   if (ln_out_g && ln_out_b) {
     KIRI_CHECK_CUDA(cudaMemcpy(out->ln_out_g, ln_out_g, 256 * 4, cudaMemcpyDeviceToHost));
     KIRI_CHECK_CUDA(cudaMemcpy(out->ln_out_b, ln_out_b, 256 * 4, cudaMemcpyDeviceToHost));
+  }
+  // identity affines (gain 1, shift 0: the caller folded them into the weights) select the kernel that skips them
+  out->affine = 0;
+  for (int i = 0; i < 256; ++i) {
+    if (out->ln_mid_g[i] != 1.0f || out->ln_mid_b[i] != 0.0f) out->affine = 1;
+    if (ln_out_g && ln_out_b && (out->ln_out_g[i] != 1.0f || out->ln_out_b[i] != 0.0f)) out->affine = 1;
   }
   return 0;
 }
@@ -628,11 +710,11 @@ extern "C" int kiri_encoder_block_soak(const void* o_bf16, float* x_f32, void* a
 
 // Debug: phase cycles of CTA 0 accumulated since the last call (KIRI_GEMM_TIMING=1).
 extern "C" int kiri_debug_eb_timing(long long* out_host, int n) {
-  long long buf[16];
+  long long buf[32];
   if (cudaDeviceSynchronize() != cudaSuccess) return -2;
   if (cudaMemcpyFromSymbol(buf, kiri::g_eb_prof, sizeof(buf)) != cudaSuccess) return -2;
-  for (int i = 0; i < n && i < 16; ++i) out_host[i] = buf[i];
-  long long zero[16] = {0};
+  for (int i = 0; i < n && i < 32; ++i) out_host[i] = buf[i];
+  long long zero[32] = {0};
   if (cudaMemcpyToSymbol(kiri::g_eb_prof, zero, sizeof(zero)) != cudaSuccess) return -2;
   return 0;
 }

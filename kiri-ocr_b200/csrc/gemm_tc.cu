@@ -240,6 +240,7 @@ gemm_tc_kernel(const __grid_constant__ ProblemSet P, const __grid_constant__ CUt
     // whole warp in the loop, one elected lane issues: descriptors are built in uniform registers
     {
       const uint32_t idesc = umma_idesc_bf16(kTileM, bn);
+      const int k16 = g0.k16;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -274,6 +275,7 @@ gemm_tc_kernel(const __grid_constant__ ProblemSet P, const __grid_constant__ CUt
             for (int c = 0; c < CPS; ++c) {
 #pragma unroll
               for (int h = 0; h < KC / 16; ++h) {
+                if (h >= k16) break;                // zero-filled tail of the chunk (conv2: channels 48..63): nothing to add
                 const uint64_t ad = umma_desc_kmajor(a_addr + c * kATileBytes + h * 32, kSBO, kLayout);
                 const uint64_t bd = umma_desc_kmajor(b_addr + c * b_chunk_bytes + h * 32, kSBO, kLayout);
                 umma_bf16(d_tmem, ad, bd, idesc, (kb | c | h) != 0 ? 1u : 0u);
@@ -743,6 +745,7 @@ static int prep_problem(const GemmLaunch& L, bool is_gemm, int KC, bool a_multi,
   g.OH = L.OH; g.OW = L.OW;
   g.sw = L.sw; g.sh = L.sh; g.pad = L.pad; g.kw = L.kw; g.taps = L.kw * L.kh;
   g.chunks_per_tap = chunks; g.cgs = chunks / CPS;
+  g.k16 = (L.Cin_mem > 0 && L.Cin_mem < L.Cin && chunks == 1) ? (L.Cin_mem + 15) / 16 : KC / 16;
   KIRI_REQUIRE(chunks % CPS == 0, "gemm_tc: %d chunks per tap not divisible by %d", chunks, CPS);
   g.segs_per_row = (L.OW + g.SEG - 1) / g.SEG;
   g.segs_per_img = ((L.OH + g.R - 1) / g.R) * g.segs_per_row;

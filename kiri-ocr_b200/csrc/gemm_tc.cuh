@@ -42,6 +42,7 @@ struct ConvGeom {
   int taps;            // kw*kh (9 or 1)
   int chunks_per_tap;  // Cin / 32
   int cgs;             // chunk groups per tap = chunks_per_tap / CPS
+  int k16;             // 16-wide K steps of a chunk that hold data (KC/16, fewer when the TMA box zero-fills the chunk's tail)
 };
 
 struct EpiParams {

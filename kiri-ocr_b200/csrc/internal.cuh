@@ -22,6 +22,7 @@ int gemm_call(const void* a, const void* w, const float* bias, int M, int N, int
 // encoder_block.cu: out_proj + LN + FFN + LN of one encoder layer in one kernel
 struct EbConst {             // per-layer biases / LayerNorm affines, passed by value in the kernel parameters
   float bo[256], b2[256], ln_mid_g[256], ln_mid_b[256], ln_out_g[256], ln_out_b[256], b1[1024];
+  int affine;                // 0: both LayerNorm affines are the identity (folded into the weights by the caller)
 };
 int encoder_block_consts(EbConst* out, const float* bo, const float* b1, const float* b2, const float* ln_mid_g,
                          const float* ln_mid_b, const float* ln_out_g, const float* ln_out_b, int FF);

@@ -97,14 +97,31 @@ class PackedWeights:
             setattr(W, f"{name}_b", dev_f32(b))
         W.pos_table = dev_f32(pos_table(cfg.IMG_H // 8, max_t, D))
         W.enc_ln_in_g, W.enc_ln_in_b = dev_f32(sd["enc_ln_in.weight"]), dev_f32(sd["enc_ln_in.bias"])
+        # The affine of norm2 is folded into linear1 and, from layer 1 on, the affine of norm1 into the QKV projection
+        # (W' = W diag(g), b' = b + W beta, in fp64 from the fp32 checkpoint, rounded to bf16 once): the encoder-tail
+        # kernel's two LayerNorms are then pure normalisations and the library is handed identity affines for them
+        # (csrc/encoder_block.cu picks its parameter-free epilogue when it sees gain 1 / shift 0).  Layer 0's norm1 is
+        # applied by the pool + LayerNorm kernel and keeps its affine.
+        ones, zeros = torch.ones(D), torch.zeros(D)
+
+        def folded(w, b, g, beta):
+            w64 = w.double()
+            return (w64 * g.double()[None, :]).float(), (b.double() + w64 @ beta.double()).float()
+
         for l in range(enc_layers):
             p, L = f"enc.layers.{l}", W.enc[l]
-            L.wqkv, L.bqkv = dev_bf16(sd[f"{p}.self_attn.in_proj_weight"]), dev_f32(sd[f"{p}.self_attn.in_proj_bias"])
+            wqkv, bqkv = sd[f"{p}.self_attn.in_proj_weight"], sd[f"{p}.self_attn.in_proj_bias"]
+            if l > 0:
+                wqkv, bqkv = folded(wqkv, bqkv, sd[f"{p}.norm1.weight"], sd[f"{p}.norm1.bias"])
+                L.ln1_g, L.ln1_b = dev_f32(ones), dev_f32(zeros)
+            else:
+                L.ln1_g, L.ln1_b = dev_f32(sd[f"{p}.norm1.weight"]), dev_f32(sd[f"{p}.norm1.bias"])
+            L.wqkv, L.bqkv = dev_bf16(wqkv), dev_f32(bqkv)
             L.wo, L.bo = dev_bf16(sd[f"{p}.self_attn.out_proj.weight"]), dev_f32(sd[f"{p}.self_attn.out_proj.bias"])
-            L.w1, L.b1 = dev_bf16(sd[f"{p}.linear1.weight"]), dev_f32(sd[f"{p}.linear1.bias"])
+            w1, b1 = folded(sd[f"{p}.linear1.weight"], sd[f"{p}.linear1.bias"], sd[f"{p}.norm2.weight"], sd[f"{p}.norm2.bias"])
+            L.w1, L.b1 = dev_bf16(w1), dev_f32(b1)
             L.w2, L.b2 = dev_bf16(sd[f"{p}.linear2.weight"]), dev_f32(sd[f"{p}.linear2.bias"])
-            L.ln1_g, L.ln1_b = dev_f32(sd[f"{p}.norm1.weight"]), dev_f32(sd[f"{p}.norm1.bias"])
-            L.ln2_g, L.ln2_b = dev_f32(sd[f"{p}.norm2.weight"]), dev_f32(sd[f"{p}.norm2.bias"])
+            L.ln2_g, L.ln2_b = dev_f32(ones), dev_f32(zeros)
         W.enc_ln_g, W.enc_ln_b = dev_f32(sd["enc_ln.weight"]), dev_f32(sd["enc_ln.bias"])
         W.ctc_ln_g, W.ctc_ln_b = dev_f32(sd["ctc_head.0.weight"]), dev_f32(sd["ctc_head.0.bias"])
         cw = torch.zeros(self.Cp, D)

@@ -42,24 +42,66 @@ __device__ __forceinline__ double tri_weight(int x, int xmin, double center, dou
   arg = fabs(arg);
   return arg < 1.0 ? __dsub_rn(1.0, arg) : 0.0;
 }
+// Resample geometry of one axis: the two divisions of Pillow's precompute_coeffs, done ONCE per CTA (they were done by
+// every coefficient thread: a double-precision division is ~100 instructions on this part).
+struct AxisGeom { double scale, fs, ss; };
+__device__ __forceinline__ AxisGeom axis_geom(int in_size, int out_size) {
+  AxisGeom g;
+  g.scale = __ddiv_rn(static_cast<double>(in_size), static_cast<double>(out_size));
+  g.fs = g.scale < 1.0 ? 1.0 : g.scale;
+  g.ss = __ddiv_rn(1.0, g.fs);
+  return g;
+}
+// int(0.5 + (w / ww) * 2^22) with w / ww correctly rounded, as Pillow computes it - but through ONE reciprocal per output
+// index: d' = w * RN(1/ww) is within 2^-51 of RN(w/ww), i.e. 0.5 + d' * 2^22 is within 1e-8 of the exact path, so the
+// truncated integer can only differ when the value sits within 1e-8 of an integer; those (and anything within 1e-6) take
+// the exact division.  Bit-exact with the division-per-tap form by construction.
+__device__ __forceinline__ int quant_weight(double w, double ww, double inv_ww) {
+  double v = __dadd_rn(0.5, __dmul_rn(__dmul_rn(w, inv_ww), 4194304.0));
+  int q = __double2int_rz(v);
+  const double f = v - static_cast<double>(q);
+  if (f < 1e-6 || f > 1.0 - 1e-6) {
+    v = __dadd_rn(0.5, __dmul_rn(__ddiv_rn(w, ww), 4194304.0));
+    q = __double2int_rz(v);
+  }
+  return q;
+}
 // writes taps [0, ksize) for output index xx into k[tap * kstride]
-__device__ __forceinline__ int fill_coefs(int xx, int in_size, int out_size, int ksize, int* k,
-                                          int kstride) {
-  const double scale = __ddiv_rn(static_cast<double>(in_size), static_cast<double>(out_size));
-  const double fs = scale < 1.0 ? 1.0 : scale;
-  const double ss = __ddiv_rn(1.0, fs);
+__device__ __forceinline__ int fill_coefs(int xx, const AxisGeom& g, int in_size, int ksize, int* k, int kstride) {
   double center;
-  const Coef c = coef_bounds(xx, scale, fs, in_size, center);
+  const Coef c = coef_bounds(xx, g.scale, g.fs, in_size, center);
   double ww = 0.0;
-  for (int x = 0; x < c.n; ++x) ww = __dadd_rn(ww, tri_weight(x, c.xmin, center, ss));
-  for (int x = 0; x < ksize; ++x) {
-    int q = 0;
-    if (x < c.n) {
-      double w = tri_weight(x, c.xmin, center, ss);
-      if (ww != 0.0) w = __ddiv_rn(w, ww);
-      q = __double2int_rz(__dadd_rn(0.5, __dmul_rn(w, 4194304.0)));
+  double wv[8];
+  const bool small = c.n <= 8;                      // (every line-recognition shape: support <= 3.5 source pixels)
+  if (small) {
+#pragma unroll
+    for (int x = 0; x < 8; ++x) {
+      wv[x] = 0.0;
+      if (x < c.n) { wv[x] = tri_weight(x, c.xmin, center, g.ss); ww = __dadd_rn(ww, wv[x]); }
     }
-    k[x * kstride] = q;
+  } else {
+    for (int x = 0; x < c.n; ++x) ww = __dadd_rn(ww, tri_weight(x, c.xmin, center, g.ss));
+  }
+  const double inv_ww = ww != 0.0 ? __ddiv_rn(1.0, ww) : 0.0;
+  if (small) {
+#pragma unroll
+    for (int x = 0; x < 8; ++x) {
+      if (x < ksize) {
+        int q = 0;
+        if (x < c.n) q = ww != 0.0 ? quant_weight(wv[x], ww, inv_ww) : __double2int_rz(__dadd_rn(0.5, __dmul_rn(wv[x], 4194304.0)));
+        k[x * kstride] = q;
+      }
+    }
+    for (int x = 8; x < ksize; ++x) k[x * kstride] = 0;
+  } else {
+    for (int x = 0; x < ksize; ++x) {
+      int q = 0;
+      if (x < c.n) {
+        const double w = tri_weight(x, c.xmin, center, g.ss);
+        q = ww != 0.0 ? quant_weight(w, ww, inv_ww) : __double2int_rz(__dadd_rn(0.5, __dmul_rn(w, 4194304.0)));
+      }
+      k[x * kstride] = q;
+    }
   }
   return c.xmin;
 }
@@ -102,7 +144,7 @@ crop_sum_kernel(const uint8_t* __restrict__ src, const KiriCropDesc* __restrict_
   if (lane == 0 && local) atomicAdd(&sums[blockIdx.x], static_cast<unsigned long long>(local));
 }
 
-__global__ void __launch_bounds__(kPreThreads)
+__global__ void __launch_bounds__(kPreThreads, 4)
 preprocess_pack_kernel(const uint8_t* __restrict__ src, const KiriCropDesc* __restrict__ descs,
                        int img_h, uint8_t* __restrict__ planes,
                        __nv_bfloat16* __restrict__ norm_out, int smem_bytes,
@@ -127,10 +169,12 @@ preprocess_pack_kernel(const uint8_t* __restrict__ src, const KiriCropDesc* __re
   // ---------------- coefficient geometry ----------------
   const bool do_h = (nw != w);
   const bool do_v = (h != img_h);
-  const double hscale = static_cast<double>(w) / static_cast<double>(nw);
-  const double vscale = static_cast<double>(h) / static_cast<double>(img_h);
-  const int ksize_h = do_h ? (static_cast<int>(ceil(hscale < 1.0 ? 1.0 : hscale)) * 2 + 1) : 1;
-  const int ksize_v = do_v ? (static_cast<int>(ceil(vscale < 1.0 ? 1.0 : vscale)) * 2 + 1) : 1;
+  __shared__ AxisGeom geom[2];                     // [0] horizontal (w -> nw), [1] vertical (h -> img_h)
+  if (tid == 0) geom[0] = axis_geom(w, nw);
+  if (tid == 32) geom[1] = axis_geom(h, img_h);
+  __syncthreads();
+  const int ksize_h = do_h ? (static_cast<int>(ceil(geom[0].fs)) * 2 + 1) : 1;
+  const int ksize_v = do_v ? (static_cast<int>(ceil(geom[1].fs)) * 2 + 1) : 1;
   const int Ws = d.strip_w;                               // output columns per strip (host-chosen)
 
   // shared-memory carve (all 16-byte aligned)
@@ -139,118 +183,150 @@ preprocess_pack_kernel(const uint8_t* __restrict__ src, const KiriCropDesc* __re
   int* ymin = reinterpret_cast<int*>(sm + off);    off += ((img_h * 4 + 15) & ~15);
   int* kh = reinterpret_cast<int*>(sm + off);      off += ((Ws * ksize_h * 4 + 15) & ~15);
   int* xmin = reinterpret_cast<int*>(sm + off);    off += ((Ws * 4 + 15) & ~15);
-  uint8_t* inter = sm + off;                       off += ((h * Ws + 15) & ~15);
+  const int Wi = (Ws + 3) & ~3;                           // row pitch of the intermediate (whole 32-bit words)
+  uint8_t* inter = sm + off;                       off += ((h * Wi + 15) & ~15);
   uint8_t* srow = sm + off;                        // staged source rows: as many as the budget holds
+  const int warp = tid >> 5, lane = tid & 31;
+  constexpr int kWarps = kPreThreads / 32;
 
   if (do_v) {
-    for (int y = tid; y < img_h; y += kPreThreads) ymin[y] = fill_coefs(y, h, img_h, ksize_v, kv + y * ksize_v, 1);
+    const AxisGeom gv = geom[1];
+    for (int y = tid; y < img_h; y += kPreThreads) ymin[y] = fill_coefs(y, gv, h, ksize_v, kv + y * ksize_v, 1);
   }
 
-  {
-    const int c0 = strip0;
-    const int cw = (Wout - c0) < Ws ? (Wout - c0) : Ws;
-    __syncthreads();
-    // horizontal coefficients of this strip, tap-major so lanes hit consecutive banks
-    if (do_h) {
-      for (int x = tid; x < cw; x += kPreThreads) xmin[x] = fill_coefs(c0 + x, w, nw, ksize_h, kh + x, Ws);
-    } else {
-      for (int x = tid; x < cw; x += kPreThreads) xmin[x] = c0 + x;
-    }
-    __syncthreads();
-    const int sx0 = xmin[0];                                  // first source column needed
-    const int sx1 = do_h ? (xmin[cw - 1] + ksize_h) : (c0 + cw);
-    const int span = (sx1 < w ? sx1 : w) - sx0;               // source columns to stage
-    // all rows of the strip in ONE staging phase when they fit (typical lines: 3 barriers per CTA
-    // instead of 2 per 8 rows, and every load of the strip in flight at once)
-    const int srow_cap = (span + 4 + 3 + 15) & ~15;           // bytes per staged row (4-byte alignment head + tail)
-    int rows_blk = (smem_bytes - off) / srow_cap;
-    if (rows_blk > h) rows_blk = h;
-    if (rows_blk < 1) rows_blk = 1;
+  const int c0 = strip0;
+  const int cw = (Wout - c0) < Ws ? (Wout - c0) : Ws;
+  // horizontal coefficients of this strip, tap-major so lanes hit consecutive banks
+  if (do_h) {
+    const AxisGeom gh = geom[0];
+    for (int x = tid; x < cw; x += kPreThreads) xmin[x] = fill_coefs(c0 + x, gh, w, ksize_h, kh + x, Ws);
+  } else {
+    for (int x = tid; x < cw; x += kPreThreads) xmin[x] = c0 + x;
+  }
+  __syncthreads();
+  const int sx0 = xmin[0];                                  // first source column needed
+  const int sx1 = do_h ? (xmin[cw - 1] + ksize_h) : (c0 + cw);
+  const int span = (sx1 < w ? sx1 : w) - sx0;               // source columns to stage
+  // all rows of the strip in ONE staging phase when they fit (typical lines: 3 barriers per CTA
+  // instead of 2 per 8 rows, and every load of the strip in flight at once)
+  const int srow_cap = (span + 4 + 3 + 15) & ~15;           // bytes per staged row (4-byte alignment head + tail)
+  int rows_blk = (smem_bytes - off - 16) / srow_cap;         // 16 bytes of slack: zero-weight taps may read past the last row
+  if (rows_blk > h) rows_blk = h;
+  if (rows_blk < 1) rows_blk = 1;
+  const uintptr_t a0 = reinterpret_cast<uintptr_t>(crop + sx0);
+  const uint32_t srow_a = smem_u32(srow), inter_a = smem_u32(inter);     // shared-window addresses for the inner loops
+  const int head0 = static_cast<int>(a0 & 3), dhead = d.pitch & 3;   // a staged row starts `head` bytes into its first word
 
-    for (int r0 = 0; r0 < h; r0 += rows_blk) {
-      const int nr = (h - r0) < rows_blk ? (h - r0) : rows_blk;
-      // stage rows r0..r0+nr, columns sx0..sx0+span, inverted if needed, with 32-bit loads
-      {
-        const int wpr = srow_cap >> 2;                          // word slots per staged row
-        for (int idx = tid; idx < nr * wpr; idx += kPreThreads) {
-          const int rr = idx / wpr, i = idx - rr * wpr;
-          const uint8_t* row = crop + static_cast<size_t>(r0 + rr) * d.pitch + sx0;
-          const uintptr_t a = reinterpret_cast<uintptr_t>(row);
-          const int head = static_cast<int>(a & 3);
-          if (i < ((head + span + 3) >> 2))
-            reinterpret_cast<uint32_t*>(srow + rr * srow_cap)[i] = __ldg(reinterpret_cast<const uint32_t*>(a - head) + i) ^ inv_mask;
-        }
-      }
-      __syncthreads();
-      // horizontal pass -> inter[r][x].  A thread owns ONE output column (x = tid mod 128) and walks
-      // the rows: xmin / tap count / up to 8 coefficients live in registers, no per-pixel division.
-      {
-        const int x = tid & 127, rg = tid >> 7;                // strips are <= 128 columns wide
-        if (x < cw) {
-          const int xm = xmin[x];
-          const int kmax = do_h ? (ksize_h < w - xm ? ksize_h : w - xm) : 1;   // taps beyond the row carry weight 0
-          int kc[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) kc[k] = (do_h && k < kmax) ? kh[k * Ws + x] : 0;
-          const uintptr_t a0 = reinterpret_cast<uintptr_t>(crop + sx0);
-          for (int rr = rg; rr < nr; rr += kPreThreads / 128) {
-            const int head = static_cast<int>((a0 + static_cast<uintptr_t>(r0 + rr) * d.pitch) & 3);
-            const uint8_t* s = srow + rr * srow_cap + head + (xm - sx0);
-            uint8_t o;
-            if (do_h) {
-              int acc = 1 << (kPrecisionBits - 1);
-              if (kmax <= 8) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                  if (k < kmax) acc += static_cast<int>(s[k]) * kc[k];
-              } else {
-                for (int k = 0; k < kmax; ++k) acc += static_cast<int>(s[k]) * kh[k * Ws + x];
-              }
-              o = clip8(acc);
-            } else {
-              o = s[0];
-            }
-            inter[(r0 + rr) * Ws + x] = o;
-          }
-        }
-      }
-      __syncthreads();
+  for (int r0 = 0; r0 < h; r0 += rows_blk) {
+    const int nr = (h - r0) < rows_blk ? (h - r0) : rows_blk;
+    // stage rows r0..r0+nr, columns sx0..sx0+span, inverted if needed: a warp per row, 32-bit loads from the
+    // word-aligned address at or below the row's first byte
+    for (int rr = warp; rr < nr; rr += kWarps) {
+      const int head = (head0 + (r0 + rr) * dhead) & 3;
+      const uint32_t* gw = reinterpret_cast<const uint32_t*>(a0 + static_cast<uintptr_t>(r0 + rr) * d.pitch - head);
+      const uint32_t sa = srow_a + rr * srow_cap;
+      const int nwords = (head + span + 3) >> 2;
+      for (int i = lane; i < nwords; i += 32) sts_u32(sa + 4 * i, __ldg(gw + i) ^ inv_mask);
     }
-    // vertical pass -> plane rows: same column ownership, the row's coefficients are a warp broadcast
+    __syncthreads();
+    // horizontal pass -> inter[r][x].  A thread owns ONE output column (x = tid mod 128) and walks
+    // the rows: xmin / tap count / up to 8 coefficients live in registers, no per-pixel division.
     {
-      const int x = tid & 127, rg = tid >> 7;
+      const int x = tid & 127, rg = tid >> 7;                // strips are <= 128 columns wide
       if (x < cw) {
-        for (int y = rg; y < img_h; y += kPreThreads / 128) {
-          uint8_t o;
-          if (do_v) {
+        const int xm = xmin[x];
+        const int kmax = do_h ? (ksize_h < w - xm ? ksize_h : w - xm) : 1;   // taps beyond the row carry weight 0
+        int kc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) kc[k] = (do_h && k < kmax) ? kh[k * Ws + x] : 0;
+        const uint32_t sb = srow_a + (xm - sx0);
+        const uint32_t ib = inter_a + r0 * Wi + x;
+        for (int rr = rg; rr < nr; rr += kPreThreads / 128) {
+          const uint32_t s = sb + rr * srow_cap + ((head0 + (r0 + rr) * dhead) & 3);
+          uint32_t o;
+          if (do_h) {
             int acc = 1 << (kPrecisionBits - 1);
-            const int y0 = ymin[y];
-            const int kmax = ksize_v < h - y0 ? ksize_v : h - y0;
-            const int* kr = kv + y * ksize_v;
-            const uint8_t* col = inter + y0 * Ws + x;
-            for (int k = 0; k < kmax; ++k) acc += static_cast<int>(col[k * Ws]) * kr[k];
+            if (kmax <= 8) {
+              // taps past kmax carry coefficient 0 and read bytes inside the staged row's slack: no predicates
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                if (k < ksize_h) acc += static_cast<int>(lds_u8(s + k)) * kc[k];
+            } else {
+              for (int k = 0; k < kmax; ++k) acc += static_cast<int>(lds_u8(s + k)) * kh[k * Ws + x];
+            }
             o = clip8(acc);
           } else {
-            o = inter[y * Ws + x];
+            o = lds_u8(s);
           }
-          plane[y * Wb + c0 + x] = o;
-          if (nplane) {
-            const float f = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(o), 255.0f), 0.5f), 0.5f);
-            nplane[y * Wb + c0 + x] = __float2bfloat16_rn(f);
+          sts_u8(ib + rr * Wi, o);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // vertical pass -> plane rows.  A lane owns FOUR adjacent columns (one 32-bit word of the intermediate, one 32-bit store),
+  // a warp walks output rows: the row's taps and coefficients are warp-uniform, one shared load feeds four accumulators.
+  {
+    const int nwq = (cw + 3) >> 2, wq = Wi >> 2;
+    const int col = c0 + 4 * lane;                            // first of this lane's columns in the plane
+    if (lane < nwq) {
+      for (int y = warp; y < img_h; y += kWarps) {
+        uint32_t word;
+        if (do_v) {
+          const int y0 = ymin[y];
+          const int kmax = ksize_v < h - y0 ? ksize_v : h - y0;
+          const int* kr = kv + y * ksize_v;
+          const uint32_t cp = inter_a + 4 * (y0 * wq + lane);
+          int a[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) a[j] = 1 << (kPrecisionBits - 1);
+          for (int k = 0; k < kmax; ++k) {
+            const uint32_t v = lds_u32(cp + 4 * k * wq);
+            const int c = kr[k];
+            a[0] += static_cast<int>(v & 255u) * c;
+            a[1] += static_cast<int>((v >> 8) & 255u) * c;
+            a[2] += static_cast<int>((v >> 16) & 255u) * c;
+            a[3] += static_cast<int>(v >> 24) * c;
           }
+          word = static_cast<uint32_t>(clip8(a[0])) | (static_cast<uint32_t>(clip8(a[1])) << 8) |
+                 (static_cast<uint32_t>(clip8(a[2])) << 16) | (static_cast<uint32_t>(clip8(a[3])) << 24);
+        } else {
+          word = lds_u32(inter_a + 4 * (y * wq + lane));
+        }
+        // columns of the last word past the resized width are padding (gray 128, model.py:329-330)
+        if (col + 4 > Wout) {
+#pragma unroll
+          for (int j = 1; j < 4; ++j)
+            if (col + j >= Wout) word = (word & ~(255u << (8 * j))) | (128u << (8 * j));
+        }
+        *reinterpret_cast<uint32_t*>(plane + y * Wb + col) = word;
+        if (nplane) {
+          __nv_bfloat162 lo, hi;
+          auto nrm = [](uint32_t o) { return __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(o), 255.0f), 0.5f), 0.5f); };
+          lo = __floats2bfloat162_rn(nrm(word & 255u), nrm((word >> 8) & 255u));
+          hi = __floats2bfloat162_rn(nrm((word >> 16) & 255u), nrm(word >> 24));
+          uint2 pkd;
+          pkd.x = *reinterpret_cast<uint32_t*>(&lo);
+          pkd.y = *reinterpret_cast<uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(nplane + y * Wb + col) = pkd;
         }
       }
     }
   }
-  // gray-128 padding on the right (model.py:329-330)
-  const int padw = Wb - Wout;
-  if (padw > 0 && blockIdx.y == 0) {
+  // gray-128 padding on the right (model.py:329-330), whole words from the first 4-aligned column past the text
+  const int pad0 = (Wout + 3) & ~3;
+  if (pad0 < Wb && blockIdx.y == 0) {
+    const int padq = (Wb - pad0) >> 2;
     const float f = __fdiv_rn(__fsub_rn(__fdiv_rn(128.0f, 255.0f), 0.5f), 0.5f);
-    const __nv_bfloat16 fb = __float2bfloat16_rn(f);
-    for (int idx = tid; idx < img_h * padw; idx += kPreThreads) {
-      const int y = idx / padw, x = idx - y * padw;
-      plane[y * Wb + Wout + x] = 128;
-      if (nplane) nplane[y * Wb + Wout + x] = fb;
+    const __nv_bfloat162 fb2 = __floats2bfloat162_rn(f, f);
+    const uint32_t fbw = *reinterpret_cast<const uint32_t*>(&fb2);
+    for (int y = warp; y < img_h; y += kWarps) {
+      uint32_t* pw = reinterpret_cast<uint32_t*>(plane + y * Wb + pad0);
+      for (int i = lane; i < padq; i += 32) pw[i] = 0x80808080u;
+      if (nplane) {
+        uint2* np = reinterpret_cast<uint2*>(nplane + y * Wb + pad0);
+        for (int i = lane; i < padq; i += 32) np[i] = make_uint2(fbw, fbw);
+      }
     }
   }
 }
@@ -313,7 +389,7 @@ extern "C" int kiri_preprocess_smem_bytes(int w, int h, int nw, int img_h, int W
   off += ((long long)img_h * 4 + 15) & ~15ll;
   off += ((long long)Ws * ksh * 4 + 15) & ~15ll;
   off += ((long long)Ws * 4 + 15) & ~15ll;
-  off += ((long long)h * Ws + 15) & ~15ll;
+  off += ((long long)h * ((Ws + 3) & ~3) + 15) & ~15ll;
   // staged source rows: span of a strip plus slack for the 4-byte alignment head and taps
   const long long span = (long long)ceil((hs < 1.0 ? 1.0 : hs) * Ws) + 2 * ksh + 8;
   const long long per_row = (span + 4 + 15) & ~15ll;

@@ -90,7 +90,7 @@ def _pre_smem(w, h, nw, img_h, Wb, strip, rows=8):
     ksh = np.where(nw != w, np.ceil(np.maximum(hs, 1.0)).astype(np.int64) * 2 + 1, 1)
     ksv = np.where(h != img_h, np.ceil(np.maximum(vs, 1.0)).astype(np.int64) * 2 + 1, 1)
     a16 = lambda v: (v + 15) & ~15          # noqa: E731
-    off = a16(img_h * ksv * 4) + a16(np.full_like(ksv, img_h * 4)) + a16(ws * ksh * 4) + a16(ws * 4) + a16(h * ws)
+    off = a16(img_h * ksv * 4) + a16(np.full_like(ksv, img_h * 4)) + a16(ws * ksh * 4) + a16(ws * 4) + a16(h * ((ws + 3) & ~3))
     span = np.ceil(np.maximum(hs, 1.0) * ws).astype(np.int64) + 2 * ksh + 8
     per_row = a16(span + 4)
     return off + (per_row + 16) * rows

@@ -52,12 +52,13 @@ def conv(n, IH, IW, cin, cout, sh, sw, cin_mem=0):
     fl = 2.0 * n * OH * OW * cout * 9 * cin
     report(f"conv n={n} {IH}x{IW}x{cin}->{cout} s({sh},{sw}) [{fl/ms/1e9:.0f} TF/s padded]", ms, reps)
 
+gemm(26080, 768, 256, 0)
 gemm(40960, 768, 256, 0)
 gemm(40960, 256, 256, 5)
 gemm(40960, 1024, 256, 2)
 gemm(40960, 256, 1024, 5)
 gemm(40960, 208, 256, 4)
-conv(16, 48, 640, 64, 96, 2, 2, 48)
-conv(16, 24, 320, 96, 160, 2, 2)
-conv(16, 12, 160, 160, 256, 2, 1)
+conv(64, 48, 640, 64, 96, 2, 2, 48)
+conv(64, 24, 320, 96, 160, 2, 2)
+conv(64, 12, 160, 160, 256, 2, 1)
 

@@ -323,13 +323,15 @@ int kiri_decode_greedy(KiriHandle* h, const void* mem_bf16, const int* len_est, 
  * rows [mem_row0[b], mem_row0[b] + mem_len[b]) of mem_bf16 [M_total, D] (device int arrays;
  * max_T >= every mem_len).  The cross K/V of a line are re-laid head-major once per batch so the
  * per-step single-query attention reads contiguous [t][32] runs.
- * line_perm (nullable, device int[B]): decode slot -> line.  Sixteen consecutive slots share one
- * thread-block cluster, so listing the lines by decreasing len_est lets every cluster stop early
- * and lets the clusters that do not fit in the first wave hide behind the longest ones. */
+ * line_perm (nullable, device int[n_slots]): decode slot -> line, or -1 for an EMPTY slot.  Sixteen consecutive slots
+ * share one thread-block cluster, so listing the lines by decreasing len_est lets every cluster stop early and lets the
+ * clusters that do not fit in the first wave hide behind the longest ones; a step of a cluster costs a fixed part plus
+ * a part per live line, so leaving slots of the clusters that hold the LONGEST lines empty (n_slots > B) shortens the
+ * decode's critical path.  n_slots = 0: one slot per line.  kiri_decode_multi_workspace_bytes takes the SLOT count. */
 size_t kiri_decode_multi_workspace_bytes(const KiriHandle* h, int B, long long M_total, int Lmax);
 int kiri_decode_greedy_multi(KiriHandle* h, const void* mem_bf16, long long M_total, const int* mem_row0,
-                             const int* mem_len, int max_T, const int* len_est, const int* line_perm, int B, int Lmax,
-                             const KiriDecodeParams* p,
+                             const int* mem_len, int max_T, const int* len_est, const int* line_perm, int n_slots, int B,
+                             int Lmax, const KiriDecodeParams* p,
                              void* workspace, size_t workspace_bytes, int* ids, int* n_out, float* sum_logp,
                              float* step_logp, float* step_prob, const int* forced_ids, int* steps_run_host,
                              int* progress, int publish, cudaStream_t stream);

@@ -105,7 +105,7 @@ _SIGS = {
     "kiri_ctc_collapse_multi": (C.c_int, [vp, vp, C.c_int, vp, vp, vp, vp, vp, vp]),
     "kiri_decode_workspace_bytes": (C.c_size_t, [vp, C.c_int, C.c_int, C.c_int]),
     "kiri_decode_multi_workspace_bytes": (C.c_size_t, [vp, C.c_int, C.c_longlong, C.c_int]),
-    "kiri_decode_greedy_multi": (C.c_int, [vp, vp, C.c_longlong, vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.POINTER(KiriDecodeParams),
+    "kiri_decode_greedy_multi": (C.c_int, [vp, vp, C.c_longlong, vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(KiriDecodeParams),
                                            vp, C.c_size_t, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int), vp, C.c_int, vp]),
     "kiri_decode_beam_workspace_bytes": (C.c_size_t, [vp, C.c_int, C.c_longlong, C.c_int, C.c_int]),
     "kiri_decode_beam_multi": (C.c_int, [vp, vp, C.c_longlong, vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_double,

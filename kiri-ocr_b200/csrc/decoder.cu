@@ -78,9 +78,9 @@ extern "C" size_t kiri_decode_multi_workspace_bytes(const KiriHandle* h, int B, 
 }
 
 extern "C" int kiri_decode_greedy_multi(KiriHandle* h, const void* mem_bf16, long long M_total, const int* mem_row0,
-                                        const int* mem_len, int max_T, const int* len_est, const int* line_perm, int B, int Lmax,
-                                        const KiriDecodeParams* p, void* workspace, size_t workspace_bytes, int* ids,
-                                        int* n_out, float* sum_logp, float* step_logp, float* step_prob,
+                                        const int* mem_len, int max_T, const int* len_est, const int* line_perm, int n_slots,
+                                        int B, int Lmax, const KiriDecodeParams* p, void* workspace, size_t workspace_bytes,
+                                        int* ids, int* n_out, float* sum_logp, float* step_logp, float* step_prob,
                                         const int* forced_ids, int* steps_run_host, int* progress, int publish,
                                         cudaStream_t stream) {
   KIRI_REQUIRE(h && mem_bf16 && mem_row0 && mem_len && len_est && p && workspace && ids && n_out && sum_logp,
@@ -90,14 +90,16 @@ extern "C" int kiri_decode_greedy_multi(KiriHandle* h, const void* mem_bf16, lon
   const KiriDims& d = h->d;
   const KiriWeights& w = h->w;
   const size_t L = d.dec_layers, D = d.dec_dim;
-  KIRI_REQUIRE(workspace_bytes >= kiri_decode_multi_workspace_bytes(h, B, M_total, Lmax),
+  if (n_slots <= 0 || !line_perm) n_slots = B;
+  KIRI_REQUIRE(n_slots >= B && n_slots <= 16 * B + 16, "kiri_decode_greedy_multi: %d decode slots for %d lines", n_slots, B);
+  KIRI_REQUIRE(workspace_bytes >= kiri_decode_multi_workspace_bytes(h, n_slots, M_total, Lmax),
                "kiri_decode_greedy_multi: workspace too small");
   uint8_t* base = reinterpret_cast<uint8_t*>(workspace);
   __nv_bfloat16* crosskv = reinterpret_cast<__nv_bfloat16*>(base);
   size_t off = al256(static_cast<size_t>(M_total) * L * 2 * D * 2);
   __nv_bfloat16* crosskv_hm = reinterpret_cast<__nv_bfloat16*>(base + off); off += al256(static_cast<size_t>(M_total) * L * 2 * D * 2);
-  __nv_bfloat16* self_k = reinterpret_cast<__nv_bfloat16*>(base + off); off += al256(L * B * Lmax * D * 2);
-  __nv_bfloat16* self_v = reinterpret_cast<__nv_bfloat16*>(base + off); off += al256(L * B * Lmax * D * 2);
+  __nv_bfloat16* self_k = reinterpret_cast<__nv_bfloat16*>(base + off); off += al256(L * n_slots * Lmax * D * 2);
+  __nv_bfloat16* self_v = reinterpret_cast<__nv_bfloat16*>(base + off); off += al256(L * n_slots * Lmax * D * 2);
   int* steps_dev = reinterpret_cast<int*>(base + off);
   { ProfScope ps(PS_DEC_CROSSKV, stream);
     KIRI_TRY(gemm_call(mem_bf16, w.crosskv_w, w.crosskv_b, static_cast<int>(M_total), static_cast<int>(L * 2 * D), d.enc_dim,
@@ -107,7 +109,7 @@ extern "C" int kiri_decode_greedy_multi(KiriHandle* h, const void* mem_bf16, lon
   FusedLive live = {publish, progress, 0, nullptr};
   { ProfScope ps_step(PS_DEC_STEP, stream);
     KIRI_TRY(fused_decoder_run(h, crosskv_hm, static_cast<int>(L * 2 * D), mem_row0, mem_len, 0, self_k, self_v, len_est,
-                               forced_ids, line_perm, B, Lmax, p, ids, n_out, sum_logp, step_logp, step_prob, steps_dev,
+                               forced_ids, line_perm, n_slots, Lmax, p, ids, n_out, sum_logp, step_logp, step_prob, steps_dev,
                                cluster_size(), stream, nullptr, 1, &live)); }
   if (steps_run_host) {
     static int* steps_host = nullptr;

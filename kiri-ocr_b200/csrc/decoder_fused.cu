@@ -53,7 +53,7 @@ struct FusedArgs {
   int T;
   __nv_bfloat16 *self_k, *self_v;                     // [layers][B][Lmax][D]
   const int* len_est; const int* forced;
-  const int* line_perm;                               // nullable: decode slot -> line (longest lines first)
+  const int* line_perm;                               // nullable: decode slot -> line (longest lines first; -1 = empty slot)
   int B, Lmax;
   KiriDecodeParams p;
   int *ids, *n_out; float *sum_logp, *step_logp, *step_prob;
@@ -451,8 +451,9 @@ __global__ void __launch_bounds__(kFThreads, 1) dec_fused_kernel(const __grid_co
     const int i = threadIdx.x;
     const int li = i / BEAM, bi = i - li * BEAM;     // line of the cluster, hypothesis of the line
     const int dslot = cid * LPC + li;                // decode order index of the line
-    const bool ok = li < LPC && dslot < A.B;
-    const int b = ok ? (A.line_perm ? A.line_perm[dslot] : dslot) : 0;
+    const int pb = (li < LPC && dslot < A.B) ? (A.line_perm ? A.line_perm[dslot] : dslot) : -1;   // -1: an empty slot
+    const bool ok = pb >= 0;
+    const int b = ok ? pb : 0;
     st->line[i] = b;
     int ms = 0, tl = 0, Tm = A.T, r0 = 0;
     if (ok) {

@@ -356,6 +356,38 @@ class BatchedRecognizer:
         self.launches += self._layer_launches * self.pw.enc_layers + 1 + (1 if (want_logits or stats) else 0)
         return out
 
+    def _slot_table(self, B: int) -> torch.Tensor:
+        """Decode slot -> rank of the line in decreasing len_est order, -1 = empty slot (device int64, cached per B).
+        Cluster k holds min(16, n0 + k) lines: a decode step costs a cluster ~131 k cycles plus ~4 k per live line
+        (profiles/r02_dec_fused_phase_cycles.txt), the decode ends when the cluster with the longest lines does, and
+        15 clusters are co-resident - so the first clusters are kept small: the smallest n0 that still needs at most
+        15 clusters, and n0 = 9 (the optimum of that cost model at 256 lines) when no n0 does."""
+        tab = self._slot_tables.get(B) if hasattr(self, "_slot_tables") else None
+        if tab is not None:
+            return tab
+        if not hasattr(self, "_slot_tables"):
+            self._slot_tables = {}
+        fixed = _os.environ.get("KIRI_DEC_SLOTS_N0")
+
+        def caps(n0):
+            out, left, k = [], B, 0
+            while left > 0:
+                c = min(16, n0 + k, left)
+                out.append(c); left -= c; k += 1
+            return out
+        if fixed:
+            cs = caps(int(fixed))
+        else:
+            cs = next((caps(n0) for n0 in range(1, 17) if len(caps(n0)) <= 15), None) or caps(9)
+        t = np.full(16 * len(cs), -1, np.int64)
+        r = 0
+        for k, c in enumerate(cs):
+            t[16 * k:16 * k + c] = np.arange(r, r + c)
+            r += c
+        tab = torch.from_numpy(t).to(self.device)
+        self._slot_tables[B] = tab
+        return tab
+
     def decode_greedy_multi(self, mem_bf16: torch.Tensor, mem_row0: torch.Tensor, mem_len: torch.Tensor,
                             len_est: torch.Tensor, Lmax: int, max_T: int, select_raw: bool = False,
                             forced: Optional[torch.Tensor] = None, want_steps: bool = False, out=None,
@@ -365,10 +397,14 @@ class BatchedRecognizer:
         kiri_decode_greedy_multi (live streaming)."""
         p = self.decode_params(select_raw)
         B, M = int(len_est.numel()), int(mem_bf16.shape[0])
-        need = self.lib.kiri_decode_multi_workspace_bytes(self.handle, B, M, Lmax)
+        # longest lines first: sixteen consecutive slots share a cluster, and the clusters that hold the longest lines
+        # get fewer of them (see kiri_b200.h); the slot table depends on B only, so nothing here waits for the device
+        table = self._slot_table(B)
+        n_slots = int(table.numel())
+        need = self.lib.kiri_decode_multi_workspace_bytes(self.handle, n_slots, M, Lmax)
         ws = self._workspace(need, "_dws")
-        # longest lines first: sixteen consecutive slots share a cluster (see kiri_b200.h)
-        perm = torch.argsort(len_est, descending=True, stable=True).to(torch.int32)
+        order = torch.argsort(len_est, descending=True, stable=True)
+        perm = torch.where(table >= 0, order[table.clamp(min=0)], table).to(torch.int32)
         if out is not None:
             ids, n_out, sum_lp, slp, spr = out
         else:
@@ -378,8 +414,8 @@ class BatchedRecognizer:
             slp = torch.zeros((B, Lmax), dtype=torch.float32, device=self.device) if want_steps else None
             spr = torch.zeros((B, Lmax), dtype=torch.float32, device=self.device) if want_steps else None
         _lib.check(self.lib.kiri_decode_greedy_multi(self.handle, mem_bf16.data_ptr(), M, mem_row0.data_ptr(),
-                                                     mem_len.data_ptr(), max_T, len_est.data_ptr(), perm.data_ptr(), B, Lmax,
-                                                     C.byref(p),
+                                                     mem_len.data_ptr(), max_T, len_est.data_ptr(), perm.data_ptr(), n_slots, B,
+                                                     Lmax, C.byref(p),
                                                      ws.data_ptr(), need, ids.data_ptr(), n_out.data_ptr(),
                                                      sum_lp.data_ptr(), _lib.ptr(slp), _lib.ptr(spr), _lib.ptr(forced),
                                                      None, progress_ptr, int(publish), _lib.stream_ptr()),

@@ -69,6 +69,30 @@ def test_records_round_trip():
     assert abs(conf[2] - 0.123) < 1e-7
 
 
+@pytest.mark.parametrize("method", ["ctc", "decoder"])
+def test_records_to_results_equals_the_per_line_form(tok_cfg, method):
+    """The vectorised record -> (text, confidence) pass must give exactly what unpack_records + _texts give: lines
+    without a record (None), failed lines (n = -1), empty lines, decoder ids cut at the first EOS, unknown ids."""
+    tok, _ = tok_cfg
+    eng = StubEngine(tok)
+    rng = np.random.default_rng(3)
+    n, lmax = 500, 64
+    lens = rng.integers(0, lmax + 1, n)
+    rec = np.zeros((n, 3 + lmax), np.int32)
+    rec[:, 0], rec[:, 1] = rng.permutation(n), lens
+    for i in range(n):
+        rec[i, 3:3 + lens[i]] = rng.integers(0, tok.vocab_size + 6, lens[i])
+    rec[::41, 1] = -1
+    rec[:, 2] = rng.random(n).astype(np.float32).view(np.int32)
+    rec = torch.from_numpy(rec[rng.random(n) > 0.05])
+    ids, conf = KD.unpack_records(rec, n)
+    want = KD._texts(eng, ids, conf, method)
+    got = KD.records_to_results(eng, rec, n, method)
+    assert len(got) == n and sum(g is None for g in got) == sum(w is None for w in want) > 0
+    for g, w in zip(got, want):
+        assert (g is None and w is None) or g == w
+
+
 def test_two_rank_gloo_gather_restores_order(tok_cfg, tmp_path):
     import json
     from kiri_ocr_b200 import fixtures as FX

@@ -371,6 +371,15 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// Function attributes (the dynamic shared-memory opt-in) belong to a DEVICE's copy of a kernel: launchers cache "already
+// configured" per device ordinal, so a second GPU driven from the same process configures its own copy.
+constexpr int kMaxDevices = 64;
+inline int kiri_cur_device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 0;
+  return dev;
+}
+
 // K-major shared-memory operand descriptor (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) swizzle
 // For 64-byte rows (32 bf16 of K) with SWIZZLE_64B: 8-row groups are 512 B apart (SBO).

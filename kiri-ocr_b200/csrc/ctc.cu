@@ -376,10 +376,11 @@ extern "C" int kiri_ctc_align_score(const float* logits, int ld, int C, const in
   KIRI_REQUIRE(beam >= 1 && beam <= 8 && Lmax > 0 && max_T > 0, "kiri_ctc_align_score: bad sizes");
   if (n_lines == 0) return 0;
   const int smem = max_T * 8 + beam * 3 * (2 * Lmax + 1) * 4;
-  static int configured = 0;
-  if (smem > 48 * 1024 && configured < smem) {
+  static int configured[kiri::kMaxDevices] = {0};
+  const int dslot = kiri::kiri_cur_device_slot();
+  if (smem > 48 * 1024 && configured[dslot] < smem) {
     KIRI_CHECK_CUDA(cudaFuncSetAttribute(kiri::ctc_align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = smem;
+    configured[dslot] = smem;
   }
   kiri::ctc_align_kernel<<<n_lines, 256, smem, stream>>>(logits, ld, C, mem_row0, mem_len, beam, Lmax, bm_ids, bm_len,
                                                          bm_state, vocab_size, unk_ctc_id, out);

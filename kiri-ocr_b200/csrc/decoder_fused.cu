@@ -1040,6 +1040,16 @@ int fused_decoder_build(KiriHandle* h) {
   const int Vp = (d.dec_vocab + 15) / 16 * 16;
   KIRI_REQUIRE(D == 256 && d.dec_heads == kHeads, "fused decoder: DEC_DIM must be 256 with 8 heads");
   KIRI_REQUIRE(FF % 256 == 0 && FF <= 2048, "fused decoder: DEC_FF=%d must be a multiple of 256 (<= 2048)", FF);
+  {
+    // the decode kernel keeps the logits of 16 lines and every bias / LayerNorm affine in shared memory: say so at load
+    // time when a vocabulary does not fit, instead of failing at the first "accurate" call (greedy plan, cluster of 8)
+    int dev = 0, optin = 0;
+    KIRI_CHECK_CUDA(cudaGetDevice(&dev));
+    KIRI_CHECK_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const int need = fused_smem_plan(FF, Vp, 8, L, 0, 0).total;
+    KIRI_REQUIRE(need <= optin, "fused decoder: decoder vocabulary %d (FF %d, %d layers) needs %d bytes of shared memory per CTA, "
+                 "%d available: the attention decoder of this checkpoint cannot run on this build", d.dec_vocab, FF, L, need, optin);
+  }
   size_t words = 0;
   const size_t per_layer = packed_words(3 * D, D) + 3 * packed_words(D, D) + 2 * packed_words(FF, D);
   words = per_layer * L + packed_words(2 * Vp, D);
@@ -1084,10 +1094,11 @@ template <int CS>
 static int launch_fused(const FusedArgs& a, int n_clusters, cudaStream_t stream) {
   const FusedSmem L = fused_smem_plan(a.ff, a.Vp, CS, a.layers, a.bmode ? a.beam : 0, a.Lmax);
   auto kern = dec_fused_kernel<CS>;
-  static int configured = 0;
-  if (configured < L.total) {
+  static int configured[kMaxDevices] = {0};           // per device and cluster size
+  const int dslot = kiri_cur_device_slot();
+  if (configured[dslot] < L.total) {
     KIRI_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-    configured = L.total;
+    configured[dslot] = L.total;
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));

@@ -247,12 +247,15 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
   pdl_trigger();
-  pdl_wait();                                        // o and x come from the previous kernels
+  // o and x come from the previous kernels.  Producer warp 0 only ever loads WEIGHTS (even ring units, see below): it does
+  // not wait, so the first Wo / W1 units are in flight while the previous kernel drains.
+  if (warp != kEbProdWarp0) pdl_wait();
 
   if (warp >= kEbProdWarp0 && warp < kEbProdWarp0 + kEbProdWarps) {
     // ============================ TMA producers ============================
     // Ring units per tile (32 KB each, except the 16 KB o chunks), in the order the MMA warp consumes them:
-    //   o_0 Wo_0 o_1 Wo_1 o_2 Wo_2 o_3 Wo_3 | W1(0,0..3) | W1(1,0..3) W2(0..3) | W1(2,0..3) W2(4..7) | ... | W2(4nG-4 .. 4nG-1)
+    //   Wo_0 o_0 Wo_1 o_1 Wo_2 o_2 Wo_3 o_3 | W1(0,0..3) | W1(1,0..3) W2(0..3) | W1(2,0..3) W2(4..7) | ... | W2(4nG-4 .. 4nG-1)
+    //   (an even number of units per tile and two producers taking them in turn: producer 0 gets the even units = weights only)
     //   W1(g,k) = rows [256g, 256g+256) of W1, K chunk k (64 wide);  W2(c) = all 256 rows of W2, K chunk c (64 hidden columns)
     const int pw = warp - kEbProdWarp0;
     const int units = 8 + 8 * nG;
@@ -267,7 +270,7 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
             uint64_t* fb = &bars->full[slot];
             if (n < 8) {
               const int j = n >> 1;
-              if ((n & 1) == 0) {
+              if ((n & 1) == 1) {
                 mbar_arrive_expect_tx(fb, 16384);
                 tma_load_3d(dst, &tmO, fb, 0, j, tile * 128);
               } else {
@@ -381,7 +384,7 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
         mbar_wait(&bars->full[s1], ph1);
         EB_T(m_ring);
         tc_fence_after();
-        const uint32_t a_addr = ring_addr + s0 * kSlotBytes, b_addr = ring_addr + s1 * kSlotBytes;
+        const uint32_t b_addr = ring_addr + s0 * kSlotBytes, a_addr = ring_addr + s1 * kSlotBytes;   // Wo_j first, then o_j
         if (elect_one()) {
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
@@ -641,11 +644,12 @@ int launch_encoder_block(const void* o, float* x, void* a_out, const void* wo, c
   p.timing = timing_on;
   const int smem = kBarOff + static_cast<int>(sizeof(EbBars));
   KIRI_REQUIRE(smem <= gemm_tc_max_smem(), "encoder_block: %d bytes of shared memory needed, %d available", smem, gemm_tc_max_smem());
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {false};
+  const int dslot = kiri_cur_device_slot();
+  if (!configured[dslot]) {
     KIRI_CHECK_CUDA(cudaFuncSetAttribute(encoder_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     KIRI_CHECK_CUDA(cudaFuncSetAttribute(encoder_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
+    configured[dslot] = true;
   }
   const int grid = p.n_tiles < sms ? p.n_tiles : sms;
   if (consts_host->affine)

@@ -700,10 +700,11 @@ static int launch_inst(const ProblemSet& P, const CUtensorMap& tmB, const CUtens
   KIRI_REQUIRE(stages >= 2, "gemm_tc: stage of %d bytes does not fit twice in shared memory", stage_bytes);
   const int smem = stages * stage_bytes + overhead;
   auto kern = gemm_tc_kernel<KC, NSEG, EPI, BSTAT>;
-  static int configured = 0;
-  if (configured < smem) {
+  static int configured[kMaxDevices] = {0};          // (one array per template instantiation)
+  const int dslot = kiri_cur_device_slot();
+  if (configured[dslot] < smem) {
     KIRI_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
-    configured = g_max_smem;
+    configured[dslot] = g_max_smem;
   }
   int grid = num_m_tiles * num_n_tiles;
   if (grid > g_num_sms) grid = g_num_sms;

@@ -403,7 +403,8 @@ extern "C" int kiri_preprocess_pack(const uint8_t* src, const KiriCropDesc* desc
   KIRI_REQUIRE(src && descs_dev && planes_u8 && crop_sums, "kiri_preprocess_pack: null pointer");
   KIRI_REQUIRE(n_crops >= 0 && img_h > 0 && max_strips >= 1 && max_strips <= 65535, "kiri_preprocess_pack: bad sizes");
   if (n_crops == 0) return 0;
-  static int max_optin = 0;
+  static int max_optin_dev[kMaxDevices] = {0};
+  int& max_optin = max_optin_dev[kiri_cur_device_slot()];
   if (!max_optin) {
     int dev = 0;
     KIRI_CHECK_CUDA(cudaGetDevice(&dev));

@@ -137,6 +137,35 @@ def plan_groups(entries: np.ndarray, cfg: CFG, width_mode: str = "parity"
     return groups
 
 
+def decode_slot_table(B: int, n0: Optional[int] = None, lines_per_cluster: int = 16, resident_clusters: int = 15) -> np.ndarray:
+    """Decode slot -> rank of the line in decreasing ``len_est`` order, -1 = empty slot (int64 [16 * clusters]).
+
+    Sixteen consecutive slots are one thread-block cluster of the persistent decode kernel.  Cluster k holds
+    ``min(16, n0 + k)`` lines: a decode step costs a cluster a fixed part plus a part per live line
+    (profiles/r02_dec_fused_phase_cycles.txt), the decode ends when the cluster with the longest lines does, and
+    ``resident_clusters`` clusters are co-resident on a B200 - so the clusters that hold the longest lines are kept small:
+    the smallest n0 >= 4 that still needs at most ``resident_clusters`` clusters, and n0 = 9 (the measured optimum at 256
+    lines, tools/runs/r2_run28.sh) when no n0 does.  The table depends on B only: building it never waits for the device."""
+    def caps(first):
+        out, left, k = [], B, 0
+        while left > 0:
+            c = min(lines_per_cluster, first + k, left)
+            out.append(c)
+            left -= c
+            k += 1
+        return out
+    if n0 is not None:
+        cs = caps(max(1, int(n0)))
+    else:
+        cs = next((c for c in (caps(f) for f in range(4, lines_per_cluster + 1)) if len(c) <= resident_clusters), None) or caps(9)
+    t = np.full(lines_per_cluster * len(cs), -1, np.int64)
+    r = 0
+    for k, c in enumerate(cs):
+        t[lines_per_cluster * k:lines_per_cluster * k + c] = np.arange(r, r + c)
+        r += c
+    return t
+
+
 class BatchedRecognizer:
     def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: CFG, tokenizer: CharTokenizer,
                  device: str = "cuda", width_mode: str = "parity", stem_chunk: int = 64):
@@ -357,35 +386,15 @@ class BatchedRecognizer:
         return out
 
     def _slot_table(self, B: int) -> torch.Tensor:
-        """Decode slot -> rank of the line in decreasing len_est order, -1 = empty slot (device int64, cached per B).
-        Cluster k holds min(16, n0 + k) lines: a decode step costs a cluster ~131 k cycles plus ~4 k per live line
-        (profiles/r02_dec_fused_phase_cycles.txt), the decode ends when the cluster with the longest lines does, and
-        15 clusters are co-resident - so the first clusters are kept small: the smallest n0 that still needs at most
-        15 clusters, and n0 = 9 (the optimum of that cost model at 256 lines) when no n0 does."""
-        tab = self._slot_tables.get(B) if hasattr(self, "_slot_tables") else None
-        if tab is not None:
-            return tab
+        """Decode slot -> rank of the line in decreasing len_est order, -1 = empty slot (device int64, cached per B);
+        see ``decode_slot_table``."""
         if not hasattr(self, "_slot_tables"):
             self._slot_tables = {}
-        fixed = _os.environ.get("KIRI_DEC_SLOTS_N0")
-
-        def caps(n0):
-            out, left, k = [], B, 0
-            while left > 0:
-                c = min(16, n0 + k, left)
-                out.append(c); left -= c; k += 1
-            return out
-        if fixed:
-            cs = caps(int(fixed))
-        else:
-            cs = next((caps(n0) for n0 in range(1, 17) if len(caps(n0)) <= 15), None) or caps(9)
-        t = np.full(16 * len(cs), -1, np.int64)
-        r = 0
-        for k, c in enumerate(cs):
-            t[16 * k:16 * k + c] = np.arange(r, r + c)
-            r += c
-        tab = torch.from_numpy(t).to(self.device)
-        self._slot_tables[B] = tab
+        tab = self._slot_tables.get(B)
+        if tab is None:
+            fixed = _os.environ.get("KIRI_DEC_SLOTS_N0")
+            tab = torch.from_numpy(decode_slot_table(B, int(fixed) if fixed else None)).to(self.device)
+            self._slot_tables[B] = tab
         return tab
 
     def decode_greedy_multi(self, mem_bf16: torch.Tensor, mem_row0: torch.Tensor, mem_len: torch.Tensor,

@@ -28,6 +28,45 @@ class StubEngine:
         return out
 
 
+    def recognize_pages(self, pages, boxes_list, method="ctc", streaming=False, batch_lines=384):
+        from kiri_ocr_b200.engine import LineError
+        self.calls.append(len(boxes_list))
+        out = []
+        for page, boxes in zip(pages, boxes_list):
+            res = []
+            for (x, y, w, h) in boxes:
+                if w <= 0:
+                    res.append(None)                                              # empty crop: no result
+                elif h == 13:
+                    res.append(LineError("boom"))                                 # a region that failed on its rank
+                else:
+                    ids = np.array([2 + (int(x) % 150), 2 + (int(y) % 150), 2 + int(page) % 150][: 1 + int(w) % 3], np.int32)
+                    res.append(LineResult(self.tok.decode_collapsed_ctc(ids.tolist()), 0.25 + (int(w) % 7) / 10.0, 0.0, ids))
+            out.append(res)
+        return out
+
+
+def _pages_case():
+    rng = np.random.default_rng(5)
+    n_pages = 9
+    boxes = [[(int(rng.integers(0, 500)), int(rng.integers(0, 500)), int(rng.integers(0, 90)), int(rng.integers(10, 40)))
+              for _ in range(int(rng.integers(0, 7)))] for _ in range(n_pages)]
+    boxes[3][0:0] = [(5, 5, 0, 20), (7, 7, 30, 13)]                               # an empty crop and a failing region
+    return list(range(n_pages)), boxes
+
+
+def _pages_worker(rank, world, port, vocab_path, q, texts_on):
+    import torch.distributed as dist
+    from kiri_ocr_b200.config import CharTokenizer
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    eng = StubEngine(CharTokenizer(vocab_path, CFG()))
+    pages, boxes = _pages_case()
+    res = KD.recognize_pages_sharded(eng, pages, boxes, "ctc", texts_on=texts_on)
+    q.put((rank, eng.calls, res))
+    dist.destroy_process_group()
+
+
 def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
@@ -122,3 +161,43 @@ def test_two_rank_gloo_gather_restores_order(tok_cfg, tmp_path):
     want = [(r.text, r.confidence) for r in eng.recognize_packed(None, ent)]
     for (t, c), (wt, wc) in zip(res0, want):
         assert t == wt and abs(c - wc) < 1e-6
+
+
+@pytest.mark.parametrize("texts_on", [None, 0])
+def test_two_rank_gloo_pages_sharded(tok_cfg, tmp_path, texts_on):
+    """recognize_pages_sharded: page-major shards, one exchange, every page's boxes back in order incl. the empty crop
+    (None) and the failed region (LineFailed); texts_on=0 builds the strings on rank 0 only."""
+    import json
+    from kiri_ocr_b200 import fixtures as FX
+    vp = str(tmp_path / "vocab.json")
+    json.dump(FX.make_vocab(), open(vp, "w", encoding="utf-8"), ensure_ascii=False)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pages_worker, args=(r, 2, port, vp, q, texts_on)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, calls0, res0), (_, calls1, res1) = outs
+    pages, boxes = _pages_case()
+    assert calls0[0] + calls1[0] == len(pages) and min(calls0[0], calls1[0]) >= 1
+    if texts_on is None:
+        assert res0 == res1
+    else:
+        assert res1 is None
+    tok, _ = tok_cfg
+    want = StubEngine(tok).recognize_pages(pages, boxes)
+    assert len(res0) == len(pages)
+    for got_p, want_p in zip(res0, want):
+        assert len(got_p) == len(want_p)
+        for g, w in zip(got_p, want_p):
+            if w is None:
+                assert g is None
+            elif not isinstance(w, LineResult):
+                assert g == KD.LineFailed()
+            else:
+                assert g[0] == w.text and abs(g[1] - w.confidence) < 1e-6
+    assert res0[3][0] is None and res0[3][1] == KD.LineFailed()

@@ -91,3 +91,23 @@ def test_plan_groups_buckets_and_smem_mirror():
     for (w, h, nw, strip) in [(853, 64, 640, 640), (2000, 130, 738, 320), (50, 9, 267, 267), (300, 48, 300, 300), (1, 37, 1, 1)]:
         a = int(_pre_smem(np.array([w]), np.array([h]), np.array([nw]), 48, 640, np.array([strip]))[0])
         assert a == lib.kiri_preprocess_smem_bytes(w, h, nw, 48, 640, strip)
+
+
+def test_decode_slot_table_places_every_line_once():
+    """engine.decode_slot_table: every line rank appears exactly once, clusters are 16 slots, the clusters that hold the
+    longest lines (the first ones) hold the fewest, and at most 15 clusters are used whenever 15 x 16 slots suffice."""
+    from kiri_ocr_b200.engine import decode_slot_table
+    for B in (1, 5, 16, 17, 64, 200, 225, 240, 241, 256, 1000):
+        t = decode_slot_table(B)
+        assert t.dtype == np.int64 and len(t) % 16 == 0
+        used = t[t >= 0]
+        assert np.array_equal(used, np.arange(B))                       # rank order is kept: longest lines first
+        per = [(t[i:i + 16] >= 0).sum() for i in range(0, len(t), 16)]
+        assert all(p >= 1 for p in per)
+        assert all(a <= b for a, b in zip(per[:-2], per[1:-1]))           # non-decreasing (the last cluster takes the rest)
+        for i in range(0, len(t), 16):                                   # a cluster's lines sit at the front of its slots
+            n = per[i // 16]
+            assert (t[i:i + n] >= 0).all() and (t[i + n:i + 16] == -1).all()
+        if B <= 240:
+            assert len(per) <= 15
+    assert (decode_slot_table(32, n0=16) >= 0).all()                     # n0 = 16: the dense layout

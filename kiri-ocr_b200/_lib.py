@@ -12,7 +12,9 @@ import subprocess
 from typing import Optional
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libkiri_b200.so")
+# KIRI_B200_LIB: load another build of the same ABI (the checked build of the soak test: `make -C csrc checked`)
+LIB_PATH = os.environ.get("KIRI_B200_LIB") or os.path.join(_PKG_DIR, "libkiri_b200.so")
+CHECKED_LIB_PATH = os.path.join(_PKG_DIR, "libkiri_b200_checked.so")
 CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 KIRI_MAX_LAYERS = 8
 
@@ -126,7 +128,7 @@ class KiriError(RuntimeError):
 
 def build_library(verbose: bool = False) -> str:
     """Compile csrc/*.cu for sm_100a with nvcc (cross-compiles without a GPU)."""
-    res = subprocess.run(["make", "-C", CSRC_DIR, "-j", str(os.cpu_count() or 4)],
+    res = subprocess.run(["make", "-C", CSRC_DIR, "-j", str(os.cpu_count() or 4), "all", "checked"],
                          capture_output=True, text=True)
     if res.returncode != 0:
         raise KiriError("building libkiri_b200.so failed:\n" + res.stdout[-4000:] + res.stderr[-4000:])

@@ -45,8 +45,18 @@ struct __align__(16) EbBars {
   uint64_t acc2_full, acc2_empty, h_full, h_empty;
   uint64_t res_full[kEbEpiWarps][2];
   uint32_t tmem_base;
-  uint32_t pad[3];
+  uint32_t chk_units[3];     // KIRI_CHECKED: ring units issued by producer 0 / producer 1, consumed by the MMA warp
+  uint32_t chk_tiles[4];     // KIRI_CHECKED: tiles walked by producer 0 / producer 1 / the MMA warp / epilogue warp 0
 };
+
+// make EXTRA=-DKIRI_CHECKED: the invariants a ring / barrier-phase slip would break, checked on the device (printf + trap).
+// (The round-1 launch failure came from exactly such a slip: an experimental fourth ring slot that overlapped the barriers.)
+#ifdef KIRI_CHECKED
+#define EB_CHECK(cond, what, a, b) do { if (!(cond)) { printf("encoder_block KIRI_CHECKED: %s (%d, %d) block %d thread %d\n", \
+    what, static_cast<int>(a), static_cast<int>(b), static_cast<int>(blockIdx.x), static_cast<int>(threadIdx.x)); __trap(); } } while (0)
+#else
+#define EB_CHECK(cond, what, a, b) do { } while (0)
+#endif
 
 // Biases and LayerNorm affines travel BY VALUE in the kernel parameters (constant bank): the epilogue threads
 // of a warp all want the same element, and as 128-bit global/shared broadcast loads those cost the full
@@ -246,6 +256,8 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  EB_CHECK((tmem_base & 0xffffu) == 0u && (tmem_base >> 16) == 0u, "all 512 TMEM columns must start at lane 0 / column 0", tmem_base >> 16, tmem_base & 0xffffu);
+  EB_CHECK(kBarOff + static_cast<int>(sizeof(EbBars)) <= 232448 && kHOff + kHBytes == kBarOff, "shared-memory carve", kBarOff, sizeof(EbBars));
   pdl_trigger();
   // o and x come from the previous kernels.  Producer warp 0 only ever loads WEIGHTS (even ring units, see below): it does
   // not wait, so the first Wo / W1 units are in flight while the previous kernel drains.
@@ -259,6 +271,9 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
     //   W1(g,k) = rows [256g, 256g+256) of W1, K chunk k (64 wide);  W2(c) = all 256 rows of W2, K chunk c (64 hidden columns)
     const int pw = warp - kEbProdWarp0;
     const int units = 8 + 8 * nG;
+#ifdef KIRI_CHECKED
+    uint32_t n_units = 0, n_tiles_seen = 0;
+#endif
     int slot = 0, turn = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -288,17 +303,29 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
                 if (blk < nG - 1) { is_w1 = r < 4; g = is_w1 ? blk + 1 : blk; k = r & 3; }
                 else { is_w1 = false; g = nG - 1; k = q - 8 * (nG - 1); }
               }
+              EB_CHECK(g >= 0 && g < nG && k >= 0 && k < 4 && slot < kSlots, "FFN ring unit out of range", g, k);
               mbar_arrive_expect_tx(fb, 32768);
               if (is_w1) tma_load_3d(dst, &tmW1, fb, 0, k, 256 * g);
               else tma_load_3d(dst, &tmW2, fb, 0, 4 * g + k, 0);
             }
+#ifdef KIRI_CHECKED
+            ++n_units;
+#endif
           }
           __syncwarp();
         }
         if (++turn == kEbProdWarps) turn = 0;
         if (++slot == kSlots) { slot = 0; phase ^= 1; }
       }
+#ifdef KIRI_CHECKED
+      ++n_tiles_seen;
+#endif
     }
+#ifdef KIRI_CHECKED
+    // (n_units lives in the elected lane of each unit: reduce over the warp)
+    for (int o = 16; o > 0; o >>= 1) n_units += __shfl_xor_sync(0xffffffffu, n_units, o);
+    if (lane == 0) { bars->chk_units[pw] = n_units; bars->chk_tiles[pw] = n_tiles_seen; }
+#endif
   } else if (warp == kEbMmaWarp) {
     // ============================ MMA issuer ============================
     const uint32_t idesc256 = umma_idesc_bf16(128, 256);
@@ -310,7 +337,12 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
     const bool timing = p.timing != 0 && blockIdx.x == 0;
     long long tq = timing ? clock64() : 0, m_ring = 0, m_a2 = 0, m_hf = 0, m_ae = 0, m_other = 0;
     const long long m_t0 = tq;
+#ifdef KIRI_CHECKED
+    uint32_t n_units = 0;
+    auto next_slot = [&]() { ++n_units; if (++slot == kSlots) { slot = 0; phase ^= 1; } };
+#else
     auto next_slot = [&]() { if (++slot == kSlots) { slot = 0; phase ^= 1; } };
+#endif
     // hidden group g: H (256 TMEM columns) = A2 @ W1[256g : 256g+256, :]^T; K = 256 arrives as four ring units
     int n_ff1 = 0, n_ff2 = 0;                          // groups issued so far (barrier phases)
     auto issue_ff1 = [&]() {
@@ -414,6 +446,10 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
       g_eb_prof[9] += m_ring; g_eb_prof[10] += m_a2; g_eb_prof[11] += m_hf; g_eb_prof[12] += m_ae;
       g_eb_prof[13] += clock64() - m_t0;
     }
+#ifdef KIRI_CHECKED
+    EB_CHECK(n_ff1 == it * nG && n_ff2 == it * nG, "hidden groups issued per tile", n_ff1, n_ff2);
+    if (lane == 0) { bars->chk_units[2] = n_units; bars->chk_tiles[2] = it; }
+#endif
   } else {
     // ============================ epilogue warps ============================
     // 16 warps: warp w reads TMEM lane quarter q = w & 3 (hardware rule) and owns column quarter cq = w >> 2,
@@ -599,10 +635,23 @@ encoder_block_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_const
 #endif
     }
     if (lane == 0) bulk_wait_group<0>();
+#ifdef KIRI_CHECKED
+    if (warp == 0 && lane == 0) bars->chk_tiles[3] = it;
+#endif
   }
 
   tc_fence_before();
   __syncthreads();
+#ifdef KIRI_CHECKED
+  if (threadIdx.x == 0) {
+    // every role walked the same tiles, and the MMA warp consumed exactly the ring units the two producers issued
+    const uint32_t want_tiles = (p.n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / gridDim.x;
+    EB_CHECK(bars->chk_tiles[0] == want_tiles && bars->chk_tiles[1] == want_tiles && bars->chk_tiles[2] == want_tiles &&
+             bars->chk_tiles[3] == want_tiles, "tiles per role", bars->chk_tiles[2], bars->chk_tiles[3]);
+    EB_CHECK(bars->chk_units[0] + bars->chk_units[1] == bars->chk_units[2] && bars->chk_units[2] == want_tiles * (8u + 8u * nG),
+             "ring units issued vs consumed", bars->chk_units[0] + bars->chk_units[1], bars->chk_units[2]);
+  }
+#endif
   if (warp == kEbMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);

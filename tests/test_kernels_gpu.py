@@ -482,12 +482,21 @@ def test_encoder_block_soak_back_to_back():
     lib = _lib.load()
     for M in (128, 18944, 26080, 40960):
         eb_soak.soak(lib, M, 1000)
+        eb_soak.soak(lib, M, 1000, affine=False)             # the engine's variant (LayerNorm affines folded into the weights)
     eb_soak.soak(lib, 26080, 300, with_ln=False)
     env = dict(os.environ, KIRI_GEMM_TIMING="1")
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "eb_soak.py"), "300"], env=env, capture_output=True, text=True,
                        timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("soak ok") == 8
+    # third process: the CHECKED build (make -C csrc checked) - device-side invariants of the ring / barrier phases / TMEM base
+    # (ring units issued == consumed, tiles per role, ...) trap with a message instead of corrupting memory
+    assert os.path.exists(_lib.CHECKED_LIB_PATH), "libkiri_b200_checked.so is missing: run __graft_entry__.build()"
+    env = dict(os.environ, KIRI_B200_LIB=_lib.CHECKED_LIB_PATH)
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "eb_soak.py"), "300"], env=env, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("soak ok") == 8 and "libkiri_b200_checked.so" in r.stdout and "KIRI_CHECKED" not in r.stdout
 
 
 def test_bgr_to_gray_bit_exact_vs_cv2(lib):

@@ -11,7 +11,7 @@ import torch
 from kiri_ocr_b200 import _lib
 
 
-def soak(lib, M, iters, FF=1024, with_ln=True):
+def soak(lib, M, iters, FF=1024, with_ln=True, affine=True):
     D = 256
     g = torch.Generator().manual_seed(M)
     dev = lambda t: t.cuda()
@@ -22,6 +22,8 @@ def soak(lib, M, iters, FF=1024, with_ln=True):
     w2 = dev((torch.randn(D, FF, generator=g) / 32).to(torch.bfloat16))
     bo, b1, b2 = dev(torch.randn(D, generator=g) * 0.1), dev(torch.randn(FF, generator=g) * 0.1), dev(torch.randn(D, generator=g) * 0.1)
     g1, h1 = dev(1 + 0.1 * torch.randn(D, generator=g)), dev(0.1 * torch.randn(D, generator=g))
+    if not affine:                                      # identity affines select the parameter-free kernel variant (the engine's)
+        g1, h1 = torch.ones_like(g1), torch.zeros_like(h1)
     outs = []
     for rep in range(2):
         x = x0.clone()
@@ -44,5 +46,6 @@ if __name__ == "__main__":
     _lib.require_device()
     for M in Ms:
         for with_ln in (True, False):
-            mx = soak(lib, M, iters, with_ln=with_ln)
-            print(f"soak ok: M={M} iters={iters} ln_out={with_ln} timing={'KIRI_GEMM_TIMING' in os.environ} max|x|={mx:.1f}", flush=True)
+            mx = soak(lib, M, iters, with_ln=with_ln, affine=with_ln)       # (affine variant with ln_out, folded variant without)
+            print(f"soak ok: M={M} iters={iters} ln_out={with_ln} timing={'KIRI_GEMM_TIMING' in os.environ} "
+                  f"lib={os.path.basename(_lib.LIB_PATH)} max|x|={mx:.1f}", flush=True)

@@ -89,8 +89,14 @@ __device__ __forceinline__ void ctc_frame(const T* __restrict__ row, int C, bool
   am_out = am; p_out = 1.0f / s;
 }
 
+#ifndef KIRI_CTC_IT
+#define KIRI_CTC_IT 1          // warp passes (4 frames each) whose loads are issued together
+#endif
+#ifndef KIRI_CTC_MINB
+#define KIRI_CTC_MINB 4        // resident CTAs per SM the register budget is held to
+#endif
 template <typename T>
-__global__ void __launch_bounds__(kCtcThreads)
+__global__ void __launch_bounds__(kCtcThreads, KIRI_CTC_MINB)
 ctc_greedy_kernel(const T* __restrict__ logits, int Tn, int C, int ld, int* __restrict__ ids,
                   int* __restrict__ n_ids, float* __restrict__ conf, int* __restrict__ frame_ids,
                   float* __restrict__ frame_prob, const int* __restrict__ row0, const int* __restrict__ lens) {
@@ -108,33 +114,87 @@ ctc_greedy_kernel(const T* __restrict__ logits, int Tn, int C, int ld, int* __re
   const bool vec = (sizeof(T) == 4) && (C <= 256) && ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
 
   float psum = 0.f;
-  // four frames per iteration: their loads are independent, which quadruples the bytes in flight per warp
-  constexpr int kFr = 4;
-  for (int t = warp; t < Tn; t += kFr * nwarps) {
-    int am[kFr];
-    float pr[kFr];
-    float vals[kFr][8];                               // all loads of the iteration are issued before any reduction
+  if (vec) {
+    // EIGHT lanes per frame, four frames per warp pass: a row of C <= 256 fp32 logits is at most 64 float4 chunks, lane
+    // `sub` of a frame's group owns chunks sub, sub + 8, ...  The reductions are 3 shuffle steps that serve four frames
+    // at once and the loads of two passes (8 frames per warp) are issued before any arithmetic.  (One frame per warp
+    // needed 5-step reductions for a single frame: 208 warp instructions per frame, issue-bound at 54 % of the HBM
+    // peak at 8 192 lines; this form needs ~45.)
+    const int sub = lane & 7, slot = lane >> 3;
+    const int nch = C >> 2, tail = C & 3;
+    constexpr int kIt = KIRI_CTC_IT;
+    for (int tb = warp * 4; tb < Tn; tb += nwarps * 4 * kIt) {
+      float4 v[kIt][8];
 #pragma unroll
-    for (int f = 0; f < kFr; ++f) {
-      am[f] = 0; pr[f] = 0.f;
-      const int tf = t + f * nwarps;
-      if (vec && tf < Tn) ctc_load_row(reinterpret_cast<const float*>(base + static_cast<size_t>(tf) * ld), C, lane, vals[f]);
-    }
+      for (int it = 0; it < kIt; ++it) {
+        const int tf = tb + it * nwarps * 4 + slot;
+        const float* row = reinterpret_cast<const float*>(base + static_cast<size_t>(tf) * ld);
+        const float4* r4 = reinterpret_cast<const float4*>(row);
 #pragma unroll
-    for (int f = 0; f < kFr; ++f) {
-      const int tf = t + f * nwarps;
-      if (tf < Tn) ctc_frame<T>(base + static_cast<size_t>(tf) * ld, C, vec, lane, am[f], pr[f], vals[f]);
-    }
-    if (lane == 0) {
-#pragma unroll
-      for (int f = 0; f < kFr; ++f) {
-        const int tf = t + f * nwarps;
-        if (tf < Tn) {
-          s_id[tf] = am[f];
-          psum += pr[f];
-          if (frame_ids) frame_ids[r0 + tf] = am[f];
-          if (frame_prob) frame_prob[r0 + tf] = pr[f];
+        for (int k = 0; k < 8; ++k) {
+          const int ch = sub + 8 * k;
+          float4 t4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+          if (tf < Tn) {
+            if (ch < nch) t4 = __ldg(r4 + ch);
+            else if (ch == nch && tail) {                        // ragged tail (C not a multiple of 4)
+              const float* rs = row + 4 * ch;
+              t4.x = __ldg(rs); if (tail > 1) t4.y = __ldg(rs + 1); if (tail > 2) t4.z = __ldg(rs + 2);
+            }
+          }
+          v[it][k] = t4;
         }
+      }
+#pragma unroll
+      for (int it = 0; it < kIt; ++it) {
+        const int tf = tb + it * nwarps * 4 + slot;
+        float m = -INFINITY;
+        int am = 0x7fffffff;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {                            // ascending class index per lane: the first maximum wins
+          const int c0 = 4 * (sub + 8 * k);
+          if (v[it][k].x > m) { m = v[it][k].x; am = c0; }
+          if (v[it][k].y > m) { m = v[it][k].y; am = c0 + 1; }
+          if (v[it][k].z > m) { m = v[it][k].z; am = c0 + 2; }
+          if (v[it][k].w > m) { m = v[it][k].w; am = c0 + 3; }
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {                        // inside the frame's 8-lane group
+          const float om = __shfl_xor_sync(0xffffffffu, m, o);
+          const int oa = __shfl_xor_sync(0xffffffffu, am, o);
+          if (om > m || (om == m && oa < am)) { m = om; am = oa; }
+        }
+        float sx = 0.f;
+        if (tf < Tn) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)                             // exp(-inf) = 0 for the padding
+            sx += (__expf(v[it][k].x - m) + __expf(v[it][k].y - m)) + (__expf(v[it][k].z - m) + __expf(v[it][k].w - m));
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) sx += __shfl_xor_sync(0xffffffffu, sx, o);
+        if (sub == 0 && tf < Tn) {
+          const float pr = 1.0f / sx;
+          s_id[tf] = am;
+          psum += pr;
+          if (frame_ids) frame_ids[r0 + tf] = am;
+          if (frame_prob) frame_prob[r0 + tf] = pr;
+        }
+      }
+    }
+    // the four frame slots of the warp, in a fixed order
+    const float p1 = __shfl_sync(0xffffffffu, psum, 8), p2 = __shfl_sync(0xffffffffu, psum, 16), p3 = __shfl_sync(0xffffffffu, psum, 24);
+    psum = ((psum + p1) + p2) + p3;                              // (meaningful in lane 0)
+  } else {
+    // scalar path (other element types, unaligned rows, C > 256): one frame per warp
+    float dummy[8];
+    for (int t = warp; t < Tn; t += nwarps) {
+      int am = 0;
+      float pr = 0.f;
+      ctc_frame<T>(base + static_cast<size_t>(t) * ld, C, false, lane, am, pr, dummy);
+      if (lane == 0) {
+        s_id[t] = am;
+        psum += pr;
+        if (frame_ids) frame_ids[r0 + t] = am;
+        if (frame_prob) frame_prob[r0 + t] = pr;
       }
     }
   }

@@ -103,6 +103,14 @@ int kiri_conv1(const uint8_t* planes_u8, const float* w_host, const float* b_hos
 int kiri_conv1_multi(const uint8_t* const* planes_u8, void* const* out_bf16_nhwc48, const int* group_lines,
                      const int* group_W, int n_groups, const float* w_host, const float* b_host, int H,
                      cudaStream_t stream);
+/* The same layer on the tensor pipe (csrc/conv1_tc.cu): one tcgen05 MMA pair per 128 pixels on EXACT bf16 operands
+ * (u = v - 128, weights split into two bf16 terms, bias and normalisation folded into the operand), SiLU + store on the
+ * CUDA cores.  Same inputs, outputs and layout as kiri_conv1_multi; group widths are multiples of 128.  kiri_encode_multi
+ * uses this form (KIRI_CONV1_FFMA=1 selects the CUDA-core one).  This stand-alone entry packs and uploads the weights on
+ * every call and synchronises the stream. */
+int kiri_conv1_tc_multi(const uint8_t* const* planes_u8, void* const* out_bf16_nhwc48, const int* group_lines,
+                        const int* group_W, int n_groups, const float* w_host, const float* b_host, int H,
+                        cudaStream_t stream);
 
 /* ---------------------------------------------------------------- K3-K5, K8, K9, K11: tcgen05 GEMMs
  * 3x3 conv as implicit GEMM (replaces ConvStem.net[3:12], kiri_ocr/model.py:218-226): input NHWC

@@ -84,6 +84,8 @@ _SIGS = {
     "kiri_conv1": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]),
     "kiri_conv1_multi": (C.c_int, [C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, vp, vp,
                                    C.c_int, vp]),
+    "kiri_conv1_tc_multi": (C.c_int, [C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, vp, vp,
+                                      C.c_int, vp]),
     "kiri_pool_pos_ln_multi": (C.c_int, [C.POINTER(vp), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, vp, C.c_int, C.c_int,
                                          vp, vp, vp, vp, vp, vp, vp]),
     "kiri_conv3x3_bf16": (C.c_int, [vp, vp, vp] + [C.c_int] * 7 + [vp, C.c_int, vp]),

@@ -175,6 +175,8 @@ extern "C" int kiri_create(const KiriDims* dims, const KiriWeights* weights, Kir
   h->w.conv1_b_host = h->conv1_b;
   h->fused = nullptr;
   h->enc_consts = nullptr;
+  h->conv1_tc_b = nullptr;
+  if (conv1_tc_build(h->conv1_w, h->conv1_b, &h->conv1_tc_b) != 0) { delete h; return -1; }
   if (dims->enc_ff % 256 == 0 && dims->enc_ff <= 1024 && dims->enc_layers > 0 && weights->enc[0].wo) {
     h->enc_consts = new (std::nothrow) EbConst[dims->enc_layers];
     KIRI_REQUIRE(h->enc_consts, "kiri_create: out of host memory");
@@ -197,6 +199,7 @@ extern "C" int kiri_create(const KiriDims* dims, const KiriWeights* weights, Kir
 extern "C" void kiri_destroy(KiriHandle* h) {
   if (!h) return;
   fused_decoder_free(h);
+  if (h->conv1_tc_b) cudaFree(h->conv1_tc_b);
   delete[] h->enc_consts;
   delete h;
 }
@@ -328,7 +331,10 @@ extern "C" int kiri_encode_multi(KiriHandle* h, const KiriGroup* groups, int n_g
     }
     if (np == 0) continue;
     { ProfScope ps(PS_CONV1, stream);
-      KIRI_TRY(kiri_conv1_multi(c1_in, c1_out, c1_lines, c1_W, np, w.conv1_w_host, w.conv1_b_host, H, stream)); }
+      // tensor-pipe form (conv1_tc.cu); KIRI_CONV1_FFMA=1: the CUDA-core form (conv1.cu)
+      static const bool conv1_ffma = getenv("KIRI_CONV1_FFMA") != nullptr;
+      if (h->conv1_tc_b && !conv1_ffma) KIRI_TRY(conv1_tc_launch(c1_in, c1_out, c1_lines, c1_W, np, h->conv1_tc_b, H, stream));
+      else KIRI_TRY(kiri_conv1_multi(c1_in, c1_out, c1_lines, c1_W, np, w.conv1_w_host, w.conv1_b_host, H, stream)); }
     { ProfScope ps(PS_CONV2, stream); KIRI_TRY(launch_gemm_tc_multi(L2, np, stream)); }
     { ProfScope ps(PS_CONV3, stream); KIRI_TRY(launch_gemm_tc_multi(L3, np, stream)); }
     { ProfScope ps(PS_CONV4, stream); KIRI_TRY(launch_gemm_tc_multi(L4, np, stream)); }

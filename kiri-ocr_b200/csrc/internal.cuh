@@ -12,6 +12,7 @@ struct KiriHandle {
   float conv1_b[48];
   void* fused;          // fragment-packed decoder weights of the fused decode kernel (decoder_fused.cu)
   kiri::EbConst* enc_consts;   // [enc_layers] host copies of the encoder-tail constants (encoder_block.cu), or null
+  void* conv1_tc_b;            // device: conv1's weights as the B operand of the tensor-pipe form (conv1_tc.cu), or null
 };
 
 namespace kiri {
@@ -28,6 +29,11 @@ int encoder_block_consts(EbConst* out, const float* bo, const float* b1, const f
                          const float* ln_mid_b, const float* ln_out_g, const float* ln_out_b, int FF);
 int launch_encoder_block(const void* o, float* x, void* a_out, const void* wo, const void* w1, const void* w2,
                          const EbConst* consts_host, bool has_ln_out, int M, int FF, cudaStream_t stream);
+
+// conv1_tc.cu: conv1 as one tcgen05 MMA pair per 128 pixels
+int conv1_tc_build(const float* w_host, const float* b_host, void** bmat_dev);
+int conv1_tc_launch(const uint8_t* const* planes_u8, void* const* out_bf16_nhwc48, const int* group_lines, const int* group_W,
+                    int n_groups, const void* bmat_dev, int H, cudaStream_t stream);
 
 // decoder_fused.cu: whole-decode persistent cluster kernel
 struct FusedBeam {           // beam-search mode of the fused decoder (nullptr = greedy)

@@ -135,10 +135,22 @@ def test_streaming_rule_raw_argmax(engines, golden, tok_cfg):
         want = [ch["token_id"] for ch in chunks]
         got = res[i].ids.tolist()
         m = min(len(want), len(got))
-        agree = sum(int(a == b) for a, b in zip(want[:m], got[:m]))
-        _report(f"decoder_stream/hard/{i}", {"steps": m, "agree_prefix": agree})
-        # the full streamed sequence, unless the oracle itself is at a near tie (2 x tolerance) at the first
-        # differing step; on this fixture every step agrees (67/67 and 52/52 in profiles/r01_parity_report.json)
-        assert got[:m] == want[:m], (i, agree, m)
+        agree = next((k for k, (a, b) in enumerate(zip(want[:m], got[:m])) if a != b), m)      # length of the common prefix
+        rec = {"steps": m, "agree_prefix": agree}
+        if agree < m:
+            # the streamed sequence may only leave the oracle's at a NEAR TIE of the raw dec_head logits: the oracle, fed the
+            # common prefix, must rank the device's token within 2 x tolerance of its own choice (bf16 operands on the
+            # device; on this random-init fixture the margins are of that size - the wide-margin fixtures of
+            # tests/test_wide_gpu.py demand the full sequence)
+            st = OM.DecoderState(sd, OM.mem_proj(sd, mem), 8)
+            seq = [1] + want[:agree]
+            for t_in in seq:
+                dec, _ = OM.decoder_step(st, torch.tensor([t_in]))
+            gap = float(dec[0, want[agree]] - dec[0, got[agree]])
+            rec["first_divergence_gap"] = gap
+            _report(f"decoder_stream/hard/{i}", rec)
+            assert 0.0 <= gap <= 2 * dec_tol(sd, 0.0), (i, agree, gap)
+            continue
+        _report(f"decoder_stream/hard/{i}", rec)
         if res[i].len_est == length:                            # same CTC length estimate -> same step bound
             assert len(got) == len(want), (i, len(got), len(want))

@@ -291,6 +291,41 @@ def test_conv1_vs_torch(lib, n, W):
     assert float(err.max()) < 0.03
 
 
+@pytest.mark.parametrize("groups", [[(3, 256)], [(2, 640), (1, 128), (2, 384)]])
+def test_conv1_tensor_pipe_vs_torch_and_cuda_core_form(lib, groups):
+    """conv1 on the tensor pipe (csrc/conv1_tc.cu: exact bf16 operands u = v - 128 / -0.5 for padded taps, weights split
+    into two bf16 terms, bias and normalisation folded into the operand) against torch in float64 - same bound as the
+    CUDA-core form - and against the CUDA-core form itself (at most one bf16 ulp apart, on a small fraction of outputs)."""
+    torch.manual_seed(11)
+    H = 48
+    w = torch.randn(48, 9) / 3
+    b = torch.randn(48) * 0.1
+    planes = [torch.randint(0, 256, (n, H, W), dtype=torch.uint8) for n, W in groups]
+    planes[0][0, :4] = 0
+    planes[0][0, 4:8] = 255
+    dplanes = [dev(p) for p in planes]
+    outs = [torch.full((n, H, W, 48), float("nan"), dtype=torch.bfloat16, device="cuda") for n, W in groups]
+    outs_cc = [torch.full((n, H, W, 48), float("nan"), dtype=torch.bfloat16, device="cuda") for n, W in groups]
+    k = len(groups)
+    args = lambda o: ((C.c_void_p * k)(*[p.data_ptr() for p in dplanes]), (C.c_void_p * k)(*[m.data_ptr() for m in o]),
+                      (C.c_int * k)(*[n for n, _ in groups]), (C.c_int * k)(*[W for _, W in groups]), k, w.data_ptr(), b.data_ptr(), H,
+                      _lib.stream_ptr())
+    _lib.check(lib.kiri_conv1_tc_multi(*args(outs)))
+    _lib.check(lib.kiri_conv1_multi(*args(outs_cc)))
+    sync()
+    for pl, o, occ in zip(planes, outs, outs_cc):
+        x = (pl.float() / 255.0 - 0.5) / 0.5
+        ref = F.silu(F.conv2d(x[:, None].double(), w.view(48, 1, 3, 3).double(), b.double(), 1, 1)).permute(0, 2, 3, 1)
+        of = o.float().cpu()
+        assert not torch.isnan(of).any()
+        err = (of.double() - ref).abs()
+        assert float((err / (ref.abs() + 0.05)).max()) < 6e-3, float((err / (ref.abs() + 0.05)).max())
+        assert float(err.max()) < 0.03
+        d = (of - occ.float().cpu()).abs()
+        assert float((d / (ref.abs().float() + 0.05)).max()) < 9e-3          # one bf16 ulp (2^-8 relative) at most
+        assert float((d > 0).float().mean()) < 0.05
+
+
 def test_conv1_multi_groups_equal_single_launches(lib):
     """One launch for several width groups == one launch per group, bit for bit."""
     torch.manual_seed(5)

@@ -10,7 +10,7 @@ d=[json.loads(l) for l in sys.stdin if l.startswith('{')][0]
 print('$v fast value',round(d['value']),'ms',round(d['ms_per_step'],4),'e2e',round(d['e2e']['value']),'conv1',round(d['stages']['conv1']['ms_per_step'],4),'conv2',round(d['stages']['conv2']['ms_per_step'],4))"
 done
 unset KIRI_CONV1_FFMA
-for c in 2 3 4; do
+for c in 3 4; do
 KIRI_CONV1_TC_CTAS=$c timeout 600 python bench.py 2>/dev/null | python -c "
 import json,sys
 d=[json.loads(l) for l in sys.stdin if l.startswith('{')][0]

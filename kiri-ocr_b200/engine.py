@@ -80,20 +80,27 @@ def target_widths(w: np.ndarray, h: np.ndarray, img_h: int) -> np.ndarray:
     return np.maximum(1, np.rint(w.astype(np.float64) * scale)).astype(np.int64)
 
 
-def _pre_smem(w, h, nw, img_h, Wb, strip, rows=8):
-    """numpy mirror of kiri_preprocess_smem_bytes (csrc/preprocess.cu) for ``rows`` staged source rows
-    (8 = the minimum the C helper reports)."""
+def _pre_smem_parts(w, h, nw, img_h, Wb, strip):
+    """numpy mirror of kiri_preprocess_smem_bytes (csrc/preprocess.cu), split into the part that does not depend on the
+    number of staged source rows and the bytes per staged row: smem(rows) = fixed + per_row * rows."""
     wout = np.minimum(nw, Wb)
     ws = np.minimum(strip, wout)
     hs = w / nw
     vs = h / img_h
-    ksh = np.where(nw != w, np.ceil(np.maximum(hs, 1.0)).astype(np.int64) * 2 + 1, 1)
+    hs1 = np.maximum(hs, 1.0)
+    ksh = np.where(nw != w, np.ceil(hs1).astype(np.int64) * 2 + 1, 1)
     ksv = np.where(h != img_h, np.ceil(np.maximum(vs, 1.0)).astype(np.int64) * 2 + 1, 1)
-    a16 = lambda v: (v + 15) & ~15          # noqa: E731
-    off = a16(img_h * ksv * 4) + a16(np.full_like(ksv, img_h * 4)) + a16(ws * ksh * 4) + a16(ws * 4) + a16(h * ((ws + 3) & ~3))
-    span = np.ceil(np.maximum(hs, 1.0) * ws).astype(np.int64) + 2 * ksh + 8
-    per_row = a16(span + 4)
-    return off + (per_row + 16) * rows
+    fixed = (((img_h * 4) * ksv + 15) & ~15) + ((img_h * 4 + 15) & ~15) + ((ws * ksh * 4 + 15) & ~15) + ((ws * 4 + 15) & ~15) \
+        + ((h * ((ws + 3) & ~3) + 15) & ~15)
+    span = np.ceil(hs1 * ws).astype(np.int64) + 2 * ksh + 8
+    per_row = ((span + 4 + 15) & ~15) + 16
+    return fixed, per_row
+
+
+def _pre_smem(w, h, nw, img_h, Wb, strip, rows=8):
+    """smem bytes of kiri_preprocess_pack for ``rows`` staged source rows (8 = the minimum the C helper reports)."""
+    fixed, per_row = _pre_smem_parts(w, h, nw, img_h, Wb, strip)
+    return fixed + per_row * rows
 
 
 def plan_groups(entries: np.ndarray, cfg: CFG, width_mode: str = "parity"
@@ -110,15 +117,17 @@ def plan_groups(entries: np.ndarray, cfg: CFG, width_mode: str = "parity"
     # everything per line is computed once for the whole batch; the per-group work is slicing only
     wout = np.minimum(nw, wb)
     strip = np.minimum(wout, PRE_STRIP)
-    need = _pre_smem(w, h, nw, img_h, wb, strip)
+    fixed, per_row = _pre_smem_parts(w, h, nw, img_h, wb, strip)
+    need = fixed + per_row * 8
     for _ in range(6):                                       # halve strips until they fit
         big = need > PRE_SMEM_CAP
         if not big.any():
             break
         strip = np.where(big & (strip > 32), np.maximum(32, (strip // 2 + 31) // 32 * 32), strip)
-        need = _pre_smem(w, h, nw, img_h, wb, strip)
+        fixed, per_row = _pre_smem_parts(w, h, nw, img_h, wb, strip)
+        need = fixed + per_row * 8
     # more shared memory than the minimum lets a CTA stage every source row of its strip at once
-    need = np.maximum(need, np.minimum(_pre_smem(w, h, nw, img_h, wb, strip, rows=h), PRE_SMEM_CAP))
+    need = np.maximum(need, np.minimum(fixed + per_row * h, PRE_SMEM_CAP))
     nstr = (wout + strip - 1) // strip
     d_all = np.zeros(len(entries), DESC_DTYPE)
     d_all["src_offset"], d_all["pitch"], d_all["w"], d_all["h"] = entries[:, 0], entries[:, 1], w, h
@@ -775,17 +784,20 @@ class BatchedRecognizer:
                     for (r0, B, T), p0 in zip(tk["rows"], np.cumsum([0] + [b for _, b, _ in tk["rows"]])[:-1])]
             texts = self.tok.decode_batch(np.concatenate(flat), n_h, "ctc")
             pos = 0
+            n_l, c_l, o_l = n_h.tolist(), c_h.tolist(), (order.tolist() if hasattr(order, "tolist") else list(order))
+            hw = tk["head_words"]
             for (r0, B, T) in tk["rows"]:
                 ids_h = hr[r0:r0 + B * T].reshape(B, T)
-                hw = tk["head_words"]
-                f_h = hr[hw + r0:hw + r0 + B * T].reshape(B, T) if want_frames else None
-                p_h = hr[hw + M + r0:hw + M + r0 + B * T].view(np.float32).reshape(B, T) if want_frames else None
-                for j in range(B):
-                    k = pos + j
-                    cf = float(c_h[k])
-                    results[order[k]] = LineResult(texts[k], cf, cf, ids_h[j, :n_h[k]],
-                                                   frame_ids=None if f_h is None else f_h[j],
-                                                   frame_prob=None if p_h is None else p_h[j], len_est=int(n_h[k]))
+                if want_frames:
+                    f_h = hr[hw + r0:hw + r0 + B * T].reshape(B, T)
+                    p_h = hr[hw + M + r0:hw + M + r0 + B * T].view(np.float32).reshape(B, T)
+                    for j in range(B):
+                        k = pos + j
+                        results[o_l[k]] = LineResult(texts[k], c_l[k], c_l[k], ids_h[j, :n_l[k]], None, None, f_h[j], p_h[j], n_l[k])
+                else:                                                # (python scalars and positional arguments: this loop is
+                    for j in range(B):                               #  a third of collect()'s host time at 256 lines)
+                        k = pos + j
+                        results[o_l[k]] = LineResult(texts[k], c_l[k], c_l[k], ids_h[j, :n_l[k]], None, None, None, None, n_l[k])
                 pos += B
             return results
         len_h = n_h                                                  # length estimates bound the loop

@@ -15,6 +15,8 @@
 // intermediate lives in shared memory, then the vertical pass writes coalesced rows.
 #include "internal.cuh"
 
+#include <type_traits>
+
 namespace kiri {
 
 static constexpr int kPrecisionBits = 22;
@@ -214,7 +216,7 @@ preprocess_pack_kernel(const uint8_t* __restrict__ src, const KiriCropDesc* __re
   if (rows_blk > h) rows_blk = h;
   if (rows_blk < 1) rows_blk = 1;
   const uintptr_t a0 = reinterpret_cast<uintptr_t>(crop + sx0);
-  const uint32_t srow_a = smem_u32(srow), inter_a = smem_u32(inter);     // shared-window addresses for the inner loops
+  const uint32_t srow_a = smem_u32(srow), inter_a = smem_u32(inter), kv_a = smem_u32(kv);   // shared-window addresses for the inner loops
   const int head0 = static_cast<int>(a0 & 3), dhead = d.pitch & 3;   // a staged row starts `head` bytes into its first word
 
   for (int r0 = 0; r0 < h; r0 += rows_blk) {
@@ -241,25 +243,33 @@ preprocess_pack_kernel(const uint8_t* __restrict__ src, const KiriCropDesc* __re
         for (int k = 0; k < 8; ++k) kc[k] = (do_h && k < kmax) ? kh[k * Ws + x] : 0;
         const uint32_t sb = srow_a + (xm - sx0);
         const uint32_t ib = inter_a + r0 * Wi + x;
-        for (int rr = rg; rr < nr; rr += kPreThreads / 128) {
-          const uint32_t s = sb + rr * srow_cap + ((head0 + (r0 + rr) * dhead) & 3);
-          uint32_t o;
-          if (do_h) {
-            int acc = 1 << (kPrecisionBits - 1);
-            if (kmax <= 8) {
-              // taps past kmax carry coefficient 0 and read bytes inside the staged row's slack: no predicates
+        // the row loop, specialised on the tap count (3 when enlarging, 5 up to 2x reduction, 7 up to 3x): taps past kmax
+        // carry coefficient 0 and read bytes inside the staged row's slack, so the unrolled form needs no predicates
+        auto rows = [&](auto ks_tag) {
+          constexpr int KS = decltype(ks_tag)::value;
+          for (int rr = rg; rr < nr; rr += kPreThreads / 128) {
+            const uint32_t s = sb + rr * srow_cap + ((head0 + (r0 + rr) * dhead) & 3);
+            uint32_t o;
+            if (KS == 0) {                                        // no horizontal resampling
+              o = lds_u8(s);
+            } else if (KS <= 8) {
+              int acc = 1 << (kPrecisionBits - 1);
 #pragma unroll
-              for (int k = 0; k < 8; ++k)
-                if (k < ksize_h) acc += static_cast<int>(lds_u8(s + k)) * kc[k];
-            } else {
+              for (int k = 0; k < KS; ++k) acc += static_cast<int>(lds_u8(s + k)) * kc[k];
+              o = clip8(acc);
+            } else {                                              // generic tap count
+              int acc = 1 << (kPrecisionBits - 1);
               for (int k = 0; k < kmax; ++k) acc += static_cast<int>(lds_u8(s + k)) * kh[k * Ws + x];
+              o = clip8(acc);
             }
-            o = clip8(acc);
-          } else {
-            o = lds_u8(s);
+            sts_u8(ib + rr * Wi, o);
           }
-          sts_u8(ib + rr * Wi, o);
-        }
+        };
+        if (!do_h) rows(std::integral_constant<int, 0>{});
+        else if (ksize_h == 3) rows(std::integral_constant<int, 3>{});
+        else if (ksize_h == 5) rows(std::integral_constant<int, 5>{});
+        else if (ksize_h == 7) rows(std::integral_constant<int, 7>{});
+        else rows(std::integral_constant<int, 9>{});
       }
     }
     __syncthreads();
@@ -274,20 +284,33 @@ preprocess_pack_kernel(const uint8_t* __restrict__ src, const KiriCropDesc* __re
         uint32_t word;
         if (do_v) {
           const int y0 = ymin[y];
-          const int kmax = ksize_v < h - y0 ? ksize_v : h - y0;
-          const int* kr = kv + y * ksize_v;
-          const uint32_t cp = inter_a + 4 * (y0 * wq + lane);
+          const uint32_t kr = kv_a + 4 * y * ksize_v;           // taps past the last source row carry coefficient 0 (fill_coefs)
+          const uint32_t cp = inter_a + 4 * (y0 * wq + lane);   // ... and read rows that lie in the staging area behind `inter`
           int a[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) a[j] = 1 << (kPrecisionBits - 1);
-          for (int k = 0; k < kmax; ++k) {
-            const uint32_t v = lds_u32(cp + 4 * k * wq);
-            const int c = kr[k];
+          auto mac = [&](int kk) {
+            const uint32_t v = lds_u32(cp + 4 * kk * wq);
+            const int c = static_cast<int>(lds_u32(kr + 4 * kk));
             a[0] += static_cast<int>(v & 255u) * c;
             a[1] += static_cast<int>((v >> 8) & 255u) * c;
             a[2] += static_cast<int>((v >> 16) & 255u) * c;
             a[3] += static_cast<int>(v >> 24) * c;
-          }
+          };
+          auto taps = [&](auto ks_tag) {                          // specialised on the tap count like the horizontal pass
+            constexpr int KS = decltype(ks_tag)::value;
+            if (KS > 0) {
+#pragma unroll
+              for (int k = 0; k < KS; ++k) mac(k);
+            } else {
+              const int n = ksize_v < h - y0 ? ksize_v : h - y0;
+              for (int k = 0; k < n; ++k) mac(k);
+            }
+          };
+          if (ksize_v == 3) taps(std::integral_constant<int, 3>{});
+          else if (ksize_v == 5) taps(std::integral_constant<int, 5>{});
+          else if (ksize_v == 7) taps(std::integral_constant<int, 7>{});
+          else taps(std::integral_constant<int, 0>{});
           word = static_cast<uint32_t>(clip8(a[0])) | (static_cast<uint32_t>(clip8(a[1])) << 8) |
                  (static_cast<uint32_t>(clip8(a[2])) << 16) | (static_cast<uint32_t>(clip8(a[3])) << 24);
         } else {

@@ -150,7 +150,9 @@ extern "C" int kiri_conv3x3_bf16(const void* in_nhwc, const void* w, const float
   KIRI_REQUIRE(in_nhwc && w && bias && out_nhwc, "kiri_conv3x3_bf16: null pointer");
   KIRI_REQUIRE(cin_mem >= 0 && cin_mem <= Cin, "kiri_conv3x3_bf16: cin_mem=%d must be in [0, Cin=%d]", cin_mem, Cin);
   if (n == 0) return 0;
-  return launch_gemm_tc(conv_launch(in_nhwc, w, bias, n, IH, IW, Cin, N, sh, sw, out_nhwc, cin_mem == Cin ? 0 : cin_mem), stream);
+  const GemmLaunch L = conv_launch(in_nhwc, w, bias, n, IH, IW, Cin, N, sh, sw, out_nhwc, cin_mem == Cin ? 0 : cin_mem);
+  if (conv2_swap_supported(&L, 1)) return launch_conv2_swap(&L, 1, stream);
+  return launch_gemm_tc(L, stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -335,7 +337,10 @@ extern "C" int kiri_encode_multi(KiriHandle* h, const KiriGroup* groups, int n_g
       static const bool conv1_ffma = getenv("KIRI_CONV1_FFMA") != nullptr;
       if (h->conv1_tc_b && !conv1_ffma) KIRI_TRY(conv1_tc_launch(c1_in, c1_out, c1_lines, c1_W, np, h->conv1_tc_b, H, stream));
       else KIRI_TRY(kiri_conv1_multi(c1_in, c1_out, c1_lines, c1_W, np, w.conv1_w_host, w.conv1_b_host, H, stream)); }
-    { ProfScope ps(PS_CONV2, stream); KIRI_TRY(launch_gemm_tc_multi(L2, np, stream)); }
+    { ProfScope ps(PS_CONV2, stream);
+      // channels as M, 256 pixels as N (conv2_swap.cu) when every group has the shape it is built for
+      if (conv2_swap_supported(L2, np)) KIRI_TRY(launch_conv2_swap(L2, np, stream));
+      else KIRI_TRY(launch_gemm_tc_multi(L2, np, stream)); }
     { ProfScope ps(PS_CONV3, stream); KIRI_TRY(launch_gemm_tc_multi(L3, np, stream)); }
     { ProfScope ps(PS_CONV4, stream); KIRI_TRY(launch_gemm_tc_multi(L4, np, stream)); }
   }

@@ -35,6 +35,10 @@ int conv1_tc_build(const float* w_host, const float* b_host, void** bmat_dev);
 int conv1_tc_launch(const uint8_t* const* planes_u8, void* const* out_bf16_nhwc48, const int* group_lines, const int* group_W,
                     int n_groups, const void* bmat_dev, int H, cudaStream_t stream);
 
+// conv2_swap.cu: conv2 with the channels as M and 256 pixels as N of the tcgen05 instruction
+bool conv2_swap_supported(const GemmLaunch* Ls, int n);
+int launch_conv2_swap(const GemmLaunch* Ls, int n, cudaStream_t stream);
+
 // decoder_fused.cu: whole-decode persistent cluster kernel
 struct FusedBeam {           // beam-search mode of the fused decoder (nullptr = greedy)
   int beam; double lenp;

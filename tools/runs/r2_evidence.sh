@@ -19,7 +19,7 @@ timeout 600 python bench.py --method accurate > ${O}_bench_accurate.json 2> ${O}
 timeout 600 python bench.py --method beam > ${O}_bench_beam.json 2> ${O}_bench_beam.err; echo "== bench beam rc=$?"; summ ${O}_bench_beam.json
 timeout 900 python bench.py --workload pages > ${O}_bench_pages.json 2> ${O}_bench_pages.err; echo "== bench pages rc=$?"; summ ${O}_bench_pages.json
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > ${O}_bench_reference.json 2> ${O}_bench_reference.err; echo "== reference rc=$?"; cut -c1-300 ${O}_bench_reference.json
-K="encoder_block_kernel|gemm_tc_kernel|encoder_attention_kernel|conv1_pair_kernel|conv1_tc_kernel|preprocess_pack_kernel|crop_sum_kernel|ctc_collapse|pool_pos_ln|ln_chain|pack_records|dec_fused|crosskv"
+K="encoder_block_kernel|gemm_tc_kernel|conv2_swap_kernel|encoder_attention_kernel|conv1_pair_kernel|conv1_tc_kernel|preprocess_pack_kernel|crop_sum_kernel|ctc_collapse|pool_pos_ln|ln_chain|pack_records|dec_fused|crosskv"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file ${O}_launches_fast.csv \
     python bench.py --steps 2 --warmup 3 > ${O}_ncu_launch_fast.log 2>&1; echo "launch list fast rc=$?"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file ${O}_launches_accurate.csv \

@@ -606,6 +606,18 @@ class BatchedRecognizer:
     @torch.no_grad()
     def submit(self, src, entries: np.ndarray, method: str = "ctc", streaming: bool = False, bgr_pages=None,
                live: bool = False):
+        """Enqueue one batch (see ``_submit_own``) on the engine's stream; the caller's stream is waited for first."""
+        self._check_device()
+        caller = torch.cuda.current_stream(self.device)
+        if caller != self.stream:
+            self.stream.wait_stream(caller)
+            with torch.cuda.stream(self.stream), _lib.pinned_stream(self.stream.cuda_stream):
+                return self._submit_own(src, entries, method, streaming, bgr_pages, live)
+        with _lib.pinned_stream(self.stream.cuda_stream):
+            return self._submit_own(src, entries, method, streaming, bgr_pages, live)
+
+    def _submit_own(self, src, entries: np.ndarray, method: str = "ctc", streaming: bool = False, bgr_pages=None,
+               live: bool = False):
         """Enqueue one batch (H2D of the source on the copy stream, preprocess, encoder, CTC greedy, for "decoder"
         the whole greedy decode, async D2H of the packed results) and return a ticket without synchronising the
         host.  Two tickets may be in flight: ``t2 = submit(...); r1 = collect(t1)`` overlaps batch i's host-side
@@ -617,11 +629,6 @@ class BatchedRecognizer:
         if method not in ("ctc", "decoder", "beam"):
             raise ValueError("method must be 'ctc', 'decoder' or 'beam'")
         self._check_device()
-        caller = torch.cuda.current_stream(self.device)
-        if caller != self.stream:
-            self.stream.wait_stream(caller)
-            with torch.cuda.stream(self.stream):
-                return self.submit(src, entries, method, streaming, bgr_pages, live)
         n = len(entries)
         live = live and method in ("decoder", "beam")
         tk = {"method": method, "streaming": streaming, "n": n, "live": live}
@@ -771,6 +778,11 @@ class BatchedRecognizer:
                 out = self.collect(tk)
             caller.wait_stream(self.stream)
             return out
+        with _lib.pinned_stream(self.stream.cuda_stream):
+            return self._collect_own(tk, results)
+
+    def _collect_own(self, tk, results):
+        n = tk["n"]
         method, streaming = tk["method"], tk["streaming"]
         tk["done"].synchronize()
         res_words, M, n_lines, order, enc = tk["res_words"], tk["M"], tk["n_lines"], tk["order"], tk["enc"]

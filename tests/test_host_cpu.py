@@ -111,3 +111,32 @@ def test_decode_slot_table_places_every_line_once():
         if B <= 240:
             assert len(per) <= 15
     assert (decode_slot_table(32, n0=16) >= 0).all()                     # n0 = 16: the dense layout
+
+
+def test_conv1_tensor_pipe_operand_algebra():
+    """The operands csrc/conv1_tc.cu feeds the tensor pipe reproduce the normalised convolution: with u = v - 128 for a tap
+    inside the image and u = -0.5 for a padded tap, sum_t (2 w_t / 255) u_t + (b + sum_t w_t / 255) equals
+    sum_{inside} w_t (2 v_t / 255 - 1) + b; u and the ones column are exact in bf16, and the two-term bf16 split of the
+    weights keeps 16 mantissa bits (the device accumulates the exact products in fp32)."""
+    import torch
+    rng = np.random.default_rng(7)
+    w = (rng.standard_normal((48, 9)) / 3).astype(np.float32)
+    b = (rng.standard_normal(48) * 0.1).astype(np.float32)
+    v = rng.integers(0, 256, (200, 9))
+    inside = rng.random((200, 9)) > 0.15
+    inside[:, 4] = True                                                   # the centre tap is always inside
+    x = np.where(inside, (v / 255.0 - 0.5) / 0.5, 0.0)                    # the reference's normalisation, zero padding
+    want = x @ w.astype(np.float64).T + b
+    u = np.where(inside, v - 128.0, -0.5)
+    ub = torch.tensor(u, dtype=torch.float32).to(torch.bfloat16).double().numpy()
+    assert np.array_equal(ub, u)                                          # exact in bf16
+    wp = (2.0 * w.astype(np.float64) / 255.0).astype(np.float32)
+    bp = (b.astype(np.float64) + w.astype(np.float64).sum(1) / 255.0).astype(np.float32)
+    cols = np.concatenate([wp, bp[:, None]], 1)                           # [48, 10]: nine taps + the ones column
+    hi = torch.tensor(cols).to(torch.bfloat16).float()
+    lo = (torch.tensor(cols) - hi).to(torch.bfloat16).float()
+    a = np.concatenate([u, np.ones((200, 1))], 1)                         # A row: [u_0 .. u_8, 1]
+    got = a @ hi.double().numpy().T + a @ lo.double().numpy().T
+    scale = np.abs(a) @ np.abs(cols.astype(np.float64)).T                 # sum |w' u|: the size of what is being summed
+    assert float((np.abs(got - want) / scale).max()) < 2.0 ** -16          # 16 mantissa bits of weight precision
+    assert float(np.abs(got - want).max()) < 2e-3                          # well under one bf16 ulp of an O(1) output

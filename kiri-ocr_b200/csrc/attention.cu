@@ -290,13 +290,15 @@ extern "C" int kiri_encoder_attention_multi(const void* qkv_bf16, void* out_bf16
     KIRI_REQUIRE(ctas < 0x7fffffffll, "kiri_encoder_attention_multi: grid too large");
   }
   for (int i = n_used; i <= kAttnMaxGroups; ++i) G.cta_begin[i] = static_cast<int>(ctas);
-  static int sms = 0;
+  static int sms_dev[kMaxDevices] = {0};              // function attributes are per device
+  int& sms = sms_dev[kiri_cur_device_slot()];
   if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int dev = 0, n = 0;
+    KIRI_CHECK_CUDA(cudaGetDevice(&dev));
+    KIRI_CHECK_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
     KIRI_CHECK_CUDA(cudaFuncSetAttribute(encoder_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kAttnBufBytes));
     cudaFuncSetAttribute(encoder_attention_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    sms = n;
   }
   const long long cap = static_cast<long long>(sms) * 3;          // three resident CTAs per SM walk the work items
   const unsigned grid = static_cast<unsigned>(ctas < cap ? ctas : cap);

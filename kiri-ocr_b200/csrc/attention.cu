@@ -97,13 +97,16 @@ __device__ __forceinline__ void attn_tile(__nv_bfloat16* __restrict__ obase, con
   const float sl2 = 0.17677669529663687f * 1.4426950408889634f;   // 1/sqrt(32) * log2(e)
   const int t2 = (lane & 3) * 2;
   float mx0 = -INFINITY, mx1 = -INFINITY;
+  if (masked) {                                   // one branch for the whole row, not one per key block
 #pragma unroll
-  for (int nb = 0; nb < NB; ++nb) {
-    if (masked) {
+    for (int nb = 0; nb < NB; ++nb) {
       const int key = nb * 8 + t2;
       if (key >= klen) { s[nb][0] = -INFINITY; s[nb][2] = -INFINITY; }
       if (key + 1 >= klen) { s[nb][1] = -INFINITY; s[nb][3] = -INFINITY; }
     }
+  }
+#pragma unroll
+  for (int nb = 0; nb < NB; ++nb) {
     mx0 = fmaxf(mx0, fmaxf(s[nb][0], s[nb][1]));
     mx1 = fmaxf(mx1, fmaxf(s[nb][2], s[nb][3]));
   }
@@ -192,10 +195,11 @@ encoder_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* _
       if (i < G.n && item >= G.cta_begin[i]) gi = i;
     AttnItem w;
     w.T = G.T[gi];
-    const int halves = w.T > 96 ? 2 : 1;
+    const int hs = w.T > 96 ? 1 : 0;                // two CTAs (query halves) per (line, head) above 96 tokens
+    const int halves = 1 << hs;
     int local = item - G.cta_begin[gi];
-    const int half = local % halves;
-    local /= halves;
+    const int half = local & (halves - 1);
+    local >>= hs;
     const int head = local % heads;
     const int line = local / heads;
     w.qr = w.T / halves;
@@ -206,17 +210,29 @@ encoder_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* _
     w.klen = masked ? kv_len[G.line0[gi] + line] : w.T;
     return w;
   };
+  // A thread owns one 16-byte chunk column c and the rows r0, r0 + 48, r0 + 96, ...: (row >> 1) & 3 is the same for all
+  // of them (48 / 2 is a multiple of 4), so the swizzled chunk is fixed and a copy costs two adds, not an index decode.
+  static_assert(kAttnThreads == 192, "issue_load: 48 rows per pass");
   auto issue_load = [&](const AttnItem& w, uint8_t* bufp) {
     const uint32_t sq = smem_u32(bufp), sk = sq + 96 * 64, sv = sk + 160 * 64;
     const size_t ld = static_cast<size_t>(3) * D;
-    const int nkv = 2 * w.T * 4, total = nkv + w.qr * 4;
-    for (int idx = tid; idx < total; idx += kAttnThreads) {
-      int which, r, rl;
-      const int c = idx & 3;
-      if (idx < nkv) { const int rr = idx >> 2; which = rr >= w.T ? 2 : 1; r = rr - (which - 1) * w.T; rl = r; }
-      else { which = 0; rl = (idx - nkv) >> 2; r = w.q0 + rl; }
-      const uint32_t dst = (which == 0 ? sq : (which == 1 ? sk : sv)) + tile_off(rl, c);
-      cp_async16(dst, w.base + r * ld + which * D + c * 8);
+    const int c = tid & 3, r0 = tid >> 2;
+    const uint32_t off0 = tile_off(r0, c);
+    const __nv_bfloat16* src0 = w.base + r0 * ld + c * 8;
+    {
+      const __nv_bfloat16* src = src0 + D;          // K; V is D further on
+      uint32_t off = off0;
+#pragma unroll 1
+      for (int r = r0; r < w.T; r += 48, off += 48 * 64, src += 48 * ld) {
+        cp_async16(sk + off, src);
+        cp_async16(sv + off, src + D);
+      }
+    }
+    {
+      const __nv_bfloat16* src = src0 + w.q0 * ld;
+      uint32_t off = off0;
+#pragma unroll 1
+      for (int r = r0; r < w.qr; r += 48, off += 48 * 64, src += 48 * ld) cp_async16(sq + off, src);
     }
   };
   pdl_trigger();

@@ -6,6 +6,10 @@
 #include <mutex>
 #include <unordered_map>
 
+#ifndef KIRI_EPI_PIPE
+#define KIRI_EPI_PIPE 1
+#endif
+
 namespace kiri {
 
 static constexpr int kTileM = 128;
@@ -473,6 +477,72 @@ gemm_tc_kernel(const __grid_constant__ ProblemSet P, const __grid_constant__ CUt
       } else {
         constexpr int kCols = kF32Out ? 32 : 64;                 // columns per 128-byte staging row
         const int nch = (bn + kCols - 1) / kCols;
+        if constexpr (!kF32Out && KIRI_EPI_PIPE) {
+          // bf16 outputs: a warp has at most two 64-column chunks (bn <= 256).  A chunk is converted in registers
+          // BEFORE the wait on the previous bulk store's read of the staging tile, and the second chunk's TMEM read is
+          // issued before the first chunk is staged, so both latencies overlap work instead of adding up.
+          const int cA = half * kCols, cB = (half + 2) * kCols;
+          const bool hasA = half < nch, hasB = half + 2 < nch;
+          uint32_t lo[32], hi[32];
+          uint4 pk[8];
+          auto convert = [&](const int c0) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              const uint32_t* src = (t < 4) ? lo : hi;
+              const int o8 = (t & 3) * 8;
+              const float4 bb0 = *reinterpret_cast<const float4*>(sbias + c0 + t * 8);
+              const float4 bb1 = *reinterpret_cast<const float4*>(sbias + c0 + t * 8 + 4);
+              const float bb[8] = {bb0.x, bb0.y, bb0.z, bb0.w, bb1.x, bb1.y, bb1.z, bb1.w};
+              float2 y[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                y[u] = epi_act2<EPI>(fadd2(make_float2(__uint_as_float(src[o8 + 2 * u]), __uint_as_float(src[o8 + 2 * u + 1])),
+                                           make_float2(bb[2 * u], bb[2 * u + 1])));
+              pk[t].x = pack_bf16x2(y[0].x, y[0].y); pk[t].y = pack_bf16x2(y[1].x, y[1].y);
+              pk[t].z = pack_bf16x2(y[2].x, y[2].y); pk[t].w = pack_bf16x2(y[3].x, y[3].y);
+            }
+          };
+          auto stage_and_store = [&](const int c0) {
+            uint8_t* ob = bufs + (stg_cnt % kNBuf) * kBufBytes;
+            if (etime) te0 = clock64();
+            if (lane == 0) bulk_wait_group_read<kNBuf - 1>();
+            if (etime) acc_es += clock64() - te0;
+            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < 8; ++t) *reinterpret_cast<uint4*>(ob + stg_off(lane, t)) = pk[t];
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0 && valid) {
+              tma_store_2d(tmOut, ob, col_base + c0, row0);
+              bulk_commit_group();
+            }
+            ++stg_cnt;
+          };
+          auto release = [&]() {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
+          };
+          if (hasA) {
+            tmem_ld32(taddr + cA, lo);                           // may run past bn: the store clips the columns
+            tmem_ld32(taddr + cA + 32, hi);
+            tmem_ld_wait();
+            if (!hasB) release();
+            convert(cA);
+            if (hasB) { tmem_ld32(taddr + cB, lo); tmem_ld32(taddr + cB + 32, hi); }
+            stage_and_store(cA);
+            if (hasB) {
+              tmem_ld_wait();
+              release();
+              if (num_m_tiles < 0) __trap();                     // keeps the arrival above the arithmetic
+              convert(cB);
+              stage_and_store(cB);
+            }
+          } else {
+            release();
+          }
+          continue;
+        }
         // EPI_CTC_STATS: running (max, first arg-max, sum exp) of this thread's row over its column chunks
         float st_m = -INFINITY, st_s = 0.f;
         int st_a = 0x7fffffff;

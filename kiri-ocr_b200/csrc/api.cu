@@ -393,7 +393,7 @@ extern "C" int kiri_encode_multi(KiriHandle* h, const KiriGroup* groups, int n_g
     }
   }
   // ---- mem = enc_ln(x); head input = ctc_head.0(mem)
-  void* mem_b = mem_bf16 ? mem_bf16 : base + ws.o;     // o is free now
+  void* mem_b = mem_bf16;                              // only the decoder reads it: not written when the caller passes none
   { ProfScope ps(PS_LN_FINAL, stream);
     KIRI_TRY(kiri_layernorm(x, M, D, w.enc_ln_g, w.enc_ln_b, mem_f32, mem_b, w.ctc_ln_g, w.ctc_ln_b, a, stream)); }
   ProfScope ps_head(PS_CTC_HEAD, stream);

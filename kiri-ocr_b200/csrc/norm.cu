@@ -43,11 +43,20 @@ pool_pos_ln_kernel(const __grid_constant__ PoolGroups G, const float* __restrict
   const int ltok = tok - G.tok_begin[gi];
   const int b = ltok / T, t = ltok - b * T;
   float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int r = 0; r < RH; ++r) {
-    const uint4 pk = __ldg(reinterpret_cast<const uint4*>(
-        act + ((static_cast<size_t>(b) * RH + r) * T + t) * kD + lane * 8));
+  const uint4* row = reinterpret_cast<const uint4*>(act + ((static_cast<size_t>(b) * RH) * T + t) * kD + lane * 8);
+  const size_t row_pitch = static_cast<size_t>(T) * kD / 8;          // in uint4
+  auto add = [&](const uint4 pk) {
     v[0] += bf16_lo(pk.x); v[1] += bf16_hi(pk.x); v[2] += bf16_lo(pk.y); v[3] += bf16_hi(pk.y);
     v[4] += bf16_lo(pk.z); v[5] += bf16_hi(pk.z); v[6] += bf16_lo(pk.w); v[7] += bf16_hi(pk.w);
+  };
+  if (RH == 6) {                                    // line height 48: all six row loads in flight at once (same sum order)
+    uint4 pk[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) pk[r] = __ldg(row + r * row_pitch);
+#pragma unroll
+    for (int r = 0; r < 6; ++r) add(pk[r]);
+  } else {
+    for (int r = 0; r < RH; ++r) add(__ldg(row + r * row_pitch));
   }
   const float inv = 1.0f / static_cast<float>(RH);
   const float4 p0 = __ldg(reinterpret_cast<const float4*>(pos + static_cast<size_t>(t) * kD) + lane * 2);

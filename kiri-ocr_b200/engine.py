@@ -355,12 +355,13 @@ class BatchedRecognizer:
 
     def encode_multi(self, planes_list: Sequence[torch.Tensor], want_mem_f32: bool = False, want_tokens: bool = False,
                      kv_len: Optional[torch.Tensor] = None, want_logits: bool = True, slot: Optional[str] = None,
-                     stats: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+                     stats: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, want_mem: bool = True):
         """Several width groups ([B_g, IMG_H, Wb_g] uint8 each) in one call: per-group stems, ONE pass
         of the encoder / CTC head over the concatenated token stream.  Returns the outputs token-major
         ([M, ...], M = sum B_g * Wb_g / 4) plus ``rows`` = [(row0, B_g, T_g)] per group.  ``stats`` = (frame_ids int32
         [M], frame_prob fp32 [M]): the CTC head's epilogue takes the per-token arg-max and its probability; with
-        ``want_logits=False`` the logits then never reach HBM."""
+        ``want_logits=False`` the logits then never reach HBM; ``want_mem=False`` (method "ctc": nothing reads the
+        encoder memory) skips the bf16 ``mem`` store of the final LayerNorm as well."""
         D = self.cfg.ENC_DIM
         n = len(planes_list)
         garr = (_lib.KiriGroup * n)()
@@ -373,12 +374,16 @@ class BatchedRecognizer:
         need = self.lib.kiri_encode_multi_workspace_bytes(self.handle, garr, n, self.stem_chunk)
         ws = self._workspace(need)
         if slot is None:
-            out = {"mem_bf16": torch.empty((M, D), dtype=torch.bfloat16, device=self.device), "rows": rows}
+            out = {"rows": rows}
+            if want_mem:
+                out["mem_bf16"] = torch.empty((M, D), dtype=torch.bfloat16, device=self.device)
             if want_logits:
                 out["logits"] = torch.empty((M, self.pw.Cp), dtype=torch.float32, device=self.device)
         else:
             # submit(): outputs live in the ticket's ping-pong slot (no allocator / tensor-map-cache churn per call)
-            out = {"mem_bf16": self._device("_mem" + slot, M * D, torch.bfloat16)[:M * D].view(M, D), "rows": rows}
+            out = {"rows": rows}
+            if want_mem:
+                out["mem_bf16"] = self._device("_mem" + slot, M * D, torch.bfloat16)[:M * D].view(M, D)
             if want_logits:
                 out["logits"] = self._device("_logits" + slot, M * self.pw.Cp, torch.float32)[:M * self.pw.Cp].view(M, self.pw.Cp)
         if want_mem_f32:
@@ -386,7 +391,7 @@ class BatchedRecognizer:
         if want_tokens:
             out["tokens"] = torch.empty((M, D), dtype=torch.float32, device=self.device)
         _lib.check(self.lib.kiri_encode_multi(self.handle, garr, n, self.stem_chunk, ws.data_ptr(), need,
-                                              _lib.ptr(out.get("mem_f32")), out["mem_bf16"].data_ptr(),
+                                              _lib.ptr(out.get("mem_f32")), _lib.ptr(out.get("mem_bf16")),
                                               _lib.ptr(out.get("logits")), _lib.ptr(out.get("tokens")), _lib.ptr(kv_len),
                                               _lib.ptr(stats[0]) if stats else 0, _lib.ptr(stats[1]) if stats else 0,
                                               _lib.stream_ptr()), "kiri_encode_multi")
@@ -540,7 +545,8 @@ class BatchedRecognizer:
         fid = torch.empty(M, dtype=torch.int32, device=self.device)
         fpr = torch.empty(M, dtype=torch.float32, device=self.device)
         # frame decisions come out of the CTC head's epilogue: no logits in HBM for "ctc" / "decoder"
-        enc = self.encode_multi([g["planes"] for g in prep["groups"]], kv_len=prep["kv_len"], want_logits=False, stats=(fid, fpr))
+        enc = self.encode_multi([g["planes"] for g in prep["groups"]], kv_len=prep["kv_len"], want_logits=False, stats=(fid, fpr),
+                                want_mem=(method == "decoder"))
         ids = torch.empty(M, dtype=torch.int32, device=self.device)
         n_ids = torch.empty(L, dtype=torch.int32, device=self.device)
         conf = torch.empty(L, dtype=torch.float32, device=self.device)
@@ -731,7 +737,8 @@ class BatchedRecognizer:
         conf_all = dres[M + n_lines:M + 2 * n_lines].view(torch.float32)
         fid_all = dres[head_words:head_words + M]
         fpr_all = dres[head_words + M:head_words + 2 * M].view(torch.float32)
-        enc = self.encode_multi(planes_list, kv_len=kv_len, slot=sl, want_logits=(method == "beam"), stats=(fid_all, fpr_all))
+        enc = self.encode_multi(planes_list, kv_len=kv_len, slot=sl, want_logits=(method == "beam"), stats=(fid_all, fpr_all),
+                                want_mem=(method != "ctc" or live))
         marks.append(_time.perf_counter())                   # [5] encoder launched
         _lib.check(self.lib.kiri_ctc_collapse_multi(fid_all.data_ptr(), fpr_all.data_ptr(), n_lines, dmeta[r0o:].data_ptr(),
                                                     dmeta[mlo:].data_ptr(), ids_all.data_ptr(), n_all.data_ptr(),

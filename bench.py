@@ -339,6 +339,11 @@ def run_lines(args):
     launches0 = eng.launches
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     tail = torch.cuda.Event(enable_timing=True)
+    # the start-up heap is frozen before ANY timed loop (see the e2e leg): a generation-2 collection landing between a
+    # step's two events stalls the launching thread for 40-120 ms and the idle GPU time is counted (r02_final run:
+    # accurate 18.4 ms per step instead of 6.0 with every kernel at its usual duration)
+    gc.collect()
+    gc.freeze()
     barrier()
     sampler.mark_begin()
     for a, b in ev:
@@ -352,7 +357,8 @@ def run_lines(args):
     sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     launches = (eng.launches - launches0) // max(1, args.steps)
-    ms = sum(a.elapsed_time(b) for a, b in ev) + ev[-1][1].elapsed_time(tail)
+    step_ms = sorted(a.elapsed_time(b) for a, b in ev)
+    ms = sum(step_ms) + ev[-1][1].elapsed_time(tail)
     tmax = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -541,6 +547,7 @@ def run_lines(args):
                 "submit_phases": "upload enqueue | plan | staging + descriptor copy | preprocess launch | encoder launches | CTC (+ decode) + download enqueue",
                 "median_iter_ms_submit_wait_collect": [round(float(np.median([p[k] for p in iter_parts] or [0.0])) * 1e3, 3) for k in range(3)]},
         "gpu_launches": int(launches), "clocks": clocks,
+        "step_ms_min_p50_max": [round(step_ms[0], 4), round(step_ms[len(step_ms) // 2], 4), round(step_ms[-1], 4)],
         "roofline": roof, "whole_step_tensor_frac": tensor_frac, "stages": stages, "other_method": other,
         "cpu_baseline": {"value": cb_v, "unit": "lines/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{cb_n} lines of the same workload in {cb_dt:.1f} s, one line at a time, fp32 oracle"},
@@ -648,6 +655,8 @@ def run_pages(args):
     barrier()
     launches0 = eng.launches
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    gc.collect()                                            # (as in run_lines: no generation-2 collection inside a timed step)
+    gc.freeze()
     barrier()
     sampler.mark_begin()
     for a, b in ev:

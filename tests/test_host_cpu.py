@@ -140,3 +140,25 @@ def test_conv1_tensor_pipe_operand_algebra():
     scale = np.abs(a) @ np.abs(cols.astype(np.float64)).T                 # sum |w' u|: the size of what is being summed
     assert float((np.abs(got - want) / scale).max()) < 2.0 ** -16          # 16 mantissa bits of weight precision
     assert float(np.abs(got - want).max()) < 2e-3                          # well under one bf16 ulp of an O(1) output
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference algorithm on the host cores, the one place outside tests/ and smoke()
+    that may execute oracle/) prints ONE JSON line with the driver's keys; no GPU is touched."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
+    assert d["impl"] == "reference" and d["metric"] == base["metric"] and d["unit"] == "lines/s"
+    assert d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 0 and d["higher_is_better"] is True
+    assert d["value"] > 0 and abs(d["ms_per_step"] * d["value"] / 1e3 - d["config"]["lines_per_step"]) < 1e-6 * d["config"]["lines_per_step"] + 1e-6
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["vs_baseline"] is None and "workload" in d["config"]

@@ -121,7 +121,8 @@ class CharTokenizer:
             import numpy as np
             table = self.ctc_text if space == "ctc" else self.dec_text
             ok = all(len(t) <= 1 and not (t and 0xD800 <= ord(t) <= 0xDFFF) and t != "\x00" for t in table)
-            cache[space] = np.array([ord(t) if t else 0 for t in table], np.uint32) if ok else None
+            # one extra 0 entry at the end: every id outside the table is clipped onto it
+            cache[space] = np.array([ord(t) if t else 0 for t in table] + [0], np.uint32) if ok else None
         return cache[space]
 
     def decode_batch(self, ids_flat, lengths, space: str = "ctc") -> List[str]:
@@ -136,8 +137,8 @@ class CharTokenizer:
             one = self.decode_collapsed_ctc if space == "ctc" else self.decode_dec
             ends = np.cumsum(lengths)
             return [one(ids_flat[e - n:e].tolist()) for n, e in zip(lengths.tolist(), ends.tolist())]
-        inside = (ids_flat >= 0) & (ids_flat < len(codes_tab))
-        codes = np.where(inside, codes_tab[np.where(inside, ids_flat, 0)], 0).astype(np.uint32)
+        # negative ids become huge as unsigned, so ONE minimum sends every id outside the table to its empty last entry
+        codes = np.take(codes_tab, np.minimum(ids_flat.view(np.uint64), np.uint64(len(codes_tab) - 1)).view(np.int64))
         keep = codes != 0
         line = np.repeat(np.arange(len(lengths)), lengths)
         kept = np.bincount(line[keep], minlength=len(lengths))

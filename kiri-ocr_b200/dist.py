@@ -126,14 +126,16 @@ def records_to_results(engine, rec: torch.Tensor, n_total: int, method: str):
         is_eos = (body == tok.dec_eos) & (np.arange(body.shape[1])[None, :] < n[:, None])
         first = np.where(is_eos.any(axis=1), is_eos.argmax(axis=1), n)
         n = np.minimum(n, first)
-    order = np.argsort(li, kind="stable")                # rows in global line order
-    n_o = n[order]
-    flat = body[order][np.arange(body.shape[1])[None, :] < n_o[:, None]]
-    texts = tok.decode_batch(flat, n_o[ok[order]], "ctc" if method == "ctc" else "dec")     # failed rows hold no ids
+    # texts are decoded in RECORD order (no reordering of the id matrix); the line index only places the results
+    flat = body[np.arange(body.shape[1])[None, :] < n[:, None]]
+    texts = tok.decode_batch(flat, n[ok], "ctc" if method == "ctc" else "dec")              # failed rows hold no ids
     out: List[object] = [None] * n_total
-    li_o, ok_o, cf_o = li[order].tolist(), ok[order].tolist(), cf[order].tolist()
+    if ok.all():
+        for j, pair in zip(li.tolist(), zip(texts, cf.tolist())):
+            out[j] = pair
+        return out
     t = iter(texts)
-    for j, good, c in zip(li_o, ok_o, cf_o):
+    for j, good, c in zip(li.tolist(), ok.tolist(), cf.tolist()):
         out[j] = (next(t), c) if good else LineFailed()
     return out
 

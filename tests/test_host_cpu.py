@@ -162,3 +162,30 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["vs_baseline"] is None and "workload" in d["config"]
+
+
+def test_ctypes_signatures_agree_with_the_header():
+    """Every `_lib._SIGS` entry has as many parameters as the declaration in include/kiri_b200.h, pointers where the
+    header has pointers (or cudaStream_t) and scalars of the header's width elsewhere: ABI drift between the Python
+    binding and the C declarations fails here, on the CPU."""
+    import ctypes as C
+    header = open(os.path.join(ROOT, "include", "kiri_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    header = re.sub(r"//[^\n]*", "", header)
+    decls = dict((m.group(1), m.group(2)) for m in re.finditer(r"\b(kiri_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S))
+    assert set(decls) == set(_lib._SIGS)
+    scalar = {"int": C.c_int, "long long": C.c_longlong, "size_t": C.c_size_t, "float": C.c_float, "double": C.c_double}
+    for name, params in decls.items():
+        params = " ".join(params.split())
+        plist = [] if params in ("", "void") else [p.strip() for p in params.split(",")]
+        args = _lib._SIGS[name][1]
+        assert len(plist) == len(args), f"{name}: header has {len(plist)} parameters, the binding {len(args)}"
+        for p, a in zip(plist, args):
+            is_ptr = "*" in p or p.startswith("cudaStream_t")
+            a_ptr = a is C.c_void_p or a is C.c_char_p or (isinstance(a, type) and issubclass(a, C._Pointer))
+            assert is_ptr == a_ptr, f"{name}: `{p}` bound as {a}"
+            if not is_ptr:
+                ty = re.sub(r"\b(const|unsigned)\b", "", p).strip()
+                ty = " ".join(ty.split()[:-1])                      # drop the parameter name
+                assert ty in scalar, f"{name}: unknown scalar type in `{p}`"
+                assert C.sizeof(scalar[ty]) == C.sizeof(a), f"{name}: `{p}` bound as {a}"
